@@ -1,0 +1,202 @@
+/*
+ * viorb_gpu.h -- C ABI of libviorb_b200.so: the B200-native (sm_100a) ORB feature front-end for VIORB.
+ *
+ * This is the drop-in boundary.  The reference (sta105/VIORB, an ORB-SLAM2 fork) has no FFI layer; its
+ * boundary is the C++ ABI of ORBextractor / ORBmatcher / Frame::ComputeStereoMatches.  Each entry point
+ * below cites the reference interface it replaces; the C++ shims in viorb_b200/host/ re-create those
+ * classes on top of this ABI.
+ *
+ * Conventions: plain pointers and sizes only; every function returns VIORB_OK (0) or a negative
+ * viorb_status and never throws; outputs are caller allocated; a context owns one CUDA stream and must
+ * not be entered concurrently (use one context per calling thread, as the reference uses one
+ * ORBextractor instance per thread -- src/Frame.cc:258-261).  There is NO CPU fallback: every entry
+ * point fails with VIORB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef VIORB_GPU_H
+#define VIORB_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    VIORB_OK = 0,
+    VIORB_ERR_INVALID = -1,       /* bad argument */
+    VIORB_ERR_CUDA = -2,          /* CUDA runtime / launch failure, or no device */
+    VIORB_ERR_CAPACITY = -3,      /* caller buffer (cap) or an internal candidate pool too small */
+    VIORB_ERR_UNSUPPORTED = -4    /* parameters outside the supported envelope */
+} viorb_status;
+
+/* Layout-identical to cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} viorb_keypoint;
+
+/* Best and second-best Hamming match of one query: distances in [0,256], map indices (-1 = none).
+ * Semantics of the sequential strict-< scan in src/ORBmatcher.cc:201-226: ties keep the lowest index. */
+typedef struct {
+    int32_t d1, i1, d2, i2;
+} viorb_top2;
+
+typedef struct viorb_ctx viorb_ctx;
+typedef struct viorb_extractor viorb_extractor;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+/* stream: a cudaStream_t owned by the caller (e.g. torch's current stream), or NULL to create one. */
+int viorb_ctx_create(int device, void* stream, viorb_ctx** out);
+int viorb_ctx_destroy(viorb_ctx* ctx);
+int viorb_ctx_synchronize(viorb_ctx* ctx);
+const char* viorb_last_error(void);                  /* thread-local message of the last failure */
+int viorb_device_count(void);
+/* number of kernel launches issued through this context so far (bench.py "gpu_launches") */
+int64_t viorb_ctx_launch_count(const viorb_ctx* ctx);
+/* pinned host memory for fast host<->device staging of batches */
+int viorb_host_alloc(size_t bytes, void** out);
+int viorb_host_free(void* p);
+
+/* ---- ORBextractor ------------------------------------------------------------------------------
+ * replaces ORB_SLAM2::ORBextractor::ORBextractor(int nfeatures, float scaleFactor, int nlevels,
+ *          int iniThFAST, int minThFAST)                         include/ORBextractor.h:52-53,
+ *                                                                 src/ORBextractor.cc:410-470        */
+int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, int nlevels,
+                           int ini_th_fast, int min_th_fast, viorb_extractor** out);
+int viorb_extractor_destroy(viorb_extractor* ex);
+/* optional tuning: frames processed per device pass (working set sized for the 126 MB L2) and the
+ * candidate pool per level as a fraction 1/div of the level's pixel count. */
+int viorb_extractor_configure(viorb_extractor* ex, int chunk_frames, int cand_div);
+
+/* GetLevels/GetScaleFactors/GetInverseScaleFactors/GetScaleSigmaSquares/GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:63-83) + mnFeaturesPerLevel; any pointer may be NULL. */
+int viorb_extractor_tables(const viorb_extractor* ex, int* nlevels, float* scale, float* inv_scale,
+                           float* sigma2, float* inv_sigma2, int* features_per_level);
+
+/* replaces ORBextractor::operator()(InputArray image, InputArray mask, vector<KeyPoint>&, OutputArray)
+ *          include/ORBextractor.h:58-60, src/ORBextractor.cc:1043-1105.
+ * image: CV_8UC1, rows x cols, row stride `step` bytes, HOST memory (mask is ignored by the reference).
+ * kps/desc: host, capacity `cap` keypoints / cap*32 bytes; *n = keypoints found.
+ * An empty image (NULL / 0x0) returns VIORB_OK with *n = 0 (src/ORBextractor.cc:1046-1047).        */
+int viorb_extract(viorb_extractor* ex, const uint8_t* image, int rows, int cols, size_t step,
+                  viorb_keypoint* kps, uint8_t* desc, int cap, int* n);
+
+/* The same operator over a batch of B equally sized frames (frame b at images + b*frame_stride),
+ * HOST buffers (pinned memory recommended): kps[b*cap ...], desc[b*cap*32 ...], counts[b].
+ * Host<->device copies are part of the call.                                                       */
+int viorb_extract_batch(viorb_extractor* ex, const uint8_t* images, int B, int rows, int cols,
+                        size_t step, size_t frame_stride, viorb_keypoint* kps, uint8_t* desc, int cap,
+                        int32_t* counts);
+
+/* Batch over DEVICE-resident frames and outputs; asynchronous on the context stream.  Errors detected
+ * on the device (pool overflow) are reported by the next viorb_extractor_check(). */
+int viorb_extract_batch_device(viorb_extractor* ex, const uint8_t* d_images, int B, int rows, int cols,
+                               size_t step, size_t frame_stride, viorb_keypoint* d_kps, uint8_t* d_desc,
+                               int cap, int32_t* d_counts);
+int viorb_extractor_check(viorb_extractor* ex);      /* synchronises, returns deferred device status */
+
+/* ORBextractor::mvImagePyramid (include/ORBextractor.h:85; read by src/Frame.cc:653,743,755,760).
+ * The pyramids of the frames of the most recent device pass stay resident; `frame` indexes into it
+ * (0 for viorb_extract).  Geometry: ROI w x h; the padded image is (w+38) x (h+38) (EDGE_THRESHOLD 19). */
+int viorb_extractor_pyramid_info(const viorb_extractor* ex, int level, int* w, int* h);
+int viorb_extractor_pyramid_download(viorb_extractor* ex, int frame, int level, uint8_t* dst_padded,
+                                     size_t dst_step);
+/* device view of the ROI origin of (frame, level) and its row stride (for device-side consumers) */
+int viorb_extractor_pyramid_device(const viorb_extractor* ex, int frame, int level,
+                                   const uint8_t** d_roi, size_t* d_step);
+/* how many frames of the last call are still resident, and the index of the first of them */
+int viorb_extractor_resident(const viorb_extractor* ex, int* first_frame, int* nframes);
+
+/* parity hooks for the stage tests: FAST candidates (x, y in level coordinates, score) of (frame, level)
+ * in no particular order, and the quadtree-selected keypoints of a level in reference list order. */
+int viorb_extractor_debug_candidates(viorb_extractor* ex, int frame, int level, int32_t* xys, int cap, int* n);
+int viorb_extractor_debug_selected(viorb_extractor* ex, int frame, int level, int32_t* xys, int cap, int* n);
+
+/* ---- ORBmatcher --------------------------------------------------------------------------------
+ * replaces static int ORBmatcher::DescriptorDistance(const cv::Mat&, const cv::Mat&)
+ *          include/ORBmatcher.h:47, src/ORBmatcher.cc:1648-1664 -- n pairs at once, host buffers.     */
+int viorb_descriptor_distance(viorb_ctx* ctx, const uint8_t* a, const uint8_t* b, int n, int32_t* dist);
+
+/* Brute-force top-2 Hamming search of Q query descriptors against M map descriptors (32 B each);
+ * inner loop semantics of src/ORBmatcher.cc:201-226 (SearchByBoW) / :76-115 (SearchByProjection):
+ * best1 = best2 = 256, strict <, first index wins.  index_base is added to the reported indices
+ * (map shard offset for multi-GPU sharding).  Host buffers; copies are part of the call.           */
+int viorb_hamming_top2(viorb_ctx* ctx, const uint8_t* queries, int Q, const uint8_t* map, int64_t M,
+                       int64_t index_base, viorb_top2* out);
+/* device-resident variant, asynchronous on the context stream */
+int viorb_hamming_top2_device(viorb_ctx* ctx, const uint8_t* d_queries, int Q, const uint8_t* d_map,
+                              int64_t M, int64_t index_base, viorb_top2* d_out);
+/* deterministic merge of `nparts` per-shard records per query ([part][Q] layout, device memory), used
+ * after the all-gather of the multi-GPU search; identical to one scan over the concatenated map.   */
+int viorb_top2_merge_device(viorb_ctx* ctx, const viorb_top2* d_parts, int nparts, int Q, viorb_top2* d_out);
+
+/* replaces void Frame::ComputeStereoMatches()           include/Frame.h:127, src/Frame.cc:646-820.
+ * Uses the pyramids resident in the two extractors (frame index `frame_l`/`frame_r` of their last pass)
+ * exactly as the reference reads mpORBextractorLeft/Right->mvImagePyramid.  Host buffers.          */
+int viorb_stereo_match(viorb_extractor* left, int frame_l, viorb_extractor* right, int frame_r,
+                       const viorb_keypoint* kps_l, const uint8_t* desc_l, int nl,
+                       const viorb_keypoint* kps_r, const uint8_t* desc_r, int nr,
+                       float mbf, float mb, float* u_right, float* depth);
+
+/* Windowed projection searches.  The caller flattens the fields the reference reads from Frame /
+ * MapPoint / KeyFrame into arrays (INTEGRATION.md shows the marshalling); results are identical to the
+ * sequential loops including the "keypoint already taken" dependence.
+ *
+ * viorb_frame_index: device-side copy of a Frame's matching state: undistorted keypoints, descriptors,
+ * mvuRight and the 64x48 grid of Frame::AssignFeaturesToGrid (src/Frame.cc:410-425).               */
+typedef struct viorb_frame_index viorb_frame_index;
+int viorb_frame_index_create(viorb_ctx* ctx, const viorb_keypoint* kps_un, const uint8_t* desc,
+                             const float* u_right /* may be NULL: all -1 */, int n,
+                             float min_x, float max_x, float min_y, float max_y,
+                             const float* scale_factors, int nlevels, viorb_frame_index** out);
+int viorb_frame_index_destroy(viorb_frame_index* fi);
+/* Frame::GetFeaturesInArea (src/Frame.cc:507-560), reference enumeration order */
+int viorb_frame_features_in_area(viorb_frame_index* fi, float x, float y, float r, int min_level,
+                                 int max_level, int32_t* out, int cap, int* n);
+
+/* replaces int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, const float th)
+ *          include/ORBmatcher.h:52, src/ORBmatcher.cc:45-129.
+ * per map point i: valid = mbTrackInView && !isBad(); proj_* = mTrackProjX/Y/XR; pred_level =
+ * mnTrackScaleLevel; view_cos = mTrackViewCos; nobs = Observations(); desc = GetDescriptor().
+ * frame_mp_obs[k] (in/out, nf) = Observations() of the map point frame keypoint k holds, 0 if none.
+ * match[k] (out, nf) = index of the map point assigned to keypoint k by this call, or -1.          */
+int viorb_search_by_projection_local(viorb_frame_index* fi, int32_t* frame_mp_obs,
+                                     const float* proj_x, const float* proj_y, const float* proj_xr,
+                                     const int32_t* pred_level, const float* view_cos, const uint8_t* valid,
+                                     const int32_t* nobs, const uint8_t* mp_desc, int nmp,
+                                     float th, float nnratio, int32_t* match, int* nmatches);
+
+/* replaces int ORBmatcher::SearchByProjection(Frame& Cur, const Frame& Last, const float th, bool bMono)
+ *          include/ORBmatcher.h:56, src/ORBmatcher.cc:1328-1471  (and, with mode 0 and th_high = ORBdist,
+ *          the relocalisation overload :1473-1600 whose search loop is the same).
+ * u, v, invz = projection of each last-frame map point into the current frame (:1359-1376);
+ * mode 0: levels [o-1,o+1]; 1 (forward): >= o; 2 (backward): [0,o]   (:1385-1390).                */
+int viorb_search_by_projection_frame(viorb_frame_index* fi, int32_t* frame_mp_obs,
+                                     const float* u, const float* v, const float* invz,
+                                     const int32_t* last_octave, const float* last_angle,
+                                     const uint8_t* valid, const int32_t* nobs, const uint8_t* mp_desc,
+                                     int nlast, float th, float mbf, int mode, int check_orientation,
+                                     int th_high, int32_t* match, int* nmatches);
+
+/* replaces int ORBmatcher::SearchForTriangulation(KeyFrame*, KeyFrame*, cv::Mat F12,
+ *          vector<pair<size_t,size_t>>&, const bool bOnlyStereo)
+ *          include/ORBmatcher.h:71-72, src/ORBmatcher.cc:657-823.
+ * DBoW2 feature vectors are passed flattened: node ids ascending, CSR offsets, keypoint indices.
+ * matches12[i] (n1) = index in KF2 matched to keypoint i of KF1, or -1.                            */
+int viorb_search_for_triangulation(viorb_ctx* ctx,
+                                   const viorb_keypoint* k1, const uint8_t* d1, const float* ur1,
+                                   const uint8_t* has_mp1, int n1,
+                                   const viorb_keypoint* k2, const uint8_t* d2, const float* ur2,
+                                   const uint8_t* has_mp2, int n2,
+                                   const int32_t* node_id1, const int32_t* node_ptr1, const int32_t* idx1, int nn1,
+                                   const int32_t* node_id2, const int32_t* node_ptr2, const int32_t* idx2, int nn2,
+                                   const float* F12, float ex, float ey,
+                                   const float* scale_factors2, const float* level_sigma2_2, int nlevels,
+                                   int only_stereo, int check_orientation,
+                                   int32_t* matches12, int* nmatches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIORB_GPU_H */

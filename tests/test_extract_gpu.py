@@ -1,0 +1,147 @@
+"""GPU parity tests of the extraction path: libviorb_b200.so (through the C ABI) vs the CPU oracle.
+
+Bar (BASELINE.json north_star): pyramid, FAST scores/candidates and descriptors bit-exact; selected
+keypoint sets >= 99.9 % (we require 100 % incl. order); IC_Angle within 1e-3 rad (we require bit-equal).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from util import CONFIGS, ROOT
+from viorb_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def api():
+    from viorb_b200 import api
+    api.lib()
+    return api
+
+
+@pytest.fixture(scope="module")
+def ctx(api):
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def sort_rows(a):
+    a = np.asarray(a).reshape(-1, 3)
+    return a[np.lexsort((a[:, 2], a[:, 0], a[:, 1]))]
+
+
+def assert_same_output(k_gpu, d_gpu, k_ref, d_ref):
+    assert len(k_gpu) == len(k_ref), (len(k_gpu), len(k_ref))
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert (k_gpu[f] == k_ref[f]).all(), f
+    # angle: bar is 1e-3 rad; the implementation is bit-exact
+    assert np.max(np.abs(k_gpu["angle"] - k_ref["angle"]), initial=0) * np.pi / 180 <= 1e-3
+    assert (k_gpu["angle"].view(np.uint32) == k_ref["angle"].view(np.uint32)).all()
+    assert (d_gpu == d_ref).all()
+
+
+@pytest.mark.parametrize("cfg,seed", [("euroc", 0), ("odd", 5), ("kitti12", 7), ("kitti", 3)])
+def test_stages_vs_oracle(api, ctx, oracle, cfg, seed):
+    h, w, nf, sf, nl, it, mt = CONFIGS[cfg]
+    img = synth.frame(h, w, seed)
+    ref = oracle.Extractor(nf, sf, nl, it, mt)
+    k_ref, d_ref = ref(img)
+    ex = api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx)
+    k_gpu, d_gpu = ex(img)
+    assert (ex.features_per_level() == ref.quotas()).all()
+    assert (ex.GetScaleFactors() == ref.scale_factors()).all()
+    for l in range(nl):
+        assert (ex.pyramid(l) == ref.pyramid(l)).all(), "pyramid level %d" % l
+        c_ref = ref.candidates(l)
+        c_ref = np.stack([c_ref["x"] + 16, c_ref["y"] + 16, c_ref["score"]], 1)
+        c_gpu = ex.debug_candidates(l)
+        assert len(c_gpu) == len(c_ref), "candidate count level %d" % l
+        assert (sort_rows(c_gpu) == sort_rows(c_ref)).all(), "candidates level %d" % l
+        s_ref = ref.level_keypoints(l)
+        s_ref = np.stack([s_ref["x"], s_ref["y"], s_ref["response"]], 1).astype(np.int32)
+        s_gpu = ex.debug_selected(l)
+        assert len(s_gpu) == len(s_ref), "selected count level %d" % l
+        assert (s_gpu == s_ref).all(), "selected keypoints (list order) level %d" % l
+    assert_same_output(k_gpu, d_gpu, k_ref, d_ref)
+    ex.close()
+
+
+@pytest.mark.parametrize("cfg,seed", [("euroc", 0), ("odd", 5), ("kitti12", 7)])
+def test_vs_golden_opencv(api, ctx, cfg, seed):
+    """against the committed outputs of real OpenCV primitives (tests/golden/make_golden.py)"""
+    h, w, nf, sf, nl, it, mt = CONFIGS[cfg]
+    g = np.load(os.path.join(GOLD, "extract_%s_seed%d.npz" % (cfg, seed)))
+    ex = api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx)
+    k, d = ex(synth.frame(h, w, seed))
+    assert_same_output(k, d, g["keypoints"], g["descriptors"])
+    ex.close()
+
+
+def test_batch_matches_single(api, ctx, oracle):
+    h, w, nf, sf, nl, it, mt = CONFIGS["euroc"]
+    B = 9
+    imgs = synth.frames(B, h, w, seed0=100)
+    ex = api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx)
+    ex.configure(chunk_frames=4)          # 3 passes, last one ragged
+    kps, desc, counts = ex.extract_batch(imgs)
+    ref = oracle.Extractor(nf, sf, nl, it, mt)
+    for b in range(B):
+        k_ref, d_ref = ref(imgs[b])
+        n = counts[b]
+        assert_same_output(kps[b, :n], desc[b, :n], k_ref, d_ref)
+    # the pyramids of the last pass stay resident (mvImagePyramid)
+    assert (ex.pyramid(3, frame=0) == ref.pyramid(3)).all()
+    ex.close()
+
+
+def test_large_frame_hd(api, ctx, oracle):
+    h, w, nf, sf, nl, it, mt = CONFIGS["hd"]
+    img = synth.frame(h, w, 2)
+    ref = oracle.Extractor(nf, sf, nl, it, mt)
+    k_ref, d_ref = ref(img)
+    ex = api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx)
+    k, d = ex(img)
+    assert_same_output(k, d, k_ref, d_ref)
+    ex.close()
+
+
+def test_edge_cases(api, ctx, oracle):
+    ex = api.ORBextractor(1000, 1.2, 8, 20, 7, ctx=ctx)
+    ref = oracle.Extractor(1000, 1.2, 8, 20, 7)
+    # empty image: silent return (ORBextractor.cc:1046-1047)
+    k, d = ex(np.zeros((0, 0), np.uint8))
+    assert len(k) == 0
+    # flat image: no keypoints (:1064-1065)
+    k, d = ex(np.full((480, 752), 77, np.uint8))
+    assert len(k) == 0 and d.shape == (0, 32)
+    # saturated checkerboard and pure noise (retry path everywhere / candidate-heavy)
+    yy, xx = np.mgrid[0:480, 0:752]
+    checker = (((yy // 8 + xx // 8) & 1) * 255).astype(np.uint8)
+    rng = np.random.default_rng(3)
+    noise = rng.integers(0, 256, (480, 752)).astype(np.uint8)
+    for img in (checker, noise):
+        k_ref, d_ref = ref(img)
+        k, d = ex(img)
+        assert_same_output(k, d, k_ref, d_ref)
+    # a sub-matrix view with a row stride
+    big = synth.frame(500, 800, 8)
+    view = big[10:490, 20:772]
+    k_ref, d_ref = ref(np.ascontiguousarray(view))
+    k, d = ex(view)
+    assert_same_output(k, d, k_ref, d_ref)
+    ex.close()
+
+
+def test_bad_arguments(api, ctx):
+    with pytest.raises(api.ViorbError):
+        api.ORBextractor(0, 1.2, 8, 20, 7, ctx=ctx)
+    with pytest.raises(api.ViorbError):
+        api.ORBextractor(1000, 1.2, 64, 20, 7, ctx=ctx)
+    ex = api.ORBextractor(1000, 1.2, 8, 20, 7, ctx=ctx)
+    with pytest.raises(api.ViorbError):
+        ex(np.zeros((40, 40), np.uint8))        # smaller than one FAST cell at the top level
+    ex.close()

@@ -1,0 +1,644 @@
+/*
+ * c_api.cu -- the extern "C" boundary of libviorb_b200.so (include/viorb_gpu.h): contexts, device
+ * workspaces, host<->device staging and kernel orchestration.  No compute happens on the host; if
+ * CUDA is unavailable every entry point fails with VIORB_ERR_CUDA (there is no CPU fallback).
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "extractor_kernels.cuh"
+#include "matcher_kernels.cuh"
+#include "viorb_gpu.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(VIORB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline int cvRoundF(float v) { return (int)lrintf(v); }
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int ensure(size_t count) {
+        if (count <= n) return VIORB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e != cudaSuccess) return fail(VIORB_ERR_CUDA, "cudaMalloc(%zu) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        n = count;
+        return VIORB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct viorb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    int sms = 148;
+    int64_t launches = 0;
+    /* matcher scratch */
+    DevBuf<uint8_t> mq, mmap;
+    DevBuf<viorb_top2> mparts, mout;
+    DevBuf<uint8_t> scratchA, scratchB;
+    DevBuf<int32_t> scratchI;
+};
+
+struct viorb_extractor {
+    viorb_ctx* ctx = nullptr;
+    int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
+    double scaleFactor = 1.2;
+    std::vector<float> scale, invScale, sigma2, invSigma2;
+    std::vector<int> quota;
+    int chunk = 64, candDiv = 32;
+    /* geometry for the current image size */
+    int rows = 0, cols = 0;
+    FrameGeom geom;
+    int nodeCap = 0;
+    DevBuf<uint16_t> tabU16;       /* xofs | yofs */
+    DevBuf<int16_t> tabI16;        /* xa | yb */
+    ResizeTables tables;
+    /* pass workspace */
+    int allocFrames = 0;
+    ExtractBuffers buf;
+    DevBuf<uint8_t> pyr;
+    DevBuf<uint32_t> cand, sel;
+    DevBuf<int> counters;          /* candCount | selCount | status */
+    DevBuf<uint16_t> nodeOf;
+    /* staging for host-buffer entry points (double buffered) */
+    DevBuf<uint8_t> in[2];
+    DevBuf<viorb_keypoint> okps[2];
+    DevBuf<uint8_t> odesc[2];
+    DevBuf<int32_t> ocnt[2];
+    cudaEvent_t evIn[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
+    int residentFirst = 0, residentCount = 0;
+};
+
+namespace {
+
+int ctx_bind(viorb_ctx* c) {
+    CU(cudaSetDevice(c->device));
+    return VIORB_OK;
+}
+
+/* ORBextractor::ORBextractor tables, src/ORBextractor.cc:410-446 */
+void build_tables(viorb_extractor* e) {
+    const int nl = e->nlevels;
+    e->scale.assign(nl, 1.0f); e->sigma2.assign(nl, 1.0f);
+    for (int i = 1; i < nl; i++) {
+        e->scale[i] = (float)(e->scale[i - 1] * e->scaleFactor);
+        e->sigma2[i] = e->scale[i] * e->scale[i];
+    }
+    e->invScale.resize(nl); e->invSigma2.resize(nl);
+    for (int i = 0; i < nl; i++) {
+        e->invScale[i] = 1.0f / e->scale[i];
+        e->invSigma2[i] = 1.0f / e->sigma2[i];
+    }
+    e->quota.resize(nl);
+    float factor = (float)(1.0f / e->scaleFactor);
+    float nDesired = e->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
+    int sum = 0;
+    for (int l = 0; l < nl - 1; l++) {
+        e->quota[l] = cvRoundF(nDesired);
+        sum += e->quota[l];
+        nDesired *= factor;
+    }
+    e->quota[nl - 1] = std::max(e->nfeatures - sum, 0);
+}
+
+/* geometry + cv::resize coefficient tables for a given image size */
+int build_geometry(viorb_extractor* e, int rows, int cols) {
+    if (e->rows == rows && e->cols == cols) return VIORB_OK;
+    FrameGeom& g = e->geom;
+    memset(&g, 0, sizeof(g));
+    g.nlevels = e->nlevels; g.rows = rows; g.cols = cols; g.iniTh = e->iniTh; g.minTh = e->minTh;
+    size_t pyrOff = 0;
+    int cellBase = 0, candBase = 0, selBase = 0, xtab = 0, ytab = 0, nodeCap = 0;
+    for (int l = 0; l < e->nlevels; l++) {
+        LevelGeom& L = g.lv[l];
+        L.w = cvRoundF((float)cols * e->invScale[l]);       /* :1112 */
+        L.h = cvRoundF((float)rows * e->invScale[l]);
+        if (L.w > 4095 + 2 * VIORB_FAST_BORDER || L.h > 4095 + 2 * VIORB_FAST_BORDER)
+            return fail(VIORB_ERR_UNSUPPORTED, "level %d is %dx%d: coordinates above 4095 are not supported", l, L.w, L.h);
+        const int W = L.w - 2 * VIORB_FAST_BORDER, H = L.h - 2 * VIORB_FAST_BORDER;
+        if (W < 30 || H < 30)
+            return fail(VIORB_ERR_UNSUPPORTED, "level %d (%dx%d) is smaller than one FAST cell; use fewer levels", l, L.w, L.h);
+        L.step = (VIORB_ROI_X0 + L.w + VIORB_EDGE + 15) / 16 * 16;
+        L.pyrOff = (int)pyrOff;
+        pyrOff += (size_t)L.step * (L.h + 2 * VIORB_EDGE);
+        pyrOff = (pyrOff + 255) / 256 * 256;
+        /* :779-787 */
+        const float width = (float)W, height = (float)H;
+        L.nCols = (int)(width / 30.f);
+        L.nRows = (int)(height / 30.f);
+        L.wCell = (int)ceilf(width / L.nCols);
+        L.hCell = (int)ceilf(height / L.nRows);
+        L.cellBase = cellBase;
+        cellBase += L.nCols * L.nRows;
+        L.quota = e->quota[l];
+        L.nIni = (int)roundf((float)W / (float)H);          /* :543 */
+        if (L.nIni < 1) return fail(VIORB_ERR_UNSUPPORTED, "portrait aspect ratio %dx%d gives zero quadtree roots", L.w, L.h);
+        long cc = (long)L.w * L.h / e->candDiv;
+        L.candCap = (int)std::min<long>(std::max<long>(cc, 1024), 65535);
+        L.candBase = candBase;
+        candBase += L.candCap;
+        L.selCap = std::max(L.quota + 4, 4 * L.nIni + 4);
+        L.selBase = selBase;
+        selBase += L.selCap;
+        nodeCap = std::max(nodeCap, L.selCap);
+        L.scale = e->scale[l];
+        L.patchSize = (int)(31 * e->scale[l]);               /* :837 */
+        L.xtab = xtab; L.ytab = ytab;
+        xtab += L.w; ytab += L.h;
+    }
+    if (pyrOff >= (1ull << 31)) return fail(VIORB_ERR_UNSUPPORTED, "pyramid larger than 2 GiB per frame");
+    g.pyrFrameBytes = pyrOff;
+    g.cellsPerFrame = cellBase; g.candPerFrame = candBase; g.selPerFrame = selBase;
+    if (viorb_octree_smem_bytes(nodeCap) > 200 * 1024)
+        return fail(VIORB_ERR_UNSUPPORTED, "per-level feature quota %d too large for the quadtree kernel", nodeCap);
+    e->nodeCap = nodeCap;
+    /* cv::resize INTER_LINEAR coefficient tables (OpenCV resize.cpp), level l from level l-1 */
+    std::vector<uint16_t> tu((size_t)xtab + ytab);
+    std::vector<int16_t> ti(2 * ((size_t)xtab + ytab));
+    for (int l = 1; l < e->nlevels; l++) {
+        const LevelGeom& L = g.lv[l];
+        const LevelGeom& P = g.lv[l - 1];
+        const double inv_sx = (double)L.w / P.w, inv_sy = (double)L.h / P.h;
+        const double sx_ = 1. / inv_sx, sy_ = 1. / inv_sy;
+        for (int dx = 0; dx < L.w; dx++) {
+            float fx = (float)((dx + 0.5) * sx_ - 0.5);
+            int sx = (int)floorf(fx);
+            fx -= sx;
+            if (sx < 0) { fx = 0; sx = 0; }
+            if (sx >= P.w - 1) { fx = 0; sx = P.w - 1; }
+            tu[L.xtab + dx] = (uint16_t)sx;
+            ti[2 * (L.xtab + dx)] = (int16_t)cvRoundF((1.f - fx) * 2048);
+            ti[2 * (L.xtab + dx) + 1] = (int16_t)cvRoundF(fx * 2048);
+        }
+        for (int dy = 0; dy < L.h; dy++) {
+            float fy = (float)((dy + 0.5) * sy_ - 0.5);
+            int sy = (int)floorf(fy);
+            fy -= sy;
+            tu[xtab + L.ytab + dy] = (uint16_t)std::max(sy, 0);
+            ti[2 * (xtab + L.ytab + dy)] = (int16_t)cvRoundF((1.f - fy) * 2048);
+            ti[2 * (xtab + L.ytab + dy) + 1] = (int16_t)cvRoundF(fy * 2048);
+        }
+    }
+    int rc;
+    if ((rc = e->tabU16.ensure(tu.size() + 1))) return rc;
+    if ((rc = e->tabI16.ensure(ti.size() + 2))) return rc;
+    CU(cudaMemcpyAsync(e->tabU16.p, tu.data(), tu.size() * 2, cudaMemcpyHostToDevice, e->ctx->stream));
+    CU(cudaMemcpyAsync(e->tabI16.p, ti.data(), ti.size() * 2, cudaMemcpyHostToDevice, e->ctx->stream));
+    CU(cudaStreamSynchronize(e->ctx->stream));
+    e->tables.xofs = e->tabU16.p;
+    e->tables.yofs = e->tabU16.p + xtab;
+    e->tables.xa = e->tabI16.p;
+    e->tables.yb = e->tabI16.p + 2 * (size_t)xtab;
+    /* ytab offsets index into the y arrays which start after the x block */
+    cudaError_t ce = (cudaError_t)viorb_octree_prepare(nodeCap);
+    if (ce != cudaSuccess) return fail(VIORB_ERR_CUDA, "octree kernel attribute: %s", cudaGetErrorString(ce));
+    e->rows = rows; e->cols = cols;
+    e->allocFrames = 0;
+    return VIORB_OK;
+}
+
+int ensure_workspace(viorb_extractor* e, int F) {
+    if (F <= e->allocFrames) return VIORB_OK;
+    const FrameGeom& g = e->geom;
+    int rc;
+    if ((rc = e->pyr.ensure((size_t)F * g.pyrFrameBytes))) return rc;
+    if ((rc = e->cand.ensure((size_t)F * g.candPerFrame))) return rc;
+    if ((rc = e->nodeOf.ensure((size_t)F * g.candPerFrame))) return rc;
+    if ((rc = e->sel.ensure((size_t)F * g.selPerFrame))) return rc;
+    if ((rc = e->counters.ensure((size_t)F * g.nlevels * 2 + 4))) return rc;
+    CU(cudaMemsetAsync(e->counters.p, 0, e->counters.n * sizeof(int), e->ctx->stream));
+    e->buf.pyr = e->pyr.p;
+    e->buf.cand = e->cand.p;
+    e->buf.nodeOf = e->nodeOf.p;
+    e->buf.sel = e->sel.p;
+    e->buf.candCount = e->counters.p;
+    e->buf.selCount = e->counters.p + (size_t)F * g.nlevels;
+    e->buf.status = e->counters.p + (size_t)F * g.nlevels * 2;
+    e->allocFrames = F;
+    return VIORB_OK;
+}
+
+/* one device pass over F frames already resident on the device */
+int run_pass(viorb_extractor* e, const uint8_t* d_images, size_t step, size_t frameStride, int F,
+             viorb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts) {
+    viorb_ctx* c = e->ctx;
+    const FrameGeom& g = e->geom;
+    CU(cudaMemsetAsync(e->buf.candCount, 0, (size_t)F * g.nlevels * sizeof(int), c->stream));
+    c->launches += viorb_launch_pyramid(g, e->tables, d_images, step, frameStride, F, e->buf, c->stream);
+    c->launches += viorb_launch_fast(g, F, e->buf, c->stream);
+    c->launches += viorb_launch_octree(g, F, e->buf, e->nodeCap, c->stream);
+    c->launches += viorb_launch_describe(g, F, e->buf, d_kps, d_desc, cap, d_counts, c->stream);
+    CU(cudaGetLastError());
+    return VIORB_OK;
+}
+
+int check_status(viorb_extractor* e) {
+    int st = 0;
+    CU(cudaMemcpyAsync(&st, e->buf.status, sizeof(int), cudaMemcpyDeviceToHost, e->ctx->stream));
+    CU(cudaStreamSynchronize(e->ctx->stream));
+    if (st) {
+        cudaMemsetAsync(e->buf.status, 0, sizeof(int), e->ctx->stream);
+        if (st & VIORB_DEV_CAND_OVERFLOW)
+            return fail(VIORB_ERR_CAPACITY, "FAST candidate pool overflow (raise it with viorb_extractor_configure cand_div)");
+        if (st & VIORB_DEV_OUT_OVERFLOW) return fail(VIORB_ERR_CAPACITY, "more keypoints than the caller's capacity");
+        return fail(VIORB_ERR_CAPACITY, "quadtree node pool overflow (device status %d)", st);
+    }
+    return VIORB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* viorb_last_error(void) { return g_err; }
+
+int viorb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int viorb_ctx_create(int device, void* stream, viorb_ctx** out) {
+    if (!out) return fail(VIORB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(VIORB_ERR_CUDA, "no CUDA device: %s (libviorb_b200 has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(VIORB_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(VIORB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    viorb_ctx* c = new (std::nothrow) viorb_ctx();
+    if (!c) return fail(VIORB_ERR_INVALID, "out of host memory");
+    c->device = device;
+    c->sms = prop.multiProcessorCount;
+    if (stream) { c->stream = (cudaStream_t)stream; c->ownStream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(VIORB_ERR_CUDA, "cudaStreamCreate failed"); }
+        c->ownStream = true;
+    }
+    if (cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return fail(VIORB_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    *out = c;
+    return VIORB_OK;
+}
+
+int viorb_ctx_destroy(viorb_ctx* c) {
+    if (!c) return VIORB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->mq.release(); c->mmap.release(); c->mparts.release(); c->mout.release();
+    c->scratchA.release(); c->scratchB.release(); c->scratchI.release();
+    if (c->ownStream) cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->h2d);
+    cudaStreamDestroy(c->d2h);
+    delete c;
+    return VIORB_OK;
+}
+
+int viorb_ctx_synchronize(viorb_ctx* c) {
+    if (!c) return fail(VIORB_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return VIORB_OK;
+}
+
+int64_t viorb_ctx_launch_count(const viorb_ctx* c) { return c ? c->launches : 0; }
+
+int viorb_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(VIORB_ERR_INVALID, "out is NULL");
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return VIORB_OK;
+}
+
+int viorb_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return VIORB_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------- extractor */
+int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, int nlevels, int ini, int mn,
+                           viorb_extractor** out) {
+    if (!ctx || !out) return fail(VIORB_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (nfeatures <= 0 || nlevels < 1 || nlevels > VIORB_MAX_LEVELS || !(scale_factor > 1.0f) || ini < mn || mn < 1 || ini > 255)
+        return fail(VIORB_ERR_INVALID, "bad ORB parameters (nfeatures %d, scale %f, levels %d, FAST %d/%d)", nfeatures,
+                    scale_factor, nlevels, ini, mn);
+    if (scale_factor == 2.0f)
+        return fail(VIORB_ERR_UNSUPPORTED, "scaleFactor == 2 takes cv::resize's INTER_AREA fast path; not implemented");
+    viorb_extractor* e = new (std::nothrow) viorb_extractor();
+    if (!e) return fail(VIORB_ERR_INVALID, "out of host memory");
+    e->ctx = ctx;
+    e->nfeatures = nfeatures; e->nlevels = nlevels; e->iniTh = ini; e->minTh = mn;
+    e->scaleFactor = scale_factor;
+    build_tables(e);
+    if (ctx_bind(ctx)) { delete e; return VIORB_ERR_CUDA; }
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&e->evIn[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->evDone[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->evOut[i], cudaEventDisableTiming);
+    }
+    *out = e;
+    return VIORB_OK;
+}
+
+int viorb_extractor_destroy(viorb_extractor* e) {
+    if (!e) return VIORB_OK;
+    cudaSetDevice(e->ctx->device);
+    cudaStreamSynchronize(e->ctx->stream);
+    cudaStreamSynchronize(e->ctx->h2d);
+    cudaStreamSynchronize(e->ctx->d2h);
+    e->tabU16.release(); e->tabI16.release(); e->pyr.release(); e->cand.release(); e->sel.release();
+    e->counters.release(); e->nodeOf.release();
+    for (int i = 0; i < 2; i++) {
+        e->in[i].release(); e->okps[i].release(); e->odesc[i].release(); e->ocnt[i].release();
+        if (e->evIn[i]) cudaEventDestroy(e->evIn[i]);
+        if (e->evDone[i]) cudaEventDestroy(e->evDone[i]);
+        if (e->evOut[i]) cudaEventDestroy(e->evOut[i]);
+    }
+    delete e;
+    return VIORB_OK;
+}
+
+int viorb_extractor_configure(viorb_extractor* e, int chunk_frames, int cand_div) {
+    if (!e) return fail(VIORB_ERR_INVALID, "extractor is NULL");
+    if (chunk_frames > 0) e->chunk = chunk_frames;
+    if (cand_div > 0 && cand_div != e->candDiv) { e->candDiv = cand_div; e->rows = e->cols = 0; }
+    return VIORB_OK;
+}
+
+int viorb_extractor_tables(const viorb_extractor* e, int* nlevels, float* scale, float* inv_scale, float* sigma2,
+                           float* inv_sigma2, int* fpl) {
+    if (!e) return fail(VIORB_ERR_INVALID, "extractor is NULL");
+    if (nlevels) *nlevels = e->nlevels;
+    for (int i = 0; i < e->nlevels; i++) {
+        if (scale) scale[i] = e->scale[i];
+        if (inv_scale) inv_scale[i] = e->invScale[i];
+        if (sigma2) sigma2[i] = e->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = e->invSigma2[i];
+        if (fpl) fpl[i] = e->quota[i];
+    }
+    return VIORB_OK;
+}
+
+int viorb_extract_batch_device(viorb_extractor* e, const uint8_t* d_images, int B, int rows, int cols, size_t step,
+                               size_t frame_stride, viorb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts) {
+    if (!e || !d_images || !d_kps || !d_desc || !d_counts) return fail(VIORB_ERR_INVALID, "NULL argument");
+    if (B <= 0 || rows <= 0 || cols <= 0 || cap <= 0 || step < (size_t)cols) return fail(VIORB_ERR_INVALID, "bad shape");
+    int rc;
+    if ((rc = ctx_bind(e->ctx))) return rc;
+    if ((rc = build_geometry(e, rows, cols))) return rc;
+    const int F = std::min(e->chunk, B);
+    if ((rc = ensure_workspace(e, F))) return rc;
+    for (int b0 = 0; b0 < B; b0 += F) {
+        const int f = std::min(F, B - b0);
+        if ((rc = run_pass(e, d_images + (size_t)b0 * frame_stride, step, frame_stride, f, d_kps + (size_t)b0 * cap,
+                           d_desc + (size_t)b0 * cap * 32, cap, d_counts + b0)))
+            return rc;
+        e->residentFirst = b0; e->residentCount = f;
+    }
+    return VIORB_OK;
+}
+
+int viorb_extractor_check(viorb_extractor* e) {
+    if (!e) return fail(VIORB_ERR_INVALID, "extractor is NULL");
+    int rc;
+    if ((rc = ctx_bind(e->ctx))) return rc;
+    if (!e->buf.status) { CU(cudaStreamSynchronize(e->ctx->stream)); return VIORB_OK; }
+    return check_status(e);
+}
+
+int viorb_extract_batch(viorb_extractor* e, const uint8_t* images, int B, int rows, int cols, size_t step,
+                        size_t frame_stride, viorb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts) {
+    if (!e || !kps || !desc || !counts) return fail(VIORB_ERR_INVALID, "NULL argument");
+    if (B <= 0 || !images || rows <= 0 || cols <= 0) {           /* empty input: silent return (:1046-1047) */
+        for (int b = 0; b < B; b++) counts[b] = 0;
+        return VIORB_OK;
+    }
+    if (cap <= 0 || step < (size_t)cols) return fail(VIORB_ERR_INVALID, "bad shape");
+    int rc;
+    viorb_ctx* c = e->ctx;
+    if ((rc = ctx_bind(c))) return rc;
+    if ((rc = build_geometry(e, rows, cols))) return rc;
+    const int F = std::min(e->chunk, B);
+    if ((rc = ensure_workspace(e, F))) return rc;
+    const size_t inFrame = (size_t)rows * cols;        /* device copy is packed */
+    for (int s = 0; s < 2; s++) {
+        if ((rc = e->in[s].ensure((size_t)F * inFrame))) return rc;
+        if ((rc = e->okps[s].ensure((size_t)F * cap))) return rc;
+        if ((rc = e->odesc[s].ensure((size_t)F * cap * 32))) return rc;
+        if ((rc = e->ocnt[s].ensure(F))) return rc;
+    }
+    /* pipeline: H2D(chunk k+1) || compute(chunk k) || D2H(chunk k-1), two staging slots */
+    CU(cudaStreamSynchronize(c->stream));
+    int k = 0;
+    for (int b0 = 0; b0 < B; b0 += F, k++) {
+        const int s = k & 1;
+        const int f = std::min(F, B - b0);
+        if (k >= 2) {
+            CU(cudaStreamWaitEvent(c->h2d, e->evDone[s], 0));    /* slot input free once its compute finished */
+            CU(cudaStreamWaitEvent(c->stream, e->evOut[s], 0));  /* slot outputs free once copied out */
+        }
+        if (frame_stride == step * rows) {
+            CU(cudaMemcpy2DAsync(e->in[s].p, cols, images + (size_t)b0 * frame_stride, step, cols, (size_t)rows * f,
+                                 cudaMemcpyHostToDevice, c->h2d));
+        } else {      /* frames are not back to back: one copy per frame */
+            for (int i = 0; i < f; i++)
+                CU(cudaMemcpy2DAsync(e->in[s].p + (size_t)i * inFrame, cols, images + (size_t)(b0 + i) * frame_stride, step,
+                                     cols, rows, cudaMemcpyHostToDevice, c->h2d));
+        }
+        CU(cudaEventRecord(e->evIn[s], c->h2d));
+        CU(cudaStreamWaitEvent(c->stream, e->evIn[s], 0));
+        if ((rc = run_pass(e, e->in[s].p, cols, inFrame, f, e->okps[s].p, e->odesc[s].p, cap, e->ocnt[s].p))) return rc;
+        CU(cudaEventRecord(e->evDone[s], c->stream));
+        CU(cudaStreamWaitEvent(c->d2h, e->evDone[s], 0));
+        CU(cudaMemcpyAsync(kps + (size_t)b0 * cap, e->okps[s].p, (size_t)f * cap * sizeof(viorb_keypoint),
+                           cudaMemcpyDeviceToHost, c->d2h));
+        CU(cudaMemcpyAsync(desc + (size_t)b0 * cap * 32, e->odesc[s].p, (size_t)f * cap * 32, cudaMemcpyDeviceToHost, c->d2h));
+        CU(cudaMemcpyAsync(counts + b0, e->ocnt[s].p, (size_t)f * sizeof(int32_t), cudaMemcpyDeviceToHost, c->d2h));
+        CU(cudaEventRecord(e->evOut[s], c->d2h));
+        e->residentFirst = b0; e->residentCount = f;
+    }
+    CU(cudaStreamSynchronize(c->d2h));
+    return check_status(e);
+}
+
+int viorb_extract(viorb_extractor* e, const uint8_t* image, int rows, int cols, size_t step, viorb_keypoint* kps,
+                  uint8_t* desc, int cap, int* n) {
+    if (!n) return fail(VIORB_ERR_INVALID, "n is NULL");
+    *n = 0;
+    if (!image || rows <= 0 || cols <= 0) return VIORB_OK;      /* empty image: silent return (:1046-1047) */
+    int32_t cnt = 0;
+    int rc = viorb_extract_batch(e, image, 1, rows, cols, step, step * rows, kps, desc, cap, &cnt);
+    if (rc) return rc;
+    *n = cnt;
+    return VIORB_OK;
+}
+
+int viorb_extractor_pyramid_info(const viorb_extractor* e, int level, int* w, int* h) {
+    if (!e || level < 0 || level >= e->nlevels || !e->rows) return fail(VIORB_ERR_INVALID, "no pyramid (level %d)", level);
+    if (w) *w = e->geom.lv[level].w;
+    if (h) *h = e->geom.lv[level].h;
+    return VIORB_OK;
+}
+
+int viorb_extractor_resident(const viorb_extractor* e, int* first, int* count) {
+    if (!e) return fail(VIORB_ERR_INVALID, "extractor is NULL");
+    if (first) *first = e->residentFirst;
+    if (count) *count = e->residentCount;
+    return VIORB_OK;
+}
+
+int viorb_extractor_pyramid_device(const viorb_extractor* e, int frame, int level, const uint8_t** d_roi, size_t* d_step) {
+    if (!e || level < 0 || level >= e->nlevels || !e->rows || frame < 0 || frame >= e->residentCount)
+        return fail(VIORB_ERR_INVALID, "frame %d / level %d not resident", frame, level);
+    const LevelGeom& L = e->geom.lv[level];
+    if (d_roi) *d_roi = e->buf.pyr + (size_t)frame * e->geom.pyrFrameBytes + L.pyrOff + (size_t)VIORB_EDGE * L.step + VIORB_ROI_X0;
+    if (d_step) *d_step = L.step;
+    return VIORB_OK;
+}
+
+int viorb_extractor_pyramid_download(viorb_extractor* e, int frame, int level, uint8_t* dst, size_t dst_step) {
+    if (!e || !dst || level < 0 || level >= e->nlevels || !e->rows || frame < 0 || frame >= e->residentCount)
+        return fail(VIORB_ERR_INVALID, "frame %d / level %d not resident", frame, level);
+    int rc;
+    if ((rc = ctx_bind(e->ctx))) return rc;
+    const LevelGeom& L = e->geom.lv[level];
+    const uint8_t* src = e->buf.pyr + (size_t)frame * e->geom.pyrFrameBytes + L.pyrOff + (VIORB_ROI_X0 - VIORB_EDGE);
+    CU(cudaMemcpy2DAsync(dst, dst_step, src, L.step, L.w + 2 * VIORB_EDGE, L.h + 2 * VIORB_EDGE, cudaMemcpyDeviceToHost,
+                         e->ctx->stream));
+    CU(cudaStreamSynchronize(e->ctx->stream));
+    return VIORB_OK;
+}
+
+static int download_packed(viorb_extractor* e, const uint32_t* d_src, const int* d_count, int capEntries, int32_t* xys,
+                           int cap, int* n) {
+    int cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, d_count, sizeof(int), cudaMemcpyDeviceToHost, e->ctx->stream));
+    CU(cudaStreamSynchronize(e->ctx->stream));
+    cnt = std::min(cnt, capEntries);
+    std::vector<uint32_t> tmp(std::max(cnt, 1));
+    CU(cudaMemcpyAsync(tmp.data(), d_src, (size_t)cnt * 4, cudaMemcpyDeviceToHost, e->ctx->stream));
+    CU(cudaStreamSynchronize(e->ctx->stream));
+    for (int i = 0; i < cnt && i < cap; i++) {
+        xys[3 * i] = tmp[i] & 0xfff;
+        xys[3 * i + 1] = (tmp[i] >> 12) & 0xfff;
+        xys[3 * i + 2] = tmp[i] >> 24;
+    }
+    *n = cnt;
+    return VIORB_OK;
+}
+
+int viorb_extractor_debug_candidates(viorb_extractor* e, int frame, int level, int32_t* xys, int cap, int* n) {
+    if (!e || !n || level < 0 || level >= e->nlevels || !e->rows || frame < 0 || frame >= e->residentCount)
+        return fail(VIORB_ERR_INVALID, "frame %d / level %d not resident", frame, level);
+    int rc;
+    if ((rc = ctx_bind(e->ctx))) return rc;
+    const LevelGeom& L = e->geom.lv[level];
+    rc = download_packed(e, e->buf.cand + (size_t)frame * e->geom.candPerFrame + L.candBase,
+                         e->buf.candCount + frame * e->nlevels + level, L.candCap, xys, cap, n);
+    if (rc) return rc;
+    for (int i = 0; i < *n && i < cap; i++) { xys[3 * i] += VIORB_FAST_BORDER; xys[3 * i + 1] += VIORB_FAST_BORDER; }
+    return VIORB_OK;
+}
+
+int viorb_extractor_debug_selected(viorb_extractor* e, int frame, int level, int32_t* xys, int cap, int* n) {
+    if (!e || !n || level < 0 || level >= e->nlevels || !e->rows || frame < 0 || frame >= e->residentCount)
+        return fail(VIORB_ERR_INVALID, "frame %d / level %d not resident", frame, level);
+    int rc;
+    if ((rc = ctx_bind(e->ctx))) return rc;
+    const LevelGeom& L = e->geom.lv[level];
+    return download_packed(e, e->buf.sel + (size_t)frame * e->geom.selPerFrame + L.selBase,
+                           e->buf.selCount + frame * e->nlevels + level, L.selCap, xys, cap, n);
+}
+
+/* ---------------------------------------------------------------------------------------------- matcher */
+int viorb_descriptor_distance(viorb_ctx* c, const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {
+    if (!c || !a || !b || !dist || n < 0) return fail(VIORB_ERR_INVALID, "bad argument");
+    if (n == 0) return VIORB_OK;
+    int rc;
+    if ((rc = ctx_bind(c))) return rc;
+    if ((rc = c->scratchA.ensure((size_t)n * 32)) || (rc = c->scratchB.ensure((size_t)n * 32)) || (rc = c->scratchI.ensure(n))) return rc;
+    CU(cudaMemcpyAsync(c->scratchA.p, a, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->scratchB.p, b, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    c->launches += viorb_launch_descriptor_distance(c->scratchA.p, c->scratchB.p, n, c->scratchI.p, c->stream);
+    CU(cudaMemcpyAsync(dist, c->scratchI.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VIORB_OK;
+}
+
+int viorb_hamming_top2_device(viorb_ctx* c, const uint8_t* d_q, int Q, const uint8_t* d_map, int64_t M, int64_t base,
+                              viorb_top2* d_out) {
+    if (!c || !d_q || !d_out || Q < 0 || M < 0 || (M > 0 && !d_map)) return fail(VIORB_ERR_INVALID, "bad argument");
+    if (base + M >= (1ll << 31)) return fail(VIORB_ERR_UNSUPPORTED, "map indices must fit in int32");
+    if (Q == 0) return VIORB_OK;
+    int rc;
+    if ((rc = ctx_bind(c))) return rc;
+    const int ns = viorb_top2_slices(Q, M, c->sms);
+    if ((rc = c->mparts.ensure((size_t)ns * Q))) return rc;
+    c->launches += viorb_launch_hamming_top2(d_q, Q, d_map, M, base, c->mparts.p, ns, d_out, c->stream);
+    CU(cudaGetLastError());
+    return VIORB_OK;
+}
+
+int viorb_hamming_top2(viorb_ctx* c, const uint8_t* q, int Q, const uint8_t* map, int64_t M, int64_t base, viorb_top2* out) {
+    if (!c || !q || !out || Q < 0 || M < 0 || (M > 0 && !map)) return fail(VIORB_ERR_INVALID, "bad argument");
+    if (Q == 0) return VIORB_OK;
+    int rc;
+    if ((rc = ctx_bind(c))) return rc;
+    if ((rc = c->mq.ensure((size_t)Q * 32)) || (rc = c->mmap.ensure((size_t)std::max<int64_t>(M, 1) * 32)) || (rc = c->mout.ensure(Q))) return rc;
+    CU(cudaMemcpyAsync(c->mq.p, q, (size_t)Q * 32, cudaMemcpyHostToDevice, c->stream));
+    if (M) CU(cudaMemcpyAsync(c->mmap.p, map, (size_t)M * 32, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = viorb_hamming_top2_device(c, c->mq.p, Q, c->mmap.p, M, base, c->mout.p))) return rc;
+    CU(cudaMemcpyAsync(out, c->mout.p, (size_t)Q * sizeof(viorb_top2), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VIORB_OK;
+}
+
+int viorb_top2_merge_device(viorb_ctx* c, const viorb_top2* d_parts, int nparts, int Q, viorb_top2* d_out) {
+    if (!c || !d_parts || !d_out || nparts < 1 || Q < 0) return fail(VIORB_ERR_INVALID, "bad argument");
+    int rc;
+    if ((rc = ctx_bind(c))) return rc;
+    c->launches += viorb_launch_top2_merge(d_parts, nparts, Q, d_out, c->stream);
+    CU(cudaGetLastError());
+    return VIORB_OK;
+}
+
+}  // extern "C"

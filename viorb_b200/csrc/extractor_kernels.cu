@@ -1,0 +1,815 @@
+/*
+ * extractor_kernels.cu -- hand-written sm_100a kernels for ORBextractor::operator()
+ * (reference: src/ORBextractor.cc:1043-1105).  One kernel per stage of the hot path:
+ *
+ *   pyr_level0_kernel / pyr_resize_kernel   ComputePyramid            :1107-1132  (+ cv::resize, copyMakeBorder)
+ *   fast_cells_kernel                       ComputeKeyPointsOctTree   :765-829    (+ cv::FAST x2 per cell)
+ *   octree_kernel                           DistributeOctTree         :539-763
+ *   orient_describe_kernel                  IC_Angle :77-104, GaussianBlur :1086, computeOrbDescriptor :108-147
+ *
+ * All integer stages are bit-exact restatements; float steps use round-to-nearest single ops without
+ * FMA contraction (the file is compiled with -fmad=false and uses __f*_rn where order matters).
+ * Nothing here is a dense contraction: no tensor cores, by design.
+ */
+#include "extractor_kernels.cuh"
+
+#include "viorb_orb_pattern.h"
+
+namespace {
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    /* BORDER_REFLECT_101 for |overshoot| < n (border 19 << n) */
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * ComputePyramid level 0: copyMakeBorder(image, temp, 19.., BORDER_REFLECT_101)   (:1127-1128)
+ * one thread = one 4-byte word of a stored row
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(128) pyr_level0_kernel(const __grid_constant__ FrameGeom g,
+                                                         const uint8_t* __restrict__ images, size_t inStep,
+                                                         size_t frameStride, uint8_t* __restrict__ pyr) {
+    const LevelGeom& L = g.lv[0];
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;                 /* stored row 0 .. h+38 */
+    const int frame = blockIdx.z;
+    if (wi * 4 >= L.step) return;
+    const int sy = reflect101(row - VIORB_EDGE, L.h);
+    const uint8_t* src = images + (size_t)frame * frameStride + (size_t)sy * inStep;
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int x = wi * 4 + j - VIORB_ROI_X0;
+        uint32_t v = 0;
+        if (x >= -VIORB_EDGE && x < L.w + VIORB_EDGE) v = src[reflect101(x, L.w)];
+        word |= v << (8 * j);
+    }
+    uint8_t* dst = pyr + (size_t)frame * g.pyrFrameBytes + L.pyrOff + (size_t)row * L.step;
+    reinterpret_cast<uint32_t*>(dst)[wi] = word;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * ComputePyramid level l > 0: resize(level l-1 ROI -> level l ROI, INTER_LINEAR) then
+ * copyMakeBorder(..., BORDER_REFLECT_101 + BORDER_ISOLATED)                     (:1120-1123)
+ * cv::resize 8-bit fixed point: T = S[sx]*a0 + S[sx+1]*a1 ; D = (((b0*(T0>>4))>>16) + ((b1*(T1>>4))>>16) + 2) >> 2
+ * The border pixels are produced by evaluating the same expression at the reflected ROI coordinate.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__ FrameGeom g, int level,
+                                                         ResizeTables t, uint8_t* __restrict__ pyr) {
+    const LevelGeom& L = g.lv[level];
+    const LevelGeom& P = g.lv[level - 1];
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    const int frame = blockIdx.z;
+    if (wi * 4 >= L.step) return;
+    uint8_t* base = pyr + (size_t)frame * g.pyrFrameBytes;
+    const int dy = reflect101(row - VIORB_EDGE, L.h);
+    const int sy = t.yofs[L.ytab + dy];
+    const int b0 = t.yb[2 * (L.ytab + dy)], b1 = t.yb[2 * (L.ytab + dy) + 1];
+    const int sy0 = min(max(sy, 0), P.h - 1), sy1 = min(max(sy + 1, 0), P.h - 1);
+    const uint8_t* S0 = base + P.pyrOff + (size_t)(sy0 + VIORB_EDGE) * P.step + VIORB_ROI_X0;
+    const uint8_t* S1 = base + P.pyrOff + (size_t)(sy1 + VIORB_EDGE) * P.step + VIORB_ROI_X0;
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int x = wi * 4 + j - VIORB_ROI_X0;
+        uint32_t v = 0;
+        if (x >= -VIORB_EDGE && x < L.w + VIORB_EDGE) {
+            const int dx = reflect101(x, L.w);
+            const int sx = t.xofs[L.xtab + dx];
+            const int a0 = t.xa[2 * (L.xtab + dx)], a1 = t.xa[2 * (L.xtab + dx) + 1];
+            const int sx1 = min(sx + 1, P.w - 1);
+            const int T0 = S0[sx] * a0 + S0[sx1] * a1;
+            const int T1 = S1[sx] * a0 + S1[sx1] * a1;
+            v = (uint32_t)((((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2) & 0xffu;
+        }
+        word |= v << (8 * j);
+    }
+    uint8_t* dst = base + L.pyrOff + (size_t)row * L.step;
+    reinterpret_cast<uint32_t*>(dst)[wi] = word;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * FAST-9/16 per cell with the iniThFAST -> minThFAST retry (:789-829, cv::FAST TYPE_9_16 + NMS).
+ *
+ * One CTA per cell.  The cell sub-image [iniX, maxX) x [iniY, maxY) is staged in shared memory; the
+ * detection window is inset by 3 (cv::FAST never tests the 3-pixel rim).  For every window pixel the
+ * threshold-independent corner score  S = max(max_arc min d, max_arc min -d) - 1  (cornerScore<16>) is
+ * computed; a pixel is a corner at threshold t iff S >= t.  cv::FAST's 3x3 non-max suppression keeps a
+ * corner iff its score is strictly greater than all 8 neighbours, where non-corners and pixels outside
+ * the window count 0 -- which is "S_p >= t and S_p > S_n for all window neighbours", so one local-max
+ * map serves both thresholds and the retry only re-filters by minThFAST.
+ * ---------------------------------------------------------------------------------------------- */
+#define FAST_TILE 68
+#define FAST_TSTRIDE 72
+#define FAST_SC 64
+
+__device__ __forceinline__ int fast_score(const uint8_t* p /* centre, row stride FAST_TSTRIDE */, int minTh) {
+    const int v = p[0];
+    int d[16];
+    d[0] = v - p[3 * FAST_TSTRIDE];
+    d[1] = v - p[3 * FAST_TSTRIDE + 1];
+    d[2] = v - p[2 * FAST_TSTRIDE + 2];
+    d[3] = v - p[1 * FAST_TSTRIDE + 3];
+    d[4] = v - p[3];
+    d[5] = v - p[-1 * FAST_TSTRIDE + 3];
+    d[6] = v - p[-2 * FAST_TSTRIDE + 2];
+    d[7] = v - p[-3 * FAST_TSTRIDE + 1];
+    d[8] = v - p[-3 * FAST_TSTRIDE];
+    d[9] = v - p[-3 * FAST_TSTRIDE - 1];
+    d[10] = v - p[-2 * FAST_TSTRIDE - 2];
+    d[11] = v - p[-1 * FAST_TSTRIDE - 3];
+    d[12] = v - p[-3];
+    d[13] = v - p[1 * FAST_TSTRIDE - 3];
+    d[14] = v - p[2 * FAST_TSTRIDE - 2];
+    d[15] = v - p[3 * FAST_TSTRIDE - 1];
+    /* high-speed rejection at minTh: every 9-arc contains ring pixel k or k+8 for each k */
+    {
+        bool dark = true, bright = true;
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            dark = dark && (d[k] > minTh || d[k + 8] > minTh);
+            bright = bright && (d[k] < -minTh || d[k + 8] < -minTh);
+        }
+        if (!dark && !bright) return 0;
+    }
+    /* sliding 9-window min and max over the circular ring */
+    int mn2[16], mx2[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mn2[k] = min(d[k], d[(k + 1) & 15]);
+        mx2[k] = max(d[k], d[(k + 1) & 15]);
+    }
+    int mn4[16], mx4[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
+        mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+    }
+    int a = -256, b = 256;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+        a = max(a, mn9);
+        b = min(b, mx9);
+    }
+    const int s = max(a, -b) - 1;
+    return s >= minTh ? s : 0;
+}
+
+__global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__ FrameGeom g,
+                                                         const uint8_t* __restrict__ pyr,
+                                                         uint32_t* __restrict__ cand, int* __restrict__ candCount,
+                                                         int* __restrict__ status) {
+    __shared__ __align__(16) uint8_t tile[FAST_TILE * FAST_TSTRIDE];
+    __shared__ uint8_t sc[(FAST_SC + 2) * (FAST_SC + 2)];
+    const int frame = blockIdx.y;
+    int l = 0;
+    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].cellBase) l++;
+    const LevelGeom& L = g.lv[l];
+    const int c = blockIdx.x - L.cellBase;
+    const int ci = c / L.nCols, cj = c - ci * L.nCols;
+    const int maxBorderX = L.w - VIORB_FAST_BORDER, maxBorderY = L.h - VIORB_FAST_BORDER;
+    const int iniY = VIORB_FAST_BORDER + ci * L.hCell;
+    const int iniX = VIORB_FAST_BORDER + cj * L.wCell;
+    if (iniY >= maxBorderY - 3 || iniX >= maxBorderX - 6) return;   /* :795-796, :804-805 */
+    const int cw = min(iniX + L.wCell + 6, maxBorderX) - iniX;
+    const int ch = min(iniY + L.hCell + 6, maxBorderY) - iniY;
+    const int ww = cw - 6, wh = ch - 6;      /* detection window */
+    if (ww <= 0 || wh <= 0) return;
+
+    const uint8_t* roi = pyr + (size_t)frame * g.pyrFrameBytes + L.pyrOff + (size_t)VIORB_EDGE * L.step + VIORB_ROI_X0;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < cw * ch; i += blockDim.x) {
+        const int y = i / cw, x = i - y * cw;
+        tile[y * FAST_TSTRIDE + x] = roi[(size_t)(iniY + y) * L.step + iniX + x];
+    }
+    const int scw = ww + 2;
+    for (int i = tid; i < scw * (wh + 2); i += blockDim.x) sc[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < ww * wh; i += blockDim.x) {
+        const int y = i / ww, x = i - y * ww;
+        sc[(y + 1) * scw + x + 1] = (uint8_t)fast_score(&tile[(y + 3) * FAST_TSTRIDE + x + 3], g.minTh);
+    }
+    __syncthreads();
+    /* local maxima + count at iniThFAST */
+    unsigned lmBits = 0;      /* one bit per pixel handled by this thread (<= 32 iterations) */
+    int nIni = 0;
+    int it = 0;
+    for (int i = tid; i < ww * wh; i += blockDim.x, it++) {
+        const int y = i / ww, x = i - y * ww;
+        const uint8_t* q = &sc[(y + 1) * scw + x + 1];
+        const int s = q[0];
+        bool lm = s > 0 && s > q[-1] && s > q[1] && s > q[-scw - 1] && s > q[-scw] && s > q[-scw + 1] &&
+                  s > q[scw - 1] && s > q[scw] && s > q[scw + 1];
+        if (lm) {
+            lmBits |= 1u << it;
+            if (s >= g.iniTh) nIni++;
+        }
+    }
+    const int total = __syncthreads_count(nIni > 0);
+    const int th = total > 0 ? g.iniTh : g.minTh;     /* retry with minThFAST only if the cell is empty (:812) */
+    it = 0;
+    int* counter = candCount + frame * g.nlevels + l;
+    uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
+    for (int i = tid; i < ww * wh; i += blockDim.x, it++) {
+        if (!(lmBits >> it & 1u)) continue;
+        const int y = i / ww, x = i - y * ww;
+        const int s = sc[(y + 1) * scw + x + 1];
+        if (s < th) continue;
+        const int pos = atomicAdd(counter, 1);
+        if (pos < L.candCap) {
+            /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
+            const uint32_t X = x + 3 + cj * L.wCell, Y = y + 3 + ci * L.hCell;
+            out[pos] = X | (Y << 12) | ((uint32_t)s << 24);
+        } else {
+            atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * DistributeOctTree (:539-763) as a depth-synchronous quadtree refinement, one CTA per (frame, level).
+ *
+ * The reference's std::list is always ordered by node creation time, newest first (children are
+ * push_front'ed, roots push_back'ed), so the list can be kept as an array in that order and rebuilt
+ * per pass:   new list = [children, newest first] ++ [surviving old nodes in old order].
+ * Normal passes expand every node holding > 1 key in list order; once  size + 3*nToExpand > N  the
+ * reference expands in (size desc, pointer desc) order and stops as soon as size >= N; the pointer
+ * is replaced by the creation order (newest first == list order), the documented tie convention.
+ * Keys never move: each key only tracks the list position of its node (nodeOf).
+ * ---------------------------------------------------------------------------------------------- */
+#define OCT_THREADS 256
+
+struct OctSmem {
+    short4* rectA; short4* rectB;   /* x0,y0,x1,y1 */
+    int* cntA; int* cntB;
+    int* cc;        /* [4*NC] child key counts */
+    int* erank;     /* [NC] expansion rank or -1 */
+    int* aux;       /* [NC] scan / new position */
+    unsigned* srt;  /* [pow2(NC)] sort keys */
+    unsigned short* childPos;   /* [4*NC] */
+};
+
+__device__ __forceinline__ int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+/* exclusive scan of data[0..n) in place; returns the total.  All threads of the block must call. */
+__device__ int block_exscan(int* data, int n, int* warpTmp /* 32 ints shared */) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int per = (n + nt - 1) / nt;
+    const int beg = min(tid * per, n), end = min(beg + per, n);
+    int sum = 0;
+    for (int i = beg; i < end; i++) sum += data[i];
+    /* block scan of per-thread sums */
+    int v = sum;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) warpTmp[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < (nt >> 5) ? warpTmp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        warpTmp[lane] = w;    /* inclusive over warps */
+    }
+    __syncthreads();
+    const int total = warpTmp[(nt >> 5) - 1];
+    int run = v - sum + (wid > 0 ? warpTmp[wid - 1] : 0);
+    __syncthreads();
+    for (int i = beg; i < end; i++) {
+        int t = data[i];
+        data[i] = run;
+        run += t;
+    }
+    __syncthreads();
+    return total;
+}
+
+__device__ void block_bitonic_sort(unsigned* a, int n /* power of two */) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned x = a[i], y = a[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int quadrant(int kx, int ky, short4 r) {
+    /* DivideNode :481-526: halfX = ceil((UR.x-UL.x)/2.f); key goes left iff pt.x < UL.x+halfX */
+    const int mx = r.x + ((r.z - r.x + 1) >> 1);
+    const int my = r.y + ((r.w - r.y + 1) >> 1);
+    return (kx < mx ? 0 : 1) + (ky < my ? 0 : 2);
+}
+
+__global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const __grid_constant__ FrameGeom g,
+                                                             const uint32_t* __restrict__ cand,
+                                                             const int* __restrict__ candCount,
+                                                             uint16_t* __restrict__ nodeOfAll,
+                                                             uint32_t* __restrict__ sel, int* __restrict__ selCount,
+                                                             int* __restrict__ status, int NC) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    __shared__ int warpTmp[32];
+    __shared__ int sh[8];
+    const int level = blockIdx.x, frame = blockIdx.y;
+    const LevelGeom& L = g.lv[level];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int n = min(candCount[frame * g.nlevels + level], L.candCap);
+    const uint32_t* keys = cand + (size_t)frame * g.candPerFrame + L.candBase;
+    uint16_t* nodeOf = nodeOfAll + (size_t)frame * g.candPerFrame + L.candBase;
+    uint32_t* out = sel + (size_t)frame * g.selPerFrame + L.selBase;
+    const int N = L.quota;
+    if (n == 0) {
+        if (tid == 0) selCount[frame * g.nlevels + level] = 0;
+        return;
+    }
+    /* carve shared memory */
+    OctSmem S;
+    {
+        unsigned char* p = smemRaw;
+        S.rectA = (short4*)p; p += sizeof(short4) * NC;
+        S.rectB = (short4*)p; p += sizeof(short4) * NC;
+        S.cntA = (int*)p; p += sizeof(int) * NC;
+        S.cntB = (int*)p; p += sizeof(int) * NC;
+        S.cc = (int*)p; p += sizeof(int) * 4 * NC;
+        S.erank = (int*)p; p += sizeof(int) * NC;
+        S.aux = (int*)p; p += sizeof(int) * NC;
+        S.srt = (unsigned*)p; p += sizeof(unsigned) * next_pow2(NC);
+        S.childPos = (unsigned short*)p;
+    }
+    short4* rect = S.rectA; short4* rectN = S.rectB;
+    int* cnt = S.cntA; int* cntN = S.cntB;
+
+    /* ---- roots (:543-585) ---- */
+    const int W = (L.w - VIORB_FAST_BORDER) - VIORB_FAST_BORDER, H = (L.h - VIORB_FAST_BORDER) - VIORB_FAST_BORDER;
+    const int nIni = L.nIni;
+    const float hX = __fdiv_rn((float)W, (float)nIni);
+    for (int i = tid; i < nIni; i += nt) {
+        rect[i] = make_short4((short)(int)__fmul_rn(hX, (float)i), 0, (short)(int)__fmul_rn(hX, (float)(i + 1)), (short)H);
+        cnt[i] = 0;
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) {
+        const int kx = keys[k] & 0xfff;
+        int r = (int)__fdiv_rn((float)kx, hX);
+        r = min(r, nIni - 1);
+        nodeOf[k] = (uint16_t)r;
+        atomicAdd(&cnt[r], 1);
+    }
+    __syncthreads();
+    /* drop empty roots, keep order */
+    for (int i = tid; i < nIni; i += nt) S.aux[i] = cnt[i] > 0 ? 1 : 0;
+    __syncthreads();
+    int Sn = block_exscan(S.aux, nIni, warpTmp);
+    for (int i = tid; i < nIni; i += nt)
+        if (cnt[i] > 0) { rectN[S.aux[i]] = rect[i]; cntN[S.aux[i]] = cnt[i]; }
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) nodeOf[k] = (uint16_t)S.aux[nodeOf[k]];
+    { short4* t = rect; rect = rectN; rectN = t; int* u = cnt; cnt = cntN; cntN = u; }
+    __syncthreads();
+
+    bool careful = false;
+    for (;;) {
+        const int prev = Sn;
+        /* number of expandable nodes */
+        int myMulti = 0;
+        for (int i = tid; i < Sn; i += nt) myMulti += cnt[i] > 1;
+        const int anyMulti = __syncthreads_or(myMulti);
+        if (!anyMulti) break;                       /* size == prevSize -> finish (:669) */
+        /* child key counts of every expandable node */
+        for (int i = tid; i < 4 * Sn; i += nt) S.cc[i] = 0;
+        __syncthreads();
+        for (int k = tid; k < n; k += nt) {
+            const int i = nodeOf[k];
+            if (cnt[i] > 1) {
+                const uint32_t key = keys[k];
+                atomicAdd(&S.cc[4 * i + quadrant(key & 0xfff, (key >> 12) & 0xfff, rect[i])], 1);
+            }
+        }
+        __syncthreads();
+        int E;     /* number of nodes expanded this pass */
+        if (!careful) {
+            /* list order (:594-665) */
+            for (int i = tid; i < Sn; i += nt) S.aux[i] = cnt[i] > 1 ? 1 : 0;
+            __syncthreads();
+            E = block_exscan(S.aux, Sn, warpTmp);
+            for (int i = tid; i < Sn; i += nt) S.erank[i] = cnt[i] > 1 ? S.aux[i] : -1;
+            __syncthreads();
+        } else {
+            /* (size desc, newest first) order with early stop at N (:673-738) */
+            for (int i = tid; i < Sn; i += nt) S.aux[i] = cnt[i] > 1 ? 1 : 0;
+            __syncthreads();
+            const int nM = block_exscan(S.aux, Sn, warpTmp);
+            const int P2 = next_pow2(nM);
+            for (int i = tid; i < P2; i += nt) S.srt[i] = 0xffffffffu;
+            __syncthreads();
+            for (int i = tid; i < Sn; i += nt)
+                if (cnt[i] > 1) S.srt[S.aux[i]] = ((unsigned)(65535 - min(cnt[i], 65535)) << 16) | (unsigned)i;
+            __syncthreads();
+            block_bitonic_sort(S.srt, P2);
+            /* gains in sorted order */
+            for (int r = tid; r < nM; r += nt) {
+                const int i = S.srt[r] & 0xffff;
+                const int ne = (S.cc[4 * i] > 0) + (S.cc[4 * i + 1] > 0) + (S.cc[4 * i + 2] > 0) + (S.cc[4 * i + 3] > 0);
+                S.aux[r] = ne - 1;
+            }
+            for (int i = tid; i < Sn; i += nt) S.erank[i] = -1;
+            if (tid == 0) sh[0] = nM;
+            __syncthreads();
+            block_exscan(S.aux, nM, warpTmp);       /* aux[r] = gain before r */
+            for (int r = tid; r < nM; r += nt) {
+                const int i = S.srt[r] & 0xffff;
+                const int ne = (S.cc[4 * i] > 0) + (S.cc[4 * i + 1] > 0) + (S.cc[4 * i + 2] > 0) + (S.cc[4 * i + 3] > 0);
+                const int before = prev + S.aux[r], after = before + ne - 1;
+                if (before < N && after >= N) sh[0] = r + 1;      /* first rank reaching N: expand r, then break */
+            }
+            __syncthreads();
+            E = sh[0];
+            for (int r = tid; r < E; r += nt) S.erank[S.srt[r] & 0xffff] = r;
+            __syncthreads();
+        }
+        /* creation ranks of the children: expansion order, then n1..n4 */
+        for (int i = tid; i < Sn; i += nt) {
+            const int e = S.erank[i];
+            if (e >= 0) S.srt[e] = (unsigned)i;       /* node expanded at rank e */
+        }
+        __syncthreads();
+        for (int e = tid; e < E; e += nt) {
+            const int i = S.srt[e];
+            S.aux[e] = (S.cc[4 * i] > 0) + (S.cc[4 * i + 1] > 0) + (S.cc[4 * i + 2] > 0) + (S.cc[4 * i + 3] > 0);
+        }
+        __syncthreads();
+        const int C = block_exscan(S.aux, E, warpTmp);      /* aux[e] = children created before rank e */
+        const int SnNew = C + (Sn - E);
+        if (SnNew > NC || SnNew > L.selCap) {
+            if (tid == 0) { atomicOr(status, VIORB_DEV_NODE_OVERFLOW); selCount[frame * g.nlevels + level] = 0; }
+            return;
+        }
+        /* children */
+        for (int e = tid; e < E; e += nt) {
+            const int i = S.srt[e];
+            const short4 r = rect[i];
+            const int mx = r.x + ((r.z - r.x + 1) >> 1), my = r.y + ((r.w - r.y + 1) >> 1);
+            int j = S.aux[e];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int c = S.cc[4 * i + q];
+                if (c > 0) {
+                    const int pos = C - 1 - j;
+                    j++;
+                    short4 cr;
+                    cr.x = (q & 1) ? (short)mx : r.x;
+                    cr.z = (q & 1) ? r.z : (short)mx;
+                    cr.y = (q & 2) ? (short)my : r.y;
+                    cr.w = (q & 2) ? r.w : (short)my;
+                    rectN[pos] = cr;
+                    cntN[pos] = c;
+                    S.childPos[4 * i + q] = (unsigned short)pos;
+                }
+            }
+        }
+        __syncthreads();
+        /* survivors keep their relative order behind the new children */
+        for (int i = tid; i < Sn; i += nt) S.aux[i] = S.erank[i] < 0 ? 1 : 0;
+        __syncthreads();
+        block_exscan(S.aux, Sn, warpTmp);
+        for (int i = tid; i < Sn; i += nt)
+            if (S.erank[i] < 0) {
+                const int pos = C + S.aux[i];
+                rectN[pos] = rect[i];
+                cntN[pos] = cnt[i];
+                S.aux[i] = pos;
+            }
+        __syncthreads();
+        for (int k = tid; k < n; k += nt) {
+            const int i = nodeOf[k];
+            if (S.erank[i] >= 0) {
+                const uint32_t key = keys[k];
+                nodeOf[k] = S.childPos[4 * i + quadrant(key & 0xfff, (key >> 12) & 0xfff, rect[i])];
+            } else {
+                nodeOf[k] = (uint16_t)S.aux[i];
+            }
+        }
+        { short4* t = rect; rect = rectN; rectN = t; int* u = cnt; cnt = cntN; cntN = u; }
+        Sn = SnNew;
+        __syncthreads();
+        if (Sn >= N || Sn == prev) break;           /* (:669, :734) */
+        if (!careful) {
+            int m = 0;
+            for (int i = tid; i < Sn; i += nt) m += cnt[i] > 1;
+            /* nToExpand = children created this pass that hold > 1 key == all multi-key nodes now */
+            for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+            if ((tid & 31) == 0) warpTmp[tid >> 5] = m;
+            __syncthreads();
+            int nToExpand = 0;
+            for (int w = 0; w < (nt >> 5); w++) nToExpand += warpTmp[w];
+            __syncthreads();
+            if (Sn + 3 * nToExpand > N) careful = true;     /* (:673) */
+        }
+    }
+
+    /* ---- retain the best key per node (:741-760): max response, first in candidate order on ties.
+     * candidate order = (cell row, cell col, y, x)  (:789-829) ---- */
+    int* best = S.cc;           /* reuse */
+    unsigned* tie = (unsigned*)S.erank;
+    for (int i = tid; i < Sn; i += nt) { best[i] = 0; tie[i] = 0xffffffffu; }
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) atomicMax(&best[nodeOf[k]], (int)(keys[k] >> 24));
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) {
+        const uint32_t key = keys[k];
+        const int i = nodeOf[k];
+        if ((int)(key >> 24) == best[i]) {
+            const int x = (key & 0xfff) - 3, y = ((key >> 12) & 0xfff) - 3;
+            const int cy = y / L.hCell, cx = x / L.wCell;
+            const unsigned ord = ((unsigned)cy << 20) | ((unsigned)cx << 12) | ((unsigned)(y - cy * L.hCell) << 6) |
+                                 (unsigned)(x - cx * L.wCell);
+            atomicMin(&tie[i], ord);
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) {
+        const uint32_t key = keys[k];
+        const int i = nodeOf[k];
+        if ((int)(key >> 24) == best[i]) {
+            const int x = (key & 0xfff) - 3, y = ((key >> 12) & 0xfff) - 3;
+            const int cy = y / L.hCell, cx = x / L.wCell;
+            const unsigned ord = ((unsigned)cy << 20) | ((unsigned)cx << 12) | ((unsigned)(y - cy * L.hCell) << 6) |
+                                 (unsigned)(x - cx * L.wCell);
+            if (ord == tie[i]) {
+                /* level coordinates: += minBorder (:840-841) */
+                const uint32_t X = (key & 0xfff) + VIORB_FAST_BORDER, Y = ((key >> 12) & 0xfff) + VIORB_FAST_BORDER;
+                out[i] = X | (Y << 12) | (key & 0xff000000u);
+            }
+        }
+    }
+    if (tid == 0) selCount[frame * g.nlevels + level] = Sn;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * IC_Angle (:77-104) + GaussianBlur 7x7 sigma 2 (:1086) + computeOrbDescriptor (:108-147), fused:
+ * one warp per selected keypoint.  The 43x43 neighbourhood (radius 18 pattern reach + 3 blur taps)
+ * is staged in shared memory from the padded pyramid (whose REFLECT_101 border equals the blur's own
+ * border rule), blurred there with the OpenCV >= 3.4 fixed-point taps [18 34 48 56 48 34 18]/256,
+ * and sampled at the 512 steered pattern points.  The blurred level image never exists in HBM.
+ * ---------------------------------------------------------------------------------------------- */
+#define DESC_WARPS 4
+#define PR 21                 /* patch radius */
+#define PW 43                 /* patch width */
+#define PSTRIDE 44
+#define BW 37                 /* blurred width (radius 18) */
+#define HSTRIDE 38
+
+__constant__ int8_t c_pattern[1024] = VIORB_ORB_PATTERN_INIT;
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+/* cv::fastAtan2 (degrees), OpenCV core mathfuncs_core atan_f32 polynomial, no FMA */
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, scale);
+    const float p3 = __fmul_rn(-0.3258083974640975f, scale);
+    const float p5 = __fmul_rn(0.1555786518463281f, scale);
+    const float p7 = __fmul_rn(-0.04432655554792128f, scale);
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+/* glibc flt-32 sincosf (double polynomial, generic reduction), every op rounded separately.
+ * Valid for |y| < 120; the extractor feeds angles in [0, 2*pi].   */
+__device__ __forceinline__ void sincosf_glibc(float y, float* sinp, float* cosp) {
+    const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+    const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+                 C4 = 0x1.99343027bf8c3p-16;
+    const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+    double x = (double)y;
+    const unsigned top = (__float_as_uint(y) >> 20) & 0x7ff;
+    int n = 0;
+    double sgnc = 1.0;     /* cosine polynomial sign (table entry 1 negates it) */
+    double xs;
+    double x2;
+    if (top < 0x3f4u) {            /* abstop12(pi/4 = 0x1.921FB6p-1f) */
+        if (top < 0x398u) {        /* abstop12(0x1p-12f) */
+            *sinp = y;
+            *cosp = 1.0f;
+            return;
+        }
+        x2 = __dmul_rn(x, x);
+        xs = x;
+    } else {
+        const double r = __dmul_rn(x, hpi_inv);
+        n = ((int)r + 0x800000) >> 24;
+        x = __dsub_rn(x, __dmul_rn((double)n, hpi));
+        const double s = (n & 3) == 1 || (n & 3) == 2 ? -1.0 : 1.0;
+        if (n & 2) sgnc = -1.0;
+        x2 = __dmul_rn(x, x);
+        xs = __dmul_rn(x, s);
+    }
+    const double c0 = C0 * sgnc, c1 = C1 * sgnc, c2k = C2 * sgnc, c3 = C3 * sgnc, c4 = C4 * sgnc;
+    const double x4 = __dmul_rn(x2, x2);
+    const double x3 = __dmul_rn(x2, xs);
+    const double cc2 = __dadd_rn(c3, __dmul_rn(x2, c4));
+    const double s1 = __dadd_rn(S2, __dmul_rn(x2, S3));
+    const double cc1 = __dadd_rn(c0, __dmul_rn(x2, c1));
+    const double x5 = __dmul_rn(x3, x2);
+    const double x6 = __dmul_rn(x4, x2);
+    const double s = __dadd_rn(xs, __dmul_rn(x3, S1));
+    const double c = __dadd_rn(cc1, __dmul_rn(x4, c2k));
+    const float sv = (float)__dadd_rn(s, __dmul_rn(x5, s1));
+    const float cv = (float)__dadd_rn(c, __dmul_rn(x6, cc2));
+    if (n & 1) { *cosp = sv; *sinp = cv; }
+    else { *sinp = sv; *cosp = cv; }
+}
+
+__global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const __grid_constant__ FrameGeom g,
+                                                                          const uint8_t* __restrict__ pyr,
+                                                                          const uint32_t* __restrict__ sel,
+                                                                          const int* __restrict__ selCount,
+                                                                          viorb_keypoint* __restrict__ kps,
+                                                                          uint8_t* __restrict__ desc, int cap,
+                                                                          int32_t* __restrict__ counts,
+                                                                          int* __restrict__ status) {
+    __shared__ __align__(16) uint8_t patch[DESC_WARPS][PW * PSTRIDE];
+    __shared__ __align__(16) uint16_t hb[DESC_WARPS][PW * HSTRIDE];
+    __shared__ __align__(16) uint8_t vb[DESC_WARPS][BW * HSTRIDE];
+    const int frame = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * DESC_WARPS + warp;
+    /* locate (level, index) of this slot in the concatenated per-level lists (:1076-1103) */
+    int level = -1, idx = 0, total = 0;
+    {
+        int acc = 0;
+        for (int l = 0; l < g.nlevels; l++) {
+            const int c = selCount[frame * g.nlevels + l];
+            if (level < 0 && slot < acc + c) { level = l; idx = slot - acc; }
+            acc += c;
+        }
+        total = acc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        counts[frame] = min(total, cap);
+        if (total > cap) atomicOr(status, VIORB_DEV_OUT_OVERFLOW);
+    }
+    if (level < 0 || slot >= cap) return;
+    const LevelGeom& L = g.lv[level];
+    const uint32_t key = sel[(size_t)frame * g.selPerFrame + L.selBase + idx];
+    const int kx = key & 0xfff, ky = (key >> 12) & 0xfff, score = key >> 24;
+    const uint8_t* roi = pyr + (size_t)frame * g.pyrFrameBytes + L.pyrOff + (size_t)VIORB_EDGE * L.step + VIORB_ROI_X0;
+    uint8_t* P = patch[warp];
+    uint16_t* Hb = hb[warp];
+    uint8_t* Vb = vb[warp];
+    /* stage the 43x43 neighbourhood */
+    for (int i = lane; i < PW * PW; i += 32) {
+        const int r = i / PW, c = i - r * PW;
+        P[r * PSTRIDE + c] = roi[(ptrdiff_t)(ky - PR + r) * L.step + (kx - PR + c)];
+    }
+    __syncwarp();
+    /* IC_Angle: lane v+15 sums row v of the circular patch */
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int v = lane - 15;
+        const int d = c_umax[v < 0 ? -v : v];
+        const uint8_t* row = &P[(PR + v) * PSTRIDE + PR];
+        int s = 0;
+        for (int u = -d; u <= d; u++) {
+            const int val = row[u];
+            m10 += u * val;
+            s += val;
+        }
+        m01 = v * s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    /* separable 7-tap blur in shared memory */
+    for (int i = lane; i < PW * BW; i += 32) {
+        const int r = i / BW, c = i - r * BW;
+        const uint8_t* s = &P[r * PSTRIDE + c];
+        Hb[r * HSTRIDE + c] = (uint16_t)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+    }
+    __syncwarp();
+    for (int i = lane; i < BW * BW; i += 32) {
+        const int r = i / BW, c = i - r * BW;
+        const uint16_t* s = &Hb[r * HSTRIDE + c];
+        const unsigned acc = 18u * (s[0] + s[6 * HSTRIDE]) + 34u * (s[HSTRIDE] + s[5 * HSTRIDE]) +
+                             48u * (s[2 * HSTRIDE] + s[4 * HSTRIDE]) + 56u * s[3 * HSTRIDE];
+        Vb[r * HSTRIDE + c] = (uint8_t)((acc + 32768u) >> 16);
+    }
+    __syncwarp();
+    /* steered BRIEF: lane i produces descriptor byte i (:123-144) */
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    float a, b;
+    sincosf_glibc(__fmul_rn(angle, factorPI), &b, &a);
+    const uint8_t* centre = &Vb[18 * HSTRIDE + 18];
+    unsigned val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int8_t* pt = &c_pattern[(lane * 8 + k) * 4];
+        const float x0 = (float)pt[0], y0 = (float)pt[1], x1 = (float)pt[2], y1 = (float)pt[3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = centre[r0 * HSTRIDE + c0], t1 = centre[r1 * HSTRIDE + c1];
+        val |= (unsigned)(t0 < t1) << k;
+    }
+    desc[((size_t)frame * cap + slot) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        viorb_keypoint kp;
+        /* pt *= mvScaleFactor[level] for level > 0 (:1094-1101) */
+        kp.x = level ? __fmul_rn((float)kx, L.scale) : (float)kx;
+        kp.y = level ? __fmul_rn((float)ky, L.scale) : (float)ky;
+        kp.size = (float)L.patchSize;
+        kp.angle = angle;
+        kp.response = (float)score;
+        kp.octave = level;
+        kp.class_id = -1;
+        kps[(size_t)frame * cap + slot] = kp;
+    }
+}
+
+}  // namespace
+
+/* ------------------------------------------------------------------------------------------------ launchers */
+int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_t* d_images, size_t step,
+                         size_t frameStride, int F, const ExtractBuffers& b, cudaStream_t s) {
+    int launches = 0;
+    for (int l = 0; l < g.nlevels; l++) {
+        const LevelGeom& L = g.lv[l];
+        dim3 grid((L.step / 4 + 127) / 128, L.h + 2 * VIORB_EDGE, F);
+        if (l == 0) pyr_level0_kernel<<<grid, 128, 0, s>>>(g, d_images, step, frameStride, b.pyr);
+        else pyr_resize_kernel<<<grid, 128, 0, s>>>(g, l, t, b.pyr);
+        launches++;
+    }
+    return launches;
+}
+
+int viorb_launch_fast(const FrameGeom& g, int F, const ExtractBuffers& b, cudaStream_t s) {
+    dim3 grid(g.cellsPerFrame, F);
+    fast_cells_kernel<<<grid, 128, 0, s>>>(g, b.pyr, b.cand, b.candCount, b.status);
+    return 1;
+}
+
+size_t viorb_octree_smem_bytes(int NC) {
+    int p2 = 1;
+    while (p2 < NC) p2 <<= 1;
+    return (size_t)NC * (2 * sizeof(short4) + 2 * sizeof(int) + 4 * sizeof(int) + 2 * sizeof(int) + 4 * sizeof(unsigned short)) +
+           (size_t)p2 * sizeof(unsigned);
+}
+
+int viorb_octree_prepare(int NC) {
+    return (int)cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)viorb_octree_smem_bytes(NC));
+}
+
+int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s) {
+    dim3 grid(g.nlevels, F);
+    octree_kernel<<<grid, OCT_THREADS, viorb_octree_smem_bytes(nodeCap), s>>>(g, b.cand, b.candCount, b.nodeOf, b.sel,
+                                                                               b.selCount, b.status, nodeCap);
+    return 1;
+}
+
+int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps, uint8_t* d_desc,
+                          int cap, int32_t* d_counts, cudaStream_t s) {
+    const int slots = g.selPerFrame < cap ? g.selPerFrame : cap;
+    dim3 grid((slots + DESC_WARPS - 1) / DESC_WARPS, F);
+    if (grid.x == 0) grid.x = 1;
+    orient_describe_kernel<<<grid, DESC_WARPS * 32, 0, s>>>(g, b.pyr, b.sel, b.selCount, d_kps, d_desc, cap, d_counts,
+                                                            b.status);
+    return 1;
+}

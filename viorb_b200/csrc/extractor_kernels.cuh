@@ -1,0 +1,91 @@
+/*
+ * extractor_kernels.cuh -- shared declarations of the sm_100a ORB extraction kernels.
+ *
+ * Device data layout (one "pass" = F frames processed together; F is sized so the pass working set
+ * stays resident in the 126 MB L2):
+ *
+ *   pyramid   [F][pyrFrameBytes]   per frame, all levels back to back.  A level is stored as
+ *                                  (h+38) rows of `step` bytes; the ROI (x=0) starts at byte 32 of a
+ *                                  row so that ROI rows are 16-byte aligned; the 19-pixel
+ *                                  REFLECT_101 border of the reference's mvImagePyramid occupies
+ *                                  bytes [13,32) and [32+w, 32+w+19) of the row.
+ *   cand      [F][candPerFrame]    FAST candidates, packed x:12 | y:12 | score:8 (window coordinates,
+ *                                  i.e. level coordinates minus 16), appended with atomics
+ *   candCount [F][nlevels]
+ *   nodeOf    [F][candPerFrame]    u16 quadtree node of each candidate (octree scratch)
+ *   sel       [F][selPerFrame]     selected keypoints per level in reference list order, packed
+ *                                  x:12 | y:12 | score:8 in LEVEL coordinates
+ *   selCount  [F][nlevels]
+ */
+#ifndef VIORB_EXTRACTOR_KERNELS_CUH
+#define VIORB_EXTRACTOR_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "viorb_gpu.h"
+
+#define VIORB_MAX_LEVELS 12
+#define VIORB_EDGE 19          /* EDGE_THRESHOLD, src/ORBextractor.cc:74 */
+#define VIORB_ROI_X0 32        /* byte offset of ROI x=0 inside a stored row */
+#define VIORB_FAST_BORDER 16   /* EDGE_THRESHOLD-3, src/ORBextractor.cc:773 */
+
+struct LevelGeom {
+    int w, h;             /* ROI size */
+    int step;             /* stored row stride in bytes (multiple of 16) */
+    int pyrOff;           /* byte offset of the stored level (row -19) inside a frame's pyramid block */
+    int nCols, nRows, wCell, hCell;   /* FAST cell grid, src/ORBextractor.cc:784-787 */
+    int cellBase;         /* first cell id of this level inside a frame */
+    int quota;            /* mnFeaturesPerLevel */
+    int candCap, candBase;
+    int selCap, selBase;
+    int nIni;             /* root nodes of the quadtree, src/ORBextractor.cc:543 */
+    int patchSize;        /* (int)(PATCH_SIZE * mvScaleFactor[level]) */
+    float scale;          /* mvScaleFactor[level] */
+    int xtab, ytab;       /* offsets into the resize tables */
+};
+
+struct FrameGeom {
+    int nlevels, rows, cols;
+    int iniTh, minTh;
+    int cellsPerFrame, candPerFrame, selPerFrame;
+    unsigned long long pyrFrameBytes;
+    LevelGeom lv[VIORB_MAX_LEVELS];
+};
+
+/* per-level bilinear tables (cv::resize fixed point, 11 fractional bits) */
+struct ResizeTables {
+    const uint16_t* xofs;    /* sx per dst x */
+    const int16_t* xa;       /* a0,a1 interleaved */
+    const uint16_t* yofs;
+    const int16_t* yb;       /* b0,b1 interleaved */
+};
+
+enum {
+    VIORB_DEV_CAND_OVERFLOW = 1,
+    VIORB_DEV_SEL_OVERFLOW = 2,
+    VIORB_DEV_NODE_OVERFLOW = 4,
+    VIORB_DEV_OUT_OVERFLOW = 8
+};
+
+struct ExtractBuffers {
+    uint8_t* pyr;
+    uint32_t* cand;
+    int* candCount;
+    uint16_t* nodeOf;
+    uint32_t* sel;
+    int* selCount;
+    int* status;          /* device status word (bit mask above) */
+};
+
+/* launchers (extractor_kernels.cu); every launcher returns the number of kernel launches issued */
+int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_t* d_images, size_t step,
+                         size_t frameStride, int F, const ExtractBuffers& b, cudaStream_t s);
+int viorb_launch_fast(const FrameGeom& g, int F, const ExtractBuffers& b, cudaStream_t s);
+int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s);
+int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps,
+                          uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s);
+size_t viorb_octree_smem_bytes(int nodeCap);
+int viorb_octree_prepare(int nodeCap);   /* opt-in dynamic shared memory; returns cudaError */
+
+#endif
