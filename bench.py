@@ -1,0 +1,398 @@
+#!/usr/bin/env python3
+"""bench.py -- ORB extraction throughput (BASELINE.json metric) on 1..8 B200s, plus the Hamming matcher.
+
+  python bench.py --gpus N --steps K --warmup W          (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                    the reference's CPU algorithm (oracle port) timed
+                                                          on the box's host cores, same config and metric
+
+A "step" is one pass of the hot path -- ORBextractor::operator() -- over one batch of synthetic frames:
+BASELINE.json configs[2], 4096 EuRoC-shape (752x480, 1000 features, 8 levels, 1.2, FAST 20/7) frames,
+sharded contiguously by frame across the ranks (no data-path collective).  `value` is frames/s with the
+frames resident in HBM; `e2e` is the same batch through the host-buffer C-ABI call (viorb_extract_batch:
+pinned host frames in, keypoints+descriptors out, copies inside the timed region).  The JSON line also
+carries `roofline` (dominant kernel, live CUDA-event timing), `cpu_baseline` (oracle port on the host
+cores, bounded sample) and `matcher` (config 5: brute-force Hamming top-2, map sharded across ranks with
+an NCCL all-gather of the per-shard top-2 records + merge kernel).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EUROC = dict(rows=480, cols=752, nfeatures=1000, scale=1.2, levels=8, ini=20, min=7)
+# compulsory bytes per EuRoC frame = W*H + sum_l (w_l+38)(h_l+38) + 60*N(=1006)
+BYTES_PER_FRAME_EUROC = 1765453
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=4096, help="frames in the whole job (all ranks)")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per device pass (0 = library default)")
+    ap.add_argument("--map", type=int, default=10_000_000, help="map descriptors in the whole job (matcher)")
+    ap.add_argument("--queries", type=int, default=1000)
+    ap.add_argument("--no-matcher", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=256, help="frames of the CPU-baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def load_oracle_native():
+    """oracle rebuilt with -march=native (the reference's own flags, CMakeLists.txt:10-11) for timing"""
+    from oracle import oracle_py
+    from viorb_b200 import build
+    try:
+        path = build.build_oracle(march="native", outdir="_build_native")
+        return oracle_py, oracle_py.lib(path)
+    except Exception:
+        return oracle_py, oracle_py.lib()
+
+
+def cpu_extract_fps(frames, nthreads):
+    """oracle port of ORBextractor::operator(), one frame per thread (the reference uses one thread per image)"""
+    O, L = load_oracle_native()
+    n = len(frames)
+    exs = [O.Extractor(EUROC["nfeatures"], EUROC["scale"], EUROC["levels"], EUROC["ini"], EUROC["min"], _lib=L)
+           for _ in range(nthreads)]
+    exs[0](frames[0])
+    stage = {}
+
+    def work(t):
+        for i in range(t, n, nthreads):
+            exs[t](frames[i])
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    dt = time.perf_counter() - t0
+    stage = exs[0].stage_seconds()
+    return n / dt, dt, stage
+
+
+def cpu_match_rate(q, dmap, nthreads):
+    O, L = load_oracle_native()
+    t0 = time.perf_counter()
+    O.hamming_top2(q, dmap, popcnt=False, nthreads=nthreads, _lib=L)     # the reference's bit-hack distance
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.hamming_top2(q, dmap, popcnt=True, nthreads=nthreads, _lib=L)
+    dt2 = time.perf_counter() - t0
+    return len(q) * len(dmap) / dt, len(q) * len(dmap) / dt2
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the reference itself cannot be built here:
+    no OpenCV C++ headers) on all host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from viorb_b200 import synth
+    cores = os.cpu_count() or 1
+    nsample = max(cores, min(args.cpu_frames, args.frames))
+    frames = synth.frames(nsample, EUROC["rows"], EUROC["cols"], seed0=0)
+    fps_all = []
+    for _ in range(args.warmup):
+        cpu_extract_fps(frames[:cores], cores)
+    t_ms = []
+    for _ in range(args.steps):
+        fps, dt, _ = cpu_extract_fps(frames, cores)
+        fps_all.append(fps)
+        t_ms.append(dt * 1e3)
+    fps = float(np.mean(fps_all))
+    sample = "%d of %d frames per step (seeds 0..%d), one frame per thread" % (nsample, args.frames, nsample - 1)
+    line = {
+        "impl": "reference", "metric": "orb_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(t_ms)), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, 0),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, chunk):
+    return {"workload": "configs[2]: %d synthetic 752x480 frames, ORBextractor 1000/1.2/8/20/7, sharded by frame"
+                        % args.frames,
+            "frames": args.frames, "shape": [EUROC["rows"], EUROC["cols"]], "nfeatures": EUROC["nfeatures"],
+            "frames_per_pass": chunk, "l2": "inputs (%.2f GB per job) larger than the 126 MB L2; no flush needed"
+                                            % (args.frames * EUROC["rows"] * EUROC["cols"] / 1e9),
+            "parallelism": "frame-sharded x%d" % args.gpus}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = "/tmp/viorb_clocks_%d.csv" % os.getpid()
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.proc.wait()
+        sm, mx, reasons = [], [], set()
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v == "Active":
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # samples under load = upper half
+        return {"sm_mhz": float(np.median(sorted(sm)[len(sm) // 2:])), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from viorb_b200 import api, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    api.lib()
+    stream = torch.cuda.current_stream()
+    ctx = api.Context(local, stream.cuda_stream)
+    ex = api.ORBextractor(EUROC["nfeatures"], EUROC["scale"], EUROC["levels"], EUROC["ini"], EUROC["min"], ctx=ctx)
+    if args.chunk:
+        ex.configure(chunk_frames=args.chunk)
+    rows, cols, cap = EUROC["rows"], EUROC["cols"], ex.cap
+
+    # ---- synthetic frames of this rank's shard (seeds are global frame indices) ----
+    f0 = args.frames * rank // world
+    f1 = args.frames * (rank + 1) // world
+    nloc = f1 - f0
+    h_imgs = api.pinned_empty((nloc, rows, cols), np.uint8)
+    synth.frames(nloc, rows, cols, seed0=f0, out=h_imgs)
+    h_kps = api.pinned_empty((nloc, cap), api.KEYPOINT)
+    h_desc = api.pinned_empty((nloc, cap, 32), np.uint8)
+    h_cnt = api.pinned_empty((nloc,), np.int32)
+    d_imgs = torch.empty((nloc, rows, cols), dtype=torch.uint8, device=dev)
+    d_imgs.copy_(torch.from_numpy(h_imgs))
+    d_kps = torch.empty((nloc, cap, 7), dtype=torch.float32, device=dev)
+    d_desc = torch.empty((nloc, cap, 32), dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros((nloc,), dtype=torch.int32, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_device():
+        ex.extract_batch_device(d_imgs, nloc, rows, cols, d_kps, d_desc, d_cnt)
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    ex.check()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = ctx.launch_count()
+    ex.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ex.profile(False)
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launch_count() - l0
+    stage_ms, passes = ex.stage_ms()
+    ex.check()
+    clk = clocks.stop()
+    value = args.frames * args.steps / (dev_ms * 1e-3)
+    total_kp = int(d_cnt.sum().item())
+
+    # ---- end to end through the host-buffer C ABI (e2e) ----
+    for _ in range(2):
+        ex.extract_batch(h_imgs, h_kps, h_desc, h_cnt)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        ex.extract_batch(h_imgs, h_kps, h_desc, h_cnt)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+    e2e = args.frames * args.steps / (e2e_ms * 1e-3)
+    assert int(h_cnt.sum()) == total_kp, "host and device paths disagree"
+    h2d = nloc * rows * cols
+    d2h = nloc * cap * 60 + nloc * 4
+
+    # ---- roofline of the dominant kernel (live CUDA-event stage timing inside the timed region) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom = max(stage_ms, key=stage_ms.get)
+    kernel_names = {"pyramid": "pyr_level0_kernel+pyr_resize_kernel x7", "fast": "fast_cells_kernel",
+                    "octree": "octree_kernel", "describe": "orient_describe_kernel"}
+    frames_timed = nloc * args.steps
+    # per-kernel algorithmic bytes per frame (DESIGN.md "Kernels"): pyramid = read input + write padded pyramid;
+    # fast = read every level ROI once + 4 B per candidate; octree = 6 B per candidate + 4 B per selected;
+    # describe = 43x43 patch + 60 B per keypoint
+    P, Ppad, ncand, nkp = 1117367, 1344493, 6085, 1006
+    alg = {"pyramid": rows * cols + Ppad, "fast": P + 4 * ncand, "octree": 6 * ncand + 4 * nkp,
+           "describe": nkp * (43 * 43 + 60)}
+    dom_ms_per_launch = stage_ms[dom] / max(passes, 1)
+    frames_per_pass = frames_timed / max(passes, 1)
+    achieved = alg[dom] * frames_per_pass / (dom_ms_per_launch * 1e-3) / 1e9
+    step_achieved = BYTES_PER_FRAME_EUROC * value / world / 1e9
+    roofline = {"bound": "hbm", "kernel": kernel_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": alg[dom] * frames_per_pass, "avg_launch_ms": dom_ms_per_launch,
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+                "step": {"achieved": step_achieved, "frac": step_achieved / peak,
+                         "bytes_per_frame": BYTES_PER_FRAME_EUROC,
+                         "note": "whole hot path per GPU by SURVEY 8(d) compulsory bytes; latency/INT-bound by design"}}
+
+    # ---- matcher: config 5, map sharded by rows across ranks, NCCL all-gather of top-2 + merge kernel ----
+    matcher = None
+    if not args.no_matcher:
+        M, Q = args.map, args.queries
+        m0, m1 = M * rank // world, M * (rank + 1) // world
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + rank)
+        d_map = torch.randint(0, 256, ((m1 - m0), 32), dtype=torch.uint8, device=dev, generator=g)
+        gq = torch.Generator(device=dev)
+        gq.manual_seed(7)
+        d_q = torch.randint(0, 256, (Q, 32), dtype=torch.uint8, device=dev, generator=gq)   # same on every rank
+        if world > 1:
+            dist.broadcast(d_q, 0)
+        mt = api.ORBmatcher(ctx=ctx)
+        d_part = torch.zeros((Q, 4), dtype=torch.int32, device=dev)
+        d_all = torch.zeros((world, Q, 4), dtype=torch.int32, device=dev)
+        d_out = torch.zeros((Q, 4), dtype=torch.int32, device=dev)
+
+        def match_step():
+            mt.hamming_top2_device(d_q, Q, d_map, m1 - m0, m0, d_part)
+            if world > 1:
+                dist.all_gather_into_tensor(d_all, d_part)
+                mt.top2_merge_device(d_all, world, Q, d_out)
+
+        for _ in range(3):
+            match_step()
+        barrier()
+        msteps = max(args.steps, 3)
+        e0.record()
+        for _ in range(msteps):
+            match_step()
+        e1.record()
+        barrier()
+        m_ms = max_over_ranks(e0.elapsed_time(e1)) / msteps
+        pairs = Q * M / (m_ms * 1e-3)
+        popc_peak = 148 * 16 * (clk.get("sm_max_mhz") or 1965.0) * 1e6
+        matcher = {"workload": "configs[4]: %d queries x %d map descriptors, map sharded x%d" % (Q, M, world),
+                   "value": pairs, "unit": "descriptor pairs/s", "ms_per_pass": m_ms,
+                   "queries_per_s": Q / (m_ms * 1e-3),
+                   "hbm": {"achieved": (32 * M + 48 * Q) / world / (m_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": (32 * M + 48 * Q) / world / (m_ms * 1e-3) / 1e9 / peak},
+                   "popc": {"achieved": 8 * pairs / world, "peak": popc_peak, "unit": "popc32/s",
+                            "frac": 8 * pairs / world / popc_peak,
+                            "note": "peak = 148 SMs x 16 POPC/clk x max SM clock (INT-pipe bound at Q=1000)"}}
+        del d_map
+
+    # ---- CPU baseline (rank 0, N == 1): oracle port on the host cores, bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        ns = min(args.cpu_frames, nloc)
+        fps, dt, st = cpu_extract_fps(h_imgs[:ns], cores)
+        fps1, dt1, st1 = cpu_extract_fps(h_imgs[:max(8, ns // 16)], 1)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "%d of the %d frames (seeds 0..%d), one frame per thread, %.1f s wall" % (ns, args.frames, ns - 1, dt),
+               "single_thread_frames_per_s": fps1,
+               "stage_ms_single_thread": {k: v * 1e3 for k, v in st1.items()}}
+        if matcher is not None:
+            qs = synth.descriptor_map(64, seed=3)
+            ms_ = synth.descriptor_map(1_000_000, seed=4)
+            hack, pop = cpu_match_rate(qs, ms_, cores)
+            matcher["cpu_baseline"] = {"value": hack, "unit": "descriptor pairs/s", "cores": cores, "kind": "port",
+                                       "sample": "64 queries x 1M map descriptors (bit-hack distance of ORBmatcher.cc:1648)",
+                                       "popcnt_variant": pop}
+
+    if rank == 0:
+        line = {
+            "metric": "orb_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, passes and int(round(frames_per_pass))),
+            "clocks": clk,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "keypoints_per_frame": total_kp / nloc,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "matcher": matcher,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

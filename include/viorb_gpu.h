@@ -69,6 +69,11 @@ int viorb_extractor_destroy(viorb_extractor* ex);
  * candidate pool per level as a fraction 1/div of the level's pixel count. */
 int viorb_extractor_configure(viorb_extractor* ex, int chunk_frames, int cand_div);
 
+/* per-stage device timing (CUDA events on the context stream around each stage of every pass):
+ * ms[0..3] = pyramid, FAST, quadtree, orient+describe, summed over `passes` passes since the last query. */
+int viorb_extractor_profile(viorb_extractor* ex, int enable);
+int viorb_extractor_stage_ms(viorb_extractor* ex, float ms[4], int* passes);
+
 /* GetLevels/GetScaleFactors/GetInverseScaleFactors/GetScaleSigmaSquares/GetInverseScaleSigmaSquares
  * (include/ORBextractor.h:63-83) + mnFeaturesPerLevel; any pointer may be NULL. */
 int viorb_extractor_tables(const viorb_extractor* ex, int* nlevels, float* scale, float* inv_scale,

@@ -49,6 +49,8 @@ def lib():
         "viorb_extractor_destroy": [vp],
         "viorb_extractor_configure": [vp, i32, i32],
         "viorb_extractor_tables": [vp, pi, vp, vp, vp, vp, vp],
+        "viorb_extractor_profile": [vp, i32],
+        "viorb_extractor_stage_ms": [vp, vp, pi],
         "viorb_extract": [vp, vp, i32, i32, sz, vp, vp, i32, pi],
         "viorb_extract_batch": [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp],
         "viorb_extract_batch_device": [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp],
@@ -238,6 +240,16 @@ class ORBextractor:
 
     def check(self):
         _ck(lib().viorb_extractor_check(self.h))
+
+    def profile(self, enable=True):
+        _ck(lib().viorb_extractor_profile(self.h, int(enable)))
+
+    def stage_ms(self):
+        """{stage: ms summed over the passes since the last query}, passes"""
+        ms = np.zeros(4, np.float32)
+        n = C.c_int()
+        _ck(lib().viorb_extractor_stage_ms(self.h, _ptr(ms), C.byref(n)))
+        return dict(zip(("pyramid", "fast", "octree", "describe"), [float(v) for v in ms])), n.value
 
     # mvImagePyramid, ORBextractor.h:85
     def pyramid(self, level, frame=0):

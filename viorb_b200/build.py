@@ -65,7 +65,7 @@ def build_synth(force=False):
     target = os.path.join(LIBDIR, "libviorb_synth.so")
     src = os.path.join(CSRC, "synth.cpp")
     if force or _stale(target, [src]):
-        cmd = [CXX, "-O2", "-fPIC", "-shared", "-std=c++14", "-o", target, src]
+        cmd = [CXX, "-O3", "-fPIC", "-shared", "-std=c++14", "-pthread", "-o", target, src]
         print("[viorb build]", " ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)
     return target

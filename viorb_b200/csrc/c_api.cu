@@ -76,7 +76,7 @@ struct viorb_extractor {
     double scaleFactor = 1.2;
     std::vector<float> scale, invScale, sigma2, invSigma2;
     std::vector<int> quota;
-    int chunk = 64, candDiv = 32;
+    int chunk = 64, candDiv = 16;
     /* geometry for the current image size */
     int rows = 0, cols = 0;
     FrameGeom geom;
@@ -98,6 +98,9 @@ struct viorb_extractor {
     DevBuf<int32_t> ocnt[2];
     cudaEvent_t evIn[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
     int residentFirst = 0, residentCount = 0;
+    int lastOverflow = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> profEvents;      /* 5 per pass: start, pyramid, fast, octree, describe */
 };
 
 namespace {
@@ -165,7 +168,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
         L.nIni = (int)roundf((float)W / (float)H);          /* :543 */
         if (L.nIni < 1) return fail(VIORB_ERR_UNSUPPORTED, "portrait aspect ratio %dx%d gives zero quadtree roots", L.w, L.h);
         long cc = (long)L.w * L.h / e->candDiv;
-        L.candCap = (int)std::min<long>(std::max<long>(cc, 1024), 65535);
+        L.candCap = (int)std::min<long>(std::max<long>(cc, 1024), (1 << 20) - 1);
         L.candBase = candBase;
         candBase += L.candCap;
         L.selCap = std::max(L.quota + 4, 4 * L.nIni + 4);
@@ -180,7 +183,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     if (pyrOff >= (1ull << 31)) return fail(VIORB_ERR_UNSUPPORTED, "pyramid larger than 2 GiB per frame");
     g.pyrFrameBytes = pyrOff;
     g.cellsPerFrame = cellBase; g.candPerFrame = candBase; g.selPerFrame = selBase;
-    if (viorb_octree_smem_bytes(nodeCap) > 200 * 1024)
+    if (nodeCap > 4096 || viorb_octree_smem_bytes(nodeCap) > 200 * 1024)
         return fail(VIORB_ERR_UNSUPPORTED, "per-level feature quota %d too large for the quadtree kernel", nodeCap);
     e->nodeCap = nodeCap;
     /* cv::resize INTER_LINEAR coefficient tables (OpenCV resize.cpp), level l from level l-1 */
@@ -255,10 +258,18 @@ int run_pass(viorb_extractor* e, const uint8_t* d_images, size_t step, size_t fr
     viorb_ctx* c = e->ctx;
     const FrameGeom& g = e->geom;
     CU(cudaMemsetAsync(e->buf.candCount, 0, (size_t)F * g.nlevels * sizeof(int), c->stream));
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (e->profiling)
+        for (int i = 0; i < 5; i++) { CU(cudaEventCreate(&ev[i])); e->profEvents.push_back(ev[i]); }
+    if (e->profiling) CU(cudaEventRecord(ev[0], c->stream));
     c->launches += viorb_launch_pyramid(g, e->tables, d_images, step, frameStride, F, e->buf, c->stream);
+    if (e->profiling) CU(cudaEventRecord(ev[1], c->stream));
     c->launches += viorb_launch_fast(g, F, e->buf, c->stream);
+    if (e->profiling) CU(cudaEventRecord(ev[2], c->stream));
     c->launches += viorb_launch_octree(g, F, e->buf, e->nodeCap, c->stream);
+    if (e->profiling) CU(cudaEventRecord(ev[3], c->stream));
     c->launches += viorb_launch_describe(g, F, e->buf, d_kps, d_desc, cap, d_counts, c->stream);
+    if (e->profiling) CU(cudaEventRecord(ev[4], c->stream));
     CU(cudaGetLastError());
     return VIORB_OK;
 }
@@ -267,6 +278,7 @@ int check_status(viorb_extractor* e) {
     int st = 0;
     CU(cudaMemcpyAsync(&st, e->buf.status, sizeof(int), cudaMemcpyDeviceToHost, e->ctx->stream));
     CU(cudaStreamSynchronize(e->ctx->stream));
+    e->lastOverflow = st;
     if (st) {
         cudaMemsetAsync(e->buf.status, 0, sizeof(int), e->ctx->stream);
         if (st & VIORB_DEV_CAND_OVERFLOW)
@@ -404,6 +416,31 @@ int viorb_extractor_configure(viorb_extractor* e, int chunk_frames, int cand_div
     return VIORB_OK;
 }
 
+int viorb_extractor_profile(viorb_extractor* e, int enable) {
+    if (!e) return fail(VIORB_ERR_INVALID, "extractor is NULL");
+    e->profiling = enable != 0;
+    return VIORB_OK;
+}
+
+int viorb_extractor_stage_ms(viorb_extractor* e, float ms[4], int* passes) {
+    if (!e || !ms) return fail(VIORB_ERR_INVALID, "NULL argument");
+    int rc;
+    if ((rc = ctx_bind(e->ctx))) return rc;
+    CU(cudaStreamSynchronize(e->ctx->stream));
+    for (int i = 0; i < 4; i++) ms[i] = 0.f;
+    const int np = (int)e->profEvents.size() / 5;
+    for (int p = 0; p < np; p++)
+        for (int i = 0; i < 4; i++) {
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, e->profEvents[5 * p + i], e->profEvents[5 * p + i + 1]));
+            ms[i] += t;
+        }
+    for (cudaEvent_t ev : e->profEvents) cudaEventDestroy(ev);
+    e->profEvents.clear();
+    if (passes) *passes = np;
+    return VIORB_OK;
+}
+
 int viorb_extractor_tables(const viorb_extractor* e, int* nlevels, float* scale, float* inv_scale, float* sigma2,
                            float* inv_sigma2, int* fpl) {
     if (!e) return fail(VIORB_ERR_INVALID, "extractor is NULL");
@@ -445,8 +482,26 @@ int viorb_extractor_check(viorb_extractor* e) {
     return check_status(e);
 }
 
+static int extract_batch_once(viorb_extractor* e, const uint8_t* images, int B, int rows, int cols, size_t step,
+                              size_t frame_stride, viorb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts);
+
 int viorb_extract_batch(viorb_extractor* e, const uint8_t* images, int B, int rows, int cols, size_t step,
                         size_t frame_stride, viorb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts) {
+    if (!e) return fail(VIORB_ERR_INVALID, "NULL argument");
+    for (;;) {
+        const int rc = extract_batch_once(e, images, B, rows, cols, step, frame_stride, kps, desc, cap, counts);
+        /* a corner-dense frame overflowed the candidate pool: grow it and run the batch again */
+        if (rc == VIORB_ERR_CAPACITY && e->lastOverflow == VIORB_DEV_CAND_OVERFLOW && e->candDiv > 4) {
+            e->candDiv /= 2;
+            e->rows = e->cols = 0;
+            continue;
+        }
+        return rc;
+    }
+}
+
+static int extract_batch_once(viorb_extractor* e, const uint8_t* images, int B, int rows, int cols, size_t step,
+                              size_t frame_stride, viorb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts) {
     if (!e || !kps || !desc || !counts) return fail(VIORB_ERR_INVALID, "NULL argument");
     if (B <= 0 || !images || rows <= 0 || cols <= 0) {           /* empty input: silent return (:1046-1047) */
         for (int b = 0; b < B; b++) counts[b] = 0;

@@ -424,12 +424,12 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const __grid_consta
             for (int i = tid; i < P2; i += nt) S.srt[i] = 0xffffffffu;
             __syncthreads();
             for (int i = tid; i < Sn; i += nt)
-                if (cnt[i] > 1) S.srt[S.aux[i]] = ((unsigned)(65535 - min(cnt[i], 65535)) << 16) | (unsigned)i;
+                if (cnt[i] > 1) S.srt[S.aux[i]] = ((unsigned)(0xfffff - cnt[i]) << 12) | (unsigned)i;   /* cnt < 2^20, i < 4096 */
             __syncthreads();
             block_bitonic_sort(S.srt, P2);
             /* gains in sorted order */
             for (int r = tid; r < nM; r += nt) {
-                const int i = S.srt[r] & 0xffff;
+                const int i = S.srt[r] & 0xfff;
                 const int ne = (S.cc[4 * i] > 0) + (S.cc[4 * i + 1] > 0) + (S.cc[4 * i + 2] > 0) + (S.cc[4 * i + 3] > 0);
                 S.aux[r] = ne - 1;
             }
@@ -438,14 +438,14 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const __grid_consta
             __syncthreads();
             block_exscan(S.aux, nM, warpTmp);       /* aux[r] = gain before r */
             for (int r = tid; r < nM; r += nt) {
-                const int i = S.srt[r] & 0xffff;
+                const int i = S.srt[r] & 0xfff;
                 const int ne = (S.cc[4 * i] > 0) + (S.cc[4 * i + 1] > 0) + (S.cc[4 * i + 2] > 0) + (S.cc[4 * i + 3] > 0);
                 const int before = prev + S.aux[r], after = before + ne - 1;
                 if (before < N && after >= N) sh[0] = r + 1;      /* first rank reaching N: expand r, then break */
             }
             __syncthreads();
             E = sh[0];
-            for (int r = tid; r < E; r += nt) S.erank[S.srt[r] & 0xffff] = r;
+            for (int r = tid; r < E; r += nt) S.erank[S.srt[r] & 0xfff] = r;
             __syncthreads();
         }
         /* creation ranks of the children: expansion order, then n1..n4 */

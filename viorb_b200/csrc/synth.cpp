@@ -8,6 +8,7 @@
  */
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -89,6 +90,17 @@ void viorb_synth_frame(int h, int w, uint64_t seed, uint8_t* out) {
     draw_shapes(img, h, w, rng);
     binomial5(img, h, w);
     add_noise(img, out, h, w, rng, 3);
+}
+
+/* n frames (seeds seed0 .. seed0+n-1), packed [n][h][w], generated on nthreads host threads */
+void viorb_synth_frames(int n, int h, int w, uint64_t seed0, uint8_t* out, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+        th.emplace_back([=] {
+            for (int i = t; i < n; i += nthreads) viorb_synth_frame(h, w, seed0 + i, out + (size_t)i * h * w);
+        });
+    for (auto& t : th) t.join();
 }
 
 /* rectified stereo pair: right(x) = left(x + d(band)), d piece-wise constant over nbands horizontal

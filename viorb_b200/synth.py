@@ -12,13 +12,13 @@ _lib = None
 def _load():
     global _lib
     if _lib is None:
-        path = os.path.join(_build.LIBDIR, "libviorb_synth.so")
-        if not os.path.exists(path):
-            path = _build.build_synth()
+        path = _build.build_synth()          # rebuilt only when synth.cpp is newer than the .so
         _lib = ctypes.CDLL(path)
         _lib.viorb_synth_frame.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p]
         _lib.viorb_synth_stereo.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _lib.viorb_synth_frames.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p,
+                                            ctypes.c_int]
         _lib.viorb_synth_bytes.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t]
     return _lib
 
@@ -31,11 +31,11 @@ def frame(h, w, seed, out=None):
     return out
 
 
-def frames(n, h, w, seed0=0, out=None):
+def frames(n, h, w, seed0=0, out=None, nthreads=None):
     if out is None:
         out = np.empty((n, h, w), np.uint8)
-    for i in range(n):
-        frame(h, w, seed0 + i, out[i])
+    assert out.flags["C_CONTIGUOUS"] and out.shape == (n, h, w)
+    _load().viorb_synth_frames(n, h, w, int(seed0), out.ctypes.data, nthreads or os.cpu_count() or 1)
     return out
 
 
