@@ -188,7 +188,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from viorb_b200 import api, synth
+    from viorb_b200 import api, sharding, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -201,7 +201,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     api.lib()
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the library launches on it and torch.cuda.Event times it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = api.Context(local, stream.cuda_stream)
     ex = api.ORBextractor(EUROC["nfeatures"], EUROC["scale"], EUROC["levels"], EUROC["ini"], EUROC["min"], ctx=ctx)
     if args.chunk:
@@ -209,8 +212,7 @@ def main():
     rows, cols, cap = EUROC["rows"], EUROC["cols"], ex.cap
 
     # ---- synthetic frames of this rank's shard (seeds are global frame indices) ----
-    f0 = args.frames * rank // world
-    f1 = args.frames * (rank + 1) // world
+    f0, f1 = sharding.shard_range(args.frames, rank, world)
     nloc = f1 - f0
     h_imgs = api.pinned_empty((nloc, rows, cols), np.uint8)
     synth.frames(nloc, rows, cols, seed0=f0, out=h_imgs)
@@ -240,12 +242,12 @@ def main():
         ex.extract_batch_device(d_imgs, nloc, rows, cols, d_kps, d_desc, d_cnt)
 
     # ---- device-resident throughput (value) ----
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     ex.check()
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
     l0 = ctx.launch_count()
     ex.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -313,7 +315,7 @@ def main():
     matcher = None
     if not args.no_matcher:
         M, Q = args.map, args.queries
-        m0, m1 = M * rank // world, M * (rank + 1) // world
+        m0, m1 = sharding.shard_range(M, rank, world)
         g = torch.Generator(device=dev)
         g.manual_seed(1234 + rank)
         d_map = torch.randint(0, 256, ((m1 - m0), 32), dtype=torch.uint8, device=dev, generator=g)

@@ -1,0 +1,66 @@
+"""Synthetic matcher scenarios shared by the CPU and GPU tests (inputs only, no expected values)."""
+import numpy as np
+
+from viorb_b200 import synth
+
+KITTI_FX, KITTI_BF = 718.856, 386.1448          # Examples/Stereo/KITTI00-02.yaml
+
+
+def flip_bits(desc, rng, max_flips):
+    out = desc.copy()
+    for i in range(len(out)):
+        for b in rng.integers(0, 256, size=int(rng.integers(0, max_flips + 1))):
+            out[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    return out
+
+
+def projection_scenario(kps, desc, scale_factors, seed, n_mp=600, conflicts=60):
+    """A current frame (kps/desc) and a set of map points projecting near its keypoints.
+    Returns dict of arrays for SearchByProjection (local) and (frame) variants."""
+    rng = np.random.default_rng(seed)
+    n = len(kps)
+    pick = rng.integers(0, n, n_mp)
+    pick[:conflicts] = pick[conflicts:2 * conflicts]          # several map points compete for the same keypoint
+    order = rng.permutation(n_mp)
+    pick = pick[order]
+    px = kps["x"][pick] + rng.normal(0, 2.0, n_mp).astype(np.float32)
+    py = kps["y"][pick] + rng.normal(0, 2.0, n_mp).astype(np.float32)
+    mp_desc = flip_bits(desc[pick], rng, 60)
+    dup = rng.integers(0, n_mp, 40)
+    mp_desc[dup] = desc[pick[dup]]                            # exact copies -> distance ties between competitors
+    octave = kps["octave"][pick]
+    pred = np.clip(octave + rng.integers(-1, 2, n_mp), 0, len(scale_factors) - 1).astype(np.int32)
+    u_right = np.where(rng.random(n) < 0.5, kps["x"] - rng.uniform(2, 60, n), -1).astype(np.float32)
+    proj_xr = (px - (kps["x"][pick] - u_right[pick]) + rng.normal(0, 3.0, n_mp)).astype(np.float32)
+    obs0 = (rng.random(n) < 0.1).astype(np.int32) * 2
+    return dict(
+        proj_x=px.astype(np.float32), proj_y=py.astype(np.float32), proj_xr=proj_xr,
+        pred_level=pred, view_cos=rng.uniform(0.99, 1.0, n_mp).astype(np.float32),
+        valid=(rng.random(n_mp) < 0.9).astype(np.uint8), nobs=rng.integers(0, 4, n_mp).astype(np.int32),
+        mp_desc=mp_desc, u_right=u_right, obs0=obs0,
+        invz=rng.uniform(0.02, 0.5, n_mp).astype(np.float32), last_octave=octave.astype(np.int32),
+        last_angle=(kps["angle"][pick] + rng.choice([0.0, 0.0, 0.0, 90.0, 200.0], n_mp) +
+                    rng.normal(0, 3, n_mp)).astype(np.float32) % np.float32(360.0))
+
+
+def feature_vector(kps, nodes_of):
+    """DBoW2::FeatureVector stand-in: {node id: [keypoint indices]} flattened to (node_ids, node_ptr, idx)."""
+    node = nodes_of(kps)
+    ids = np.unique(node)
+    ptr, idx = [0], []
+    for i in ids:
+        members = np.nonzero(node == i)[0]
+        idx.extend(members.tolist())
+        ptr.append(len(idx))
+    return ids.astype(np.int32), np.array(ptr, np.int32), np.array(idx, np.int32)
+
+
+def row_band_nodes(band=24, drop_every=7):
+    def f(kps):
+        node = (kps["y"] // band).astype(np.int32) * 3 + 5
+        node[node % drop_every == 0] += 100000          # some nodes exist in one key frame only
+        return node
+    return f
+
+
+RECTIFIED_F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32)   # l = x1' F12 = [0, 1, -y1]

@@ -1,0 +1,118 @@
+"""CPU tests of the matcher oracle (pins it against plain numpy) and of the multi-rank host logic."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import scenarios as S
+from util import CONFIGS, ROOT
+from viorb_b200 import sharding, synth
+
+
+def np_dist(q, m):
+    return np.unpackbits(q[:, None, :] ^ m[None, :, :], axis=2).sum(2).astype(np.int32)
+
+
+def test_descriptor_distance(oracle):
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (200, 32)).astype(np.uint8)
+    b = rng.integers(0, 256, (200, 32)).astype(np.uint8)
+    d = np_dist(a, b)
+    for i in range(200):
+        assert oracle.descriptor_distance(a[i], b[i]) == d[i, i] == oracle.descriptor_distance(a[i], b[i], popcnt=True)
+    assert oracle.descriptor_distance(a[0], a[0]) == 0 and oracle.descriptor_distance(a[0], ~a[0]) == 256
+
+
+def test_top2_vs_numpy(oracle):
+    dmap = synth.descriptor_map(3000, seed=1)
+    dmap[100] = dmap[7]            # exact duplicates -> ties
+    q = synth.queries_from_map(dmap, 50, seed=2)
+    q[0] = dmap[7]
+    got = oracle.hamming_top2(q, dmap, nthreads=2)
+    d = np_dist(q, dmap)
+    order = np.argsort(d, axis=1, kind="stable")
+    assert (got["i1"] == order[:, 0]).all() and (got["i2"] == order[:, 1]).all()
+    assert (got["d1"] == d[np.arange(50), order[:, 0]]).all() and (got["d2"] == d[np.arange(50), order[:, 1]]).all()
+    assert got["i1"][0] == 7 and got["i2"][0] == 100 and got["d2"][0] == 0
+    assert (got == oracle.hamming_top2(q, dmap, popcnt=False)).all()
+    empty = oracle.hamming_top2(q, dmap[:0])
+    assert (empty["i1"] == -1).all() and (empty["d1"] == 256).all()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_sharded_merge_equals_full_scan(oracle, world):
+    dmap = synth.descriptor_map(5000, seed=3)
+    dmap[::7] = dmap[0]
+    q = synth.queries_from_map(dmap, 40, seed=4)
+    full = oracle.hamming_top2(q, dmap)
+    parts = np.stack([oracle.hamming_top2(q, dmap[b:e], index_base=b) for b, e in sharding.all_shards(len(dmap), world)])
+    assert (oracle.top2_merge(parts) == full).all()
+
+
+def test_shard_ranges():
+    for n in (0, 1, 7, 4096, 10_000_000):
+        for w in (1, 2, 4, 8):
+            r = sharding.all_shards(n, w)
+            assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+
+
+def test_grid_vs_naive(oracle):
+    h, w = 376, 1241
+    e = oracle.Extractor(500, 1.2, 8, 20, 7)
+    k, d = e(synth.frame(h, w, 3))
+    g = oracle.Grid(k, 0.0, float(w), 0.0, float(h))
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        x, y, r = float(rng.uniform(0, w)), float(rng.uniform(0, h)), float(rng.choice([5.0, 20.0, 50.0]))
+        lo, hi = [(-1, -1), (0, 2), (3, -1)][int(rng.integers(0, 3))]
+        got = set(g.features_in_area(x, y, r, lo, hi).tolist())
+        ok = (np.abs(k["x"] - np.float32(x)) < r) & (np.abs(k["y"] - np.float32(y)) < r)
+        if lo > 0 or hi >= 0:
+            ok &= k["octave"] >= lo
+            if hi >= 0:
+                ok &= k["octave"] <= hi
+        # the grid only visits cells overlapping the window, which always covers the naive set
+        assert got == set(np.nonzero(ok)[0].tolist())
+
+
+def test_stereo_recovers_synthetic_disparity(oracle):
+    h, w, nf, sf, nl, it, mt = CONFIGS["kitti"]
+    left, right, disp = synth.stereo_pair(h, w, 7)
+    ol, orr = oracle.Extractor(nf, sf, nl, it, mt), oracle.Extractor(nf, sf, nl, it, mt)
+    kl, dl = ol(left)
+    kr, dr = orr(right)
+    mbf, mb = S.KITTI_BF, S.KITTI_BF / S.KITTI_FX
+    ur, depth, bd, bi, n = oracle.stereo_match(kl, dl, kr, dr, [ol.pyramid(l) for l in range(nl)],
+                                               [orr.pyramid(l) for l in range(nl)], ol.scale_factors(), mbf, mb)
+    ok = ur >= 0
+    assert n == ok.sum() and n > 300
+    band = (kl["y"][ok] * len(disp) / h).astype(int)
+    err = np.abs((kl["x"][ok] - ur[ok]) - disp[band])
+    assert np.median(err) < 1.0
+    assert np.allclose(depth[ok], mbf / (kl["x"][ok] - ur[ok]), rtol=1e-5)
+
+
+def test_projection_scenario_is_meaningful(oracle):
+    h, w, nf, sf, nl, it, mt = CONFIGS["kitti"]
+    e = oracle.Extractor(nf, sf, nl, it, mt)
+    k, d = e(synth.frame(h, w, 9))
+    sc = S.projection_scenario(k, d, e.scale_factors(), seed=11)
+    g = oracle.Grid(k, 0.0, float(w), 0.0, float(h))
+    n, match, obs = oracle.search_by_projection_local(g, d, sc["u_right"], sc["obs0"], e.scale_factors(), sc["proj_x"],
+                                                      sc["proj_y"], sc["proj_xr"], sc["pred_level"], sc["view_cos"],
+                                                      sc["valid"], sc["nobs"], sc["mp_desc"], 3.0, 0.8)
+    assert n > 50 and (match >= 0).sum() <= n
+    assert ((obs > 0) >= (sc["obs0"] > 0)).all()
+
+
+def test_two_rank_gloo_top2_merge():
+    """world_size-2 gloo run of the sharded matcher host logic (CPU stand-in shard scan = the oracle)"""
+    script = os.path.join(ROOT, "tests", "gloo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "RANK0 OK" in p.stdout and "RANK1 OK" in p.stdout

@@ -1,0 +1,173 @@
+"""GPU parity tests: stereo matcher, frame grid and the windowed Hamming searches vs the CPU oracle.
+Everything is compared bit-for-bit (float outputs as raw bits, indices and counts exactly)."""
+import numpy as np
+import pytest
+
+import scenarios as S
+from util import CONFIGS
+from viorb_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from viorb_b200 import api
+    api.lib()
+    return api
+
+
+@pytest.fixture(scope="module")
+def ctx(api):
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def stereo(api, ctx, oracle):
+    """KITTI-shape synthetic pair (BASELINE config 2) extracted by both implementations"""
+    h, w, nf, sf, nl, it, mt = CONFIGS["kitti"]
+    left, right, disp = synth.stereo_pair(h, w, 7)
+    exl, exr = api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx), api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx)
+    kl, dl = exl(left)
+    kr, dr = exr(right)
+    ol, orr = oracle.Extractor(nf, sf, nl, it, mt), oracle.Extractor(nf, sf, nl, it, mt)
+    kl2, dl2 = ol(left)
+    kr2, dr2 = orr(right)
+    assert (kl == kl2).all() and (dl == dl2).all() and (kr == kr2).all() and (dr == dr2).all()
+    yield dict(exl=exl, exr=exr, kl=kl, dl=dl, kr=kr, dr=dr, ol=ol, orr=orr, disp=disp, shape=(h, w), nl=nl)
+    exl.close()
+    exr.close()
+
+
+def test_compute_stereo_matches(api, oracle, stereo):
+    s = stereo
+    mbf, mb = S.KITTI_BF, S.KITTI_BF / S.KITTI_FX
+    ur, depth = api.ComputeStereoMatches(s["exl"], s["exr"], s["kl"], s["dl"], s["kr"], s["dr"], mbf, mb)
+    pl = [s["ol"].pyramid(l) for l in range(s["nl"])]
+    pr = [s["orr"].pyramid(l) for l in range(s["nl"])]
+    ur_ref, depth_ref, bd, bi, n = oracle.stereo_match(s["kl"], s["dl"], s["kr"], s["dr"], pl, pr,
+                                                       s["ol"].scale_factors(), mbf, mb)
+    assert n > 300                                        # the synthetic pair really has stereo matches
+    assert (bits(ur) == bits(ur_ref)).all()
+    assert (bits(depth) == bits(depth_ref)).all()
+    # sanity: recovered disparities are the synthetic band disparities
+    ok = ur >= 0
+    band = (s["kl"]["y"][ok] * len(s["disp"]) / s["shape"][0]).astype(int)
+    err = np.abs((s["kl"]["x"][ok] - ur[ok]) - s["disp"][band])
+    assert np.median(err) < 1.0
+
+
+def test_stereo_edge_cases(api, stereo):
+    s = stereo
+    mbf, mb = S.KITTI_BF, S.KITTI_BF / S.KITTI_FX
+    ur, depth = api.ComputeStereoMatches(s["exl"], s["exr"], s["kl"][:0], s["dl"][:0], s["kr"], s["dr"], mbf, mb)
+    assert len(ur) == 0
+    ur, depth = api.ComputeStereoMatches(s["exl"], s["exr"], s["kl"], s["dl"], s["kr"][:0], s["dr"][:0], mbf, mb)
+    assert (ur == -1).all() and (depth == -1).all()
+
+
+@pytest.fixture(scope="module")
+def frame(api, ctx, stereo):
+    s = stereo
+    h, w = s["shape"]
+    sf = s["ol"].scale_factors()
+    sc = S.projection_scenario(s["kl"], s["dl"], sf, seed=11)
+    fi = api.FrameIndex(ctx, s["kl"], s["dl"], sc["u_right"], (0.0, float(w), 0.0, float(h)), sf)
+    yield dict(fi=fi, sc=sc, sf=sf, bounds=(0.0, float(w), 0.0, float(h)))
+    fi.close()
+
+
+def test_get_features_in_area(oracle, stereo, frame):
+    g = oracle.Grid(stereo["kl"], *frame["bounds"])
+    rng = np.random.default_rng(1)
+    h, w = stereo["shape"]
+    for _ in range(60):
+        x, y = float(rng.uniform(-20, w + 20)), float(rng.uniform(-20, h + 20))
+        r = float(rng.choice([3.0, 10.0, 25.0, 60.0]))
+        lo, hi = [(-1, -1), (0, 3), (2, -1), (1, 2), (4, 4)][int(rng.integers(0, 5))]
+        got = frame["fi"].GetFeaturesInArea(x, y, r, lo, hi)
+        ref = g.features_in_area(x, y, r, lo, hi)
+        assert len(got) == len(ref) and (got == ref).all()       # same indices in the reference's order
+
+
+@pytest.mark.parametrize("th,nnratio", [(1.0, 0.8), (3.0, 0.8), (5.0, 0.6)])
+def test_search_by_projection_local(api, ctx, oracle, stereo, frame, th, nnratio):
+    s, sc = stereo, frame["sc"]
+    g = oracle.Grid(s["kl"], *frame["bounds"])
+    n_ref, m_ref, obs_ref = oracle.search_by_projection_local(
+        g, s["dl"], sc["u_right"], sc["obs0"], frame["sf"], sc["proj_x"], sc["proj_y"], sc["proj_xr"], sc["pred_level"],
+        sc["view_cos"], sc["valid"], sc["nobs"], sc["mp_desc"], th, nnratio)
+    m = api.ORBmatcher(nnratio, True, ctx=ctx)
+    n, match, obs = m.SearchByProjectionLocal(frame["fi"], sc["obs0"], sc["proj_x"], sc["proj_y"], sc["proj_xr"],
+                                              sc["pred_level"], sc["view_cos"], sc["valid"], sc["nobs"], sc["mp_desc"], th)
+    assert n_ref > 50
+    assert n == n_ref and (match == m_ref).all() and (obs == obs_ref).all()
+
+
+@pytest.mark.parametrize("mode,th,check_ori,th_high", [(0, 15.0, True, 100), (1, 7.0, True, 100), (2, 7.0, False, 100),
+                                                       (0, 10.0, True, 64)])
+def test_search_by_projection_frame(api, ctx, oracle, stereo, frame, mode, th, check_ori, th_high):
+    s, sc = stereo, frame["sc"]
+    g = oracle.Grid(s["kl"], *frame["bounds"])
+    n_ref, m_ref, obs_ref = oracle.search_by_projection_frame(
+        g, s["dl"], sc["u_right"], sc["obs0"], frame["sf"], sc["proj_x"], sc["proj_y"], sc["invz"], sc["last_octave"],
+        sc["last_angle"], sc["valid"], sc["nobs"], sc["mp_desc"], th, S.KITTI_BF, mode, check_ori, th_high)
+    m = api.ORBmatcher(0.9, check_ori, ctx=ctx)
+    n, match, obs = m.SearchByProjectionFrame(frame["fi"], sc["obs0"], sc["proj_x"], sc["proj_y"], sc["invz"],
+                                              sc["last_octave"], sc["last_angle"], sc["valid"], sc["nobs"], sc["mp_desc"],
+                                              th, S.KITTI_BF, mode, th_high)
+    assert n_ref > 30
+    assert n == n_ref and (match == m_ref).all() and (obs == obs_ref).all()
+
+
+def test_search_sequential_dependence(api, ctx, oracle, stereo, frame):
+    """a chain of map points that all want the same keypoint: the fixed-point iteration must reproduce
+    the sequential 'already taken' skips (ORBmatcher.cc:87-89,123) exactly"""
+    s = stereo
+    k, d = s["kl"], s["dl"]
+    g = oracle.Grid(k, *frame["bounds"])
+    n = 64
+    target = int(np.argmax(k["octave"] == 0))
+    sc = dict(proj_x=np.full(n, k["x"][target], np.float32), proj_y=np.full(n, k["y"][target], np.float32),
+              proj_xr=np.zeros(n, np.float32), pred_level=np.zeros(n, np.int32), view_cos=np.ones(n, np.float32),
+              valid=np.ones(n, np.uint8), nobs=np.arange(n, dtype=np.int32) % 3, mp_desc=np.repeat(d[target:target + 1], n, 0))
+    ur = np.full(len(k), -1, np.float32)
+    obs0 = np.zeros(len(k), np.int32)
+    fi = api.FrameIndex(ctx, k, d, ur, frame["bounds"], frame["sf"])
+    n_ref, m_ref, obs_ref = oracle.search_by_projection_local(g, d, ur, obs0, frame["sf"], sc["proj_x"], sc["proj_y"],
+                                                              sc["proj_xr"], sc["pred_level"], sc["view_cos"], sc["valid"],
+                                                              sc["nobs"], sc["mp_desc"], 5.0, 0.8)
+    m = api.ORBmatcher(0.8, True, ctx=ctx)
+    n_gpu, match, obs = m.SearchByProjectionLocal(fi, obs0, sc["proj_x"], sc["proj_y"], sc["proj_xr"], sc["pred_level"],
+                                                  sc["view_cos"], sc["valid"], sc["nobs"], sc["mp_desc"], 5.0)
+    assert n_gpu == n_ref and (match == m_ref).all() and (obs == obs_ref).all()
+    fi.close()
+
+
+@pytest.mark.parametrize("only_stereo,check_ori", [(False, False), (False, True), (True, False)])
+def test_search_for_triangulation(api, ctx, oracle, stereo, only_stereo, check_ori):
+    s = stereo
+    rng = np.random.default_rng(4)
+    k1, d1, k2, d2 = s["kl"], s["dl"], s["kr"], s["dr"]
+    ur1 = np.where(rng.random(len(k1)) < 0.4, k1["x"] - 10, -1).astype(np.float32)
+    ur2 = np.where(rng.random(len(k2)) < 0.4, k2["x"] - 10, -1).astype(np.float32)
+    mp1 = (rng.random(len(k1)) < 0.2).astype(np.uint8)
+    mp2 = (rng.random(len(k2)) < 0.2).astype(np.uint8)
+    fv1 = S.feature_vector(k1, S.row_band_nodes())
+    fv2 = S.feature_vector(k2, S.row_band_nodes(drop_every=5))
+    sf = s["ol"].scale_factors()
+    sigma2 = (sf * sf).astype(np.float32)
+    ex, ey = 600.0, 180.0            # an epipole inside the image so the exclusion gate is exercised
+    n_ref, m_ref = oracle.search_for_triangulation(k1, d1, ur1, mp1, k2, d2, ur2, mp2, fv1, fv2, S.RECTIFIED_F12, ex, ey,
+                                                   sf, sigma2, only_stereo, check_ori)
+    m = api.ORBmatcher(0.6, check_ori, ctx=ctx)
+    n, m12 = m.SearchForTriangulation(k1, d1, ur1, mp1, k2, d2, ur2, mp2, fv1, fv2, S.RECTIFIED_F12, ex, ey, sf, sigma2,
+                                      only_stereo)
+    assert n_ref > (5 if only_stereo else 40)
+    assert n == n_ref and (m12 == m_ref).all()

@@ -16,6 +16,7 @@
 #include "extractor_kernels.cuh"
 #include "matcher_kernels.cuh"
 #include "viorb_gpu.h"
+#include "viorb_internal.h"
 
 namespace {
 
@@ -68,6 +69,7 @@ struct viorb_ctx {
     DevBuf<viorb_top2> mparts, mout;
     DevBuf<uint8_t> scratchA, scratchB;
     DevBuf<int32_t> scratchI;
+    DevBuf<uint8_t> arena;
 };
 
 struct viorb_extractor {
@@ -101,6 +103,7 @@ struct viorb_extractor {
     int lastOverflow = 0;
     bool profiling = false;
     std::vector<cudaEvent_t> profEvents;      /* 5 per pass: start, pyramid, fast, octree, describe */
+    std::vector<cudaEvent_t> profPool;
 };
 
 namespace {
@@ -260,7 +263,11 @@ int run_pass(viorb_extractor* e, const uint8_t* d_images, size_t step, size_t fr
     CU(cudaMemsetAsync(e->buf.candCount, 0, (size_t)F * g.nlevels * sizeof(int), c->stream));
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (e->profiling)
-        for (int i = 0; i < 5; i++) { CU(cudaEventCreate(&ev[i])); e->profEvents.push_back(ev[i]); }
+        for (int i = 0; i < 5; i++) {
+            if (e->profPool.empty()) CU(cudaEventCreate(&ev[i]));
+            else { ev[i] = e->profPool.back(); e->profPool.pop_back(); }
+            e->profEvents.push_back(ev[i]);
+        }
     if (e->profiling) CU(cudaEventRecord(ev[0], c->stream));
     c->launches += viorb_launch_pyramid(g, e->tables, d_images, step, frameStride, F, e->buf, c->stream);
     if (e->profiling) CU(cudaEventRecord(ev[1], c->stream));
@@ -337,7 +344,7 @@ int viorb_ctx_destroy(viorb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->mq.release(); c->mmap.release(); c->mparts.release(); c->mout.release();
-    c->scratchA.release(); c->scratchB.release(); c->scratchI.release();
+    c->scratchA.release(); c->scratchB.release(); c->scratchI.release(); c->arena.release();
     if (c->ownStream) cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->h2d);
     cudaStreamDestroy(c->d2h);
@@ -416,6 +423,29 @@ int viorb_extractor_configure(viorb_extractor* e, int chunk_frames, int cand_div
     return VIORB_OK;
 }
 
+}  // extern "C" (reopened below)
+
+int viorb_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+cudaStream_t viorb_ctx_stream(viorb_ctx* c) { return c->stream; }
+int viorb_ctx_device(const viorb_ctx* c) { return c->device; }
+int viorb_ctx_bind(viorb_ctx* c) { return ctx_bind(c); }
+int viorb_ctx_scratch(viorb_ctx* c, size_t bytes, uint8_t** out) {
+    int rc = c->arena.ensure(bytes);
+    if (rc) return rc;
+    *out = c->arena.p;
+    return VIORB_OK;
+}
+void viorb_ctx_add_launches(viorb_ctx* c, int n) { c->launches += n; }
+viorb_ctx* viorb_extractor_ctx(viorb_extractor* e) { return e->ctx; }
+
+extern "C" {
+
 int viorb_extractor_profile(viorb_extractor* e, int enable) {
     if (!e) return fail(VIORB_ERR_INVALID, "extractor is NULL");
     e->profiling = enable != 0;
@@ -435,7 +465,7 @@ int viorb_extractor_stage_ms(viorb_extractor* e, float ms[4], int* passes) {
             CU(cudaEventElapsedTime(&t, e->profEvents[5 * p + i], e->profEvents[5 * p + i + 1]));
             ms[i] += t;
         }
-    for (cudaEvent_t ev : e->profEvents) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->profEvents) e->profPool.push_back(ev);
     e->profEvents.clear();
     if (passes) *passes = np;
     return VIORB_OK;
@@ -531,7 +561,9 @@ static int extract_batch_once(viorb_extractor* e, const uint8_t* images, int B, 
             CU(cudaStreamWaitEvent(c->h2d, e->evDone[s], 0));    /* slot input free once its compute finished */
             CU(cudaStreamWaitEvent(c->stream, e->evOut[s], 0));  /* slot outputs free once copied out */
         }
-        if (frame_stride == step * rows) {
+        if (step == (size_t)cols && frame_stride == inFrame) {       /* packed frames: one flat copy */
+            CU(cudaMemcpyAsync(e->in[s].p, images + (size_t)b0 * frame_stride, (size_t)f * inFrame, cudaMemcpyHostToDevice, c->h2d));
+        } else if (frame_stride == step * rows) {
             CU(cudaMemcpy2DAsync(e->in[s].p, cols, images + (size_t)b0 * frame_stride, step, cols, (size_t)rows * f,
                                  cudaMemcpyHostToDevice, c->h2d));
         } else {      /* frames are not back to back: one copy per frame */

@@ -1,21 +1,335 @@
-/* temporary stubs -- replaced by the windowed-search / stereo implementation */
+/*
+ * c_api_match.cu -- extern "C" entry points of the windowed matchers and the stereo matcher
+ * (include/viorb_gpu.h): host<->device marshalling around search_kernels.cu.  No host compute.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "matcher_kernels.cuh"
 #include "viorb_gpu.h"
-extern "C" {
-int viorb_stereo_match(viorb_extractor*, int, viorb_extractor*, int, const viorb_keypoint*, const uint8_t*, int,
-                       const viorb_keypoint*, const uint8_t*, int, float, float, float*, float*) { return VIORB_ERR_UNSUPPORTED; }
-int viorb_frame_index_create(viorb_ctx*, const viorb_keypoint*, const uint8_t*, const float*, int, float, float, float,
-                             float, const float*, int, viorb_frame_index**) { return VIORB_ERR_UNSUPPORTED; }
-int viorb_frame_index_destroy(viorb_frame_index*) { return VIORB_ERR_UNSUPPORTED; }
-int viorb_frame_features_in_area(viorb_frame_index*, float, float, float, int, int, int32_t*, int, int*) { return VIORB_ERR_UNSUPPORTED; }
-int viorb_search_by_projection_local(viorb_frame_index*, int32_t*, const float*, const float*, const float*, const int32_t*,
-                                     const float*, const uint8_t*, const int32_t*, const uint8_t*, int, float, float,
-                                     int32_t*, int*) { return VIORB_ERR_UNSUPPORTED; }
-int viorb_search_by_projection_frame(viorb_frame_index*, int32_t*, const float*, const float*, const float*, const int32_t*,
-                                     const float*, const uint8_t*, const int32_t*, const uint8_t*, int, float, float, int,
-                                     int, int, int32_t*, int*) { return VIORB_ERR_UNSUPPORTED; }
-int viorb_search_for_triangulation(viorb_ctx*, const viorb_keypoint*, const uint8_t*, const float*, const uint8_t*, int,
-                                   const viorb_keypoint*, const uint8_t*, const float*, const uint8_t*, int,
-                                   const int32_t*, const int32_t*, const int32_t*, int, const int32_t*, const int32_t*,
-                                   const int32_t*, int, const float*, float, float, const float*, const float*, int, int,
-                                   int, int32_t*, int*) { return VIORB_ERR_UNSUPPORTED; }
+#include "viorb_internal.h"
+
+/* launchers of search_kernels.cu */
+int viorb_launch_stereo(const StereoParams& p, const viorb_keypoint* d_kl, const uint8_t* d_dl,
+                        const viorb_keypoint* d_kr, const uint8_t* d_dr, int* d_scratch, float* d_uRight,
+                        float* d_depth, int* d_sad, cudaStream_t s);
+int viorb_launch_grid_build(const viorb_keypoint* d_kps, int n, float minX, float minY, float invW, float invH,
+                            int* d_cellOf, int* d_cellStart, int* d_cellItems, cudaStream_t s);
+int viorb_launch_features_in_area(const FrameIndexDev& fi, float x, float y, float r, int minLevel, int maxLevel,
+                                  unsigned long long* d_keys, int* d_count, cudaStream_t s);
+int viorb_launch_search_local(const FrameIndexDev& fi, const float* projX, const float* projY, const float* projXR,
+                              const int* predLevel, const float* viewCos, const uint8_t* valid, const int* nobs,
+                              const uint8_t* mpDesc, int nmp, float th, float nnratio, int* d_obs, int* d_claim,
+                              int* d_minClaim, int* d_match, int* d_nmatches, cudaStream_t s);
+int viorb_launch_search_frame(const FrameIndexDev& fi, const float* u, const float* v, const float* invz,
+                              const int* lastOctave, const float* lastAngle, const uint8_t* valid, const int* nobs,
+                              const uint8_t* mpDesc, int nlast, float th, float mbf, int mode, int checkOri, int thHigh,
+                              int* d_obs, int* d_claim, int* d_minClaim, int* d_match, int* d_nmatches, cudaStream_t s);
+int viorb_launch_triangulation(const viorb_keypoint* k1, const uint8_t* d1, const float* ur1, const uint8_t* mp1, int n1,
+                               const viorb_keypoint* k2, const uint8_t* d2, const float* ur2, const uint8_t* mp2, int n2,
+                               const int* nodeId1, const int* nodePtr1, const int* idx1, int nn1, int nentries1,
+                               const int* nodeId2, const int* nodePtr2, const int* idx2, int nn2, const float* F12,
+                               float ex, float ey, const float* scale2, const float* sigma2, int nlevels, int onlyStereo,
+                               int checkOri, int* d_matches12, int* d_nmatches, cudaStream_t s);
+
+namespace {
+
+/* bump allocator over one device scratch buffer: a call uploads all its inputs into a single arena */
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t cap = 0, off = 0;
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+
+template <typename T>
+int upload(viorb_ctx* c, T* dst, const T* src, size_t n) {
+    if (n == 0) return VIORB_OK;
+    VCU(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, viorb_ctx_stream(c)));
+    return VIORB_OK;
 }
+
+}  // namespace
+
+struct viorb_frame_index {
+    viorb_ctx* ctx = nullptr;
+    uint8_t* mem = nullptr;
+    FrameIndexDev dev;
+    int* cellOf = nullptr;
+    int n = 0;
+};
+
+extern "C" {
+
+int viorb_stereo_match(viorb_extractor* left, int frame_l, viorb_extractor* right, int frame_r,
+                       const viorb_keypoint* kps_l, const uint8_t* desc_l, int nl, const viorb_keypoint* kps_r,
+                       const uint8_t* desc_r, int nr, float mbf, float mb, float* u_right, float* depth) {
+    if (!left || !right || nl < 0 || nr < 0 || (nl > 0 && (!kps_l || !desc_l || !u_right || !depth)) ||
+        (nr > 0 && (!kps_r || !desc_r)))
+        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    if (nl == 0) return VIORB_OK;
+    viorb_ctx* c = viorb_extractor_ctx(left);
+    if (viorb_extractor_ctx(right) != c && viorb_ctx_device(viorb_extractor_ctx(right)) != viorb_ctx_device(c))
+        return viorb_fail(VIORB_ERR_INVALID, "left and right extractors live on different devices");
+    int rc;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    StereoParams p;
+    memset(&p, 0, sizeof(p));
+    int nlevels = 0;
+    float scale[16], inv[16];
+    if ((rc = viorb_extractor_tables(left, &nlevels, scale, inv, nullptr, nullptr, nullptr))) return rc;
+    p.nlevels = nlevels; p.nl = nl; p.nr = nr; p.mbf = mbf; p.mb = mb;
+    for (int l = 0; l < nlevels; l++) {
+        int w, h, w2, h2;
+        const uint8_t *rl, *rr;
+        size_t sl, sr;
+        if ((rc = viorb_extractor_pyramid_info(left, l, &w, &h))) return rc;
+        if ((rc = viorb_extractor_pyramid_info(right, l, &w2, &h2))) return rc;
+        if (w != w2 || h != h2) return viorb_fail(VIORB_ERR_INVALID, "left/right pyramids differ in size");
+        if ((rc = viorb_extractor_pyramid_device(left, frame_l, l, &rl, &sl))) return rc;
+        if ((rc = viorb_extractor_pyramid_device(right, frame_r, l, &rr, &sr))) return rc;
+        p.scale[l] = scale[l]; p.invScale[l] = inv[l];
+        p.lv[l].roiL = rl; p.lv[l].roiR = rr; p.lv[l].w = w; p.lv[l].h = h; p.lv[l].stepL = (int)sl; p.lv[l].stepR = (int)sr;
+    }
+    p.nRows = p.lv[0].h;
+    /* the extractors may run on other streams of the same device: make their work visible */
+    if ((rc = viorb_ctx_synchronize(viorb_extractor_ctx(right)))) return rc;
+    if ((rc = viorb_ctx_synchronize(c))) return rc;
+    const size_t bytes = pad((size_t)nl * sizeof(viorb_keypoint)) + pad((size_t)nl * 32) + pad((size_t)std::max(nr, 1) * sizeof(viorb_keypoint)) +
+                         pad((size_t)std::max(nr, 1) * 32) + 3 * pad((size_t)nl * 4) + pad(64) + 4096;
+    Arena a;
+    if ((rc = viorb_ctx_scratch(c, bytes, &a.base))) return rc;
+    a.cap = bytes;
+    viorb_keypoint* dkl = a.take<viorb_keypoint>(nl);
+    uint8_t* ddl = a.take<uint8_t>((size_t)nl * 32);
+    viorb_keypoint* dkr = a.take<viorb_keypoint>(std::max(nr, 1));
+    uint8_t* ddr = a.take<uint8_t>((size_t)std::max(nr, 1) * 32);
+    float* dur = a.take<float>(nl);
+    float* ddp = a.take<float>(nl);
+    int* dsad = a.take<int>(nl);
+    int* dscr = a.take<int>(16);
+    if ((rc = upload(c, dkl, kps_l, nl)) || (rc = upload(c, ddl, desc_l, (size_t)nl * 32)) ||
+        (rc = upload(c, dkr, kps_r, nr)) || (rc = upload(c, ddr, desc_r, (size_t)nr * 32)))
+        return rc;
+    viorb_ctx_add_launches(c, viorb_launch_stereo(p, dkl, ddl, dkr, ddr, dscr, dur, ddp, dsad, viorb_ctx_stream(c)));
+    VCU(cudaGetLastError());
+    VCU(cudaMemcpyAsync(u_right, dur, (size_t)nl * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaMemcpyAsync(depth, ddp, (size_t)nl * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    return VIORB_OK;
+}
+
+int viorb_frame_index_create(viorb_ctx* c, const viorb_keypoint* kps_un, const uint8_t* desc, const float* u_right, int n,
+                             float min_x, float max_x, float min_y, float max_y, const float* scale_factors, int nlevels,
+                             viorb_frame_index** out) {
+    if (!c || !out || n < 0 || (n > 0 && (!kps_un || !desc)) || !scale_factors || nlevels < 1 || nlevels > 12)
+        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    if (n >= (1 << 20)) return viorb_fail(VIORB_ERR_UNSUPPORTED, "more than 2^20 keypoints in one frame");
+    *out = nullptr;
+    int rc;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    viorb_frame_index* fi = new (std::nothrow) viorb_frame_index();
+    if (!fi) return viorb_fail(VIORB_ERR_INVALID, "out of host memory");
+    const int nn = std::max(n, 1);
+    const size_t bytes = pad((size_t)nn * sizeof(viorb_keypoint)) + pad((size_t)nn * 32) + pad((size_t)nn * 4) * 3 +
+                         pad((64 * 48 + 1) * 4) + 4096;
+    if (cudaMalloc((void**)&fi->mem, bytes) != cudaSuccess) { delete fi; return viorb_fail(VIORB_ERR_CUDA, "cudaMalloc failed"); }
+    Arena a;
+    a.base = fi->mem; a.cap = bytes;
+    viorb_keypoint* dk = a.take<viorb_keypoint>(nn);
+    uint8_t* dd = a.take<uint8_t>((size_t)nn * 32);
+    float* dur = a.take<float>(nn);
+    int* cellOf = a.take<int>(nn);
+    int* cellItems = a.take<int>(nn);
+    int* cellStart = a.take<int>(64 * 48 + 1);
+    fi->ctx = c; fi->n = n; fi->cellOf = cellOf;
+    cudaStream_t s = viorb_ctx_stream(c);
+    std::vector<float> ur;
+    if (!u_right) { ur.assign(nn, -1.0f); u_right = ur.data(); }
+    if ((rc = upload(c, dk, kps_un, n)) || (rc = upload(c, dd, desc, (size_t)n * 32)) || (rc = upload(c, dur, u_right, n))) {
+        cudaFree(fi->mem); delete fi; return rc;
+    }
+    FrameIndexDev& d = fi->dev;
+    memset(&d, 0, sizeof(d));
+    d.kps = dk; d.desc = dd; d.uRight = dur; d.cellStart = cellStart; d.cellItems = cellItems; d.n = n;
+    d.minX = min_x; d.maxX = max_x; d.minY = min_y; d.maxY = max_y;
+    d.invW = 64.0f / (max_x - min_x);         /* mfGridElementWidthInv, src/Frame.cc:181 */
+    d.invH = 48.0f / (max_y - min_y);
+    d.nlevels = nlevels;
+    for (int l = 0; l < nlevels; l++) d.scale[l] = scale_factors[l];
+    viorb_ctx_add_launches(c, viorb_launch_grid_build(dk, n, min_x, min_y, d.invW, d.invH, cellOf, cellStart, cellItems, s));
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { cudaFree(fi->mem); delete fi; return viorb_fail(VIORB_ERR_CUDA, "grid build: %s", cudaGetErrorString(e)); }
+    *out = fi;
+    return VIORB_OK;
+}
+
+int viorb_frame_index_destroy(viorb_frame_index* fi) {
+    if (!fi) return VIORB_OK;
+    cudaSetDevice(viorb_ctx_device(fi->ctx));
+    cudaStreamSynchronize(viorb_ctx_stream(fi->ctx));
+    cudaFree(fi->mem);
+    delete fi;
+    return VIORB_OK;
+}
+
+int viorb_frame_features_in_area(viorb_frame_index* fi, float x, float y, float r, int min_level, int max_level,
+                                 int32_t* out, int cap, int* n) {
+    if (!fi || !n || (cap > 0 && !out)) return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    viorb_ctx* c = fi->ctx;
+    int rc;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    const size_t bytes = pad((size_t)std::max(fi->n, 1) * 8) + pad(64) + 1024;
+    Arena a;
+    if ((rc = viorb_ctx_scratch(c, bytes, &a.base))) return rc;
+    unsigned long long* keys = a.take<unsigned long long>(std::max(fi->n, 1));
+    int* cnt = a.take<int>(4);
+    viorb_ctx_add_launches(c, viorb_launch_features_in_area(fi->dev, x, y, r, min_level, max_level, keys, cnt, viorb_ctx_stream(c)));
+    int h = 0;
+    VCU(cudaMemcpyAsync(&h, cnt, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    std::vector<unsigned long long> k(std::max(h, 1));
+    VCU(cudaMemcpy(k.data(), keys, (size_t)h * 8, cudaMemcpyDeviceToHost));
+    std::sort(k.begin(), k.begin() + h);          /* presentation order only: enumeration rank is part of the key */
+    for (int i = 0; i < h && i < cap; i++) out[i] = (int32_t)(k[i] & 0xffffffffu);
+    *n = h;
+    return VIORB_OK;
+}
+
+static int search_common_alloc(viorb_ctx* c, int nf, int nq, size_t extra, Arena* a) {
+    const size_t bytes = pad((size_t)std::max(nf, 1) * 4) * 3 + pad((size_t)std::max(nq, 1) * 4) + extra + pad(64) + 8192;
+    int rc;
+    if ((rc = viorb_ctx_scratch(c, bytes, &a->base))) return rc;
+    a->cap = bytes;
+    return VIORB_OK;
+}
+
+int viorb_search_by_projection_local(viorb_frame_index* fi, int32_t* frame_mp_obs, const float* proj_x, const float* proj_y,
+                                     const float* proj_xr, const int32_t* pred_level, const float* view_cos,
+                                     const uint8_t* valid, const int32_t* nobs, const uint8_t* mp_desc, int nmp, float th,
+                                     float nnratio, int32_t* match, int* nmatches) {
+    if (!fi || !frame_mp_obs || !match || !nmatches || nmp < 0 ||
+        (nmp > 0 && (!proj_x || !proj_y || !proj_xr || !pred_level || !view_cos || !valid || !nobs || !mp_desc)))
+        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    viorb_ctx* c = fi->ctx;
+    int rc;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    const int nf = fi->n, nq = std::max(nmp, 1);
+    Arena a;
+    if ((rc = search_common_alloc(c, nf, nmp, 5 * pad((size_t)nq * 4) + pad(nq) + pad((size_t)nq * 32), &a))) return rc;
+    int* dobs = a.take<int>(std::max(nf, 1));
+    int* dmin = a.take<int>(std::max(nf, 1));
+    int* dmatch = a.take<int>(std::max(nf, 1));
+    int* dclaim = a.take<int>(nq);
+    float* dpx = a.take<float>(nq); float* dpy = a.take<float>(nq); float* dpr = a.take<float>(nq);
+    float* dvc = a.take<float>(nq); int* dlv = a.take<int>(nq); int* dno = a.take<int>(nq);
+    uint8_t* dva = a.take<uint8_t>(nq); uint8_t* dde = a.take<uint8_t>((size_t)nq * 32);
+    int* dn = a.take<int>(4);
+    if ((rc = upload(c, dobs, frame_mp_obs, nf)) || (rc = upload(c, dpx, proj_x, nmp)) || (rc = upload(c, dpy, proj_y, nmp)) ||
+        (rc = upload(c, dpr, proj_xr, nmp)) || (rc = upload(c, dvc, view_cos, nmp)) || (rc = upload(c, dlv, pred_level, nmp)) ||
+        (rc = upload(c, dno, nobs, nmp)) || (rc = upload(c, dva, valid, nmp)) || (rc = upload(c, dde, mp_desc, (size_t)nmp * 32)))
+        return rc;
+    viorb_ctx_add_launches(c, viorb_launch_search_local(fi->dev, dpx, dpy, dpr, dlv, dvc, dva, dno, dde, nmp, th, nnratio, dobs,
+                                                        dclaim, dmin, dmatch, dn, viorb_ctx_stream(c)));
+    VCU(cudaGetLastError());
+    VCU(cudaMemcpyAsync(match, dmatch, (size_t)nf * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaMemcpyAsync(frame_mp_obs, dobs, (size_t)nf * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    return VIORB_OK;
+}
+
+int viorb_search_by_projection_frame(viorb_frame_index* fi, int32_t* frame_mp_obs, const float* u, const float* v,
+                                     const float* invz, const int32_t* last_octave, const float* last_angle,
+                                     const uint8_t* valid, const int32_t* nobs, const uint8_t* mp_desc, int nlast, float th,
+                                     float mbf, int mode, int check_orientation, int th_high, int32_t* match, int* nmatches) {
+    if (!fi || !frame_mp_obs || !match || !nmatches || nlast < 0 || mode < 0 || mode > 2 ||
+        (nlast > 0 && (!u || !v || !invz || !last_octave || !last_angle || !valid || !nobs || !mp_desc)))
+        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    viorb_ctx* c = fi->ctx;
+    int rc;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    const int nf = fi->n, nq = std::max(nlast, 1);
+    Arena a;
+    if ((rc = search_common_alloc(c, nf, nlast, 6 * pad((size_t)nq * 4) + pad(nq) + pad((size_t)nq * 32), &a))) return rc;
+    int* dobs = a.take<int>(std::max(nf, 1));
+    int* dmin = a.take<int>(std::max(nf, 1));
+    int* dmatch = a.take<int>(std::max(nf, 1));
+    int* dclaim = a.take<int>(nq);
+    float* du = a.take<float>(nq); float* dv = a.take<float>(nq); float* dz = a.take<float>(nq); float* dan = a.take<float>(nq);
+    int* doc = a.take<int>(nq); int* dno = a.take<int>(nq);
+    uint8_t* dva = a.take<uint8_t>(nq); uint8_t* dde = a.take<uint8_t>((size_t)nq * 32);
+    int* dn = a.take<int>(4);
+    if ((rc = upload(c, dobs, frame_mp_obs, nf)) || (rc = upload(c, du, u, nlast)) || (rc = upload(c, dv, v, nlast)) ||
+        (rc = upload(c, dz, invz, nlast)) || (rc = upload(c, dan, last_angle, nlast)) || (rc = upload(c, doc, last_octave, nlast)) ||
+        (rc = upload(c, dno, nobs, nlast)) || (rc = upload(c, dva, valid, nlast)) || (rc = upload(c, dde, mp_desc, (size_t)nlast * 32)))
+        return rc;
+    viorb_ctx_add_launches(c, viorb_launch_search_frame(fi->dev, du, dv, dz, doc, dan, dva, dno, dde, nlast, th, mbf, mode,
+                                                        check_orientation, th_high, dobs, dclaim, dmin, dmatch, dn,
+                                                        viorb_ctx_stream(c)));
+    VCU(cudaGetLastError());
+    VCU(cudaMemcpyAsync(match, dmatch, (size_t)nf * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaMemcpyAsync(frame_mp_obs, dobs, (size_t)nf * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    return VIORB_OK;
+}
+
+int viorb_search_for_triangulation(viorb_ctx* c, const viorb_keypoint* k1, const uint8_t* d1, const float* ur1,
+                                   const uint8_t* has_mp1, int n1, const viorb_keypoint* k2, const uint8_t* d2,
+                                   const float* ur2, const uint8_t* has_mp2, int n2, const int32_t* node_id1,
+                                   const int32_t* node_ptr1, const int32_t* idx1, int nn1, const int32_t* node_id2,
+                                   const int32_t* node_ptr2, const int32_t* idx2, int nn2, const float* F12, float ex, float ey,
+                                   const float* scale_factors2, const float* level_sigma2_2, int nlevels, int only_stereo,
+                                   int check_orientation, int32_t* matches12, int* nmatches) {
+    if (!c || n1 < 0 || n2 < 0 || nn1 < 0 || nn2 < 0 || !F12 || !scale_factors2 || !level_sigma2_2 || !matches12 || !nmatches ||
+        nlevels < 1 || nlevels > 12 || (n1 > 0 && (!k1 || !d1 || !ur1 || !has_mp1)) || (n2 > 0 && (!k2 || !d2 || !ur2 || !has_mp2)) ||
+        (nn1 > 0 && (!node_id1 || !node_ptr1 || !idx1)) || (nn2 > 0 && (!node_id2 || !node_ptr2 || !idx2)))
+        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    if (n2 >= (1 << 24)) return viorb_fail(VIORB_ERR_UNSUPPORTED, "more than 2^24 keypoints");
+    int rc;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    const int e1 = nn1 > 0 ? node_ptr1[nn1] : 0, e2 = nn2 > 0 ? node_ptr2[nn2] : 0;
+    const int m1 = std::max(n1, 1), m2 = std::max(n2, 1);
+    const size_t bytes = pad((size_t)m1 * 28) + pad((size_t)m1 * 32) + pad((size_t)m1 * 4) * 2 + pad(m1) + pad((size_t)m2 * 28) +
+                         pad((size_t)m2 * 32) + pad((size_t)m2 * 4) + pad(m2) + pad((size_t)(nn1 + 2) * 4) * 2 + pad((size_t)(e1 + 1) * 4) +
+                         pad((size_t)(nn2 + 2) * 4) * 2 + pad((size_t)(e2 + 1) * 4) + pad(64) + 16384;
+    Arena a;
+    if ((rc = viorb_ctx_scratch(c, bytes, &a.base))) return rc;
+    viorb_keypoint* dk1 = a.take<viorb_keypoint>(m1); uint8_t* dd1 = a.take<uint8_t>((size_t)m1 * 32);
+    float* du1 = a.take<float>(m1); uint8_t* dm1 = a.take<uint8_t>(m1); int* dmatch = a.take<int>(m1);
+    viorb_keypoint* dk2 = a.take<viorb_keypoint>(m2); uint8_t* dd2 = a.take<uint8_t>((size_t)m2 * 32);
+    float* du2 = a.take<float>(m2); uint8_t* dm2 = a.take<uint8_t>(m2);
+    int* dni1 = a.take<int>(nn1 + 1); int* dnp1 = a.take<int>(nn1 + 2); int* di1 = a.take<int>(e1 + 1);
+    int* dni2 = a.take<int>(nn2 + 1); int* dnp2 = a.take<int>(nn2 + 2); int* di2 = a.take<int>(e2 + 1);
+    int* dn = a.take<int>(4);
+    if ((rc = upload(c, dk1, k1, n1)) || (rc = upload(c, dd1, d1, (size_t)n1 * 32)) || (rc = upload(c, du1, ur1, n1)) ||
+        (rc = upload(c, dm1, has_mp1, n1)) || (rc = upload(c, dk2, k2, n2)) || (rc = upload(c, dd2, d2, (size_t)n2 * 32)) ||
+        (rc = upload(c, du2, ur2, n2)) || (rc = upload(c, dm2, has_mp2, n2)) || (rc = upload(c, dni1, node_id1, nn1)) ||
+        (rc = upload(c, dnp1, node_ptr1, nn1 ? nn1 + 1 : 0)) || (rc = upload(c, di1, idx1, e1)) || (rc = upload(c, dni2, node_id2, nn2)) ||
+        (rc = upload(c, dnp2, node_ptr2, nn2 ? nn2 + 1 : 0)) || (rc = upload(c, di2, idx2, e2)))
+        return rc;
+    viorb_ctx_add_launches(c, viorb_launch_triangulation(dk1, dd1, du1, dm1, n1, dk2, dd2, du2, dm2, n2, dni1, dnp1, di1, nn1, e1,
+                                                         dni2, dnp2, di2, nn2, F12, ex, ey, scale_factors2, level_sigma2_2, nlevels,
+                                                         only_stereo, check_orientation, dmatch, dn, viorb_ctx_stream(c)));
+    VCU(cudaGetLastError());
+    VCU(cudaMemcpyAsync(matches12, dmatch, (size_t)n1 * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    return VIORB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,673 @@
+/*
+ * search_kernels.cu -- sm_100a kernels for the small windowed matchers of the hot path:
+ *
+ *   stereo_match_kernel (+ rank / filter)   Frame::ComputeStereoMatches            src/Frame.cc:646-820
+ *   grid_build_kernel                       Frame::AssignFeaturesToGrid / PosInGrid src/Frame.cc:410-425,562-572
+ *   features_in_area_kernel                 Frame::GetFeaturesInArea                src/Frame.cc:507-560
+ *   search_local_kernel                     ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)   :45-129
+ *   search_frame_kernel                     ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)  :1328-1471
+ *   triangulation_kernel (+ finalize)       ORBmatcher::SearchForTriangulation                               :657-823
+ *
+ * The projection searches carry a sequential dependence in the reference (a keypoint claimed by an
+ * earlier map point is skipped by later ones, ORBmatcher.cc:87-89,123).  Query i's result depends only
+ * on the results of queries j < i, so the kernels iterate the whole query set in parallel to the
+ * unique fixed point of that triangular system: after pass k every query whose dependence chain is
+ * shorter than k holds its sequential answer; the loop ends when a pass changes nothing (typically
+ * 2-3 passes).  All of it is integer / popc work with a few single-rounded float gates; no tensor cores.
+ */
+#include <limits.h>
+
+#include "matcher_kernels.cuh"
+
+namespace {
+
+#define TH_HIGH 100
+#define TH_LOW 50
+#define HISTO_LENGTH 30
+#define GRID_COLS 64
+#define GRID_ROWS 48
+
+__device__ __forceinline__ int hamming_rows(const uint8_t* a, const uint8_t* b) {
+    const uint4 a0 = reinterpret_cast<const uint4*>(a)[0], a1 = reinterpret_cast<const uint4*>(a)[1];
+    const uint4 b0 = reinterpret_cast<const uint4*>(b)[0], b1 = reinterpret_cast<const uint4*>(b)[1];
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t < v ? t : v;
+    }
+    return v;
+}
+
+/* two smallest keys over the warp; every lane contributes its own (k1 <= k2) */
+__device__ __forceinline__ void warp_two_min(unsigned long long& k1, unsigned long long& k2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long b1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        const unsigned long long b2 = __shfl_xor_sync(0xffffffffu, k2, o);
+        const unsigned long long lo = k1 < b1 ? k1 : b1, hi = k1 < b1 ? b1 : k1;
+        const unsigned long long s2 = k2 < b2 ? k2 : b2;
+        k1 = lo;
+        k2 = hi < s2 ? hi : s2;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame::ComputeStereoMatches, one warp per left keypoint.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(128) stereo_match_kernel(const __grid_constant__ StereoParams p,
+                                                           const viorb_keypoint* __restrict__ kl,
+                                                           const uint8_t* __restrict__ dl,
+                                                           const viorb_keypoint* __restrict__ kr,
+                                                           const uint8_t* __restrict__ dr, float* __restrict__ uRight,
+                                                           float* __restrict__ depth, int* __restrict__ sad,
+                                                           int* __restrict__ nMatched) {
+    const int lane = threadIdx.x & 31;
+    const int iL = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (iL >= p.nl) return;
+    const viorb_keypoint kpL = kl[iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    if (lane == 0) { uRight[iL] = -1.0f; depth[iL] = -1.0f; sad[iL] = -1; }
+    const float minZ = p.mb;
+    const float minD = 0;
+    const float maxD = __fdiv_rn(p.mbf, minZ);
+    const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
+    if (maxU < 0) return;                                          /* :699-700 */
+    const int yi = (int)vL;                                        /* vRowIndices[vL] :691 */
+    unsigned long long best = ~0ull;
+    const uint8_t* dL = dl + (size_t)iL * 32;
+    for (int iR = lane; iR < p.nr; iR += 32) {
+        const viorb_keypoint kpR = kr[iR];
+        const float r = __fmul_rn(2.0f, p.scale[kpR.octave]);      /* :667 */
+        const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
+        if (yi < minr || yi > maxr) continue;                      /* row table :668-672 */
+        if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+        const float uR = kpR.x;
+        if (uR >= minU && uR <= maxU) {
+            const int dist = hamming_rows(dL, dr + (size_t)iR * 32);
+            if (dist < TH_HIGH) {                                  /* bestDist starts at TH_HIGH, strict < */
+                const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)iR;
+                best = key < best ? key : best;
+            }
+        }
+    }
+    best = warp_min_u64(best);
+    if (best == ~0ull) return;
+    const int bestDist = (int)(best >> 32), bestIdxR = (int)(best & 0xffffffffu);
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    if (!(bestDist < thOrbDist)) return;
+    /* sub-pixel match by correlation (:732-803) */
+    const float uR0 = kr[bestIdxR].x;
+    const float scaleFactor = p.invScale[levelL];
+    const float scaleduL = roundf(__fmul_rn(kpL.x, scaleFactor));
+    const float scaledvL = roundf(__fmul_rn(kpL.y, scaleFactor));
+    const float scaleduR0 = roundf(__fmul_rn(uR0, scaleFactor));
+    const int w = 5, L = 5;
+    const StereoLevel& lv = p.lv[levelL];
+    const int cvL = (int)scaledvL, cuL = (int)scaleduL, cuR = (int)scaleduR0;
+    if (cvL - w < 0 || cvL + w + 1 > lv.h || cuL - w < 0 || cuL + w + 1 > lv.w) return;   /* cv::Mat range (C.5) */
+    const float iniu = __fadd_rn(scaleduR0, (float)(L - w));
+    const float endu = __fadd_rn(scaleduR0, (float)(L + w + 1));
+    if (iniu < 0 || endu >= lv.w) return;                          /* :753-756 */
+    if (cuR - L - w < 0 || cuR + L + w + 1 > lv.w) return;         /* colRange would throw */
+    int il[4], py[4], px[4];
+    const int cL = lv.roiL[(size_t)cvL * lv.stepL + cuL];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int pidx = lane + 32 * k;
+        py[k] = pidx / 11; px[k] = pidx - py[k] * 11;
+        il[k] = pidx < 121 ? (int)lv.roiL[(size_t)(cvL - w + py[k]) * lv.stepL + (cuL - w + px[k])] - cL : 0;
+    }
+    int bestSad = INT_MAX, bestinc = 0;
+    int d[11];
+#pragma unroll
+    for (int inc = -L; inc <= L; inc++) {
+        const int cR = lv.roiR[(size_t)cvL * lv.stepR + (cuR + inc)];
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (lane + 32 * k < 121) {
+                const int ir = (int)lv.roiR[(size_t)(cvL - w + py[k]) * lv.stepR + (cuR + inc - w + px[k])] - cR;
+                s += abs(il[k] - ir);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        d[inc + L] = s;
+        if (s < bestSad) { bestSad = s; bestinc = inc; }
+    }
+    if (bestinc == -L || bestinc == L) return;
+    float dist1 = 0, dist2 = 0, dist3 = 0;
+#pragma unroll
+    for (int i = 1; i < 10; i++)
+        if (i == bestinc + L) { dist1 = (float)d[i - 1]; dist2 = (float)d[i]; dist3 = (float)d[i + 1]; }
+    const float deltaR = __fdiv_rn(__fsub_rn(dist1, dist3),
+                                   __fmul_rn(2.0f, __fsub_rn(__fadd_rn(dist1, dist3), __fmul_rn(2.0f, dist2))));
+    if (deltaR < -1 || deltaR > 1) return;
+    float bestuR = __fmul_rn(p.scale[levelL], __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+    float disparity = __fsub_rn(uL, bestuR);
+    if (disparity >= minD && disparity < maxD) {
+        if (disparity <= 0) {
+            disparity = 0.01f;
+            bestuR = (float)((double)uL - 0.01);
+        }
+        if (lane == 0) {
+            depth[iL] = __fdiv_rn(p.mbf, disparity);
+            uRight[iL] = bestuR;
+            sad[iL] = bestSad;
+            atomicAdd(nMatched, 1);
+        }
+    }
+}
+
+/* median of the accepted SAD values: the element of rank size/2 in the (sad, iL) order (:806-807) */
+__global__ void stereo_rank_kernel(const int* __restrict__ sad, int nl, const int* __restrict__ nMatched,
+                                   int* __restrict__ median) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nl) return;
+    const int s = sad[i];
+    if (s < 0) return;
+    int rank = 0;
+    for (int j = 0; j < nl; j++) {
+        const int t = sad[j];
+        rank += (t >= 0) && (t < s || (t == s && j < i));
+    }
+    if (rank == *nMatched / 2) *median = s;
+}
+
+__global__ void stereo_filter_kernel(const int* __restrict__ sad, int nl, const int* __restrict__ median,
+                                     float* __restrict__ uRight, float* __restrict__ depth) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nl) return;
+    const int s = sad[i];
+    if (s < 0) return;
+    const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), (float)*median);      /* :808 */
+    if (!((float)s < thDist)) { uRight[i] = -1; depth[i] = -1; }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * 64x48 grid: AssignFeaturesToGrid.  Single CTA; slot order inside a cell = keypoint index order.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(1024) grid_build_kernel(const viorb_keypoint* __restrict__ kps, int n, float minX,
+                                                          float minY, float invW, float invH, int* __restrict__ cellOf,
+                                                          int* __restrict__ cellStart, int* __restrict__ cellItems) {
+    __shared__ int cnt[GRID_COLS * GRID_ROWS + 1];
+    __shared__ int part[1024];
+    const int tid = threadIdx.x;
+    const int NCELL = GRID_COLS * GRID_ROWS;
+    for (int c = tid; c <= NCELL; c += 1024) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        /* PosInGrid :562-572 */
+        const int posX = (int)roundf(__fmul_rn(__fsub_rn(kps[i].x, minX), invW));
+        const int posY = (int)roundf(__fmul_rn(__fsub_rn(kps[i].y, minY), invH));
+        int c = -1;
+        if (!(posX < 0 || posX >= GRID_COLS || posY < 0 || posY >= GRID_ROWS)) {
+            c = posX * GRID_ROWS + posY;
+            atomicAdd(&cnt[c], 1);
+        }
+        cellOf[i] = c;
+    }
+    __syncthreads();
+    /* exclusive scan of 3072 counters: 3 per thread */
+    const int per = (NCELL + 1023) / 1024;
+    int s = 0;
+    for (int k = 0; k < per; k++) {
+        const int c = tid * per + k;
+        if (c < NCELL) s += cnt[c];
+    }
+    part[tid] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int t = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += t;
+        __syncthreads();
+    }
+    int run = part[tid] - s;
+    for (int k = 0; k < per; k++) {
+        const int c = tid * per + k;
+        if (c < NCELL) {
+            const int t = cnt[c];
+            cellStart[c] = run;
+            cnt[c] = run;
+            run += t;
+        }
+    }
+    if (tid == 1023) cellStart[NCELL] = part[1023];
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int c = cellOf[i];
+        if (c < 0) continue;
+        int r = 0;
+        for (int j = 0; j < i; j++) r += cellOf[j] == c;
+        cellItems[cnt[c] + r] = i;
+    }
+}
+
+/* GetFeaturesInArea enumeration (:507-560): calls f(pos, idx) for every keypoint that passes the level and
+ * window gates, in parallel over the lanes of a warp; `pos` is the rank of the keypoint in the reference's
+ * sequential enumeration (cells ix-major, then iy, then slot), so ties can be broken exactly. */
+template <typename F>
+__device__ __forceinline__ void for_features_in_area(const FrameIndexDev& fi, float x, float y, float r, int minLevel,
+                                                     int maxLevel, int lane, F f) {
+    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, fi.minX), r), fi.invW)));
+    if (nMinCellX >= GRID_COLS) return;
+    const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, fi.minX), r), fi.invW)));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, fi.minY), r), fi.invH)));
+    if (nMinCellY >= GRID_ROWS) return;
+    const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, fi.minY), r), fi.invH)));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    int pos = 0;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
+        /* cells (ix, nMinCellY..nMaxCellY) are contiguous in the CSR */
+        const int beg = fi.cellStart[ix * GRID_ROWS + nMinCellY], end = fi.cellStart[ix * GRID_ROWS + nMaxCellY + 1];
+        for (int j = beg + lane; j < end; j += 32) {
+            const int idx = fi.cellItems[j];
+            const viorb_keypoint kp = fi.kps[idx];
+            if (bCheckLevels) {
+                if (kp.octave < minLevel) continue;
+                if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+            }
+            const float distx = __fsub_rn(kp.x, x), disty = __fsub_rn(kp.y, y);
+            if (fabsf(distx) < r && fabsf(disty) < r) f(pos + (j - beg), idx, kp.octave);
+        }
+        pos += end - beg;
+    }
+}
+
+__global__ void features_in_area_kernel(FrameIndexDev fi, float x, float y, float r, int minLevel, int maxLevel,
+                                        unsigned long long* __restrict__ keys, int* __restrict__ count) {
+    /* single warp: emit (pos, idx) pairs; the host sorts by pos (test / debugging entry point) */
+    const int lane = threadIdx.x;
+    for_features_in_area(fi, x, y, r, minLevel, maxLevel, lane, [&](int pos, int idx, int) {
+        const int k = atomicAdd(count, 1);
+        keys[k] = ((unsigned long long)pos << 32) | (unsigned)idx;
+    });
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)     (:45-129)
+ * single CTA, one warp per map point per pass, fixed-point iteration (see file header)
+ * ---------------------------------------------------------------------------------------------- */
+struct LocalArgs {
+    const float *projX, *projY, *projXR, *viewCos;
+    const int* predLevel;
+    const uint8_t* valid;
+    const int* nobs;
+    const uint8_t* mpDesc;
+    int nmp;
+    float th, nnratio;
+};
+
+__global__ void __launch_bounds__(1024) search_local_kernel(FrameIndexDev fi, LocalArgs a, int* __restrict__ obs,
+                                                            int* __restrict__ claim, int* __restrict__ minClaim,
+                                                            int* __restrict__ match, int* __restrict__ nmatches) {
+    __shared__ int changed;
+    __shared__ int total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int i = tid; i < a.nmp; i += blockDim.x) claim[i] = -1;
+    for (int k = tid; k < fi.n; k += blockDim.x) { minClaim[k] = INT_MAX; match[k] = -1; }
+    if (tid == 0) total = 0;
+    __syncthreads();
+    const bool bFactor = a.th != 1.0f;
+    for (int iter = 0; iter <= a.nmp; iter++) {
+        if (tid == 0) changed = 0;
+        __syncthreads();
+        for (int i = warp; i < a.nmp; i += nwarps) {
+            int result = -1;
+            if (a.valid[i]) {
+                const int lvl = a.predLevel[i];
+                float r = (double)a.viewCos[i] > 0.998 ? 2.5f : 4.0f;          /* RadiusByViewingCos :131-137 */
+                if (bFactor) r = __fmul_rn(r, a.th);
+                const float rad = __fmul_rn(r, fi.scale[lvl]);
+                const uint8_t* dMP = a.mpDesc + (size_t)i * 32;
+                const float projXR = a.projXR[i];
+                unsigned long long k1 = ~0ull, k2 = ~0ull;
+                for_features_in_area(fi, a.projX[i], a.projY[i], rad, lvl - 1, lvl, lane, [&](int pos, int idx, int oct) {
+                    if (obs[idx] > 0 || minClaim[idx] < i) return;               /* :87-89 (+ earlier matches :123) */
+                    const float ur = fi.uRight[idx];
+                    if (ur > 0) {
+                        const float er = fabsf(__fsub_rn(projXR, ur));
+                        if (er > rad) return;                                     /* :91-96 */
+                    }
+                    const int dist = hamming_rows(dMP, fi.desc + (size_t)idx * 32);
+                    const unsigned long long key = ((unsigned long long)dist << 48) | ((unsigned long long)pos << 28) |
+                                                   ((unsigned long long)oct << 20) | (unsigned)idx;
+                    if (key < k1) { k2 = k1; k1 = key; }
+                    else if (key < k2) k2 = key;
+                });
+                warp_two_min(k1, k2);
+                if (k1 != ~0ull) {
+                    const int bestDist = (int)(k1 >> 48), bestLevel = (int)((k1 >> 20) & 0xff), bestIdx = (int)(k1 & 0xfffff);
+                    const int bestDist2 = k2 != ~0ull ? (int)(k2 >> 48) : 256;
+                    const int bestLevel2 = k2 != ~0ull ? (int)((k2 >> 20) & 0xff) : -1;
+                    if (bestDist <= TH_HIGH) {
+                        if (!(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(a.nnratio, (float)bestDist2)))
+                            result = bestIdx;                                     /* :118-124 */
+                    }
+                }
+            }
+            if (lane == 0 && result != claim[i]) { claim[i] = result; changed = 1; }
+        }
+        __syncthreads();
+        if (!changed) break;
+        for (int k = tid; k < fi.n; k += blockDim.x) minClaim[k] = INT_MAX;
+        __syncthreads();
+        for (int i = tid; i < a.nmp; i += blockDim.x)
+            if (claim[i] >= 0 && a.nobs[i] > 0) atomicMin(&minClaim[claim[i]], i);
+        __syncthreads();
+    }
+    /* the last claimant of a keypoint owns it (F.mvpMapPoints[bestIdx]=pMP overwrites) */
+    for (int i = tid; i < a.nmp; i += blockDim.x)
+        if (claim[i] >= 0) { atomicMax(&match[claim[i]], i); atomicAdd(&total, 1); }
+    __syncthreads();
+    for (int k = tid; k < fi.n; k += blockDim.x)
+        if (match[k] >= 0) obs[k] = a.nobs[match[k]];
+    if (tid == 0) *nmatches = total;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, bMono)   (:1328-1471, search from :1378)
+ * ---------------------------------------------------------------------------------------------- */
+struct FrameArgs {
+    const float *u, *v, *invz, *lastAngle;
+    const int* lastOctave;
+    const uint8_t* valid;
+    const int* nobs;
+    const uint8_t* mpDesc;
+    int nlast;
+    float th, mbf;
+    int mode, checkOri, thHigh;
+};
+
+/* ComputeThreeMaxima :1602-1643 on bin counts */
+__device__ void three_maxima(const int* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < L; i++) {
+        const int s = histo[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+}
+
+__device__ __forceinline__ int rot_bin(float a1, float a2) {
+    /* :1434-1439: rot = a1 - a2; if (rot < 0) rot += 360; bin = round(rot * (1/30)) ; bin == 30 -> 0 */
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+__global__ void __launch_bounds__(1024) search_frame_kernel(FrameIndexDev fi, FrameArgs a, int* __restrict__ obs,
+                                                            int* __restrict__ claim, int* __restrict__ minClaim,
+                                                            int* __restrict__ match, int* __restrict__ nmatches) {
+    __shared__ int changed;
+    __shared__ int total;
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int keep[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int i = tid; i < a.nlast; i += blockDim.x) claim[i] = -1;
+    for (int k = tid; k < fi.n; k += blockDim.x) { minClaim[k] = INT_MAX; match[k] = -1; }
+    if (tid < HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) total = 0;
+    __syncthreads();
+    for (int iter = 0; iter <= a.nlast; iter++) {
+        if (tid == 0) changed = 0;
+        __syncthreads();
+        for (int i = warp; i < a.nlast; i += nwarps) {
+            int result = -1;
+            const float u = a.u[i], v = a.v[i];
+            if (a.valid[i] && !(u < fi.minX || u > fi.maxX) && !(v < fi.minY || v > fi.maxY)) {
+                const int oct = a.lastOctave[i];
+                const float radius = __fmul_rn(a.th, fi.scale[oct]);
+                int minL, maxL;
+                if (a.mode == 1) { minL = oct; maxL = -1; }                 /* forward  :1385-1386 */
+                else if (a.mode == 2) { minL = 0; maxL = oct; }             /* backward :1387-1388 */
+                else { minL = oct - 1; maxL = oct + 1; }
+                const float ur = __fsub_rn(u, __fmul_rn(a.mbf, a.invz[i]));
+                const uint8_t* dMP = a.mpDesc + (size_t)i * 32;
+                unsigned long long k1 = ~0ull;
+                for_features_in_area(fi, u, v, radius, minL, maxL, lane, [&](int pos, int idx, int) {
+                    if (obs[idx] > 0 || minClaim[idx] < i) return;
+                    const float uR = fi.uRight[idx];
+                    if (uR > 0) {
+                        const float er = fabsf(__fsub_rn(ur, uR));
+                        if (er > radius) return;
+                    }
+                    const int dist = hamming_rows(dMP, fi.desc + (size_t)idx * 32);
+                    const unsigned long long key = ((unsigned long long)dist << 48) | ((unsigned long long)pos << 24) | (unsigned)idx;
+                    k1 = key < k1 ? key : k1;
+                });
+                k1 = warp_min_u64(k1);
+                if (k1 != ~0ull && (int)(k1 >> 48) <= a.thHigh) result = (int)(k1 & 0xffffff);
+            }
+            if (lane == 0 && result != claim[i]) { claim[i] = result; changed = 1; }
+        }
+        __syncthreads();
+        if (!changed) break;
+        for (int k = tid; k < fi.n; k += blockDim.x) minClaim[k] = INT_MAX;
+        __syncthreads();
+        for (int i = tid; i < a.nlast; i += blockDim.x)
+            if (claim[i] >= 0 && a.nobs[i] > 0) atomicMin(&minClaim[claim[i]], i);
+        __syncthreads();
+    }
+    for (int i = tid; i < a.nlast; i += blockDim.x)
+        if (claim[i] >= 0) {
+            atomicMax(&match[claim[i]], i);
+            atomicAdd(&total, 1);
+            if (a.checkOri) atomicAdd(&hist[rot_bin(a.lastAngle[i], fi.kps[claim[i]].angle)], 1);
+        }
+    __syncthreads();
+    if (a.checkOri) {
+        if (tid == 0) three_maxima(hist, HISTO_LENGTH, keep[0], keep[1], keep[2]);
+        __syncthreads();
+        /* every claim in a rejected bin nulls its keypoint and decrements the count (:1455-1465) */
+        for (int i = tid; i < a.nlast; i += blockDim.x)
+            if (claim[i] >= 0) {
+                const int b = rot_bin(a.lastAngle[i], fi.kps[claim[i]].angle);
+                if (b != keep[0] && b != keep[1] && b != keep[2]) { match[claim[i]] = -2; atomicSub(&total, 1); }
+            }
+        __syncthreads();
+    }
+    for (int k = tid; k < fi.n; k += blockDim.x) {
+        const int m = match[k];
+        if (m >= 0) obs[k] = a.nobs[m];
+        else if (m == -2) { obs[k] = 0; match[k] = -1; }
+    }
+    if (tid == 0) *nmatches = total;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchForTriangulation (:657-823): one warp per keypoint entry of KF1's feature vector
+ * ---------------------------------------------------------------------------------------------- */
+struct TriArgs {
+    const viorb_keypoint *k1, *k2;
+    const uint8_t *d1, *d2;
+    const float *ur1, *ur2;
+    const uint8_t *mp1, *mp2;
+    const int *nodeId1, *nodePtr1, *idx1, *nodeId2, *nodePtr2, *idx2;
+    int n1, n2, nn1, nn2, nentries1;
+    float F12[9];
+    float ex, ey;
+    float scale2[12], sigma2[12];
+    int onlyStereo, checkOri;
+};
+
+__device__ __forceinline__ bool check_dist_epipolar(const viorb_keypoint& kp1, const viorb_keypoint& kp2, const float* F,
+                                                    const float* sigma2) {
+    /* :140-157, left-to-right single-rounded float arithmetic */
+    const float a = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, F[0]), __fmul_rn(kp1.y, F[3])), F[6]);
+    const float b = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, F[1]), __fmul_rn(kp1.y, F[4])), F[7]);
+    const float c = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, F[2]), __fmul_rn(kp1.y, F[5])), F[8]);
+    const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, kp2.x), __fmul_rn(b, kp2.y)), c);
+    const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+    if (den == 0) return false;
+    const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+    return (double)dsqr < __dmul_rn(3.84, (double)sigma2[kp2.octave]);
+}
+
+__global__ void __launch_bounds__(128) triangulation_kernel(const __grid_constant__ TriArgs a, int* __restrict__ matches12) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (e >= a.nentries1) return;
+    /* node f1 of entry e: last f with nodePtr1[f] <= e */
+    int lo = 0, hi = a.nn1 - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a.nodePtr1[mid] <= e) lo = mid; else hi = mid - 1;
+    }
+    const int node = a.nodeId1[lo];
+    /* same node in KF2 (the merge walk of :691-789 visits exactly the common node ids) */
+    int l2 = 0, h2 = a.nn2 - 1, f2 = -1;
+    while (l2 <= h2) {
+        const int mid = (l2 + h2) >> 1;
+        const int v = a.nodeId2[mid];
+        if (v == node) { f2 = mid; break; }
+        if (v < node) l2 = mid + 1; else h2 = mid - 1;
+    }
+    if (f2 < 0) return;
+    const int idx1 = a.idx1[e];
+    if (a.mp1[idx1]) return;                                    /* already a MapPoint :704-705 */
+    const bool bStereo1 = a.ur1[idx1] >= 0;
+    if (a.onlyStereo && !bStereo1) return;
+    const viorb_keypoint kp1 = a.k1[idx1];
+    const uint8_t* d1 = a.d1 + (size_t)idx1 * 32;
+    const int beg = a.nodePtr2[f2], end = a.nodePtr2[f2 + 1];
+    /* best = min distance, LAST candidate wins ties (dist > bestDist -> continue, :738) */
+    unsigned long long best = ~0ull;
+    for (int j = beg + lane; j < end; j += 32) {
+        const int idx2 = a.idx2[j];
+        if (a.mp2[idx2]) continue;
+        const bool bStereo2 = a.ur2[idx2] >= 0;
+        if (a.onlyStereo && !bStereo2) continue;
+        const int dist = hamming_rows(d1, a.d2 + (size_t)idx2 * 32);
+        if (dist > TH_LOW) continue;
+        const viorb_keypoint kp2 = a.k2[idx2];
+        if (!bStereo1 && !bStereo2) {
+            const float distex = __fsub_rn(a.ex, kp2.x), distey = __fsub_rn(a.ey, kp2.y);
+            if (__fadd_rn(__fmul_rn(distex, distex), __fmul_rn(distey, distey)) < __fmul_rn(100.f, a.scale2[kp2.octave])) continue;
+        }
+        if (!check_dist_epipolar(kp1, kp2, a.F12, a.sigma2)) continue;
+        const unsigned long long key = ((unsigned long long)dist << 48) | ((unsigned long long)(0xffffff - (j - beg)) << 24) |
+                                       (unsigned)idx2;
+        best = key < best ? key : best;
+    }
+    best = warp_min_u64(best);
+    if (lane == 0 && best != ~0ull) matches12[idx1] = (int)(best & 0xffffff);
+}
+
+__global__ void __launch_bounds__(1024) triangulation_finalize_kernel(const viorb_keypoint* __restrict__ k1,
+                                                                      const viorb_keypoint* __restrict__ k2, int n1,
+                                                                      int checkOri, int* __restrict__ matches12,
+                                                                      int* __restrict__ nmatches) {
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int keep[3];
+    __shared__ int total;
+    const int tid = threadIdx.x;
+    if (tid < HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) total = 0;
+    __syncthreads();
+    for (int i = tid; i < n1; i += blockDim.x)
+        if (matches12[i] >= 0) {
+            atomicAdd(&total, 1);
+            if (checkOri) atomicAdd(&hist[rot_bin(k1[i].angle, k2[matches12[i]].angle)], 1);
+        }
+    __syncthreads();
+    if (checkOri) {
+        if (tid == 0) three_maxima(hist, HISTO_LENGTH, keep[0], keep[1], keep[2]);
+        __syncthreads();
+        for (int i = tid; i < n1; i += blockDim.x)
+            if (matches12[i] >= 0) {
+                const int b = rot_bin(k1[i].angle, k2[matches12[i]].angle);
+                if (b != keep[0] && b != keep[1] && b != keep[2]) { matches12[i] = -1; atomicSub(&total, 1); }
+            }
+        __syncthreads();
+    }
+    if (tid == 0) *nmatches = total;
+}
+
+}  // namespace
+
+/* ------------------------------------------------------------------------------------------------ launchers */
+int viorb_launch_stereo(const StereoParams& p, const viorb_keypoint* d_kl, const uint8_t* d_dl,
+                        const viorb_keypoint* d_kr, const uint8_t* d_dr, int* d_scratch /* [2]: nMatched, median */,
+                        float* d_uRight, float* d_depth, int* d_sad, cudaStream_t s) {
+    if (p.nl <= 0) return 0;
+    cudaMemsetAsync(d_scratch, 0, 2 * sizeof(int), s);
+    stereo_match_kernel<<<(p.nl + 3) / 4, 128, 0, s>>>(p, d_kl, d_dl, d_kr, d_dr, d_uRight, d_depth, d_sad, d_scratch);
+    stereo_rank_kernel<<<(p.nl + 127) / 128, 128, 0, s>>>(d_sad, p.nl, d_scratch, d_scratch + 1);
+    stereo_filter_kernel<<<(p.nl + 127) / 128, 128, 0, s>>>(d_sad, p.nl, d_scratch + 1, d_uRight, d_depth);
+    return 3;
+}
+
+int viorb_launch_grid_build(const viorb_keypoint* d_kps, int n, float minX, float minY, float invW, float invH,
+                            int* d_cellOf, int* d_cellStart, int* d_cellItems, cudaStream_t s) {
+    grid_build_kernel<<<1, 1024, 0, s>>>(d_kps, n, minX, minY, invW, invH, d_cellOf, d_cellStart, d_cellItems);
+    return 1;
+}
+
+int viorb_launch_features_in_area(const FrameIndexDev& fi, float x, float y, float r, int minLevel, int maxLevel,
+                                  unsigned long long* d_keys, int* d_count, cudaStream_t s) {
+    cudaMemsetAsync(d_count, 0, sizeof(int), s);
+    features_in_area_kernel<<<1, 32, 0, s>>>(fi, x, y, r, minLevel, maxLevel, d_keys, d_count);
+    return 1;
+}
+
+int viorb_launch_search_local(const FrameIndexDev& fi, const float* projX, const float* projY, const float* projXR,
+                              const int* predLevel, const float* viewCos, const uint8_t* valid, const int* nobs,
+                              const uint8_t* mpDesc, int nmp, float th, float nnratio, int* d_obs, int* d_claim,
+                              int* d_minClaim, int* d_match, int* d_nmatches, cudaStream_t s) {
+    LocalArgs a;
+    a.projX = projX; a.projY = projY; a.projXR = projXR; a.viewCos = viewCos; a.predLevel = predLevel;
+    a.valid = valid; a.nobs = nobs; a.mpDesc = mpDesc; a.nmp = nmp; a.th = th; a.nnratio = nnratio;
+    search_local_kernel<<<1, 1024, 0, s>>>(fi, a, d_obs, d_claim, d_minClaim, d_match, d_nmatches);
+    return 1;
+}
+
+int viorb_launch_search_frame(const FrameIndexDev& fi, const float* u, const float* v, const float* invz,
+                              const int* lastOctave, const float* lastAngle, const uint8_t* valid, const int* nobs,
+                              const uint8_t* mpDesc, int nlast, float th, float mbf, int mode, int checkOri, int thHigh,
+                              int* d_obs, int* d_claim, int* d_minClaim, int* d_match, int* d_nmatches, cudaStream_t s) {
+    FrameArgs a;
+    a.u = u; a.v = v; a.invz = invz; a.lastAngle = lastAngle; a.lastOctave = lastOctave; a.valid = valid; a.nobs = nobs;
+    a.mpDesc = mpDesc; a.nlast = nlast; a.th = th; a.mbf = mbf; a.mode = mode; a.checkOri = checkOri; a.thHigh = thHigh;
+    search_frame_kernel<<<1, 1024, 0, s>>>(fi, a, d_obs, d_claim, d_minClaim, d_match, d_nmatches);
+    return 1;
+}
+
+int viorb_launch_triangulation(const viorb_keypoint* k1, const uint8_t* d1, const float* ur1, const uint8_t* mp1, int n1,
+                               const viorb_keypoint* k2, const uint8_t* d2, const float* ur2, const uint8_t* mp2, int n2,
+                               const int* nodeId1, const int* nodePtr1, const int* idx1, int nn1, int nentries1,
+                               const int* nodeId2, const int* nodePtr2, const int* idx2, int nn2, const float* F12,
+                               float ex, float ey, const float* scale2, const float* sigma2, int nlevels, int onlyStereo,
+                               int checkOri, int* d_matches12, int* d_nmatches, cudaStream_t s) {
+    TriArgs a;
+    a.k1 = k1; a.k2 = k2; a.d1 = d1; a.d2 = d2; a.ur1 = ur1; a.ur2 = ur2; a.mp1 = mp1; a.mp2 = mp2;
+    a.nodeId1 = nodeId1; a.nodePtr1 = nodePtr1; a.idx1 = idx1; a.nodeId2 = nodeId2; a.nodePtr2 = nodePtr2; a.idx2 = idx2;
+    a.n1 = n1; a.n2 = n2; a.nn1 = nn1; a.nn2 = nn2; a.nentries1 = nentries1;
+    for (int i = 0; i < 9; i++) a.F12[i] = F12[i];
+    a.ex = ex; a.ey = ey;
+    for (int i = 0; i < 12; i++) { a.scale2[i] = i < nlevels ? scale2[i] : 0.f; a.sigma2[i] = i < nlevels ? sigma2[i] : 0.f; }
+    a.onlyStereo = onlyStereo; a.checkOri = checkOri;
+    cudaMemsetAsync(d_matches12, 0xff, (size_t)n1 * sizeof(int), s);
+    int launches = 0;
+    if (nentries1 > 0 && nn1 > 0 && nn2 > 0) {
+        triangulation_kernel<<<(nentries1 + 3) / 4, 128, 0, s>>>(a, d_matches12);
+        launches++;
+    }
+    triangulation_finalize_kernel<<<1, 1024, 0, s>>>(k1, k2, n1, checkOri, d_matches12, d_nmatches);
+    return launches + 1;
+}
