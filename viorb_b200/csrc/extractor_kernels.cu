@@ -94,78 +94,59 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
 /* ------------------------------------------------------------------------------------------------
  * FAST-9/16 per cell with the iniThFAST -> minThFAST retry (:789-829, cv::FAST TYPE_9_16 + NMS).
  *
- * One CTA per cell.  The cell sub-image [iniX, maxX) x [iniY, maxY) is staged in shared memory; the
- * detection window is inset by 3 (cv::FAST never tests the 3-pixel rim).  For every window pixel the
- * threshold-independent corner score  S = max(max_arc min d, max_arc min -d) - 1  (cornerScore<16>) is
- * computed; a pixel is a corner at threshold t iff S >= t.  cv::FAST's 3x3 non-max suppression keeps a
- * corner iff its score is strictly greater than all 8 neighbours, where non-corners and pixels outside
- * the window count 0 -- which is "S_p >= t and S_p > S_n for all window neighbours", so one local-max
- * map serves both thresholds and the retry only re-filters by minThFAST.
+ * One CTA per cell.  The cell sub-image [iniX, maxX) x [iniY, maxY) is staged in shared memory with its
+ * detection window (inset 3: cv::FAST never tests the 3-pixel rim) on a 4-byte boundary.  Each thread
+ * scores FOUR horizontally adjacent pixels at once: the 16 ring samples are fetched as 32-bit words,
+ * split into two s16x2 registers (pixels 0/2 and 1/3) and the threshold-independent corner score
+ *     S = max( max_arc min_{9} d , max_arc min_{9} -d ) - 1          (cornerScore<16>)
+ * is evaluated with the packed 3-input DPX min/max (VIMNMX3.S16x2): min9 = min3(min3,min3,min3).
+ * A pixel is a corner at threshold t iff S >= t.  cv::FAST's 3x3 non-max suppression keeps a corner iff
+ * its score is strictly greater than all 8 neighbours, where non-corners and pixels outside the window
+ * count 0 -- i.e. "S_p >= t and S_p > S_n for all window neighbours", so one local-max map serves both
+ * thresholds and the per-cell retry (:812) only re-filters by minThFAST.
  * ---------------------------------------------------------------------------------------------- */
-#define FAST_TILE 68
-#define FAST_TSTRIDE 72
-#define FAST_SC 64
+#define FAST_ROWS 68            /* cell sub-image rows  (hCell + 6 <= 66) */
+#define FAST_TW 19              /* tile row stride in words: 1 lead byte + (wCell + 6 <= 66) bytes, padded */
+#define FAST_SCW 18             /* score row stride in words: 1 zero word + 15 quads + 1 zero word, padded */
 
-__device__ __forceinline__ int fast_score(const uint8_t* p /* centre, row stride FAST_TSTRIDE */, int minTh) {
-    const int v = p[0];
-    int d[16];
-    d[0] = v - p[3 * FAST_TSTRIDE];
-    d[1] = v - p[3 * FAST_TSTRIDE + 1];
-    d[2] = v - p[2 * FAST_TSTRIDE + 2];
-    d[3] = v - p[1 * FAST_TSTRIDE + 3];
-    d[4] = v - p[3];
-    d[5] = v - p[-1 * FAST_TSTRIDE + 3];
-    d[6] = v - p[-2 * FAST_TSTRIDE + 2];
-    d[7] = v - p[-3 * FAST_TSTRIDE + 1];
-    d[8] = v - p[-3 * FAST_TSTRIDE];
-    d[9] = v - p[-3 * FAST_TSTRIDE - 1];
-    d[10] = v - p[-2 * FAST_TSTRIDE - 2];
-    d[11] = v - p[-1 * FAST_TSTRIDE - 3];
-    d[12] = v - p[-3];
-    d[13] = v - p[1 * FAST_TSTRIDE - 3];
-    d[14] = v - p[2 * FAST_TSTRIDE - 2];
-    d[15] = v - p[3 * FAST_TSTRIDE - 1];
-    /* high-speed rejection at minTh: every 9-arc contains ring pixel k or k+8 for each k */
-    {
-        bool dark = true, bright = true;
-#pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-            dark = dark && (d[k] > minTh || d[k + 8] > minTh);
-            bright = bright && (d[k] < -minTh || d[k + 8] < -minTh);
-        }
-        if (!dark && !bright) return 0;
-    }
-    /* sliding 9-window min and max over the circular ring */
-    int mn2[16], mx2[16];
+__device__ __forceinline__ unsigned funnel_bytes(unsigned lo, unsigned hi, int sh) {
+    /* bytes sh..sh+3 of the 8-byte little-endian sequence lo|hi (sh in 0..3) */
+    return __byte_perm(lo, hi, 0x3210u + 0x1111u * (unsigned)sh);
+}
+
+/* packed score of two pixels (s16 lanes) from the 16 packed ring differences e[k] = ring_k - centre */
+__device__ __forceinline__ unsigned fast_score_s16x2(const unsigned (&e)[16]) {
+    unsigned mn3[16], mx3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        mn2[k] = min(d[k], d[(k + 1) & 15]);
-        mx2[k] = max(d[k], d[(k + 1) & 15]);
+        mn3[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+        mx3[k] = __vimax3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
     }
-    int mn4[16], mx4[16];
+    unsigned mn9[16], mx9[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
-        mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+        mn9[k] = __vimin3_s16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
+        mx9[k] = __vimax3_s16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
     }
-    int a = -256, b = 256;
+    /* a = max over arcs of min e (ring brighter), b = min over arcs of max e (ring darker) */
+    unsigned a = __vimax3_s16x2(mn9[0], mn9[1], mn9[2]), b = __vimin3_s16x2(mx9[0], mx9[1], mx9[2]);
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-        a = max(a, mn9);
-        b = min(b, mx9);
+    for (int k = 3; k < 15; k += 2) {
+        a = __vimax3_s16x2(a, mn9[k], mn9[k + 1]);
+        b = __vimin3_s16x2(b, mx9[k], mx9[k + 1]);
     }
-    const int s = max(a, -b) - 1;
-    return s >= minTh ? s : 0;
+    a = __vmaxs2(a, mn9[15]);
+    b = __vmins2(b, mx9[15]);
+    /* score = max(a, -b) - 1 */
+    return __vsub2(__vmaxs2(a, __vneg2(b)), 0x00010001u);
 }
 
 __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__ FrameGeom g,
                                                          const uint8_t* __restrict__ pyr,
                                                          uint32_t* __restrict__ cand, int* __restrict__ candCount,
                                                          int* __restrict__ status) {
-    __shared__ __align__(16) uint8_t tile[FAST_TILE * FAST_TSTRIDE];
-    __shared__ uint8_t sc[(FAST_SC + 2) * (FAST_SC + 2)];
+    __shared__ unsigned tile[FAST_ROWS * FAST_TW];
+    __shared__ unsigned sc[(FAST_ROWS - 4) * FAST_SCW];
     const int frame = blockIdx.y;
     int l = 0;
     while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].cellBase) l++;
@@ -180,53 +161,112 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     const int ch = min(iniY + L.hCell + 6, maxBorderY) - iniY;
     const int ww = cw - 6, wh = ch - 6;      /* detection window */
     if (ww <= 0 || wh <= 0) return;
-
-    const uint8_t* roi = pyr + (size_t)frame * g.pyrFrameBytes + L.pyrOff + (size_t)VIORB_EDGE * L.step + VIORB_ROI_X0;
     const int tid = threadIdx.x;
-    for (int i = tid; i < cw * ch; i += blockDim.x) {
-        const int y = i / cw, x = i - y * cw;
-        tile[y * FAST_TSTRIDE + x] = roi[(size_t)(iniY + y) * L.step + iniX + x];
+    const int NQ = (ww + 3) >> 2;            /* quads per window row */
+    const int NW = NQ + 2;                   /* tile words per row: quads + one word each side */
+
+    /* stage: tile byte (4 + x) of row y = level pixel (iniX + 3 + x, iniY + y); word w covers x in [4w-4, 4w) */
+    {
+        const uint8_t* roi = pyr + (size_t)frame * g.pyrFrameBytes + L.pyrOff + (size_t)VIORB_EDGE * L.step + VIORB_ROI_X0;
+        const int gx0 = iniX + 3 - 4;                        /* level x of tile byte 0 (>= 15) */
+        const int sh = gx0 & 3;
+        const uint8_t* base = roi + (size_t)iniY * L.step + (gx0 - sh);   /* 4-byte aligned */
+        for (int i = tid; i < ch * NW; i += blockDim.x) {
+            const int y = i / NW, w = i - y * NW;
+            const unsigned* src = reinterpret_cast<const unsigned*>(base + (size_t)y * L.step) + w;
+            const unsigned lo = __ldg(src), hi = __ldg(src + 1);
+            tile[y * FAST_TW + w] = funnel_bytes(lo, hi, sh);
+        }
+        for (int i = tid; i < (wh + 2) * FAST_SCW; i += blockDim.x) sc[i] = 0;
     }
-    const int scw = ww + 2;
-    for (int i = tid; i < scw * (wh + 2); i += blockDim.x) sc[i] = 0;
     __syncthreads();
-    for (int i = tid; i < ww * wh; i += blockDim.x) {
-        const int y = i / ww, x = i - y * ww;
-        sc[(y + 1) * scw + x + 1] = (uint8_t)fast_score(&tile[(y + 3) * FAST_TSTRIDE + x + 3], g.minTh);
+
+    /* scores, four pixels per task */
+    const unsigned minThP = (unsigned)g.minTh * 0x00010001u;
+    const int ntask = NQ * wh;
+    for (int t = tid; t < ntask; t += blockDim.x) {
+        const int y = t / NQ, q = t - y * NQ;
+        const unsigned* row = &tile[(y + 3) * FAST_TW + q];   /* words: [q] = x-4..x-1, [q+1] = x..x+3, [q+2] = x+4..x+7 */
+        unsigned eA[16], eB[16];
+        {
+            const unsigned cw4 = row[1];
+            const unsigned nvA = __vneg2(__byte_perm(cw4, 0, 0x4240)), nvB = __vneg2(__byte_perm(cw4, 0, 0x4341));
+#define RING(k, dy, dx)                                                                              \
+            {                                                                                        \
+                const unsigned* r_ = row + (dy) * FAST_TW;                                          \
+                const unsigned w_ = (dx) == 0 ? r_[1]                                                \
+                                   : (dx) > 0 ? funnel_bytes(r_[1], r_[2], (dx))                     \
+                                              : funnel_bytes(r_[0], r_[1], 4 + (dx));                \
+                eA[k] = __vadd2(__byte_perm(w_, 0, 0x4240), nvA);                                    \
+                eB[k] = __vadd2(__byte_perm(w_, 0, 0x4341), nvB);                                    \
+            }
+            RING(0, 3, 0) RING(1, 3, 1) RING(2, 2, 2) RING(3, 1, 3) RING(4, 0, 3) RING(5, -1, 3) RING(6, -2, 2) RING(7, -3, 1)
+            RING(8, -3, 0) RING(9, -3, -1) RING(10, -2, -2) RING(11, -1, -3) RING(12, 0, -3) RING(13, 1, -3) RING(14, 2, -2)
+            RING(15, 3, -1)
+#undef RING
+        }
+        /* high-speed rejection: every 9-arc contains one of the compass points 0,4,8,12, so a quad whose
+         * compass differences all stay within +-minTh holds no corner at any threshold >= minTh */
+        const unsigned hi = __vmaxs2(__vimax3_s16x2(eA[0], eA[4], eA[8]), __vimax3_s16x2(eB[0], eB[4], eB[8]));
+        const unsigned lo = __vmins2(__vimin3_s16x2(eA[0], eA[4], eA[8]), __vimin3_s16x2(eB[0], eB[4], eB[8]));
+        const unsigned hi2 = __vmaxs2(hi, __vmaxs2(eA[12], eB[12])), lo2 = __vmins2(lo, __vmins2(eA[12], eB[12]));
+        if (__vmaxs2(hi2, minThP) == minThP && __vmins2(lo2, __vneg2(minThP)) == __vneg2(minThP)) continue;
+        unsigned sA = fast_score_s16x2(eA), sB = fast_score_s16x2(eB);
+        /* keep S >= minTh, else 0 (lane-wise) */
+        sA &= __vcmpges2(sA, minThP);
+        sB &= __vcmpges2(sB, minThP);
+        unsigned word = sA | (sB << 8);                       /* bytes = pixels x, x+1, x+2, x+3 */
+        const int x = q * 4;
+        if (x + 4 > ww) word &= 0xffffffffu >> (8 * (x + 4 - ww));   /* beyond the window: not a corner */
+        sc[(y + 1) * FAST_SCW + q + 1] = word;
     }
     __syncthreads();
-    /* local maxima + count at iniThFAST */
-    unsigned lmBits = 0;      /* one bit per pixel handled by this thread (<= 32 iterations) */
-    int nIni = 0;
-    int it = 0;
-    for (int i = tid; i < ww * wh; i += blockDim.x, it++) {
-        const int y = i / ww, x = i - y * ww;
-        const uint8_t* q = &sc[(y + 1) * scw + x + 1];
-        const int s = q[0];
-        bool lm = s > 0 && s > q[-1] && s > q[1] && s > q[-scw - 1] && s > q[-scw] && s > q[-scw + 1] &&
-                  s > q[scw - 1] && s > q[scw] && s > q[scw + 1];
-        if (lm) {
-            lmBits |= 1u << it;
-            if (s >= g.iniTh) nIni++;
+
+    /* 3x3 local maxima (window-clipped) + count at iniThFAST */
+    const uint8_t* scb = reinterpret_cast<const uint8_t*>(sc);
+    unsigned lmBits = 0;      /* 4 bits per task handled by this thread */
+    int nIni = 0, it = 0;
+    for (int t = tid; t < ntask; t += blockDim.x, it++) {
+        const int y = t / NQ, q = t - y * NQ;
+        const unsigned word = sc[(y + 1) * FAST_SCW + q + 1];
+        if (word == 0) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int s = (word >> (8 * j)) & 0xff;
+            if (s == 0) continue;
+            const uint8_t* p = scb + ((y + 1) * FAST_SCW + q + 1) * 4 + j;
+            const bool lm = s > p[-1] && s > p[1] && s > p[-FAST_SCW * 4 - 1] && s > p[-FAST_SCW * 4] && s > p[-FAST_SCW * 4 + 1] &&
+                            s > p[FAST_SCW * 4 - 1] && s > p[FAST_SCW * 4] && s > p[FAST_SCW * 4 + 1];
+            if (lm) {
+                lmBits |= 1u << (4 * it + j);
+                if (s >= g.iniTh) nIni++;
+            }
         }
     }
     const int total = __syncthreads_count(nIni > 0);
     const int th = total > 0 ? g.iniTh : g.minTh;     /* retry with minThFAST only if the cell is empty (:812) */
-    it = 0;
+    if (lmBits == 0) return;
     int* counter = candCount + frame * g.nlevels + l;
     uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
-    for (int i = tid; i < ww * wh; i += blockDim.x, it++) {
-        if (!(lmBits >> it & 1u)) continue;
-        const int y = i / ww, x = i - y * ww;
-        const int s = sc[(y + 1) * scw + x + 1];
-        if (s < th) continue;
-        const int pos = atomicAdd(counter, 1);
-        if (pos < L.candCap) {
-            /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
-            const uint32_t X = x + 3 + cj * L.wCell, Y = y + 3 + ci * L.hCell;
-            out[pos] = X | (Y << 12) | ((uint32_t)s << 24);
-        } else {
-            atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
+    it = 0;
+    for (int t = tid; t < ntask; t += blockDim.x, it++) {
+        const unsigned bits4 = (lmBits >> (4 * it)) & 0xfu;
+        if (!bits4) continue;
+        const int y = t / NQ, q = t - y * NQ;
+        const unsigned word = sc[(y + 1) * FAST_SCW + q + 1];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (!(bits4 >> j & 1u)) continue;
+            const unsigned s = (word >> (8 * j)) & 0xff;
+            if ((int)s < th) continue;
+            const int pos = atomicAdd(counter, 1);
+            if (pos < L.candCap) {
+                /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
+                const uint32_t X = q * 4 + j + 3 + cj * L.wCell, Y = y + 3 + ci * L.hCell;
+                out[pos] = X | (Y << 12) | (s << 24);
+            } else {
+                atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
+            }
         }
     }
 }
@@ -573,14 +613,15 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const __grid_consta
  * border rule), blurred there with the OpenCV >= 3.4 fixed-point taps [18 34 48 56 48 34 18]/256,
  * and sampled at the 512 steered pattern points.  The blurred level image never exists in HBM.
  * ---------------------------------------------------------------------------------------------- */
-#define DESC_WARPS 4
+#define DESC_WARPS 8
 #define PR 21                 /* patch radius */
-#define PW 43                 /* patch width */
-#define PSTRIDE 44
+#define PROWS 43              /* patch rows / columns */
+#define PWORDS 12             /* patch row stride in 32-bit words (48 bytes, 43 used) */
 #define BW 37                 /* blurred width (radius 18) */
-#define HSTRIDE 38
+#define HT_STRIDE 44          /* u16 per column of the transposed horizontal-pass buffer (43 rows + pad) */
+#define VSTRIDE 40            /* bytes per row of the blurred patch */
 
-__constant__ int8_t c_pattern[1024] = VIORB_ORB_PATTERN_INIT;
+__device__ __align__(16) const int8_t d_pattern[1024] = VIORB_ORB_PATTERN_INIT;   /* read as 2 x uint4 per lane */
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 /* cv::fastAtan2 (degrees), OpenCV core mathfuncs_core atan_f32 polynomial, no FMA */
@@ -661,9 +702,9 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
                                                                           uint8_t* __restrict__ desc, int cap,
                                                                           int32_t* __restrict__ counts,
                                                                           int* __restrict__ status) {
-    __shared__ __align__(16) uint8_t patch[DESC_WARPS][PW * PSTRIDE];
-    __shared__ __align__(16) uint16_t hb[DESC_WARPS][PW * HSTRIDE];
-    __shared__ __align__(16) uint8_t vb[DESC_WARPS][BW * HSTRIDE];
+    /* per warp: patch (43 x 12 words; later reused for the blurred 37x37 bytes) + transposed H-pass buffer */
+    __shared__ __align__(16) unsigned patchW[DESC_WARPS][PROWS * PWORDS];
+    __shared__ __align__(16) unsigned hbW[DESC_WARPS][BW * HT_STRIDE / 2];
     const int frame = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * DESC_WARPS + warp;
@@ -687,28 +728,36 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
     const uint32_t key = sel[(size_t)frame * g.selPerFrame + L.selBase + idx];
     const int kx = key & 0xfff, ky = (key >> 12) & 0xfff, score = key >> 24;
     const uint8_t* roi = pyr + (size_t)frame * g.pyrFrameBytes + L.pyrOff + (size_t)VIORB_EDGE * L.step + VIORB_ROI_X0;
-    uint8_t* P = patch[warp];
-    uint16_t* Hb = hb[warp];
-    uint8_t* Vb = vb[warp];
-    /* stage the 43x43 neighbourhood */
-    for (int i = lane; i < PW * PW; i += 32) {
-        const int r = i / PW, c = i - r * PW;
-        P[r * PSTRIDE + c] = roi[(ptrdiff_t)(ky - PR + r) * L.step + (kx - PR + c)];
+    unsigned* P = patchW[warp];
+    unsigned* Hw = hbW[warp];
+    /* stage the 43x43 neighbourhood as aligned words: patch byte (r, c) = level pixel (kx-21+c, ky-21+r) */
+    {
+        const int gx0 = kx - PR;
+        const int sh = gx0 & 3;
+        const uint8_t* base = roi + (ptrdiff_t)(ky - PR) * L.step + (gx0 - sh);    /* 4-byte aligned */
+        for (int i = lane; i < PROWS * PWORDS; i += 32) {
+            const int r = i / PWORDS, w = i - r * PWORDS;
+            const unsigned* src = reinterpret_cast<const unsigned*>(base + (ptrdiff_t)r * L.step) + w;
+            P[i] = funnel_bytes(__ldg(src), __ldg(src + 1), sh);
+        }
     }
+    /* this lane's 8 binary tests (16 sampling points) */
+    const uint4 pat0 = __ldg(reinterpret_cast<const uint4*>(d_pattern) + 2 * lane);
+    const uint4 pat1 = __ldg(reinterpret_cast<const uint4*>(d_pattern) + 2 * lane + 1);
     __syncwarp();
     /* IC_Angle: lane v+15 sums row v of the circular patch */
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int v = lane - 15;
         const int d = c_umax[v < 0 ? -v : v];
-        const uint8_t* row = &P[(PR + v) * PSTRIDE + PR];
-        int s = 0;
+        const uint8_t* row = reinterpret_cast<const uint8_t*>(P) + (PR + v) * (PWORDS * 4) + PR;
+        int sacc = 0;
         for (int u = -d; u <= d; u++) {
             const int val = row[u];
             m10 += u * val;
-            s += val;
+            sacc += val;
         }
-        m01 = v * s;
+        m01 = v * sacc;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -716,36 +765,66 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
         m01 += __shfl_xor_sync(0xffffffffu, m01, o);
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
-    /* separable 7-tap blur in shared memory */
-    for (int i = lane; i < PW * BW; i += 32) {
-        const int r = i / BW, c = i - r * BW;
-        const uint8_t* s = &P[r * PSTRIDE + c];
-        Hb[r * HSTRIDE + c] = (uint16_t)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+    /* horizontal 7-tap pass, four outputs per task, two IDP.4A each; the 16-bit sums (exact: the taps sum
+     * to 256) are stored transposed so that the vertical pass reads vertically adjacent pairs as words */
+    {
+        const unsigned KLO = 18u | (34u << 8) | (48u << 16) | (56u << 24), KHI = 48u | (34u << 8) | (18u << 16);
+        unsigned short* Hs = reinterpret_cast<unsigned short*>(Hw);
+        for (int t = lane; t < PROWS * 10; t += 32) {
+            const int r = t / 10, j = t - r * 10;
+            const unsigned w0 = P[r * PWORDS + j], w1 = P[r * PWORDS + j + 1], w2 = P[r * PWORDS + j + 2];
+            const unsigned h0 = __dp4a(w0, KLO, __dp4a(w1, KHI, 0u));
+            const unsigned h1 = __dp4a(funnel_bytes(w0, w1, 1), KLO, __dp4a(funnel_bytes(w1, w2, 1), KHI, 0u));
+            const unsigned h2 = __dp4a(funnel_bytes(w0, w1, 2), KLO, __dp4a(funnel_bytes(w1, w2, 2), KHI, 0u));
+            const unsigned h3 = __dp4a(funnel_bytes(w0, w1, 3), KLO, __dp4a(funnel_bytes(w1, w2, 3), KHI, 0u));
+            const int c = 4 * j;
+            Hs[c * HT_STRIDE + r] = (unsigned short)h0;
+            if (c + 1 < BW) Hs[(c + 1) * HT_STRIDE + r] = (unsigned short)h1;
+            if (c + 2 < BW) Hs[(c + 2) * HT_STRIDE + r] = (unsigned short)h2;
+            if (c + 3 < BW) Hs[(c + 3) * HT_STRIDE + r] = (unsigned short)h3;
+        }
     }
     __syncwarp();
-    for (int i = lane; i < BW * BW; i += 32) {
-        const int r = i / BW, c = i - r * BW;
-        const uint16_t* s = &Hb[r * HSTRIDE + c];
-        const unsigned acc = 18u * (s[0] + s[6 * HSTRIDE]) + 34u * (s[HSTRIDE] + s[5 * HSTRIDE]) +
-                             48u * (s[2 * HSTRIDE] + s[4 * HSTRIDE]) + 56u * s[3 * HSTRIDE];
-        Vb[r * HSTRIDE + c] = (uint8_t)((acc + 32768u) >> 16);
+    /* vertical pass: a task walks half a column with a sliding window of four words (8 rows); each pair of
+     * output rows shares the window.  out = (sum + 32768) >> 16, GaussianBlur's fixed-point rounding */
+    uint8_t* Vb = reinterpret_cast<uint8_t*>(P);       /* the patch is dead now */
+    {
+        const unsigned E01 = 18u | (34u << 8), E23 = 48u | (56u << 8), E45 = 48u | (34u << 8), E6 = 18u;   /* even row */
+        const unsigned O0 = 18u << 8, O12 = 34u | (48u << 8), O34 = 56u | (48u << 8), O56 = 34u | (18u << 8);  /* odd row */
+        for (int t = lane; t < BW * 2; t += 32) {
+            const int c = t >> 1, half = t & 1;
+            const int r0 = half ? 20 : 0, r1 = half ? BW : 20;
+            const unsigned* col = Hw + c * (HT_STRIDE / 2) + (r0 >> 1);
+            unsigned a = col[0], b = col[1], cc = col[2];
+            for (int r = r0; r < r1; r += 2) {
+                const unsigned d = col[((r - r0) >> 1) + 3];
+                const unsigned ve = __dp2a_lo(a, E01, __dp2a_lo(b, E23, __dp2a_lo(cc, E45, __dp2a_lo(d, E6, 32768u))));
+                Vb[r * VSTRIDE + c] = (uint8_t)(ve >> 16);
+                if (r + 1 < r1) {
+                    const unsigned vo = __dp2a_lo(a, O0, __dp2a_lo(b, O12, __dp2a_lo(cc, O34, __dp2a_lo(d, O56, 32768u))));
+                    Vb[(r + 1) * VSTRIDE + c] = (uint8_t)(vo >> 16);
+                }
+                a = b; b = cc; cc = d;
+            }
+        }
     }
     __syncwarp();
     /* steered BRIEF: lane i produces descriptor byte i (:123-144) */
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     float a, b;
     sincosf_glibc(__fmul_rn(angle, factorPI), &b, &a);
-    const uint8_t* centre = &Vb[18 * HSTRIDE + 18];
+    const uint8_t* centre = &Vb[18 * VSTRIDE + 18];
+    const unsigned pw[8] = {pat0.x, pat0.y, pat0.z, pat0.w, pat1.x, pat1.y, pat1.z, pat1.w};
     unsigned val = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const int8_t* pt = &c_pattern[(lane * 8 + k) * 4];
-        const float x0 = (float)pt[0], y0 = (float)pt[1], x1 = (float)pt[2], y1 = (float)pt[3];
+        const float x0 = (float)(int8_t)(pw[k] & 0xff), y0 = (float)(int8_t)((pw[k] >> 8) & 0xff);
+        const float x1 = (float)(int8_t)((pw[k] >> 16) & 0xff), y1 = (float)(int8_t)(pw[k] >> 24);
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
         const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
         const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = centre[r0 * HSTRIDE + c0], t1 = centre[r1 * HSTRIDE + c1];
+        const int t0 = centre[r0 * VSTRIDE + c0], t1 = centre[r1 * VSTRIDE + c1];
         val |= (unsigned)(t0 < t1) << k;
     }
     desc[((size_t)frame * cap + slot) * 32 + lane] = (uint8_t)val;
