@@ -380,8 +380,9 @@ int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, in
     if (nfeatures <= 0 || nlevels < 1 || nlevels > VIORB_MAX_LEVELS || !(scale_factor > 1.0f) || ini < mn || mn < 1 || ini > 255)
         return fail(VIORB_ERR_INVALID, "bad ORB parameters (nfeatures %d, scale %f, levels %d, FAST %d/%d)", nfeatures,
                     scale_factor, nlevels, ini, mn);
-    if (scale_factor == 2.0f)
-        return fail(VIORB_ERR_UNSUPPORTED, "scaleFactor == 2 takes cv::resize's INTER_AREA fast path; not implemented");
+    if (scale_factor > 1.5f)
+        return fail(VIORB_ERR_UNSUPPORTED, "scaleFactor > 1.5 is outside the pyramid kernel's tile envelope "
+                                           "(and 2.0 would take cv::resize's INTER_AREA path); shipped configs use 1.2");
     viorb_extractor* e = new (std::nothrow) viorb_extractor();
     if (!e) return fail(VIORB_ERR_INVALID, "out of host memory");
     e->ctx = ctx;

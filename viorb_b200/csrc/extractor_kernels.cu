@@ -55,40 +55,95 @@ __global__ void __launch_bounds__(128) pyr_level0_kernel(const __grid_constant__
  * copyMakeBorder(..., BORDER_REFLECT_101 + BORDER_ISOLATED)                     (:1120-1123)
  * cv::resize 8-bit fixed point: T = S[sx]*a0 + S[sx+1]*a1 ; D = (((b0*(T0>>4))>>16) + ((b1*(T1>>4))>>16) + 2) >> 2
  * The border pixels are produced by evaluating the same expression at the reflected ROI coordinate.
+ *
+ * One CTA = a 128 x 32 tile of the stored (padded) level: the source rectangle it needs (about 1.2x
+ * larger) is staged in shared memory with 16-byte loads; each thread owns four adjacent output columns
+ * (their x coefficients live in registers) and walks eight rows, writing one 32-bit word per row.
  * ---------------------------------------------------------------------------------------------- */
+#define RZ_TW 128               /* tile width in stored bytes */
+#define RZ_TH 32                /* tile height in stored rows */
+#define RZ_SSTRIDE 224          /* staged source row stride (bytes): 128*1.5 + 1 + 15, rounded up to 16 */
+#define RZ_SROWS 52             /* staged source rows: 32*1.5 + 2, padded (scaleFactor <= 1.5) */
+
+__device__ __forceinline__ void reflected_range(int a, int b, int n, int& dmin, int& dmax) {
+    /* min / max of reflect101(i, n) over i in [a, b], with -19 <= a <= b <= n+18 */
+    const int ra = reflect101(a, n), rb = reflect101(b, n);
+    dmin = (a <= 0 && b >= 0) ? 0 : min(ra, rb);
+    dmax = (a <= n - 1 && b >= n - 1) ? n - 1 : max(ra, rb);
+}
+
 __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__ FrameGeom g, int level,
                                                          ResizeTables t, uint8_t* __restrict__ pyr) {
+    __shared__ __align__(16) uint8_t src[RZ_SROWS * RZ_SSTRIDE];
     const LevelGeom& L = g.lv[level];
     const LevelGeom& P = g.lv[level - 1];
-    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = blockIdx.y;
     const int frame = blockIdx.z;
-    if (wi * 4 >= L.step) return;
+    const int tid = threadIdx.x;
     uint8_t* base = pyr + (size_t)frame * g.pyrFrameBytes;
-    const int dy = reflect101(row - VIORB_EDGE, L.h);
-    const int sy = t.yofs[L.ytab + dy];
-    const int b0 = t.yb[2 * (L.ytab + dy)], b1 = t.yb[2 * (L.ytab + dy) + 1];
-    const int sy0 = min(max(sy, 0), P.h - 1), sy1 = min(max(sy + 1, 0), P.h - 1);
-    const uint8_t* S0 = base + P.pyrOff + (size_t)(sy0 + VIORB_EDGE) * P.step + VIORB_ROI_X0;
-    const uint8_t* S1 = base + P.pyrOff + (size_t)(sy1 + VIORB_EDGE) * P.step + VIORB_ROI_X0;
-    uint32_t word = 0;
+    /* tile in ROI coordinates of level l: columns [xa, xa+128), rows [ya, ya+32) */
+    const int xa = blockIdx.x * RZ_TW - VIORB_ROI_X0, ya = blockIdx.y * RZ_TH - VIORB_EDGE;
+    const int xlo = max(xa, -VIORB_EDGE), xhi = min(xa + RZ_TW - 1, L.w + VIORB_EDGE - 1);
+    const int ylo = ya, yhi = min(ya + RZ_TH - 1, L.h + VIORB_EDGE - 1);
+    const int stepWords = L.step >> 2;
+    const int wi = blockIdx.x * (RZ_TW / 4) + (tid & 31);          /* stored word of this thread */
+    if (xlo > xhi) {                                                  /* only alignment padding: write zeros */
+        if (wi < stepWords)
+            for (int r = (tid >> 5) * 8; r < (tid >> 5) * 8 + 8; r++)
+                if (ya + r <= yhi) reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(ya + r + VIORB_EDGE) * L.step)[wi] = 0;
+        return;
+    }
+    int dxmin, dxmax, dymin, dymax;
+    reflected_range(xlo, xhi, L.w, dxmin, dxmax);
+    reflected_range(ylo, yhi, L.h, dymin, dymax);
+    /* source rectangle (level l-1 ROI coordinates), x origin aligned down to 16 bytes */
+    const int sx0 = (int)t.xofs[L.xtab + dxmin] & ~15;
+    const int sx1 = min((int)t.xofs[L.xtab + dxmax] + 1, P.w - 1);
+    const int sy0 = min((int)t.yofs[L.ytab + dymin], P.h - 1);
+    const int sy1 = min((int)t.yofs[L.ytab + dymax] + 1, P.h - 1);
+    const int nvec = ((sx1 - sx0) >> 4) + 1;                         /* 16-byte vectors per staged row */
+    const int nrow = sy1 - sy0 + 1;
+    {
+        const uint8_t* sroi = base + P.pyrOff + (size_t)VIORB_EDGE * P.step + VIORB_ROI_X0;   /* 16-byte aligned */
+        for (int i = tid; i < nrow * nvec; i += 128) {
+            const int r = i / nvec, v = i - r * nvec;
+            const uint4 val = *reinterpret_cast<const uint4*>(sroi + (size_t)(sy0 + r) * P.step + sx0 + 16 * v);
+            *reinterpret_cast<uint4*>(&src[r * RZ_SSTRIDE + 16 * v]) = val;
+        }
+    }
+    /* this thread's four output columns */
+    int so[4], so1[4], a0[4], a1[4];
+    bool ok[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int x = wi * 4 + j - VIORB_ROI_X0;
-        uint32_t v = 0;
-        if (x >= -VIORB_EDGE && x < L.w + VIORB_EDGE) {
-            const int dx = reflect101(x, L.w);
-            const int sx = t.xofs[L.xtab + dx];
-            const int a0 = t.xa[2 * (L.xtab + dx)], a1 = t.xa[2 * (L.xtab + dx) + 1];
-            const int sx1 = min(sx + 1, P.w - 1);
-            const int T0 = S0[sx] * a0 + S0[sx1] * a1;
-            const int T1 = S1[sx] * a0 + S1[sx1] * a1;
-            v = (uint32_t)((((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2) & 0xffu;
-        }
-        word |= v << (8 * j);
+        const int x = xa + (tid & 31) * 4 + j;
+        ok[j] = x >= -VIORB_EDGE && x < L.w + VIORB_EDGE;
+        const int dx = ok[j] ? reflect101(x, L.w) : dxmin;
+        const int sx = t.xofs[L.xtab + dx];
+        so[j] = sx - sx0;
+        so1[j] = min(sx + 1, P.w - 1) - sx0;
+        a0[j] = t.xa[2 * (L.xtab + dx)];
+        a1[j] = t.xa[2 * (L.xtab + dx) + 1];
     }
-    uint8_t* dst = base + L.pyrOff + (size_t)row * L.step;
-    reinterpret_cast<uint32_t*>(dst)[wi] = word;
+    __syncthreads();
+    if (wi >= stepWords) return;
+    for (int r = (tid >> 5) * 8; r < (tid >> 5) * 8 + 8; r++) {
+        const int y = ya + r;
+        if (y > yhi) break;
+        const int dy = reflect101(y, L.h);
+        const int sy = t.yofs[L.ytab + dy];
+        const int b0 = t.yb[2 * (L.ytab + dy)], b1 = t.yb[2 * (L.ytab + dy) + 1];
+        const uint8_t* S0 = &src[(min(sy, P.h - 1) - sy0) * RZ_SSTRIDE];
+        const uint8_t* S1 = &src[(min(sy + 1, P.h - 1) - sy0) * RZ_SSTRIDE];
+        uint32_t word = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int T0 = S0[so[j]] * a0[j] + S0[so1[j]] * a1[j];
+            const int T1 = S1[so[j]] * a0[j] + S1[so1[j]] * a1[j];
+            const uint32_t v = (uint32_t)((((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2) & 0xffu;
+            word |= (ok[j] ? v : 0u) << (8 * j);
+        }
+        reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(y + VIORB_EDGE) * L.step)[wi] = word;
+    }
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -114,13 +169,36 @@ __device__ __forceinline__ unsigned funnel_bytes(unsigned lo, unsigned hi, int s
     return __byte_perm(lo, hi, 0x3210u + 0x1111u * (unsigned)sh);
 }
 
-/* packed score of two pixels (s16 lanes) from the 16 packed ring differences e[k] = ring_k - centre */
-__device__ __forceinline__ unsigned fast_score_s16x2(const unsigned (&e)[16]) {
+/* ring sample k of four adjacent pixels as two s16x2 registers (A = pixels 0,2; B = pixels 1,3), raw grey
+ * values.  row = &tile word holding x-4..x-1 of the centre row; ring offsets are compile-time constants. */
+#define FAST_RING_LIST(OP)                                                                            \
+    OP(0, 3, 0) OP(1, 3, 1) OP(2, 2, 2) OP(3, 1, 3) OP(4, 0, 3) OP(5, -1, 3) OP(6, -2, 2) OP(7, -3, 1)    \
+    OP(8, -3, 0) OP(9, -3, -1) OP(10, -2, -2) OP(11, -1, -3) OP(12, 0, -3) OP(13, 1, -3) OP(14, 2, -2) OP(15, 3, -1)
+
+__device__ __forceinline__ void fast_load_ring(const unsigned* row, unsigned (&rA)[16], unsigned (&rB)[16]) {
+#define RING(k, dy, dx)                                                                                \
+    {                                                                                                  \
+        const unsigned* r_ = row + (dy) * FAST_TW;                                                    \
+        const unsigned w_ = (dx) == 0 ? r_[1] : (dx) > 0 ? funnel_bytes(r_[1], r_[2], (dx))           \
+                                                          : funnel_bytes(r_[0], r_[1], 4 + (dx));      \
+        rA[k] = __byte_perm(w_, 0, 0x4240);                                                            \
+        rB[k] = __byte_perm(w_, 0, 0x4341);                                                            \
+    }
+    FAST_RING_LIST(RING)
+#undef RING
+}
+
+/* cornerScore<16> of two pixels (s16 lanes) from the raw ring samples r[k] and the centre value v:
+ *   S = max( max_arc min_9 (r - v), max_arc min_9 (v - r) ) - 1 = max(a - v, v - b) - 1
+ * with a = max_arc min_9 r, b = min_arc max_9 r  (the centre is constant over the ring, so the 9-window
+ * min/max trees run on the raw samples: min9 = min3(min3, min3, min3) with VIMNMX3.S16x2).
+ * Returns relu(S - (minTh - 1)): zero iff the pixel is not a corner at minTh, order preserving otherwise. */
+__device__ __forceinline__ unsigned fast_score_s16x2(const unsigned (&r)[16], unsigned v, unsigned negBias) {
     unsigned mn3[16], mx3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        mn3[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
-        mx3[k] = __vimax3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+        mn3[k] = __vimin3_s16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+        mx3[k] = __vimax3_s16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
     }
     unsigned mn9[16], mx9[16];
 #pragma unroll
@@ -128,7 +206,6 @@ __device__ __forceinline__ unsigned fast_score_s16x2(const unsigned (&e)[16]) {
         mn9[k] = __vimin3_s16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
         mx9[k] = __vimax3_s16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
     }
-    /* a = max over arcs of min e (ring brighter), b = min over arcs of max e (ring darker) */
     unsigned a = __vimax3_s16x2(mn9[0], mn9[1], mn9[2]), b = __vimin3_s16x2(mx9[0], mx9[1], mx9[2]);
 #pragma unroll
     for (int k = 3; k < 15; k += 2) {
@@ -137,8 +214,8 @@ __device__ __forceinline__ unsigned fast_score_s16x2(const unsigned (&e)[16]) {
     }
     a = __vmaxs2(a, mn9[15]);
     b = __vmins2(b, mx9[15]);
-    /* score = max(a, -b) - 1 */
-    return __vsub2(__vmaxs2(a, __vneg2(b)), 0x00010001u);
+    const unsigned best = __vmaxs2(__vsub2(a, v), __vsub2(v, b));          /* max(a - v, v - b) = S + 1 */
+    return __viaddmax_s16x2_relu(best, negBias, 0u);                         /* relu(S + 1 - minTh) */
 }
 
 __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__ FrameGeom g,
@@ -147,6 +224,8 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
                                                          int* __restrict__ status) {
     __shared__ unsigned tile[FAST_ROWS * FAST_TW];
     __shared__ unsigned sc[(FAST_ROWS - 4) * FAST_SCW];
+    __shared__ unsigned short work[15 * 60];          /* quads that survive the high-speed test */
+    __shared__ int nwork;
     const int frame = blockIdx.y;
     int l = 0;
     while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].cellBase) l++;
@@ -161,7 +240,7 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     const int ch = min(iniY + L.hCell + 6, maxBorderY) - iniY;
     const int ww = cw - 6, wh = ch - 6;      /* detection window */
     if (ww <= 0 || wh <= 0) return;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int NQ = (ww + 3) >> 2;            /* quads per window row */
     const int NW = NQ + 2;                   /* tile words per row: quads + one word each side */
 
@@ -178,43 +257,63 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
             tile[y * FAST_TW + w] = funnel_bytes(lo, hi, sh);
         }
         for (int i = tid; i < (wh + 2) * FAST_SCW; i += blockDim.x) sc[i] = 0;
+        if (tid == 0) nwork = 0;
     }
     __syncthreads();
 
-    /* scores, four pixels per task */
-    const unsigned minThP = (unsigned)g.minTh * 0x00010001u;
+    /* phase 1 -- high-speed test on every quad.  A 9-arc of the 16-ring always contains a pair of opposite
+     * samples (k, k+8), so a corner at threshold t needs an opposite pair that is brighter than v + t on both
+     * ends, or darker than v - t on both ends.  Straight edges and flat areas fail this test. */
+    const unsigned thP = (unsigned)g.minTh * 0x00010001u, nthP = __vneg2(thP);
     const int ntask = NQ * wh;
-    for (int t = tid; t < ntask; t += blockDim.x) {
-        const int y = t / NQ, q = t - y * NQ;
-        const unsigned* row = &tile[(y + 3) * FAST_TW + q];   /* words: [q] = x-4..x-1, [q+1] = x..x+3, [q+2] = x+4..x+7 */
-        unsigned eA[16], eB[16];
-        {
+    for (int t0 = 0; t0 < ntask; t0 += blockDim.x) {
+        const int t = t0 + tid;
+        bool keep = false;
+        if (t < ntask) {
+            const int y = t / NQ, q = t - y * NQ;
+            const unsigned* row = &tile[(y + 3) * FAST_TW + q];
+            unsigned rA[16], rB[16];
+            fast_load_ring(row, rA, rB);
             const unsigned cw4 = row[1];
             const unsigned nvA = __vneg2(__byte_perm(cw4, 0, 0x4240)), nvB = __vneg2(__byte_perm(cw4, 0, 0x4341));
-#define RING(k, dy, dx)                                                                              \
-            {                                                                                        \
-                const unsigned* r_ = row + (dy) * FAST_TW;                                          \
-                const unsigned w_ = (dx) == 0 ? r_[1]                                                \
-                                   : (dx) > 0 ? funnel_bytes(r_[1], r_[2], (dx))                     \
-                                              : funnel_bytes(r_[0], r_[1], 4 + (dx));                \
-                eA[k] = __vadd2(__byte_perm(w_, 0, 0x4240), nvA);                                    \
-                eB[k] = __vadd2(__byte_perm(w_, 0, 0x4341), nvB);                                    \
+            unsigned loA[8], hiA[8], loB[8], hiB[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                loA[k] = __vmins2(rA[k], rA[k + 8]); hiA[k] = __vmaxs2(rA[k], rA[k + 8]);
+                loB[k] = __vmins2(rB[k], rB[k + 8]); hiB[k] = __vmaxs2(rB[k], rB[k + 8]);
             }
-            RING(0, 3, 0) RING(1, 3, 1) RING(2, 2, 2) RING(3, 1, 3) RING(4, 0, 3) RING(5, -1, 3) RING(6, -2, 2) RING(7, -3, 1)
-            RING(8, -3, 0) RING(9, -3, -1) RING(10, -2, -2) RING(11, -1, -3) RING(12, 0, -3) RING(13, 1, -3) RING(14, 2, -2)
-            RING(15, 3, -1)
-#undef RING
+            const unsigned brightA = __vimax3_s16x2(__vimax3_s16x2(loA[0], loA[1], loA[2]), __vimax3_s16x2(loA[3], loA[4], loA[5]),
+                                                    __vmaxs2(loA[6], loA[7]));
+            const unsigned brightB = __vimax3_s16x2(__vimax3_s16x2(loB[0], loB[1], loB[2]), __vimax3_s16x2(loB[3], loB[4], loB[5]),
+                                                    __vmaxs2(loB[6], loB[7]));
+            const unsigned darkA = __vimin3_s16x2(__vimin3_s16x2(hiA[0], hiA[1], hiA[2]), __vimin3_s16x2(hiA[3], hiA[4], hiA[5]),
+                                                  __vmins2(hiA[6], hiA[7]));
+            const unsigned darkB = __vimin3_s16x2(__vimin3_s16x2(hiB[0], hiB[1], hiB[2]), __vimin3_s16x2(hiB[3], hiB[4], hiB[5]),
+                                                  __vmins2(hiB[6], hiB[7]));
+            const unsigned up = __vmaxs2(__vadd2(brightA, nvA), __vadd2(brightB, nvB));   /* best opposite-pair excess */
+            const unsigned dn = __vmins2(__vadd2(darkA, nvA), __vadd2(darkB, nvB));
+            keep = !(__vmaxs2(up, thP) == thP && __vmins2(dn, nthP) == nthP);
         }
-        /* high-speed rejection: every 9-arc contains one of the compass points 0,4,8,12, so a quad whose
-         * compass differences all stay within +-minTh holds no corner at any threshold >= minTh */
-        const unsigned hi = __vmaxs2(__vimax3_s16x2(eA[0], eA[4], eA[8]), __vimax3_s16x2(eB[0], eB[4], eB[8]));
-        const unsigned lo = __vmins2(__vimin3_s16x2(eA[0], eA[4], eA[8]), __vimin3_s16x2(eB[0], eB[4], eB[8]));
-        const unsigned hi2 = __vmaxs2(hi, __vmaxs2(eA[12], eB[12])), lo2 = __vmins2(lo, __vmins2(eA[12], eB[12]));
-        if (__vmaxs2(hi2, minThP) == minThP && __vmins2(lo2, __vneg2(minThP)) == __vneg2(minThP)) continue;
-        unsigned sA = fast_score_s16x2(eA), sB = fast_score_s16x2(eB);
-        /* keep S >= minTh, else 0 (lane-wise) */
-        sA &= __vcmpges2(sA, minThP);
-        sB &= __vcmpges2(sB, minThP);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        int basePos = 0;
+        if (lane == 0 && m) basePos = atomicAdd(&nwork, __popc(m));
+        basePos = __shfl_sync(0xffffffffu, basePos, 0);
+        if (keep) work[basePos + __popc(m & ((1u << lane) - 1))] = (unsigned short)t;
+    }
+    __syncthreads();
+
+    /* phase 2 -- exact cornerScore on the surviving quads only, densely packed over the CTA */
+    const unsigned negBias = __vneg2(thP);
+    const int nw = nwork;
+    for (int i = tid; i < nw; i += blockDim.x) {
+        const int t = work[i];
+        const int y = t / NQ, q = t - y * NQ;
+        const unsigned* row = &tile[(y + 3) * FAST_TW + q];
+        unsigned rA[16], rB[16];
+        fast_load_ring(row, rA, rB);
+        const unsigned cw4 = row[1];
+        const unsigned sA = fast_score_s16x2(rA, __byte_perm(cw4, 0, 0x4240), negBias);
+        const unsigned sB = fast_score_s16x2(rB, __byte_perm(cw4, 0, 0x4341), negBias);
         unsigned word = sA | (sB << 8);                       /* bytes = pixels x, x+1, x+2, x+3 */
         const int x = q * 4;
         if (x + 4 > ww) word &= 0xffffffffu >> (8 * (x + 4 - ww));   /* beyond the window: not a corner */
@@ -222,48 +321,51 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     }
     __syncthreads();
 
-    /* 3x3 local maxima (window-clipped) + count at iniThFAST */
+    /* 3x3 local maxima (window-clipped) + count at iniThFAST.  sc holds S - (minTh - 1), 0 = no corner */
     const uint8_t* scb = reinterpret_cast<const uint8_t*>(sc);
-    unsigned lmBits = 0;      /* 4 bits per task handled by this thread */
+    const int iniShift = g.iniTh - g.minTh + 1;
+    unsigned lmBits = 0;      /* 4 bits per surviving quad handled by this thread */
     int nIni = 0, it = 0;
-    for (int t = tid; t < ntask; t += blockDim.x, it++) {
+    for (int i = tid; i < nw; i += blockDim.x, it++) {
+        const int t = work[i];
         const int y = t / NQ, q = t - y * NQ;
         const unsigned word = sc[(y + 1) * FAST_SCW + q + 1];
         if (word == 0) continue;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const int s = (word >> (8 * j)) & 0xff;
-            if (s == 0) continue;
+            const int sv = (word >> (8 * j)) & 0xff;
+            if (sv == 0) continue;
             const uint8_t* p = scb + ((y + 1) * FAST_SCW + q + 1) * 4 + j;
-            const bool lm = s > p[-1] && s > p[1] && s > p[-FAST_SCW * 4 - 1] && s > p[-FAST_SCW * 4] && s > p[-FAST_SCW * 4 + 1] &&
-                            s > p[FAST_SCW * 4 - 1] && s > p[FAST_SCW * 4] && s > p[FAST_SCW * 4 + 1];
+            const bool lm = sv > p[-1] && sv > p[1] && sv > p[-FAST_SCW * 4 - 1] && sv > p[-FAST_SCW * 4] && sv > p[-FAST_SCW * 4 + 1] &&
+                            sv > p[FAST_SCW * 4 - 1] && sv > p[FAST_SCW * 4] && sv > p[FAST_SCW * 4 + 1];
             if (lm) {
                 lmBits |= 1u << (4 * it + j);
-                if (s >= g.iniTh) nIni++;
+                if (sv >= iniShift) nIni++;
             }
         }
     }
     const int total = __syncthreads_count(nIni > 0);
-    const int th = total > 0 ? g.iniTh : g.minTh;     /* retry with minThFAST only if the cell is empty (:812) */
+    const int thShift = total > 0 ? iniShift : 1;     /* retry with minThFAST only if the cell is empty (:812) */
     if (lmBits == 0) return;
     int* counter = candCount + frame * g.nlevels + l;
     uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
     it = 0;
-    for (int t = tid; t < ntask; t += blockDim.x, it++) {
+    for (int i = tid; i < nw; i += blockDim.x, it++) {
         const unsigned bits4 = (lmBits >> (4 * it)) & 0xfu;
         if (!bits4) continue;
+        const int t = work[i];
         const int y = t / NQ, q = t - y * NQ;
         const unsigned word = sc[(y + 1) * FAST_SCW + q + 1];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if (!(bits4 >> j & 1u)) continue;
-            const unsigned s = (word >> (8 * j)) & 0xff;
-            if ((int)s < th) continue;
+            const int sv = (word >> (8 * j)) & 0xff;
+            if (sv < thShift) continue;
             const int pos = atomicAdd(counter, 1);
             if (pos < L.candCap) {
                 /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
                 const uint32_t X = q * 4 + j + 3 + cj * L.wCell, Y = y + 3 + ci * L.hCell;
-                out[pos] = X | (Y << 12) | (s << 24);
+                out[pos] = X | (Y << 12) | ((uint32_t)(sv + g.minTh - 1) << 24);
             } else {
                 atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
             }
@@ -618,10 +720,10 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const __grid_consta
 #define PROWS 43              /* patch rows / columns */
 #define PWORDS 12             /* patch row stride in 32-bit words (48 bytes, 43 used) */
 #define BW 37                 /* blurred width (radius 18) */
-#define HT_STRIDE 44          /* u16 per column of the transposed horizontal-pass buffer (43 rows + pad) */
-#define VSTRIDE 40            /* bytes per row of the blurred patch */
+#define HT_WORDS 24           /* words per column of the transposed horizontal-pass buffer: 48 u16 (43 rows + pad) */
+#define VT_STRIDE 40          /* bytes per column of the transposed blurred patch (37 rows + pad) */
 
-__device__ __align__(16) const int8_t d_pattern[1024] = VIORB_ORB_PATTERN_INIT;   /* read as 2 x uint4 per lane */
+__device__ __align__(16) const float d_pattern[1024] = VIORB_ORB_PATTERN_INIT;   /* as floats: x*b + y*a needs no I2F */
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 /* cv::fastAtan2 (degrees), OpenCV core mathfuncs_core atan_f32 polynomial, no FMA */
@@ -704,7 +806,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
                                                                           int* __restrict__ status) {
     /* per warp: patch (43 x 12 words; later reused for the blurred 37x37 bytes) + transposed H-pass buffer */
     __shared__ __align__(16) unsigned patchW[DESC_WARPS][PROWS * PWORDS];
-    __shared__ __align__(16) unsigned hbW[DESC_WARPS][BW * HT_STRIDE / 2];
+    __shared__ __align__(16) unsigned hbW[DESC_WARPS][BW * HT_WORDS];
     const int frame = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * DESC_WARPS + warp;
@@ -730,20 +832,33 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
     const uint8_t* roi = pyr + (size_t)frame * g.pyrFrameBytes + L.pyrOff + (size_t)VIORB_EDGE * L.step + VIORB_ROI_X0;
     unsigned* P = patchW[warp];
     unsigned* Hw = hbW[warp];
-    /* stage the 43x43 neighbourhood as aligned words: patch byte (r, c) = level pixel (kx-21+c, ky-21+r) */
+    /* stage the 43x43 neighbourhood as aligned words: patch byte (r, c) = level pixel (kx-21+c, ky-21+r).
+     * All loads are issued before the first use (17 x 2 independent LDG.32 in flight per lane). */
     {
         const int gx0 = kx - PR;
         const int sh = gx0 & 3;
         const uint8_t* base = roi + (ptrdiff_t)(ky - PR) * L.step + (gx0 - sh);    /* 4-byte aligned */
-        for (int i = lane; i < PROWS * PWORDS; i += 32) {
+        unsigned lo[17], hi[17];
+#pragma unroll
+        for (int k = 0; k < 17; k++) {
+            const int i = lane + 32 * k;
             const int r = i / PWORDS, w = i - r * PWORDS;
-            const unsigned* src = reinterpret_cast<const unsigned*>(base + (ptrdiff_t)r * L.step) + w;
-            P[i] = funnel_bytes(__ldg(src), __ldg(src + 1), sh);
+            if (i < PROWS * PWORDS) {
+                const unsigned* src = reinterpret_cast<const unsigned*>(base + (ptrdiff_t)r * L.step) + w;
+                lo[k] = __ldg(src);
+                hi[k] = __ldg(src + 1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 17; k++) {
+            const int i = lane + 32 * k;
+            if (i < PROWS * PWORDS) P[i] = funnel_bytes(lo[k], hi[k], sh);
         }
     }
-    /* this lane's 8 binary tests (16 sampling points) */
-    const uint4 pat0 = __ldg(reinterpret_cast<const uint4*>(d_pattern) + 2 * lane);
-    const uint4 pat1 = __ldg(reinterpret_cast<const uint4*>(d_pattern) + 2 * lane + 1);
+    /* this lane's 8 binary tests (16 sampling points, 32 floats) */
+    float4 pat[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) pat[k] = __ldg(reinterpret_cast<const float4*>(d_pattern) + 8 * lane + k);
     __syncwarp();
     /* IC_Angle: lane v+15 sums row v of the circular patch */
     int m10 = 0, m01 = 0;
@@ -765,47 +880,53 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
         m01 += __shfl_xor_sync(0xffffffffu, m01, o);
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
-    /* horizontal 7-tap pass, four outputs per task, two IDP.4A each; the 16-bit sums (exact: the taps sum
-     * to 256) are stored transposed so that the vertical pass reads vertically adjacent pairs as words */
+    /* horizontal 7-tap pass: a task = 2 rows x 4 columns, two IDP.4A per output.  The 16-bit sums (exact:
+     * the taps sum to 256) of vertically adjacent rows are packed into one word and stored transposed
+     * (Hw[c][r/2]) so the vertical pass can use IDP.2A on row pairs. */
     {
         const unsigned KLO = 18u | (34u << 8) | (48u << 16) | (56u << 24), KHI = 48u | (34u << 8) | (18u << 16);
-        unsigned short* Hs = reinterpret_cast<unsigned short*>(Hw);
-        for (int t = lane; t < PROWS * 10; t += 32) {
-            const int r = t / 10, j = t - r * 10;
-            const unsigned w0 = P[r * PWORDS + j], w1 = P[r * PWORDS + j + 1], w2 = P[r * PWORDS + j + 2];
-            const unsigned h0 = __dp4a(w0, KLO, __dp4a(w1, KHI, 0u));
-            const unsigned h1 = __dp4a(funnel_bytes(w0, w1, 1), KLO, __dp4a(funnel_bytes(w1, w2, 1), KHI, 0u));
-            const unsigned h2 = __dp4a(funnel_bytes(w0, w1, 2), KLO, __dp4a(funnel_bytes(w1, w2, 2), KHI, 0u));
-            const unsigned h3 = __dp4a(funnel_bytes(w0, w1, 3), KLO, __dp4a(funnel_bytes(w1, w2, 3), KHI, 0u));
+        for (int t = lane; t < 22 * 10; t += 32) {
+            const int rp = t / 10, j = t - rp * 10;          /* row pair, column quad */
+            const unsigned* p0 = &P[(2 * rp) * PWORDS + j];
+            const unsigned* p1 = rp < 21 ? p0 + PWORDS : p0; /* row 43 does not exist: its sums are never used */
+            const unsigned a0 = p0[0], a1 = p0[1], a2 = p0[2], b0 = p1[0], b1 = p1[1], b2 = p1[2];
+            unsigned h[4];
+            h[0] = __dp4a(a0, KLO, __dp4a(a1, KHI, 0u)) | (__dp4a(b0, KLO, __dp4a(b1, KHI, 0u)) << 16);
+#pragma unroll
+            for (int i = 1; i < 4; i++)
+                h[i] = __dp4a(funnel_bytes(a0, a1, i), KLO, __dp4a(funnel_bytes(a1, a2, i), KHI, 0u)) |
+                       (__dp4a(funnel_bytes(b0, b1, i), KLO, __dp4a(funnel_bytes(b1, b2, i), KHI, 0u)) << 16);
             const int c = 4 * j;
-            Hs[c * HT_STRIDE + r] = (unsigned short)h0;
-            if (c + 1 < BW) Hs[(c + 1) * HT_STRIDE + r] = (unsigned short)h1;
-            if (c + 2 < BW) Hs[(c + 2) * HT_STRIDE + r] = (unsigned short)h2;
-            if (c + 3 < BW) Hs[(c + 3) * HT_STRIDE + r] = (unsigned short)h3;
+            Hw[c * HT_WORDS + rp] = h[0];
+            if (c + 1 < BW) Hw[(c + 1) * HT_WORDS + rp] = h[1];
+            if (c + 2 < BW) Hw[(c + 2) * HT_WORDS + rp] = h[2];
+            if (c + 3 < BW) Hw[(c + 3) * HT_WORDS + rp] = h[3];
         }
     }
     __syncwarp();
-    /* vertical pass: a task walks half a column with a sliding window of four words (8 rows); each pair of
-     * output rows shares the window.  out = (sum + 32768) >> 16, GaussianBlur's fixed-point rounding */
-    uint8_t* Vb = reinterpret_cast<uint8_t*>(P);       /* the patch is dead now */
+    /* vertical pass: a task = 8 output rows of one column, read as two 16-byte vectors (8 row pairs); even and
+     * odd rows use the tap pairs shifted by one.  out = (sum + 32768) >> 16 (GaussianBlur's rounding); the
+     * blurred patch is stored transposed as well (Vt[c][r]) so a task writes two words. */
+    uint8_t* Vt = reinterpret_cast<uint8_t*>(P);       /* the patch is dead now */
     {
         const unsigned E01 = 18u | (34u << 8), E23 = 48u | (56u << 8), E45 = 48u | (34u << 8), E6 = 18u;   /* even row */
         const unsigned O0 = 18u << 8, O12 = 34u | (48u << 8), O34 = 56u | (48u << 8), O56 = 34u | (18u << 8);  /* odd row */
-        for (int t = lane; t < BW * 2; t += 32) {
-            const int c = t >> 1, half = t & 1;
-            const int r0 = half ? 20 : 0, r1 = half ? BW : 20;
-            const unsigned* col = Hw + c * (HT_STRIDE / 2) + (r0 >> 1);
-            unsigned a = col[0], b = col[1], cc = col[2];
-            for (int r = r0; r < r1; r += 2) {
-                const unsigned d = col[((r - r0) >> 1) + 3];
-                const unsigned ve = __dp2a_lo(a, E01, __dp2a_lo(b, E23, __dp2a_lo(cc, E45, __dp2a_lo(d, E6, 32768u))));
-                Vb[r * VSTRIDE + c] = (uint8_t)(ve >> 16);
-                if (r + 1 < r1) {
-                    const unsigned vo = __dp2a_lo(a, O0, __dp2a_lo(b, O12, __dp2a_lo(cc, O34, __dp2a_lo(d, O56, 32768u))));
-                    Vb[(r + 1) * VSTRIDE + c] = (uint8_t)(vo >> 16);
-                }
-                a = b; b = cc; cc = d;
+        for (int t = lane; t < BW * 5; t += 32) {
+            const int c = t / 5, seg = t - c * 5;            /* rows 8*seg .. 8*seg+7 */
+            const uint4 q0 = *reinterpret_cast<const uint4*>(&Hw[c * HT_WORDS + 4 * seg]);
+            const uint4 q1 = *reinterpret_cast<const uint4*>(&Hw[c * HT_WORDS + 4 * seg + 4]);
+            const unsigned w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            unsigned out[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned ve = __dp2a_lo(w[k], E01, __dp2a_lo(w[k + 1], E23, __dp2a_lo(w[k + 2], E45, __dp2a_lo(w[k + 3], E6, 32768u))));
+                const unsigned vo = __dp2a_lo(w[k], O0, __dp2a_lo(w[k + 1], O12, __dp2a_lo(w[k + 2], O34, __dp2a_lo(w[k + 3], O56, 32768u))));
+                out[2 * k] = ve >> 16;
+                out[2 * k + 1] = vo >> 16;
             }
+            unsigned* dst = reinterpret_cast<unsigned*>(Vt + c * VT_STRIDE + 8 * seg);
+            dst[0] = out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24);
+            dst[1] = out[4] | (out[5] << 8) | (out[6] << 16) | (out[7] << 24);
         }
     }
     __syncwarp();
@@ -813,18 +934,16 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     float a, b;
     sincosf_glibc(__fmul_rn(angle, factorPI), &b, &a);
-    const uint8_t* centre = &Vb[18 * VSTRIDE + 18];
-    const unsigned pw[8] = {pat0.x, pat0.y, pat0.z, pat0.w, pat1.x, pat1.y, pat1.z, pat1.w};
+    const uint8_t* centre = &Vt[18 * VT_STRIDE + 18];
     unsigned val = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const float x0 = (float)(int8_t)(pw[k] & 0xff), y0 = (float)(int8_t)((pw[k] >> 8) & 0xff);
-        const float x1 = (float)(int8_t)((pw[k] >> 16) & 0xff), y1 = (float)(int8_t)(pw[k] >> 24);
+        const float x0 = pat[k].x, y0 = pat[k].y, x1 = pat[k].z, y1 = pat[k].w;
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
         const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
         const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = centre[r0 * VSTRIDE + c0], t1 = centre[r1 * VSTRIDE + c1];
+        const int t0 = centre[c0 * VT_STRIDE + r0], t1 = centre[c1 * VT_STRIDE + r1];
         val |= (unsigned)(t0 < t1) << k;
     }
     desc[((size_t)frame * cap + slot) * 32 + lane] = (uint8_t)val;
@@ -850,9 +969,13 @@ int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_
     int launches = 0;
     for (int l = 0; l < g.nlevels; l++) {
         const LevelGeom& L = g.lv[l];
-        dim3 grid((L.step / 4 + 127) / 128, L.h + 2 * VIORB_EDGE, F);
-        if (l == 0) pyr_level0_kernel<<<grid, 128, 0, s>>>(g, d_images, step, frameStride, b.pyr);
-        else pyr_resize_kernel<<<grid, 128, 0, s>>>(g, l, t, b.pyr);
+        if (l == 0) {
+            dim3 grid((L.step / 4 + 127) / 128, L.h + 2 * VIORB_EDGE, F);
+            pyr_level0_kernel<<<grid, 128, 0, s>>>(g, d_images, step, frameStride, b.pyr);
+        } else {
+            dim3 grid((L.step + RZ_TW - 1) / RZ_TW, (L.h + 2 * VIORB_EDGE + RZ_TH - 1) / RZ_TH, F);
+            pyr_resize_kernel<<<grid, 128, 0, s>>>(g, l, t, b.pyr);
+        }
         launches++;
     }
     return launches;
