@@ -78,13 +78,15 @@ struct viorb_extractor {
     double scaleFactor = 1.2;
     std::vector<float> scale, invScale, sigma2, invSigma2;
     std::vector<int> quota;
-    int chunk = 64, candDiv = 16;
+    int chunk = 128, candDiv = 16;
     /* geometry for the current image size */
     int rows = 0, cols = 0;
     FrameGeom geom;
     int nodeCap = 0;
     DevBuf<uint16_t> tabU16;       /* xofs | yofs */
     DevBuf<int16_t> tabI16;        /* xa | yb */
+    DevBuf<int4> groups;           /* FAST cell groups: {level, cell row, first cell, cells} */
+    int ngroups = 0;
     ResizeTables tables;
     /* pass workspace */
     int allocFrames = 0;
@@ -216,7 +218,23 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
             ti[2 * (xtab + L.ytab + dy) + 1] = (int16_t)cvRoundF(fy * 2048);
         }
     }
+    /* FAST cell groups: the cells the reference visits (:789-806), VIORB_FAST_GROUP neighbours per CTA */
+    std::vector<int4> groups;
+    for (int l = 0; l < e->nlevels; l++) {
+        const LevelGeom& L = g.lv[l];
+        const int maxBorderX = L.w - VIORB_FAST_BORDER, maxBorderY = L.h - VIORB_FAST_BORDER;
+        for (int i = 0; i < L.nRows; i++) {
+            if (VIORB_FAST_BORDER + i * L.hCell >= maxBorderY - 3) continue;
+            int nvalid = 0;
+            while (nvalid < L.nCols && VIORB_FAST_BORDER + nvalid * L.wCell < maxBorderX - 6) nvalid++;
+            const int G = L.wCell <= 45 ? VIORB_FAST_GROUP : 1;
+            for (int j = 0; j < nvalid; j += G) groups.push_back(make_int4(l, i, j, std::min(G, nvalid - j)));
+        }
+    }
+    e->ngroups = (int)groups.size();
     int rc;
+    if ((rc = e->groups.ensure(groups.size() + 1))) return rc;
+    CU(cudaMemcpyAsync(e->groups.p, groups.data(), groups.size() * sizeof(int4), cudaMemcpyHostToDevice, e->ctx->stream));
     if ((rc = e->tabU16.ensure(tu.size() + 1))) return rc;
     if ((rc = e->tabI16.ensure(ti.size() + 2))) return rc;
     CU(cudaMemcpyAsync(e->tabU16.p, tu.data(), tu.size() * 2, cudaMemcpyHostToDevice, e->ctx->stream));
@@ -271,7 +289,7 @@ int run_pass(viorb_extractor* e, const uint8_t* d_images, size_t step, size_t fr
     if (e->profiling) CU(cudaEventRecord(ev[0], c->stream));
     c->launches += viorb_launch_pyramid(g, e->tables, d_images, step, frameStride, F, e->buf, c->stream);
     if (e->profiling) CU(cudaEventRecord(ev[1], c->stream));
-    c->launches += viorb_launch_fast(g, F, e->buf, c->stream);
+    c->launches += viorb_launch_fast(g, e->groups.p, e->ngroups, F, e->buf, c->stream);
     if (e->profiling) CU(cudaEventRecord(ev[2], c->stream));
     c->launches += viorb_launch_octree(g, F, e->buf, e->nodeCap, c->stream);
     if (e->profiling) CU(cudaEventRecord(ev[3], c->stream));
@@ -405,7 +423,7 @@ int viorb_extractor_destroy(viorb_extractor* e) {
     cudaStreamSynchronize(e->ctx->stream);
     cudaStreamSynchronize(e->ctx->h2d);
     cudaStreamSynchronize(e->ctx->d2h);
-    e->tabU16.release(); e->tabI16.release(); e->pyr.release(); e->cand.release(); e->sel.release();
+    e->tabU16.release(); e->tabI16.release(); e->groups.release(); e->pyr.release(); e->cand.release(); e->sel.release();
     e->counters.release(); e->nodeOf.release();
     for (int i = 0; i < 2; i++) {
         e->in[i].release(); e->okps[i].release(); e->odesc[i].release(); e->ocnt[i].release();

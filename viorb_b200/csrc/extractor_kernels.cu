@@ -26,28 +26,40 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 /* ------------------------------------------------------------------------------------------------
  * ComputePyramid level 0: copyMakeBorder(image, temp, 19.., BORDER_REFLECT_101)   (:1127-1128)
- * one thread = one 4-byte word of a stored row
+ * one thread = one 16-byte vector of a stored row; interior vectors are straight 128-bit copies
  * ---------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(128) pyr_level0_kernel(const __grid_constant__ FrameGeom g,
                                                          const uint8_t* __restrict__ images, size_t inStep,
-                                                         size_t frameStride, uint8_t* __restrict__ pyr) {
+                                                         size_t frameStride, uint8_t* __restrict__ pyr, int aligned) {
     const LevelGeom& L = g.lv[0];
-    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = blockIdx.y;                 /* stored row 0 .. h+38 */
+    const int vi = blockIdx.x * blockDim.x + threadIdx.x;      /* 16-byte vector index inside the stored row */
+    const int row = blockIdx.y;                                 /* stored row 0 .. h+38 */
     const int frame = blockIdx.z;
-    if (wi * 4 >= L.step) return;
+    if (vi * 16 >= L.step) return;
     const int sy = reflect101(row - VIORB_EDGE, L.h);
     const uint8_t* src = images + (size_t)frame * frameStride + (size_t)sy * inStep;
-    uint32_t word = 0;
+    const int x0 = vi * 16 - VIORB_ROI_X0;
+    uint4 out;
+    if (aligned && x0 >= 0 && x0 + 16 <= L.w) {
+        out = __ldg(reinterpret_cast<const uint4*>(src + x0));
+    } else {
+        uint32_t wds[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int x = wi * 4 + j - VIORB_ROI_X0;
-        uint32_t v = 0;
-        if (x >= -VIORB_EDGE && x < L.w + VIORB_EDGE) v = src[reflect101(x, L.w)];
-        word |= v << (8 * j);
+        for (int q = 0; q < 4; q++) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int x = x0 + 4 * q + j;
+                uint32_t v = 0;
+                if (x >= -VIORB_EDGE && x < L.w + VIORB_EDGE) v = src[reflect101(x, L.w)];
+                word |= v << (8 * j);
+            }
+            wds[q] = word;
+        }
+        out = make_uint4(wds[0], wds[1], wds[2], wds[3]);
     }
     uint8_t* dst = pyr + (size_t)frame * g.pyrFrameBytes + L.pyrOff + (size_t)row * L.step;
-    reinterpret_cast<uint32_t*>(dst)[wi] = word;
+    reinterpret_cast<uint4*>(dst)[vi] = out;
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -160,9 +172,12 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
  * count 0 -- i.e. "S_p >= t and S_p > S_n for all window neighbours", so one local-max map serves both
  * thresholds and the per-cell retry (:812) only re-filters by minThFAST.
  * ---------------------------------------------------------------------------------------------- */
+#define FAST_GROUP 4            /* horizontally adjacent cells per CTA */
 #define FAST_ROWS 68            /* cell sub-image rows  (hCell + 6 <= 66) */
-#define FAST_TW 19              /* tile row stride in words: 1 lead byte + (wCell + 6 <= 66) bytes, padded */
-#define FAST_SCW 18             /* score row stride in words: 1 zero word + 15 quads + 1 zero word, padded */
+#define FAST_MAXQ 45            /* quads per window row: 4 cells x wCell (<= 45 when nCols >= 2; one cell of <= 59 otherwise) */
+#define FAST_TW 49              /* tile row stride in words (odd): 1 lead word + 45 quads + 1 tail word, padded */
+#define FAST_SCW 49             /* score row stride in words (odd): 1 zero word + 45 quads + 1 zero word, padded */
+#define FAST_MAXWORK (FAST_MAXQ * 60)
 
 __device__ __forceinline__ unsigned funnel_bytes(unsigned lo, unsigned hi, int sh) {
     /* bytes sh..sh+3 of the 8-byte little-endian sequence lo|hi (sh in 0..3) */
@@ -219,26 +234,29 @@ __device__ __forceinline__ unsigned fast_score_s16x2(const unsigned (&r)[16], un
 }
 
 __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__ FrameGeom g,
+                                                         const int4* __restrict__ groups,
                                                          const uint8_t* __restrict__ pyr,
                                                          uint32_t* __restrict__ cand, int* __restrict__ candCount,
                                                          int* __restrict__ status) {
     __shared__ unsigned tile[FAST_ROWS * FAST_TW];
     __shared__ unsigned sc[(FAST_ROWS - 4) * FAST_SCW];
-    __shared__ unsigned short work[15 * 60];          /* quads that survive the high-speed test */
+    __shared__ unsigned short work[FAST_MAXWORK];     /* quads that survive the high-speed test */
+    __shared__ unsigned char lmq[FAST_MAXWORK];       /* local-maximum bits of the surviving quads */
     __shared__ int nwork;
+    __shared__ int cellIni[FAST_GROUP];               /* per cell: does it hold a corner at iniThFAST? */
     const int frame = blockIdx.y;
-    int l = 0;
-    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].cellBase) l++;
+    /* a CTA owns up to FAST_GROUP horizontally adjacent cells of one cell row: {level, cell row, first cell, n} */
+    const int4 grp = __ldg(&groups[blockIdx.x]);
+    const int l = grp.x, ci = grp.y, cj0 = grp.z, ncell = grp.w;
     const LevelGeom& L = g.lv[l];
-    const int c = blockIdx.x - L.cellBase;
-    const int ci = c / L.nCols, cj = c - ci * L.nCols;
     const int maxBorderX = L.w - VIORB_FAST_BORDER, maxBorderY = L.h - VIORB_FAST_BORDER;
     const int iniY = VIORB_FAST_BORDER + ci * L.hCell;
-    const int iniX = VIORB_FAST_BORDER + cj * L.wCell;
-    if (iniY >= maxBorderY - 3 || iniX >= maxBorderX - 6) return;   /* :795-796, :804-805 */
-    const int cw = min(iniX + L.wCell + 6, maxBorderX) - iniX;
+    const int iniX = VIORB_FAST_BORDER + cj0 * L.wCell;
+    /* the cells of the group tile the window exactly: cell j detects x in [j*wCell, (j+1)*wCell), the last one
+     * is clipped at maxBorderX (:798-806).  Skipped cells (:795-796, :804-805) are not in the table. */
+    const int cwG = min(iniX + ncell * L.wCell + 6, maxBorderX) - iniX;
     const int ch = min(iniY + L.hCell + 6, maxBorderY) - iniY;
-    const int ww = cw - 6, wh = ch - 6;      /* detection window */
+    const int ww = cwG - 6, wh = ch - 6;      /* detection window of the whole group */
     if (ww <= 0 || wh <= 0) return;
     const int tid = threadIdx.x, lane = tid & 31;
     const int NQ = (ww + 3) >> 2;            /* quads per window row */
@@ -258,6 +276,7 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
         }
         for (int i = tid; i < (wh + 2) * FAST_SCW; i += blockDim.x) sc[i] = 0;
         if (tid == 0) nwork = 0;
+        if (tid < FAST_GROUP) cellIni[tid] = 0;
     }
     __syncthreads();
 
@@ -321,37 +340,39 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     }
     __syncthreads();
 
-    /* 3x3 local maxima (window-clipped) + count at iniThFAST.  sc holds S - (minTh - 1), 0 = no corner */
+    /* 3x3 local maxima + per-cell count at iniThFAST.  sc holds S - (minTh - 1), 0 = no corner.  cv::FAST runs
+     * on the cell's own sub-image, so neighbours in another cell (or outside the window) count as 0. */
     const uint8_t* scb = reinterpret_cast<const uint8_t*>(sc);
     const int iniShift = g.iniTh - g.minTh + 1;
-    unsigned lmBits = 0;      /* 4 bits per surviving quad handled by this thread */
-    int nIni = 0, it = 0;
-    for (int i = tid; i < nw; i += blockDim.x, it++) {
+    for (int i = tid; i < nw; i += blockDim.x) {
         const int t = work[i];
         const int y = t / NQ, q = t - y * NQ;
         const unsigned word = sc[(y + 1) * FAST_SCW + q + 1];
-        if (word == 0) continue;
+        unsigned bits = 0;
+        if (word != 0) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int sv = (word >> (8 * j)) & 0xff;
-            if (sv == 0) continue;
-            const uint8_t* p = scb + ((y + 1) * FAST_SCW + q + 1) * 4 + j;
-            const bool lm = sv > p[-1] && sv > p[1] && sv > p[-FAST_SCW * 4 - 1] && sv > p[-FAST_SCW * 4] && sv > p[-FAST_SCW * 4 + 1] &&
-                            sv > p[FAST_SCW * 4 - 1] && sv > p[FAST_SCW * 4] && sv > p[FAST_SCW * 4 + 1];
-            if (lm) {
-                lmBits |= 1u << (4 * it + j);
-                if (sv >= iniShift) nIni++;
+            for (int j = 0; j < 4; j++) {
+                const int sv = (word >> (8 * j)) & 0xff;
+                if (sv == 0) continue;
+                const int x = q * 4 + j;
+                const int cg = x / L.wCell, xin = x - cg * L.wCell;
+                const uint8_t* p = scb + ((y + 1) * FAST_SCW + q + 1) * 4 + j;
+                bool lm = sv > p[-FAST_SCW * 4] && sv > p[FAST_SCW * 4];
+                if (xin > 0) lm = lm && sv > p[-1] && sv > p[-FAST_SCW * 4 - 1] && sv > p[FAST_SCW * 4 - 1];
+                if (xin < L.wCell - 1) lm = lm && sv > p[1] && sv > p[-FAST_SCW * 4 + 1] && sv > p[FAST_SCW * 4 + 1];
+                if (lm) {
+                    bits |= 1u << j;
+                    if (sv >= iniShift) cellIni[cg] = 1;
+                }
             }
         }
+        lmq[i] = (unsigned char)bits;
     }
-    const int total = __syncthreads_count(nIni > 0);
-    const int thShift = total > 0 ? iniShift : 1;     /* retry with minThFAST only if the cell is empty (:812) */
-    if (lmBits == 0) return;
+    __syncthreads();
     int* counter = candCount + frame * g.nlevels + l;
     uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
-    it = 0;
-    for (int i = tid; i < nw; i += blockDim.x, it++) {
-        const unsigned bits4 = (lmBits >> (4 * it)) & 0xfu;
+    for (int i = tid; i < nw; i += blockDim.x) {
+        const unsigned bits4 = lmq[i];
         if (!bits4) continue;
         const int t = work[i];
         const int y = t / NQ, q = t - y * NQ;
@@ -360,11 +381,13 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
         for (int j = 0; j < 4; j++) {
             if (!(bits4 >> j & 1u)) continue;
             const int sv = (word >> (8 * j)) & 0xff;
-            if (sv < thShift) continue;
+            const int x = q * 4 + j;
+            /* the cell is retried with minThFAST only if it found nothing at iniThFAST (:812) */
+            if (sv < (cellIni[x / L.wCell] ? iniShift : 1)) continue;
             const int pos = atomicAdd(counter, 1);
             if (pos < L.candCap) {
                 /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
-                const uint32_t X = q * 4 + j + 3 + cj * L.wCell, Y = y + 3 + ci * L.hCell;
+                const uint32_t X = x + 3 + cj0 * L.wCell, Y = y + 3 + ci * L.hCell;
                 out[pos] = X | (Y << 12) | ((uint32_t)(sv + g.minTh - 1) << 24);
             } else {
                 atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
@@ -718,9 +741,10 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const __grid_consta
 #define DESC_WARPS 8
 #define PR 21                 /* patch radius */
 #define PROWS 43              /* patch rows / columns */
-#define PWORDS 12             /* patch row stride in 32-bit words (48 bytes, 43 used) */
+#define PWORDS 13             /* patch row stride in 32-bit words (odd: conflict-free row pairs; 12 words used) */
 #define BW 37                 /* blurred width (radius 18) */
-#define HT_WORDS 24           /* words per column of the transposed horizontal-pass buffer: 48 u16 (43 rows + pad) */
+#define HT_WORDS 25           /* words per column of the transposed horizontal-pass buffer (>= 23; = 1 mod 8 so the
+                                 transposed stores of 4-column quads fall into distinct banks) */
 #define VT_STRIDE 40          /* bytes per column of the transposed blurred patch (37 rows + pad) */
 
 __device__ __align__(16) const float d_pattern[1024] = VIORB_ORB_PATTERN_INIT;   /* as floats: x*b + y*a needs no I2F */
@@ -833,26 +857,24 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
     unsigned* P = patchW[warp];
     unsigned* Hw = hbW[warp];
     /* stage the 43x43 neighbourhood as aligned words: patch byte (r, c) = level pixel (kx-21+c, ky-21+r).
-     * All loads are issued before the first use (17 x 2 independent LDG.32 in flight per lane). */
+     * Half a warp loads one row (13 aligned words), the funnel shift takes the next word from the next lane;
+     * all 22 loads of a lane are issued before the first use. */
     {
         const int gx0 = kx - PR;
         const int sh = gx0 & 3;
-        const uint8_t* base = roi + (ptrdiff_t)(ky - PR) * L.step + (gx0 - sh);    /* 4-byte aligned */
-        unsigned lo[17], hi[17];
+        const int w = lane & 15, rsub = lane >> 4;
+        const uint8_t* base = roi + (ptrdiff_t)(ky - PR + rsub) * L.step + (gx0 - sh) + 4 * w;    /* 4-byte aligned */
+        unsigned g[22];
 #pragma unroll
-        for (int k = 0; k < 17; k++) {
-            const int i = lane + 32 * k;
-            const int r = i / PWORDS, w = i - r * PWORDS;
-            if (i < PROWS * PWORDS) {
-                const unsigned* src = reinterpret_cast<const unsigned*>(base + (ptrdiff_t)r * L.step) + w;
-                lo[k] = __ldg(src);
-                hi[k] = __ldg(src + 1);
-            }
+        for (int k = 0; k < 22; k++) {
+            const int r = 2 * k + rsub;
+            g[k] = (w < 13 && r < PROWS) ? __ldg(reinterpret_cast<const unsigned*>(base + (ptrdiff_t)(2 * k) * L.step)) : 0u;
         }
 #pragma unroll
-        for (int k = 0; k < 17; k++) {
-            const int i = lane + 32 * k;
-            if (i < PROWS * PWORDS) P[i] = funnel_bytes(lo[k], hi[k], sh);
+        for (int k = 0; k < 22; k++) {
+            const int r = 2 * k + rsub;
+            const unsigned hi = __shfl_down_sync(0xffffffffu, g[k], 1);
+            if (w < 12 && r < PROWS) P[r * PWORDS + w] = funnel_bytes(g[k], hi, sh);
         }
     }
     /* this lane's 8 binary tests (16 sampling points, 32 floats) */
@@ -891,11 +913,11 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
             const unsigned* p1 = rp < 21 ? p0 + PWORDS : p0; /* row 43 does not exist: its sums are never used */
             const unsigned a0 = p0[0], a1 = p0[1], a2 = p0[2], b0 = p1[0], b1 = p1[1], b2 = p1[2];
             unsigned h[4];
-            h[0] = __dp4a(a0, KLO, __dp4a(a1, KHI, 0u)) | (__dp4a(b0, KLO, __dp4a(b1, KHI, 0u)) << 16);
+            h[0] = __byte_perm(__dp4a(a0, KLO, __dp4a(a1, KHI, 0u)), __dp4a(b0, KLO, __dp4a(b1, KHI, 0u)), 0x5410);
 #pragma unroll
             for (int i = 1; i < 4; i++)
-                h[i] = __dp4a(funnel_bytes(a0, a1, i), KLO, __dp4a(funnel_bytes(a1, a2, i), KHI, 0u)) |
-                       (__dp4a(funnel_bytes(b0, b1, i), KLO, __dp4a(funnel_bytes(b1, b2, i), KHI, 0u)) << 16);
+                h[i] = __byte_perm(__dp4a(funnel_bytes(a0, a1, i), KLO, __dp4a(funnel_bytes(a1, a2, i), KHI, 0u)),
+                                   __dp4a(funnel_bytes(b0, b1, i), KLO, __dp4a(funnel_bytes(b1, b2, i), KHI, 0u)), 0x5410);
             const int c = 4 * j;
             Hw[c * HT_WORDS + rp] = h[0];
             if (c + 1 < BW) Hw[(c + 1) * HT_WORDS + rp] = h[1];
@@ -904,7 +926,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
         }
     }
     __syncwarp();
-    /* vertical pass: a task = 8 output rows of one column, read as two 16-byte vectors (8 row pairs); even and
+    /* vertical pass: a task = 8 output rows of one column, read as 7 words (row pairs); even and
      * odd rows use the tap pairs shifted by one.  out = (sum + 32768) >> 16 (GaussianBlur's rounding); the
      * blurred patch is stored transposed as well (Vt[c][r]) so a task writes two words. */
     uint8_t* Vt = reinterpret_cast<uint8_t*>(P);       /* the patch is dead now */
@@ -913,9 +935,10 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
         const unsigned O0 = 18u << 8, O12 = 34u | (48u << 8), O34 = 56u | (48u << 8), O56 = 34u | (18u << 8);  /* odd row */
         for (int t = lane; t < BW * 5; t += 32) {
             const int c = t / 5, seg = t - c * 5;            /* rows 8*seg .. 8*seg+7 */
-            const uint4 q0 = *reinterpret_cast<const uint4*>(&Hw[c * HT_WORDS + 4 * seg]);
-            const uint4 q1 = *reinterpret_cast<const uint4*>(&Hw[c * HT_WORDS + 4 * seg + 4]);
-            const unsigned w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            const unsigned* hcol = &Hw[c * HT_WORDS + 4 * seg];
+            unsigned w[7];
+#pragma unroll
+            for (int k = 0; k < 7; k++) w[k] = hcol[k];
             unsigned out[8];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -970,8 +993,9 @@ int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_
     for (int l = 0; l < g.nlevels; l++) {
         const LevelGeom& L = g.lv[l];
         if (l == 0) {
-            dim3 grid((L.step / 4 + 127) / 128, L.h + 2 * VIORB_EDGE, F);
-            pyr_level0_kernel<<<grid, 128, 0, s>>>(g, d_images, step, frameStride, b.pyr);
+            dim3 grid((L.step / 16 + 127) / 128, L.h + 2 * VIORB_EDGE, F);
+            const int aligned = ((uintptr_t)d_images % 16 == 0) && (step % 16 == 0) && (frameStride % 16 == 0);
+            pyr_level0_kernel<<<grid, 128, 0, s>>>(g, d_images, step, frameStride, b.pyr, aligned);
         } else {
             dim3 grid((L.step + RZ_TW - 1) / RZ_TW, (L.h + 2 * VIORB_EDGE + RZ_TH - 1) / RZ_TH, F);
             pyr_resize_kernel<<<grid, 128, 0, s>>>(g, l, t, b.pyr);
@@ -981,9 +1005,9 @@ int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_
     return launches;
 }
 
-int viorb_launch_fast(const FrameGeom& g, int F, const ExtractBuffers& b, cudaStream_t s) {
-    dim3 grid(g.cellsPerFrame, F);
-    fast_cells_kernel<<<grid, 128, 0, s>>>(g, b.pyr, b.cand, b.candCount, b.status);
+int viorb_launch_fast(const FrameGeom& g, const int4* d_groups, int ngroups, int F, const ExtractBuffers& b, cudaStream_t s) {
+    dim3 grid(ngroups, F);
+    fast_cells_kernel<<<grid, 128, 0, s>>>(g, d_groups, b.pyr, b.cand, b.candCount, b.status);
     return 1;
 }
 

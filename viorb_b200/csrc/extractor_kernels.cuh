@@ -81,7 +81,8 @@ struct ExtractBuffers {
 /* launchers (extractor_kernels.cu); every launcher returns the number of kernel launches issued */
 int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_t* d_images, size_t step,
                          size_t frameStride, int F, const ExtractBuffers& b, cudaStream_t s);
-int viorb_launch_fast(const FrameGeom& g, int F, const ExtractBuffers& b, cudaStream_t s);
+int viorb_launch_fast(const FrameGeom& g, const int4* d_groups, int ngroups, int F, const ExtractBuffers& b, cudaStream_t s);
+#define VIORB_FAST_GROUP 4      /* horizontally adjacent FAST cells per CTA (extractor_kernels.cu FAST_GROUP) */
 int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s);
 int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps,
                           uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s);
