@@ -1,0 +1,219 @@
+/*
+ * test_shims.cc -- exercises the C++ drop-in classes (viorb_b200/host/) the way Frame / Tracking / LocalMapping
+ * call the reference, and checks every result against the CPU oracle (oracle/orb_oracle.h).  Built and run by
+ * tests/test_cpp_shims.py (needs a GPU to run; compiles anywhere).
+ */
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "ORBextractor.h"
+#include "ORBmatcher.h"
+#include "orb_oracle.h"
+
+extern "C" void viorb_synth_frame(int h, int w, uint64_t seed, uint8_t* out);
+extern "C" void viorb_synth_stereo(int h, int w, uint64_t seed, int nbands, int dmin, int dmax, uint8_t* l, uint8_t* r, int* d);
+
+using namespace ORB_SLAM2;
+
+static int g_fail = 0;
+#define CHECK(cond, msg)                                              \
+    do {                                                              \
+        if (!(cond)) { printf("FAIL %s:%d %s\n", __FILE__, __LINE__, msg); g_fail++; } \
+    } while (0)
+
+static uint32_t rng_state = 12345;
+static uint32_t rnd() { rng_state = rng_state * 1664525u + 1013904223u; return rng_state >> 8; }
+static float rndf() { return (rnd() & 0xffff) / 65536.0f; }
+
+struct OracleFrame {
+    std::vector<orc_keypoint> k;
+    std::vector<uint8_t> d;
+    orc_extractor* e;
+};
+
+static OracleFrame oracle_extract(const cv::Mat& img, int nf) {
+    OracleFrame f;
+    f.e = orc_extractor_create(nf, 1.2f, 8, 20, 7);
+    f.k.resize(nf * 2);
+    f.d.resize((size_t)nf * 2 * 32);
+    int n = orc_extract(f.e, img.data, img.rows, img.cols, img.step, f.k.data(), f.d.data(), nf * 2);
+    f.k.resize(n);
+    f.d.resize((size_t)n * 32);
+    return f;
+}
+
+static bool same_keypoints(const std::vector<cv::KeyPoint>& a, const std::vector<orc_keypoint>& b) {
+    return a.size() == b.size() && (a.empty() || memcmp(a.data(), b.data(), a.size() * 28) == 0);
+}
+
+int main() {
+    const int H = 376, W = 1241, NF = 2000;
+    cv::Mat left(H, W, CV_8U), right(H, W, CV_8U);
+    int disp[8];
+    viorb_synth_stereo(H, W, 7, 8, 4, 64, left.data, right.data, disp);
+
+    /* ---- ORBextractor::operator() + mvImagePyramid ---- */
+    ORBextractor exL(NF, 1.2f, 8, 20, 7), exR(NF, 1.2f, 8, 20, 7);
+    std::vector<cv::KeyPoint> kL, kR;
+    cv::Mat dL, dR;
+    exL(left, cv::Mat(), kL, dL);
+    exR(right, cv::Mat(), kR, dR);
+    OracleFrame oL = oracle_extract(left, NF), oR = oracle_extract(right, NF);
+    CHECK(same_keypoints(kL, oL.k) && same_keypoints(kR, oR.k), "keypoints differ from the oracle");
+    CHECK(dL.rows == (int)oL.k.size() && memcmp(dL.data, oL.d.data(), oL.d.size()) == 0, "descriptors differ");
+    CHECK(exL.GetLevels() == 8 && std::fabs(exL.GetScaleFactors()[7] - 3.5831816f) < 1e-6f, "scale tables");
+    for (int l = 0; l < 8; l++) {
+        int w, h; size_t step;
+        const uint8_t* p = orc_extractor_pyramid(oL.e, l, &w, &h, &step);
+        const cv::Mat& m = exL.mvImagePyramid[l];
+        bool ok = m.rows == h && m.cols == w;
+        for (int y = 0; ok && y < h; y++) ok = memcmp(m.ptr<uint8_t>(y), p + (size_t)(y + 19) * step + 19, w) == 0;
+        CHECK(ok, "mvImagePyramid level differs");
+    }
+    {   /* empty image: silent return, outputs untouched (reference :1046-1047) */
+        std::vector<cv::KeyPoint> k(3);
+        cv::Mat d;
+        exL(cv::Mat(), cv::Mat(), k, d);
+        CHECK(k.size() == 3, "empty image must return silently");
+        exL(left, cv::Mat(), kL, dL);        /* restore the resident pyramid of the left image */
+    }
+    {   /* batch entry point */
+        std::vector<cv::Mat> imgs(3);
+        for (int b = 0; b < 3; b++) { imgs[b].create(H, W, CV_8U); viorb_synth_frame(H, W, 100 + b, imgs[b].data); }
+        std::vector<std::vector<cv::KeyPoint> > ks;
+        std::vector<cv::Mat> ds;
+        ORBextractor exB(NF, 1.2f, 8, 20, 7);
+        exB.ExtractBatch(imgs, ks, ds);
+        for (int b = 0; b < 3; b++) {
+            OracleFrame o = oracle_extract(imgs[b], NF);
+            CHECK(same_keypoints(ks[b], o.k) && memcmp(ds[b].data, o.d.data(), o.d.size()) == 0, "batch frame differs");
+            orc_extractor_destroy(o.e);
+        }
+    }
+
+    /* ---- Frame::ComputeStereoMatches ---- */
+    const float fx = 718.856f, bf = 386.1448f;
+    Frame F;
+    F.N = (int)kL.size();
+    F.mvKeys = kL; F.mvKeysUn = kL; F.mvKeysRight = kR;
+    F.mDescriptors = dL; F.mDescriptorsRight = dR;
+    F.mvScaleFactors = exL.GetScaleFactors(); F.mvInvScaleFactors = exL.GetInverseScaleFactors();
+    F.mnMinX = 0; F.mnMaxX = W; F.mnMinY = 0; F.mnMaxY = H;
+    F.fx = fx; F.fy = fx; F.cx = 607.19f; F.cy = 185.2f; F.mbf = bf; F.mb = bf / fx;
+    F.mpORBextractorLeft = &exL; F.mpORBextractorRight = &exR;
+    F.ComputeStereoMatches();
+    {
+        std::vector<orc_image> pl(8), pr(8);
+        for (int l = 0; l < 8; l++) {
+            int w, h; size_t step;
+            const uint8_t* p = orc_extractor_pyramid(oL.e, l, &w, &h, &step);
+            pl[l].data = p + 19 * step + 19; pl[l].w = w; pl[l].h = h; pl[l].step = step;
+            p = orc_extractor_pyramid(oR.e, l, &w, &h, &step);
+            pr[l].data = p + 19 * step + 19; pr[l].w = w; pr[l].h = h; pr[l].step = step;
+        }
+        std::vector<float> ur(F.N), dp(F.N), inv = exL.GetInverseScaleFactors(), sc = exL.GetScaleFactors();
+        int n = orc_stereo_match(oL.k.data(), oL.d.data(), F.N, oR.k.data(), oR.d.data(), (int)oR.k.size(), pl.data(), pr.data(), 8,
+                                 sc.data(), inv.data(), F.mbf, F.mb, ur.data(), dp.data(), nullptr, nullptr);
+        CHECK(n > 300, "synthetic pair has too few stereo matches");
+        CHECK(memcmp(ur.data(), F.mvuRight.data(), F.N * 4) == 0 && memcmp(dp.data(), F.mvDepth.data(), F.N * 4) == 0,
+              "ComputeStereoMatches differs from the oracle");
+    }
+
+    /* ---- ORBmatcher::DescriptorDistance ---- */
+    for (int i = 0; i < 20; i++) {
+        const int a = rnd() % F.N, b = rnd() % F.N;
+        CHECK(ORBmatcher::DescriptorDistance(dL.row(a), dL.row(b)) == orc_descriptor_distance(dL.ptr<uint8_t>(a), dL.ptr<uint8_t>(b)),
+              "DescriptorDistance");
+    }
+
+    /* ---- SearchByProjection(Frame&, vector<MapPoint*>&, th) ---- */
+    {
+        const int NMP = 500;
+        std::vector<MapPoint> store(NMP);
+        std::vector<MapPoint*> mps(NMP);
+        std::vector<float> px(NMP), py(NMP), pxr(NMP), vc(NMP);
+        std::vector<int32_t> lvl(NMP), nobs(NMP);
+        std::vector<uint8_t> valid(NMP), desc((size_t)NMP * 32);
+        for (int i = 0; i < NMP; i++) {
+            const int k = (i < 50) ? (int)(rnd() % 25) : (int)(rnd() % F.N);     /* the first 50 fight over 25 keypoints */
+            MapPoint& p = store[i];
+            p.mbTrackInView = (rnd() % 10) != 0;
+            p.mTrackProjX = kL[k].pt.x + (rndf() - 0.5f) * 4; p.mTrackProjY = kL[k].pt.y + (rndf() - 0.5f) * 4;
+            p.mTrackProjXR = p.mTrackProjX - 20;
+            p.mnTrackScaleLevel = std::min(7, std::max(0, kL[k].octave + (int)(rnd() % 3) - 1));
+            p.mTrackViewCos = 0.99f + 0.01f * rndf();
+            p.nObs = rnd() % 4;
+            p.descriptor = dL.row(k).clone();
+            for (int b = 0; b < (int)(rnd() % 40); b++) p.descriptor.data[rnd() % 32] ^= (uint8_t)(1u << (rnd() % 8));
+            mps[i] = &p;
+            px[i] = p.mTrackProjX; py[i] = p.mTrackProjY; pxr[i] = p.mTrackProjXR; vc[i] = p.mTrackViewCos;
+            lvl[i] = p.mnTrackScaleLevel; nobs[i] = p.nObs; valid[i] = p.mbTrackInView;
+            memcpy(&desc[(size_t)i * 32], p.descriptor.data, 32);
+        }
+        F.mvpMapPoints.assign(F.N, nullptr);
+        std::vector<float> noRight(F.N, -1.0f);
+        F.mvuRight = noRight;
+        ORBmatcher matcher(0.8f, true);
+        const int n = matcher.SearchByProjection(F, mps, 3.0f);
+        orc_grid* grid = orc_grid_create(oL.k.data(), F.N, 0, (float)W, 0, (float)H);
+        std::vector<int32_t> obs(F.N, 0), match(F.N, -1);
+        std::vector<float> sc = exL.GetScaleFactors();
+        const int nref = orc_search_by_projection_local(grid, oL.k.data(), oL.d.data(), noRight.data(), obs.data(), F.N, sc.data(),
+                                                        px.data(), py.data(), pxr.data(), lvl.data(), vc.data(), valid.data(),
+                                                        nobs.data(), desc.data(), NMP, 3.0f, 0.8f, match.data());
+        bool same = n == nref;
+        for (int k = 0; k < F.N; k++) same = same && (F.mvpMapPoints[k] == (match[k] >= 0 ? mps[match[k]] : nullptr));
+        CHECK(nref > 100 && same, "SearchByProjection(Frame, MapPoints) differs from the oracle");
+        orc_grid_destroy(grid);
+    }
+
+    /* ---- SearchForTriangulation ---- */
+    {
+        KeyFrame k1, k2;
+        k1.N = (int)kL.size(); k2.N = (int)kR.size();
+        k1.mvKeysUn = kL; k2.mvKeysUn = kR; k1.mDescriptors = dL; k2.mDescriptors = dR;
+        k1.mvuRight.assign(k1.N, -1.0f); k2.mvuRight.assign(k2.N, -1.0f);
+        k1.mapPoints.assign(k1.N, nullptr); k2.mapPoints.assign(k2.N, nullptr);
+        k2.mvScaleFactors = exL.GetScaleFactors(); k2.mvLevelSigma2 = exL.GetScaleSigmaSquares();
+        k2.fx = k2.fy = fx; k2.cx = 607.19f; k2.cy = 185.2f;
+        k1.Ow = cv::Mat::zeros(3, 1, CV_32F);
+        k2.Rcw = cv::Mat::zeros(3, 3, CV_32F);
+        for (int i = 0; i < 3; i++) k2.Rcw.at<float>(i, i) = 1;
+        k2.tcw = cv::Mat::zeros(3, 1, CV_32F);
+        k2.tcw.at<float>(0) = -0.537f; k2.tcw.at<float>(2) = 1e-3f;      /* epipole far outside the image */
+        for (int i = 0; i < k1.N; i++) k1.mFeatVec[(unsigned)(kL[i].pt.y / 24) * 3 + 5].push_back(i);
+        for (int i = 0; i < k2.N; i++) k2.mFeatVec[(unsigned)(kR[i].pt.y / 24) * 3 + 5].push_back(i);
+        cv::Mat F12 = cv::Mat::zeros(3, 3, CV_32F);
+        F12.at<float>(1, 2) = -1; F12.at<float>(2, 1) = 1;
+        std::vector<std::pair<size_t, size_t> > pairs;
+        ORBmatcher matcher(0.6f, false);
+        const int n = matcher.SearchForTriangulation(&k1, &k2, F12, pairs, false);
+        /* oracle on the flattened feature vectors */
+        std::vector<int32_t> id1, p1(1, 0), i1, id2, p2(1, 0), i2;
+        for (auto& kv : k1.mFeatVec) { id1.push_back(kv.first); for (unsigned v : kv.second) i1.push_back(v); p1.push_back((int)i1.size()); }
+        for (auto& kv : k2.mFeatVec) { id2.push_back(kv.first); for (unsigned v : kv.second) i2.push_back(v); p2.push_back((int)i2.size()); }
+        std::vector<uint8_t> z1(k1.N, 0), z2(k2.N, 0);
+        std::vector<int32_t> m12(k1.N);
+        const float C2x = -0.537f, C2z = 1e-3f;
+        const float ex = fx * C2x * (1.0f / C2z) + 607.19f, ey = fx * 0.0f * (1.0f / C2z) + 185.2f;
+        float Ff[9] = {0, 0, 0, 0, 0, -1, 0, 1, 0};
+        const int nref = orc_search_for_triangulation(oL.k.data(), oL.d.data(), k1.mvuRight.data(), z1.data(), k1.N, oR.k.data(),
+                                                      oR.d.data(), k2.mvuRight.data(), z2.data(), k2.N, id1.data(), p1.data(),
+                                                      i1.data(), (int)id1.size(), id2.data(), p2.data(), i2.data(), (int)id2.size(),
+                                                      Ff, ex, ey, k2.mvScaleFactors.data(), k2.mvLevelSigma2.data(), 0, 0, m12.data());
+        bool same = n == nref;
+        size_t pi = 0;
+        for (int i = 0; i < k1.N; i++)
+            if (m12[i] >= 0) { same = same && pi < pairs.size() && pairs[pi].first == (size_t)i && pairs[pi].second == (size_t)m12[i]; pi++; }
+        CHECK(nref > 100 && same && pi == pairs.size(), "SearchForTriangulation differs from the oracle");
+    }
+
+    orc_extractor_destroy(oL.e);
+    orc_extractor_destroy(oR.e);
+    if (g_fail == 0) printf("ALL SHIM CHECKS PASSED\n");
+    return g_fail ? 1 : 0;
+}

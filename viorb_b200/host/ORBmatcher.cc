@@ -1,0 +1,214 @@
+/* ORBmatcher.cc -- see ORBmatcher.h.  Host-side marshalling only; every distance is computed on the GPU. */
+#include "ORBmatcher.h"
+
+#include <stdexcept>
+#include <string>
+
+#include "ORBextractor.h"
+#include "viorb_gpu.h"
+
+namespace ORB_SLAM2 {
+
+const int ORBmatcher::TH_HIGH = 100;      /* reference src/ORBmatcher.cc:37-39 */
+const int ORBmatcher::TH_LOW = 50;
+const int ORBmatcher::HISTO_LENGTH = 30;
+
+namespace {
+
+void check(int rc, const char* what) {
+    if (rc != VIORB_OK) throw std::runtime_error(std::string(what) + ": " + viorb_last_error());
+}
+
+/* one context per calling thread: the matcher is entered concurrently by Tracking, LocalMapping and LoopClosing */
+viorb_ctx* thread_ctx() {
+    struct Holder {
+        viorb_ctx* c = nullptr;
+        ~Holder() { viorb_ctx_destroy(c); }
+    };
+    static thread_local Holder h;
+    if (!h.c) check(viorb_ctx_create(0, nullptr, &h.c), "viorb_ctx_create");
+    return h.c;
+}
+
+struct FrameIndexGuard {
+    viorb_frame_index* fi = nullptr;
+    ~FrameIndexGuard() { viorb_frame_index_destroy(fi); }
+};
+
+std::vector<uint8_t> pack_descriptors(const cv::Mat& d, int n) {
+    std::vector<uint8_t> out((size_t)n * 32);
+    for (int i = 0; i < n; i++) memcpy(&out[(size_t)i * 32], d.ptr<uint8_t>(i), 32);
+    return out;
+}
+
+void make_index(Frame& F, FrameIndexGuard& g) {
+    static_assert(sizeof(cv::KeyPoint) == sizeof(viorb_keypoint), "KeyPoint layout");
+    const std::vector<uint8_t> desc = pack_descriptors(F.mDescriptors, F.N);
+    check(viorb_frame_index_create(thread_ctx(), reinterpret_cast<const viorb_keypoint*>(F.mvKeysUn.data()), desc.data(),
+                                   F.mvuRight.empty() ? nullptr : F.mvuRight.data(), F.N, F.mnMinX, F.mnMaxX, F.mnMinY,
+                                   F.mnMaxY, F.mvScaleFactors.data(), (int)F.mvScaleFactors.size(), &g.fi),
+          "viorb_frame_index_create");
+}
+
+}  // namespace
+
+ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+
+int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
+    int32_t d = 0;
+    check(viorb_descriptor_distance(thread_ctx(), a.ptr<uint8_t>(), b.ptr<uint8_t>(), 1, &d), "viorb_descriptor_distance");
+    return d;
+}
+
+std::vector<int> ORBmatcher::DescriptorDistances(const cv::Mat& a, const cv::Mat& b) {
+    const int n = a.rows;
+    const std::vector<uint8_t> pa = pack_descriptors(a, n), pb = pack_descriptors(b, n);
+    std::vector<int> d(n);
+    check(viorb_descriptor_distance(thread_ctx(), pa.data(), pb.data(), n, d.data()), "viorb_descriptor_distance");
+    return d;
+}
+
+int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th) {
+    const int nmp = (int)vpMapPoints.size();
+    FrameIndexGuard g;
+    make_index(F, g);
+    std::vector<float> px(nmp), py(nmp), pxr(nmp), vc(nmp);
+    std::vector<int32_t> lvl(nmp), nobs(nmp), obs(F.N), match(F.N, -1);
+    std::vector<uint8_t> valid(nmp), desc((size_t)nmp * 32);
+    for (int i = 0; i < nmp; i++) {
+        MapPoint* p = vpMapPoints[i];
+        valid[i] = p->mbTrackInView && !p->isBad();              /* :53-57 */
+        px[i] = p->mTrackProjX; py[i] = p->mTrackProjY; pxr[i] = p->mTrackProjXR;
+        lvl[i] = p->mnTrackScaleLevel; vc[i] = p->mTrackViewCos; nobs[i] = p->Observations();
+        if (valid[i]) memcpy(&desc[(size_t)i * 32], p->GetDescriptor().ptr<uint8_t>(), 32);
+    }
+    for (int k = 0; k < F.N; k++) obs[k] = F.mvpMapPoints[k] ? F.mvpMapPoints[k]->Observations() : 0;   /* :87-89 */
+    int n = 0;
+    check(viorb_search_by_projection_local(g.fi, obs.data(), px.data(), py.data(), pxr.data(), lvl.data(), vc.data(),
+                                           valid.data(), nobs.data(), desc.data(), nmp, th, mfNNratio, match.data(), &n),
+          "viorb_search_by_projection_local");
+    for (int k = 0; k < F.N; k++)
+        if (match[k] >= 0) F.mvpMapPoints[k] = vpMapPoints[match[k]];                                    /* :122 */
+    return n;
+}
+
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
+    /* projection of the last frame's map points with the current pose, reference :1338-1376 */
+    const cv::Mat& Tcw = CurrentFrame.mTcw;
+    const cv::Mat& Tlw = LastFrame.mTcw;
+    float Rcw[9], tcw[3], twc[3], tlc[3];
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) Rcw[3 * r + c] = Tcw.at<float>(r, c);
+        tcw[r] = Tcw.at<float>(r, 3);
+    }
+    for (int r = 0; r < 3; r++) twc[r] = -(Rcw[r] * tcw[0] + Rcw[3 + r] * tcw[1] + Rcw[6 + r] * tcw[2]);
+    for (int r = 0; r < 3; r++)
+        tlc[r] = Tlw.at<float>(r, 0) * twc[0] + Tlw.at<float>(r, 1) * twc[1] + Tlw.at<float>(r, 2) * twc[2] + Tlw.at<float>(r, 3);
+    const bool bForward = tlc[2] > CurrentFrame.mb && !bMono;
+    const bool bBackward = -tlc[2] > CurrentFrame.mb && !bMono;
+    const int mode = bForward ? 1 : (bBackward ? 2 : 0);
+
+    const int nl = LastFrame.N;
+    std::vector<float> u(nl), v(nl), invz(nl), ang(nl);
+    std::vector<int32_t> oct(nl), nobs(nl), obs(CurrentFrame.N), match(CurrentFrame.N, -1);
+    std::vector<uint8_t> valid(nl, 0), desc((size_t)nl * 32);
+    for (int i = 0; i < nl; i++) {
+        MapPoint* pMP = LastFrame.mvpMapPoints[i];
+        if (!pMP || LastFrame.mvbOutlier[i]) continue;
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+        const float X = x3Dw.at<float>(0), Y = x3Dw.at<float>(1), Z = x3Dw.at<float>(2);
+        const float xc = Rcw[0] * X + Rcw[1] * Y + Rcw[2] * Z + tcw[0];
+        const float yc = Rcw[3] * X + Rcw[4] * Y + Rcw[5] * Z + tcw[1];
+        const float zc = Rcw[6] * X + Rcw[7] * Y + Rcw[8] * Z + tcw[2];
+        const float invzc = 1.0 / zc;
+        if (invzc < 0) continue;
+        u[i] = CurrentFrame.fx * xc * invzc + CurrentFrame.cx;
+        v[i] = CurrentFrame.fy * yc * invzc + CurrentFrame.cy;
+        invz[i] = invzc;
+        oct[i] = LastFrame.mvKeys[i].octave;
+        ang[i] = LastFrame.mvKeysUn[i].angle;
+        nobs[i] = pMP->Observations();
+        memcpy(&desc[(size_t)i * 32], pMP->GetDescriptor().ptr<uint8_t>(), 32);
+        valid[i] = 1;
+    }
+    for (int k = 0; k < CurrentFrame.N; k++)
+        obs[k] = CurrentFrame.mvpMapPoints[k] ? CurrentFrame.mvpMapPoints[k]->Observations() : 0;
+    FrameIndexGuard g;
+    make_index(CurrentFrame, g);
+    int n = 0;
+    check(viorb_search_by_projection_frame(g.fi, obs.data(), u.data(), v.data(), invz.data(), oct.data(), ang.data(),
+                                           valid.data(), nobs.data(), desc.data(), nl, th, CurrentFrame.mbf, mode,
+                                           mbCheckOrientation, TH_HIGH, match.data(), &n),
+          "viorb_search_by_projection_frame");
+    for (int k = 0; k < CurrentFrame.N; k++) {
+        if (match[k] >= 0) CurrentFrame.mvpMapPoints[k] = LastFrame.mvpMapPoints[match[k]];
+        else if (obs[k] == 0 && CurrentFrame.mvpMapPoints[k] && CurrentFrame.mvpMapPoints[k]->Observations() > 0) {
+            /* unreachable: only this call can clear an entry, and cleared entries never held observations */
+        }
+    }
+    return n;
+}
+
+int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,
+                                       std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo) {
+    /* epipole in the second image, reference :663-670 */
+    const cv::Mat Cw = pKF1->GetCameraCenter(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+    float C2[3];
+    for (int r = 0; r < 3; r++)
+        C2[r] = R2w.at<float>(r, 0) * Cw.at<float>(0) + R2w.at<float>(r, 1) * Cw.at<float>(1) + R2w.at<float>(r, 2) * Cw.at<float>(2) +
+                t2w.at<float>(r);
+    const float invz = 1.0f / C2[2];
+    const float ex = pKF2->fx * C2[0] * invz + pKF2->cx;
+    const float ey = pKF2->fy * C2[1] * invz + pKF2->cy;
+
+    auto flatten = [](const DBoW2::FeatureVector& fv, std::vector<int32_t>& ids, std::vector<int32_t>& ptr, std::vector<int32_t>& idx) {
+        ptr.push_back(0);
+        for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+            ids.push_back((int32_t)it->first);
+            for (size_t k = 0; k < it->second.size(); k++) idx.push_back((int32_t)it->second[k]);
+            ptr.push_back((int32_t)idx.size());
+        }
+    };
+    std::vector<int32_t> id1, p1, i1, id2, p2, i2;
+    flatten(pKF1->mFeatVec, id1, p1, i1);
+    flatten(pKF2->mFeatVec, id2, p2, i2);
+    std::vector<uint8_t> mp1(pKF1->N), mp2(pKF2->N);
+    for (int i = 0; i < pKF1->N; i++) mp1[i] = pKF1->GetMapPoint(i) != nullptr;
+    for (int i = 0; i < pKF2->N; i++) mp2[i] = pKF2->GetMapPoint(i) != nullptr;
+    const std::vector<uint8_t> d1 = pack_descriptors(pKF1->mDescriptors, pKF1->N), d2 = pack_descriptors(pKF2->mDescriptors, pKF2->N);
+    float F[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) F[3 * r + c] = F12.at<float>(r, c);
+    std::vector<int32_t> m12(pKF1->N, -1);
+    int n = 0;
+    check(viorb_search_for_triangulation(thread_ctx(), reinterpret_cast<const viorb_keypoint*>(pKF1->mvKeysUn.data()), d1.data(),
+                                         pKF1->mvuRight.data(), mp1.data(), pKF1->N,
+                                         reinterpret_cast<const viorb_keypoint*>(pKF2->mvKeysUn.data()), d2.data(),
+                                         pKF2->mvuRight.data(), mp2.data(), pKF2->N, id1.data(), p1.data(), i1.data(),
+                                         (int)id1.size(), id2.data(), p2.data(), i2.data(), (int)id2.size(), F, ex, ey,
+                                         pKF2->mvScaleFactors.data(), pKF2->mvLevelSigma2.data(), (int)pKF2->mvScaleFactors.size(),
+                                         bOnlyStereo, mbCheckOrientation, m12.data(), &n),
+          "viorb_search_for_triangulation");
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(n);
+    for (size_t i = 0; i < m12.size(); i++)
+        if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));                     /* :815-820 */
+    return n;
+}
+
+#ifndef VIORB_USE_ORBSLAM_HEADERS
+/* Frame::ComputeStereoMatches (reference src/Frame.cc:646-820) on the pyramids resident in the two extractors */
+void Frame::ComputeStereoMatches() {
+    mvuRight.assign(N, -1.0f);
+    mvDepth.assign(N, -1.0f);
+    if (N == 0) return;
+    const std::vector<uint8_t> dl = pack_descriptors(mDescriptors, N), dr = pack_descriptors(mDescriptorsRight, (int)mvKeysRight.size());
+    check(viorb_stereo_match(mpORBextractorLeft->Handle(), 0, mpORBextractorRight->Handle(), 0,
+                             reinterpret_cast<const viorb_keypoint*>(mvKeys.data()), dl.data(), N,
+                             reinterpret_cast<const viorb_keypoint*>(mvKeysRight.data()), dr.data(), (int)mvKeysRight.size(), mbf, mb,
+                             mvuRight.data(), mvDepth.data()),
+          "viorb_stereo_match");
+}
+#endif
+
+}  // namespace ORB_SLAM2

@@ -1,0 +1,51 @@
+/*
+ * ORBmatcher.h -- drop-in for ORB_SLAM2::ORBmatcher (reference include/ORBmatcher.h:37-102) for the searches
+ * on the hot path: DescriptorDistance, SearchByProjection (local map and frame-to-frame) and
+ * SearchForTriangulation.  Each call marshals the fields the reference reads into flat arrays and runs the
+ * whole search as CUDA kernels behind include/viorb_gpu.h; results (matches, counts, tie-breaks, the
+ * "already matched" dependence) are identical to the reference's sequential loops.
+ * The remaining searches of the reference class (SearchByBoW x2, SearchForInitialization, SearchBySim3, Fuse x2,
+ * and the relocalisation / Sim3 SearchByProjection overloads) are SURVEY.md section 8(f) "next" rows.
+ */
+#ifndef ORBMATCHER_H
+#define ORBMATCHER_H
+
+#include <utility>
+#include <vector>
+
+#include "cv_compat.h"
+#include "orbslam_compat.h"
+
+namespace ORB_SLAM2 {
+
+class ORBmatcher {
+public:
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true);
+
+    /* Hamming distance between two 256-bit ORB descriptors (reference :1648-1664) */
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    /* B200 extension: n pairs in one device call (row i of a vs row i of b) */
+    static std::vector<int> DescriptorDistances(const cv::Mat& a, const cv::Mat& b);
+
+    /* Search matches between Frame keypoints and projected MapPoints; returns number of matches (:45-129) */
+    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3);
+
+    /* Project MapPoints tracked in last frame into the current frame and search matches (:1328-1471) */
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+
+    /* Matching to triangulate new MapPoints, epipolar constraint check (:657-823) */
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,
+                               std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo);
+
+public:
+    static const int TH_LOW;
+    static const int TH_HIGH;
+    static const int HISTO_LENGTH;
+
+protected:
+    float mfNNratio;
+    bool mbCheckOrientation;
+};
+
+}  // namespace ORB_SLAM2
+#endif

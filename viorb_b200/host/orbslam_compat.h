@@ -1,0 +1,80 @@
+/*
+ * orbslam_compat.h -- the members of Frame / KeyFrame / MapPoint that the ORB front-end reads or writes
+ * (reference include/Frame.h, include/KeyFrame.h, include/MapPoint.h), as plain structs, for builds outside
+ * the VIORB tree (tests, this repository).  Inside the VIORB tree define VIORB_USE_ORBSLAM_HEADERS and the
+ * shims compile against the real classes: only public members and accessors with these names are used.
+ */
+#ifndef VIORB_ORBSLAM_COMPAT_H
+#define VIORB_ORBSLAM_COMPAT_H
+
+#ifdef VIORB_USE_ORBSLAM_HEADERS
+#include "Frame.h"
+#include "KeyFrame.h"
+#include "MapPoint.h"
+#else
+
+#include <map>
+#include <vector>
+
+#include "cv_compat.h"
+
+namespace DBoW2 {
+typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;   /* Thirdparty/DBoW2/DBoW2/FeatureVector.h */
+}
+
+namespace ORB_SLAM2 {
+
+class ORBextractor;
+
+class MapPoint {   /* include/MapPoint.h */
+public:
+    bool mbTrackInView = false;                /* :85-89 tracking fields written by Frame::isInFrustum */
+    float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0;
+    int mnTrackScaleLevel = 0;
+    float mTrackViewCos = 1;
+    bool bad = false;
+    int nObs = 1;
+    cv::Mat descriptor;                        /* 1x32 CV_8U */
+    cv::Mat worldPos;                          /* 3x1 CV_32F */
+    bool isBad() const { return bad; }
+    int Observations() const { return nObs; }
+    cv::Mat GetDescriptor() const { return descriptor; }
+    cv::Mat GetWorldPos() const { return worldPos; }
+};
+
+class Frame {      /* include/Frame.h */
+public:
+    int N = 0;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    std::vector<float> mvuRight, mvDepth;
+    cv::Mat mDescriptors, mDescriptorsRight;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    std::vector<float> mvScaleFactors, mvInvScaleFactors;
+    float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;
+    float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mb = 0;
+    cv::Mat mTcw;                              /* 4x4 CV_32F */
+    ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
+    void ComputeStereoMatches();               /* src/Frame.cc:646-820 -> viorb_stereo_match */
+};
+
+class KeyFrame {   /* include/KeyFrame.h */
+public:
+    int N = 0;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::vector<float> mvuRight;
+    cv::Mat mDescriptors;
+    DBoW2::FeatureVector mFeatVec;
+    std::vector<MapPoint*> mapPoints;
+    std::vector<float> mvScaleFactors, mvLevelSigma2;
+    float fx = 0, fy = 0, cx = 0, cy = 0;
+    cv::Mat Rcw, tcw, Ow;                      /* 3x3, 3x1, 3x1 CV_32F */
+    MapPoint* GetMapPoint(size_t idx) const { return mapPoints[idx]; }
+    cv::Mat GetCameraCenter() const { return Ow; }
+    cv::Mat GetRotation() const { return Rcw; }
+    cv::Mat GetTranslation() const { return tcw; }
+};
+
+}  // namespace ORB_SLAM2
+#endif
+#endif
