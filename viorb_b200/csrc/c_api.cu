@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -88,13 +89,21 @@ struct viorb_extractor {
     DevBuf<int4> groups;           /* FAST cell groups: {level, cell row, first cell, cells} */
     int ngroups = 0;
     ResizeTables tables;
-    /* pass workspace */
-    int allocFrames = 0;
-    ExtractBuffers buf;
-    DevBuf<uint8_t> pyr;
-    DevBuf<uint32_t> cand, sel;
-    DevBuf<int> counters;          /* candCount | selCount | status */
-    DevBuf<uint16_t> nodeOf;
+    /* pass workspaces: consecutive passes alternate between two lanes (own stream + buffers) so that the
+     * latency-bound kernels of one pass overlap with those of the next */
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t evDone = nullptr;
+        int allocFrames = 0;
+        ExtractBuffers buf = {};
+        DevBuf<uint8_t> pyr;
+        DevBuf<uint32_t> cand, sel;
+        DevBuf<int> counters;      /* candCount | selCount | status */
+        DevBuf<uint16_t> nodeOf;
+    } lanes[2];
+    int nlanes = 2;
+    cudaEvent_t evFork = nullptr;
+    ExtractBuffers buf = {};       /* buffers of the most recent pass (resident pyramids, debug views) */
     /* staging for host-buffer entry points (double buffered) */
     DevBuf<uint8_t> in[2];
     DevBuf<viorb_keypoint> okps[2];
@@ -146,6 +155,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     FrameGeom& g = e->geom;
     memset(&g, 0, sizeof(g));
     g.nlevels = e->nlevels; g.rows = rows; g.cols = cols; g.iniTh = e->iniTh; g.minTh = e->minTh;
+    g.dbg = getenv("VIORB_DEBUG") ? atoi(getenv("VIORB_DEBUG")) : 0;
     size_t pyrOff = 0;
     int cellBase = 0, candBase = 0, selBase = 0, xtab = 0, ytab = 0, nodeCap = 0;
     for (int l = 0; l < e->nlevels; l++) {
@@ -248,37 +258,44 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     cudaError_t ce = (cudaError_t)viorb_octree_prepare(nodeCap);
     if (ce != cudaSuccess) return fail(VIORB_ERR_CUDA, "octree kernel attribute: %s", cudaGetErrorString(ce));
     e->rows = rows; e->cols = cols;
-    e->allocFrames = 0;
+    for (int i = 0; i < 2; i++) e->lanes[i].allocFrames = 0;
     return VIORB_OK;
 }
 
 int ensure_workspace(viorb_extractor* e, int F) {
-    if (F <= e->allocFrames) return VIORB_OK;
     const FrameGeom& g = e->geom;
-    int rc;
-    if ((rc = e->pyr.ensure((size_t)F * g.pyrFrameBytes))) return rc;
-    if ((rc = e->cand.ensure((size_t)F * g.candPerFrame))) return rc;
-    if ((rc = e->nodeOf.ensure((size_t)F * g.candPerFrame))) return rc;
-    if ((rc = e->sel.ensure((size_t)F * g.selPerFrame))) return rc;
-    if ((rc = e->counters.ensure((size_t)F * g.nlevels * 2 + 4))) return rc;
-    CU(cudaMemsetAsync(e->counters.p, 0, e->counters.n * sizeof(int), e->ctx->stream));
-    e->buf.pyr = e->pyr.p;
-    e->buf.cand = e->cand.p;
-    e->buf.nodeOf = e->nodeOf.p;
-    e->buf.sel = e->sel.p;
-    e->buf.candCount = e->counters.p;
-    e->buf.selCount = e->counters.p + (size_t)F * g.nlevels;
-    e->buf.status = e->counters.p + (size_t)F * g.nlevels * 2;
-    e->allocFrames = F;
+    for (int li = 0; li < e->nlanes; li++) {
+        viorb_extractor::Lane& ln = e->lanes[li];
+        if (F <= ln.allocFrames) continue;
+        int rc;
+        if ((rc = ln.pyr.ensure((size_t)F * g.pyrFrameBytes))) return rc;
+        if ((rc = ln.cand.ensure((size_t)F * g.candPerFrame))) return rc;
+        if ((rc = ln.nodeOf.ensure((size_t)F * g.candPerFrame))) return rc;
+        if ((rc = ln.sel.ensure((size_t)F * g.selPerFrame))) return rc;
+        if ((rc = ln.counters.ensure((size_t)F * g.nlevels * 2 + 4))) return rc;
+        CU(cudaMemsetAsync(ln.counters.p, 0, ln.counters.n * sizeof(int), e->ctx->stream));
+        ln.buf.pyr = ln.pyr.p;
+        ln.buf.cand = ln.cand.p;
+        ln.buf.nodeOf = ln.nodeOf.p;
+        ln.buf.sel = ln.sel.p;
+        ln.buf.candCount = ln.counters.p;
+        ln.buf.selCount = ln.counters.p + (size_t)F * g.nlevels;
+        ln.buf.status = ln.counters.p + (size_t)F * g.nlevels * 2;
+        ln.allocFrames = F;
+    }
+    CU(cudaStreamSynchronize(e->ctx->stream));
+    e->buf = e->lanes[0].buf;
     return VIORB_OK;
 }
 
 /* one device pass over F frames already resident on the device */
-int run_pass(viorb_extractor* e, const uint8_t* d_images, size_t step, size_t frameStride, int F,
+int run_pass(viorb_extractor* e, int lane, const uint8_t* d_images, size_t step, size_t frameStride, int F,
              viorb_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_counts) {
     viorb_ctx* c = e->ctx;
     const FrameGeom& g = e->geom;
-    CU(cudaMemsetAsync(e->buf.candCount, 0, (size_t)F * g.nlevels * sizeof(int), c->stream));
+    viorb_extractor::Lane& ln = e->lanes[lane];
+    cudaStream_t st = ln.stream;
+    CU(cudaMemsetAsync(ln.buf.candCount, 0, (size_t)F * g.nlevels * sizeof(int), st));
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (e->profiling)
         for (int i = 0; i < 5; i++) {
@@ -286,26 +303,50 @@ int run_pass(viorb_extractor* e, const uint8_t* d_images, size_t step, size_t fr
             else { ev[i] = e->profPool.back(); e->profPool.pop_back(); }
             e->profEvents.push_back(ev[i]);
         }
-    if (e->profiling) CU(cudaEventRecord(ev[0], c->stream));
-    c->launches += viorb_launch_pyramid(g, e->tables, d_images, step, frameStride, F, e->buf, c->stream);
-    if (e->profiling) CU(cudaEventRecord(ev[1], c->stream));
-    c->launches += viorb_launch_fast(g, e->groups.p, e->ngroups, F, e->buf, c->stream);
-    if (e->profiling) CU(cudaEventRecord(ev[2], c->stream));
-    c->launches += viorb_launch_octree(g, F, e->buf, e->nodeCap, c->stream);
-    if (e->profiling) CU(cudaEventRecord(ev[3], c->stream));
-    c->launches += viorb_launch_describe(g, F, e->buf, d_kps, d_desc, cap, d_counts, c->stream);
-    if (e->profiling) CU(cudaEventRecord(ev[4], c->stream));
+    if (e->profiling) CU(cudaEventRecord(ev[0], st));
+    c->launches += viorb_launch_pyramid(g, e->tables, d_images, step, frameStride, F, ln.buf, st);
+    if (e->profiling) CU(cudaEventRecord(ev[1], st));
+    c->launches += viorb_launch_fast(g, e->groups.p, e->ngroups, F, ln.buf, st);
+    if (e->profiling) CU(cudaEventRecord(ev[2], st));
+    c->launches += viorb_launch_octree(g, F, ln.buf, e->nodeCap, st);
+    if (e->profiling) CU(cudaEventRecord(ev[3], st));
+    c->launches += viorb_launch_describe(g, F, ln.buf, d_kps, d_desc, cap, d_counts, st);
+    if (e->profiling) CU(cudaEventRecord(ev[4], st));
     CU(cudaGetLastError());
+    e->buf = ln.buf;
+    return VIORB_OK;
+}
+
+/* lanes start after everything already queued on the context stream ... */
+int lanes_fork(viorb_extractor* e) {
+    CU(cudaEventRecord(e->evFork, e->ctx->stream));
+    for (int li = 0; li < e->nlanes; li++) CU(cudaStreamWaitEvent(e->lanes[li].stream, e->evFork, 0));
+    return VIORB_OK;
+}
+
+/* ... and the context stream continues after both lanes have drained */
+int lanes_join(viorb_extractor* e) {
+    for (int li = 0; li < e->nlanes; li++) {
+        CU(cudaEventRecord(e->lanes[li].evDone, e->lanes[li].stream));
+        CU(cudaStreamWaitEvent(e->ctx->stream, e->lanes[li].evDone, 0));
+    }
     return VIORB_OK;
 }
 
 int check_status(viorb_extractor* e) {
     int st = 0;
-    CU(cudaMemcpyAsync(&st, e->buf.status, sizeof(int), cudaMemcpyDeviceToHost, e->ctx->stream));
+    for (int li = 0; li < e->nlanes; li++) {
+        int s1 = 0;
+        if (!e->lanes[li].buf.status) continue;
+        CU(cudaStreamSynchronize(e->lanes[li].stream));
+        CU(cudaMemcpyAsync(&s1, e->lanes[li].buf.status, sizeof(int), cudaMemcpyDeviceToHost, e->ctx->stream));
+        CU(cudaStreamSynchronize(e->ctx->stream));
+        if (s1) cudaMemsetAsync(e->lanes[li].buf.status, 0, sizeof(int), e->ctx->stream);
+        st |= s1;
+    }
     CU(cudaStreamSynchronize(e->ctx->stream));
     e->lastOverflow = st;
     if (st) {
-        cudaMemsetAsync(e->buf.status, 0, sizeof(int), e->ctx->stream);
         if (st & VIORB_DEV_CAND_OVERFLOW)
             return fail(VIORB_ERR_CAPACITY, "FAST candidate pool overflow (raise it with viorb_extractor_configure cand_div)");
         if (st & VIORB_DEV_OUT_OVERFLOW) return fail(VIORB_ERR_CAPACITY, "more keypoints than the caller's capacity");
@@ -395,7 +436,7 @@ int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, in
                            viorb_extractor** out) {
     if (!ctx || !out) return fail(VIORB_ERR_INVALID, "NULL argument");
     *out = nullptr;
-    if (nfeatures <= 0 || nlevels < 1 || nlevels > VIORB_MAX_LEVELS || !(scale_factor > 1.0f) || ini < mn || mn < 1 || ini > 255)
+    if (nfeatures <= 0 || nlevels < 1 || nlevels > VIORB_MAX_LEVELS || !(scale_factor > 1.0f) || ini < mn || mn < 1 || mn > 127 || ini > 255)
         return fail(VIORB_ERR_INVALID, "bad ORB parameters (nfeatures %d, scale %f, levels %d, FAST %d/%d)", nfeatures,
                     scale_factor, nlevels, ini, mn);
     if (scale_factor > 1.5f)
@@ -408,7 +449,10 @@ int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, in
     e->scaleFactor = scale_factor;
     build_tables(e);
     if (ctx_bind(ctx)) { delete e; return VIORB_ERR_CUDA; }
+    cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
     for (int i = 0; i < 2; i++) {
+        cudaStreamCreateWithFlags(&e->lanes[i].stream, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&e->lanes[i].evDone, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->evIn[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->evDone[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->evOut[i], cudaEventDisableTiming);
@@ -423,8 +467,14 @@ int viorb_extractor_destroy(viorb_extractor* e) {
     cudaStreamSynchronize(e->ctx->stream);
     cudaStreamSynchronize(e->ctx->h2d);
     cudaStreamSynchronize(e->ctx->d2h);
-    e->tabU16.release(); e->tabI16.release(); e->groups.release(); e->pyr.release(); e->cand.release(); e->sel.release();
-    e->counters.release(); e->nodeOf.release();
+    e->tabU16.release(); e->tabI16.release(); e->groups.release();
+    for (int i = 0; i < 2; i++) {
+        viorb_extractor::Lane& ln = e->lanes[i];
+        if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
+        if (ln.evDone) cudaEventDestroy(ln.evDone);
+        ln.pyr.release(); ln.cand.release(); ln.sel.release(); ln.counters.release(); ln.nodeOf.release();
+    }
+    if (e->evFork) cudaEventDestroy(e->evFork);
     for (int i = 0; i < 2; i++) {
         e->in[i].release(); e->okps[i].release(); e->odesc[i].release(); e->ocnt[i].release();
         if (e->evIn[i]) cudaEventDestroy(e->evIn[i]);
@@ -513,21 +563,23 @@ int viorb_extract_batch_device(viorb_extractor* e, const uint8_t* d_images, int 
     if ((rc = build_geometry(e, rows, cols))) return rc;
     const int F = std::min(e->chunk, B);
     if ((rc = ensure_workspace(e, F))) return rc;
-    for (int b0 = 0; b0 < B; b0 += F) {
+    if ((rc = lanes_fork(e))) return rc;
+    int k = 0;
+    for (int b0 = 0; b0 < B; b0 += F, k++) {
         const int f = std::min(F, B - b0);
-        if ((rc = run_pass(e, d_images + (size_t)b0 * frame_stride, step, frame_stride, f, d_kps + (size_t)b0 * cap,
-                           d_desc + (size_t)b0 * cap * 32, cap, d_counts + b0)))
+        if ((rc = run_pass(e, e->profiling ? 0 : k % e->nlanes, d_images + (size_t)b0 * frame_stride, step, frame_stride, f,
+                           d_kps + (size_t)b0 * cap, d_desc + (size_t)b0 * cap * 32, cap, d_counts + b0)))
             return rc;
         e->residentFirst = b0; e->residentCount = f;
     }
-    return VIORB_OK;
+    return lanes_join(e);
 }
 
 int viorb_extractor_check(viorb_extractor* e) {
     if (!e) return fail(VIORB_ERR_INVALID, "extractor is NULL");
     int rc;
     if ((rc = ctx_bind(e->ctx))) return rc;
-    if (!e->buf.status) { CU(cudaStreamSynchronize(e->ctx->stream)); return VIORB_OK; }
+    CU(cudaStreamSynchronize(e->ctx->stream));
     return check_status(e);
 }
 
@@ -578,7 +630,6 @@ static int extract_batch_once(viorb_extractor* e, const uint8_t* images, int B, 
         const int f = std::min(F, B - b0);
         if (k >= 2) {
             CU(cudaStreamWaitEvent(c->h2d, e->evDone[s], 0));    /* slot input free once its compute finished */
-            CU(cudaStreamWaitEvent(c->stream, e->evOut[s], 0));  /* slot outputs free once copied out */
         }
         if (step == (size_t)cols && frame_stride == inFrame) {       /* packed frames: one flat copy */
             CU(cudaMemcpyAsync(e->in[s].p, images + (size_t)b0 * frame_stride, (size_t)f * inFrame, cudaMemcpyHostToDevice, c->h2d));
@@ -591,9 +642,11 @@ static int extract_batch_once(viorb_extractor* e, const uint8_t* images, int B, 
                                      cols, rows, cudaMemcpyHostToDevice, c->h2d));
         }
         CU(cudaEventRecord(e->evIn[s], c->h2d));
-        CU(cudaStreamWaitEvent(c->stream, e->evIn[s], 0));
-        if ((rc = run_pass(e, e->in[s].p, cols, inFrame, f, e->okps[s].p, e->odesc[s].p, cap, e->ocnt[s].p))) return rc;
-        CU(cudaEventRecord(e->evDone[s], c->stream));
+        cudaStream_t ls = e->lanes[s].stream;
+        CU(cudaStreamWaitEvent(ls, e->evIn[s], 0));
+        if (k >= 2) CU(cudaStreamWaitEvent(ls, e->evOut[s], 0));     /* slot outputs free once copied out */
+        if ((rc = run_pass(e, s, e->in[s].p, cols, inFrame, f, e->okps[s].p, e->odesc[s].p, cap, e->ocnt[s].p))) return rc;
+        CU(cudaEventRecord(e->evDone[s], ls));
         CU(cudaStreamWaitEvent(c->d2h, e->evDone[s], 0));
         CU(cudaMemcpyAsync(kps + (size_t)b0 * cap, e->okps[s].p, (size_t)f * cap * sizeof(viorb_keypoint),
                            cudaMemcpyDeviceToHost, c->d2h));

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     const int ch = min(iniY + L.hCell + 6, maxBorderY) - iniY;
     const int ww = cwG - 6, wh = ch - 6;      /* detection window of the whole group */
     if (ww <= 0 || wh <= 0) return;
+    if (g.dbg & 16) return;
     const int tid = threadIdx.x, lane = tid & 31;
     const int NQ = (ww + 3) >> 2;            /* quads per window row */
     const int NW = NQ + 2;                   /* tile words per row: quads + one word each side */
@@ -268,11 +269,27 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
         const int gx0 = iniX + 3 - 4;                        /* level x of tile byte 0 (>= 15) */
         const int sh = gx0 & 3;
         const uint8_t* base = roi + (size_t)iniY * L.step + (gx0 - sh);   /* 4-byte aligned */
-        for (int i = tid; i < ch * NW; i += blockDim.x) {
-            const int y = i / NW, w = i - y * NW;
-            const unsigned* src = reinterpret_cast<const unsigned*>(base + (size_t)y * L.step) + w;
-            const unsigned lo = __ldg(src), hi = __ldg(src + 1);
-            tile[y * FAST_TW + w] = funnel_bytes(lo, hi, sh);
+        /* batches of 8 words per thread: all 16 loads of a batch are in flight before the first use */
+        const unsigned invNW = 0xffffffffu / (unsigned)NW + 1u;       /* i / NW == umulhi(i, invNW) for i < 2^16 */
+        const int total = ch * NW;
+        if (!(g.dbg & 8))
+        for (int i0 = tid; i0 < total; i0 += 8 * 128) {
+            unsigned lo[8], hi[8];
+            int dst[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int i = i0 + 128 * k;
+                const int y = (int)__umulhi((unsigned)i, invNW), w = i - y * NW;
+                dst[k] = i < total ? y * FAST_TW + w : -1;
+                if (i < total) {
+                    const unsigned* src = reinterpret_cast<const unsigned*>(base + (size_t)y * L.step) + w;
+                    lo[k] = __ldg(src);
+                    hi[k] = __ldg(src + 1);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (dst[k] >= 0) tile[dst[k]] = funnel_bytes(lo[k], hi[k], sh);
         }
         for (int i = tid; i < (wh + 2) * FAST_SCW; i += blockDim.x) sc[i] = 0;
         if (tid == 0) nwork = 0;
@@ -285,15 +302,29 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
      * ends, or darker than v - t on both ends.  Straight edges and flat areas fail this test. */
     const unsigned thP = (unsigned)g.minTh * 0x00010001u, nthP = __vneg2(thP);
     const int ntask = NQ * wh;
+    const unsigned invNQ = 0xffffffffu / (unsigned)NQ + 1u;          /* t / NQ == umulhi(t, invNQ) for t < 2^16 */
     for (int t0 = 0; t0 < ntask; t0 += blockDim.x) {
         const int t = t0 + tid;
         bool keep = false;
-        if (t < ntask) {
-            const int y = t / NQ, q = t - y * NQ;
+        if (g.dbg & 1) keep = (g.dbg & 4) && t < ntask;
+        else if (t < ntask) {
+            const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
             const unsigned* row = &tile[(y + 3) * FAST_TW + q];
+            const unsigned cw4 = row[1];
+            /* byte-domain pre-test on the four compass samples (k = 0, 4, 8, 12): every 9-arc contains one of
+             * them, so if |ring - centre| <= minTh at all four, for all four pixels, the quad is flat.
+             * flag byte bit 7 = (|d| > minTh); carries between bytes can only add false positives. */
+            {
+                const unsigned addc = (unsigned)(127 - g.minTh) * 0x01010101u;
+                const unsigned d0 = __vabsdiffu4(row[3 * FAST_TW + 1], cw4), d8 = __vabsdiffu4(row[-3 * FAST_TW + 1], cw4);
+                const unsigned d4 = __vabsdiffu4(funnel_bytes(row[1], row[2], 3), cw4);
+                const unsigned d12 = __vabsdiffu4(funnel_bytes(row[0], row[1], 1), cw4);
+                const unsigned f = (((d0 + addc) | d0) | ((d8 + addc) | d8) | ((d4 + addc) | d4) | ((d12 + addc) | d12)) & 0x80808080u;
+                if (f == 0) goto quad_done;
+            }
+            {
             unsigned rA[16], rB[16];
             fast_load_ring(row, rA, rB);
-            const unsigned cw4 = row[1];
             const unsigned nvA = __vneg2(__byte_perm(cw4, 0, 0x4240)), nvB = __vneg2(__byte_perm(cw4, 0, 0x4341));
             unsigned loA[8], hiA[8], loB[8], hiB[8];
 #pragma unroll
@@ -312,6 +343,8 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
             const unsigned up = __vmaxs2(__vadd2(brightA, nvA), __vadd2(brightB, nvB));   /* best opposite-pair excess */
             const unsigned dn = __vmins2(__vadd2(darkA, nvA), __vadd2(darkB, nvB));
             keep = !(__vmaxs2(up, thP) == thP && __vmins2(dn, nthP) == nthP);
+            }
+        quad_done:;
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         int basePos = 0;
@@ -323,10 +356,10 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
 
     /* phase 2 -- exact cornerScore on the surviving quads only, densely packed over the CTA */
     const unsigned negBias = __vneg2(thP);
-    const int nw = nwork;
+    const int nw = (g.dbg & 2) ? 0 : nwork;
     for (int i = tid; i < nw; i += blockDim.x) {
         const int t = work[i];
-        const int y = t / NQ, q = t - y * NQ;
+        const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
         const unsigned* row = &tile[(y + 3) * FAST_TW + q];
         unsigned rA[16], rB[16];
         fast_load_ring(row, rA, rB);
@@ -346,7 +379,7 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     const int iniShift = g.iniTh - g.minTh + 1;
     for (int i = tid; i < nw; i += blockDim.x) {
         const int t = work[i];
-        const int y = t / NQ, q = t - y * NQ;
+        const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
         const unsigned word = sc[(y + 1) * FAST_SCW + q + 1];
         unsigned bits = 0;
         if (word != 0) {
@@ -369,13 +402,17 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
         lmq[i] = (unsigned char)bits;
     }
     __syncthreads();
-    int* counter = candCount + frame * g.nlevels + l;
-    uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
+    /* emission: candidates are first appended to a CTA-local list (reusing the work array as 32-bit slots is
+     * not possible -- it is still read -- so they go to the dead tile), then one global atomic reserves the
+     * CTA's range of the (frame, level) pool and the list is copied out */
+    unsigned* local = tile;                          /* the tile is dead after phase 2 */
+    if (tid == 0) nwork = 0;                         /* reuse as the CTA-local candidate counter */
+    __syncthreads();
     for (int i = tid; i < nw; i += blockDim.x) {
         const unsigned bits4 = lmq[i];
         if (!bits4) continue;
         const int t = work[i];
-        const int y = t / NQ, q = t - y * NQ;
+        const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
         const unsigned word = sc[(y + 1) * FAST_SCW + q + 1];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -384,16 +421,22 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
             const int x = q * 4 + j;
             /* the cell is retried with minThFAST only if it found nothing at iniThFAST (:812) */
             if (sv < (cellIni[x / L.wCell] ? iniShift : 1)) continue;
-            const int pos = atomicAdd(counter, 1);
-            if (pos < L.candCap) {
-                /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
-                const uint32_t X = x + 3 + cj0 * L.wCell, Y = y + 3 + ci * L.hCell;
-                out[pos] = X | (Y << 12) | ((uint32_t)(sv + g.minTh - 1) << 24);
-            } else {
-                atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
-            }
+            /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
+            const uint32_t X = x + 3 + cj0 * L.wCell, Y = y + 3 + ci * L.hCell;
+            local[atomicAdd(&nwork, 1)] = X | (Y << 12) | ((uint32_t)(sv + g.minTh - 1) << 24);
         }
     }
+    __syncthreads();
+    const int nloc = nwork;
+    if (nloc == 0) return;
+    __shared__ int gbase;
+    if (tid == 0) gbase = atomicAdd(candCount + frame * g.nlevels + l, nloc);
+    __syncthreads();
+    uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
+    const int b0 = gbase;
+    if (b0 + nloc > L.candCap && tid == 0) atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
+    for (int i = tid; i < nloc; i += blockDim.x)
+        if (b0 + i < L.candCap) out[b0 + i] = local[i];
 }
 
 /* ------------------------------------------------------------------------------------------------

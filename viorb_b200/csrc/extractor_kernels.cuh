@@ -48,6 +48,7 @@ struct LevelGeom {
 struct FrameGeom {
     int nlevels, rows, cols;
     int iniTh, minTh;
+    int dbg;              /* VIORB_DEBUG experiment mask (0 in production) */
     int cellsPerFrame, candPerFrame, selPerFrame;
     unsigned long long pyrFrameBytes;
     LevelGeom lv[VIORB_MAX_LEVELS];
