@@ -39,7 +39,8 @@ def test_descriptor_distance(api, ctx, oracle):
     assert m.DescriptorDistance(a[3], b[77]) == np_hamming(a[3], b[77])
 
 
-@pytest.mark.parametrize("Q,M", [(1000, 50000), (1, 1), (5, 255), (129, 256), (300, 100001), (7, 0)])
+@pytest.mark.parametrize("Q,M", [(1000, 50000), (1, 1), (5, 255), (129, 256), (300, 100001), (7, 0), (1, 200003), (2, 70001),
+                                 (3, 65536), (4, 99999), (8, 123457), (9, 40000)])
 def test_top2_vs_oracle(api, ctx, oracle, Q, M):
     m = api.ORBmatcher(ctx=ctx)
     dmap = synth.descriptor_map(max(M, 1), seed=1234)[:M]
