@@ -176,7 +176,14 @@ int viorb_search_by_projection_local(viorb_frame_index* fi, int32_t* frame_mp_ob
  *          include/ORBmatcher.h:56, src/ORBmatcher.cc:1328-1471  (and, with mode 0 and th_high = ORBdist,
  *          the relocalisation overload :1473-1600 whose search loop is the same).
  * u, v, invz = projection of each last-frame map point into the current frame (:1359-1376);
- * mode 0: levels [o-1,o+1]; 1 (forward): >= o; 2 (backward): [0,o]   (:1385-1390).                */
+ * mode & 7 = level window: 0: [o-1,o+1]; 1 (forward): >= o; 2 (backward): [0,o] (:1385-1390); 3: [o-1,o].
+ * mode & 8 = no stereo (uRight) gate.  The same search loop serves the other two overloads:
+ *   SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist)        :1473-1600 (relocalisation):
+ *     mode 0|8, th_high = ORBdist, last_octave = PredictScale(dist3D), frame_mp_obs[k] = (mvpMapPoints[k] != NULL),
+ *     nobs = 1 for every point (any assigned keypoint is skipped, :1541-1542);
+ *   SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th)             :290-403 (loop closing):
+ *     mode 3|8, th_high = TH_LOW, no orientation check, the frame index built from the KeyFrame's keypoints,
+ *     frame_mp_obs[k] = (vpMatched[k] != NULL), nobs = 1.                                             */
 int viorb_search_by_projection_frame(viorb_frame_index* fi, int32_t* frame_mp_obs,
                                      const float* u, const float* v, const float* invz,
                                      const int32_t* last_octave, const float* last_angle,

@@ -387,8 +387,13 @@ extern "C" int orc_search_by_projection_frame(const orc_grid* grid, const orc_ke
         int nLastOctave = last_octave[i];
         float radius = th * mvScaleFactors[nLastOctave];
         std::vector<size_t> vIndices2;
-        if (mode == 1) vIndices2 = features_in_area(grid, u, v, radius, nLastOctave, -1);
-        else if (mode == 2) vIndices2 = features_in_area(grid, u, v, radius, 0, nLastOctave);
+        /* mode & 7: level window of the overload (:1385-1390; 3 = the Sim3 overload's [l-1, l], :375-379, applied
+         * there as a filter after KeyFrame::GetFeaturesInArea, which enumerates in the same order);
+         * mode & 8: no stereo gate (the KeyFrame overloads :290-403 and :1473-1600 have none) */
+        const int lm = mode & 7;
+        if (lm == 1) vIndices2 = features_in_area(grid, u, v, radius, nLastOctave, -1);
+        else if (lm == 2) vIndices2 = features_in_area(grid, u, v, radius, 0, nLastOctave);
+        else if (lm == 3) vIndices2 = features_in_area(grid, u, v, radius, nLastOctave - 1, nLastOctave);
         else vIndices2 = features_in_area(grid, u, v, radius, nLastOctave - 1, nLastOctave + 1);
         if (vIndices2.empty()) continue;
         const uint8_t* dMP = mpdesc + (size_t)i * 32;
@@ -396,7 +401,7 @@ extern "C" int orc_search_by_projection_frame(const orc_grid* grid, const orc_ke
         for (size_t k = 0; k < vIndices2.size(); k++) {
             const size_t i2 = vIndices2[k];
             if (frame_mp_obs[i2] > 0) continue;
-            if (mvuRight[i2] > 0) {
+            if (!(mode & 8) && mvuRight[i2] > 0) {
                 const float ur = u - mbf * invzc;
                 const float er = std::fabs(ur - mvuRight[i2]);
                 if (er > radius) continue;

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <set>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -168,6 +169,70 @@ int main() {
         bool same = n == nref;
         for (int k = 0; k < F.N; k++) same = same && (F.mvpMapPoints[k] == (match[k] >= 0 ? mps[match[k]] : nullptr));
         CHECK(nref > 100 && same, "SearchByProjection(Frame, MapPoints) differs from the oracle");
+        orc_grid_destroy(grid);
+    }
+
+    /* ---- SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, ORBdist)  (relocalisation overload) ---- */
+    {
+        const int NQ = 400;
+        KeyFrame kf;
+        kf.N = NQ;
+        kf.mvKeysUn.resize(NQ);
+        kf.mapPoints.assign(NQ, nullptr);
+        std::vector<MapPoint> store(NQ);
+        F.mTcw = cv::Mat::zeros(4, 4, CV_32F);
+        for (int i = 0; i < 4; i++) F.mTcw.at<float>(i, i) = 1;
+        F.mvpMapPoints.assign(F.N, nullptr);
+        MapPoint taken;
+        for (int k = 0; k < F.N; k += 9) F.mvpMapPoints[k] = &taken;           /* already assigned keypoints are skipped */
+        std::vector<float> u(NQ), v(NQ), invz(NQ), ang(NQ);
+        std::vector<int32_t> lvl(NQ), nobs(NQ, 1), obs(F.N), match(F.N, -1);
+        std::vector<uint8_t> valid(NQ, 0), desc((size_t)NQ * 32);
+        std::set<MapPoint*> found;
+        for (int i = 0; i < NQ; i++) {
+            const int k = (i < 40) ? (int)(rnd() % 20) : (int)(rnd() % F.N);
+            MapPoint& p = store[i];
+            const float z = 4.0f + 4.0f * rndf();
+            p.worldPos = cv::Mat(3, 1, CV_32F);
+            p.worldPos.at<float>(0) = (kL[k].pt.x + (rndf() - 0.5f) * 6 - F.cx) / F.fx * z;
+            p.worldPos.at<float>(1) = (kL[k].pt.y + (rndf() - 0.5f) * 6 - F.cy) / F.fy * z;
+            p.worldPos.at<float>(2) = z;
+            const float X = p.worldPos.at<float>(0), Y = p.worldPos.at<float>(1), Z = p.worldPos.at<float>(2);
+            const float d3 = (float)std::sqrt((double)X * X + (double)Y * Y + (double)Z * Z);
+            p.mfMaxDistance = d3 * std::pow(1.2f, (float)kL[k].octave) * 0.99f;
+            p.mfMinDistance = 0.01f;
+            p.descriptor = dL.row(k).clone();
+            for (int b = 0; b < (int)(rnd() % 30); b++) p.descriptor.data[rnd() % 32] ^= (uint8_t)(1u << (rnd() % 8));
+            p.bad = (rnd() % 17) == 0;
+            kf.mapPoints[i] = (rnd() % 11) == 0 ? nullptr : &p;
+            if ((rnd() % 13) == 0) found.insert(&p);
+            kf.mvKeysUn[i].angle = kL[k].angle + ((rnd() % 5) == 0 ? 120.f : 2.f * rndf());
+            /* the marshalling the shim performs, restated for the oracle */
+            MapPoint* q = kf.mapPoints[i];
+            if (!q || q->isBad() || found.count(q)) continue;
+            const float invzc = 1.0 / Z;
+            const float uu = F.fx * X * invzc + F.cx, vv = F.fy * Y * invzc + F.cy;
+            if (uu < F.mnMinX || uu > F.mnMaxX || vv < F.mnMinY || vv > F.mnMaxY) continue;
+            if (d3 < q->GetMinDistanceInvariance() || d3 > q->GetMaxDistanceInvariance()) continue;
+            u[i] = uu; v[i] = vv; invz[i] = invzc; lvl[i] = q->PredictScale(d3, &F); ang[i] = kf.mvKeysUn[i].angle;
+            memcpy(&desc[(size_t)i * 32], q->descriptor.data, 32);
+            valid[i] = 1;
+        }
+        for (int k = 0; k < F.N; k++) obs[k] = F.mvpMapPoints[k] ? 1 : 0;
+        std::vector<float> noRight(F.N, -1.0f), sc = exL.GetScaleFactors();
+        F.mvuRight = noRight;
+        ORBmatcher matcher(0.75f, true);
+        const int n = matcher.SearchByProjection(F, &kf, found, 10.0f, 100);
+        orc_grid* grid = orc_grid_create(oL.k.data(), F.N, 0, (float)W, 0, (float)H);
+        const int nref = orc_search_by_projection_frame(grid, oL.k.data(), oL.d.data(), noRight.data(), obs.data(), F.N, sc.data(),
+                                                        u.data(), v.data(), invz.data(), lvl.data(), ang.data(), valid.data(),
+                                                        nobs.data(), desc.data(), NQ, 10.0f, F.mbf, 0 | 8, 1, 100, match.data());
+        bool same = n == nref;
+        for (int k = 0; k < F.N; k++) {
+            MapPoint* want = match[k] >= 0 ? kf.mapPoints[match[k]] : ((k % 9) == 0 && obs[k] ? &taken : nullptr);
+            same = same && F.mvpMapPoints[k] == want;
+        }
+        CHECK(nref > 80 && same, "SearchByProjection(Frame, KeyFrame, ...) differs from the oracle");
         orc_grid_destroy(grid);
     }
 

@@ -111,7 +111,8 @@ def test_search_by_projection_local(api, ctx, oracle, stereo, frame, th, nnratio
 
 
 @pytest.mark.parametrize("mode,th,check_ori,th_high", [(0, 15.0, True, 100), (1, 7.0, True, 100), (2, 7.0, False, 100),
-                                                       (0, 10.0, True, 64)])
+                                                       (0, 10.0, True, 64), (0 | 8, 10.0, True, 64), (0 | 8, 3.0, True, 100),
+                                                       (3 | 8, 10.0, False, 50)])
 def test_search_by_projection_frame(api, ctx, oracle, stereo, frame, mode, th, check_ori, th_high):
     s, sc = stereo, frame["sc"]
     g = oracle.Grid(s["kl"], *frame["bounds"])
@@ -124,6 +125,26 @@ def test_search_by_projection_frame(api, ctx, oracle, stereo, frame, mode, th, c
                                               th, S.KITTI_BF, mode, th_high)
     assert n_ref > 30
     assert n == n_ref and (match == m_ref).all() and (obs == obs_ref).all()
+
+
+@pytest.mark.parametrize("mode,th,check_ori,th_high", [(0 | 8, 10.0, True, 100), (3 | 8, 10.0, False, 50)])
+def test_search_by_projection_keyframe_overloads(api, ctx, oracle, stereo, frame, mode, th, check_ori, th_high):
+    """relocalisation (ORBmatcher.cc:1473-1600) and Sim3 (:290-403) overloads: any assigned keypoint blocks,
+    every match blocks later map points (nobs = 1), no stereo gate"""
+    s, sc = stereo, frame["sc"]
+    g = oracle.Grid(s["kl"], *frame["bounds"])
+    obs0 = (sc["obs0"] > 0).astype(np.int32)
+    nobs = np.ones(len(sc["valid"]), np.int32)
+    n_ref, m_ref, obs_ref = oracle.search_by_projection_frame(
+        g, s["dl"], sc["u_right"], obs0, frame["sf"], sc["proj_x"], sc["proj_y"], sc["invz"], sc["pred_level"],
+        sc["last_angle"], sc["valid"], nobs, sc["mp_desc"], th, S.KITTI_BF, mode, check_ori, th_high)
+    m = api.ORBmatcher(0.75, check_ori, ctx=ctx)
+    n, match, obs = m.SearchByProjectionFrame(frame["fi"], obs0, sc["proj_x"], sc["proj_y"], sc["invz"], sc["pred_level"],
+                                              sc["last_angle"], sc["valid"], nobs, sc["mp_desc"], th, S.KITTI_BF, mode, th_high)
+    assert n_ref > 30
+    assert n == n_ref and (match == m_ref).all() and (obs == obs_ref).all()
+    # every keypoint is claimed at most once and previously assigned keypoints are never taken
+    assert (match[obs0 > 0] == -1).all()
 
 
 def test_search_sequential_dependence(api, ctx, oracle, stereo, frame):

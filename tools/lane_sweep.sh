@@ -1,0 +1,9 @@
+#!/bin/bash
+for l in 1 2 3 4; do for c in 64 128; do
+  VIORB_LANES=$l python bench.py --steps 3 --warmup 3 --no-matcher --no-cpu --chunk $c 2>/dev/null > /tmp/lane.json
+  python - "$l" "$c" <<'PY'
+import sys, json
+d = json.load(open('/tmp/lane.json'))
+print("lanes", sys.argv[1], "chunk", sys.argv[2], round(d["value"]), "e2e", round(d["e2e"]["value"]))
+PY
+done; done

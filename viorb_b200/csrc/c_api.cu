@@ -100,7 +100,7 @@ struct viorb_extractor {
         DevBuf<uint32_t> cand, sel;
         DevBuf<int> counters;      /* candCount | selCount | status */
         DevBuf<uint16_t> nodeOf;
-    } lanes[2];
+    } lanes[4];
     int nlanes = 2;
     cudaEvent_t evFork = nullptr;
     ExtractBuffers buf = {};       /* buffers of the most recent pass (resident pyramids, debug views) */
@@ -237,7 +237,9 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
             if (VIORB_FAST_BORDER + i * L.hCell >= maxBorderY - 3) continue;
             int nvalid = 0;
             while (nvalid < L.nCols && VIORB_FAST_BORDER + nvalid * L.wCell < maxBorderX - 6) nvalid++;
-            const int G = L.wCell <= 45 ? VIORB_FAST_GROUP : 1;
+            /* cells per CTA: as many as fit the kernel's tile (45 quads wide) and work lists (2048 quads) */
+            int G = VIORB_FAST_GROUP;
+            while (G > 1 && (G * L.wCell > 180 || ((G * L.wCell + 3) / 4) * std::min(L.hCell, 59) > 2048)) G--;
             for (int j = 0; j < nvalid; j += G) groups.push_back(make_int4(l, i, j, std::min(G, nvalid - j)));
         }
     }
@@ -258,7 +260,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     cudaError_t ce = (cudaError_t)viorb_octree_prepare(nodeCap);
     if (ce != cudaSuccess) return fail(VIORB_ERR_CUDA, "octree kernel attribute: %s", cudaGetErrorString(ce));
     e->rows = rows; e->cols = cols;
-    for (int i = 0; i < 2; i++) e->lanes[i].allocFrames = 0;
+    for (int i = 0; i < 4; i++) e->lanes[i].allocFrames = 0;
     return VIORB_OK;
 }
 
@@ -450,9 +452,12 @@ int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, in
     build_tables(e);
     if (ctx_bind(ctx)) { delete e; return VIORB_ERR_CUDA; }
     cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
-    for (int i = 0; i < 2; i++) {
+    if (getenv("VIORB_LANES")) e->nlanes = std::min(4, std::max(1, atoi(getenv("VIORB_LANES"))));
+    for (int i = 0; i < 4; i++) {
         cudaStreamCreateWithFlags(&e->lanes[i].stream, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&e->lanes[i].evDone, cudaEventDisableTiming);
+    }
+    for (int i = 0; i < 2; i++) {
         cudaEventCreateWithFlags(&e->evIn[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->evDone[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->evOut[i], cudaEventDisableTiming);
@@ -468,7 +473,7 @@ int viorb_extractor_destroy(viorb_extractor* e) {
     cudaStreamSynchronize(e->ctx->h2d);
     cudaStreamSynchronize(e->ctx->d2h);
     e->tabU16.release(); e->tabI16.release(); e->groups.release();
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 4; i++) {
         viorb_extractor::Lane& ln = e->lanes[i];
         if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
         if (ln.evDone) cudaEventDestroy(ln.evDone);

@@ -256,7 +256,7 @@ int viorb_search_by_projection_frame(viorb_frame_index* fi, int32_t* frame_mp_ob
                                      const float* invz, const int32_t* last_octave, const float* last_angle,
                                      const uint8_t* valid, const int32_t* nobs, const uint8_t* mp_desc, int nlast, float th,
                                      float mbf, int mode, int check_orientation, int th_high, int32_t* match, int* nmatches) {
-    if (!fi || !frame_mp_obs || !match || !nmatches || nlast < 0 || mode < 0 || mode > 2 ||
+    if (!fi || !frame_mp_obs || !match || !nmatches || nlast < 0 || mode < 0 || (mode & 7) > 3 || mode > 15 ||
         (nlast > 0 && (!u || !v || !invz || !last_octave || !last_angle || !valid || !nobs || !mp_desc)))
         return viorb_fail(VIORB_ERR_INVALID, "bad argument");
     viorb_ctx* c = fi->ctx;

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
 #define FAST_MAXQ 45            /* quads per window row: 4 cells x wCell (<= 45 when nCols >= 2; one cell of <= 59 otherwise) */
 #define FAST_TW 49              /* tile row stride in words (odd): 1 lead word + 45 quads + 1 tail word, padded */
 #define FAST_SCW 49             /* score row stride in words (odd): 1 zero word + 45 quads + 1 zero word, padded */
-#define FAST_MAXWORK (FAST_MAXQ * 60)
+#define FAST_MAXWORK 2048        /* quads per CTA: the host sizes the cell groups so that NQ * wh <= 2048 */
 
 __device__ __forceinline__ unsigned funnel_bytes(unsigned lo, unsigned hi, int sh) {
     /* bytes sh..sh+3 of the 8-byte little-endian sequence lo|hi (sh in 0..3) */
@@ -240,9 +240,10 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
                                                          int* __restrict__ status) {
     __shared__ unsigned tile[FAST_ROWS * FAST_TW];
     __shared__ unsigned sc[(FAST_ROWS - 4) * FAST_SCW];
+    __shared__ unsigned short work0[FAST_MAXWORK];    /* quads that are not flat (compass pre-test) */
     __shared__ unsigned short work[FAST_MAXWORK];     /* quads that survive the high-speed test */
     __shared__ unsigned char lmq[FAST_MAXWORK];       /* local-maximum bits of the surviving quads */
-    __shared__ int nwork;
+    __shared__ int nwork, nwork0;
     __shared__ int cellIni[FAST_GROUP];               /* per cell: does it hold a corner at iniThFAST? */
     const int frame = blockIdx.y;
     /* a CTA owns up to FAST_GROUP horizontally adjacent cells of one cell row: {level, cell row, first cell, n} */
@@ -292,37 +293,55 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
                 if (dst[k] >= 0) tile[dst[k]] = funnel_bytes(lo[k], hi[k], sh);
         }
         for (int i = tid; i < (wh + 2) * FAST_SCW; i += blockDim.x) sc[i] = 0;
-        if (tid == 0) nwork = 0;
+        if (tid == 0) { nwork = 0; nwork0 = 0; }
         if (tid < FAST_GROUP) cellIni[tid] = 0;
     }
     __syncthreads();
 
-    /* phase 1 -- high-speed test on every quad.  A 9-arc of the 16-ring always contains a pair of opposite
-     * samples (k, k+8), so a corner at threshold t needs an opposite pair that is brighter than v + t on both
-     * ends, or darker than v - t on both ends.  Straight edges and flat areas fail this test. */
-    const unsigned thP = (unsigned)g.minTh * 0x00010001u, nthP = __vneg2(thP);
+    /* phase 0 -- byte-domain pre-test on the four compass samples (k = 0, 4, 8, 12) of every quad: each 9-arc
+     * contains one of them, so if |ring - centre| <= minTh at all four, for all four pixels, the quad is flat.
+     * flag byte bit 7 = (|d| > minTh); carries between bytes can only add false positives.  Non-flat quads are
+     * compacted so the later phases run on dense warps. */
     const int ntask = NQ * wh;
     const unsigned invNQ = 0xffffffffu / (unsigned)NQ + 1u;          /* t / NQ == umulhi(t, invNQ) for t < 2^16 */
-    for (int t0 = 0; t0 < ntask; t0 += blockDim.x) {
-        const int t = t0 + tid;
-        bool keep = false;
-        if (g.dbg & 1) keep = (g.dbg & 4) && t < ntask;
-        else if (t < ntask) {
-            const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
-            const unsigned* row = &tile[(y + 3) * FAST_TW + q];
-            const unsigned cw4 = row[1];
-            /* byte-domain pre-test on the four compass samples (k = 0, 4, 8, 12): every 9-arc contains one of
-             * them, so if |ring - centre| <= minTh at all four, for all four pixels, the quad is flat.
-             * flag byte bit 7 = (|d| > minTh); carries between bytes can only add false positives. */
-            {
-                const unsigned addc = (unsigned)(127 - g.minTh) * 0x01010101u;
+    {
+        const unsigned addc = (unsigned)(127 - g.minTh) * 0x01010101u;
+        for (int t0 = 0; t0 < ntask; t0 += blockDim.x) {
+            const int t = t0 + tid;
+            bool keep = false;
+            if (t < ntask) {
+                const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
+                const unsigned* row = &tile[(y + 3) * FAST_TW + q];
+                const unsigned cw4 = row[1];
                 const unsigned d0 = __vabsdiffu4(row[3 * FAST_TW + 1], cw4), d8 = __vabsdiffu4(row[-3 * FAST_TW + 1], cw4);
                 const unsigned d4 = __vabsdiffu4(funnel_bytes(row[1], row[2], 3), cw4);
                 const unsigned d12 = __vabsdiffu4(funnel_bytes(row[0], row[1], 1), cw4);
-                const unsigned f = (((d0 + addc) | d0) | ((d8 + addc) | d8) | ((d4 + addc) | d4) | ((d12 + addc) | d12)) & 0x80808080u;
-                if (f == 0) goto quad_done;
+                keep = ((((d0 + addc) | d0) | ((d8 + addc) | d8) | ((d4 + addc) | d4) | ((d12 + addc) | d12)) & 0x80808080u) != 0;
+                if (g.dbg & 1) keep = (g.dbg & 4) != 0;
             }
-            {
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            int basePos = 0;
+            if (lane == 0 && m) basePos = atomicAdd(&nwork0, __popc(m));
+            basePos = __shfl_sync(0xffffffffu, basePos, 0);
+            if (keep) work0[basePos + __popc(m & ((1u << lane) - 1))] = (unsigned short)t;
+        }
+    }
+    __syncthreads();
+
+    /* phase 1 -- high-speed test on the non-flat quads.  A 9-arc of the 16-ring always contains a pair of opposite
+     * samples (k, k+8), so a corner at threshold t needs an opposite pair that is brighter than v + t on both
+     * ends, or darker than v - t on both ends.  Straight edges fail this test. */
+    const unsigned thP = (unsigned)g.minTh * 0x00010001u, nthP = __vneg2(thP);
+    const int n0 = nwork0;
+    for (int i0 = 0; i0 < n0; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        bool keep = false;
+        int t = 0;
+        if (i < n0) {
+            t = work0[i];
+            const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
+            const unsigned* row = &tile[(y + 3) * FAST_TW + q];
+            const unsigned cw4 = row[1];
             unsigned rA[16], rB[16];
             fast_load_ring(row, rA, rB);
             const unsigned nvA = __vneg2(__byte_perm(cw4, 0, 0x4240)), nvB = __vneg2(__byte_perm(cw4, 0, 0x4341));
@@ -343,8 +362,6 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
             const unsigned up = __vmaxs2(__vadd2(brightA, nvA), __vadd2(brightB, nvB));   /* best opposite-pair excess */
             const unsigned dn = __vmins2(__vadd2(darkA, nvA), __vadd2(darkB, nvB));
             keep = !(__vmaxs2(up, thP) == thP && __vmins2(dn, nthP) == nthP);
-            }
-        quad_done:;
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         int basePos = 0;
@@ -388,7 +405,7 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
                 const int sv = (word >> (8 * j)) & 0xff;
                 if (sv == 0) continue;
                 const int x = q * 4 + j;
-                const int cg = x / L.wCell, xin = x - cg * L.wCell;
+                const int cg = (x >= L.wCell) + (x >= 2 * L.wCell) + (x >= 3 * L.wCell), xin = x - cg * L.wCell;
                 const uint8_t* p = scb + ((y + 1) * FAST_SCW + q + 1) * 4 + j;
                 bool lm = sv > p[-FAST_SCW * 4] && sv > p[FAST_SCW * 4];
                 if (xin > 0) lm = lm && sv > p[-1] && sv > p[-FAST_SCW * 4 - 1] && sv > p[FAST_SCW * 4 - 1];
@@ -420,7 +437,7 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
             const int sv = (word >> (8 * j)) & 0xff;
             const int x = q * 4 + j;
             /* the cell is retried with minThFAST only if it found nothing at iniThFAST (:812) */
-            if (sv < (cellIni[x / L.wCell] ? iniShift : 1)) continue;
+            if (sv < (cellIni[(x >= L.wCell) + (x >= 2 * L.wCell) + (x >= 3 * L.wCell)] ? iniShift : 1)) continue;
             /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
             const uint32_t X = x + 3 + cj0 * L.wCell, Y = y + 3 + ci * L.hCell;
             local[atomicAdd(&nwork, 1)] = X | (Y << 12) | ((uint32_t)(sv + g.minTh - 1) << 24);
@@ -906,18 +923,22 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
         const int gx0 = kx - PR;
         const int sh = gx0 & 3;
         const int w = lane & 15, rsub = lane >> 4;
-        const uint8_t* base = roi + (ptrdiff_t)(ky - PR + rsub) * L.step + (gx0 - sh) + 4 * w;    /* 4-byte aligned */
+        /* word pointer of (row rsub, word w); rows advance by two per step (64-bit add only) */
+        const unsigned* p = reinterpret_cast<const unsigned*>(roi + (ptrdiff_t)(ky - PR + rsub) * L.step + (gx0 - sh)) + w;
+        const ptrdiff_t twoRows = (ptrdiff_t)(L.step >> 1);           /* 2 * step bytes in words */
+        const bool okW = w < 13;
         unsigned g[22];
 #pragma unroll
         for (int k = 0; k < 22; k++) {
-            const int r = 2 * k + rsub;
-            g[k] = (w < 13 && r < PROWS) ? __ldg(reinterpret_cast<const unsigned*>(base + (ptrdiff_t)(2 * k) * L.step)) : 0u;
+            const bool ok = okW && (k < 21 || rsub == 0);               /* row 2k + rsub < 43 */
+            g[k] = ok ? __ldg(p) : 0u;
+            p += twoRows;
         }
+        unsigned* dst = P + rsub * PWORDS + w;
 #pragma unroll
         for (int k = 0; k < 22; k++) {
-            const int r = 2 * k + rsub;
             const unsigned hi = __shfl_down_sync(0xffffffffu, g[k], 1);
-            if (w < 12 && r < PROWS) P[r * PWORDS + w] = funnel_bytes(g[k], hi, sh);
+            if (w < 12 && (k < 21 || rsub == 0)) dst[k * 2 * PWORDS] = funnel_bytes(g[k], hi, sh);
         }
     }
     /* this lane's 8 binary tests (16 sampling points, 32 floats) */

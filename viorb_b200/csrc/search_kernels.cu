@@ -434,16 +434,19 @@ __global__ void __launch_bounds__(1024) search_frame_kernel(FrameIndexDev fi, Fr
                 const int oct = a.lastOctave[i];
                 const float radius = __fmul_rn(a.th, fi.scale[oct]);
                 int minL, maxL;
-                if (a.mode == 1) { minL = oct; maxL = -1; }                 /* forward  :1385-1386 */
-                else if (a.mode == 2) { minL = 0; maxL = oct; }             /* backward :1387-1388 */
+                const int lm = a.mode & 7;
+                if (lm == 1) { minL = oct; maxL = -1; }                     /* forward  :1385-1386 */
+                else if (lm == 2) { minL = 0; maxL = oct; }                 /* backward :1387-1388 */
+                else if (lm == 3) { minL = oct - 1; maxL = oct; }           /* Sim3 overload :375-379 */
                 else { minL = oct - 1; maxL = oct + 1; }
+                const bool stereoGate = !(a.mode & 8);                      /* the KeyFrame overloads have no uRight gate */
                 const float ur = __fsub_rn(u, __fmul_rn(a.mbf, a.invz[i]));
                 const uint8_t* dMP = a.mpDesc + (size_t)i * 32;
                 unsigned long long k1 = ~0ull;
                 for_features_in_area(fi, u, v, radius, minL, maxL, lane, [&](int pos, int idx, int) {
                     if (obs[idx] > 0 || minClaim[idx] < i) return;
                     const float uR = fi.uRight[idx];
-                    if (uR > 0) {
+                    if (stereoGate && uR > 0) {
                         const float er = fabsf(__fsub_rn(ur, uR));
                         if (er > radius) return;
                     }

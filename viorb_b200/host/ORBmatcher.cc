@@ -1,6 +1,8 @@
 /* ORBmatcher.cc -- see ORBmatcher.h.  Host-side marshalling only; every distance is computed on the GPU. */
 #include "ORBmatcher.h"
 
+#include <algorithm>
+#include <cmath>
 #include <stdexcept>
 #include <string>
 
@@ -146,6 +148,111 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
             /* unreachable: only this call can clear an entry, and cleared entries never held observations */
         }
     }
+    return n;
+}
+
+
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th,
+                                   const int ORBdist) {
+    /* projection and scale prediction on the host (reference :1477-1530), the search on the GPU */
+    const cv::Mat& Tcw = CurrentFrame.mTcw;
+    float Rcw[9], tcw[3], Ow[3];
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) Rcw[3 * r + c] = Tcw.at<float>(r, c);
+        tcw[r] = Tcw.at<float>(r, 3);
+    }
+    for (int r = 0; r < 3; r++) Ow[r] = -(Rcw[r] * tcw[0] + Rcw[3 + r] * tcw[1] + Rcw[6 + r] * tcw[2]);
+    const std::vector<MapPoint*> vpMPs = pKF->GetMapPointMatches();
+    const int nq = (int)vpMPs.size();
+    std::vector<float> u(nq), v(nq), invz(nq), ang(nq);
+    std::vector<int32_t> lvl(nq), nobs(nq, 1), obs(CurrentFrame.N), match(CurrentFrame.N, -1);
+    std::vector<uint8_t> valid(nq, 0), desc((size_t)std::max(nq, 1) * 32);
+    for (int i = 0; i < nq; i++) {
+        MapPoint* pMP = vpMPs[i];
+        if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+        const float X = x3Dw.at<float>(0), Y = x3Dw.at<float>(1), Z = x3Dw.at<float>(2);
+        const float xc = Rcw[0] * X + Rcw[1] * Y + Rcw[2] * Z + tcw[0];
+        const float yc = Rcw[3] * X + Rcw[4] * Y + Rcw[5] * Z + tcw[1];
+        const float zc = Rcw[6] * X + Rcw[7] * Y + Rcw[8] * Z + tcw[2];
+        const float invzc = 1.0 / zc;
+        const float uu = CurrentFrame.fx * xc * invzc + CurrentFrame.cx, vv = CurrentFrame.fy * yc * invzc + CurrentFrame.cy;
+        if (uu < CurrentFrame.mnMinX || uu > CurrentFrame.mnMaxX) continue;
+        if (vv < CurrentFrame.mnMinY || vv > CurrentFrame.mnMaxY) continue;
+        const float px = X - Ow[0], py = Y - Ow[1], pz = Z - Ow[2];
+        const float dist3D = (float)std::sqrt((double)px * px + (double)py * py + (double)pz * pz);     /* cv::norm */
+        if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+        u[i] = uu; v[i] = vv; invz[i] = invzc;
+        lvl[i] = pMP->PredictScale(dist3D, &CurrentFrame);
+        ang[i] = pKF->mvKeysUn[i].angle;
+        memcpy(&desc[(size_t)i * 32], pMP->GetDescriptor().ptr<uint8_t>(), 32);
+        valid[i] = 1;
+    }
+    for (int k = 0; k < CurrentFrame.N; k++) obs[k] = CurrentFrame.mvpMapPoints[k] ? 1 : 0;             /* :1541-1542 */
+    FrameIndexGuard g;
+    make_index(CurrentFrame, g);
+    int n = 0;
+    check(viorb_search_by_projection_frame(g.fi, obs.data(), u.data(), v.data(), invz.data(), lvl.data(), ang.data(),
+                                           valid.data(), nobs.data(), desc.data(), nq, th, CurrentFrame.mbf, 0 | 8,
+                                           mbCheckOrientation, ORBdist, match.data(), &n),
+          "viorb_search_by_projection_frame");
+    for (int k = 0; k < CurrentFrame.N; k++)
+        if (match[k] >= 0) CurrentFrame.mvpMapPoints[k] = vpMPs[match[k]];
+    return n;
+}
+
+int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints,
+                                   std::vector<MapPoint*>& vpMatched, int th) {
+    /* Sim3 decomposition, projection and gates on the host (reference :292-366), the search on the GPU */
+    float sR[9], Rcw[9], tcw[3], Ow[3];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) sR[3 * r + c] = Scw.at<float>(r, c);
+    const float scw = (float)std::sqrt((double)sR[0] * sR[0] + (double)sR[1] * sR[1] + (double)sR[2] * sR[2]);
+    for (int i = 0; i < 9; i++) Rcw[i] = sR[i] / scw;
+    for (int r = 0; r < 3; r++) tcw[r] = Scw.at<float>(r, 3) / scw;
+    for (int r = 0; r < 3; r++) Ow[r] = -(Rcw[r] * tcw[0] + Rcw[3 + r] * tcw[1] + Rcw[6 + r] * tcw[2]);
+    std::set<MapPoint*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPoint*>(nullptr));
+    const int nq = (int)vpPoints.size();
+    std::vector<float> u(nq), v(nq), invz(nq, 0.f), ang(nq, 0.f);
+    std::vector<int32_t> lvl(nq), nobs(nq, 1), obs(pKF->N), match(pKF->N, -1);
+    std::vector<uint8_t> valid(nq, 0), desc((size_t)std::max(nq, 1) * 32);
+    for (int i = 0; i < nq; i++) {
+        MapPoint* pMP = vpPoints[i];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+        const cv::Mat p3Dw = pMP->GetWorldPos();
+        const float X = p3Dw.at<float>(0), Y = p3Dw.at<float>(1), Z = p3Dw.at<float>(2);
+        const float xc = Rcw[0] * X + Rcw[1] * Y + Rcw[2] * Z + tcw[0];
+        const float yc = Rcw[3] * X + Rcw[4] * Y + Rcw[5] * Z + tcw[1];
+        const float zc = Rcw[6] * X + Rcw[7] * Y + Rcw[8] * Z + tcw[2];
+        if (zc < 0.0) continue;
+        const float iz = 1 / zc;
+        const float uu = pKF->fx * (xc * iz) + pKF->cx, vv = pKF->fy * (yc * iz) + pKF->cy;
+        if (!pKF->IsInImage(uu, vv)) continue;
+        const float px = X - Ow[0], py = Y - Ow[1], pz = Z - Ow[2];
+        const float dist = (float)std::sqrt((double)px * px + (double)py * py + (double)pz * pz);
+        if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) continue;
+        const cv::Mat Pn = pMP->GetNormal();
+        if (px * Pn.at<float>(0) + py * Pn.at<float>(1) + pz * Pn.at<float>(2) < 0.5 * dist) continue;   /* < 60 deg */
+        u[i] = uu; v[i] = vv;
+        lvl[i] = pMP->PredictScale(dist, pKF);
+        memcpy(&desc[(size_t)i * 32], pMP->GetDescriptor().ptr<uint8_t>(), 32);
+        valid[i] = 1;
+    }
+    for (int k = 0; k < pKF->N; k++) obs[k] = vpMatched[k] ? 1 : 0;                                      /* :372-373 */
+    const std::vector<uint8_t> kdesc = pack_descriptors(pKF->mDescriptors, pKF->N);
+    FrameIndexGuard g;
+    check(viorb_frame_index_create(thread_ctx(), reinterpret_cast<const viorb_keypoint*>(pKF->mvKeysUn.data()), kdesc.data(),
+                                   nullptr, pKF->N, pKF->mnMinX, pKF->mnMaxX, pKF->mnMinY, pKF->mnMaxY,
+                                   pKF->mvScaleFactors.data(), (int)pKF->mvScaleFactors.size(), &g.fi),
+          "viorb_frame_index_create");
+    int n = 0;
+    check(viorb_search_by_projection_frame(g.fi, obs.data(), u.data(), v.data(), invz.data(), lvl.data(), ang.data(),
+                                           valid.data(), nobs.data(), desc.data(), nq, (float)th, 0.f, 3 | 8, 0, TH_LOW,
+                                           match.data(), &n),
+          "viorb_search_by_projection_frame");
+    for (int k = 0; k < pKF->N; k++)
+        if (match[k] >= 0) vpMatched[k] = vpPoints[match[k]];                                            /* :396 */
     return n;
 }
 

@@ -1,15 +1,15 @@
 /*
  * ORBmatcher.h -- drop-in for ORB_SLAM2::ORBmatcher (reference include/ORBmatcher.h:37-102) for the searches
- * on the hot path: DescriptorDistance, SearchByProjection (local map and frame-to-frame) and
- * SearchForTriangulation.  Each call marshals the fields the reference reads into flat arrays and runs the
+ * on the hot path: DescriptorDistance, the four SearchByProjection overloads and SearchForTriangulation.  Each call marshals the fields the reference reads into flat arrays and runs the
  * whole search as CUDA kernels behind include/viorb_gpu.h; results (matches, counts, tie-breaks, the
  * "already matched" dependence) are identical to the reference's sequential loops.
- * The remaining searches of the reference class (SearchByBoW x2, SearchForInitialization, SearchBySim3, Fuse x2,
- * and the relocalisation / Sim3 SearchByProjection overloads) are SURVEY.md section 8(f) "next" rows.
+ * The remaining searches of the reference class (SearchByBoW x2, SearchForInitialization, SearchBySim3, Fuse x2)
+ * are SURVEY.md section 8(f) "next" rows.
  */
 #ifndef ORBMATCHER_H
 #define ORBMATCHER_H
 
+#include <set>
 #include <utility>
 #include <vector>
 
@@ -32,6 +32,14 @@ public:
 
     /* Project MapPoints tracked in last frame into the current frame and search matches (:1328-1471) */
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+
+    /* Project MapPoints seen in KeyFrame into the Frame and search matches; used in relocalisation (:1473-1600) */
+    int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th,
+                           const int ORBdist);
+
+    /* Project MapPoints using a similarity transformation and search matches; used in loop detection (:290-403) */
+    int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints,
+                           std::vector<MapPoint*>& vpMatched, int th);
 
     /* Matching to triangulate new MapPoints, epipolar constraint check (:657-823) */
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,

@@ -13,7 +13,9 @@
 #include "MapPoint.h"
 #else
 
+#include <cmath>
 #include <map>
+#include <set>
 #include <vector>
 
 #include "cv_compat.h"
@@ -36,10 +38,23 @@ public:
     int nObs = 1;
     cv::Mat descriptor;                        /* 1x32 CV_8U */
     cv::Mat worldPos;                          /* 3x1 CV_32F */
+    cv::Mat normal;                            /* 3x1 CV_32F mean viewing direction */
+    float mfMinDistance = 0, mfMaxDistance = 0;
     bool isBad() const { return bad; }
     int Observations() const { return nObs; }
     cv::Mat GetDescriptor() const { return descriptor; }
     cv::Mat GetWorldPos() const { return worldPos; }
+    cv::Mat GetNormal() const { return normal; }
+    float GetMinDistanceInvariance() const { return 0.8f * mfMinDistance; }     /* src/MapPoint.cc:380-384 */
+    float GetMaxDistanceInvariance() const { return 1.2f * mfMaxDistance; }     /* :386-390 */
+    template <class FrameOrKeyFrame>
+    int PredictScale(const float& currentDist, FrameOrKeyFrame* pF) const {     /* :392-424 */
+        const float ratio = mfMaxDistance / currentDist;
+        int nScale = (int)std::ceil(std::log(ratio) / pF->mfLogScaleFactor);
+        if (nScale < 0) nScale = 0;
+        else if (nScale >= pF->mnScaleLevels) nScale = pF->mnScaleLevels - 1;
+        return nScale;
+    }
 };
 
 class Frame {      /* include/Frame.h */
@@ -53,6 +68,8 @@ public:
     std::vector<float> mvScaleFactors, mvInvScaleFactors;
     float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;
     float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mb = 0;
+    int mnScaleLevels = 8;
+    float mfLogScaleFactor = 0.18232156f;      /* log(1.2) */
     cv::Mat mTcw;                              /* 4x4 CV_32F */
     ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
     void ComputeStereoMatches();               /* src/Frame.cc:646-820 -> viorb_stereo_match */
@@ -68,8 +85,13 @@ public:
     std::vector<MapPoint*> mapPoints;
     std::vector<float> mvScaleFactors, mvLevelSigma2;
     float fx = 0, fy = 0, cx = 0, cy = 0;
+    float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;
+    int mnScaleLevels = 8;
+    float mfLogScaleFactor = 0.18232156f;
     cv::Mat Rcw, tcw, Ow;                      /* 3x3, 3x1, 3x1 CV_32F */
     MapPoint* GetMapPoint(size_t idx) const { return mapPoints[idx]; }
+    std::vector<MapPoint*> GetMapPointMatches() const { return mapPoints; }
+    bool IsInImage(const float& x, const float& y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }
     cv::Mat GetCameraCenter() const { return Ow; }
     cv::Mat GetRotation() const { return Rcw; }
     cv::Mat GetTranslation() const { return tcw; }
