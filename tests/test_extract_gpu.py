@@ -98,8 +98,10 @@ def test_batch_matches_single(api, ctx, oracle):
     ex.close()
 
 
-def test_large_frame_hd(api, ctx, oracle):
-    h, w, nf, sf, nl, it, mt = CONFIGS["hd"]
+@pytest.mark.parametrize("cfg", ["hd", "uhd"])
+def test_large_frames(api, ctx, oracle, cfg):
+    """BASELINE config 4: 1920x1080 and 3840x2160, 5000 features"""
+    h, w, nf, sf, nl, it, mt = CONFIGS[cfg]
     img = synth.frame(h, w, 2)
     ref = oracle.Extractor(nf, sf, nl, it, mt)
     k_ref, d_ref = ref(img)
