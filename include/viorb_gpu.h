@@ -208,6 +208,15 @@ int viorb_search_for_triangulation(viorb_ctx* ctx,
                                    int only_stereo, int check_orientation,
                                    int32_t* matches12, int* nmatches);
 
+/* replaces void MapPoint::ComputeDistinctiveDescriptors()      include/MapPoint.h:71, src/MapPoint.cc:249-314,
+ * batched over the nmp map points a keyframe insertion touches (callers src/LocalMapping.cc:1176,1475,1559).
+ * obs_desc: the descriptors of each point's non-bad observations in std::map<KeyFrame*,size_t> iteration order
+ * (:269-275), concatenated; point p owns rows [obs_ptr[p], obs_ptr[p+1]) (obs_ptr[0] = 0, nmp+1 entries).
+ * best[p] = BestIdx within the point's rows (the row to clone into mDescriptor), -1 for a point without
+ * observations (the reference returns early, :262-263,277-278); best_median (may be NULL) = BestMedian.  */
+int viorb_distinctive_descriptors(viorb_ctx* ctx, const uint8_t* obs_desc, const int32_t* obs_ptr, int nmp,
+                                  int32_t* best, int32_t* best_median);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,8 +3,8 @@
  *
  * Restates /root/reference/src/ORBmatcher.cc (DescriptorDistance :1648-1664, SearchByProjection
  * :45-129 and :1328-1471, SearchForTriangulation :657-823, ComputeThreeMaxima :1602-1643),
- * /root/reference/src/Frame.cc (ComputeStereoMatches :646-820, grid :410-425,507-572) on plain
- * arrays.  Build with -ffp-contract=off.
+ * /root/reference/src/Frame.cc (ComputeStereoMatches :646-820, grid :410-425,507-572) and
+ * /root/reference/src/MapPoint.cc (ComputeDistinctiveDescriptors :249-314) on plain arrays.  Build with -ffp-contract=off.
  */
 #include "orb_oracle.h"
 
@@ -527,4 +527,33 @@ extern "C" int orc_search_for_triangulation(const orc_keypoint* k1, const uint8_
         }
     }
     return nmatches;
+}
+
+/* MapPoint::ComputeDistinctiveDescriptors, MapPoint.cc:249-314, for one point: desc = the N descriptors of its
+ * non-bad observations in map iteration order (:269-275).  Returns BestIdx (-1 when N == 0, the early return of
+ * :277-278) and BestMedian through *median.  The float Distances[N][N] of :284 holds integers <= 256 exactly. */
+extern "C" int orc_distinctive_descriptor(const uint8_t* desc, int N, int* median_out) {
+    if (median_out) *median_out = INT_MAX;
+    if (N <= 0) return -1;
+    std::vector<float> D((size_t)N * N);
+    for (int i = 0; i < N; i++) {
+        D[(size_t)i * N + i] = 0;
+        for (int j = i + 1; j < N; j++) {
+            const int distij = orc_descriptor_distance(desc + (size_t)i * 32, desc + (size_t)j * 32);
+            D[(size_t)i * N + j] = distij;
+            D[(size_t)j * N + i] = distij;
+        }
+    }
+    int BestMedian = INT_MAX, BestIdx = 0;
+    for (int i = 0; i < N; i++) {
+        std::vector<int> vDists(D.begin() + (size_t)i * N, D.begin() + (size_t)(i + 1) * N);
+        std::sort(vDists.begin(), vDists.end());
+        const int median = vDists[(size_t)(0.5 * (N - 1))];
+        if (median < BestMedian) {
+            BestMedian = median;
+            BestIdx = i;
+        }
+    }
+    if (median_out) *median_out = BestMedian;
+    return BestIdx;
 }

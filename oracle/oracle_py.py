@@ -79,6 +79,7 @@ def lib(path=None):
                                                  f32, f32, i32, i32, i32, vp]
     L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp,
                                                vp, i32, vp, f32, f32, vp, vp, i32, i32, vp]
+    L.orc_distinctive_descriptor.argtypes = [vp, i32, C.POINTER(i32)]
     L.orc_num_threads.argtypes = []
     if path.endswith(os.path.join("_build", "liborb_oracle.so")):
         _lib = L
@@ -322,3 +323,17 @@ def search_for_triangulation(k1, d1, ur1, has_mp1, k2, d2, ur2, has_mp2, fv1, fv
                                            _p(a[8]), _p(a[9]), len(a[7]), _p(a[10]), ex, ey, _p(a[11]), _p(a[12]),
                                            int(only_stereo), int(check_ori), _p(m12))
     return n, m12
+
+
+def distinctive_descriptors(obs_desc, obs_ptr):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:249-314) per point of a CSR batch -> (best, median)."""
+    obs_desc = _c(obs_desc, np.uint8).reshape(-1, 32)
+    obs_ptr = np.asarray(obs_ptr, np.int64)
+    best = np.zeros(len(obs_ptr) - 1, np.int32)
+    med = np.zeros(len(obs_ptr) - 1, np.int32)
+    for p in range(len(best)):
+        rows = _c(obs_desc[obs_ptr[p]:obs_ptr[p + 1]])
+        m = C.c_int()
+        best[p] = lib().orc_distinctive_descriptor(_p(rows) if len(rows) else None, len(rows), C.byref(m))
+        med[p] = m.value
+    return best, med

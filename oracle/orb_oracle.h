@@ -146,6 +146,8 @@ int orc_search_for_triangulation(const orc_keypoint* k1, const uint8_t* d1, cons
                                  int only_stereo, int check_ori, int32_t* matches12 /* n1 */);
 
 /* synthetic-input independent helpers */
+/* MapPoint::ComputeDistinctiveDescriptors, MapPoint.cc:249-314 (one point) */
+int orc_distinctive_descriptor(const uint8_t* desc, int N, int* median_out);
 int orc_num_threads(void);
 
 #ifdef __cplusplus

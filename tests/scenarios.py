@@ -64,3 +64,22 @@ def row_band_nodes(band=24, drop_every=7):
 
 
 RECTIFIED_F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32)   # l = x1' F12 = [0, 1, -y1]
+
+
+def distinctive_batch(seed, nmp=300, max_obs=40, big=(0, 1, 2, 33, 257)):
+    """CSR batch of map-point observation descriptors for MapPoint::ComputeDistinctiveDescriptors: clusters of noisy
+    copies of a base descriptor (so medians tie between rows), plus points with 0/1/2 and many observations."""
+    rng = np.random.default_rng(seed)
+    counts = list(big) + [int(c) for c in rng.integers(1, max_obs, nmp - len(big))]
+    rows, ptr = [], [0]
+    for c in counts:
+        base = rng.integers(0, 256, 32).astype(np.uint8)
+        d = np.repeat(base[None], c, 0)
+        flips = rng.integers(0, 256, (c, 32)).astype(np.uint8) & rng.integers(0, 256, (c, 32)).astype(np.uint8) \
+            & rng.integers(0, 256, (c, 32)).astype(np.uint8)
+        d ^= flips
+        if c > 3:
+            d[c // 2] = d[0]                      # exact duplicates -> equal medians, first row must win
+        rows.append(d)
+        ptr.append(ptr[-1] + c)
+    return np.concatenate(rows).astype(np.uint8), np.asarray(ptr, np.int32)

@@ -116,3 +116,18 @@ def test_two_rank_gloo_top2_merge():
                        env=env, capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "RANK0 OK" in p.stdout and "RANK1 OK" in p.stdout
+
+
+def test_distinctive_descriptor_vs_numpy(oracle):
+    """MapPoint.cc:249-314 restatement against an independent numpy statement (sort each row, take [int(0.5*(N-1))],
+    first least median)."""
+    desc, ptr = S.distinctive_batch(3, nmp=60)
+    best, med = oracle.distinctive_descriptors(desc, ptr)
+    for p in range(len(ptr) - 1):
+        rows = desc[ptr[p]:ptr[p + 1]]
+        if len(rows) == 0:
+            assert best[p] == -1
+            continue
+        D = np.sort(np_dist(rows, rows), axis=1)
+        m = D[:, int(0.5 * (len(rows) - 1))]
+        assert best[p] == int(np.argmin(m)) and med[p] == m.min()

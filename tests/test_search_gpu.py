@@ -192,3 +192,15 @@ def test_search_for_triangulation(api, ctx, oracle, stereo, only_stereo, check_o
                                       only_stereo)
     assert n_ref > (5 if only_stereo else 40)
     assert n == n_ref and (m12 == m_ref).all()
+
+
+def test_distinctive_descriptors(api, ctx, oracle):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:249-314) batched: BestIdx and BestMedian identical"""
+    m = api.ORBmatcher(ctx=ctx)
+    for seed in (0, 1):
+        desc, ptr = S.distinctive_batch(seed)
+        best, med = m.ComputeDistinctiveDescriptors(desc, ptr)
+        rb, rm = oracle.distinctive_descriptors(desc, ptr)
+        assert (best == rb).all() and (med == rm).all()
+    best, med = m.ComputeDistinctiveDescriptors(np.zeros((0, 32), np.uint8), np.zeros(4, np.int32))
+    assert (best == -1).all()

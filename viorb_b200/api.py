@@ -71,6 +71,7 @@ def lib():
         "viorb_frame_features_in_area": [vp, f32, f32, f32, i32, i32, vp, i32, pi],
         "viorb_search_by_projection_local": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, vp, pi],
         "viorb_search_by_projection_frame": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, i32, i32, i32, vp, pi],
+        "viorb_distinctive_descriptors": [vp, vp, vp, i32, vp, vp],
         "viorb_search_for_triangulation": [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp,
                                            i32, vp, f32, f32, vp, vp, i32, i32, i32, vp, pi],
     }
@@ -373,6 +374,17 @@ class ORBmatcher:
             len(a[9]), _ptr(a[12]), ex, ey, _ptr(a[13]), _ptr(a[14]), len(a[13]), int(bOnlyStereo),
             int(self.mbCheckOrientation), _ptr(m12), C.byref(n)))
         return n.value, m12
+
+    def ComputeDistinctiveDescriptors(self, obs_desc, obs_ptr):
+        """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:249-314) over a CSR batch of map points:
+        returns (BestIdx per point, BestMedian per point)."""
+        d = np.ascontiguousarray(obs_desc, np.uint8).reshape(-1, 32)
+        p = np.ascontiguousarray(obs_ptr, np.int32)
+        best = np.zeros(len(p) - 1, np.int32)
+        med = np.zeros(len(p) - 1, np.int32)
+        _ck(lib().viorb_distinctive_descriptors(self.ctx.h, _ptr(d) if len(d) else None, _ptr(p), len(best),
+                                                _ptr(best), _ptr(med)))
+        return best, med
 
 
 def ComputeStereoMatches(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, mbf, mb, frame_l=0, frame_r=0):

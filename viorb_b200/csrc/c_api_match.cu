@@ -38,6 +38,9 @@ int viorb_launch_triangulation(const viorb_keypoint* k1, const uint8_t* d1, cons
                                float ex, float ey, const float* scale2, const float* sigma2, int nlevels, int onlyStereo,
                                int checkOri, int* d_matches12, int* d_nmatches, cudaStream_t s);
 
+int viorb_launch_distinctive(const uint8_t* d_desc, const int* d_ptr, int nmp, int* d_best, int* d_bestMedian,
+                             cudaStream_t s);
+
 namespace {
 
 /* bump allocator over one device scratch buffer: a call uploads all its inputs into a single arena */
@@ -328,6 +331,33 @@ int viorb_search_for_triangulation(viorb_ctx* c, const viorb_keypoint* k1, const
     VCU(cudaGetLastError());
     VCU(cudaMemcpyAsync(matches12, dmatch, (size_t)n1 * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
     VCU(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    return VIORB_OK;
+}
+
+int viorb_distinctive_descriptors(viorb_ctx* c, const uint8_t* obs_desc, const int32_t* obs_ptr, int nmp, int32_t* best,
+                                  int32_t* best_median) {
+    if (!c || nmp < 0 || (nmp > 0 && (!obs_ptr || !best))) return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    if (nmp == 0) return VIORB_OK;
+    if (obs_ptr[0] != 0) return viorb_fail(VIORB_ERR_INVALID, "obs_ptr[0] must be 0");
+    for (int i = 0; i < nmp; i++)
+        if (obs_ptr[i + 1] < obs_ptr[i]) return viorb_fail(VIORB_ERR_INVALID, "obs_ptr must be non-decreasing");
+    const size_t total = (size_t)obs_ptr[nmp];
+    if (total > 0 && !obs_desc) return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    int rc;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    const size_t bytes = pad(std::max<size_t>(total, 1) * 32) + pad((size_t)(nmp + 1) * 4) + 2 * pad((size_t)nmp * 4) + 2048;
+    Arena a;
+    if ((rc = viorb_ctx_scratch(c, bytes, &a.base))) return rc;
+    uint8_t* dd = a.take<uint8_t>(std::max<size_t>(total, 1) * 32);
+    int* dp = a.take<int>(nmp + 1);
+    int* db = a.take<int>(nmp);
+    int* dm = a.take<int>(nmp);
+    if ((rc = upload(c, dd, obs_desc, total * 32)) || (rc = upload(c, dp, obs_ptr, (size_t)nmp + 1))) return rc;
+    viorb_ctx_add_launches(c, viorb_launch_distinctive(dd, dp, nmp, db, dm, viorb_ctx_stream(c)));
+    VCU(cudaGetLastError());
+    VCU(cudaMemcpyAsync(best, db, (size_t)nmp * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    if (best_median) VCU(cudaMemcpyAsync(best_median, dm, (size_t)nmp * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
     VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
     return VIORB_OK;
 }

@@ -602,6 +602,68 @@ __global__ void __launch_bounds__(1024) triangulation_finalize_kernel(const vior
     if (tid == 0) *nmatches = total;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:249-314), batched: one CTA per map point, one
+ * warp per row of the point's N x N Hamming matrix.  The matrix is never stored: the median of row i,
+ * vDists[(int)(0.5*(N-1))] of the sorted row (:298-299), is the smallest value whose cumulative count in
+ * the row's 257-bin histogram reaches rank+1 (distances are integers in [0, 256]; the diagonal counts as 0,
+ * :286).  The first row with the least median wins (strict <, :301-305).
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(128) distinctive_kernel(const uint8_t* __restrict__ desc, const int* __restrict__ ptr,
+                                                          int* __restrict__ best, int* __restrict__ bestMedian) {
+    __shared__ unsigned hist[4][288];
+    __shared__ unsigned long long red[4];
+    const int mp = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int beg = ptr[mp], N = ptr[mp + 1] - beg;
+    if (N <= 0) {
+        if (threadIdx.x == 0) { best[mp] = -1; if (bestMedian) bestMedian[mp] = INT_MAX; }
+        return;
+    }
+    const uint8_t* d0 = desc + (size_t)beg * 32;
+    const unsigned rank = (unsigned)(int)(0.5 * (N - 1)) + 1u;
+    unsigned long long mine = ~0ull;
+    for (int i = warp; i < N; i += 4) {
+#pragma unroll
+        for (int b = 0; b < 9; b++) hist[warp][lane * 9 + b] = 0;
+        __syncwarp();
+        for (int j = lane; j < N; j += 32)
+            atomicAdd(&hist[warp][i == j ? 0 : hamming_rows(d0 + (size_t)i * 32, d0 + (size_t)j * 32)], 1u);
+        __syncwarp();
+        unsigned cnt[9], sum = 0;
+#pragma unroll
+        for (int b = 0; b < 9; b++) { cnt[b] = hist[warp][lane * 9 + b]; sum += cnt[b]; }
+        unsigned incl = sum;                                   /* inclusive scan of the per-lane bin sums */
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, incl >= rank);
+        const int src = __ffs(hit) - 1;                        /* hit != 0: the last lane's incl == N >= rank */
+        int median = 0;
+        if (lane == src) {
+            unsigned c = incl - sum;
+#pragma unroll
+            for (int b = 0; b < 9; b++) {
+                c += cnt[b];
+                if (c >= rank) { median = lane * 9 + b; break; }
+            }
+        }
+        median = __shfl_sync(0xffffffffu, median, src);
+        const unsigned long long key = ((unsigned long long)(unsigned)median << 32) | (unsigned)i;
+        mine = key < mine ? key : mine;
+        __syncwarp();
+    }
+    if (lane == 0) red[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long b = red[0];
+        for (int w = 1; w < 4; w++) b = red[w] < b ? red[w] : b;
+        best[mp] = (int)(b & 0xffffffffu);
+        if (bestMedian) bestMedian[mp] = (int)(b >> 32);
+    }
+}
+
 }  // namespace
 
 /* ------------------------------------------------------------------------------------------------ launchers */
@@ -673,4 +735,11 @@ int viorb_launch_triangulation(const viorb_keypoint* k1, const uint8_t* d1, cons
     }
     triangulation_finalize_kernel<<<1, 1024, 0, s>>>(k1, k2, n1, checkOri, d_matches12, d_nmatches);
     return launches + 1;
+}
+
+int viorb_launch_distinctive(const uint8_t* d_desc, const int* d_ptr, int nmp, int* d_best, int* d_bestMedian,
+                             cudaStream_t s) {
+    if (nmp <= 0) return 0;
+    distinctive_kernel<<<nmp, 128, 0, s>>>(d_desc, d_ptr, d_best, d_bestMedian);
+    return 1;
 }
