@@ -88,6 +88,7 @@ struct viorb_extractor {
     DevBuf<int16_t> tabI16;        /* xa | yb */
     DevBuf<int4> groups;           /* FAST cell groups: {level, cell row, first cell, cells} */
     int ngroups = 0;
+    int groupClass[5] = {0, 0, 0, 0, 0};   /* groups sorted by tile byte shift: class sh = [groupClass[sh], groupClass[sh+1]) */
     ResizeTables tables;
     /* pass workspaces: consecutive passes alternate between two lanes (own stream + buffers) so that the
      * latency-bound kernels of one pass overlap with those of the next */
@@ -100,6 +101,7 @@ struct viorb_extractor {
         DevBuf<uint32_t> cand, sel;
         DevBuf<int> counters;      /* candCount | selCount | status */
         DevBuf<uint16_t> nodeOf;
+        TmaMaps maps;              /* TMA descriptors of this lane's pyramid buffer */
     } lanes[4];
     int nlanes = 2;
     cudaEvent_t evFork = nullptr;
@@ -244,6 +246,14 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
         }
     }
     e->ngroups = (int)groups.size();
+    {   /* sort by the byte shift of the group's window inside a 4-byte word of the stored row (fast_cells_kernel<SH>) */
+        auto shiftOf = [&](const int4& gr) { return (VIORB_ROI_X0 + VIORB_FAST_BORDER + gr.z * g.lv[gr.x].wCell + 3) & 3; };
+        std::stable_sort(groups.begin(), groups.end(), [&](const int4& a, const int4& b) { return shiftOf(a) < shiftOf(b); });
+        int cnt[4] = {0, 0, 0, 0};
+        for (const int4& gr : groups) cnt[shiftOf(gr)]++;
+        e->groupClass[0] = 0;
+        for (int i = 0; i < 4; i++) e->groupClass[i + 1] = e->groupClass[i] + cnt[i];
+    }
     int rc;
     if ((rc = e->groups.ensure(groups.size() + 1))) return rc;
     CU(cudaMemcpyAsync(e->groups.p, groups.data(), groups.size() * sizeof(int4), cudaMemcpyHostToDevice, e->ctx->stream));
@@ -277,6 +287,7 @@ int ensure_workspace(viorb_extractor* e, int F) {
         if ((rc = ln.counters.ensure((size_t)F * g.nlevels * 2 + 4))) return rc;
         CU(cudaMemsetAsync(ln.counters.p, 0, ln.counters.n * sizeof(int), e->ctx->stream));
         ln.buf.pyr = ln.pyr.p;
+        if (viorb_encode_tma_maps(g, ln.pyr.p, F, &ln.maps)) return fail(VIORB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
         ln.buf.cand = ln.cand.p;
         ln.buf.nodeOf = ln.nodeOf.p;
         ln.buf.sel = ln.sel.p;
@@ -308,7 +319,7 @@ int run_pass(viorb_extractor* e, int lane, const uint8_t* d_images, size_t step,
     if (e->profiling) CU(cudaEventRecord(ev[0], st));
     c->launches += viorb_launch_pyramid(g, e->tables, d_images, step, frameStride, F, ln.buf, st);
     if (e->profiling) CU(cudaEventRecord(ev[1], st));
-    c->launches += viorb_launch_fast(g, e->groups.p, e->ngroups, F, ln.buf, st);
+    c->launches += viorb_launch_fast(g, ln.maps, e->groups.p, e->groupClass, F, ln.buf, st);
     if (e->profiling) CU(cudaEventRecord(ev[2], st));
     c->launches += viorb_launch_octree(g, F, ln.buf, e->nodeCap, st);
     if (e->profiling) CU(cudaEventRecord(ev[3], st));

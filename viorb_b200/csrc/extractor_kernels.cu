@@ -13,6 +13,9 @@
  */
 #include "extractor_kernels.cuh"
 
+#include <cuda.h>
+#include <string.h>
+
 #include "viorb_orb_pattern.h"
 
 namespace {
@@ -138,22 +141,36 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
     }
     __syncthreads();
     if (wi >= stepWords) return;
+    /* consecutive output rows mostly share a source row (sy advances by 1 or 2 per output row at scale 1.2):
+     * the horizontal pass of the lower source row is kept in registers and reused as the upper row of the next */
+    int prevS1 = -1;
+    int Tp[4] = {0, 0, 0, 0};
     for (int r = (tid >> 5) * 8; r < (tid >> 5) * 8 + 8; r++) {
         const int y = ya + r;
         if (y > yhi) break;
         const int dy = reflect101(y, L.h);
         const int sy = t.yofs[L.ytab + dy];
         const int b0 = t.yb[2 * (L.ytab + dy)], b1 = t.yb[2 * (L.ytab + dy) + 1];
-        const uint8_t* S0 = &src[(min(sy, P.h - 1) - sy0) * RZ_SSTRIDE];
-        const uint8_t* S1 = &src[(min(sy + 1, P.h - 1) - sy0) * RZ_SSTRIDE];
+        const int s0 = min(sy, P.h - 1) - sy0, s1 = min(sy + 1, P.h - 1) - sy0;
+        const uint8_t* S0 = &src[s0 * RZ_SSTRIDE];
+        const uint8_t* S1 = &src[s1 * RZ_SSTRIDE];
+        int T0[4], T1[4];
+        if (s0 == prevS1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) T0[j] = Tp[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) T0[j] = (S0[so[j]] * a0[j] + S0[so1[j]] * a1[j]) >> 4;
+        }
         uint32_t word = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const int T0 = S0[so[j]] * a0[j] + S0[so1[j]] * a1[j];
-            const int T1 = S1[so[j]] * a0[j] + S1[so1[j]] * a1[j];
-            const uint32_t v = (uint32_t)((((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2) & 0xffu;
+            T1[j] = (S1[so[j]] * a0[j] + S1[so1[j]] * a1[j]) >> 4;
+            const uint32_t v = (uint32_t)((((b0 * T0[j]) >> 16) + ((b1 * T1[j]) >> 16) + 2) >> 2) & 0xffu;
             word |= (ok[j] ? v : 0u) << (8 * j);
+            Tp[j] = T1[j];
         }
+        prevS1 = s1;
         reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(y + VIORB_EDGE) * L.step)[wi] = word;
     }
 }
@@ -173,29 +190,65 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
  * thresholds and the per-cell retry (:812) only re-filters by minThFAST.
  * ---------------------------------------------------------------------------------------------- */
 #define FAST_GROUP 4            /* horizontally adjacent cells per CTA */
-#define FAST_ROWS 68            /* cell sub-image rows  (hCell + 6 <= 66) */
+#define FAST_ROWS VIORB_FAST_TILE_ROWS   /* cell sub-image rows  (hCell + 6 <= 66) */
 #define FAST_MAXQ 45            /* quads per window row: 4 cells x wCell (<= 45 when nCols >= 2; one cell of <= 59 otherwise) */
-#define FAST_TW 49              /* tile row stride in words (odd): 1 lead word + 45 quads + 1 tail word, padded */
+#define FAST_TW (VIORB_FAST_TILE_BYTES / 4)   /* tile row stride in words = the TMA box width: 1 lead word + 45 quads + 1 tail word */
 #define FAST_SCW 49             /* score row stride in words (odd): 1 zero word + 45 quads + 1 zero word, padded */
 #define FAST_MAXWORK 2048        /* quads per CTA: the host sizes the cell groups so that NQ * wh <= 2048 */
+#define FAST_MAXPIX 4096        /* corner pixels (score > 0) per CTA before non-max suppression */
 
 __device__ __forceinline__ unsigned funnel_bytes(unsigned lo, unsigned hi, int sh) {
     /* bytes sh..sh+3 of the 8-byte little-endian sequence lo|hi (sh in 0..3) */
     return __byte_perm(lo, hi, 0x3210u + 0x1111u * (unsigned)sh);
 }
 
+/* ---- TMA (cp.async.bulk.tensor) + mbarrier, raw PTX ---- */
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      /* the init must be visible to the async proxy */
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "MBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra MBAR_WAIT_%=;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+/* one 3-D box {x, y, z} of the tensor described by `map` into shared memory; completes `bar` with the box bytes */
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* map, int x, int y, int z, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+/* Four adjacent pixels x+dx .. x+dx+3 of the window row `r` (r = word holding window bytes 4q .. 4q+3 when the
+ * shift is 0).  The TMA box starts on a 16-byte boundary of the stored row, so the detection window starts at
+ * byte SH (0..3) of a tile word; S = SH + dx is a compile-time constant and the access folds to one aligned
+ * word (S % 4 == 0) or two words and one PRMT. */
+template <int S>
+__device__ __forceinline__ unsigned fast_ld4(const unsigned* r) {
+    constexpr int w = S >= 0 ? S / 4 : -((3 - S) / 4);
+    constexpr int b = S - 4 * w;
+    if (b == 0) return r[w];
+    return funnel_bytes(r[w], r[w + 1], b);
+}
+
 /* ring sample k of four adjacent pixels as two s16x2 registers (A = pixels 0,2; B = pixels 1,3), raw grey
- * values.  row = &tile word holding x-4..x-1 of the centre row; ring offsets are compile-time constants. */
+ * values; ring offsets are compile-time constants. */
 #define FAST_RING_LIST(OP)                                                                            \
     OP(0, 3, 0) OP(1, 3, 1) OP(2, 2, 2) OP(3, 1, 3) OP(4, 0, 3) OP(5, -1, 3) OP(6, -2, 2) OP(7, -3, 1)    \
     OP(8, -3, 0) OP(9, -3, -1) OP(10, -2, -2) OP(11, -1, -3) OP(12, 0, -3) OP(13, 1, -3) OP(14, 2, -2) OP(15, 3, -1)
 
+template <int SH>
 __device__ __forceinline__ void fast_load_ring(const unsigned* row, unsigned (&rA)[16], unsigned (&rB)[16]) {
 #define RING(k, dy, dx)                                                                                \
     {                                                                                                  \
-        const unsigned* r_ = row + (dy) * FAST_TW;                                                    \
-        const unsigned w_ = (dx) == 0 ? r_[1] : (dx) > 0 ? funnel_bytes(r_[1], r_[2], (dx))           \
-                                                          : funnel_bytes(r_[0], r_[1], 4 + (dx));      \
+        const unsigned w_ = fast_ld4<SH + (dx)>(row + (dy) * FAST_TW);                                 \
         rA[k] = __byte_perm(w_, 0, 0x4240);                                                            \
         rB[k] = __byte_perm(w_, 0, 0x4341);                                                            \
     }
@@ -233,18 +286,22 @@ __device__ __forceinline__ unsigned fast_score_s16x2(const unsigned (&r)[16], un
     return __viaddmax_s16x2_relu(best, negBias, 0u);                         /* relu(S + 1 - minTh) */
 }
 
+template <int SH>
 __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__ FrameGeom g,
+                                                         const __grid_constant__ TmaMaps maps,
                                                          const int4* __restrict__ groups,
-                                                         const uint8_t* __restrict__ pyr,
                                                          uint32_t* __restrict__ cand, int* __restrict__ candCount,
                                                          int* __restrict__ status) {
-    __shared__ unsigned tile[FAST_ROWS * FAST_TW];
+    /* tile and work0 are contiguous: once both are dead (after phase 2) the region holds the corner-pixel list */
+    __shared__ __align__(128) unsigned char raw[FAST_ROWS * FAST_TW * 4 + FAST_MAXWORK * 2];
     __shared__ unsigned sc[(FAST_ROWS - 4) * FAST_SCW];
-    __shared__ unsigned short work0[FAST_MAXWORK];    /* quads that are not flat (compass pre-test) */
     __shared__ unsigned short work[FAST_MAXWORK];     /* quads that survive the high-speed test */
-    __shared__ unsigned char lmq[FAST_MAXWORK];       /* local-maximum bits of the surviving quads */
-    __shared__ int nwork, nwork0;
-    __shared__ int cellIni[FAST_GROUP];               /* per cell: does it hold a corner at iniThFAST? */
+    __shared__ __align__(8) unsigned long long bar;   /* mbarrier of the TMA tile load */
+    __shared__ int nwork, nwork0, npix, nout, gbase;
+    __shared__ int cellCnt[FAST_GROUP][2];            /* per cell: local maxima below / at-or-above iniThFAST */
+    unsigned* tile = reinterpret_cast<unsigned*>(raw);
+    unsigned short* work0 = reinterpret_cast<unsigned short*>(raw + FAST_ROWS * FAST_TW * 4);   /* non-flat quads */
+    unsigned short* pix = reinterpret_cast<unsigned short*>(raw);   /* corner pixels: x | y << 8 | localmax << 15 */
     const int frame = blockIdx.y;
     /* a CTA owns up to FAST_GROUP horizontally adjacent cells of one cell row: {level, cell row, first cell, n} */
     const int4 grp = __ldg(&groups[blockIdx.x]);
@@ -262,46 +319,31 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     if (g.dbg & 16) return;
     const int tid = threadIdx.x, lane = tid & 31;
     const int NQ = (ww + 3) >> 2;            /* quads per window row */
-    const int NW = NQ + 2;                   /* tile words per row: quads + one word each side */
 
-    /* stage: tile byte (4 + x) of row y = level pixel (iniX + 3 + x, iniY + y); word w covers x in [4w-4, 4w) */
-    {
-        const uint8_t* roi = pyr + (size_t)frame * g.pyrFrameBytes + L.pyrOff + (size_t)VIORB_EDGE * L.step + VIORB_ROI_X0;
-        const int gx0 = iniX + 3 - 4;                        /* level x of tile byte 0 (>= 15) */
-        const int sh = gx0 & 3;
-        const uint8_t* base = roi + (size_t)iniY * L.step + (gx0 - sh);   /* 4-byte aligned */
-        /* batches of 8 words per thread: all 16 loads of a batch are in flight before the first use */
-        const unsigned invNW = 0xffffffffu / (unsigned)NW + 1u;       /* i / NW == umulhi(i, invNW) for i < 2^16 */
-        const int total = ch * NW;
-        if (!(g.dbg & 8))
-        for (int i0 = tid; i0 < total; i0 += 8 * 128) {
-            unsigned lo[8], hi[8];
-            int dst[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int i = i0 + 128 * k;
-                const int y = (int)__umulhi((unsigned)i, invNW), w = i - y * NW;
-                dst[k] = i < total ? y * FAST_TW + w : -1;
-                if (i < total) {
-                    const unsigned* src = reinterpret_cast<const unsigned*>(base + (size_t)y * L.step) + w;
-                    lo[k] = __ldg(src);
-                    hi[k] = __ldg(src + 1);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (dst[k] >= 0) tile[dst[k]] = funnel_bytes(lo[k], hi[k], sh);
-        }
-        for (int i = tid; i < (wh + 2) * FAST_SCW; i += blockDim.x) sc[i] = 0;
-        if (tid == 0) { nwork = 0; nwork0 = 0; }
-        if (tid < FAST_GROUP) cellIni[tid] = 0;
+    /* stage: one TMA box per CTA.  The box starts at the 16-byte boundary A at or below window x = -3 of the
+     * stored row (TMA needs a 16-byte aligned start), so window pixel x of row y sits at tile byte
+     * 4*w0 + SH + x of row y, SH = (stored byte of window x=0) & 3 -- the same for all groups of a launch (the
+     * host sorts the groups by SH; with 4-cell groups every window starts at byte 51 + 4k*wCell, SH = 3).
+     * Bytes of the box outside the stored level read as 0 and are never used. */
+    const int gstart = VIORB_ROI_X0 + iniX + 3;
+    const int boxX = (gstart - 3) & ~15;
+    const int w0 = (gstart - boxX) >> 2;
+    if (tid == 0) {
+        const int boxH = min(L.hCell + 6, FAST_ROWS);
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, (unsigned)(VIORB_FAST_TILE_BYTES * boxH));
+        tma_load_3d(tile, &maps.fast[l], boxX, VIORB_EDGE + iniY, frame, &bar);
+        nwork = 0; nwork0 = 0; npix = 0; nout = 0;
     }
+    for (int i = tid; i < (wh + 2) * FAST_SCW; i += blockDim.x) sc[i] = 0;
+    if (tid < FAST_GROUP * 2) (&cellCnt[0][0])[tid] = 0;
     __syncthreads();
+    mbar_wait(&bar, 0);
 
-    /* phase 0 -- byte-domain pre-test on the four compass samples (k = 0, 4, 8, 12) of every quad: each 9-arc
-     * contains one of them, so if |ring - centre| <= minTh at all four, for all four pixels, the quad is flat.
-     * flag byte bit 7 = (|d| > minTh); carries between bytes can only add false positives.  Non-flat quads are
-     * compacted so the later phases run on dense warps. */
+    /* phase 0 -- byte-domain pre-test on the four compass samples (k = 0, 4, 8, 12) of every quad: every 9-arc
+     * of the ring contains two ADJACENT compass samples, so a pixel can only be a corner at minTh if
+     * |ring - centre| > minTh at two adjacent compass points.  flag byte bit 7 = (|d| > minTh); carries between
+     * bytes can only add false positives.  Surviving quads are compacted so the later phases run on dense warps. */
     const int ntask = NQ * wh;
     const unsigned invNQ = 0xffffffffu / (unsigned)NQ + 1u;          /* t / NQ == umulhi(t, invNQ) for t < 2^16 */
     {
@@ -311,13 +353,14 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
             bool keep = false;
             if (t < ntask) {
                 const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
-                const unsigned* row = &tile[(y + 3) * FAST_TW + q];
-                const unsigned cw4 = row[1];
-                const unsigned d0 = __vabsdiffu4(row[3 * FAST_TW + 1], cw4), d8 = __vabsdiffu4(row[-3 * FAST_TW + 1], cw4);
-                const unsigned d4 = __vabsdiffu4(funnel_bytes(row[1], row[2], 3), cw4);
-                const unsigned d12 = __vabsdiffu4(funnel_bytes(row[0], row[1], 1), cw4);
-                keep = ((((d0 + addc) | d0) | ((d8 + addc) | d8) | ((d4 + addc) | d4) | ((d12 + addc) | d12)) & 0x80808080u) != 0;
-                if (g.dbg & 1) keep = (g.dbg & 4) != 0;
+                const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
+                const unsigned cw4 = fast_ld4<SH>(row);
+                const unsigned d0 = __vabsdiffu4(fast_ld4<SH>(row + 3 * FAST_TW), cw4);
+                const unsigned d8 = __vabsdiffu4(fast_ld4<SH>(row - 3 * FAST_TW), cw4);
+                const unsigned d4 = __vabsdiffu4(fast_ld4<SH + 3>(row), cw4);
+                const unsigned d12 = __vabsdiffu4(fast_ld4<SH - 3>(row), cw4);
+                const unsigned f0 = (d0 + addc) | d0, f4 = (d4 + addc) | d4, f8 = (d8 + addc) | d8, f12 = (d12 + addc) | d12;
+                keep = ((((f0 | f8) & (f4 | f12))) & 0x80808080u) != 0;   /* (f0&f4)|(f4&f8)|(f8&f12)|(f12&f0) */
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             int basePos = 0;
@@ -340,10 +383,10 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
         if (i < n0) {
             t = work0[i];
             const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
-            const unsigned* row = &tile[(y + 3) * FAST_TW + q];
-            const unsigned cw4 = row[1];
+            const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
+            const unsigned cw4 = fast_ld4<SH>(row);
             unsigned rA[16], rB[16];
-            fast_load_ring(row, rA, rB);
+            fast_load_ring<SH>(row, rA, rB);
             const unsigned nvA = __vneg2(__byte_perm(cw4, 0, 0x4240)), nvB = __vneg2(__byte_perm(cw4, 0, 0x4341));
             unsigned loA[8], hiA[8], loB[8], hiB[8];
 #pragma unroll
@@ -377,10 +420,10 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     for (int i = tid; i < nw; i += blockDim.x) {
         const int t = work[i];
         const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
-        const unsigned* row = &tile[(y + 3) * FAST_TW + q];
+        const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
         unsigned rA[16], rB[16];
-        fast_load_ring(row, rA, rB);
-        const unsigned cw4 = row[1];
+        fast_load_ring<SH>(row, rA, rB);
+        const unsigned cw4 = fast_ld4<SH>(row);
         const unsigned sA = fast_score_s16x2(rA, __byte_perm(cw4, 0, 0x4240), negBias);
         const unsigned sB = fast_score_s16x2(rB, __byte_perm(cw4, 0, 0x4341), negBias);
         unsigned word = sA | (sB << 8);                       /* bytes = pixels x, x+1, x+2, x+3 */
@@ -390,70 +433,97 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     }
     __syncthreads();
 
-    /* 3x3 local maxima + per-cell count at iniThFAST.  sc holds S - (minTh - 1), 0 = no corner.  cv::FAST runs
-     * on the cell's own sub-image, so neighbours in another cell (or outside the window) count as 0. */
+    /* corner pixels (score > 0) as a dense list -- the tile and work0 are dead, the list takes their place
+     * (capacity 8576 >= 4 * FAST_MAXWORK entries) */
+    for (int i0 = 0; i0 < nw; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        unsigned word = 0;
+        int y = 0, q = 0;
+        if (i < nw) {
+            const int t = work[i];
+            y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t;
+            q = t - y * NQ;
+            word = sc[(y + 1) * FAST_SCW + q + 1];
+        }
+        const unsigned lt = (1u << lane) - 1;
+        const unsigned m0 = __ballot_sync(0xffffffffu, (word & 0x000000ffu) != 0), m1 = __ballot_sync(0xffffffffu, (word & 0x0000ff00u) != 0);
+        const unsigned m2 = __ballot_sync(0xffffffffu, (word & 0x00ff0000u) != 0), m3 = __ballot_sync(0xffffffffu, (word & 0xff000000u) != 0);
+        const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
+        int basePos = 0;
+        if (lane == 0 && (m0 | m1 | m2 | m3)) basePos = atomicAdd(&npix, c0 + c1 + c2 + c3);
+        basePos = __shfl_sync(0xffffffffu, basePos, 0);
+        const unsigned e = (unsigned)(q * 4) | ((unsigned)y << 8);
+        if (word & 0x000000ffu) pix[basePos + __popc(m0 & lt)] = (unsigned short)e;
+        if (word & 0x0000ff00u) pix[basePos + c0 + __popc(m1 & lt)] = (unsigned short)(e + 1);
+        if (word & 0x00ff0000u) pix[basePos + c0 + c1 + __popc(m2 & lt)] = (unsigned short)(e + 2);
+        if (word & 0xff000000u) pix[basePos + c0 + c1 + c2 + __popc(m3 & lt)] = (unsigned short)(e + 3);
+    }
+    __syncthreads();
+
+    /* 3x3 non-max suppression, one thread per corner pixel.  sc holds S - (minTh - 1), 0 = no corner.  cv::FAST
+     * runs on the cell's own sub-image, so neighbours in another cell (or outside the window) count as 0.
+     * A local maximum at minThFAST with S >= iniThFAST is also one at iniThFAST (weaker neighbours only drop to 0). */
     const uint8_t* scb = reinterpret_cast<const uint8_t*>(sc);
     const int iniShift = g.iniTh - g.minTh + 1;
-    for (int i = tid; i < nw; i += blockDim.x) {
-        const int t = work[i];
-        const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
-        const unsigned word = sc[(y + 1) * FAST_SCW + q + 1];
-        unsigned bits = 0;
-        if (word != 0) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int sv = (word >> (8 * j)) & 0xff;
-                if (sv == 0) continue;
-                const int x = q * 4 + j;
-                const int cg = (x >= L.wCell) + (x >= 2 * L.wCell) + (x >= 3 * L.wCell), xin = x - cg * L.wCell;
-                const uint8_t* p = scb + ((y + 1) * FAST_SCW + q + 1) * 4 + j;
-                bool lm = sv > p[-FAST_SCW * 4] && sv > p[FAST_SCW * 4];
-                if (xin > 0) lm = lm && sv > p[-1] && sv > p[-FAST_SCW * 4 - 1] && sv > p[FAST_SCW * 4 - 1];
-                if (xin < L.wCell - 1) lm = lm && sv > p[1] && sv > p[-FAST_SCW * 4 + 1] && sv > p[FAST_SCW * 4 + 1];
-                if (lm) {
-                    bits |= 1u << j;
-                    if (sv >= iniShift) cellIni[cg] = 1;
-                }
+    const int np = npix;
+    for (int i = tid; i < np; i += blockDim.x) {
+        const unsigned e = pix[i];
+        const int x = e & 0xff, y = (e >> 8) & 0x3f;
+        const int cg = (x >= L.wCell) + (x >= 2 * L.wCell) + (x >= 3 * L.wCell), xin = x - cg * L.wCell;
+        const uint8_t* p = scb + ((y + 1) * FAST_SCW + 1) * 4 + x;
+        const int sv = p[0];
+        const int up = p[-FAST_SCW * 4], dn = p[FAST_SCW * 4];
+        const int lf = max(max((int)p[-1], (int)p[-FAST_SCW * 4 - 1]), (int)p[FAST_SCW * 4 - 1]);
+        const int rt = max(max((int)p[1], (int)p[-FAST_SCW * 4 + 1]), (int)p[FAST_SCW * 4 + 1]);
+        int nb = max(up, dn);
+        if (xin > 0) nb = max(nb, lf);
+        if (xin < L.wCell - 1) nb = max(nb, rt);
+        if (sv > nb) {
+            pix[i] = (unsigned short)(e | 0x8000u);
+            atomicAdd(&cellCnt[cg][sv >= iniShift], 1);
+        }
+    }
+    __syncthreads();
+    /* the cell is retried with minThFAST only if it found nothing at iniThFAST (:812): per cell the kept local
+     * maxima are those >= iniThFAST if there is one, else all of them.  One global atomic reserves the CTA's
+     * range of the (frame, level) candidate pool. */
+    if (tid == 0) {
+        int total = 0;
+        for (int c = 0; c < FAST_GROUP; c++) total += cellCnt[c][1] ? cellCnt[c][1] : cellCnt[c][0];
+        int b = 0;
+        if (total) {
+            b = atomicAdd(candCount + frame * g.nlevels + l, total);
+            if (b + total > L.candCap) atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
+        }
+        gbase = total ? b : -1;
+    }
+    __syncthreads();
+    const int b0 = gbase;
+    if (b0 < 0) return;
+    uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
+    for (int i0 = 0; i0 < np; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        bool keep = false;
+        uint32_t rec = 0;
+        if (i < np) {
+            const unsigned e = pix[i];
+            if (e & 0x8000u) {
+                const int x = e & 0xff, y = (e >> 8) & 0x3f;
+                const int cg = (x >= L.wCell) + (x >= 2 * L.wCell) + (x >= 3 * L.wCell);
+                const int sv = scb[((y + 1) * FAST_SCW + 1) * 4 + x];
+                keep = sv >= (cellCnt[cg][1] ? iniShift : 1);
+                /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
+                rec = (uint32_t)(x + 3 + cj0 * L.wCell) | ((uint32_t)(y + 3 + ci * L.hCell) << 12) |
+                      ((uint32_t)(sv + g.minTh - 1) << 24);
             }
         }
-        lmq[i] = (unsigned char)bits;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        int basePos = 0;
+        if (lane == 0 && m) basePos = atomicAdd(&nout, __popc(m));
+        basePos = __shfl_sync(0xffffffffu, basePos, 0);
+        const int pos = b0 + basePos + __popc(m & ((1u << lane) - 1));
+        if (keep && pos < L.candCap) out[pos] = rec;
     }
-    __syncthreads();
-    /* emission: candidates are first appended to a CTA-local list (reusing the work array as 32-bit slots is
-     * not possible -- it is still read -- so they go to the dead tile), then one global atomic reserves the
-     * CTA's range of the (frame, level) pool and the list is copied out */
-    unsigned* local = tile;                          /* the tile is dead after phase 2 */
-    if (tid == 0) nwork = 0;                         /* reuse as the CTA-local candidate counter */
-    __syncthreads();
-    for (int i = tid; i < nw; i += blockDim.x) {
-        const unsigned bits4 = lmq[i];
-        if (!bits4) continue;
-        const int t = work[i];
-        const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
-        const unsigned word = sc[(y + 1) * FAST_SCW + q + 1];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (!(bits4 >> j & 1u)) continue;
-            const int sv = (word >> (8 * j)) & 0xff;
-            const int x = q * 4 + j;
-            /* the cell is retried with minThFAST only if it found nothing at iniThFAST (:812) */
-            if (sv < (cellIni[(x >= L.wCell) + (x >= 2 * L.wCell) + (x >= 3 * L.wCell)] ? iniShift : 1)) continue;
-            /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
-            const uint32_t X = x + 3 + cj0 * L.wCell, Y = y + 3 + ci * L.hCell;
-            local[atomicAdd(&nwork, 1)] = X | (Y << 12) | ((uint32_t)(sv + g.minTh - 1) << 24);
-        }
-    }
-    __syncthreads();
-    const int nloc = nwork;
-    if (nloc == 0) return;
-    __shared__ int gbase;
-    if (tid == 0) gbase = atomicAdd(candCount + frame * g.nlevels + l, nloc);
-    __syncthreads();
-    uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
-    const int b0 = gbase;
-    if (b0 + nloc > L.candCap && tid == 0) atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
-    for (int i = tid; i < nloc; i += blockDim.x)
-        if (b0 + i < L.candCap) out[b0 + i] = local[i];
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -1069,10 +1139,56 @@ int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_
     return launches;
 }
 
-int viorb_launch_fast(const FrameGeom& g, const int4* d_groups, int ngroups, int F, const ExtractBuffers& b, cudaStream_t s) {
-    dim3 grid(ngroups, F);
-    fast_cells_kernel<<<grid, 128, 0, s>>>(g, d_groups, b.pyr, b.cand, b.candCount, b.status);
-    return 1;
+int viorb_launch_fast(const FrameGeom& g, const TmaMaps& maps, const int4* d_groups, const int* classStart, int F,
+                      const ExtractBuffers& b, cudaStream_t s) {
+    int launches = 0;
+    for (int sh = 0; sh < 4; sh++) {
+        const int n = classStart[sh + 1] - classStart[sh];
+        if (n <= 0) continue;
+        dim3 grid(n, F);
+        const int4* grp = d_groups + classStart[sh];
+        switch (sh) {
+            case 0: fast_cells_kernel<0><<<grid, 128, 0, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
+            case 1: fast_cells_kernel<1><<<grid, 128, 0, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
+            case 2: fast_cells_kernel<2><<<grid, 128, 0, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
+            default: fast_cells_kernel<3><<<grid, 128, 0, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
+        }
+        launches++;
+    }
+    return launches;
+}
+
+/* CUtensorMap of every stored pyramid level {step bytes, h+38 rows, F frames}, box = the FAST tile of the level.
+ * cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime so that the library does
+ * not link libcuda (the build box has no driver). */
+int viorb_encode_tma_maps(const FrameGeom& g, uint8_t* d_pyr, int F, TmaMaps* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+        encode = (EncodeFn)fn;
+    }
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    for (int l = 0; l < g.nlevels; l++) {
+        const LevelGeom& L = g.lv[l];
+        const cuuint64_t dims[3] = {(cuuint64_t)L.step, (cuuint64_t)(L.h + 2 * VIORB_EDGE), (cuuint64_t)F};
+        const cuuint64_t strides[2] = {(cuuint64_t)L.step, (cuuint64_t)g.pyrFrameBytes};
+        int boxH = L.hCell + 6 < FAST_ROWS ? L.hCell + 6 : FAST_ROWS;
+        if (boxH < 1) boxH = 1;
+        const cuuint32_t box[3] = {VIORB_FAST_TILE_BYTES, (cuuint32_t)boxH, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUtensorMap m;
+        const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + L.pyrOff, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return -2;
+        memcpy(out->fast[l], &m, 128);
+    }
+    return 0;
 }
 
 size_t viorb_octree_smem_bytes(int NC) {

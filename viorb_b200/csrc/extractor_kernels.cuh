@@ -79,10 +79,24 @@ struct ExtractBuffers {
     int* status;          /* device status word (bit mask above) */
 };
 
+/* TMA descriptors (CUtensorMap, 128 bytes each) of the stored pyramid levels of one lane: a level is the 3-D
+ * tensor {step bytes, h+38 rows, F frames}; fast_cells_kernel fetches its cell strip with one
+ * cp.async.bulk.tensor per CTA (box = VIORB_FAST_TILE_BYTES x (hCell+6) x 1, out-of-range bytes read as 0). */
+struct TmaMaps {
+    alignas(64) unsigned char fast[VIORB_MAX_LEVELS][128];
+};
+#define VIORB_FAST_TILE_BYTES 208   /* box width: <= 15 alignment bytes + 3 rim + 180 window + 3 rim, padded to 16 bytes */
+#define VIORB_FAST_TILE_ROWS 68     /* box height bound: hCell + 6 */
+/* encodes the maps for a pyramid buffer holding F frames (host, driver entry point cuTensorMapEncodeTiled) */
+int viorb_encode_tma_maps(const FrameGeom& g, uint8_t* d_pyr, int F, TmaMaps* out);
+
 /* launchers (extractor_kernels.cu); every launcher returns the number of kernel launches issued */
 int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_t* d_images, size_t step,
                          size_t frameStride, int F, const ExtractBuffers& b, cudaStream_t s);
-int viorb_launch_fast(const FrameGeom& g, const int4* d_groups, int ngroups, int F, const ExtractBuffers& b, cudaStream_t s);
+/* d_groups is sorted by the byte shift SH = (stored byte of the group's window x=0) & 3; class sh owns
+ * [classStart[sh], classStart[sh+1]) and is one launch of the kernel instantiated for that shift */
+int viorb_launch_fast(const FrameGeom& g, const TmaMaps& maps, const int4* d_groups, const int* classStart, int F,
+                      const ExtractBuffers& b, cudaStream_t s);
 #define VIORB_FAST_GROUP 4      /* horizontally adjacent FAST cells per CTA (extractor_kernels.cu FAST_GROUP) */
 int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s);
 int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps,
