@@ -29,23 +29,51 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 /* ------------------------------------------------------------------------------------------------
  * ComputePyramid level 0: copyMakeBorder(image, temp, 19.., BORDER_REFLECT_101)   (:1127-1128)
- * one thread = one 16-byte vector of a stored row; interior vectors are straight 128-bit copies
+ * One CTA = 16 stored rows of one frame.  Interior 16-byte vectors of a stored row are straight 128-bit
+ * copies (any source alignment: five 32-bit loads and a byte funnel when the source is not 16-byte aligned);
+ * the few vectors per row that hold reflected border pixels or alignment padding are gathered byte by byte
+ * in a second, densely packed loop so that the slow path does not diverge the copy warps.
  * ---------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(128) pyr_level0_kernel(const __grid_constant__ FrameGeom g,
+#define L0_ROWS 16
+
+__device__ __forceinline__ uint4 load16_any(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const int sh = (int)(a & 3);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a - sh);
+    const uint32_t v0 = __ldg(w), v1 = __ldg(w + 1), v2 = __ldg(w + 2), v3 = __ldg(w + 3);
+    const uint32_t v4 = sh ? __ldg(w + 4) : 0u;        /* same 4-byte word as byte 15: never past the needed data */
+    const unsigned sel = 0x3210u + 0x1111u * (unsigned)sh;
+    return make_uint4(__byte_perm(v0, v1, sel), __byte_perm(v1, v2, sel), __byte_perm(v2, v3, sel), __byte_perm(v3, v4, sel));
+}
+
+__global__ void __launch_bounds__(256) pyr_level0_kernel(const __grid_constant__ FrameGeom g,
                                                          const uint8_t* __restrict__ images, size_t inStep,
                                                          size_t frameStride, uint8_t* __restrict__ pyr, int aligned) {
     const LevelGeom& L = g.lv[0];
-    const int vi = blockIdx.x * blockDim.x + threadIdx.x;      /* 16-byte vector index inside the stored row */
-    const int row = blockIdx.y;                                 /* stored row 0 .. h+38 */
-    const int frame = blockIdx.z;
-    if (vi * 16 >= L.step) return;
-    const int sy = reflect101(row - VIORB_EDGE, L.h);
-    const uint8_t* src = images + (size_t)frame * frameStride + (size_t)sy * inStep;
-    const int x0 = vi * 16 - VIORB_ROI_X0;
-    uint4 out;
-    if (aligned && x0 >= 0 && x0 + 16 <= L.w) {
-        out = __ldg(reinterpret_cast<const uint4*>(src + x0));
-    } else {
+    const int frame = blockIdx.y;
+    const int row0 = blockIdx.x * L0_ROWS;                      /* first stored row of this CTA */
+    const int nrows = min(L0_ROWS, L.h + 2 * VIORB_EDGE - row0);
+    const int V = L.step >> 4;                                   /* 16-byte vectors per stored row */
+    /* interior vectors: x0 = 16*vi - 32 >= 0 and x0 + 16 <= w */
+    const int viLo = VIORB_ROI_X0 / 16, viHi = (L.w + VIORB_ROI_X0) / 16 - 1;
+    const int nInt = max(viHi - viLo + 1, 0), nBor = V - nInt;
+    const uint8_t* img = images + (size_t)frame * frameStride;
+    uint8_t* dst0 = pyr + (size_t)frame * g.pyrFrameBytes + L.pyrOff;
+    if (nInt > 0) {
+        const unsigned inv = 0xffffffffu / (unsigned)nInt + 1u;     /* i / nInt == umulhi(i, inv) for i < 2^16 */
+        for (int i = threadIdx.x; i < nrows * nInt; i += blockDim.x) {
+            const int r = (int)__umulhi((unsigned)i, inv), vi = viLo + i - r * nInt;
+            const uint8_t* src = img + (size_t)reflect101(row0 + r - VIORB_EDGE, L.h) * inStep + (vi * 16 - VIORB_ROI_X0);
+            const uint4 v = aligned ? __ldg(reinterpret_cast<const uint4*>(src)) : load16_any(src);
+            reinterpret_cast<uint4*>(dst0 + (size_t)(row0 + r) * L.step)[vi] = v;
+        }
+    }
+    const unsigned invB = 0xffffffffu / (unsigned)max(nBor, 1) + 1u;
+    for (int i = threadIdx.x; i < nrows * nBor; i += blockDim.x) {
+        const int r = (int)__umulhi((unsigned)i, invB), k = i - r * nBor;
+        const int vi = (nInt > 0 && k >= viLo) ? k + nInt : k;
+        const uint8_t* src = img + (size_t)reflect101(row0 + r - VIORB_EDGE, L.h) * inStep;
+        const int x0 = vi * 16 - VIORB_ROI_X0;
         uint32_t wds[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -59,10 +87,8 @@ __global__ void __launch_bounds__(128) pyr_level0_kernel(const __grid_constant__
             }
             wds[q] = word;
         }
-        out = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        reinterpret_cast<uint4*>(dst0 + (size_t)(row0 + r) * L.step)[vi] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
     }
-    uint8_t* dst = pyr + (size_t)frame * g.pyrFrameBytes + L.pyrOff + (size_t)row * L.step;
-    reinterpret_cast<uint4*>(dst)[vi] = out;
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -71,14 +97,19 @@ __global__ void __launch_bounds__(128) pyr_level0_kernel(const __grid_constant__
  * cv::resize 8-bit fixed point: T = S[sx]*a0 + S[sx+1]*a1 ; D = (((b0*(T0>>4))>>16) + ((b1*(T1>>4))>>16) + 2) >> 2
  * The border pixels are produced by evaluating the same expression at the reflected ROI coordinate.
  *
- * One CTA = a 128 x 32 tile of the stored (padded) level: the source rectangle it needs (about 1.2x
- * larger) is staged in shared memory with 16-byte loads; each thread owns four adjacent output columns
- * (their x coefficients live in registers) and walks eight rows, writing one 32-bit word per row.
+ * One CTA = a 128 x 64 tile of the stored (padded) level: the source rectangle it needs (about 1.2x larger)
+ * is staged in shared memory with 16-byte loads.  A thread owns four adjacent output columns and walks 16
+ * rows.  Horizontal pass of a source row: the <= 8 source bytes the four columns touch are fetched as three
+ * aligned words and normalised with two PRMTs; each column's pair (S[sx], S[sx+1]) is one PRMT and its T one
+ * IDP.2A with the packed (a0, a1).  Consecutive output rows share a source row, so the lower row's T values
+ * stay in registers and become the upper row of the next output row.  Vertical pass: (b * T) >> 16 is one
+ * IMAD.HI with b pre-shifted by 16.
  * ---------------------------------------------------------------------------------------------- */
 #define RZ_TW 128               /* tile width in stored bytes */
-#define RZ_TH 32                /* tile height in stored rows */
+#define RZ_TH 64                /* tile height in stored rows */
+#define RZ_WROWS 16             /* rows per warp */
 #define RZ_SSTRIDE 224          /* staged source row stride (bytes): 128*1.5 + 1 + 15, rounded up to 16 */
-#define RZ_SROWS 52             /* staged source rows: 32*1.5 + 2, padded (scaleFactor <= 1.5) */
+#define RZ_SROWS 100            /* staged source rows: 64*1.5 + 2, padded (scaleFactor <= 1.5) */
 
 __device__ __forceinline__ void reflected_range(int a, int b, int n, int& dmin, int& dmax) {
     /* min / max of reflect101(i, n) over i in [a, b], with -19 <= a <= b <= n+18 */
@@ -90,20 +121,22 @@ __device__ __forceinline__ void reflected_range(int a, int b, int n, int& dmin, 
 __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__ FrameGeom g, int level,
                                                          ResizeTables t, uint8_t* __restrict__ pyr) {
     __shared__ __align__(16) uint8_t src[RZ_SROWS * RZ_SSTRIDE];
+    __shared__ uint4 rowInfo[RZ_TH];          /* {staged byte offset of row sy | of row sy+1 << 16, b0 << 16, b1 << 16, -} */
     const LevelGeom& L = g.lv[level];
     const LevelGeom& P = g.lv[level - 1];
     const int frame = blockIdx.z;
     const int tid = threadIdx.x;
     uint8_t* base = pyr + (size_t)frame * g.pyrFrameBytes;
-    /* tile in ROI coordinates of level l: columns [xa, xa+128), rows [ya, ya+32) */
+    /* tile in ROI coordinates of level l: columns [xa, xa+128), rows [ya, ya+64) */
     const int xa = blockIdx.x * RZ_TW - VIORB_ROI_X0, ya = blockIdx.y * RZ_TH - VIORB_EDGE;
     const int xlo = max(xa, -VIORB_EDGE), xhi = min(xa + RZ_TW - 1, L.w + VIORB_EDGE - 1);
     const int ylo = ya, yhi = min(ya + RZ_TH - 1, L.h + VIORB_EDGE - 1);
     const int stepWords = L.step >> 2;
     const int wi = blockIdx.x * (RZ_TW / 4) + (tid & 31);          /* stored word of this thread */
+    const int r0 = (tid >> 5) * RZ_WROWS;
     if (xlo > xhi) {                                                  /* only alignment padding: write zeros */
         if (wi < stepWords)
-            for (int r = (tid >> 5) * 8; r < (tid >> 5) * 8 + 8; r++)
+            for (int r = r0; r < r0 + RZ_WROWS; r++)
                 if (ya + r <= yhi) reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(ya + r + VIORB_EDGE) * L.step)[wi] = 0;
         return;
     }
@@ -115,63 +148,80 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
     const int sx1 = min((int)t.xofs[L.xtab + dxmax] + 1, P.w - 1);
     const int sy0 = min((int)t.yofs[L.ytab + dymin], P.h - 1);
     const int sy1 = min((int)t.yofs[L.ytab + dymax] + 1, P.h - 1);
-    const int nvec = ((sx1 - sx0) >> 4) + 1;                         /* 16-byte vectors per staged row */
+    const int nvec = ((sx1 - sx0) >> 4) + 1;                         /* 16-byte vectors per staged row (<= 14) */
     const int nrow = sy1 - sy0 + 1;
     {
         const uint8_t* sroi = base + P.pyrOff + (size_t)VIORB_EDGE * P.step + VIORB_ROI_X0;   /* 16-byte aligned */
-        for (int i = tid; i < nrow * nvec; i += 128) {
-            const int r = i / nvec, v = i - r * nvec;
-            const uint4 val = *reinterpret_cast<const uint4*>(sroi + (size_t)(sy0 + r) * P.step + sx0 + 16 * v);
-            *reinterpret_cast<uint4*>(&src[r * RZ_SSTRIDE + 16 * v]) = val;
-        }
+        const int v = tid & 15;
+        if (v < nvec)
+            for (int r = tid >> 4; r < nrow; r += 8)
+                *reinterpret_cast<uint4*>(&src[r * RZ_SSTRIDE + 16 * v]) =
+                    *reinterpret_cast<const uint4*>(sroi + (size_t)(sy0 + r) * P.step + sx0 + 16 * v);
     }
-    /* this thread's four output columns */
-    int so[4], so1[4], a0[4], a1[4];
-    bool ok[4];
+    if (tid < RZ_TH && ya + tid <= yhi) {
+        const int dy = reflect101(ya + tid, L.h);
+        const int sy = t.yofs[L.ytab + dy];
+        const unsigned b0 = (unsigned)t.yb[2 * (L.ytab + dy)], b1 = (unsigned)t.yb[2 * (L.ytab + dy) + 1];
+        const unsigned o0 = (unsigned)((min(sy, P.h - 1) - sy0) * RZ_SSTRIDE), o1 = (unsigned)((min(sy + 1, P.h - 1) - sy0) * RZ_SSTRIDE);
+        rowInfo[tid] = make_uint4(o0 | (o1 << 16), b0 << 16, b1 << 16, 0u);
+    }
+    /* this thread's four output columns: staged offsets relative to the lowest one (<= 6 at scale <= 1.5) */
+    int rel[4];
+    unsigned coef[4], okMask = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int x = xa + (tid & 31) * 4 + j;
-        ok[j] = x >= -VIORB_EDGE && x < L.w + VIORB_EDGE;
-        const int dx = ok[j] ? reflect101(x, L.w) : dxmin;
-        const int sx = t.xofs[L.xtab + dx];
-        so[j] = sx - sx0;
-        so1[j] = min(sx + 1, P.w - 1) - sx0;
-        a0[j] = t.xa[2 * (L.xtab + dx)];
-        a1[j] = t.xa[2 * (L.xtab + dx) + 1];
+        const bool ok = x >= -VIORB_EDGE && x < L.w + VIORB_EDGE;
+        /* columns in the alignment padding borrow the nearest stored column so the 8-byte window stays valid */
+        const int dx = reflect101(min(max(x, -VIORB_EDGE), L.w + VIORB_EDGE - 1), L.w);
+        rel[j] = (int)t.xofs[L.xtab + dx] - sx0;
+        coef[j] = (unsigned)(unsigned short)t.xa[2 * (L.xtab + dx)] | ((unsigned)(unsigned short)t.xa[2 * (L.xtab + dx) + 1] << 16);
+        okMask |= ok ? 0xffu << (8 * j) : 0u;
+    }
+    const int lo = min(min(rel[0], rel[1]), min(rel[2], rel[3]));
+    const int wb = lo >> 2;                                        /* first staged word of the 8-byte window */
+    const unsigned selN = 0x3210u + 0x1111u * (unsigned)(lo & 3);  /* normalise: window byte 0 = staged byte lo */
+    unsigned selP[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const unsigned d = (unsigned)(rel[j] - lo);
+        selP[j] = d | ((d + 1) << 4);
     }
     __syncthreads();
     if (wi >= stepWords) return;
-    /* consecutive output rows mostly share a source row (sy advances by 1 or 2 per output row at scale 1.2):
-     * the horizontal pass of the lower source row is kept in registers and reused as the upper row of the next */
-    int prevS1 = -1;
-    int Tp[4] = {0, 0, 0, 0};
-    for (int r = (tid >> 5) * 8; r < (tid >> 5) * 8 + 8; r++) {
-        const int y = ya + r;
-        if (y > yhi) break;
-        const int dy = reflect101(y, L.h);
-        const int sy = t.yofs[L.ytab + dy];
-        const int b0 = t.yb[2 * (L.ytab + dy)], b1 = t.yb[2 * (L.ytab + dy) + 1];
-        const int s0 = min(sy, P.h - 1) - sy0, s1 = min(sy + 1, P.h - 1) - sy0;
-        const uint8_t* S0 = &src[s0 * RZ_SSTRIDE];
-        const uint8_t* S1 = &src[s1 * RZ_SSTRIDE];
-        int T0[4], T1[4];
-        if (s0 == prevS1) {
+    const unsigned* srcw = reinterpret_cast<const unsigned*>(src) + wb;
+    unsigned prevO1 = 0xffffffffu;
+    unsigned Tp[4] = {0, 0, 0, 0};
+    uint32_t* out = reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(ya + r0 + VIORB_EDGE) * L.step) + wi;
+    for (int r = r0; r < r0 + RZ_WROWS; r++, out += stepWords) {
+        if (ya + r > yhi) break;
+        const uint4 ri = rowInfo[r];
+        const unsigned o0 = ri.x & 0xffffu, o1 = ri.x >> 16;
+        unsigned T0[4], T1[4];
+        if (o0 == prevO1) {
 #pragma unroll
             for (int j = 0; j < 4; j++) T0[j] = Tp[j];
         } else {
+            const unsigned* w = srcw + (o0 >> 2);
+            const unsigned W0 = __byte_perm(w[0], w[1], selN), W1 = __byte_perm(w[1], w[2], selN);
 #pragma unroll
-            for (int j = 0; j < 4; j++) T0[j] = (S0[so[j]] * a0[j] + S0[so1[j]] * a1[j]) >> 4;
+            for (int j = 0; j < 4; j++) T0[j] = __dp2a_lo(coef[j], __byte_perm(W0, W1, selP[j]), 0u) >> 4;
+        }
+        {
+            const unsigned* w = srcw + (o1 >> 2);
+            const unsigned W0 = __byte_perm(w[0], w[1], selN), W1 = __byte_perm(w[1], w[2], selN);
+#pragma unroll
+            for (int j = 0; j < 4; j++) T1[j] = __dp2a_lo(coef[j], __byte_perm(W0, W1, selP[j]), 0u) >> 4;
         }
         uint32_t word = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            T1[j] = (S1[so[j]] * a0[j] + S1[so1[j]] * a1[j]) >> 4;
-            const uint32_t v = (uint32_t)((((b0 * T0[j]) >> 16) + ((b1 * T1[j]) >> 16) + 2) >> 2) & 0xffu;
-            word |= (ok[j] ? v : 0u) << (8 * j);
+            const uint32_t v = (__umulhi(ri.y, T0[j]) + __umulhi(ri.z, T1[j]) + 2u) >> 2;     /* <= 255 */
+            word |= v << (8 * j);
             Tp[j] = T1[j];
         }
-        prevS1 = s1;
-        reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(y + VIORB_EDGE) * L.step)[wi] = word;
+        prevO1 = o1;
+        *out = word & okMask;
     }
 }
 
@@ -1127,9 +1177,9 @@ int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_
     for (int l = 0; l < g.nlevels; l++) {
         const LevelGeom& L = g.lv[l];
         if (l == 0) {
-            dim3 grid((L.step / 16 + 127) / 128, L.h + 2 * VIORB_EDGE, F);
+            dim3 grid((L.h + 2 * VIORB_EDGE + L0_ROWS - 1) / L0_ROWS, F);
             const int aligned = ((uintptr_t)d_images % 16 == 0) && (step % 16 == 0) && (frameStride % 16 == 0);
-            pyr_level0_kernel<<<grid, 128, 0, s>>>(g, d_images, step, frameStride, b.pyr, aligned);
+            pyr_level0_kernel<<<grid, 256, 0, s>>>(g, d_images, step, frameStride, b.pyr, aligned);
         } else {
             dim3 grid((L.step + RZ_TW - 1) / RZ_TW, (L.h + 2 * VIORB_EDGE + RZ_TH - 1) / RZ_TH, F);
             pyr_resize_kernel<<<grid, 128, 0, s>>>(g, l, t, b.pyr);
