@@ -232,6 +232,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     }
     /* FAST cell groups: the cells the reference visits (:789-806), VIORB_FAST_GROUP neighbours per CTA */
     std::vector<int4> groups;
+    int fastRows = 8, fastWork = 64;
     for (int l = 0; l < e->nlevels; l++) {
         const LevelGeom& L = g.lv[l];
         const int maxBorderX = L.w - VIORB_FAST_BORDER, maxBorderY = L.h - VIORB_FAST_BORDER;
@@ -242,9 +243,22 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
             /* cells per CTA: as many as fit the kernel's tile (45 quads wide) and work lists (2048 quads) */
             int G = VIORB_FAST_GROUP;
             while (G > 1 && (G * L.wCell > 180 || ((G * L.wCell + 3) / 4) * std::min(L.hCell, 59) > 2048)) G--;
-            for (int j = 0; j < nvalid; j += G) groups.push_back(make_int4(l, i, j, std::min(G, nvalid - j)));
+            for (int j = 0; j < nvalid; j += G) {
+                const int n = std::min(G, nvalid - j);
+                groups.push_back(make_int4(l, i, j, n));
+                /* the group's detection window (fast_cells_kernel): ww x wh pixels, NQ quads per row */
+                const int iniX = VIORB_FAST_BORDER + j * L.wCell, iniY = VIORB_FAST_BORDER + i * L.hCell;
+                const int ww = std::min(iniX + n * L.wCell + 6, maxBorderX) - iniX - 6;
+                const int wh = std::min(iniY + L.hCell + 6, maxBorderY) - iniY - 6;
+                if (ww > 0 && wh > 0) fastWork = std::max(fastWork, ((ww + 3) / 4) * wh);
+            }
         }
+        fastRows = std::max(fastRows, std::min(L.hCell + 6, VIORB_FAST_TILE_ROWS));
     }
+    g.fastTileRows = fastRows;
+    g.fastMaxWork = (fastWork + 63) & ~63;
+    g.fastPixBytes = (std::max(fastRows * VIORB_FAST_TILE_BYTES + g.fastMaxWork * 2, g.fastMaxWork * 8) + 127) & ~127;
+    if (viorb_fast_prepare(g) != 0) return fail(VIORB_ERR_CUDA, "FAST kernel attribute: %s", cudaGetErrorString(cudaGetLastError()));
     e->ngroups = (int)groups.size();
     {   /* sort by the byte shift of the group's window inside a 4-byte word of the stored row (fast_cells_kernel<SH>) */
         auto shiftOf = [&](const int4& gr) { return (VIORB_ROI_X0 + VIORB_FAST_BORDER + gr.z * g.lv[gr.x].wCell + 3) & 3; };

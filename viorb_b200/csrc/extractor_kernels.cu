@@ -244,8 +244,6 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
 #define FAST_MAXQ 45            /* quads per window row: 4 cells x wCell (<= 45 when nCols >= 2; one cell of <= 59 otherwise) */
 #define FAST_TW (VIORB_FAST_TILE_BYTES / 4)   /* tile row stride in words = the TMA box width: 1 lead word + 45 quads + 1 tail word */
 #define FAST_SCW 49             /* score row stride in words (odd): 1 zero word + 45 quads + 1 zero word, padded */
-#define FAST_MAXWORK 2048        /* quads per CTA: the host sizes the cell groups so that NQ * wh <= 2048 */
-#define FAST_MAXPIX 4096        /* corner pixels (score > 0) per CTA before non-max suppression */
 
 __device__ __forceinline__ unsigned funnel_bytes(unsigned lo, unsigned hi, int sh) {
     /* bytes sh..sh+3 of the 8-byte little-endian sequence lo|hi (sh in 0..3) */
@@ -337,20 +335,23 @@ __device__ __forceinline__ unsigned fast_score_s16x2(const unsigned (&r)[16], un
 }
 
 template <int SH>
-__global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__ FrameGeom g,
+__global__ void __launch_bounds__(128, 8) fast_cells_kernel(const __grid_constant__ FrameGeom g,
                                                          const __grid_constant__ TmaMaps maps,
                                                          const int4* __restrict__ groups,
                                                          uint32_t* __restrict__ cand, int* __restrict__ candCount,
                                                          int* __restrict__ status) {
     /* tile and work0 are contiguous: once both are dead (after phase 2) the region holds the corner-pixel list */
-    __shared__ __align__(128) unsigned char raw[FAST_ROWS * FAST_TW * 4 + FAST_MAXWORK * 2];
-    __shared__ unsigned sc[(FAST_ROWS - 4) * FAST_SCW];
-    __shared__ unsigned short work[FAST_MAXWORK];     /* quads that survive the high-speed test */
+    /* dynamic shared memory, sized by the host for this geometry (FrameGeom::fast*):
+     *   [ tile: fastTileRows x 208 B | work0: fastMaxWork u16 | pad ]  = fastPixBytes  (later: the corner-pixel list)
+     *   [ sc: (fastTileRows - 4) x 196 B ] [ work: fastMaxWork u16 ] */
+    extern __shared__ __align__(128) unsigned char raw[];
+    unsigned* sc = reinterpret_cast<unsigned*>(raw + g.fastPixBytes);
+    unsigned short* work = reinterpret_cast<unsigned short*>(raw + g.fastPixBytes + (g.fastTileRows - 4) * FAST_SCW * 4);   /* quads that survive the high-speed test */
     __shared__ __align__(8) unsigned long long bar;   /* mbarrier of the TMA tile load */
     __shared__ int nwork, nwork0, npix, nout, gbase;
     __shared__ int cellCnt[FAST_GROUP][2];            /* per cell: local maxima below / at-or-above iniThFAST */
     unsigned* tile = reinterpret_cast<unsigned*>(raw);
-    unsigned short* work0 = reinterpret_cast<unsigned short*>(raw + FAST_ROWS * FAST_TW * 4);   /* non-flat quads */
+    unsigned short* work0 = reinterpret_cast<unsigned short*>(raw + g.fastTileRows * FAST_TW * 4);   /* non-flat quads */
     unsigned short* pix = reinterpret_cast<unsigned short*>(raw);   /* corner pixels: x | y << 8 | localmax << 15 */
     const int frame = blockIdx.y;
     /* a CTA owns up to FAST_GROUP horizontally adjacent cells of one cell row: {level, cell row, first cell, n} */
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     const int boxX = (gstart - 3) & ~15;
     const int w0 = (gstart - boxX) >> 2;
     if (tid == 0) {
-        const int boxH = min(L.hCell + 6, FAST_ROWS);
+        const int boxH = min(L.hCell + 6, g.fastTileRows);
         mbar_init(&bar, 1);
         mbar_expect_tx(&bar, (unsigned)(VIORB_FAST_TILE_BYTES * boxH));
         tma_load_3d(tile, &maps.fast[l], boxX, VIORB_EDGE + iniY, frame, &bar);
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     __syncthreads();
 
     /* corner pixels (score > 0) as a dense list -- the tile and work0 are dead, the list takes their place
-     * (capacity 8576 >= 4 * FAST_MAXWORK entries) */
+     * (the host sizes the region for 4 * fastMaxWork entries) */
     for (int i0 = 0; i0 < nw; i0 += blockDim.x) {
         const int i = i0 + tid;
         unsigned word = 0;
@@ -1189,19 +1190,33 @@ int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_
     return launches;
 }
 
+size_t viorb_fast_smem_bytes(const FrameGeom& g) {
+    return (size_t)g.fastPixBytes + (size_t)(g.fastTileRows - 4) * FAST_SCW * 4 + (size_t)g.fastMaxWork * 2;
+}
+
+int viorb_fast_prepare(const FrameGeom& g) {
+    const int smem = (int)viorb_fast_smem_bytes(g);
+    cudaError_t e = cudaFuncSetAttribute(fast_cells_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fast_cells_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fast_cells_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fast_cells_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return (int)e;
+}
+
 int viorb_launch_fast(const FrameGeom& g, const TmaMaps& maps, const int4* d_groups, const int* classStart, int F,
                       const ExtractBuffers& b, cudaStream_t s) {
     int launches = 0;
+    const size_t smem = viorb_fast_smem_bytes(g);
     for (int sh = 0; sh < 4; sh++) {
         const int n = classStart[sh + 1] - classStart[sh];
         if (n <= 0) continue;
         dim3 grid(n, F);
         const int4* grp = d_groups + classStart[sh];
         switch (sh) {
-            case 0: fast_cells_kernel<0><<<grid, 128, 0, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
-            case 1: fast_cells_kernel<1><<<grid, 128, 0, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
-            case 2: fast_cells_kernel<2><<<grid, 128, 0, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
-            default: fast_cells_kernel<3><<<grid, 128, 0, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
+            case 0: fast_cells_kernel<0><<<grid, 128, smem, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
+            case 1: fast_cells_kernel<1><<<grid, 128, smem, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
+            case 2: fast_cells_kernel<2><<<grid, 128, smem, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
+            default: fast_cells_kernel<3><<<grid, 128, smem, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
         }
         launches++;
     }
@@ -1227,7 +1242,7 @@ int viorb_encode_tma_maps(const FrameGeom& g, uint8_t* d_pyr, int F, TmaMaps* ou
         const LevelGeom& L = g.lv[l];
         const cuuint64_t dims[3] = {(cuuint64_t)L.step, (cuuint64_t)(L.h + 2 * VIORB_EDGE), (cuuint64_t)F};
         const cuuint64_t strides[2] = {(cuuint64_t)L.step, (cuuint64_t)g.pyrFrameBytes};
-        int boxH = L.hCell + 6 < FAST_ROWS ? L.hCell + 6 : FAST_ROWS;
+        int boxH = L.hCell + 6 < g.fastTileRows ? L.hCell + 6 : g.fastTileRows;
         if (boxH < 1) boxH = 1;
         const cuuint32_t box[3] = {VIORB_FAST_TILE_BYTES, (cuuint32_t)boxH, 1};
         const cuuint32_t estr[3] = {1, 1, 1};

@@ -50,6 +50,9 @@ struct FrameGeom {
     int iniTh, minTh;
     int dbg;              /* VIORB_DEBUG experiment mask (0 in production) */
     int cellsPerFrame, candPerFrame, selPerFrame;
+    /* fast_cells_kernel shared-memory layout for this geometry: tile rows (max hCell + 6), quads per CTA (max NQ * wh),
+     * bytes of the tile + work0 region, which later holds the corner-pixel list (>= 8 * fastMaxWork) */
+    int fastTileRows, fastMaxWork, fastPixBytes;
     unsigned long long pyrFrameBytes;
     LevelGeom lv[VIORB_MAX_LEVELS];
 };
@@ -97,6 +100,8 @@ int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_
  * [classStart[sh], classStart[sh+1]) and is one launch of the kernel instantiated for that shift */
 int viorb_launch_fast(const FrameGeom& g, const TmaMaps& maps, const int4* d_groups, const int* classStart, int F,
                       const ExtractBuffers& b, cudaStream_t s);
+size_t viorb_fast_smem_bytes(const FrameGeom& g);
+int viorb_fast_prepare(const FrameGeom& g);   /* opt-in dynamic shared memory; returns cudaError */
 #define VIORB_FAST_GROUP 4      /* horizontally adjacent FAST cells per CTA (extractor_kernels.cu FAST_GROUP) */
 int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s);
 int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps,
