@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--queries", type=int, default=1000)
     ap.add_argument("--no-matcher", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-frames", type=int, default=256, help="frames of the CPU-baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=2048, help="frames of the CPU-baseline sample (about 30 CPU-seconds)")
     return ap.parse_args()
 
 
@@ -322,8 +322,20 @@ def main():
     frames_per_pass = frames_timed / max(passes, 1)
     achieved = alg[dom] * frames_per_pass / (dom_ms_per_launch * 1e-3) / 1e9
     step_achieved = BYTES_PER_FRAME_EUROC * value / world / 1e9
+    # dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json,
+    # written by tools/ncu_summary.py; same launch shape: 128 frames per pass)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        names = {"pyramid": ["pyr_level0_kernel", "pyr_resize_kernel"], "fast": ["fast_cells_kernel"],
+                 "octree": ["octree_kernel"], "describe": ["orient_describe_kernel"]}[dom]
+        if all(n in tj for n in names) and int(round(frames_per_pass)) == 128:
+            traffic = float(sum(l["dram_bytes"] for n in names for l in tj[n]["launches"]))
+            traffic_src = "ncu --set full, %s (dram__bytes_read.sum + dram__bytes_write.sum per 128-frame launch)" % tj[names[0]]["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": kernel_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg[dom] * frames_per_pass, "avg_launch_ms": dom_ms_per_launch,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
                 "stage_timing": "separate pass of the same %d steps with per-stage CUDA events, single lane: %.2f ms/step "

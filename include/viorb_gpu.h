@@ -217,6 +217,32 @@ int viorb_search_for_triangulation(viorb_ctx* ctx,
 int viorb_distinctive_descriptors(viorb_ctx* ctx, const uint8_t* obs_desc, const int32_t* obs_ptr, int nmp,
                                   int32_t* best, int32_t* best_median);
 
+/* ---- DBoW2 vocabulary transform ---------------------------------------------------
+ * replaces ORBVocabulary (= DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>) as used by
+ *          Frame::ComputeBoW src/Frame.cc:575-582 and KeyFrame::ComputeBoW src/KeyFrame.cc:350-359:
+ *          mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4)
+ *          Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1138-1204 (vector transform), :1230-1272 (tree descent).
+ * The tree is passed as loadFromTextFile reads it (:1351-1437): node 0 is the root; node i > 0 has parent[i] < i,
+ * a 32-byte descriptor and a weight; children keep node-id order; a node without children is a leaf (isLeaf())
+ * and leaves get word ids 0, 1, ... in node order.  weighting: 0 TF_IDF, 1 TF, 2 IDF, 3 BINARY; scoring: 0 L1_NORM,
+ * 1 L2_NORM, 2 CHI_SQUARE, 3 KL, 4 BHATTACHARYYA, 5 DOT_PRODUCT (BowVector.h:36-53) -- it selects the normalisation
+ * (ScoringObject.h:74-90).                                                                                      */
+typedef struct viorb_vocabulary viorb_vocabulary;
+int viorb_vocabulary_create(viorb_ctx* ctx, int k, int L, int weighting, int scoring, int nnodes, const int32_t* parent,
+                            const uint8_t* node_desc, const double* node_weight, viorb_vocabulary** out);
+int viorb_vocabulary_destroy(viorb_vocabulary* voc);
+int viorb_vocabulary_info(const viorb_vocabulary* voc, int* nnodes, int* nwords);
+/* transform(features, v, fv, levelsup) of n descriptors (host, n x 32 bytes).  Outputs (host, caller allocated):
+ *   BowVector    bow_ids[*nbow] ascending word ids, bow_values[*nbow] (capacity n each);
+ *   FeatureVector in the flattened form viorb_search_for_triangulation takes: fv_node[*nfv] ascending node ids,
+ *                fv_ptr[*nfv + 1] offsets into fv_idx, fv_idx[...] feature indices ascending within a node
+ *                (capacities n, n + 1, n);
+ *   word_of / node_of (may be NULL, n each): the word id and the node at level L - levelsup of every feature.
+ * A feature that reaches a leaf above level L - levelsup reports node 0 (the reference leaves *nid unset there). */
+int viorb_bow_transform(viorb_vocabulary* voc, const uint8_t* desc, int n, int levelsup, int32_t* bow_ids,
+                        double* bow_values, int* nbow, int32_t* fv_node, int32_t* fv_ptr, int32_t* fv_idx, int* nfv,
+                        int32_t* word_of, int32_t* node_of);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,7 +31,7 @@ def lib(path=None):
         return _lib
     if path is None:
         path = os.path.join(_HERE, "_build", "liborb_oracle.so")
-        srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.cpp", "match_oracle.cpp", "orb_oracle.h")]
+        srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.cpp", "match_oracle.cpp", "bow_oracle.cpp", "orb_oracle.h")]
         if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
             subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
     L = C.CDLL(path)
@@ -80,6 +80,10 @@ def lib(path=None):
     L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp,
                                                vp, i32, vp, f32, f32, vp, vp, i32, i32, vp]
     L.orc_distinctive_descriptor.argtypes = [vp, i32, C.POINTER(i32)]
+    L.orc_vocabulary_create.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp]
+    L.orc_vocabulary_create.restype = vp
+    L.orc_vocabulary_destroy.argtypes = [vp]
+    L.orc_bow_transform.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, C.POINTER(i32), vp, vp]
     L.orc_num_threads.argtypes = []
     if path.endswith(os.path.join("_build", "liborb_oracle.so")):
         _lib = L
@@ -337,3 +341,29 @@ def distinctive_descriptors(obs_desc, obs_ptr):
         best[p] = lib().orc_distinctive_descriptor(_p(rows) if len(rows) else None, len(rows), C.byref(m))
         med[p] = m.value
     return best, med
+
+
+class Vocabulary:
+    """DBoW2 TemplatedVocabulary<FORB> restatement (bow_oracle.cpp): transform() only."""
+
+    def __init__(self, k, L, parent, node_desc, node_weight, weighting=0, scoring=0):
+        par, d, w = _c(parent, np.int32), _c(node_desc, np.uint8), _c(node_weight, np.float64)
+        self.h = lib().orc_vocabulary_create(k, L, weighting, scoring, len(par), _p(par), _p(d), _p(w))
+
+    def __del__(self):
+        try:
+            lib().orc_vocabulary_destroy(self.h)
+        except Exception:
+            pass
+
+    def transform(self, desc, levelsup=4):
+        d = _c(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        ids, vals = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+        fvn, fvp, fvi = np.zeros(max(n, 1), np.int32), np.zeros(n + 1, np.int32), np.zeros(max(n, 1), np.int32)
+        wo, no = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+        nf = C.c_int()
+        nb = lib().orc_bow_transform(self.h, _p(d), n, levelsup, _p(ids), _p(vals), _p(fvn), _p(fvp), _p(fvi), C.byref(nf),
+                                     _p(wo), _p(no))
+        nfv = nf.value
+        return ((ids[:nb], vals[:nb]), (fvn[:nfv], fvp[:nfv + 1], fvi[:fvp[nfv] if nfv else 0]), wo[:n], no[:n])

@@ -148,6 +148,14 @@ int orc_search_for_triangulation(const orc_keypoint* k1, const uint8_t* d1, cons
 /* synthetic-input independent helpers */
 /* MapPoint::ComputeDistinctiveDescriptors, MapPoint.cc:249-314 (one point) */
 int orc_distinctive_descriptor(const uint8_t* desc, int N, int* median_out);
+/* DBoW2 vocabulary transform (bow_oracle.cpp) */
+typedef struct orc_vocabulary orc_vocabulary;
+orc_vocabulary* orc_vocabulary_create(int k, int L, int weighting, int scoring, int nnodes, const int32_t* parent,
+                                      const uint8_t* desc, const double* weight);
+void orc_vocabulary_destroy(orc_vocabulary* v);
+int orc_bow_transform(const orc_vocabulary* voc, const uint8_t* desc, int n, int levelsup, int32_t* bow_ids,
+                      double* bow_values, int32_t* fv_node, int32_t* fv_ptr, int32_t* fv_idx, int* nfv,
+                      int32_t* word_of, int32_t* node_of);
 int orc_num_threads(void);
 
 #ifdef __cplusplus

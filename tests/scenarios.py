@@ -83,3 +83,50 @@ def distinctive_batch(seed, nmp=300, max_obs=40, big=(0, 1, 2, 33, 257)):
         rows.append(d)
         ptr.append(ptr[-1] + c)
     return np.concatenate(rows).astype(np.uint8), np.asarray(ptr, np.int32)
+
+
+def vocabulary(seed, k=6, L=4, unbalanced=True):
+    """Synthetic DBoW2 tree in loadFromTextFile form: (parent, desc, weight) per node, node 0 = root.  Children are
+    noisy copies of their parent (so the descent is meaningful) with some exact duplicates among siblings (ties: the
+    first child must win); with `unbalanced` some inner nodes are leaves above depth L; ~5% of the words are stopped
+    (weight 0)."""
+    rng = np.random.default_rng(seed)
+    parent, desc, depth = [0], [np.zeros(32, np.uint8)], [0]
+    frontier = [0]
+    while frontier:
+        nxt = []
+        for p in frontier:
+            if depth[p] >= L or (unbalanced and depth[p] >= 1 and rng.random() < 0.15):
+                continue
+            nch = k if not unbalanced else int(rng.integers(2, k + 1))
+            base = desc[p] if p else rng.integers(0, 256, 32).astype(np.uint8)
+            for c in range(nch):
+                d = base ^ (rng.integers(0, 256, 32).astype(np.uint8) & rng.integers(0, 256, 32).astype(np.uint8)
+                            & (rng.integers(0, 256, 32).astype(np.uint8) if depth[p] else 0xff))
+                if c == nch - 1 and nch > 2 and rng.random() < 0.3:
+                    d = desc[len(desc) - 1].copy()          # duplicate of the previous sibling
+                parent.append(p); desc.append(d.astype(np.uint8)); depth.append(depth[p] + 1)
+                nxt.append(len(parent) - 1)
+        frontier = nxt
+    n = len(parent)
+    children = np.bincount(np.asarray(parent[1:]), minlength=n)
+    weight = np.zeros(n)
+    leaves = [i for i in range(1, n) if children[i] == 0]
+    weight[leaves] = -np.log(rng.uniform(0.001, 0.9, len(leaves)))
+    stopped = rng.random(len(leaves)) < 0.05
+    weight[np.asarray(leaves)[stopped]] = 0.0
+    return np.asarray(parent, np.int32), np.stack(desc).astype(np.uint8), weight
+
+
+def vocabulary_features(seed, voc, n=700):
+    """descriptors to transform: noisy copies of random leaves (many features per word) plus fresh random ones"""
+    parent, desc, weight = voc
+    rng = np.random.default_rng(seed)
+    children = np.bincount(parent[1:], minlength=len(parent))
+    leaves = np.nonzero(children[1:] == 0)[0] + 1
+    pick = desc[rng.choice(leaves[:max(len(leaves) // 3, 1)], n)]
+    noise = rng.integers(0, 256, (n, 32)).astype(np.uint8) & rng.integers(0, 256, (n, 32)).astype(np.uint8) \
+        & rng.integers(0, 256, (n, 32)).astype(np.uint8) & rng.integers(0, 256, (n, 32)).astype(np.uint8)
+    out = pick ^ noise
+    out[::7] = rng.integers(0, 256, (len(out[::7]), 32)).astype(np.uint8)
+    return out.astype(np.uint8)

@@ -131,3 +131,63 @@ def test_distinctive_descriptor_vs_numpy(oracle):
         D = np.sort(np_dist(rows, rows), axis=1)
         m = D[:, int(0.5 * (len(rows) - 1))]
         assert best[p] == int(np.argmin(m)) and med[p] == m.min()
+
+
+def _np_transform(voc, feats, L, levelsup, weighting, scoring):
+    """independent statement of TemplatedVocabulary::transform with python dicts and IEEE doubles"""
+    parent, desc, weight = voc
+    n = len(parent)
+    kids = [[] for _ in range(n)]
+    for i in range(1, n):
+        kids[parent[i]].append(i)
+    wid, nw = {}, 0
+    for i in range(1, n):
+        if not kids[i]:
+            wid[i] = nw
+            nw += 1
+    bow, fv, words, nodes = {}, {}, [], []
+    for i, f in enumerate(feats):
+        node, level, nid = 0, 0, 0
+        while kids[node]:
+            level += 1
+            d = np.unpackbits(desc[kids[node]] ^ f[None], axis=1).sum(1)
+            node = kids[node][int(np.argmin(d))]
+            if level == L - levelsup:
+                nid = node
+        w = float(weight[node])
+        words.append(wid[node]); nodes.append(nid)
+        if w > 0:
+            if weighting in (0, 1):
+                bow[wid[node]] = bow[wid[node]] + w if wid[node] in bow else w
+            else:
+                bow.setdefault(wid[node], w)
+            fv.setdefault(nid, []).append(i)
+    ids = sorted(bow)
+    vals = [bow[i] for i in ids]
+    must = scoring != 5
+    if weighting in (0, 1) and vals and not must:
+        vals = [v / float(len(vals)) for v in vals]
+    if must:
+        norm = 0.0
+        for v in vals:
+            norm = norm + (abs(v) if scoring != 1 else v * v)
+        if scoring == 1:
+            norm = float(np.sqrt(np.float64(norm)))
+        if norm > 0:
+            vals = [v / norm for v in vals]
+    return ids, vals, fv, words, nodes
+
+
+@pytest.mark.parametrize("weighting,scoring", [(0, 0), (1, 1), (2, 5), (3, 0), (0, 5)])
+def test_bow_transform_vs_numpy(oracle, weighting, scoring):
+    """bow_oracle.cpp (DBoW2 TemplatedVocabulary.h:1138-1272 restated) against an independent python statement"""
+    voc = S.vocabulary(11, k=5, L=4)
+    feats = S.vocabulary_features(12, voc, n=300)
+    V = oracle.Vocabulary(5, 4, *voc, weighting=weighting, scoring=scoring)
+    (ids, vals), (fvn, fvp, fvi), words, nodes = V.transform(feats, levelsup=2)
+    rids, rvals, rfv, rwords, rnodes = _np_transform(voc, feats, 4, 2, weighting, scoring)
+    assert list(ids) == rids and list(words) == rwords and list(nodes) == rnodes
+    assert np.array_equal(np.asarray(rvals, np.float64).view(np.uint64), vals.view(np.uint64))
+    assert list(fvn) == sorted(rfv)
+    for j, nid in enumerate(fvn):
+        assert list(fvi[fvp[j]:fvp[j + 1]]) == rfv[nid]

@@ -204,3 +204,23 @@ def test_distinctive_descriptors(api, ctx, oracle):
         assert (best == rb).all() and (med == rm).all()
     best, med = m.ComputeDistinctiveDescriptors(np.zeros((0, 32), np.uint8), np.zeros(4, np.int32))
     assert (best == -1).all()
+
+
+@pytest.mark.parametrize("weighting,scoring,k,L,levelsup", [(0, 0, 10, 4, 2), (1, 1, 6, 5, 4), (2, 5, 6, 4, 1), (3, 0, 6, 4, 2),
+                                                             (0, 5, 6, 4, 6)])
+def test_bow_transform(api, ctx, oracle, weighting, scoring, k, L, levelsup):
+    """ORBVocabulary::transform (DBoW2 TemplatedVocabulary.h:1138-1272): BowVector ids and values (doubles, bit for
+    bit), FeatureVector node ids and index lists, per-feature word and node identical to the oracle"""
+    voc = S.vocabulary(21 + k, k=k, L=L)
+    V = api.ORBVocabulary(k, L, *voc, weighting=weighting, scoring=scoring, ctx=ctx)
+    R = oracle.Vocabulary(k, L, *voc, weighting=weighting, scoring=scoring)
+    for n in (1, 37, 1500):
+        feats = S.vocabulary_features(n, voc, n=n)
+        (ids, vals), (fvn, fvp, fvi), words, nodes = V.transform(feats, levelsup)
+        (rids, rvals), (rfvn, rfvp, rfvi), rwords, rnodes = R.transform(feats, levelsup)
+        assert np.array_equal(words, rwords) and np.array_equal(nodes, rnodes)
+        assert np.array_equal(ids, rids) and np.array_equal(vals.view(np.uint64), rvals.view(np.uint64))
+        assert np.array_equal(fvn, rfvn) and np.array_equal(fvp, rfvp) and np.array_equal(fvi, rfvi)
+    (ids, vals), (fvn, fvp, fvi), _, _ = V.transform(np.zeros((0, 32), np.uint8), levelsup)
+    assert len(ids) == 0 and len(fvn) == 0
+    V.close()

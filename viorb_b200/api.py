@@ -72,6 +72,10 @@ def lib():
         "viorb_search_by_projection_local": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, vp, pi],
         "viorb_search_by_projection_frame": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, i32, i32, i32, vp, pi],
         "viorb_distinctive_descriptors": [vp, vp, vp, i32, vp, vp],
+        "viorb_vocabulary_create": [vp, i32, i32, i32, i32, i32, vp, vp, vp, pp],
+        "viorb_vocabulary_destroy": [vp],
+        "viorb_vocabulary_info": [vp, pi, pi],
+        "viorb_bow_transform": [vp, vp, i32, i32, vp, vp, pi, vp, vp, vp, pi, vp, vp],
         "viorb_search_for_triangulation": [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp,
                                            i32, vp, f32, f32, vp, vp, i32, i32, i32, vp, pi],
     }
@@ -385,6 +389,53 @@ class ORBmatcher:
         _ck(lib().viorb_distinctive_descriptors(self.ctx.h, _ptr(d) if len(d) else None, _ptr(p), len(best),
                                                 _ptr(best), _ptr(med)))
         return best, med
+
+
+class ORBVocabulary:
+    """Mirror of ORB_SLAM2::ORBVocabulary (DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>) for transform():
+    the tree as loadFromTextFile reads it -- parent[i], descriptor[i], weight[i] per node, node 0 = root."""
+    TF_IDF, TF, IDF, BINARY = 0, 1, 2, 3
+    L1_NORM, L2_NORM, CHI_SQUARE, KL, BHATTACHARYYA, DOT_PRODUCT = range(6)
+
+    def __init__(self, k, L, parent, node_desc, node_weight, weighting=0, scoring=0, ctx=None):
+        self.ctx = ctx or Context()
+        par = np.ascontiguousarray(parent, np.int32)
+        d = np.ascontiguousarray(node_desc, np.uint8).reshape(-1, 32)
+        w = np.ascontiguousarray(node_weight, np.float64)
+        assert len(par) == len(d) == len(w)
+        h = C.c_void_p()
+        _ck(lib().viorb_vocabulary_create(self.ctx.h, k, L, weighting, scoring, len(par), _ptr(par), _ptr(d), _ptr(w),
+                                          C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().viorb_vocabulary_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        a, b = C.c_int(), C.c_int()
+        _ck(lib().viorb_vocabulary_info(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def transform(self, desc, levelsup=4):
+        """-> (BowVector (ids, values), FeatureVector (node ids, ptr, feature idx), word per feature, node per feature)"""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        ids, vals = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+        fvn, fvp, fvi = np.zeros(max(n, 1), np.int32), np.zeros(n + 1, np.int32), np.zeros(max(n, 1), np.int32)
+        wo, no = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+        nb, nf = C.c_int(), C.c_int()
+        _ck(lib().viorb_bow_transform(self.h, _ptr(d) if n else None, n, levelsup, _ptr(ids), _ptr(vals), C.byref(nb),
+                                      _ptr(fvn), _ptr(fvp), _ptr(fvi), C.byref(nf), _ptr(wo), _ptr(no)))
+        nfv = nf.value
+        return ((ids[:nb.value], vals[:nb.value]), (fvn[:nfv], fvp[:nfv + 1], fvi[:fvp[nfv] if nfv else 0]), wo[:n], no[:n])
 
 
 def ComputeStereoMatches(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, mbf, mb, frame_l=0, frame_r=0):

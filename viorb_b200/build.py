@@ -19,7 +19,7 @@ LIBDIR = os.path.join(ROOT, "viorb_b200", "lib")
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 CXX = os.environ.get("CXX") or shutil.which("g++") or "g++"
 
-CUDA_SOURCES = ["extractor_kernels.cu", "matcher_kernels.cu", "c_api.cu", "c_api_match.cu", "search_kernels.cu"]
+CUDA_SOURCES = ["extractor_kernels.cu", "matcher_kernels.cu", "c_api.cu", "c_api_match.cu", "search_kernels.cu", "bow_kernels.cu"]
 HOST_SOURCES = ["ORBextractor.cc", "ORBmatcher.cc"]   # C++ shims compiled into the same library
 
 NVCC_FLAGS = [
