@@ -217,6 +217,28 @@ int viorb_search_for_triangulation(viorb_ctx* ctx,
 int viorb_distinctive_descriptors(viorb_ctx* ctx, const uint8_t* obs_desc, const int32_t* obs_ptr, int nmp,
                                   int32_t* best, int32_t* best_median);
 
+/* replaces int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)
+ *          include/ORBmatcher.h:61, src/ORBmatcher.cc:159-288                                        (mode 0)
+ *     and  int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)
+ *          include/ORBmatcher.h:62, src/ORBmatcher.cc:522-655                                        (mode 1).
+ * Set 1 is pKF / pKF1 (k1 = mvKeysUn, valid1[i] = its MapPoint i exists and !isBad()); set 2 is F (k2 = F.mvKeys,
+ * valid2 = NULL) or pKF2 (k2 = mvKeysUn, valid2 as valid1).  Feature vectors flattened as for
+ * viorb_search_for_triangulation.  mode 0: match[k] (n2 entries) = index in pKF of the map point given to frame
+ * keypoint k, or -1; mode 1: match[i] (n1 entries) = keypoint of pKF2 whose map point is matched to keypoint i.  */
+int viorb_search_by_bow(viorb_ctx* ctx, int mode, const viorb_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                        const viorb_keypoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2,
+                        const int32_t* node_id1, const int32_t* node_ptr1, const int32_t* idx1, int nn1,
+                        const int32_t* node_id2, const int32_t* node_ptr2, const int32_t* idx2, int nn2,
+                        float nnratio, int check_orientation, int32_t* match, int* nmatches);
+
+/* replaces int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched,
+ *          vector<int>& vnMatches12, int windowSize)       include/ORBmatcher.h:66, src/ORBmatcher.cc:405-520.
+ * f2 = frame index of F2 (mvKeysUn, descriptors, grid); k1_un / d1 = F1.mvKeysUn / mDescriptors;
+ * prev_matched (in/out, n1 x 2 floats) = vbPrevMatched; matches12 (out, n1) = vnMatches12.              */
+int viorb_search_for_initialization(viorb_frame_index* f2, const viorb_keypoint* k1_un, const uint8_t* d1, int n1,
+                                    float* prev_matched, int window_size, float nnratio, int check_orientation,
+                                    int32_t* matches12, int* nmatches);
+
 /* ---- DBoW2 vocabulary transform ---------------------------------------------------
  * replaces ORBVocabulary (= DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>) as used by
  *          Frame::ComputeBoW src/Frame.cc:575-582 and KeyFrame::ComputeBoW src/KeyFrame.cc:350-359:

@@ -557,3 +557,152 @@ extern "C" int orc_distinctive_descriptor(const uint8_t* desc, int N, int* media
     if (median_out) *median_out = BestMedian;
     return BestIdx;
 }
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), ORBmatcher.cc:159-288 (mode 0) and
+ * ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&), ORBmatcher.cc:522-655 (mode 1), on the flattened
+ * inputs of the C ABI.  mode 0: match has n2 entries (vpMapPointMatches, as the index of the map point in pKF);
+ * mode 1: n1 entries (vpMatches12, as the keypoint index in pKF2). */
+extern "C" int orc_search_by_bow(int mode, const orc_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                                 const orc_keypoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2,
+                                 const int32_t* node_id1, const int32_t* node_ptr1, const int32_t* idx1v, int nn1,
+                                 const int32_t* node_id2, const int32_t* node_ptr2, const int32_t* idx2v, int nn2,
+                                 float mfNNratio, int check_ori, int32_t* match) {
+    const int nOut = mode == 0 ? n2 : n1;
+    for (int i = 0; i < nOut; i++) match[i] = -1;
+    std::vector<bool> vbMatched2(n2, false);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int f1 = 0, f2 = 0;
+    while (f1 < nn1 && f2 < nn2) {
+        if (node_id1[f1] == node_id2[f2]) {
+            for (int e1 = node_ptr1[f1]; e1 < node_ptr1[f1 + 1]; e1++) {
+                const int idx1 = idx1v[e1];
+                if (!valid1[idx1]) continue;                              /* !pMP || pMP->isBad() */
+                const uint8_t* dA = d1 + (size_t)idx1 * 32;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int e2 = node_ptr2[f2]; e2 < node_ptr2[f2 + 1]; e2++) {
+                    const int idx2 = idx2v[e2];
+                    if (mode == 0) {
+                        if (match[idx2] >= 0) continue;                   /* vpMapPointMatches[realIdxF] (:196) */
+                    } else {
+                        if (vbMatched2[idx2] || !valid2[idx2]) continue;  /* :571-575 */
+                    }
+                    const int dist = orc_descriptor_distance(dA, d2 + (size_t)idx2 * 32);
+                    if (dist < bestDist1) {
+                        bestDist2 = bestDist1;
+                        bestDist1 = dist;
+                        bestIdx2 = idx2;
+                    } else if (dist < bestDist2) {
+                        bestDist2 = dist;
+                    }
+                }
+                const bool pass = mode == 0 ? bestDist1 <= TH_LOW : bestDist1 < TH_LOW;     /* :216 vs :597 */
+                if (pass) {
+                    if (static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
+                        if (mode == 0) match[bestIdx2] = idx1;
+                        else { match[idx1] = bestIdx2; vbMatched2[bestIdx2] = true; }
+                        if (check_ori) {
+                            float rot = k1[idx1].angle - k2[bestIdx2].angle;
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)roundf(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            rotHist[bin].push_back(mode == 0 ? bestIdx2 : idx1);
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+            f1++; f2++;
+        } else if (node_id1[f1] < node_id2[f2]) {
+            f1 = (int)(std::lower_bound(node_id1, node_id1 + nn1, node_id2[f2]) - node_id1);
+        } else {
+            f2 = (int)(std::lower_bound(node_id2, node_id2 + nn2, node_id1[f1]) - node_id2);
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) {
+                match[rotHist[i][j]] = -1;
+                nmatches--;
+            }
+        }
+    }
+    return nmatches;
+}
+
+/* ORBmatcher::SearchForInitialization, ORBmatcher.cc:405-520.  grid2 / k2 / d2 = F2 (mvKeysUn); prev = vbPrevMatched
+ * (in/out, n1 x 2). */
+extern "C" int orc_search_for_initialization(const orc_grid* grid2, const orc_keypoint* k2, const uint8_t* d2, int n2,
+                                             const orc_keypoint* k1, const uint8_t* d1, int n1, float* prev,
+                                             int windowSize, float mfNNratio, int check_ori, int32_t* vnMatches12) {
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) vnMatches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> vMatchedDistance(n2, INT_MAX);
+    std::vector<int> vnMatches21(n2, -1);
+    for (int i1 = 0; i1 < n1; i1++) {
+        const orc_keypoint kp1 = k1[i1];
+        const int level1 = kp1.octave;
+        if (level1 > 0) continue;
+        std::vector<size_t> vIndices2 = features_in_area(grid2, prev[2 * i1], prev[2 * i1 + 1], (float)windowSize, level1, level1);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dA = d1 + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (size_t k = 0; k < vIndices2.size(); k++) {
+            const size_t i2 = vIndices2[k];
+            const int dist = orc_descriptor_distance(dA, d2 + i2 * 32);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) {
+                bestDist2 = bestDist;
+                bestDist = dist;
+                bestIdx2 = (int)i2;
+            } else if (dist < bestDist2) {
+                bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * mfNNratio) {
+                if (vnMatches21[bestIdx2] >= 0) {
+                    vnMatches12[vnMatches21[bestIdx2]] = -1;
+                    nmatches--;
+                }
+                vnMatches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_ori) {
+                    float rot = k1[i1].angle - k2[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)roundf(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) {
+                const int idx1 = rotHist[i][j];
+                if (vnMatches12[idx1] >= 0) {
+                    vnMatches12[idx1] = -1;
+                    nmatches--;
+                }
+            }
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++)
+        if (vnMatches12[i1] >= 0) {
+            prev[2 * i1] = k2[vnMatches12[i1]].x;
+            prev[2 * i1 + 1] = k2[vnMatches12[i1]].y;
+        }
+    return nmatches;
+}

@@ -80,6 +80,8 @@ def lib(path=None):
     L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp,
                                                vp, i32, vp, f32, f32, vp, vp, i32, i32, vp]
     L.orc_distinctive_descriptor.argtypes = [vp, i32, C.POINTER(i32)]
+    L.orc_search_by_bow.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
+    L.orc_search_for_initialization.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, f32, i32, vp]
     L.orc_vocabulary_create.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp]
     L.orc_vocabulary_create.restype = vp
     L.orc_vocabulary_destroy.argtypes = [vp]
@@ -367,3 +369,27 @@ class Vocabulary:
                                      _p(wo), _p(no))
         nfv = nf.value
         return ((ids[:nb], vals[:nb]), (fvn[:nfv], fvp[:nfv + 1], fvi[:fvp[nfv] if nfv else 0]), wo[:n], no[:n])
+
+
+def search_by_bow(mode, k1, d1, valid1, k2, d2, valid2, fv1, fv2, nnratio, check_ori=True):
+    """ORBmatcher::SearchByBoW: mode 0 = (KeyFrame, Frame) -> match per frame keypoint; 1 = (KF1, KF2) -> per KF1 keypoint"""
+    i32, u8 = np.int32, np.uint8
+    k1, k2 = _c(k1, KEYPOINT), _c(k2, KEYPOINT)
+    d1, d2, v1 = _c(d1, u8), _c(d2, u8), _c(valid1, u8)
+    v2 = _c(valid2, u8) if valid2 is not None else None
+    a = [_c(x, i32) for x in (fv1[0], fv1[1], fv1[2], fv2[0], fv2[1], fv2[2])]
+    match = np.full(len(k2) if mode == 0 else len(k1), -1, i32)
+    n = lib().orc_search_by_bow(mode, _p(k1), _p(d1), _p(v1), len(k1), _p(k2), _p(d2), _p(v2), len(k2), _p(a[0]), _p(a[1]),
+                                _p(a[2]), len(a[0]), _p(a[3]), _p(a[4]), _p(a[5]), len(a[3]), nnratio, int(check_ori),
+                                _p(match))
+    return n, match
+
+
+def search_for_initialization(grid2, d2, k1, d1, prev, window, nnratio, check_ori=True):
+    i32, u8 = np.int32, np.uint8
+    k1, d1, d2 = _c(k1, KEYPOINT), _c(d1, u8), _c(d2, u8)
+    prev = np.ascontiguousarray(prev, np.float32).copy()
+    m12 = np.full(len(k1), -1, i32)
+    n = lib().orc_search_for_initialization(grid2.g, _p(grid2.kps), _p(d2), len(grid2.kps), _p(k1), _p(d1), len(k1), _p(prev),
+                                            int(window), nnratio, int(check_ori), _p(m12))
+    return n, m12, prev

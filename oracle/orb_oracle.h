@@ -148,6 +148,15 @@ int orc_search_for_triangulation(const orc_keypoint* k1, const uint8_t* d1, cons
 /* synthetic-input independent helpers */
 /* MapPoint::ComputeDistinctiveDescriptors, MapPoint.cc:249-314 (one point) */
 int orc_distinctive_descriptor(const uint8_t* desc, int N, int* median_out);
+/* ORBmatcher::SearchByBoW x2 (ORBmatcher.cc:159-288, :522-655) and SearchForInitialization (:405-520) */
+int orc_search_by_bow(int mode, const orc_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                      const orc_keypoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2,
+                      const int32_t* node_id1, const int32_t* node_ptr1, const int32_t* idx1v, int nn1,
+                      const int32_t* node_id2, const int32_t* node_ptr2, const int32_t* idx2v, int nn2,
+                      float mfNNratio, int check_ori, int32_t* match);
+int orc_search_for_initialization(const orc_grid* grid2, const orc_keypoint* k2, const uint8_t* d2, int n2,
+                                  const orc_keypoint* k1, const uint8_t* d1, int n1, float* prev,
+                                  int windowSize, float mfNNratio, int check_ori, int32_t* vnMatches12);
 /* DBoW2 vocabulary transform (bow_oracle.cpp) */
 typedef struct orc_vocabulary orc_vocabulary;
 orc_vocabulary* orc_vocabulary_create(int k, int L, int weighting, int scoring, int nnodes, const int32_t* parent,

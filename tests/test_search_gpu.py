@@ -224,3 +224,52 @@ def test_bow_transform(api, ctx, oracle, weighting, scoring, k, L, levelsup):
     (ids, vals), (fvn, fvp, fvi), _, _ = V.transform(np.zeros((0, 32), np.uint8), levelsup)
     assert len(ids) == 0 and len(fvn) == 0
     V.close()
+
+
+def _bow_inputs(s, seed):
+    """two keypoint sets with feature vectors; some descriptors of set 1 are planted into set 2 (exact ties)"""
+    rng = np.random.default_rng(seed)
+    k1, d1, k2, d2 = s["kl"], s["dl"], s["kr"].copy(), s["dr"].copy()
+    fv1 = S.feature_vector(k1, S.row_band_nodes())
+    fv2 = S.feature_vector(k2, S.row_band_nodes(drop_every=5))
+    # plant near-copies of set-1 descriptors into set 2 inside the same node band, several per source (competition)
+    for _ in range(300):
+        i = int(rng.integers(0, len(k1)))
+        band = np.nonzero((k2["y"] // 24) == (k1["y"][i] // 24))[0]
+        if len(band) == 0:
+            continue
+        j = int(band[rng.integers(0, len(band))])
+        d2[j] = S.flip_bits(d1[i:i + 1], rng, 12)[0]
+        k2["angle"][j] = (k1["angle"][i] + rng.choice([0.0, 0.0, 0.0, 0.0, 100.0, 250.0])) % 360.0
+    v1 = (rng.random(len(k1)) < 0.8).astype(np.uint8)
+    v2 = (rng.random(len(k2)) < 0.8).astype(np.uint8)
+    return k1, d1, v1, k2, d2, v2, fv1, fv2
+
+
+@pytest.mark.parametrize("mode,check_ori,nnratio", [(0, True, 0.7), (0, False, 0.9), (1, True, 0.75), (1, False, 0.6)])
+def test_search_by_bow(api, ctx, oracle, stereo, mode, check_ori, nnratio):
+    """ORBmatcher::SearchByBoW, both overloads (ORBmatcher.cc:159-288, :522-655)"""
+    k1, d1, v1, k2, d2, v2, fv1, fv2 = _bow_inputs(stereo, 5 + mode)
+    n_ref, m_ref = oracle.search_by_bow(mode, k1, d1, v1, k2, d2, v2 if mode else None, fv1, fv2, nnratio, check_ori)
+    m = api.ORBmatcher(nnratio, check_ori, ctx=ctx)
+    n, match = m.SearchByBoW(mode, k1, d1, v1, k2, d2, v2 if mode else None, fv1, fv2)
+    assert n_ref > 50
+    assert n == n_ref and (match == m_ref).all()
+
+
+@pytest.mark.parametrize("window,check_ori,nnratio", [(100, True, 0.9), (30, False, 0.9), (100, True, 0.6)])
+def test_search_for_initialization(api, ctx, oracle, stereo, window, check_ori, nnratio):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:405-520) incl. the stolen-match dependence"""
+    s = stereo
+    h, w = s["shape"]
+    sf = s["ol"].scale_factors()
+    k1, d1, k2, d2 = s["kl"], s["dl"], s["kr"], s["dr"]
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    g2 = oracle.Grid(k2, 0.0, float(w), 0.0, float(h))
+    n_ref, m_ref, p_ref = oracle.search_for_initialization(g2, d2, k1, d1, prev, window, nnratio, check_ori)
+    fi2 = api.FrameIndex(ctx, k2, d2, None, (0.0, float(w), 0.0, float(h)), sf)
+    m = api.ORBmatcher(nnratio, check_ori, ctx=ctx)
+    n, m12, p = m.SearchForInitialization(fi2, k1, d1, prev, window)
+    fi2.close()
+    assert n_ref > 20
+    assert n == n_ref and (m12 == m_ref).all() and (p.view(np.uint32) == p_ref.view(np.uint32)).all()

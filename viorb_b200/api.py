@@ -72,6 +72,8 @@ def lib():
         "viorb_search_by_projection_local": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, vp, pi],
         "viorb_search_by_projection_frame": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, i32, i32, i32, vp, pi],
         "viorb_distinctive_descriptors": [vp, vp, vp, i32, vp, vp],
+        "viorb_search_by_bow": [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp, pi],
+        "viorb_search_for_initialization": [vp, vp, vp, i32, vp, i32, f32, i32, vp, pi],
         "viorb_vocabulary_create": [vp, i32, i32, i32, i32, i32, vp, vp, vp, pp],
         "viorb_vocabulary_destroy": [vp],
         "viorb_vocabulary_info": [vp, pi, pi],
@@ -378,6 +380,34 @@ class ORBmatcher:
             len(a[9]), _ptr(a[12]), ex, ey, _ptr(a[13]), _ptr(a[14]), len(a[13]), int(bOnlyStereo),
             int(self.mbCheckOrientation), _ptr(m12), C.byref(n)))
         return n.value, m12
+
+    def SearchByBoW(self, mode, k1, d1, valid1, k2, d2, valid2, fv1, fv2):
+        """mode 0: SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) -> (nmatches, index in pKF per frame keypoint);
+        mode 1: SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) -> (nmatches, keypoint of pKF2 per keypoint of pKF1)"""
+        i32, u8 = np.int32, np.uint8
+        k1, k2 = np.ascontiguousarray(k1, KEYPOINT), np.ascontiguousarray(k2, KEYPOINT)
+        d1, d2, v1 = np.ascontiguousarray(d1, u8), np.ascontiguousarray(d2, u8), np.ascontiguousarray(valid1, u8)
+        v2 = np.ascontiguousarray(valid2, u8) if valid2 is not None else None
+        a = [np.ascontiguousarray(x, i32) for x in (fv1[0], fv1[1], fv1[2], fv2[0], fv2[1], fv2[2])]
+        match = np.full(len(k2) if mode == 0 else len(k1), -1, i32)
+        n = C.c_int()
+        _ck(lib().viorb_search_by_bow(self.ctx.h, mode, _ptr(k1), _ptr(d1), _ptr(v1), len(k1), _ptr(k2), _ptr(d2), _ptr(v2),
+                                      len(k2), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), len(a[0]), _ptr(a[3]), _ptr(a[4]),
+                                      _ptr(a[5]), len(a[3]), self.mfNNratio, int(self.mbCheckOrientation), _ptr(match),
+                                      C.byref(n)))
+        return n.value, match
+
+    def SearchForInitialization(self, fi2, k1_un, d1, prev_matched, windowSize=10):
+        """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize); fi2 = FrameIndex of F2.
+        -> (nmatches, vnMatches12, updated vbPrevMatched)"""
+        k1 = np.ascontiguousarray(k1_un, KEYPOINT)
+        d1 = np.ascontiguousarray(d1, np.uint8)
+        prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+        m12 = np.full(len(k1), -1, np.int32)
+        n = C.c_int()
+        _ck(lib().viorb_search_for_initialization(fi2.h, _ptr(k1), _ptr(d1), len(k1), _ptr(prev), int(windowSize),
+                                                  self.mfNNratio, int(self.mbCheckOrientation), _ptr(m12), C.byref(n)))
+        return n.value, m12, prev
 
     def ComputeDistinctiveDescriptors(self, obs_desc, obs_ptr):
         """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:249-314) over a CSR batch of map points:

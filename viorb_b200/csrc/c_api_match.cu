@@ -41,6 +41,16 @@ int viorb_launch_triangulation(const viorb_keypoint* k1, const uint8_t* d1, cons
 int viorb_launch_distinctive(const uint8_t* d_desc, const int* d_ptr, int nmp, int* d_best, int* d_bestMedian,
                              cudaStream_t s);
 
+int viorb_launch_search_bow(int mode, const viorb_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                            const viorb_keypoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2, const int* nodeId1,
+                            const int* nodePtr1, const int* idx1, int nn1, const int* nodeId2, const int* nodePtr2,
+                            const int* idx2, int nn2, float nnratio, int checkOri, int* d_taken, int* d_match,
+                            int* d_nmatches, cudaStream_t s);
+int viorb_launch_search_init(const FrameIndexDev& f2, const viorb_keypoint* k1, const uint8_t* d1, int n1, float* d_prev,
+                             float window, float nnratio, int checkOri, unsigned long long* d_entries, long long cap,
+                             int* d_start, int* d_count, unsigned long long* d_cursor, int* d_overflow, int* d_matchedDist,
+                             int* d_matches21, int* d_binOf, int* d_matches12, int* d_nmatches, cudaStream_t s);
+
 namespace {
 
 /* bump allocator over one device scratch buffer: a call uploads all its inputs into a single arena */
@@ -359,6 +369,88 @@ int viorb_distinctive_descriptors(viorb_ctx* c, const uint8_t* obs_desc, const i
     VCU(cudaMemcpyAsync(best, db, (size_t)nmp * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
     if (best_median) VCU(cudaMemcpyAsync(best_median, dm, (size_t)nmp * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
     VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    return VIORB_OK;
+}
+
+int viorb_search_by_bow(viorb_ctx* c, int mode, const viorb_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                        const viorb_keypoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2, const int32_t* node_id1,
+                        const int32_t* node_ptr1, const int32_t* idx1, int nn1, const int32_t* node_id2,
+                        const int32_t* node_ptr2, const int32_t* idx2, int nn2, float nnratio, int check_orientation,
+                        int32_t* match, int* nmatches) {
+    if (!c || (mode != 0 && mode != 1) || n1 < 0 || n2 < 0 || nn1 < 0 || nn2 < 0 || !match || !nmatches ||
+        (n1 > 0 && (!k1 || !d1 || !valid1)) || (n2 > 0 && (!k2 || !d2)) || (mode == 1 && n2 > 0 && !valid2) ||
+        (nn1 > 0 && (!node_id1 || !node_ptr1 || !idx1)) || (nn2 > 0 && (!node_id2 || !node_ptr2 || !idx2)))
+        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    if (n2 >= (1 << 24)) return viorb_fail(VIORB_ERR_UNSUPPORTED, "more than 2^24 keypoints");
+    int rc;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    const int e1 = nn1 > 0 ? node_ptr1[nn1] : 0, e2 = nn2 > 0 ? node_ptr2[nn2] : 0;
+    const int m1 = std::max(n1, 1), m2 = std::max(n2, 1), mo = std::max(m1, m2);
+    const size_t bytes = pad((size_t)m1 * 28) + pad((size_t)m1 * 32) + pad(m1) + pad((size_t)m2 * 28) + pad((size_t)m2 * 32) + pad(m2) +
+                         pad((size_t)m2 * 4) + pad((size_t)mo * 4) + pad((size_t)(nn1 + 2) * 4) * 2 + pad((size_t)(e1 + 1) * 4) +
+                         pad((size_t)(nn2 + 2) * 4) * 2 + pad((size_t)(e2 + 1) * 4) + pad(64) + 16384;
+    Arena a;
+    if ((rc = viorb_ctx_scratch(c, bytes, &a.base))) return rc;
+    viorb_keypoint* dk1 = a.take<viorb_keypoint>(m1); uint8_t* dd1 = a.take<uint8_t>((size_t)m1 * 32); uint8_t* dv1 = a.take<uint8_t>(m1);
+    viorb_keypoint* dk2 = a.take<viorb_keypoint>(m2); uint8_t* dd2 = a.take<uint8_t>((size_t)m2 * 32); uint8_t* dv2 = a.take<uint8_t>(m2);
+    int* dtaken = a.take<int>(m2); int* dmatch = a.take<int>(mo);
+    int* dni1 = a.take<int>(nn1 + 1); int* dnp1 = a.take<int>(nn1 + 2); int* di1 = a.take<int>(e1 + 1);
+    int* dni2 = a.take<int>(nn2 + 1); int* dnp2 = a.take<int>(nn2 + 2); int* di2 = a.take<int>(e2 + 1);
+    int* dn = a.take<int>(4);
+    if ((rc = upload(c, dk1, k1, n1)) || (rc = upload(c, dd1, d1, (size_t)n1 * 32)) || (rc = upload(c, dv1, valid1, n1)) ||
+        (rc = upload(c, dk2, k2, n2)) || (rc = upload(c, dd2, d2, (size_t)n2 * 32)) || (valid2 && (rc = upload(c, dv2, valid2, n2))) ||
+        (rc = upload(c, dni1, node_id1, nn1)) || (rc = upload(c, dnp1, node_ptr1, nn1 ? nn1 + 1 : 0)) || (rc = upload(c, di1, idx1, e1)) ||
+        (rc = upload(c, dni2, node_id2, nn2)) || (rc = upload(c, dnp2, node_ptr2, nn2 ? nn2 + 1 : 0)) || (rc = upload(c, di2, idx2, e2)))
+        return rc;
+    viorb_ctx_add_launches(c, viorb_launch_search_bow(mode, dk1, dd1, dv1, n1, dk2, dd2, valid2 ? dv2 : nullptr, n2, dni1, dnp1, di1,
+                                                      nn1, dni2, dnp2, di2, nn2, nnratio, check_orientation, dtaken, dmatch, dn,
+                                                      viorb_ctx_stream(c)));
+    VCU(cudaGetLastError());
+    VCU(cudaMemcpyAsync(match, dmatch, (size_t)(mode == 0 ? n2 : n1) * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    return VIORB_OK;
+}
+
+int viorb_search_for_initialization(viorb_frame_index* f2, const viorb_keypoint* k1_un, const uint8_t* d1, int n1,
+                                    float* prev_matched, int window_size, float nnratio, int check_orientation,
+                                    int32_t* matches12, int* nmatches) {
+    if (!f2 || n1 < 0 || !matches12 || !nmatches || (n1 > 0 && (!k1_un || !d1 || !prev_matched)))
+        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    viorb_ctx* c = f2->ctx;
+    int rc;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    const int n2 = f2->n;
+    if (n2 >= (1 << 24)) return viorb_fail(VIORB_ERR_UNSUPPORTED, "more than 2^24 keypoints");
+    /* candidate pool: only level-0 keypoints of F1 search (:424-426) and only level-0 keypoints of F2 are returned */
+    long long q0 = 0;
+    for (int i = 0; i < n1; i++) q0 += k1_un[i].octave <= 0;
+    const long long cap = std::max<long long>(q0 * std::max(n2, 1), 1);
+    if (cap > (1ll << 28)) return viorb_fail(VIORB_ERR_UNSUPPORTED, "candidate pool of %lld entries", cap);
+    const int m1 = std::max(n1, 1), m2 = std::max(n2, 1);
+    const size_t bytes = pad((size_t)m1 * 28) + pad((size_t)m1 * 32) + pad((size_t)m1 * 8) + pad((size_t)cap * 8) + 4 * pad((size_t)m1 * 4) +
+                         2 * pad((size_t)m2 * 4) + 3 * pad(64) + 16384;
+    Arena a;
+    if ((rc = viorb_ctx_scratch(c, bytes, &a.base))) return rc;
+    viorb_keypoint* dk1 = a.take<viorb_keypoint>(m1); uint8_t* dd1 = a.take<uint8_t>((size_t)m1 * 32);
+    float* dprev = a.take<float>((size_t)m1 * 2);
+    unsigned long long* dent = a.take<unsigned long long>((size_t)cap);
+    int* dstart = a.take<int>(m1); int* dcount = a.take<int>(m1); int* dbin = a.take<int>(m1); int* dm12 = a.take<int>(m1);
+    int* dmd = a.take<int>(m2); int* dm21 = a.take<int>(m2);
+    unsigned long long* dcur = a.take<unsigned long long>(2);
+    int* dovf = a.take<int>(4); int* dn = a.take<int>(4);
+    if ((rc = upload(c, dk1, k1_un, n1)) || (rc = upload(c, dd1, d1, (size_t)n1 * 32)) || (rc = upload(c, dprev, prev_matched, (size_t)n1 * 2)))
+        return rc;
+    viorb_ctx_add_launches(c, viorb_launch_search_init(f2->dev, dk1, dd1, n1, dprev, (float)window_size, nnratio, check_orientation, dent,
+                                                       cap, dstart, dcount, dcur, dovf, dmd, dm21, dbin, dm12, dn, viorb_ctx_stream(c)));
+    VCU(cudaGetLastError());
+    int ovf = 0;
+    VCU(cudaMemcpyAsync(matches12, dm12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaMemcpyAsync(prev_matched, dprev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaMemcpyAsync(&ovf, dovf, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    if (ovf) return viorb_fail(VIORB_ERR_CAPACITY, "candidate pool overflow");
     return VIORB_OK;
 }
 

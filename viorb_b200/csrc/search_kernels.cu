@@ -17,6 +17,8 @@
  */
 #include <limits.h>
 
+#include <algorithm>
+
 #include "matcher_kernels.cuh"
 
 namespace {
@@ -664,6 +666,203 @@ __global__ void __launch_bounds__(128) distinctive_kernel(const uint8_t* __restr
     }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)          (:159-288)  mode 0
+ * ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)       (:522-655)  mode 1
+ * The merge walk over the two FeatureVectors visits exactly the common node ids; a feature belongs to one node,
+ * so the "already matched" state (vpMapPointMatches / vbMatched2) of a node's candidates is only touched by the
+ * queries of the same node: one warp owns a node pair, runs its queries in list order (the reference's order)
+ * and scans the candidates with its lanes (top-2 by warp reduction; ties keep the first list position).
+ * ---------------------------------------------------------------------------------------------- */
+struct BowArgs {
+    const uint8_t *d1, *d2;
+    const uint8_t *valid1, *valid2;      /* valid2 may be NULL (mode 0: every frame keypoint is a candidate) */
+    const int *nodeId1, *nodePtr1, *idx1, *nodeId2, *nodePtr2, *idx2;
+    int nn1, nn2, mode;
+    float nnratio;
+};
+
+__global__ void __launch_bounds__(128) search_bow_kernel(const __grid_constant__ BowArgs a, int* __restrict__ taken,
+                                                         int* __restrict__ match) {
+    const int lane = threadIdx.x & 31;
+    const int f1 = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (f1 >= a.nn1) return;
+    const int node = a.nodeId1[f1];
+    int l2 = 0, h2 = a.nn2 - 1, f2 = -1;
+    while (l2 <= h2) {
+        const int mid = (l2 + h2) >> 1;
+        const int v = a.nodeId2[mid];
+        if (v == node) { f2 = mid; break; }
+        if (v < node) l2 = mid + 1; else h2 = mid - 1;
+    }
+    if (f2 < 0) return;
+    const int beg2 = a.nodePtr2[f2], end2 = a.nodePtr2[f2 + 1];
+    for (int e = a.nodePtr1[f1]; e < a.nodePtr1[f1 + 1]; e++) {
+        const int i1 = a.idx1[e];
+        if (!a.valid1[i1]) continue;                        /* !pMP || pMP->isBad() */
+        const uint8_t* d1 = a.d1 + (size_t)i1 * 32;
+        unsigned long long k1 = ~0ull, k2 = ~0ull;
+        for (int j = beg2 + lane; j < end2; j += 32) {
+            const int i2 = a.idx2[j];
+            if (taken[i2]) continue;
+            if (a.valid2 && !a.valid2[i2]) continue;
+            const int dist = hamming_rows(d1, a.d2 + (size_t)i2 * 32);
+            if (dist >= 256) continue;                       /* bestDist1 = bestDist2 = 256, strict < */
+            const unsigned long long key = ((unsigned long long)dist << 48) | ((unsigned long long)(j - beg2) << 24) | (unsigned)i2;
+            if (key < k1) { k2 = k1; k1 = key; }
+            else if (key < k2) k2 = key;
+        }
+        warp_two_min(k1, k2);
+        if (k1 == ~0ull) continue;
+        const int best1 = (int)(k1 >> 48), best2 = k2 == ~0ull ? 256 : (int)(k2 >> 48), bestIdx = (int)(k1 & 0xffffff);
+        const bool ok = (a.mode == 0 ? best1 <= TH_LOW : best1 < TH_LOW) && (float)best1 < __fmul_rn(a.nnratio, (float)best2);
+        if (ok && lane == 0) {
+            taken[bestIdx] = 1;
+            if (a.mode == 0) match[bestIdx] = i1; else match[i1] = bestIdx;
+        }
+        __syncwarp();
+    }
+}
+
+/* rotation-histogram filter (:246-265, :633-652) and match count.  match[i] = j pairs keypoint i of set A with
+ * keypoint j of set B; rot = angle(first) - angle(second) where first is A when aFirst, else B. */
+__global__ void __launch_bounds__(1024) rotation_finalize_kernel(const viorb_keypoint* __restrict__ kA,
+                                                                 const viorb_keypoint* __restrict__ kB, int nA, int aFirst,
+                                                                 int checkOri, int* __restrict__ match,
+                                                                 int* __restrict__ nmatches) {
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int keep[3];
+    __shared__ int total;
+    const int tid = threadIdx.x;
+    if (tid < HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) total = 0;
+    __syncthreads();
+    for (int i = tid; i < nA; i += blockDim.x)
+        if (match[i] >= 0) {
+            atomicAdd(&total, 1);
+            if (checkOri) atomicAdd(&hist[aFirst ? rot_bin(kA[i].angle, kB[match[i]].angle) : rot_bin(kB[match[i]].angle, kA[i].angle)], 1);
+        }
+    __syncthreads();
+    if (checkOri) {
+        if (tid == 0) three_maxima(hist, HISTO_LENGTH, keep[0], keep[1], keep[2]);
+        __syncthreads();
+        for (int i = tid; i < nA; i += blockDim.x)
+            if (match[i] >= 0) {
+                const int b = aFirst ? rot_bin(kA[i].angle, kB[match[i]].angle) : rot_bin(kB[match[i]].angle, kA[i].angle);
+                if (b != keep[0] && b != keep[1] && b != keep[2]) { match[i] = -1; atomicSub(&total, 1); }
+            }
+        __syncthreads();
+    }
+    if (tid == 0) *nmatches = total;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchForInitialization                                     (:405-520)
+ * Phase 1 (parallel, one warp per level-0 keypoint of F1): the candidates GetFeaturesInArea returns in F2 and
+ * their distances, as keys dist | enumeration rank | index.  Phase 2 (one warp, F1 order): the loop-carried
+ * part -- vMatchedDistance / vnMatches21 let a later keypoint steal an earlier one's match (:444-470) -- runs
+ * over the precomputed keys only.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(128) init_candidates_kernel(FrameIndexDev f2, const viorb_keypoint* __restrict__ k1,
+                                                              const uint8_t* __restrict__ d1, int n1,
+                                                              const float* __restrict__ prev, float window,
+                                                              unsigned long long* __restrict__ entries, long long cap,
+                                                              int* __restrict__ start, int* __restrict__ count,
+                                                              unsigned long long* __restrict__ cursor, int* __restrict__ overflow) {
+    __shared__ int slot[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i1 = blockIdx.x * 4 + warp;
+    if (i1 >= n1) return;
+    const viorb_keypoint kp1 = k1[i1];
+    int cnt = 0;
+    const int level1 = kp1.octave;
+    const float x = prev[2 * i1], y = prev[2 * i1 + 1];
+    if (level1 <= 0) for_features_in_area(f2, x, y, window, level1, level1, lane, [&](int, int, int) { cnt++; });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    unsigned long long base = 0;
+    if (lane == 0) {
+        if (cnt) base = atomicAdd(cursor, (unsigned long long)cnt);
+        if ((long long)(base + cnt) > cap) { atomicExch(overflow, 1); }
+        start[i1] = (int)base;
+        count[i1] = (long long)(base + cnt) > cap ? 0 : cnt;
+        slot[warp] = 0;
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    if (cnt == 0 || (long long)(base + cnt) > cap) return;
+    const uint8_t* dq = d1 + (size_t)i1 * 32;
+    for_features_in_area(f2, x, y, window, level1, level1, lane, [&](int pos, int idx, int) {
+        const int dist = hamming_rows(dq, f2.desc + (size_t)idx * 32);
+        entries[base + atomicAdd(&slot[warp], 1)] = ((unsigned long long)dist << 48) | ((unsigned long long)pos << 24) | (unsigned)idx;
+    });
+}
+
+__global__ void __launch_bounds__(32) init_match_kernel(const viorb_keypoint* __restrict__ k1, const viorb_keypoint* __restrict__ k2,
+                                                        int n1, int n2, const unsigned long long* __restrict__ entries,
+                                                        const int* __restrict__ start, const int* __restrict__ count,
+                                                        float nnratio, int checkOri, int* __restrict__ matchedDist,
+                                                        int* __restrict__ matches21, int* __restrict__ binOf,
+                                                        int* __restrict__ matches12, float* __restrict__ prev,
+                                                        int* __restrict__ nmatches) {
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int keep[3];
+    const int lane = threadIdx.x;
+    if (lane < HISTO_LENGTH) hist[lane] = 0;
+    for (int i = lane; i < n2; i += 32) { matchedDist[i] = INT_MAX; matches21[i] = -1; }
+    for (int i = lane; i < n1; i += 32) { matches12[i] = -1; binOf[i] = -1; }
+    __syncwarp();
+    int total = 0;                                          /* kept by lane 0 */
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int c = count[i1];
+        if (c == 0) continue;
+        const unsigned long long* e = entries + start[i1];
+        unsigned long long a = ~0ull, b = ~0ull;
+        for (int j = lane; j < c; j += 32) {
+            const unsigned long long key = e[j];
+            if (matchedDist[(int)(key & 0xffffff)] <= (int)(key >> 48)) continue;       /* :444-445 */
+            if (key < a) { b = a; a = key; }
+            else if (key < b) b = key;
+        }
+        warp_two_min(a, b);
+        if (a == ~0ull) continue;
+        const int bestDist = (int)(a >> 48), bestIdx2 = (int)(a & 0xffffff);
+        const float second = b == ~0ull ? (float)INT_MAX : (float)(int)(b >> 48);
+        if (bestDist <= TH_LOW && (float)bestDist < __fmul_rn(second, nnratio)) {
+            if (lane == 0) {
+                if (matches21[bestIdx2] >= 0) { matches12[matches21[bestIdx2]] = -1; total--; }
+                matches12[i1] = bestIdx2;
+                matches21[bestIdx2] = i1;
+                matchedDist[bestIdx2] = bestDist;
+                total++;
+                if (checkOri) {
+                    const int bin = rot_bin(k1[i1].angle, k2[bestIdx2].angle);
+                    hist[bin]++;                             /* rotHist keeps stolen entries too (:462-471) */
+                    binOf[i1] = bin;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (checkOri) {
+        if (lane == 0) three_maxima(hist, HISTO_LENGTH, keep[0], keep[1], keep[2]);
+        __syncwarp();
+        int removed = 0;
+        for (int i = lane; i < n1; i += 32) {
+            const int bin = binOf[i];
+            if (bin >= 0 && bin != keep[0] && bin != keep[1] && bin != keep[2] && matches12[i] >= 0) { matches12[i] = -1; removed++; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        total -= removed;
+    }
+    __syncwarp();
+    for (int i = lane; i < n1; i += 32)                     /* update prev matched (:513-516) */
+        if (matches12[i] >= 0) { prev[2 * i] = k2[matches12[i]].x; prev[2 * i + 1] = k2[matches12[i]].y; }
+    if (lane == 0) *nmatches = total;
+}
+
 }  // namespace
 
 /* ------------------------------------------------------------------------------------------------ launchers */
@@ -742,4 +941,45 @@ int viorb_launch_distinctive(const uint8_t* d_desc, const int* d_ptr, int nmp, i
     if (nmp <= 0) return 0;
     distinctive_kernel<<<nmp, 128, 0, s>>>(d_desc, d_ptr, d_best, d_bestMedian);
     return 1;
+}
+
+int viorb_launch_search_bow(int mode, const viorb_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                            const viorb_keypoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2, const int* nodeId1,
+                            const int* nodePtr1, const int* idx1, int nn1, const int* nodeId2, const int* nodePtr2,
+                            const int* idx2, int nn2, float nnratio, int checkOri, int* d_taken, int* d_match,
+                            int* d_nmatches, cudaStream_t s) {
+    BowArgs a;
+    a.d1 = d1; a.d2 = d2; a.valid1 = valid1; a.valid2 = valid2;
+    a.nodeId1 = nodeId1; a.nodePtr1 = nodePtr1; a.idx1 = idx1; a.nodeId2 = nodeId2; a.nodePtr2 = nodePtr2; a.idx2 = idx2;
+    a.nn1 = nn1; a.nn2 = nn2; a.mode = mode; a.nnratio = nnratio;
+    const int nOut = mode == 0 ? n2 : n1;
+    cudaMemsetAsync(d_match, 0xff, (size_t)std::max(nOut, 1) * sizeof(int), s);
+    cudaMemsetAsync(d_taken, 0, (size_t)std::max(n2, 1) * sizeof(int), s);
+    int launches = 0;
+    if (nn1 > 0 && nn2 > 0) {
+        search_bow_kernel<<<(nn1 + 3) / 4, 128, 0, s>>>(a, d_taken, d_match);
+        launches++;
+    }
+    /* mode 0: match is indexed by the frame keypoint, rot = kpKF.angle - F.mvKeys[idx].angle (:229);
+     * mode 1: indexed by KF1's keypoint, rot = vKeysUn1[idx1].angle - vKeysUn2[bestIdx2].angle (:616) */
+    if (mode == 0) rotation_finalize_kernel<<<1, 1024, 0, s>>>(k2, k1, n2, 0, checkOri, d_match, d_nmatches);
+    else rotation_finalize_kernel<<<1, 1024, 0, s>>>(k1, k2, n1, 1, checkOri, d_match, d_nmatches);
+    return launches + 1;
+}
+
+int viorb_launch_search_init(const FrameIndexDev& f2, const viorb_keypoint* k1, const uint8_t* d1, int n1, float* d_prev,
+                             float window, float nnratio, int checkOri, unsigned long long* d_entries, long long cap,
+                             int* d_start, int* d_count, unsigned long long* d_cursor, int* d_overflow, int* d_matchedDist,
+                             int* d_matches21, int* d_binOf, int* d_matches12, int* d_nmatches, cudaStream_t s) {
+    cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), s);
+    cudaMemsetAsync(d_overflow, 0, sizeof(int), s);
+    int launches = 0;
+    if (n1 > 0) {
+        init_candidates_kernel<<<(n1 + 3) / 4, 128, 0, s>>>(f2, k1, d1, n1, d_prev, window, d_entries, cap, d_start, d_count,
+                                                           d_cursor, d_overflow);
+        launches++;
+    }
+    init_match_kernel<<<1, 32, 0, s>>>(k1, f2.kps, n1, f2.n, d_entries, d_start, d_count, nnratio, checkOri, d_matchedDist,
+                                       d_matches21, d_binOf, d_matches12, d_prev, d_nmatches);
+    return launches + 1;
 }
