@@ -155,6 +155,22 @@ int viorb_frame_index_create(viorb_ctx* ctx, const viorb_keypoint* kps_un, const
                              const float* u_right /* may be NULL: all -1 */, int n,
                              float min_x, float max_x, float min_y, float max_y,
                              const float* scale_factors, int nlevels, viorb_frame_index** out);
+/* The same index from the RAW keypoints of ORBextractor::operator(): Frame::UndistortKeyPoints (src/Frame.cc:584-614,
+ * cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK)), Frame::ComputeImageBounds (:616-645) and
+ * AssignFeaturesToGrid run on the device; keypoints do not return to the host between extraction and matching
+ * (SURVEY.md 8(f) F3).  dist_coef = mDistCoef (k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4]]]), ndist in {0,4,5,8,12};
+ * cols, rows = image size for the bounds.                                                                  */
+int viorb_frame_index_create_distorted(viorb_ctx* ctx, const viorb_keypoint* kps, const uint8_t* desc,
+                                       const float* u_right, int n, float fx, float fy, float cx, float cy,
+                                       const float* dist_coef, int ndist, int cols, int rows,
+                                       const float* scale_factors, int nlevels, viorb_frame_index** out);
+/* mvKeysUn (may be NULL) and {mnMinX, mnMaxX, mnMinY, mnMaxY} (may be NULL) of an index */
+int viorb_frame_index_keys(viorb_frame_index* fi, viorb_keypoint* kps_un, float bounds[4]);
+/* stand-alone forms of the two Frame members, host buffers */
+int viorb_undistort_keypoints(viorb_ctx* ctx, const viorb_keypoint* kps, int n, float fx, float fy, float cx, float cy,
+                              const float* dist_coef, int ndist, viorb_keypoint* kps_un);
+int viorb_compute_image_bounds(viorb_ctx* ctx, int cols, int rows, float fx, float fy, float cx, float cy,
+                               const float* dist_coef, int ndist, float bounds[4]);
 int viorb_frame_index_destroy(viorb_frame_index* fi);
 /* Frame::GetFeaturesInArea (src/Frame.cc:507-560), reference enumeration order */
 int viorb_frame_features_in_area(viorb_frame_index* fi, float x, float y, float r, int min_level,
@@ -238,6 +254,30 @@ int viorb_search_by_bow(viorb_ctx* ctx, int mode, const viorb_keypoint* k1, cons
 int viorb_search_for_initialization(viorb_frame_index* f2, const viorb_keypoint* k1_un, const uint8_t* d1, int n1,
                                     float* prev_matched, int window_size, float nnratio, int check_orientation,
                                     int32_t* matches12, int* nmatches);
+
+/* Independent windowed top-1 search of projected map points in a KeyFrame: the search loop shared by
+ *   int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th)
+ *       include/ORBmatcher.h:81, src/ORBmatcher.cc:825-976 -- pass ur = u - bf*invz and inv_level_sigma2 =
+ *       pKF->mvInvLevelSigma2 (chi-square gates 7.8 / 5.99, :901-925), th_dist = TH_LOW;
+ *   int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>&, float th, vector<MapPoint*>&)
+ *       include/ORBmatcher.h:84, src/ORBmatcher.cc:978-1100 -- ur = NULL, th_dist = TH_LOW.
+ * kf = frame index of the KeyFrame (mvKeysUn, mDescriptors, mvuRight, grid).  Per map point i: valid[i] = it passed the
+ * reference's projection gates (:846-881 / :1001-1041, evaluated by the caller), u/v = projection, pred_level =
+ * PredictScale(dist3D, pKF).  best_idx[i] = keypoint with the least distance <= th_dist (first in GetFeaturesInArea
+ * order on ties) or -1; the caller replays the Replace / AddObservation bookkeeping (:945-967) in order.          */
+int viorb_search_window_top1(viorb_frame_index* kf, const float* u, const float* v, const float* ur,
+                             const int32_t* pred_level, const uint8_t* valid, const uint8_t* mp_desc, int n, float th,
+                             int th_dist, const float* inv_level_sigma2, int32_t* best_idx, int32_t* best_dist);
+
+/* replaces int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const float& s12,
+ *          const cv::Mat& R12, const cv::Mat& t12, const float th)   include/ORBmatcher.h:76-77, src/ORBmatcher.cc:1102-1326.
+ * kf1 / kf2 = frame indices of the two key frames.  Arrays *12 have kf1->n entries (map point of keypoint i1 of KF1
+ * projected into KF2: valid12[i1] = has a good map point, not already matched, passed the gates of :1155-1191);
+ * arrays *21 the reverse (:1234-1270).  match12[i1] = idx2 where both directions agree (:1305-1320), else -1.     */
+int viorb_search_by_sim3(viorb_frame_index* kf1, viorb_frame_index* kf2, const float* u12, const float* v12,
+                         const int32_t* level12, const uint8_t* valid12, const uint8_t* mp_desc1, const float* u21,
+                         const float* v21, const int32_t* level21, const uint8_t* valid21, const uint8_t* mp_desc2,
+                         float th, int32_t* match12, int* nfound);
 
 /* ---- DBoW2 vocabulary transform ---------------------------------------------------
  * replaces ORBVocabulary (= DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>) as used by

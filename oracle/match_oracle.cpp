@@ -706,3 +706,138 @@ extern "C" int orc_search_for_initialization(const orc_grid* grid2, const orc_ke
         }
     return nmatches;
 }
+
+/* Frame::UndistortKeyPoints (Frame.cc:584-614): cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK).  OpenCV is a
+ * third-party dependency (pinned 2.4.x by the reference; 4.13 in this image): cvUndistortPoints normalises with the
+ * inverse intrinsics, runs five iterations of the distortion compensation in double precision and re-projects with
+ * P*R = K.  Pinned bit for bit against cv2.undistortPoints (tests/test_oracle.py::test_undistort_vs_cv2).
+ * dist = k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4]]]. */
+static void undistort_point(double fx, double fy, double cx, double cy, const double* k, float uf, float vf, float* xo, float* yo) {
+    const double ifx = 1. / fx, ify = 1. / fy;
+    const double u = uf, v = vf;
+    double x = (u - cx) * ifx, y = (v - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+        if (icdist < 0) {       /* OpenCV >= 3.4 only; 2.4 has no such exit (never taken for physical lenses) */
+            x = (u - cx) * ifx;
+            y = (v - cy) * ify;
+            break;
+        }
+        const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+        const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    const double xx = fx * x + 0. * y + cx;
+    const double yy = 0. * x + fy * y + cy;
+    const double ww = 1. / (0. * x + 0. * y + 1.);
+    *xo = (float)(xx * ww);
+    *yo = (float)(yy * ww);
+}
+
+extern "C" void orc_undistort_keypoints(const orc_keypoint* kps, int n, float fx, float fy, float cx, float cy,
+                                        const float* dist, int ndist, orc_keypoint* out) {
+    double k[12] = {0};
+    for (int i = 0; i < ndist && i < 12; i++) k[i] = dist[i];
+    for (int i = 0; i < n; i++) {
+        out[i] = kps[i];
+        if (ndist > 0 && dist[0] != 0.0)          /* :586-590 */
+            undistort_point(fx, fy, cx, cy, k, kps[i].x, kps[i].y, &out[i].x, &out[i].y);
+    }
+}
+
+/* Frame::ComputeImageBounds, Frame.cc:616-645 -> {mnMinX, mnMaxX, mnMinY, mnMaxY} */
+extern "C" void orc_compute_image_bounds(int cols, int rows, float fx, float fy, float cx, float cy, const float* dist,
+                                         int ndist, float* bounds) {
+    if (ndist > 0 && dist[0] != 0.0) {
+        double k[12] = {0};
+        for (int i = 0; i < ndist && i < 12; i++) k[i] = dist[i];
+        float m[4][2];
+        const float in[4][2] = {{0.0f, 0.0f}, {(float)cols, 0.0f}, {0.0f, (float)rows}, {(float)cols, (float)rows}};
+        for (int i = 0; i < 4; i++) undistort_point(fx, fy, cx, cy, k, in[i][0], in[i][1], &m[i][0], &m[i][1]);
+        bounds[0] = std::min(m[0][0], m[2][0]);
+        bounds[1] = std::max(m[1][0], m[3][0]);
+        bounds[2] = std::min(m[0][1], m[1][1]);
+        bounds[3] = std::max(m[2][1], m[3][1]);
+    } else {
+        bounds[0] = 0.0f; bounds[1] = (float)cols; bounds[2] = 0.0f; bounds[3] = (float)rows;
+    }
+}
+
+/* The per-map-point search loop of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (ORBmatcher.cc:883-943, with ur != NULL),
+ * Fuse(KeyFrame*, Scw, ...) (:1043-1073) and SearchBySim3 (:1193-1226, :1272-1303) on a KeyFrame grid
+ * (KeyFrame::GetFeaturesInArea, KeyFrame.cc:906-945).  valid[i] = the caller's projection gates passed. */
+extern "C" void orc_search_window_top1(const orc_grid* grid, const orc_keypoint* kps_un, const uint8_t* kdesc,
+                                       const float* mvuRight, const float* scale_factors, const float* u, const float* v,
+                                       const float* ur, const int32_t* pred_level, const uint8_t* valid, const uint8_t* mp_desc,
+                                       int n, float th, int th_dist, const float* inv_level_sigma2, int32_t* best_idx,
+                                       int32_t* best_dist) {
+    for (int i = 0; i < n; i++) {
+        best_idx[i] = -1;
+        if (best_dist) best_dist[i] = INT_MAX;
+        if (!valid[i]) continue;
+        const int nPredictedLevel = pred_level[i];
+        const float radius = th * scale_factors[nPredictedLevel];
+        const std::vector<size_t> vIndices = features_in_area(grid, u[i], v[i], radius, -1, -1);
+        if (vIndices.empty()) continue;
+        const uint8_t* dMP = mp_desc + (size_t)i * 32;
+        int bestDist = ur ? 256 : INT_MAX;       /* :885 vs :1045,:1198 */
+        int bestIdx = -1;
+        for (size_t k = 0; k < vIndices.size(); k++) {
+            const size_t idx = vIndices[k];
+            const orc_keypoint& kp = kps_un[idx];
+            const int kpLevel = kp.octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            if (ur) {
+                if (mvuRight[idx] >= 0) {
+                    const float ex = u[i] - kp.x;
+                    const float ey = v[i] - kp.y;
+                    const float er = ur[i] - mvuRight[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+                } else {
+                    const float ex = u[i] - kp.x;
+                    const float ey = v[i] - kp.y;
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+                }
+            }
+            const int dist = orc_descriptor_distance(dMP, kdesc + idx * 32);
+            if (dist < bestDist) {
+                bestDist = dist;
+                bestIdx = (int)idx;
+            }
+        }
+        if (bestDist <= th_dist) {
+            best_idx[i] = bestIdx;
+            if (best_dist) best_dist[i] = bestDist;
+        }
+    }
+}
+
+/* ORBmatcher::SearchBySim3, ORBmatcher.cc:1102-1326, from the projections on (the matrix algebra of :1105-1191 is the
+ * caller's): both searches with TH_HIGH, then the agreement check (:1305-1320). */
+extern "C" int orc_search_by_sim3(const orc_grid* g1, const orc_keypoint* k1, const uint8_t* d1, const float* sf1, int n1,
+                                  const orc_grid* g2, const orc_keypoint* k2, const uint8_t* d2, const float* sf2, int n2,
+                                  const float* u12, const float* v12, const int32_t* level12, const uint8_t* valid12,
+                                  const uint8_t* mp_desc1, const float* u21, const float* v21, const int32_t* level21,
+                                  const uint8_t* valid21, const uint8_t* mp_desc2, float th, int32_t* match12) {
+    std::vector<int32_t> vnMatch1(std::max(n1, 1), -1), vnMatch2(std::max(n2, 1), -1);
+    orc_search_window_top1(g2, k2, d2, NULL, sf2, u12, v12, NULL, level12, valid12, mp_desc1, n1, th, TH_HIGH, NULL, vnMatch1.data(), NULL);
+    orc_search_window_top1(g1, k1, d1, NULL, sf1, u21, v21, NULL, level21, valid21, mp_desc2, n2, th, TH_HIGH, NULL, vnMatch2.data(), NULL);
+    int nFound = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        match12[i1] = -1;
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0) {
+            const int idx1 = vnMatch2[idx2];
+            if (idx1 == i1) {
+                match12[i1] = idx2;
+                nFound++;
+            }
+        }
+    }
+    return nFound;
+}

@@ -82,6 +82,13 @@ def lib(path=None):
     L.orc_distinctive_descriptor.argtypes = [vp, i32, C.POINTER(i32)]
     L.orc_search_by_bow.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
     L.orc_search_for_initialization.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, f32, i32, vp]
+    L.orc_undistort_keypoints.argtypes = [vp, i32, f32, f32, f32, f32, vp, i32, vp]
+    L.orc_undistort_keypoints.restype = None
+    L.orc_compute_image_bounds.argtypes = [i32, i32, f32, f32, f32, f32, vp, i32, vp]
+    L.orc_compute_image_bounds.restype = None
+    L.orc_search_window_top1.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, i32, vp, vp, vp]
+    L.orc_search_window_top1.restype = None
+    L.orc_search_by_sim3.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp]
     L.orc_vocabulary_create.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp]
     L.orc_vocabulary_create.restype = vp
     L.orc_vocabulary_destroy.argtypes = [vp]
@@ -393,3 +400,49 @@ def search_for_initialization(grid2, d2, k1, d1, prev, window, nnratio, check_or
     n = lib().orc_search_for_initialization(grid2.g, _p(grid2.kps), _p(d2), len(grid2.kps), _p(k1), _p(d1), len(k1), _p(prev),
                                             int(window), nnratio, int(check_ori), _p(m12))
     return n, m12, prev
+
+
+def undistort_keypoints(kps, fx, fy, cx, cy, dist):
+    """Frame::UndistortKeyPoints (Frame.cc:584-614)"""
+    kps = _c(kps, KEYPOINT)
+    dist = _c(dist, np.float32).ravel()
+    out = np.zeros(len(kps), KEYPOINT)
+    lib().orc_undistort_keypoints(_p(kps), len(kps), fx, fy, cx, cy, _p(dist) if len(dist) else None, len(dist), _p(out))
+    return out
+
+
+def compute_image_bounds(cols, rows, fx, fy, cx, cy, dist):
+    """Frame::ComputeImageBounds (Frame.cc:616-645) -> (mnMinX, mnMaxX, mnMinY, mnMaxY)"""
+    dist = _c(dist, np.float32).ravel()
+    b = np.zeros(4, np.float32)
+    lib().orc_compute_image_bounds(cols, rows, fx, fy, cx, cy, _p(dist) if len(dist) else None, len(dist), _p(b))
+    return b
+
+
+def search_window_top1(grid, kdesc, u_right, scale_factors, u, v, ur, pred_level, valid, mp_desc, th, th_dist,
+                       inv_level_sigma2=None):
+    """search loop of Fuse x2 / SearchBySim3 (ORBmatcher.cc:883-943, :1043-1073, :1193-1226) -> (best_idx, best_dist)"""
+    f32, i32, u8 = np.float32, np.int32, np.uint8
+    n = len(u)
+    a = [_c(x, t) for x, t in ((kdesc, u8), (u_right, f32), (scale_factors, f32), (u, f32), (v, f32), (pred_level, i32),
+                               (valid, u8), (mp_desc, u8))]
+    urr = _c(ur, f32) if ur is not None else None
+    inv = _c(inv_level_sigma2, f32) if inv_level_sigma2 is not None else None
+    bi, bd = np.full(n, -1, i32), np.zeros(n, i32)
+    lib().orc_search_window_top1(grid.g, _p(grid.kps), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(urr), _p(a[5]),
+                                 _p(a[6]), _p(a[7]), n, th, th_dist, _p(inv), _p(bi), _p(bd))
+    return bi, bd
+
+
+def search_by_sim3(g1, d1, sf1, g2, d2, sf2, q12, q21, th):
+    """q12 = (u, v, level, valid, mp_desc) of KF1's map points projected into KF2; q21 the reverse"""
+    f32, i32, u8 = np.float32, np.int32, np.uint8
+    def prep(q):
+        return [_c(q[0], f32), _c(q[1], f32), _c(q[2], i32), _c(q[3], u8), _c(q[4], u8)]
+    a, b = prep(q12), prep(q21)
+    d1, d2, sf1, sf2 = _c(d1, u8), _c(d2, u8), _c(sf1, f32), _c(sf2, f32)
+    m = np.full(len(g1.kps), -1, i32)
+    n = lib().orc_search_by_sim3(g1.g, _p(g1.kps), _p(d1), _p(sf1), len(g1.kps), g2.g, _p(g2.kps), _p(d2), _p(sf2), len(g2.kps),
+                                 _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(b[0]), _p(b[1]), _p(b[2]), _p(b[3]),
+                                 _p(b[4]), th, _p(m))
+    return n, m

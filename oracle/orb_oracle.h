@@ -157,6 +157,21 @@ int orc_search_by_bow(int mode, const orc_keypoint* k1, const uint8_t* d1, const
 int orc_search_for_initialization(const orc_grid* grid2, const orc_keypoint* k2, const uint8_t* d2, int n2,
                                   const orc_keypoint* k1, const uint8_t* d1, int n1, float* prev,
                                   int windowSize, float mfNNratio, int check_ori, int32_t* vnMatches12);
+/* search loops of Fuse x2 (ORBmatcher.cc:825-1100) and SearchBySim3 (:1102-1326) */
+void orc_search_window_top1(const orc_grid* grid, const orc_keypoint* kps_un, const uint8_t* kdesc, const float* mvuRight,
+                            const float* scale_factors, const float* u, const float* v, const float* ur,
+                            const int32_t* pred_level, const uint8_t* valid, const uint8_t* mp_desc, int n, float th,
+                            int th_dist, const float* inv_level_sigma2, int32_t* best_idx, int32_t* best_dist);
+int orc_search_by_sim3(const orc_grid* g1, const orc_keypoint* k1, const uint8_t* d1, const float* sf1, int n1,
+                       const orc_grid* g2, const orc_keypoint* k2, const uint8_t* d2, const float* sf2, int n2,
+                       const float* u12, const float* v12, const int32_t* level12, const uint8_t* valid12,
+                       const uint8_t* mp_desc1, const float* u21, const float* v21, const int32_t* level21,
+                       const uint8_t* valid21, const uint8_t* mp_desc2, float th, int32_t* match12);
+/* Frame::UndistortKeyPoints / ComputeImageBounds (Frame.cc:584-645) */
+void orc_undistort_keypoints(const orc_keypoint* kps, int n, float fx, float fy, float cx, float cy,
+                             const float* dist, int ndist, orc_keypoint* out);
+void orc_compute_image_bounds(int cols, int rows, float fx, float fy, float cx, float cy, const float* dist,
+                              int ndist, float* bounds);
 /* DBoW2 vocabulary transform (bow_oracle.cpp) */
 typedef struct orc_vocabulary orc_vocabulary;
 orc_vocabulary* orc_vocabulary_create(int k, int L, int weighting, int scoring, int nnodes, const int32_t* parent,

@@ -7,12 +7,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <map>
 #include <set>
 #include <vector>
 
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
+#include "ORBVocabulary.h"
 #include "orb_oracle.h"
 
 extern "C" void viorb_synth_frame(int h, int w, uint64_t seed, uint8_t* out);
@@ -275,6 +277,114 @@ int main() {
         for (int i = 0; i < k1.N; i++)
             if (m12[i] >= 0) { same = same && pi < pairs.size() && pairs[pi].first == (size_t)i && pairs[pi].second == (size_t)m12[i]; pi++; }
         CHECK(nref > 100 && same && pi == pairs.size(), "SearchForTriangulation differs from the oracle");
+    }
+
+    /* ---- SearchByBoW x2 and SearchForInitialization ---- */
+    {
+        KeyFrame k1, k2;
+        Frame F;
+        k1.N = (int)kL.size(); k2.N = (int)kR.size(); F.N = (int)kR.size();
+        k1.mvKeysUn = kL; k2.mvKeysUn = kR; k1.mDescriptors = dL; k2.mDescriptors = dR;
+        F.mvKeys = kR; F.mvKeysUn = kR; F.mDescriptors = dR;
+        F.mnMinX = 0; F.mnMaxX = (float)W; F.mnMinY = 0; F.mnMaxY = (float)H;
+        F.mvScaleFactors = exL.GetScaleFactors();
+        std::vector<MapPoint> pool1(k1.N), pool2(k2.N);
+        k1.mapPoints.assign(k1.N, nullptr); k2.mapPoints.assign(k2.N, nullptr);
+        std::vector<uint8_t> v1(k1.N, 0), v2(k2.N, 0);
+        for (int i = 0; i < k1.N; i++) if (rnd() % 10 < 8) { k1.mapPoints[i] = &pool1[i]; pool1[i].bad = rnd() % 20 == 0; v1[i] = !pool1[i].bad; }
+        for (int i = 0; i < k2.N; i++) if (rnd() % 10 < 8) { k2.mapPoints[i] = &pool2[i]; pool2[i].bad = rnd() % 20 == 0; v2[i] = !pool2[i].bad; }
+        for (int i = 0; i < k1.N; i++) k1.mFeatVec[(unsigned)(kL[i].pt.y / 24) * 3 + 5].push_back(i);
+        for (int i = 0; i < k2.N; i++) { k2.mFeatVec[(unsigned)(kR[i].pt.y / 24) * 3 + 5].push_back(i); F.mFeatVec[(unsigned)(kR[i].pt.y / 24) * 3 + 5].push_back(i); }
+        std::vector<int32_t> id1, p1(1, 0), i1, id2, p2(1, 0), i2;
+        for (auto& kv : k1.mFeatVec) { id1.push_back(kv.first); for (unsigned v : kv.second) i1.push_back(v); p1.push_back((int)i1.size()); }
+        for (auto& kv : k2.mFeatVec) { id2.push_back(kv.first); for (unsigned v : kv.second) i2.push_back(v); p2.push_back((int)i2.size()); }
+        ORBmatcher matcher(0.75f, true);
+        std::vector<MapPoint*> mF, m12;
+        const int nF = matcher.SearchByBoW(&k1, F, mF);
+        std::vector<int32_t> rF(F.N), r12(k1.N);
+        const int nFref = orc_search_by_bow(0, oL.k.data(), oL.d.data(), v1.data(), k1.N, oR.k.data(), oR.d.data(), nullptr, F.N, id1.data(),
+                                            p1.data(), i1.data(), (int)id1.size(), id2.data(), p2.data(), i2.data(), (int)id2.size(), 0.75f, 1,
+                                            rF.data());
+        bool same = nF == nFref && (int)mF.size() == F.N;
+        for (int k = 0; same && k < F.N; k++) same = mF[k] == (rF[k] >= 0 ? k1.mapPoints[rF[k]] : nullptr);
+        CHECK(nFref > 50 && same, "SearchByBoW(KeyFrame, Frame) differs from the oracle");
+        const int n12 = matcher.SearchByBoW(&k1, &k2, m12);
+        const int n12ref = orc_search_by_bow(1, oL.k.data(), oL.d.data(), v1.data(), k1.N, oR.k.data(), oR.d.data(), v2.data(), k2.N, id1.data(),
+                                             p1.data(), i1.data(), (int)id1.size(), id2.data(), p2.data(), i2.data(), (int)id2.size(), 0.75f, 1,
+                                             r12.data());
+        same = n12 == n12ref && (int)m12.size() == k1.N;
+        for (int i = 0; same && i < k1.N; i++) same = m12[i] == (r12[i] >= 0 ? k2.mapPoints[r12[i]] : nullptr);
+        CHECK(n12ref > 30 && same, "SearchByBoW(KeyFrame, KeyFrame) differs from the oracle");
+
+        Frame F1;
+        F1.N = (int)kL.size(); F1.mvKeysUn = kL; F1.mDescriptors = dL;
+        std::vector<cv::Point2f> prev(F1.N);
+        std::vector<float> prevRef((size_t)F1.N * 2);
+        for (int i = 0; i < F1.N; i++) { prev[i].x = kL[i].pt.x; prev[i].y = kL[i].pt.y; prevRef[2 * i] = kL[i].pt.x; prevRef[2 * i + 1] = kL[i].pt.y; }
+        std::vector<int> vn12;
+        ORBmatcher initMatcher(0.9f, true);
+        const int nI = initMatcher.SearchForInitialization(F1, F, prev, vn12, 100);
+        orc_grid* grid = orc_grid_create(oR.k.data(), (int)oR.k.size(), 0, (float)W, 0, (float)H);
+        std::vector<int32_t> rI(F1.N);
+        const int nIref = orc_search_for_initialization(grid, oR.k.data(), oR.d.data(), (int)oR.k.size(), oL.k.data(), oL.d.data(), F1.N,
+                                                        prevRef.data(), 100, 0.9f, 1, rI.data());
+        same = nI == nIref && (int)vn12.size() == F1.N;
+        for (int i = 0; same && i < F1.N; i++) same = vn12[i] == rI[i] && prev[i].x == prevRef[2 * i] && prev[i].y == prevRef[2 * i + 1];
+        CHECK(nIref > 20 && same, "SearchForInitialization differs from the oracle");
+        orc_grid_destroy(grid);
+    }
+
+    /* ---- ORBVocabulary::loadFromTextFile + transform (Frame::ComputeBoW) ---- */
+    {
+        /* a small random tree in the text format of TemplatedVocabulary::saveToTextFile */
+        const int K = 5, LV = 3;
+        std::vector<int32_t> parent(1, 0);
+        std::vector<int> depth(1, 0);
+        std::vector<uint8_t> nd(32, 0);
+        std::vector<double> wt(1, 0.0);
+        for (size_t p = 0; p < parent.size(); p++) {
+            if (depth[p] >= LV) continue;
+            for (int c = 0; c < K; c++) {
+                parent.push_back((int32_t)p); depth.push_back(depth[p] + 1);
+                for (int b = 0; b < 32; b++) nd.push_back((uint8_t)((p ? nd[p * 32 + b] : 0) ^ (rnd() & rnd() & 0xff)));
+                wt.push_back(depth[p] + 1 == LV ? (rnd() % 17 == 0 ? 0.0 : 0.25 + rndf() * 6.0) : 0.0);
+            }
+        }
+        const char* path = "/tmp/viorb_test_voc.txt";
+        {
+            std::ofstream f(path);
+            f.precision(17);
+            f << K << " " << LV << " " << " " << 0 << " " << 0 << std::endl;
+            for (size_t i = 1; i < parent.size(); i++) {
+                f << parent[i] << " " << (depth[i] == LV ? 1 : 0) << " ";
+                for (int b = 0; b < 32; b++) f << (int)nd[i * 32 + b] << " ";
+                f << wt[i] << std::endl;
+            }
+        }
+        ORBVocabulary voc;
+        CHECK(voc.loadFromTextFile(path) && voc.size() == 125, "ORBVocabulary::loadFromTextFile");
+        std::vector<cv::Mat> feats;
+        for (int i = 0; i < dL.rows; i++) feats.push_back(dL.row(i));
+        DBoW2::BowVector bv;
+        DBoW2::FeatureVector fvv;
+        voc.transform(feats, bv, fvv, 2);
+        orc_vocabulary* ov = orc_vocabulary_create(K, LV, 0, 0, (int)parent.size(), parent.data(), nd.data(), wt.data());
+        const int n = dL.rows;
+        std::vector<int32_t> ids(n), fvn(n), fvp(n + 1), fvi(n), wo(n), no(n);
+        std::vector<double> vals(n);
+        int nf = 0;
+        const int nb = orc_bow_transform(ov, oL.d.data(), n, 2, ids.data(), vals.data(), fvn.data(), fvp.data(), fvi.data(), &nf, wo.data(), no.data());
+        bool same = (int)bv.size() == nb && (int)fvv.size() == nf;
+        int k = 0;
+        for (DBoW2::BowVector::const_iterator it = bv.begin(); same && it != bv.end(); ++it, ++k)
+            same = (int)it->first == ids[k] && memcmp(&it->second, &vals[k], 8) == 0;
+        k = 0;
+        for (DBoW2::FeatureVector::const_iterator it = fvv.begin(); same && it != fvv.end(); ++it, ++k) {
+            same = (int)it->first == fvn[k] && (int)it->second.size() == fvp[k + 1] - fvp[k];
+            for (size_t j = 0; same && j < it->second.size(); j++) same = (int)it->second[j] == fvi[fvp[k] + j];
+        }
+        CHECK(nb > 20 && same, "ORBVocabulary::transform differs from the oracle");
+        orc_vocabulary_destroy(ov);
     }
 
     orc_extractor_destroy(oL.e);

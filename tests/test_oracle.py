@@ -170,3 +170,40 @@ def test_octree_list_order_model(oracle):
         sel = oracle.distribute_octree(c, 16, 736, 16, 464, N)
         assert len(set(sel.tolist())) == len(sel)
         assert len(sel) <= N + 3 or n <= N
+
+
+EUROC_K = (458.654, 457.296, 367.215, 248.375)                 # Examples/Monocular/EuRoC.yaml
+EUROC_DIST = [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05]
+TUM1_K = (517.306408, 516.469215, 318.643040, 255.313989)     # Examples/Monocular/TUM1.yaml (with k3)
+TUM1_DIST = [0.262383, -0.953104, -0.005358, 0.002628, 1.163314]
+
+
+@pytest.mark.parametrize("K,dist,size", [(EUROC_K, EUROC_DIST, (752, 480)), (TUM1_K, TUM1_DIST, (640, 480)),
+                                         (EUROC_K, [0.0, 0.1, 0.0, 0.0], (752, 480))])
+def test_undistort_vs_cv2(oracle, K, dist, size):
+    """Frame::UndistortKeyPoints / ComputeImageBounds restatement is bit-equal to cv2.undistortPoints (the call of
+    Frame.cc:602 with R = I, P = K), incl. the no-distortion shortcut of :586"""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    n = 4000
+    kps = np.zeros(n, oracle.KEYPOINT)
+    kps["x"] = rng.uniform(0, size[0], n).astype(np.float32)
+    kps["y"] = rng.uniform(0, size[1], n).astype(np.float32)
+    kps["octave"] = rng.integers(0, 8, n)
+    got = oracle.undistort_keypoints(kps, *K, dist)
+    Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], np.float32)
+    D = np.array(dist, np.float32).reshape(-1, 1)
+    if D[0, 0] != 0.0:
+        pts = np.stack([kps["x"], kps["y"]], 1).reshape(-1, 1, 2)
+        ref = cv2.undistortPoints(pts, Km, D, None, Km).reshape(-1, 2)
+        corners = np.array([[0, 0], [size[0], 0], [0, size[1]], [size[0], size[1]]], np.float32).reshape(-1, 1, 2)
+        c = cv2.undistortPoints(corners, Km, D, None, Km).reshape(-1, 2)
+        bref = np.array([min(c[0, 0], c[2, 0]), max(c[1, 0], c[3, 0]), min(c[0, 1], c[1, 1]), max(c[2, 1], c[3, 1])], np.float32)
+    else:
+        ref = np.stack([kps["x"], kps["y"]], 1)
+        bref = np.array([0, size[0], 0, size[1]], np.float32)
+    assert (got["x"].view(np.uint32) == ref[:, 0].view(np.uint32)).all()
+    assert (got["y"].view(np.uint32) == ref[:, 1].view(np.uint32)).all()
+    assert (got["octave"] == kps["octave"]).all()
+    b = oracle.compute_image_bounds(size[0], size[1], *K, dist)
+    assert (b.view(np.uint32) == bref.view(np.uint32)).all()

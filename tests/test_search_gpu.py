@@ -273,3 +273,85 @@ def test_search_for_initialization(api, ctx, oracle, stereo, window, check_ori, 
     fi2.close()
     assert n_ref > 20
     assert n == n_ref and (m12 == m_ref).all() and (p.view(np.uint32) == p_ref.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("K,dist,size", [((458.654, 457.296, 367.215, 248.375), [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], (752, 480)),
+                                         ((517.306408, 516.469215, 318.643040, 255.313989), [0.262383, -0.953104, -0.005358, 0.002628, 1.163314], (640, 480)),
+                                         ((718.856, 718.856, 607.1928, 185.2157), [0.0, 0.0, 0.0, 0.0], (1241, 376))])
+def test_undistort_and_grid_on_device(api, ctx, oracle, stereo, K, dist, size):
+    """Frame::UndistortKeyPoints, ComputeImageBounds and AssignFeaturesToGrid on the device (Frame.cc:584-645, 410-425):
+    mvKeysUn and the bounds bit-equal to the oracle (itself pinned on cv2.undistortPoints), and the grid built from
+    the raw keypoints answers GetFeaturesInArea like the oracle grid of the undistorted ones"""
+    s = stereo
+    rng = np.random.default_rng(9)
+    kps = s["kl"].copy()
+    kps["x"] = (kps["x"] * (size[0] / 1241.0)).astype(np.float32)
+    kps["y"] = (kps["y"] * (size[1] / 376.0)).astype(np.float32)
+    ref = oracle.undistort_keypoints(kps, *K, dist)
+    got = api.UndistortKeyPoints(ctx, kps, K, dist)
+    assert got.tobytes() == ref.tobytes()
+    bref = oracle.compute_image_bounds(size[0], size[1], *K, dist)
+    b = api.ComputeImageBounds(ctx, size[0], size[1], K, dist)
+    assert (b.view(np.uint32) == bref.view(np.uint32)).all()
+    sf = s["ol"].scale_factors()
+    fi = api.FrameIndex.from_distorted(ctx, kps, s["dl"], None, K, dist, size, sf)
+    k_un, bounds = fi.keys()
+    assert k_un.tobytes() == ref.tobytes() and (bounds.view(np.uint32) == bref.view(np.uint32)).all()
+    g = oracle.Grid(ref, *[float(v) for v in bref])
+    for _ in range(40):
+        x, y = float(rng.uniform(-20, size[0] + 20)), float(rng.uniform(-20, size[1] + 20))
+        r = float(rng.choice([5.0, 20.0, 60.0]))
+        a, c = fi.GetFeaturesInArea(x, y, r), g.features_in_area(x, y, r)
+        assert len(a) == len(c) and (a == c).all()
+    fi.close()
+
+
+def _window_queries(k_src, d_src, k_dst, seed, disp):
+    """map points of `src` keypoints projected near the corresponding place in `dst` (stereo pair: shift by disparity)"""
+    rng = np.random.default_rng(seed)
+    n = len(k_src)
+    u = (k_src["x"] - disp + rng.normal(0, 1.5, n)).astype(np.float32)
+    v = (k_src["y"] + rng.normal(0, 1.0, n)).astype(np.float32)
+    level = np.clip(k_src["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
+    valid = (rng.random(n) < 0.85).astype(np.uint8)
+    return u, v, level, valid, S.flip_bits(d_src, rng, 20)
+
+
+@pytest.mark.parametrize("gates,th", [(True, 3.0), (False, 4.0), (False, 10.0)])
+def test_search_window_top1(api, ctx, oracle, stereo, gates, th):
+    """search loop of both ORBmatcher::Fuse overloads (ORBmatcher.cc:883-943 with the chi-square gates, :1043-1073)"""
+    s = stereo
+    h, w = s["shape"]
+    sf = s["ol"].scale_factors()
+    inv_sigma2 = (1.0 / (sf * sf)).astype(np.float32)
+    rng = np.random.default_rng(2)
+    kr, dr, kl, dl = s["kr"], s["dr"], s["kl"], s["dl"]
+    u_right = np.where(rng.random(len(kr)) < 0.5, kr["x"] - rng.uniform(2, 40, len(kr)), -1).astype(np.float32)
+    u, v, level, valid, mpd = _window_queries(kl, dl, kr, 3, 20.0)
+    ur = (u - rng.uniform(2, 40, len(u))).astype(np.float32) if gates else None
+    g = oracle.Grid(kr, 0.0, float(w), 0.0, float(h))
+    rb, rd = oracle.search_window_top1(g, dr, u_right, sf, u, v, ur, level, valid, mpd, th, 50, inv_sigma2 if gates else None)
+    fi = api.FrameIndex(ctx, kr, dr, u_right, (0.0, float(w), 0.0, float(h)), sf)
+    m = api.ORBmatcher(ctx=ctx)
+    bi, bd = m.SearchWindowTop1(fi, u, v, ur, level, valid, mpd, th, 50, inv_sigma2 if gates else None)
+    fi.close()
+    assert (rb >= 0).sum() > (5 if gates else 30)
+    assert (bi == rb).all() and (bd[rb >= 0] == rd[rb >= 0]).all()
+
+
+def test_search_by_sim3(api, ctx, oracle, stereo):
+    """ORBmatcher::SearchBySim3 (ORBmatcher.cc:1102-1326): both directional searches and the agreement check"""
+    s = stereo
+    h, w = s["shape"]
+    sf = s["ol"].scale_factors()
+    kl, dl, kr, dr = s["kl"], s["dl"], s["kr"], s["dr"]
+    q12 = _window_queries(kl, dl, kr, 5, 20.0)
+    q21 = _window_queries(kr, dr, kl, 6, -20.0)
+    g1, g2 = oracle.Grid(kl, 0.0, float(w), 0.0, float(h)), oracle.Grid(kr, 0.0, float(w), 0.0, float(h))
+    n_ref, m_ref = oracle.search_by_sim3(g1, dl, sf, g2, dr, sf, q12, q21, 25.0)
+    f1 = api.FrameIndex(ctx, kl, dl, None, (0.0, float(w), 0.0, float(h)), sf)
+    f2 = api.FrameIndex(ctx, kr, dr, None, (0.0, float(w), 0.0, float(h)), sf)
+    n, m12 = api.ORBmatcher(ctx=ctx).SearchBySim3(f1, f2, q12, q21, 25.0)
+    f1.close(); f2.close()
+    assert n_ref > 20
+    assert n == n_ref and (m12 == m_ref).all()

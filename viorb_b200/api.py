@@ -68,10 +68,16 @@ def lib():
         "viorb_stereo_match": [vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, f32, f32, vp, vp],
         "viorb_frame_index_create": [vp, vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, pp],
         "viorb_frame_index_destroy": [vp],
+        "viorb_frame_index_create_distorted": [vp, vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, i32, i32, vp, i32, pp],
+        "viorb_frame_index_keys": [vp, vp, vp],
+        "viorb_undistort_keypoints": [vp, vp, i32, f32, f32, f32, f32, vp, i32, vp],
+        "viorb_compute_image_bounds": [vp, i32, i32, f32, f32, f32, f32, vp, i32, vp],
         "viorb_frame_features_in_area": [vp, f32, f32, f32, i32, i32, vp, i32, pi],
         "viorb_search_by_projection_local": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, vp, pi],
         "viorb_search_by_projection_frame": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, i32, i32, i32, vp, pi],
         "viorb_distinctive_descriptors": [vp, vp, vp, i32, vp, vp],
+        "viorb_search_window_top1": [vp, vp, vp, vp, vp, vp, vp, i32, f32, i32, vp, vp, vp],
+        "viorb_search_by_sim3": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, pi],
         "viorb_search_by_bow": [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp, pi],
         "viorb_search_for_initialization": [vp, vp, vp, i32, vp, i32, f32, i32, vp, pi],
         "viorb_vocabulary_create": [vp, i32, i32, i32, i32, i32, vp, vp, vp, pp],
@@ -294,6 +300,32 @@ class FrameIndex:
         self.h = h
         self.n = len(self.kps)
 
+    @classmethod
+    def from_distorted(cls, ctx, kps, desc, u_right, K, dist_coef, image_size, scale_factors):
+        """Frame::UndistortKeyPoints + ComputeImageBounds + AssignFeaturesToGrid on the device (Frame.cc:584-645,410-425).
+        K = (fx, fy, cx, cy); image_size = (cols, rows)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.kps = np.ascontiguousarray(kps, KEYPOINT)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.u_right = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        dc = np.ascontiguousarray(dist_coef, np.float32).ravel()
+        h = C.c_void_p()
+        _ck(lib().viorb_frame_index_create_distorted(ctx.h, _ptr(self.kps), _ptr(self.desc), _ptr(self.u_right), len(self.kps),
+                                                     K[0], K[1], K[2], K[3], _ptr(dc) if len(dc) else None, len(dc),
+                                                     image_size[0], image_size[1], _ptr(sf), len(sf), C.byref(h)))
+        self.h = h
+        self.n = len(self.kps)
+        return self
+
+    def keys(self):
+        """-> (mvKeysUn, (mnMinX, mnMaxX, mnMinY, mnMaxY))"""
+        k = np.zeros(self.n, KEYPOINT)
+        b = np.zeros(4, np.float32)
+        _ck(lib().viorb_frame_index_keys(self.h, _ptr(k) if self.n else None, _ptr(b)))
+        return k, b
+
     def close(self):
         if getattr(self, "h", None):
             lib().viorb_frame_index_destroy(self.h)
@@ -409,6 +441,32 @@ class ORBmatcher:
                                                   self.mfNNratio, int(self.mbCheckOrientation), _ptr(m12), C.byref(n)))
         return n.value, m12, prev
 
+    def SearchWindowTop1(self, kf, u, v, ur, pred_level, valid, mp_desc, th, th_dist, inv_level_sigma2=None):
+        """search loop of Fuse(KeyFrame*, vpMapPoints, th) (ur given) / Fuse(KeyFrame*, Scw, ...) (ur None):
+        -> (bestIdx per map point or -1, bestDist)"""
+        f32, i32, u8 = np.float32, np.int32, np.uint8
+        a = [np.ascontiguousarray(x, t) for x, t in ((u, f32), (v, f32), (pred_level, i32), (valid, u8), (mp_desc, u8))]
+        urr = np.ascontiguousarray(ur, f32) if ur is not None else None
+        inv = np.ascontiguousarray(inv_level_sigma2, f32) if inv_level_sigma2 is not None else None
+        n = len(a[0])
+        bi, bd = np.full(n, -1, i32), np.zeros(n, i32)
+        _ck(lib().viorb_search_window_top1(kf.h, _ptr(a[0]), _ptr(a[1]), _ptr(urr), _ptr(a[2]), _ptr(a[3]), _ptr(a[4]), n, th,
+                                           th_dist, _ptr(inv), _ptr(bi), _ptr(bd)))
+        return bi, bd
+
+    def SearchBySim3(self, kf1, kf2, q12, q21, th):
+        """q12 = (u, v, level, valid, mp_desc) of KF1's map points projected into KF2, q21 the reverse
+        -> (nFound, idx2 per keypoint of KF1 or -1)"""
+        f32, i32, u8 = np.float32, np.int32, np.uint8
+        def prep(q):
+            return [np.ascontiguousarray(q[0], f32), np.ascontiguousarray(q[1], f32), np.ascontiguousarray(q[2], i32),
+                    np.ascontiguousarray(q[3], u8), np.ascontiguousarray(q[4], u8)]
+        a, b = prep(q12), prep(q21)
+        m = np.full(kf1.n, -1, i32)
+        n = C.c_int()
+        _ck(lib().viorb_search_by_sim3(kf1.h, kf2.h, *[_ptr(x) for x in a], *[_ptr(x) for x in b], th, _ptr(m), C.byref(n)))
+        return n.value, m
+
     def ComputeDistinctiveDescriptors(self, obs_desc, obs_ptr):
         """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:249-314) over a CSR batch of map points:
         returns (BestIdx per point, BestMedian per point)."""
@@ -419,6 +477,25 @@ class ORBmatcher:
         _ck(lib().viorb_distinctive_descriptors(self.ctx.h, _ptr(d) if len(d) else None, _ptr(p), len(best),
                                                 _ptr(best), _ptr(med)))
         return best, med
+
+
+def UndistortKeyPoints(ctx, kps, K, dist_coef):
+    """Frame::UndistortKeyPoints (Frame.cc:584-614); K = (fx, fy, cx, cy)"""
+    k = np.ascontiguousarray(kps, KEYPOINT)
+    dc = np.ascontiguousarray(dist_coef, np.float32).ravel()
+    out = np.zeros(len(k), KEYPOINT)
+    _ck(lib().viorb_undistort_keypoints(ctx.h, _ptr(k), len(k), K[0], K[1], K[2], K[3], _ptr(dc) if len(dc) else None, len(dc),
+                                        _ptr(out)))
+    return out
+
+
+def ComputeImageBounds(ctx, cols, rows, K, dist_coef):
+    """Frame::ComputeImageBounds (Frame.cc:616-645) -> (mnMinX, mnMaxX, mnMinY, mnMaxY)"""
+    dc = np.ascontiguousarray(dist_coef, np.float32).ravel()
+    b = np.zeros(4, np.float32)
+    _ck(lib().viorb_compute_image_bounds(ctx.h, cols, rows, K[0], K[1], K[2], K[3], _ptr(dc) if len(dc) else None, len(dc),
+                                         _ptr(b)))
+    return b
 
 
 class ORBVocabulary:

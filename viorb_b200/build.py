@@ -20,7 +20,7 @@ NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nv
 CXX = os.environ.get("CXX") or shutil.which("g++") or "g++"
 
 CUDA_SOURCES = ["extractor_kernels.cu", "matcher_kernels.cu", "c_api.cu", "c_api_match.cu", "search_kernels.cu", "bow_kernels.cu"]
-HOST_SOURCES = ["ORBextractor.cc", "ORBmatcher.cc"]   # C++ shims compiled into the same library
+HOST_SOURCES = ["ORBextractor.cc", "ORBmatcher.cc", "ORBVocabulary.cc"]   # C++ shims compiled into the same library
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

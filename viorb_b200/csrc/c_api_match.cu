@@ -51,6 +51,11 @@ int viorb_launch_search_init(const FrameIndexDev& f2, const viorb_keypoint* k1, 
                              int* d_start, int* d_count, unsigned long long* d_cursor, int* d_overflow, int* d_matchedDist,
                              int* d_matches21, int* d_binOf, int* d_matches12, int* d_nmatches, cudaStream_t s);
 
+int viorb_launch_search_window(const FrameIndexDev& fi, const float* u, const float* v, const float* ur, const int* level,
+                               const uint8_t* valid, const uint8_t* desc, int n, float th, int thDist, const float* invSigma2,
+                               int nlevels, int* d_bestIdx, int* d_bestDist, cudaStream_t s);
+int viorb_launch_sim3_agree(const int* d_m1, const int* d_m2, int n1, int* d_match12, int* d_nfound, cudaStream_t s);
+
 namespace {
 
 /* bump allocator over one device scratch buffer: a call uploads all its inputs into a single arena */
@@ -145,11 +150,21 @@ int viorb_stereo_match(viorb_extractor* left, int frame_l, viorb_extractor* righ
     return VIORB_OK;
 }
 
-int viorb_frame_index_create(viorb_ctx* c, const viorb_keypoint* kps_un, const uint8_t* desc, const float* u_right, int n,
-                             float min_x, float max_x, float min_y, float max_y, const float* scale_factors, int nlevels,
-                             viorb_frame_index** out) {
-    if (!c || !out || n < 0 || (n > 0 && (!kps_un || !desc)) || !scale_factors || nlevels < 1 || nlevels > 12)
-        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+static int make_undistort_params(float fx, float fy, float cx, float cy, const float* dist, int ndist, UndistortParams* p) {
+    if (ndist != 0 && ndist != 4 && ndist != 5 && ndist != 8 && ndist != 12) return viorb_fail(VIORB_ERR_UNSUPPORTED, "distortion model with %d coefficients", ndist);
+    if (ndist > 0 && !dist) return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    memset(p, 0, sizeof(*p));
+    p->fx = fx; p->fy = fy; p->cx = cx; p->cy = cy;
+    p->ifx = 1.0 / (double)fx; p->ify = 1.0 / (double)fy;
+    for (int i = 0; i < ndist; i++) p->k[i] = (double)dist[i];
+    p->active = ndist > 0 && dist[0] != 0.0f;            /* src/Frame.cc:586 */
+    return VIORB_OK;
+}
+
+/* shared by the two constructors: kps are already undistorted (und == NULL) or are undistorted on the device */
+static int frame_index_build(viorb_ctx* c, const viorb_keypoint* kps, const uint8_t* desc, const float* u_right, int n,
+                             const UndistortParams* und, int cols, int rows, const float* bounds_in,
+                             const float* scale_factors, int nlevels, viorb_frame_index** out) {
     if (n >= (1 << 20)) return viorb_fail(VIORB_ERR_UNSUPPORTED, "more than 2^20 keypoints in one frame");
     *out = nullptr;
     int rc;
@@ -157,36 +172,118 @@ int viorb_frame_index_create(viorb_ctx* c, const viorb_keypoint* kps_un, const u
     viorb_frame_index* fi = new (std::nothrow) viorb_frame_index();
     if (!fi) return viorb_fail(VIORB_ERR_INVALID, "out of host memory");
     const int nn = std::max(n, 1);
-    const size_t bytes = pad((size_t)nn * sizeof(viorb_keypoint)) + pad((size_t)nn * 32) + pad((size_t)nn * 4) * 3 +
-                         pad((64 * 48 + 1) * 4) + 4096;
+    const size_t bytes = pad((size_t)nn * sizeof(viorb_keypoint)) * 2 + pad((size_t)nn * 32) + pad((size_t)nn * 4) * 3 +
+                         pad((64 * 48 + 1) * 4) + pad(64) + 4096;
     if (cudaMalloc((void**)&fi->mem, bytes) != cudaSuccess) { delete fi; return viorb_fail(VIORB_ERR_CUDA, "cudaMalloc failed"); }
     Arena a;
     a.base = fi->mem; a.cap = bytes;
     viorb_keypoint* dk = a.take<viorb_keypoint>(nn);
+    viorb_keypoint* draw = a.take<viorb_keypoint>(nn);
     uint8_t* dd = a.take<uint8_t>((size_t)nn * 32);
     float* dur = a.take<float>(nn);
     int* cellOf = a.take<int>(nn);
     int* cellItems = a.take<int>(nn);
     int* cellStart = a.take<int>(64 * 48 + 1);
+    float* dbounds = a.take<float>(4);
     fi->ctx = c; fi->n = n; fi->cellOf = cellOf;
     cudaStream_t s = viorb_ctx_stream(c);
     std::vector<float> ur;
     if (!u_right) { ur.assign(nn, -1.0f); u_right = ur.data(); }
-    if ((rc = upload(c, dk, kps_un, n)) || (rc = upload(c, dd, desc, (size_t)n * 32)) || (rc = upload(c, dur, u_right, n))) {
+    if ((rc = upload(c, und ? draw : dk, kps, n)) || (rc = upload(c, dd, desc, (size_t)n * 32)) || (rc = upload(c, dur, u_right, n))) {
         cudaFree(fi->mem); delete fi; return rc;
+    }
+    float b[4] = {0, 0, 0, 0};
+    if (und) {
+        /* Frame::UndistortKeyPoints + ComputeImageBounds on the device; only the four bounds come back */
+        viorb_ctx_add_launches(c, viorb_launch_undistort(*und, draw, n, dk, s));
+        viorb_ctx_add_launches(c, viorb_launch_image_bounds(*und, cols, rows, dbounds, s));
+        cudaError_t e = cudaMemcpyAsync(b, dbounds, sizeof(b), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { cudaFree(fi->mem); delete fi; return viorb_fail(VIORB_ERR_CUDA, "undistort: %s", cudaGetErrorString(e)); }
+    } else {
+        memcpy(b, bounds_in, sizeof(b));
     }
     FrameIndexDev& d = fi->dev;
     memset(&d, 0, sizeof(d));
     d.kps = dk; d.desc = dd; d.uRight = dur; d.cellStart = cellStart; d.cellItems = cellItems; d.n = n;
-    d.minX = min_x; d.maxX = max_x; d.minY = min_y; d.maxY = max_y;
-    d.invW = 64.0f / (max_x - min_x);         /* mfGridElementWidthInv, src/Frame.cc:181 */
-    d.invH = 48.0f / (max_y - min_y);
+    d.minX = b[0]; d.maxX = b[1]; d.minY = b[2]; d.maxY = b[3];
+    d.invW = 64.0f / (d.maxX - d.minX);         /* mfGridElementWidthInv, src/Frame.cc:181 */
+    d.invH = 48.0f / (d.maxY - d.minY);
     d.nlevels = nlevels;
     for (int l = 0; l < nlevels; l++) d.scale[l] = scale_factors[l];
-    viorb_ctx_add_launches(c, viorb_launch_grid_build(dk, n, min_x, min_y, d.invW, d.invH, cellOf, cellStart, cellItems, s));
+    viorb_ctx_add_launches(c, viorb_launch_grid_build(dk, n, d.minX, d.minY, d.invW, d.invH, cellOf, cellStart, cellItems, s));
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { cudaFree(fi->mem); delete fi; return viorb_fail(VIORB_ERR_CUDA, "grid build: %s", cudaGetErrorString(e)); }
     *out = fi;
+    return VIORB_OK;
+}
+
+int viorb_frame_index_create(viorb_ctx* c, const viorb_keypoint* kps_un, const uint8_t* desc, const float* u_right, int n,
+                             float min_x, float max_x, float min_y, float max_y, const float* scale_factors, int nlevels,
+                             viorb_frame_index** out) {
+    if (!c || !out || n < 0 || (n > 0 && (!kps_un || !desc)) || !scale_factors || nlevels < 1 || nlevels > 12)
+        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    const float b[4] = {min_x, max_x, min_y, max_y};
+    return frame_index_build(c, kps_un, desc, u_right, n, nullptr, 0, 0, b, scale_factors, nlevels, out);
+}
+
+int viorb_frame_index_create_distorted(viorb_ctx* c, const viorb_keypoint* kps, const uint8_t* desc, const float* u_right, int n,
+                                       float fx, float fy, float cx, float cy, const float* dist_coef, int ndist, int cols,
+                                       int rows, const float* scale_factors, int nlevels, viorb_frame_index** out) {
+    if (!c || !out || n < 0 || (n > 0 && (!kps || !desc)) || !scale_factors || nlevels < 1 || nlevels > 12 || cols <= 0 || rows <= 0)
+        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    UndistortParams p;
+    int rc;
+    if ((rc = make_undistort_params(fx, fy, cx, cy, dist_coef, ndist, &p))) return rc;
+    return frame_index_build(c, kps, desc, u_right, n, &p, cols, rows, nullptr, scale_factors, nlevels, out);
+}
+
+int viorb_frame_index_keys(viorb_frame_index* fi, viorb_keypoint* kps_un, float bounds[4]) {
+    if (!fi) return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    int rc;
+    if ((rc = viorb_ctx_bind(fi->ctx))) return rc;
+    if (kps_un && fi->n > 0) {
+        VCU(cudaMemcpyAsync(kps_un, fi->dev.kps, (size_t)fi->n * sizeof(viorb_keypoint), cudaMemcpyDeviceToHost, viorb_ctx_stream(fi->ctx)));
+        VCU(cudaStreamSynchronize(viorb_ctx_stream(fi->ctx)));
+    }
+    if (bounds) { bounds[0] = fi->dev.minX; bounds[1] = fi->dev.maxX; bounds[2] = fi->dev.minY; bounds[3] = fi->dev.maxY; }
+    return VIORB_OK;
+}
+
+int viorb_undistort_keypoints(viorb_ctx* c, const viorb_keypoint* kps, int n, float fx, float fy, float cx, float cy,
+                              const float* dist_coef, int ndist, viorb_keypoint* kps_un) {
+    if (!c || n < 0 || (n > 0 && (!kps || !kps_un))) return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    UndistortParams p;
+    int rc;
+    if ((rc = make_undistort_params(fx, fy, cx, cy, dist_coef, ndist, &p))) return rc;
+    if (n == 0) return VIORB_OK;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    Arena a;
+    if ((rc = viorb_ctx_scratch(c, 2 * pad((size_t)n * sizeof(viorb_keypoint)) + 1024, &a.base))) return rc;
+    viorb_keypoint* din = a.take<viorb_keypoint>(n);
+    viorb_keypoint* dout = a.take<viorb_keypoint>(n);
+    if ((rc = upload(c, din, kps, n))) return rc;
+    viorb_ctx_add_launches(c, viorb_launch_undistort(p, din, n, dout, viorb_ctx_stream(c)));
+    VCU(cudaGetLastError());
+    VCU(cudaMemcpyAsync(kps_un, dout, (size_t)n * sizeof(viorb_keypoint), cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    return VIORB_OK;
+}
+
+int viorb_compute_image_bounds(viorb_ctx* c, int cols, int rows, float fx, float fy, float cx, float cy, const float* dist_coef,
+                               int ndist, float bounds[4]) {
+    if (!c || !bounds || cols <= 0 || rows <= 0) return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    UndistortParams p;
+    int rc;
+    if ((rc = make_undistort_params(fx, fy, cx, cy, dist_coef, ndist, &p))) return rc;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    Arena a;
+    if ((rc = viorb_ctx_scratch(c, 1024, &a.base))) return rc;
+    float* db = a.take<float>(4);
+    viorb_ctx_add_launches(c, viorb_launch_image_bounds(p, cols, rows, db, viorb_ctx_stream(c)));
+    VCU(cudaGetLastError());
+    VCU(cudaMemcpyAsync(bounds, db, 16, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
     return VIORB_OK;
 }
 
@@ -451,6 +548,86 @@ int viorb_search_for_initialization(viorb_frame_index* f2, const viorb_keypoint*
     VCU(cudaMemcpyAsync(&ovf, dovf, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
     VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
     if (ovf) return viorb_fail(VIORB_ERR_CAPACITY, "candidate pool overflow");
+    return VIORB_OK;
+}
+
+/* uploads one direction's queries into the arena and launches the windowed top-1 search */
+static int window_search_upload(viorb_ctx* c, Arena& a, viorb_frame_index* kf, const float* u, const float* v, const float* ur,
+                                const int32_t* level, const uint8_t* valid, const uint8_t* desc, int n, float th, int thDist,
+                                const float* invSigma2, int** d_best, int** d_dist) {
+    const int m = std::max(n, 1);
+    float* du = a.take<float>(m); float* dv = a.take<float>(m); float* dr = a.take<float>(m);
+    int* dl = a.take<int>(m); uint8_t* dva = a.take<uint8_t>(m); uint8_t* dde = a.take<uint8_t>((size_t)m * 32);
+    *d_best = a.take<int>(m);
+    *d_dist = a.take<int>(m);
+    int rc;
+    if ((rc = upload(c, du, u, n)) || (rc = upload(c, dv, v, n)) || (ur && (rc = upload(c, dr, ur, n))) || (rc = upload(c, dl, level, n)) ||
+        (rc = upload(c, dva, valid, n)) || (rc = upload(c, dde, desc, (size_t)n * 32)))
+        return rc;
+    viorb_ctx_add_launches(c, viorb_launch_search_window(kf->dev, du, dv, ur ? dr : nullptr, dl, dva, dde, n, th, thDist, invSigma2,
+                                                         kf->dev.nlevels, *d_best, *d_dist, viorb_ctx_stream(c)));
+    return VIORB_OK;
+}
+
+static size_t window_search_bytes(int n) {
+    const size_t m = (size_t)std::max(n, 1);
+    return 6 * pad(m * 4) + pad(m) + pad(m * 32) + 4096;
+}
+
+static int check_levels(const int32_t* level, const uint8_t* valid, int n, int nlevels) {
+    for (int i = 0; i < n; i++)
+        if (valid[i] && (level[i] < 0 || level[i] >= nlevels)) return viorb_fail(VIORB_ERR_INVALID, "query %d: level %d out of range", i, level[i]);
+    return VIORB_OK;
+}
+
+int viorb_search_window_top1(viorb_frame_index* kf, const float* u, const float* v, const float* ur, const int32_t* pred_level,
+                             const uint8_t* valid, const uint8_t* mp_desc, int n, float th, int th_dist,
+                             const float* inv_level_sigma2, int32_t* best_idx, int32_t* best_dist) {
+    if (!kf || n < 0 || !best_idx || (n > 0 && (!u || !v || !pred_level || !valid || !mp_desc)) || (ur && !inv_level_sigma2))
+        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    if (kf->n >= (1 << 24)) return viorb_fail(VIORB_ERR_UNSUPPORTED, "more than 2^24 keypoints");
+    if (n == 0) return VIORB_OK;
+    viorb_ctx* c = kf->ctx;
+    int rc;
+    if ((rc = check_levels(pred_level, valid, n, kf->dev.nlevels))) return rc;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    Arena a;
+    if ((rc = viorb_ctx_scratch(c, window_search_bytes(n), &a.base))) return rc;
+    int *db = nullptr, *dd = nullptr;
+    if ((rc = window_search_upload(c, a, kf, u, v, ur, pred_level, valid, mp_desc, n, th, th_dist, inv_level_sigma2, &db, &dd))) return rc;
+    VCU(cudaGetLastError());
+    VCU(cudaMemcpyAsync(best_idx, db, (size_t)n * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    if (best_dist) VCU(cudaMemcpyAsync(best_dist, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    return VIORB_OK;
+}
+
+int viorb_search_by_sim3(viorb_frame_index* kf1, viorb_frame_index* kf2, const float* u12, const float* v12,
+                         const int32_t* level12, const uint8_t* valid12, const uint8_t* mp_desc1, const float* u21,
+                         const float* v21, const int32_t* level21, const uint8_t* valid21, const uint8_t* mp_desc2, float th,
+                         int32_t* match12, int* nfound) {
+    if (!kf1 || !kf2 || !match12 || !nfound || kf1->ctx != kf2->ctx) return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    const int n1 = kf1->n, n2 = kf2->n;
+    if ((n1 > 0 && (!u12 || !v12 || !level12 || !valid12 || !mp_desc1)) || (n2 > 0 && (!u21 || !v21 || !level21 || !valid21 || !mp_desc2)))
+        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    if (n1 >= (1 << 24) || n2 >= (1 << 24)) return viorb_fail(VIORB_ERR_UNSUPPORTED, "more than 2^24 keypoints");
+    viorb_ctx* c = kf1->ctx;
+    int rc;
+    if ((rc = check_levels(level12, valid12, n1, kf2->dev.nlevels)) || (rc = check_levels(level21, valid21, n2, kf1->dev.nlevels))) return rc;
+    if ((rc = viorb_ctx_bind(c))) return rc;
+    Arena a;
+    if ((rc = viorb_ctx_scratch(c, window_search_bytes(n1) + window_search_bytes(n2) + pad((size_t)std::max(n1, 1) * 4) + 1024, &a.base))) return rc;
+    int *dm1 = nullptr, *dm2 = nullptr, *dd = nullptr;
+    /* KF1's map points searched in KF2 (:1149-1226), KF2's in KF1 (:1228-1303), TH_HIGH = 100 */
+    if ((rc = window_search_upload(c, a, kf2, u12, v12, nullptr, level12, valid12, mp_desc1, n1, th, 100, nullptr, &dm1, &dd))) return rc;
+    if ((rc = window_search_upload(c, a, kf1, u21, v21, nullptr, level21, valid21, mp_desc2, n2, th, 100, nullptr, &dm2, &dd))) return rc;
+    int* dmatch = a.take<int>(std::max(n1, 1));
+    int* dn = a.take<int>(4);
+    viorb_ctx_add_launches(c, viorb_launch_sim3_agree(dm1, dm2, n1, dmatch, dn, viorb_ctx_stream(c)));
+    VCU(cudaGetLastError());
+    VCU(cudaMemcpyAsync(match12, dmatch, (size_t)n1 * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaMemcpyAsync(nfound, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
+    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
     return VIORB_OK;
 }
 

@@ -45,4 +45,15 @@ struct FrameIndexDev {
     int nlevels;
 };
 
+
+/* Frame::UndistortKeyPoints / ComputeImageBounds (src/Frame.cc:584-645): cv::undistortPoints(mat, mat, mK, mDistCoef,
+ * cv::Mat(), mK) in double precision, five fixed-point iterations */
+struct UndistortParams {
+    double fx, fy, cx, cy, ifx, ify;
+    double k[12];            /* k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 (OpenCV order), zero padded */
+    int active;              /* mDistCoef.at<float>(0) != 0.0 (:586) */
+};
+int viorb_launch_undistort(const UndistortParams& p, const viorb_keypoint* d_in, int n, viorb_keypoint* d_out, cudaStream_t s);
+int viorb_launch_image_bounds(const UndistortParams& p, int cols, int rows, float* d_bounds, cudaStream_t s);
+
 #endif

@@ -863,6 +863,145 @@ __global__ void __launch_bounds__(32) init_match_kernel(const viorb_keypoint* __
     if (lane == 0) *nmatches = total;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Frame::UndistortKeyPoints (src/Frame.cc:584-614) and Frame::ComputeImageBounds (:616-645):
+ * cv::undistortPoints(pts, pts, mK, mDistCoef, cv::Mat(), mK) -- OpenCV's cvUndistortPoints: normalise with the
+ * inverse intrinsics, five iterations of x = (x0 - delta(x)) * icdist(x) in double precision, re-project with
+ * P = K.  Every double operation is rounded separately (no FMA), in the order of the OpenCV expression.
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void undistort_point(const UndistortParams& p, float uf, float vf, float& xo, float& yo) {
+    const double u = (double)uf, v = (double)vf;
+    double x = __dmul_rn(__dsub_rn(u, p.cx), p.ifx), y = __dmul_rn(__dsub_rn(v, p.cy), p.ify);
+    const double x0 = x, y0 = y;
+    const double* k = p.k;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+        const double num = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[7], r2), k[6]), r2), k[5]), r2));
+        const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[4], r2), k[1]), r2), k[0]), r2));
+        const double icdist = __ddiv_rn(num, den);
+        if (icdist < 0) {                       /* OpenCV >= 3.4: give up and return the normalised input point */
+            x = __dmul_rn(__dsub_rn(u, p.cx), p.ifx);
+            y = __dmul_rn(__dsub_rn(v, p.cy), p.ify);
+            break;
+        }
+        const double twox = __dmul_rn(2.0, x), twoy = __dmul_rn(2.0, y);
+        double dX = __dmul_rn(__dmul_rn(__dmul_rn(2.0, k[2]), x), y);
+        dX = __dadd_rn(dX, __dmul_rn(k[3], __dadd_rn(r2, __dmul_rn(twox, x))));
+        dX = __dadd_rn(dX, __dmul_rn(k[8], r2));
+        dX = __dadd_rn(dX, __dmul_rn(__dmul_rn(k[9], r2), r2));
+        double dY = __dmul_rn(k[2], __dadd_rn(r2, __dmul_rn(twoy, y)));
+        dY = __dadd_rn(dY, __dmul_rn(__dmul_rn(__dmul_rn(2.0, k[3]), x), y));
+        dY = __dadd_rn(dY, __dmul_rn(k[10], r2));
+        dY = __dadd_rn(dY, __dmul_rn(__dmul_rn(k[11], r2), r2));
+        x = __dmul_rn(__dsub_rn(x0, dX), icdist);
+        y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+    }
+    /* RR = P * R = K:  xx = fx*x + 0*y + cx, yy = 0*x + fy*y + cy, ww = 1 / (0*x + 0*y + 1) */
+    const double xx = __dadd_rn(__dadd_rn(__dmul_rn(p.fx, x), __dmul_rn(0.0, y)), p.cx);
+    const double yy = __dadd_rn(__dadd_rn(__dmul_rn(0.0, x), __dmul_rn(p.fy, y)), p.cy);
+    const double ww = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dmul_rn(0.0, x), __dmul_rn(0.0, y)), 1.0));
+    xo = (float)__dmul_rn(xx, ww);
+    yo = (float)__dmul_rn(yy, ww);
+}
+
+__global__ void __launch_bounds__(128) undistort_kernel(const __grid_constant__ UndistortParams p,
+                                                        const viorb_keypoint* __restrict__ in, int n,
+                                                        viorb_keypoint* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    viorb_keypoint kp = in[i];
+    if (p.active) undistort_point(p, kp.x, kp.y, kp.x, kp.y);       /* else mvKeysUn = mvKeys (:586-590) */
+    out[i] = kp;
+}
+
+__global__ void image_bounds_kernel(const __grid_constant__ UndistortParams p, int cols, int rows, float* __restrict__ bounds) {
+    /* :616-645: corners (0,0) (cols,0) (0,rows) (cols,rows) */
+    if (threadIdx.x != 0) return;
+    if (!p.active) { bounds[0] = 0.0f; bounds[1] = (float)cols; bounds[2] = 0.0f; bounds[3] = (float)rows; return; }
+    float x[4], y[4];
+    undistort_point(p, 0.0f, 0.0f, x[0], y[0]);
+    undistort_point(p, (float)cols, 0.0f, x[1], y[1]);
+    undistort_point(p, 0.0f, (float)rows, x[2], y[2]);
+    undistort_point(p, (float)cols, (float)rows, x[3], y[3]);
+    bounds[0] = fminf(x[0], x[2]);      /* mnMinX */
+    bounds[1] = fmaxf(x[1], x[3]);      /* mnMaxX */
+    bounds[2] = fminf(y[0], y[1]);      /* mnMinY */
+    bounds[3] = fmaxf(y[2], y[3]);      /* mnMaxY */
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Independent windowed top-1 search of projected map points in a KeyFrame: the inner loops of
+ *   ORBmatcher::SearchBySim3 (:1102-1326, both directions, TH_HIGH),
+ *   ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (:825-976, chi-square reprojection gates, TH_LOW),
+ *   ORBmatcher::Fuse(KeyFrame*, cv::Mat Scw, ...) (:978-1100, TH_LOW).
+ * KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:906-945) enumerates like Frame's; the level filter
+ * [nPredictedLevel-1, nPredictedLevel] is applied inside the enumeration (same set, same order).  No query depends
+ * on another: one warp per query over the whole grid.
+ * ---------------------------------------------------------------------------------------------- */
+struct WindowArgs {
+    const float *u, *v, *ur;         /* ur == NULL: no reprojection-error gates */
+    const int* level;
+    const uint8_t* valid;
+    const uint8_t* desc;
+    int n, thDist;
+    float th;
+    float invSigma2[12];
+};
+
+__global__ void __launch_bounds__(128) search_window_kernel(FrameIndexDev fi, const __grid_constant__ WindowArgs a,
+                                                            int* __restrict__ bestIdx, int* __restrict__ bestDist) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= a.n) return;
+    unsigned long long k1 = ~0ull;
+    if (a.valid[i]) {
+        const float u = a.u[i], v = a.v[i];
+        const int lvl = a.level[i];
+        const float radius = __fmul_rn(a.th, fi.scale[lvl]);
+        const float ur = a.ur ? a.ur[i] : 0.f;
+        const uint8_t* dMP = a.desc + (size_t)i * 32;
+        for_features_in_area(fi, u, v, radius, lvl - 1, lvl, lane, [&](int pos, int idx, int octave) {
+            if (a.ur) {                                               /* Fuse :901-925 */
+                const viorb_keypoint kp = fi.kps[idx];
+                const float kpr = fi.uRight[idx];
+                const float ex = __fsub_rn(u, kp.x), ey = __fsub_rn(v, kp.y);
+                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                if (kpr >= 0) {
+                    const float er = __fsub_rn(ur, kpr);
+                    e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                    if ((double)__fmul_rn(e2, a.invSigma2[octave]) > 7.8) return;
+                } else {
+                    if ((double)__fmul_rn(e2, a.invSigma2[octave]) > 5.99) return;
+                }
+            }
+            const int dist = hamming_rows(dMP, fi.desc + (size_t)idx * 32);
+            const unsigned long long key = ((unsigned long long)dist << 48) | ((unsigned long long)pos << 24) | (unsigned)idx;
+            k1 = key < k1 ? key : k1;
+        });
+        k1 = warp_min_u64(k1);
+    }
+    if (lane == 0) {
+        const bool ok = k1 != ~0ull && (int)(k1 >> 48) <= a.thDist && (int)(k1 >> 48) < 256;
+        bestIdx[i] = ok ? (int)(k1 & 0xffffff) : -1;
+        if (bestDist) bestDist[i] = ok ? (int)(k1 >> 48) : INT_MAX;
+    }
+}
+
+/* SearchBySim3 "check agreement" (:1305-1320) */
+__global__ void __launch_bounds__(256) sim3_agree_kernel(const int* __restrict__ m1, const int* __restrict__ m2, int n1,
+                                                         int* __restrict__ match12, int* __restrict__ nfound) {
+    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    int idx2 = -1;
+    if (i1 < n1) {
+        idx2 = m1[i1];
+        ok = idx2 >= 0 && m2[idx2] == i1;
+        match12[i1] = ok ? idx2 : -1;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(nfound, __popc(m));
+}
+
 }  // namespace
 
 /* ------------------------------------------------------------------------------------------------ launchers */
@@ -982,4 +1121,33 @@ int viorb_launch_search_init(const FrameIndexDev& f2, const viorb_keypoint* k1, 
     init_match_kernel<<<1, 32, 0, s>>>(k1, f2.kps, n1, f2.n, d_entries, d_start, d_count, nnratio, checkOri, d_matchedDist,
                                        d_matches21, d_binOf, d_matches12, d_prev, d_nmatches);
     return launches + 1;
+}
+
+int viorb_launch_undistort(const UndistortParams& p, const viorb_keypoint* d_in, int n, viorb_keypoint* d_out, cudaStream_t s) {
+    if (n <= 0) return 0;
+    undistort_kernel<<<(n + 127) / 128, 128, 0, s>>>(p, d_in, n, d_out);
+    return 1;
+}
+
+int viorb_launch_image_bounds(const UndistortParams& p, int cols, int rows, float* d_bounds, cudaStream_t s) {
+    image_bounds_kernel<<<1, 32, 0, s>>>(p, cols, rows, d_bounds);
+    return 1;
+}
+
+int viorb_launch_search_window(const FrameIndexDev& fi, const float* u, const float* v, const float* ur, const int* level,
+                               const uint8_t* valid, const uint8_t* desc, int n, float th, int thDist, const float* invSigma2,
+                               int nlevels, int* d_bestIdx, int* d_bestDist, cudaStream_t s) {
+    if (n <= 0) return 0;
+    WindowArgs a;
+    a.u = u; a.v = v; a.ur = ur; a.level = level; a.valid = valid; a.desc = desc; a.n = n; a.thDist = thDist; a.th = th;
+    for (int i = 0; i < 12; i++) a.invSigma2[i] = (invSigma2 && i < nlevels) ? invSigma2[i] : 0.f;
+    search_window_kernel<<<(n + 3) / 4, 128, 0, s>>>(fi, a, d_bestIdx, d_bestDist);
+    return 1;
+}
+
+int viorb_launch_sim3_agree(const int* d_m1, const int* d_m2, int n1, int* d_match12, int* d_nfound, cudaStream_t s) {
+    cudaMemsetAsync(d_nfound, 0, sizeof(int), s);
+    if (n1 <= 0) return 0;
+    sim3_agree_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(d_m1, d_m2, n1, d_match12, d_nfound);
+    return 1;
 }

@@ -52,6 +52,16 @@ void make_index(Frame& F, FrameIndexGuard& g) {
           "viorb_frame_index_create");
 }
 
+/* DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>) -> node ids, CSR offsets, keypoint indices */
+void flatten(const DBoW2::FeatureVector& fv, std::vector<int32_t>& ids, std::vector<int32_t>& ptr, std::vector<int32_t>& idx) {
+    ptr.push_back(0);
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+        ids.push_back((int32_t)it->first);
+        for (size_t k = 0; k < it->second.size(); k++) idx.push_back((int32_t)it->second[k]);
+        ptr.push_back((int32_t)idx.size());
+    }
+}
+
 }  // namespace
 
 ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
@@ -268,14 +278,6 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F
     const float ex = pKF2->fx * C2[0] * invz + pKF2->cx;
     const float ey = pKF2->fy * C2[1] * invz + pKF2->cy;
 
-    auto flatten = [](const DBoW2::FeatureVector& fv, std::vector<int32_t>& ids, std::vector<int32_t>& ptr, std::vector<int32_t>& idx) {
-        ptr.push_back(0);
-        for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
-            ids.push_back((int32_t)it->first);
-            for (size_t k = 0; k < it->second.size(); k++) idx.push_back((int32_t)it->second[k]);
-            ptr.push_back((int32_t)idx.size());
-        }
-    };
     std::vector<int32_t> id1, p1, i1, id2, p2, i2;
     flatten(pKF1->mFeatVec, id1, p1, i1);
     flatten(pKF2->mFeatVec, id2, p2, i2);
@@ -300,6 +302,65 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F
     vMatchedPairs.reserve(n);
     for (size_t i = 0; i < m12.size(); i++)
         if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));                     /* :815-820 */
+    return n;
+}
+
+int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
+    const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));                      /* :163 */
+    std::vector<int32_t> id1, p1, i1, id2, p2, i2;
+    flatten(pKF->mFeatVec, id1, p1, i1);
+    flatten(F.mFeatVec, id2, p2, i2);
+    std::vector<uint8_t> v1(pKF->N);
+    for (int i = 0; i < pKF->N; i++) v1[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();            /* :190-196 */
+    const std::vector<uint8_t> d1 = pack_descriptors(pKF->mDescriptors, pKF->N), d2 = pack_descriptors(F.mDescriptors, F.N);
+    std::vector<int32_t> match(F.N, -1);
+    int n = 0;
+    check(viorb_search_by_bow(thread_ctx(), 0, reinterpret_cast<const viorb_keypoint*>(pKF->mvKeysUn.data()), d1.data(), v1.data(),
+                              pKF->N, reinterpret_cast<const viorb_keypoint*>(F.mvKeys.data()), d2.data(), nullptr, F.N, id1.data(),
+                              p1.data(), i1.data(), (int)id1.size(), id2.data(), p2.data(), i2.data(), (int)id2.size(), mfNNratio,
+                              mbCheckOrientation, match.data(), &n),
+          "viorb_search_by_bow");
+    for (int k = 0; k < F.N; k++)
+        if (match[k] >= 0) vpMapPointMatches[k] = vpMapPointsKF[match[k]];                              /* :220 */
+    return n;
+}
+
+int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12) {
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+    vpMatches12 = std::vector<MapPoint*>(vpMapPoints1.size(), static_cast<MapPoint*>(NULL));            /* :534 */
+    std::vector<int32_t> id1, p1, i1, id2, p2, i2;
+    flatten(pKF1->mFeatVec, id1, p1, i1);
+    flatten(pKF2->mFeatVec, id2, p2, i2);
+    std::vector<uint8_t> v1(pKF1->N), v2(pKF2->N);
+    for (int i = 0; i < pKF1->N; i++) v1[i] = vpMapPoints1[i] && !vpMapPoints1[i]->isBad();
+    for (int i = 0; i < pKF2->N; i++) v2[i] = vpMapPoints2[i] && !vpMapPoints2[i]->isBad();
+    const std::vector<uint8_t> d1 = pack_descriptors(pKF1->mDescriptors, pKF1->N), d2 = pack_descriptors(pKF2->mDescriptors, pKF2->N);
+    std::vector<int32_t> match(pKF1->N, -1);
+    int n = 0;
+    check(viorb_search_by_bow(thread_ctx(), 1, reinterpret_cast<const viorb_keypoint*>(pKF1->mvKeysUn.data()), d1.data(), v1.data(),
+                              pKF1->N, reinterpret_cast<const viorb_keypoint*>(pKF2->mvKeysUn.data()), d2.data(), v2.data(), pKF2->N,
+                              id1.data(), p1.data(), i1.data(), (int)id1.size(), id2.data(), p2.data(), i2.data(), (int)id2.size(),
+                              mfNNratio, mbCheckOrientation, match.data(), &n),
+          "viorb_search_by_bow");
+    for (int i = 0; i < pKF1->N; i++)
+        if (match[i] >= 0) vpMatches12[i] = vpMapPoints2[match[i]];                                     /* :601 */
+    return n;
+}
+
+int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched,
+                                        std::vector<int>& vnMatches12, int windowSize) {
+    FrameIndexGuard g;
+    make_index(F2, g);
+    const int n1 = (int)F1.mvKeysUn.size();
+    const std::vector<uint8_t> d1 = pack_descriptors(F1.mDescriptors, n1);
+    static_assert(sizeof(cv::Point2f) == 2 * sizeof(float), "Point2f layout");
+    vnMatches12 = std::vector<int>(n1, -1);
+    int n = 0;
+    check(viorb_search_for_initialization(g.fi, reinterpret_cast<const viorb_keypoint*>(F1.mvKeysUn.data()), d1.data(), n1,
+                                          reinterpret_cast<float*>(vbPrevMatched.data()), windowSize, mfNNratio, mbCheckOrientation,
+                                          vnMatches12.data(), &n),
+          "viorb_search_for_initialization");
     return n;
 }
 

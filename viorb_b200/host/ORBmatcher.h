@@ -1,10 +1,10 @@
 /*
  * ORBmatcher.h -- drop-in for ORB_SLAM2::ORBmatcher (reference include/ORBmatcher.h:37-102) for the searches
- * on the hot path: DescriptorDistance, the four SearchByProjection overloads and SearchForTriangulation.  Each call marshals the fields the reference reads into flat arrays and runs the
- * whole search as CUDA kernels behind include/viorb_gpu.h; results (matches, counts, tie-breaks, the
- * "already matched" dependence) are identical to the reference's sequential loops.
- * The remaining searches of the reference class (SearchByBoW x2, SearchForInitialization, SearchBySim3, Fuse x2)
- * are SURVEY.md section 8(f) "next" rows.
+ * on the hot path: DescriptorDistance, the four SearchByProjection overloads, SearchForTriangulation, both
+ * SearchByBoW overloads and SearchForInitialization.  Each call marshals the fields the reference reads into flat
+ * arrays and runs the whole search as CUDA kernels behind include/viorb_gpu.h; results (matches, counts,
+ * tie-breaks, the "already matched" dependence) are identical to the reference's sequential loops.
+ * The searches that mutate the map graph (SearchBySim3, Fuse x2) stay SURVEY.md section 8(f) "next" rows.
  */
 #ifndef ORBMATCHER_H
 #define ORBMATCHER_H
@@ -40,6 +40,15 @@ public:
     /* Project MapPoints using a similarity transformation and search matches; used in loop detection (:290-403) */
     int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints,
                            std::vector<MapPoint*>& vpMatched, int th);
+
+    /* Search matches between MapPoints in a KeyFrame and ORB in a Frame, brute force constrained to ORB of the same
+     * vocabulary node; used in relocalisation and loop detection (:159-288) */
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);              /* (:522-655) */
+
+    /* Matching for the map initialisation, monocular case only (:405-520) */
+    int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                                int windowSize = 10);
 
     /* Matching to triangulate new MapPoints, epipolar constraint check (:657-823) */
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,

@@ -22,6 +22,7 @@
 
 namespace DBoW2 {
 typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;   /* Thirdparty/DBoW2/DBoW2/FeatureVector.h */
+typedef std::map<unsigned int, double> BowVector;                          /* Thirdparty/DBoW2/DBoW2/BowVector.h:56-57 */
 }
 
 namespace ORB_SLAM2 {
@@ -64,6 +65,7 @@ public:
     std::vector<float> mvuRight, mvDepth;
     cv::Mat mDescriptors, mDescriptorsRight;
     std::vector<MapPoint*> mvpMapPoints;
+    DBoW2::FeatureVector mFeatVec;
     std::vector<bool> mvbOutlier;
     std::vector<float> mvScaleFactors, mvInvScaleFactors;
     float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;
