@@ -30,8 +30,10 @@ KEYS = [
 
 
 def short(name):
-    m = re.search(r"([A-Za-z0-9_]+)\s*(<.*>)?\(", name)
-    return m.group(1) if m else name[:40]
+    name = re.sub(r"^void\s+", "", name.strip())
+    name = re.sub(r"<unnamed>::|\(anonymous namespace\)::", "", name)
+    m = re.match(r"([A-Za-z0-9_:]+)", name)
+    return m.group(1).split("::")[-1] if m else name[:40]
 
 
 def to_bytes(val, unit):
@@ -70,18 +72,21 @@ def main():
     traffic = {}
     tpath = os.path.join(out, "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath))
+        traffic = {k: v for k, v in json.load(open(tpath)).items() if v.get("source") != tag and k != "void"}
     if os.path.exists(rep):
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-        rows = list(csv.reader(raw.splitlines()))
-        hdr, units = rows[0], rows[1]
         seen = {}
-        for r in rows[2:]:
-            k = short(r[hdr.index("Kernel Name")])
-            key = (k, r[hdr.index("launch__grid_size")])
-            seen.setdefault(key, r)       # first launch of every (kernel, grid) pair
+        for rp in (rep, os.path.join(go, tag + "_prof_match.ncu-rep")):
+            if not os.path.exists(rp):
+                continue
+            raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+            rows = list(csv.reader(raw.splitlines()))
+            hdr, units = rows[0], rows[1]
+            for r in rows[2:]:
+                k = short(r[hdr.index("Kernel Name")])
+                key = (k, r[hdr.index("launch__grid_size")])
+                seen.setdefault(key, (r, hdr, units))       # first launch of every (kernel, grid) pair
         md += ["## `--set full` (first captured launch per kernel and grid)", ""]
-        for (k, grid), r in seen.items():
+        for (k, grid), (r, hdr, units) in seen.items():
             md.append("### %s (grid %s)" % (k, grid))
             md.append("")
             for m in KEYS:
