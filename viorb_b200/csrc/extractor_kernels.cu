@@ -250,6 +250,14 @@ __device__ __forceinline__ unsigned funnel_bytes(unsigned lo, unsigned hi, int s
     return __byte_perm(lo, hi, 0x3210u + 0x1111u * (unsigned)sh);
 }
 
+/* shared-memory atomic add issued as written: the callers already elect one lane per warp, and the compiler's own
+ * warp-aggregation wrapper (VOTEU/FLO/UPOPC around ATOMS) would only add instructions */
+__device__ __forceinline__ int smem_add(int* p, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
+}
+
 /* ---- TMA (cp.async.bulk.tensor) + mbarrier, raw PTX ---- */
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -399,25 +407,38 @@ __global__ void __launch_bounds__(128, 8) fast_cells_kernel(const __grid_constan
     const unsigned invNQ = 0xffffffffu / (unsigned)NQ + 1u;          /* t / NQ == umulhi(t, invNQ) for t < 2^16 */
     {
         const unsigned addc = (unsigned)(127 - g.minTh) * 0x01010101u;
-        for (int t0 = 0; t0 < ntask; t0 += blockDim.x) {
-            const int t = t0 + tid;
-            bool keep = false;
-            if (t < ntask) {
-                const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
-                const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
-                const unsigned cw4 = fast_ld4<SH>(row);
-                const unsigned d0 = __vabsdiffu4(fast_ld4<SH>(row + 3 * FAST_TW), cw4);
-                const unsigned d8 = __vabsdiffu4(fast_ld4<SH>(row - 3 * FAST_TW), cw4);
-                const unsigned d4 = __vabsdiffu4(fast_ld4<SH + 3>(row), cw4);
-                const unsigned d12 = __vabsdiffu4(fast_ld4<SH - 3>(row), cw4);
-                const unsigned f0 = (d0 + addc) | d0, f4 = (d4 + addc) | d4, f8 = (d8 + addc) | d8, f12 = (d12 + addc) | d12;
-                keep = ((((f0 | f8) & (f4 | f12))) & 0x80808080u) != 0;   /* (f0&f4)|(f4&f8)|(f8&f12)|(f12&f0) */
+        const unsigned lt = (1u << lane) - 1;
+        /* four tasks per thread and iteration: four ballots, one shared atomic per warp */
+        for (int t0 = 0; t0 < ntask; t0 += 4 * blockDim.x) {
+            bool keep[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int t = t0 + j * blockDim.x + tid;
+                keep[j] = false;
+                if (t < ntask) {
+                    const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
+                    const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
+                    const unsigned cw4 = fast_ld4<SH>(row);
+                    const unsigned d0 = __vabsdiffu4(fast_ld4<SH>(row + 3 * FAST_TW), cw4);
+                    const unsigned d8 = __vabsdiffu4(fast_ld4<SH>(row - 3 * FAST_TW), cw4);
+                    const unsigned d4 = __vabsdiffu4(fast_ld4<SH + 3>(row), cw4);
+                    const unsigned d12 = __vabsdiffu4(fast_ld4<SH - 3>(row), cw4);
+                    const unsigned f0 = (d0 + addc) | d0, f4 = (d4 + addc) | d4, f8 = (d8 + addc) | d8, f12 = (d12 + addc) | d12;
+                    keep[j] = ((((f0 | f8) & (f4 | f12))) & 0x80808080u) != 0;   /* (f0&f4)|(f4&f8)|(f8&f12)|(f12&f0) */
+                }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            const unsigned m0 = __ballot_sync(0xffffffffu, keep[0]), m1 = __ballot_sync(0xffffffffu, keep[1]);
+            const unsigned m2 = __ballot_sync(0xffffffffu, keep[2]), m3 = __ballot_sync(0xffffffffu, keep[3]);
+            if ((m0 | m1 | m2 | m3) == 0) continue;
+            const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
             int basePos = 0;
-            if (lane == 0 && m) basePos = atomicAdd(&nwork0, __popc(m));
+            if (lane == 0) basePos = smem_add(&nwork0, c0 + c1 + c2 + c3);
             basePos = __shfl_sync(0xffffffffu, basePos, 0);
-            if (keep) work0[basePos + __popc(m & ((1u << lane) - 1))] = (unsigned short)t;
+            const int tb = t0 + tid;
+            if (keep[0]) work0[basePos + __popc(m0 & lt)] = (unsigned short)tb;
+            if (keep[1]) work0[basePos + c0 + __popc(m1 & lt)] = (unsigned short)(tb + blockDim.x);
+            if (keep[2]) work0[basePos + c0 + c1 + __popc(m2 & lt)] = (unsigned short)(tb + 2 * blockDim.x);
+            if (keep[3]) work0[basePos + c0 + c1 + c2 + __popc(m3 & lt)] = (unsigned short)(tb + 3 * blockDim.x);
         }
     }
     __syncthreads();
@@ -459,7 +480,7 @@ __global__ void __launch_bounds__(128, 8) fast_cells_kernel(const __grid_constan
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         int basePos = 0;
-        if (lane == 0 && m) basePos = atomicAdd(&nwork, __popc(m));
+        if (lane == 0 && m) basePos = smem_add(&nwork, __popc(m));
         basePos = __shfl_sync(0xffffffffu, basePos, 0);
         if (keep) work[basePos + __popc(m & ((1u << lane) - 1))] = (unsigned short)t;
     }
@@ -501,7 +522,7 @@ __global__ void __launch_bounds__(128, 8) fast_cells_kernel(const __grid_constan
         const unsigned m2 = __ballot_sync(0xffffffffu, (word & 0x00ff0000u) != 0), m3 = __ballot_sync(0xffffffffu, (word & 0xff000000u) != 0);
         const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
         int basePos = 0;
-        if (lane == 0 && (m0 | m1 | m2 | m3)) basePos = atomicAdd(&npix, c0 + c1 + c2 + c3);
+        if (lane == 0 && (m0 | m1 | m2 | m3)) basePos = smem_add(&npix, c0 + c1 + c2 + c3);
         basePos = __shfl_sync(0xffffffffu, basePos, 0);
         const unsigned e = (unsigned)(q * 4) | ((unsigned)y << 8);
         if (word & 0x000000ffu) pix[basePos + __popc(m0 & lt)] = (unsigned short)e;
@@ -570,7 +591,7 @@ __global__ void __launch_bounds__(128, 8) fast_cells_kernel(const __grid_constan
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         int basePos = 0;
-        if (lane == 0 && m) basePos = atomicAdd(&nout, __popc(m));
+        if (lane == 0 && m) basePos = smem_add(&nout, __popc(m));
         basePos = __shfl_sync(0xffffffffu, basePos, 0);
         const int pos = b0 + basePos + __popc(m & ((1u << lane) - 1));
         if (keep && pos < L.candCap) out[pos] = rec;
