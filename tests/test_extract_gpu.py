@@ -147,3 +147,30 @@ def test_bad_arguments(api, ctx):
     with pytest.raises(api.ViorbError):
         ex(np.zeros((40, 40), np.uint8))        # smaller than one FAST cell at the top level
     ex.close()
+
+
+# (h, w, nfeatures, scale, levels, iniTh, minTh): odd sizes (unaligned rows, ragged tiles, single-cell levels), the
+# scale-factor envelope (1.1 .. 1.5), few/many levels, thresholds far apart and equal
+SWEEP = [(97, 131, 200, 1.2, 3, 20, 7), (333, 250, 500, 1.25, 5, 15, 5), (480, 640, 1500, 1.5, 4, 20, 7),
+         (241, 1023, 800, 1.1, 8, 25, 10), (720, 1280, 3000, 1.3, 6, 20, 20), (128, 128, 300, 1.2, 4, 30, 3),
+         (479, 751, 1000, 1.2, 8, 20, 7), (600, 799, 1200, 1.41, 5, 12, 7)]
+
+
+@pytest.mark.parametrize("cfg", SWEEP, ids=lambda c: "%dx%d_s%.2f_l%d" % (c[1], c[0], c[3], c[4]))
+def test_parameter_sweep(api, ctx, oracle, cfg):
+    """whole operator() on shapes and parameters away from the benchmark configs (strided view of a wider buffer too)"""
+    h, w, nf, sf, nl, it, mt = cfg
+    img = synth.frame(h, w, h * 7 + w)
+    ref = oracle.Extractor(nf, sf, nl, it, mt)
+    k_ref, d_ref = ref(img)
+    ex = api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx)
+    k_gpu, d_gpu = ex(img)
+    assert len(k_ref) > 20
+    assert_same_output(k_gpu, d_gpu, k_ref, d_ref)
+    for l in range(nl):
+        assert (ex.pyramid(l) == ref.pyramid(l)).all(), "pyramid level %d" % l
+    wide = np.zeros((h, w + 13), np.uint8)
+    wide[:, 5:5 + w] = img
+    k2, d2 = ex(wide[:, 5:5 + w])          # unaligned base pointer and row stride
+    assert_same_output(k2, d2, k_ref, d_ref)
+    ex.close()

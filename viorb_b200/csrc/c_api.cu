@@ -477,7 +477,7 @@ int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, in
     build_tables(e);
     if (ctx_bind(ctx)) { delete e; return VIORB_ERR_CUDA; }
     cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
-    if (getenv("VIORB_LANES")) e->nlanes = std::min(4, std::max(1, atoi(getenv("VIORB_LANES"))));
+    if (getenv("VIORB_LANES")) e->nlanes = std::min(4, std::max(2, atoi(getenv("VIORB_LANES"))));   /* the host-buffer path pairs lanes with its two staging slots */
     for (int i = 0; i < 4; i++) {
         cudaStreamCreateWithFlags(&e->lanes[i].stream, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&e->lanes[i].evDone, cudaEventDisableTiming);
