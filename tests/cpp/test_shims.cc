@@ -387,6 +387,201 @@ int main() {
         orc_vocabulary_destroy(ov);
     }
 
+    /* ---- Fuse x2 and SearchBySim3: search on the GPU, map-graph bookkeeping replayed on the host ---- */
+    {
+        const float cxK = 607.19f, cyK = 185.2f;
+        auto make_kf = [&](KeyFrame& k, const std::vector<cv::KeyPoint>& kk, const cv::Mat& dd) {
+            k.N = (int)kk.size(); k.mvKeysUn = kk; k.mDescriptors = dd;
+            k.mvuRight.assign(k.N, -1.0f);
+            for (int i = 0; i < k.N; i += 3) k.mvuRight[i] = kk[i].pt.x - 20.0f;
+            k.mapPoints.assign(k.N, nullptr);
+            k.mvScaleFactors = exL.GetScaleFactors();
+            k.mvInvLevelSigma2 = exL.GetInverseScaleSigmaSquares();
+            k.fx = k.fy = fx; k.cx = cxK; k.cy = cyK; k.mbf = 386.1448f;
+            k.mnMinX = 0; k.mnMaxX = (float)W; k.mnMinY = 0; k.mnMaxY = (float)H;
+            k.Rcw = cv::Mat::zeros(3, 3, CV_32F);
+            for (int i = 0; i < 3; i++) k.Rcw.at<float>(i, i) = 1;
+            k.tcw = cv::Mat::zeros(3, 1, CV_32F);
+            k.Ow = cv::Mat::zeros(3, 1, CV_32F);
+        };
+        /* a map point that projects near keypoint i of (kk, dd) in a camera at the origin */
+        auto make_mp = [&](MapPoint& mp, const std::vector<cv::KeyPoint>& kk, const cv::Mat& dd, int i, float du) {
+            const float z = 4.0f + 6.0f * rndf();
+            mp.worldPos = cv::Mat(3, 1, CV_32F);
+            mp.worldPos.at<float>(0) = (kk[i].pt.x + du - cxK) / fx * z;
+            mp.worldPos.at<float>(1) = (kk[i].pt.y - cyK) / fx * z;
+            mp.worldPos.at<float>(2) = z;
+            mp.normal = cv::Mat(3, 1, CV_32F);
+            const float nrm = std::sqrt(mp.worldPos.at<float>(0) * mp.worldPos.at<float>(0) + mp.worldPos.at<float>(1) * mp.worldPos.at<float>(1) + z * z);
+            for (int r = 0; r < 3; r++) mp.normal.at<float>(r) = mp.worldPos.at<float>(r) / nrm;
+            /* PredictScale = ceil(log(max/dist)/log 1.2) = the keypoint's octave (+1 sometimes) */
+            mp.mfMaxDistance = nrm * std::pow(1.2f, (float)kk[i].octave + 0.4f * rndf());
+            mp.mfMinDistance = mp.mfMaxDistance / 5.0f;
+            mp.descriptor = cv::Mat(1, 32, CV_8U);
+            memcpy(mp.descriptor.data, dd.ptr<uint8_t>(i), 32);
+            for (int b = 0; b < 6; b++) mp.descriptor.data[rnd() % 32] ^= (uint8_t)(1u << (rnd() % 8));
+            mp.nObs = 1 + rnd() % 4;
+        };
+        KeyFrame kf;
+        make_kf(kf, kR, dR);
+        std::vector<MapPoint> inKF(kf.N), cand(600);
+        for (int i = 0; i < kf.N; i += 2) { make_mp(inKF[i], kR, dR, i, 0.0f); kf.mapPoints[i] = &inKF[i]; inKF[i].mObservations[&kf] = i; }
+        std::vector<MapPoint*> vp;
+        std::vector<float> qu, qv, qur; std::vector<int32_t> ql; std::vector<uint8_t> qvalid, qd;
+        for (size_t m = 0; m < cand.size(); m++) {
+            const int i = rnd() % kf.N;
+            make_mp(cand[m], kR, dR, i, 0.7f * (rndf() - 0.5f));
+            vp.push_back(m % 37 == 5 ? nullptr : &cand[m]);
+            if (m % 41 == 7) cand[m].bad = true;
+        }
+        /* expected: oracle search with the projection math of the reference (:846-881), then the bookkeeping replayed */
+        std::vector<int32_t> best(vp.size(), -1);
+        {
+            const int n = (int)vp.size();
+            qu.assign(n, 0); qv.assign(n, 0); qur.assign(n, 0); ql.assign(n, 0); qvalid.assign(n, 0); qd.assign((size_t)n * 32, 0);
+            for (int i = 0; i < n; i++) {
+                MapPoint* p = vp[i];
+                if (!p || p->isBad()) continue;
+                const float X = p->worldPos.at<float>(0), Y = p->worldPos.at<float>(1), Z = p->worldPos.at<float>(2);
+                const float invz = 1 / Z;
+                const float u = fx * (X * invz) + cxK, v = fx * (Y * invz) + cyK;
+                if (!kf.IsInImage(u, v)) continue;
+                const float d3 = (float)std::sqrt((double)X * X + (double)Y * Y + (double)Z * Z);
+                if (d3 < p->GetMinDistanceInvariance() || d3 > p->GetMaxDistanceInvariance()) continue;
+                qu[i] = u; qv[i] = v; qur[i] = u - kf.mbf * invz; ql[i] = p->PredictScale(d3, &kf); qvalid[i] = 1;
+                memcpy(&qd[(size_t)i * 32], p->descriptor.data, 32);
+            }
+            orc_grid* grid = orc_grid_create(oR.k.data(), kf.N, 0, (float)W, 0, (float)H);
+            orc_search_window_top1(grid, oR.k.data(), oR.d.data(), kf.mvuRight.data(), kf.mvScaleFactors.data(), qu.data(), qv.data(),
+                                   qur.data(), ql.data(), qvalid.data(), qd.data(), n, 3.0f, 50, kf.mvInvLevelSigma2.data(), best.data(), nullptr);
+            orc_grid_destroy(grid);
+        }
+        int nFusedRef = 0, nAdd = 0, nRep = 0;
+        std::vector<MapPoint*> expectKF = kf.mapPoints;
+        std::vector<int> expectBad(vp.size(), 0);
+        {   /* replay on copies of the flags only: which keypoints receive which point, which points turn bad */
+            std::vector<MapPoint*> slot = kf.mapPoints;
+            std::map<MapPoint*, bool> bad, inkf;
+            std::map<MapPoint*, int> nobs;
+            for (size_t i = 0; i < vp.size(); i++) {
+                MapPoint* p = vp[i];
+                if (!p) continue;
+                const bool isbad = bad.count(p) ? bad[p] : p->bad;
+                if (isbad || inkf[p]) continue;
+                if (best[i] < 0) continue;
+                MapPoint* q = slot[best[i]];
+                if (q) {
+                    const bool qbad = bad.count(q) ? bad[q] : q->bad;
+                    if (!qbad) {
+                        const int oq = nobs.count(q) ? nobs[q] : q->nObs, op = nobs.count(p) ? nobs[p] : p->nObs;
+                        if (oq > op) { bad[p] = true; }                                  /* pMP->Replace(pMPinKF): p had no observations */
+                        else { bad[q] = true; slot[best[i]] = p; inkf[p] = true; nobs[p] = op + 1; }   /* pMPinKF->Replace(pMP) */
+                        nRep++;
+                    }
+                } else { slot[best[i]] = p; inkf[p] = true; nobs[p] = (nobs.count(p) ? nobs[p] : p->nObs) + 1; nAdd++; }
+                nFusedRef++;
+            }
+            expectKF = slot;
+            for (size_t i = 0; i < vp.size(); i++) expectBad[i] = vp[i] ? (bad.count(vp[i]) ? bad[vp[i]] : vp[i]->bad) : 0;
+        }
+        ORBmatcher fm(0.6f, true);
+        const int nFused = fm.Fuse(&kf, vp, 3.0f);
+        bool same = nFused == nFusedRef;
+        for (int k = 0; same && k < kf.N; k++) same = kf.mapPoints[k] == expectKF[k];
+        for (size_t i = 0; same && i < vp.size(); i++) same = !vp[i] || (int)vp[i]->isBad() == expectBad[i];
+        CHECK(nFusedRef > 100 && nAdd > 20 && nRep > 20 && same, "Fuse(KeyFrame, vpMapPoints, th) differs from the oracle replay");
+
+        /* Fuse with a Sim3 (identity, scale 1): no chi-square gates, replace list instead of Replace() */
+        KeyFrame kf2;
+        make_kf(kf2, kR, dR);
+        std::vector<MapPoint> in2(kf2.N), cand2(400);
+        for (int i = 0; i < kf2.N; i += 2) { make_mp(in2[i], kR, dR, i, 0.0f); kf2.mapPoints[i] = &in2[i]; }
+        std::vector<MapPoint*> vp2, rep2(cand2.size(), nullptr);
+        for (size_t m = 0; m < cand2.size(); m++) { make_mp(cand2[m], kR, dR, rnd() % kf2.N, 2.0f * (rndf() - 0.5f)); vp2.push_back(&cand2[m]); }
+        cv::Mat Scw = cv::Mat::zeros(4, 4, CV_32F);
+        for (int i = 0; i < 4; i++) Scw.at<float>(i, i) = 1;
+        std::vector<int32_t> best2(vp2.size(), -1);
+        {
+            const int n = (int)vp2.size();
+            qu.assign(n, 0); qv.assign(n, 0); ql.assign(n, 0); qvalid.assign(n, 0); qd.assign((size_t)n * 32, 0);
+            for (int i = 0; i < n; i++) {
+                MapPoint* p = vp2[i];
+                const float X = p->worldPos.at<float>(0), Y = p->worldPos.at<float>(1), Z = p->worldPos.at<float>(2);
+                const float invz = 1.0 / Z;
+                const float u = fx * (X * invz) + cxK, v = fx * (Y * invz) + cyK;
+                if (!kf2.IsInImage(u, v)) continue;
+                const float d3 = (float)std::sqrt((double)X * X + (double)Y * Y + (double)Z * Z);
+                if (d3 < p->GetMinDistanceInvariance() || d3 > p->GetMaxDistanceInvariance()) continue;
+                qu[i] = u; qv[i] = v; ql[i] = p->PredictScale(d3, &kf2); qvalid[i] = 1;
+                memcpy(&qd[(size_t)i * 32], p->descriptor.data, 32);
+            }
+            orc_grid* grid = orc_grid_create(oR.k.data(), kf2.N, 0, (float)W, 0, (float)H);
+            orc_search_window_top1(grid, oR.k.data(), oR.d.data(), kf2.mvuRight.data(), kf2.mvScaleFactors.data(), qu.data(), qv.data(), nullptr,
+                                   ql.data(), qvalid.data(), qd.data(), n, 4.0f, 50, nullptr, best2.data(), nullptr);
+            orc_grid_destroy(grid);
+        }
+        const std::vector<MapPoint*> before2 = kf2.mapPoints;
+        const int nF2 = fm.Fuse(&kf2, Scw, vp2, 4.0f, rep2);
+        int nF2ref = 0;
+        same = true;
+        {
+            std::vector<MapPoint*> slot = before2;
+            for (size_t i = 0; i < vp2.size(); i++) {
+                if (best2[i] < 0) { same = same && rep2[i] == nullptr; continue; }
+                MapPoint* q = slot[best2[i]];
+                if (q) same = same && rep2[i] == q;
+                else { slot[best2[i]] = vp2[i]; same = same && rep2[i] == nullptr; }
+                nF2ref++;
+            }
+            for (int k = 0; same && k < kf2.N; k++) same = kf2.mapPoints[k] == slot[k];
+        }
+        CHECK(nF2ref > 100 && nF2 == nF2ref && same, "Fuse(KeyFrame, Scw, ...) differs from the oracle replay");
+
+        /* SearchBySim3 between two key frames at the same pose (s = 1, R = I, t = 0): mutual best within the window */
+        KeyFrame a, b;
+        make_kf(a, kL, dL);
+        make_kf(b, kR, dR);
+        std::vector<MapPoint> pa(a.N), pb(b.N);
+        for (int i = 0; i < a.N; i++) if (rnd() % 4) { make_mp(pa[i], kL, dL, i, -20.0f); a.mapPoints[i] = &pa[i]; }
+        for (int i = 0; i < b.N; i++) if (rnd() % 4) { make_mp(pb[i], kR, dR, i, 20.0f); b.mapPoints[i] = &pb[i]; }
+        std::vector<MapPoint*> m12(a.N, nullptr);
+        cv::Mat R12 = cv::Mat::zeros(3, 3, CV_32F), t12 = cv::Mat::zeros(3, 1, CV_32F);
+        for (int i = 0; i < 3; i++) R12.at<float>(i, i) = 1;
+        const float s12 = 1.0f;
+        const int nS = fm.SearchBySim3(&a, &b, m12, s12, R12, t12, 7.5f);
+        auto sim_q = [&](KeyFrame& from, KeyFrame& to, std::vector<float>& u, std::vector<float>& v, std::vector<int32_t>& l,
+                         std::vector<uint8_t>& ok, std::vector<uint8_t>& d) {
+            const int n = from.N;
+            u.assign(n, 0); v.assign(n, 0); l.assign(n, 0); ok.assign(n, 0); d.assign((size_t)n * 32, 0);
+            for (int i = 0; i < n; i++) {
+                MapPoint* p = from.mapPoints[i];
+                if (!p) continue;
+                const float X = p->worldPos.at<float>(0), Y = p->worldPos.at<float>(1), Z = p->worldPos.at<float>(2);
+                const float invz = 1.0 / Z;
+                const float uu = fx * (X * invz) + cxK, vv = fx * (Y * invz) + cyK;
+                if (!to.IsInImage(uu, vv)) continue;
+                const float d3 = (float)std::sqrt((double)X * X + (double)Y * Y + (double)Z * Z);
+                if (d3 < p->GetMinDistanceInvariance() || d3 > p->GetMaxDistanceInvariance()) continue;
+                u[i] = uu; v[i] = vv; l[i] = p->PredictScale(d3, &to); ok[i] = 1;
+                memcpy(&d[(size_t)i * 32], p->descriptor.data, 32);
+            }
+        };
+        std::vector<float> u12, v12, u21, v21; std::vector<int32_t> l12, l21; std::vector<uint8_t> ok12, ok21, d12, d21;
+        sim_q(a, b, u12, v12, l12, ok12, d12);
+        sim_q(b, a, u21, v21, l21, ok21, d21);
+        orc_grid* ga = orc_grid_create(oL.k.data(), a.N, 0, (float)W, 0, (float)H);
+        orc_grid* gb = orc_grid_create(oR.k.data(), b.N, 0, (float)W, 0, (float)H);
+        std::vector<int32_t> rm(a.N);
+        const int nSref = orc_search_by_sim3(ga, oL.k.data(), oL.d.data(), a.mvScaleFactors.data(), a.N, gb, oR.k.data(), oR.d.data(),
+                                             b.mvScaleFactors.data(), b.N, u12.data(), v12.data(), l12.data(), ok12.data(), d12.data(),
+                                             u21.data(), v21.data(), l21.data(), ok21.data(), d21.data(), 7.5f, rm.data());
+        same = nS == nSref;
+        for (int i = 0; same && i < a.N; i++) same = m12[i] == (rm[i] >= 0 ? b.mapPoints[rm[i]] : nullptr);
+        CHECK(nSref > 20 && same, "SearchBySim3 differs from the oracle");
+        orc_grid_destroy(ga);
+        orc_grid_destroy(gb);
+    }
+
     orc_extractor_destroy(oL.e);
     orc_extractor_destroy(oR.e);
     if (g_fail == 0) printf("ALL SHIM CHECKS PASSED\n");

@@ -41,6 +41,10 @@ def test_shims_compile_and_link():
                 "ORB_SLAM2::ORBmatcher::SearchByBoW(ORB_SLAM2::KeyFrame*, ORB_SLAM2::Frame&, std::vector<ORB_SLAM2::MapPoint*",
                 "ORB_SLAM2::ORBmatcher::SearchByBoW(ORB_SLAM2::KeyFrame*, ORB_SLAM2::KeyFrame*, std::vector<ORB_SLAM2::MapPoint*",
                 "ORB_SLAM2::ORBmatcher::SearchForInitialization(ORB_SLAM2::Frame&, ORB_SLAM2::Frame&, std::vector<cv::Point2",
+                "ORB_SLAM2::ORBmatcher::SearchBySim3(ORB_SLAM2::KeyFrame*, ORB_SLAM2::KeyFrame*, std::vector<ORB_SLAM2::MapPoint*",
+                "ORB_SLAM2::ORBmatcher::Fuse(ORB_SLAM2::KeyFrame*, std::vector<ORB_SLAM2::MapPoint*",
+                "ORB_SLAM2::ORBmatcher::Fuse(ORB_SLAM2::KeyFrame*, cv::Mat, std::vector<ORB_SLAM2::MapPoint*",
+                "ORB_SLAM2::ORBVocabulary::loadFromTextFile(", "ORB_SLAM2::ORBVocabulary::transform(",
                 "ORB_SLAM2::Frame::ComputeStereoMatches()"):
         assert sym in out, sym
 

@@ -364,6 +364,228 @@ int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Po
     return n;
 }
 
+namespace {
+
+void make_kf_index(KeyFrame* pKF, FrameIndexGuard& g) {
+    const std::vector<uint8_t> kdesc = pack_descriptors(pKF->mDescriptors, pKF->N);
+    check(viorb_frame_index_create(thread_ctx(), reinterpret_cast<const viorb_keypoint*>(pKF->mvKeysUn.data()), kdesc.data(),
+                                   pKF->mvuRight.empty() ? nullptr : pKF->mvuRight.data(), pKF->N, pKF->mnMinX, pKF->mnMaxX,
+                                   pKF->mnMinY, pKF->mnMaxY, pKF->mvScaleFactors.data(), (int)pKF->mvScaleFactors.size(), &g.fi),
+          "viorb_frame_index_create");
+}
+
+/* query arrays of one projected map-point set */
+struct Queries {
+    std::vector<float> u, v, ur;
+    std::vector<int32_t> lvl;
+    std::vector<uint8_t> valid, desc;
+    explicit Queries(int n) : u(n), v(n), ur(n), lvl(n), valid(n, 0), desc((size_t)std::max(n, 1) * 32) {}
+};
+
+/* one direction of SearchBySim3 (:1149-1191 / :1228-1270): map points of `from`, camera pose (Rw, tw) of their key frame,
+ * similarity (sR, t) into the other key frame `to` */
+void sim3_queries(const std::vector<MapPoint*>& pts, const std::vector<bool>& already, const float* Rw, const float* tw,
+                  const float* sR, const float* t, KeyFrame* to, float fx, float fy, float cx, float cy, Queries& q) {
+    for (size_t i = 0; i < pts.size(); i++) {
+        MapPoint* pMP = pts[i];
+        if (!pMP || already[i]) continue;
+        if (pMP->isBad()) continue;
+        const cv::Mat p3Dw = pMP->GetWorldPos();
+        const float X = p3Dw.at<float>(0), Y = p3Dw.at<float>(1), Z = p3Dw.at<float>(2);
+        float a[3], b[3];
+        for (int r = 0; r < 3; r++) a[r] = Rw[3 * r] * X + Rw[3 * r + 1] * Y + Rw[3 * r + 2] * Z + tw[r];
+        for (int r = 0; r < 3; r++) b[r] = sR[3 * r] * a[0] + sR[3 * r + 1] * a[1] + sR[3 * r + 2] * a[2] + t[r];
+        if (b[2] < 0.0) continue;                                     /* depth must be positive */
+        const float invz = 1.0 / b[2];
+        const float x = b[0] * invz, y = b[1] * invz;
+        const float uu = fx * x + cx, vv = fy * y + cy;
+        if (!to->IsInImage(uu, vv)) continue;
+        const float dist3D = (float)std::sqrt((double)b[0] * b[0] + (double)b[1] * b[1] + (double)b[2] * b[2]);
+        if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+        q.u[i] = uu; q.v[i] = vv;
+        q.lvl[i] = pMP->PredictScale(dist3D, to);
+        memcpy(&q.desc[i * 32], pMP->GetDescriptor().ptr<uint8_t>(), 32);
+        q.valid[i] = 1;
+    }
+}
+
+}  // namespace
+
+int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12,
+                             const cv::Mat& R12, const cv::Mat& t12, const float th) {
+    const float fx = pKF1->fx, fy = pKF1->fy, cx = pKF1->cx, cy = pKF1->cy;
+    float R1w[9], t1w[3], R2w[9], t2w[3], sR12[9], sR21[9], t12f[3], t21[3];
+    const cv::Mat mR1w = pKF1->GetRotation(), mt1w = pKF1->GetTranslation(), mR2w = pKF2->GetRotation(), mt2w = pKF2->GetTranslation();
+    for (int r = 0; r < 3; r++) {
+        t1w[r] = mt1w.at<float>(r); t2w[r] = mt2w.at<float>(r); t12f[r] = t12.at<float>(r);
+        for (int c = 0; c < 3; c++) {
+            R1w[3 * r + c] = mR1w.at<float>(r, c); R2w[3 * r + c] = mR2w.at<float>(r, c);
+            sR12[3 * r + c] = s12 * R12.at<float>(r, c);                       /* :1119 */
+            sR21[3 * r + c] = (float)((1.0 / s12) * R12.at<float>(c, r));      /* :1120 */
+        }
+    }
+    for (int r = 0; r < 3; r++) t21[r] = -(sR21[3 * r] * t12f[0] + sR21[3 * r + 1] * t12f[1] + sR21[3 * r + 2] * t12f[2]);   /* :1121 */
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+    const int N1 = (int)vpMapPoints1.size(), N2 = (int)vpMapPoints2.size();
+    std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+    for (int i = 0; i < N1; i++) {                                             /* :1132-1143 */
+        MapPoint* pMP = vpMatches12[i];
+        if (pMP) {
+            vbAlreadyMatched1[i] = true;
+            const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+            if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
+        }
+    }
+    Queries q12(N1), q21(N2);
+    sim3_queries(vpMapPoints1, vbAlreadyMatched1, R1w, t1w, sR21, t21, pKF2, fx, fy, cx, cy, q12);
+    sim3_queries(vpMapPoints2, vbAlreadyMatched2, R2w, t2w, sR12, t12f, pKF1, fx, fy, cx, cy, q21);
+    FrameIndexGuard g1, g2;
+    make_kf_index(pKF1, g1);
+    make_kf_index(pKF2, g2);
+    std::vector<int32_t> match(std::max(N1, 1), -1);
+    int nFound = 0;
+    check(viorb_search_by_sim3(g1.fi, g2.fi, q12.u.data(), q12.v.data(), q12.lvl.data(), q12.valid.data(), q12.desc.data(),
+                               q21.u.data(), q21.v.data(), q21.lvl.data(), q21.valid.data(), q21.desc.data(), th, match.data(), &nFound),
+          "viorb_search_by_sim3");
+    for (int i1 = 0; i1 < N1; i1++)
+        if (match[i1] >= 0) vpMatches12[i1] = vpMapPoints2[match[i1]];         /* :1315 */
+    return nFound;
+}
+
+int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th) {
+    const cv::Mat mRcw = pKF->GetRotation(), mtcw = pKF->GetTranslation(), mOw = pKF->GetCameraCenter();
+    float Rcw[9], tcw[3], Ow[3];
+    for (int r = 0; r < 3; r++) {
+        tcw[r] = mtcw.at<float>(r); Ow[r] = mOw.at<float>(r);
+        for (int c = 0; c < 3; c++) Rcw[3 * r + c] = mRcw.at<float>(r, c);
+    }
+    const float fx = pKF->fx, fy = pKF->fy, cx = pKF->cx, cy = pKF->cy, bf = pKF->mbf;
+    const int nMPs = (int)vpMapPoints.size();
+    /* projection gates of :846-881 for every point that is not bad now; isBad / IsInKeyFrame are re-checked in order below */
+    auto project = [&](MapPoint* pMP, Queries& q, int i) {
+        q.valid[i] = 0;
+        const cv::Mat p3Dw = pMP->GetWorldPos();
+        const float X = p3Dw.at<float>(0), Y = p3Dw.at<float>(1), Z = p3Dw.at<float>(2);
+        float p[3];
+        for (int r = 0; r < 3; r++) p[r] = Rcw[3 * r] * X + Rcw[3 * r + 1] * Y + Rcw[3 * r + 2] * Z + tcw[r];
+        if (p[2] < 0.0f) return;
+        const float invz = 1 / p[2];
+        const float x = p[0] * invz, y = p[1] * invz;
+        const float u = fx * x + cx, v = fy * y + cy;
+        if (!pKF->IsInImage(u, v)) return;
+        const float ur = u - bf * invz;
+        const float px = X - Ow[0], py = Y - Ow[1], pz = Z - Ow[2];
+        const float dist3D = (float)std::sqrt((double)px * px + (double)py * py + (double)pz * pz);
+        if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) return;
+        const cv::Mat Pn = pMP->GetNormal();
+        if (px * Pn.at<float>(0) + py * Pn.at<float>(1) + pz * Pn.at<float>(2) < 0.5 * dist3D) return;
+        q.u[i] = u; q.v[i] = v; q.ur[i] = ur;
+        q.lvl[i] = pMP->PredictScale(dist3D, pKF);
+        memcpy(&q.desc[(size_t)i * 32], pMP->GetDescriptor().ptr<uint8_t>(), 32);
+        q.valid[i] = 1;
+    };
+    Queries q(nMPs);
+    std::vector<cv::Mat> descAtSearch(nMPs);
+    for (int i = 0; i < nMPs; i++) {
+        MapPoint* pMP = vpMapPoints[i];
+        if (!pMP || pMP->isBad()) continue;
+        project(pMP, q, i);
+        descAtSearch[i] = pMP->GetDescriptor();
+    }
+    FrameIndexGuard g;
+    make_kf_index(pKF, g);
+    std::vector<int32_t> best(std::max(nMPs, 1), -1);
+    check(viorb_search_window_top1(g.fi, q.u.data(), q.v.data(), q.ur.data(), q.lvl.data(), q.valid.data(), q.desc.data(), nMPs, th,
+                                   TH_LOW, pKF->mvInvLevelSigma2.data(), best.data(), nullptr),
+          "viorb_search_window_top1");
+    int nFused = 0;
+    for (int i = 0; i < nMPs; i++) {
+        MapPoint* pMP = vpMapPoints[i];
+        if (!pMP) continue;
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;                   /* :842-843, in loop order */
+        int bestIdx = best[i];
+        const cv::Mat dNow = pMP->GetDescriptor();
+        if (!q.valid[i] || dNow.data != descAtSearch[i].data || memcmp(dNow.ptr<uint8_t>(), &q.desc[(size_t)i * 32], 32) != 0) {
+            /* an earlier Replace recomputed this point's descriptor (MapPoint.cc:221): search it again on its own */
+            Queries q1(1);
+            project(pMP, q1, 0);
+            int32_t b1 = -1;
+            if (q1.valid[0])
+                check(viorb_search_window_top1(g.fi, q1.u.data(), q1.v.data(), q1.ur.data(), q1.lvl.data(), q1.valid.data(), q1.desc.data(), 1,
+                                               th, TH_LOW, pKF->mvInvLevelSigma2.data(), &b1, nullptr),
+                      "viorb_search_window_top1");
+            bestIdx = b1;
+        }
+        if (bestIdx < 0) continue;
+        MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx);                          /* :945-967 */
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) {
+                if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                else pMPinKF->Replace(pMP);
+            }
+        } else {
+            pMP->AddObservation(pKF, bestIdx);
+            pKF->AddMapPoint(pMP, bestIdx);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+
+int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint) {
+    float sR[9], Rcw[9], tcw[3], Ow[3];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) sR[3 * r + c] = Scw.at<float>(r, c);
+    const float scw = (float)std::sqrt((double)sR[0] * sR[0] + (double)sR[1] * sR[1] + (double)sR[2] * sR[2]);     /* :989 */
+    for (int i = 0; i < 9; i++) Rcw[i] = sR[i] / scw;
+    for (int r = 0; r < 3; r++) tcw[r] = Scw.at<float>(r, 3) / scw;
+    for (int r = 0; r < 3; r++) Ow[r] = -(Rcw[r] * tcw[0] + Rcw[3 + r] * tcw[1] + Rcw[6 + r] * tcw[2]);
+    const std::set<MapPoint*> spAlreadyFound = pKF->GetMapPoints();                                                /* :995 */
+    const int nPoints = (int)vpPoints.size();
+    Queries q(nPoints);
+    for (int i = 0; i < nPoints; i++) {
+        MapPoint* pMP = vpPoints[i];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+        const cv::Mat p3Dw = pMP->GetWorldPos();
+        const float X = p3Dw.at<float>(0), Y = p3Dw.at<float>(1), Z = p3Dw.at<float>(2);
+        float p[3];
+        for (int r = 0; r < 3; r++) p[r] = Rcw[3 * r] * X + Rcw[3 * r + 1] * Y + Rcw[3 * r + 2] * Z + tcw[r];
+        if (p[2] < 0.0f) continue;
+        const float invz = 1.0 / p[2];
+        const float u = pKF->fx * (p[0] * invz) + pKF->cx, v = pKF->fy * (p[1] * invz) + pKF->cy;
+        if (!pKF->IsInImage(u, v)) continue;
+        const float px = X - Ow[0], py = Y - Ow[1], pz = Z - Ow[2];
+        const float dist3D = (float)std::sqrt((double)px * px + (double)py * py + (double)pz * pz);
+        if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+        const cv::Mat Pn = pMP->GetNormal();
+        if (px * Pn.at<float>(0) + py * Pn.at<float>(1) + pz * Pn.at<float>(2) < 0.5 * dist3D) continue;
+        q.u[i] = u; q.v[i] = v;
+        q.lvl[i] = pMP->PredictScale(dist3D, pKF);
+        memcpy(&q.desc[(size_t)i * 32], pMP->GetDescriptor().ptr<uint8_t>(), 32);
+        q.valid[i] = 1;
+    }
+    FrameIndexGuard g;
+    make_kf_index(pKF, g);
+    std::vector<int32_t> best(std::max(nPoints, 1), -1);
+    check(viorb_search_window_top1(g.fi, q.u.data(), q.v.data(), nullptr, q.lvl.data(), q.valid.data(), q.desc.data(), nPoints, th, TH_LOW,
+                                   nullptr, best.data(), nullptr),
+          "viorb_search_window_top1");
+    int nFused = 0;
+    for (int iMP = 0; iMP < nPoints; iMP++) {                                   /* :1076-1094: no state read by later searches */
+        if (best[iMP] < 0) continue;
+        MapPoint* pMP = vpPoints[iMP];
+        MapPoint* pMPinKF = pKF->GetMapPoint(best[iMP]);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) vpReplacePoint[iMP] = pMPinKF;
+        } else {
+            pMP->AddObservation(pKF, best[iMP]);
+            pKF->AddMapPoint(pMP, best[iMP]);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+
 #ifndef VIORB_USE_ORBSLAM_HEADERS
 /* Frame::ComputeStereoMatches (reference src/Frame.cc:646-820) on the pyramids resident in the two extractors */
 void Frame::ComputeStereoMatches() {

@@ -4,7 +4,8 @@
  * SearchByBoW overloads and SearchForInitialization.  Each call marshals the fields the reference reads into flat
  * arrays and runs the whole search as CUDA kernels behind include/viorb_gpu.h; results (matches, counts,
  * tie-breaks, the "already matched" dependence) are identical to the reference's sequential loops.
- * The searches that mutate the map graph (SearchBySim3, Fuse x2) stay SURVEY.md section 8(f) "next" rows.
+ * SearchBySim3 and the two Fuse overloads run their search loops on the GPU in one call and then replay the reference's
+ * map-graph bookkeeping (Replace / AddObservation / AddMapPoint) on the host in the reference's order.
  */
 #ifndef ORBMATCHER_H
 #define ORBMATCHER_H
@@ -49,6 +50,15 @@ public:
     /* Matching for the map initialisation, monocular case only (:405-520) */
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
                                 int windowSize = 10);
+
+    /* Search matches between MapPoints seen in KF1 and KF2 transforming by a Sim3 [s12*R12|t12] (:1102-1326) */
+    int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12,
+                     const cv::Mat& t12, const float th);
+
+    /* Project MapPoints into KeyFrame and search for duplicated MapPoints (:825-976) */
+    int Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th = 3.0);
+    /* Project MapPoints into KeyFrame using a given Sim3 and search for duplicated MapPoints (:978-1100) */
+    int Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint);
 
     /* Matching to triangulate new MapPoints, epipolar constraint check (:657-823) */
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,

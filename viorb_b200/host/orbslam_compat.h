@@ -28,9 +28,22 @@ typedef std::map<unsigned int, double> BowVector;                          /* Th
 namespace ORB_SLAM2 {
 
 class ORBextractor;
+class KeyFrame;
 
 class MapPoint {   /* include/MapPoint.h */
 public:
+    /* observation bookkeeping used by Fuse / SearchBySim3 (include/MapPoint.h:55-64), reduced to what the searches touch */
+    std::map<KeyFrame*, size_t> mObservations;
+    MapPoint* mpReplaced = nullptr;
+    int descriptorEpoch = 0;                   /* bumped when Replace recomputes the distinctive descriptor */
+    void AddObservation(KeyFrame* pKF, size_t idx) {
+        if (mObservations.count(pKF)) return;
+        mObservations[pKF] = idx;
+        nObs++;
+    }
+    int GetIndexInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) ? (int)mObservations[pKF] : -1; }
+    bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }
+    inline void Replace(MapPoint* pMP);        /* src/MapPoint.cc:181-225 */
     bool mbTrackInView = false;                /* :85-89 tracking fields written by Frame::isInFrustum */
     float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0;
     int mnTrackScaleLevel = 0;
@@ -91,6 +104,17 @@ public:
     int mnScaleLevels = 8;
     float mfLogScaleFactor = 0.18232156f;
     cv::Mat Rcw, tcw, Ow;                      /* 3x3, 3x1, 3x1 CV_32F */
+    std::vector<float> mvInvLevelSigma2;
+    float mbf = 0;
+    void AddMapPoint(MapPoint* pMP, const size_t& idx) { mapPoints[idx] = pMP; }
+    void ReplaceMapPointMatch(const size_t& idx, MapPoint* pMP) { mapPoints[idx] = pMP; }
+    void EraseMapPointMatch(const size_t& idx) { mapPoints[idx] = nullptr; }
+    std::set<MapPoint*> GetMapPoints() const {
+        std::set<MapPoint*> s;
+        for (size_t i = 0; i < mapPoints.size(); i++)
+            if (mapPoints[i] && !mapPoints[i]->isBad()) s.insert(mapPoints[i]);
+        return s;
+    }
     MapPoint* GetMapPoint(size_t idx) const { return mapPoints[idx]; }
     std::vector<MapPoint*> GetMapPointMatches() const { return mapPoints; }
     bool IsInImage(const float& x, const float& y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }
@@ -98,6 +122,24 @@ public:
     cv::Mat GetRotation() const { return Rcw; }
     cv::Mat GetTranslation() const { return tcw; }
 };
+
+inline void MapPoint::Replace(MapPoint* pMP) {
+    if (pMP == this) return;
+    std::map<KeyFrame*, size_t> obs = mObservations;
+    mObservations.clear();
+    bad = true;
+    mpReplaced = pMP;
+    for (std::map<KeyFrame*, size_t>::iterator mit = obs.begin(); mit != obs.end(); ++mit) {
+        KeyFrame* pKF = mit->first;
+        if (!pMP->IsInKeyFrame(pKF)) {
+            pKF->ReplaceMapPointMatch(mit->second, pMP);
+            pMP->AddObservation(pKF, mit->second);
+        } else {
+            pKF->EraseMapPointMatch(mit->second);
+        }
+    }
+    pMP->descriptorEpoch++;                    /* pMP->ComputeDistinctiveDescriptors() */
+}
 
 }  // namespace ORB_SLAM2
 #endif
