@@ -30,6 +30,12 @@ def main():
     img[:] = synth.frame(480, 752, 0)
     ex = api.ORBextractor(1000, 1.2, 8, 20, 7, ctx=ctx)
     out["euroc_frame_extract"] = timeit(lambda: ex(img))
+    ex.profile(True)
+    for _ in range(50):
+        ex(img)
+    st, passes = ex.stage_ms()
+    ex.profile(False)
+    out["euroc_frame_stage_us"] = {k: 1e3 * v / max(passes, 1) for k, v in st.items()}
     left, right, _ = synth.stereo_pair(376, 1241, 7)
     exl, exr = api.ORBextractor(2000, 1.2, 8, 20, 7, ctx=ctx), api.ORBextractor(2000, 1.2, 8, 20, 7, ctx=ctx)
 

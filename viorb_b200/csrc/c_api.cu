@@ -105,6 +105,12 @@ struct viorb_extractor {
     } lanes[4];
     int nlanes = 2;
     cudaEvent_t evFork = nullptr;
+    int* hostStatus = nullptr;     /* pinned copy of the device status word (single-pass host path) */
+    /* CUDA graph of one single-frame pass (memset + 12 kernels) on lane 0: the per-frame call replays it instead of
+     * issuing 13 launches; rebuilt when the geometry, the buffers or the capacity change */
+    cudaGraphExec_t frameGraph = nullptr;
+    const void* graphKey[4] = {nullptr, nullptr, nullptr, nullptr};
+    int graphCap = 0, graphGen = -1, graphLaunches = 0, geomGen = 0;
     ExtractBuffers buf = {};       /* buffers of the most recent pass (resident pyramids, debug views) */
     /* staging for host-buffer entry points (double buffered) */
     DevBuf<uint8_t> in[2];
@@ -284,6 +290,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     cudaError_t ce = (cudaError_t)viorb_octree_prepare(nodeCap);
     if (ce != cudaSuccess) return fail(VIORB_ERR_CUDA, "octree kernel attribute: %s", cudaGetErrorString(ce));
     e->rows = rows; e->cols = cols;
+    e->geomGen++;                  /* invalidates the captured single-frame graph */
     for (int i = 0; i < 4; i++) e->lanes[i].allocFrames = 0;
     return VIORB_OK;
 }
@@ -477,6 +484,7 @@ int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, in
     build_tables(e);
     if (ctx_bind(ctx)) { delete e; return VIORB_ERR_CUDA; }
     cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
+    cudaHostAlloc((void**)&e->hostStatus, 64, cudaHostAllocDefault);
     if (getenv("VIORB_LANES")) e->nlanes = std::min(4, std::max(2, atoi(getenv("VIORB_LANES"))));   /* the host-buffer path pairs lanes with its two staging slots */
     for (int i = 0; i < 4; i++) {
         cudaStreamCreateWithFlags(&e->lanes[i].stream, cudaStreamNonBlocking);
@@ -505,6 +513,8 @@ int viorb_extractor_destroy(viorb_extractor* e) {
         ln.pyr.release(); ln.cand.release(); ln.sel.release(); ln.counters.release(); ln.nodeOf.release();
     }
     if (e->evFork) cudaEventDestroy(e->evFork);
+    if (e->hostStatus) cudaFreeHost(e->hostStatus);
+    if (e->frameGraph) cudaGraphExecDestroy(e->frameGraph);
     for (int i = 0; i < 2; i++) {
         e->in[i].release(); e->okps[i].release(); e->odesc[i].release(); e->ocnt[i].release();
         if (e->evIn[i]) cudaEventDestroy(e->evIn[i]);
@@ -652,8 +662,56 @@ static int extract_batch_once(viorb_extractor* e, const uint8_t* images, int B, 
         if ((rc = e->odesc[s].ensure((size_t)F * cap * 32))) return rc;
         if ((rc = e->ocnt[s].ensure(F))) return rc;
     }
-    /* pipeline: H2D(chunk k+1) || compute(chunk k) || D2H(chunk k-1), two staging slots */
     CU(cudaStreamSynchronize(c->stream));
+    if (B <= F && e->hostStatus && !e->profiling) {
+        /* one pass (the per-frame call of Frame::ExtractORB): copy in, kernels, copy out and the device status word
+         * on a single stream, one synchronisation -- no cross-stream events on the latency path */
+        viorb_extractor::Lane& ln = e->lanes[0];
+        cudaStream_t ls = ln.stream;
+        if (step == (size_t)cols && frame_stride == inFrame) {
+            CU(cudaMemcpyAsync(e->in[0].p, images, (size_t)B * inFrame, cudaMemcpyHostToDevice, ls));
+        } else if (frame_stride == step * rows) {
+            CU(cudaMemcpy2DAsync(e->in[0].p, cols, images, step, cols, (size_t)rows * B, cudaMemcpyHostToDevice, ls));
+        } else {
+            for (int i = 0; i < B; i++)
+                CU(cudaMemcpy2DAsync(e->in[0].p + (size_t)i * inFrame, cols, images + (size_t)i * frame_stride, step, cols, rows,
+                                     cudaMemcpyHostToDevice, ls));
+        }
+        if (B == 1 && !getenv("VIORB_NO_GRAPH")) {
+            const void* key[4] = {e->in[0].p, e->okps[0].p, e->odesc[0].p, ln.buf.pyr};
+            if (!e->frameGraph || memcmp(key, e->graphKey, sizeof(key)) != 0 || e->graphCap != cap || e->graphGen != e->geomGen) {
+                if (e->frameGraph) { cudaGraphExecDestroy(e->frameGraph); e->frameGraph = nullptr; }
+                cudaGraph_t graph = nullptr;
+                CU(cudaStreamBeginCapture(ls, cudaStreamCaptureModeThreadLocal));
+                const long long before = c->launches;
+                rc = run_pass(e, 0, e->in[0].p, cols, inFrame, 1, e->okps[0].p, e->odesc[0].p, cap, e->ocnt[0].p);
+                e->graphLaunches = (int)(c->launches - before);
+                c->launches = before;
+                cudaError_t ce = cudaStreamEndCapture(ls, &graph);
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (ce != cudaSuccess) return fail(VIORB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+                ce = cudaGraphInstantiate(&e->frameGraph, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) { e->frameGraph = nullptr; return fail(VIORB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)); }
+                memcpy(e->graphKey, key, sizeof(key));
+                e->graphCap = cap; e->graphGen = e->geomGen;
+            }
+            CU(cudaGraphLaunch(e->frameGraph, ls));
+            c->launches += e->graphLaunches;
+            e->buf = ln.buf;
+        } else if ((rc = run_pass(e, 0, e->in[0].p, cols, inFrame, B, e->okps[0].p, e->odesc[0].p, cap, e->ocnt[0].p))) {
+            return rc;
+        }
+        CU(cudaMemcpyAsync(kps, e->okps[0].p, (size_t)B * cap * sizeof(viorb_keypoint), cudaMemcpyDeviceToHost, ls));
+        CU(cudaMemcpyAsync(desc, e->odesc[0].p, (size_t)B * cap * 32, cudaMemcpyDeviceToHost, ls));
+        CU(cudaMemcpyAsync(counts, e->ocnt[0].p, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, ls));
+        CU(cudaMemcpyAsync(e->hostStatus, ln.buf.status, sizeof(int), cudaMemcpyDeviceToHost, ls));
+        CU(cudaStreamSynchronize(ls));
+        e->residentFirst = 0; e->residentCount = B;
+        if (*e->hostStatus == 0) { e->lastOverflow = 0; return VIORB_OK; }
+        return check_status(e);          /* rare: reads, reports and clears the device status */
+    }
+    /* pipeline: H2D(chunk k+1) || compute(chunk k) || D2H(chunk k-1), two staging slots */
     int k = 0;
     for (int b0 = 0; b0 < B; b0 += F, k++) {
         const int s = k & 1;
