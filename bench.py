@@ -300,6 +300,35 @@ def main():
     h2d = nloc * rows * cols
     d2h = nloc * cap * 60 + nloc * 4
 
+    # ---- per-call latency of the drop-in entry points (configs[0]: one EuRoC frame; configs[1]: KITTI stereo pair) ----
+    latency = None
+    if rank == 0:
+        def med_ms(fn, n, warm):
+            for _ in range(warm):
+                fn()
+            ts = []
+            for _ in range(n):
+                t0 = time.perf_counter()
+                fn()
+                ts.append((time.perf_counter() - t0) * 1e3)
+            return float(np.median(ts))
+        one = h_imgs[0]
+        lat_frame = med_ms(lambda: ex(one), 100, 10)
+        left, right, _ = synth.stereo_pair(376, 1241, 7)
+        exl = api.ORBextractor(2000, 1.2, 8, 20, 7, ctx=ctx)
+        exr = api.ORBextractor(2000, 1.2, 8, 20, 7, ctx=ctx)
+
+        def stereo_pair():
+            kl, dl = exl(left)
+            kr, dr = exr(right)
+            api.ComputeStereoMatches(exl, exr, kl, dl, kr, dr, 386.1448, 386.1448 / 718.856)
+
+        lat_pair = med_ms(stereo_pair, 30, 5)
+        exl.close()
+        exr.close()
+        latency = {"configs[0] one 752x480 frame, viorb_extract host->host, median ms": lat_frame,
+                   "configs[1] KITTI 1241x376 stereo pair, 2 x viorb_extract + viorb_stereo_match, median ms": lat_pair}
+
     # ---- roofline of the dominant kernel (live CUDA-event stage timing inside the timed region) ----
     peaks = {}
     try:
@@ -324,18 +353,24 @@ def main():
     step_achieved = BYTES_PER_FRAME_EUROC * value / world / 1e9
     # dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json,
     # written by tools/ncu_summary.py; same launch shape: 128 frames per pass)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, pipes = None, None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         names = {"pyramid": ["pyr_level0_kernel", "pyr_resize_kernel"], "fast": ["fast_cells_kernel"],
                  "octree": ["octree_kernel"], "describe": ["orient_describe_kernel"]}[dom]
         if all(n in tj for n in names) and int(round(frames_per_pass)) == 128:
             traffic = float(sum(l["dram_bytes"] for n in names for l in tj[n]["launches"]))
+            l0 = tj[names[0]]["launches"][0]
+            if l0.get("alu_pipe_pct") is not None:
+                pipes = {"alu_pipe_pct_of_peak": l0["alu_pipe_pct"], "issue_active_pct": l0["issue_active_pct"],
+                         "dram_pct_of_peak": l0.get("dram_pct"),
+                         "note": "same ncu capture: the kernel is bound by the integer ALU pipe (64 lanes/clk/SM measured, "
+                                 "tools/ubench/pipes.cu), not by HBM"}
             traffic_src = "ncu --set full, %s (dram__bytes_read.sum + dram__bytes_write.sum per 128-frame launch)" % tj[names[0]]["source"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": kernel_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "pipes": pipes, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg[dom] * frames_per_pass, "avg_launch_ms": dom_ms_per_launch,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
                 "stage_timing": "separate pass of the same %d steps with per-stage CUDA events, single lane: %.2f ms/step "
@@ -441,6 +476,7 @@ def main():
             "keypoints_per_frame": total_kp / nloc,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "latency": latency,
             "matcher": matcher,
         }
         print(json.dumps(line), flush=True)

@@ -98,8 +98,13 @@ def main():
             if e.get("source") != tag:
                 e.clear()
                 e.update({"source": tag, "launches": []})
+            def pct(name):
+                return float(r[hdr.index(name)].replace(",", "")) if name in hdr else None
             e["launches"].append({"grid": int(grid), "dram_bytes": rd + wr,
-                                  "us": float(r[hdr.index("gpu__time_duration.sum")].replace(",", ""))})
+                                  "us": float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")),
+                                  "alu_pipe_pct": pct("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                                  "issue_active_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                  "dram_pct": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")})
             md.append("")
         # ---- SASS phase breakdown between barriers for the two big kernels
         for kname in ("fast_cells_kernel", "orient_describe_kernel", "pyr_resize_kernel"):

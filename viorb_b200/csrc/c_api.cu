@@ -103,7 +103,7 @@ struct viorb_extractor {
         DevBuf<uint16_t> nodeOf;
         TmaMaps maps;              /* TMA descriptors of this lane's pyramid buffer */
     } lanes[4];
-    int nlanes = 2;
+    int nlanes = 4;
     cudaEvent_t evFork = nullptr;
     int* hostStatus = nullptr;     /* pinned copy of the device status word (single-pass host path) */
     /* CUDA graph of one single-frame pass (memset + 12 kernels) on lane 0: the per-frame call replays it instead of
@@ -113,11 +113,14 @@ struct viorb_extractor {
     int graphCap = 0, graphGen = -1, graphLaunches = 0, geomGen = 0;
     ExtractBuffers buf = {};       /* buffers of the most recent pass (resident pyramids, debug views) */
     /* staging for host-buffer entry points (double buffered) */
-    DevBuf<uint8_t> in[2];
-    DevBuf<viorb_keypoint> okps[2];
-    DevBuf<uint8_t> odesc[2];
-    DevBuf<int32_t> ocnt[2];
-    cudaEvent_t evIn[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
+    /* host-buffer path: VIORB_SLOTS staging slots, slot s runs on lane s (H2D(k+2) || H2D(k+1) || compute(k) || D2H(k-1)) */
+    DevBuf<uint8_t> in[4];
+    DevBuf<viorb_keypoint> okps[4];
+    DevBuf<uint8_t> odesc[4];
+    DevBuf<int32_t> ocnt[4];
+    cudaEvent_t evIn[4] = {nullptr, nullptr, nullptr, nullptr}, evDone[4] = {nullptr, nullptr, nullptr, nullptr},
+                evOut[4] = {nullptr, nullptr, nullptr, nullptr};
+    int nslots = 4;
     int residentFirst = 0, residentCount = 0;
     int lastOverflow = 0;
     bool profiling = false;
@@ -490,7 +493,9 @@ int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, in
         cudaStreamCreateWithFlags(&e->lanes[i].stream, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&e->lanes[i].evDone, cudaEventDisableTiming);
     }
-    for (int i = 0; i < 2; i++) {
+    if (getenv("VIORB_SLOTS")) e->nslots = std::min(4, std::max(2, atoi(getenv("VIORB_SLOTS"))));
+    e->nlanes = std::max(e->nlanes, e->nslots);
+    for (int i = 0; i < 4; i++) {
         cudaEventCreateWithFlags(&e->evIn[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->evDone[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->evOut[i], cudaEventDisableTiming);
@@ -515,7 +520,7 @@ int viorb_extractor_destroy(viorb_extractor* e) {
     if (e->evFork) cudaEventDestroy(e->evFork);
     if (e->hostStatus) cudaFreeHost(e->hostStatus);
     if (e->frameGraph) cudaGraphExecDestroy(e->frameGraph);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 4; i++) {
         e->in[i].release(); e->okps[i].release(); e->odesc[i].release(); e->ocnt[i].release();
         if (e->evIn[i]) cudaEventDestroy(e->evIn[i]);
         if (e->evDone[i]) cudaEventDestroy(e->evDone[i]);
@@ -656,7 +661,8 @@ static int extract_batch_once(viorb_extractor* e, const uint8_t* images, int B, 
     const int F = std::min(e->chunk, B);
     if ((rc = ensure_workspace(e, F))) return rc;
     const size_t inFrame = (size_t)rows * cols;        /* device copy is packed */
-    for (int s = 0; s < 2; s++) {
+    const int nslots = B <= F ? 1 : std::min(e->nslots, (B + F - 1) / F);
+    for (int s = 0; s < nslots; s++) {
         if ((rc = e->in[s].ensure((size_t)F * inFrame))) return rc;
         if ((rc = e->okps[s].ensure((size_t)F * cap))) return rc;
         if ((rc = e->odesc[s].ensure((size_t)F * cap * 32))) return rc;
@@ -711,12 +717,12 @@ static int extract_batch_once(viorb_extractor* e, const uint8_t* images, int B, 
         if (*e->hostStatus == 0) { e->lastOverflow = 0; return VIORB_OK; }
         return check_status(e);          /* rare: reads, reports and clears the device status */
     }
-    /* pipeline: H2D(chunk k+1) || compute(chunk k) || D2H(chunk k-1), two staging slots */
+    /* pipeline: H2D(chunks k+1, k+2) || compute(chunk k) || D2H(chunk k-1), `nslots` staging slots */
     int k = 0;
     for (int b0 = 0; b0 < B; b0 += F, k++) {
-        const int s = k & 1;
+        const int s = k % nslots;
         const int f = std::min(F, B - b0);
-        if (k >= 2) {
+        if (k >= nslots) {
             CU(cudaStreamWaitEvent(c->h2d, e->evDone[s], 0));    /* slot input free once its compute finished */
         }
         if (step == (size_t)cols && frame_stride == inFrame) {       /* packed frames: one flat copy */
@@ -732,7 +738,7 @@ static int extract_batch_once(viorb_extractor* e, const uint8_t* images, int B, 
         CU(cudaEventRecord(e->evIn[s], c->h2d));
         cudaStream_t ls = e->lanes[s].stream;
         CU(cudaStreamWaitEvent(ls, e->evIn[s], 0));
-        if (k >= 2) CU(cudaStreamWaitEvent(ls, e->evOut[s], 0));     /* slot outputs free once copied out */
+        if (k >= nslots) CU(cudaStreamWaitEvent(ls, e->evOut[s], 0));     /* slot outputs free once copied out */
         if ((rc = run_pass(e, s, e->in[s].p, cols, inFrame, f, e->okps[s].p, e->odesc[s].p, cap, e->ocnt[s].p))) return rc;
         CU(cudaEventRecord(e->evDone[s], ls));
         CU(cudaStreamWaitEvent(c->d2h, e->evDone[s], 0));
