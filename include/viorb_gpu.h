@@ -164,6 +164,13 @@ int viorb_frame_index_create_distorted(viorb_ctx* ctx, const viorb_keypoint* kps
                                        const float* u_right, int n, float fx, float fy, float cx, float cy,
                                        const float* dist_coef, int ndist, int cols, int rows,
                                        const float* scale_factors, int nlevels, viorb_frame_index** out);
+/* The same from DEVICE-resident raw keypoints / descriptors (one frame's slice of the viorb_extract_batch_device
+ * outputs): extraction -> undistortion -> grid -> matching without the keypoints ever visiting the host.
+ * d_u_right may be NULL (monocular: all -1).                                                                     */
+int viorb_frame_index_create_device(viorb_ctx* ctx, const viorb_keypoint* d_kps, const uint8_t* d_desc,
+                                    const float* d_u_right, int n, float fx, float fy, float cx, float cy,
+                                    const float* dist_coef, int ndist, int cols, int rows,
+                                    const float* scale_factors, int nlevels, viorb_frame_index** out);
 /* mvKeysUn (may be NULL) and {mnMinX, mnMaxX, mnMinY, mnMaxY} (may be NULL) of an index */
 int viorb_frame_index_keys(viorb_frame_index* fi, viorb_keypoint* kps_un, float bounds[4]);
 /* stand-alone forms of the two Frame members, host buffers */

@@ -174,3 +174,50 @@ def test_parameter_sweep(api, ctx, oracle, cfg):
     k2, d2 = ex(wide[:, 5:5 + w])          # unaligned base pointer and row stride
     assert_same_output(k2, d2, k_ref, d_ref)
     ex.close()
+
+
+def test_device_batch_path_and_device_frame_index(api, ctx, oracle):
+    """viorb_extract_batch_device (device frames in, device outputs, ragged last pass) returns the bytes of the host
+    path, and a frame index built from its device outputs (undistortion + grid on the device, no host round trip)
+    equals the oracle's undistorted keypoints and grid queries"""
+    torch = pytest.importorskip("torch")
+    h, w, nf, sf, nl, it, mt = CONFIGS["euroc"]
+    B = 9
+    imgs = synth.frames(B, h, w, seed0=40)
+    ex = api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx)
+    ex.configure(chunk_frames=4)
+    kps_h, desc_h, cnt_h = ex.extract_batch(imgs)
+    cap = ex.cap
+    d_imgs = torch.from_numpy(imgs).cuda()
+    d_kps = torch.zeros((B, cap, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ex.extract_batch_device(d_imgs, B, h, w, d_kps, d_desc, d_cnt)
+    ex.check()
+    cnt_d = d_cnt.cpu().numpy()
+    assert (cnt_d == cnt_h).all()
+    kd = d_kps.cpu().numpy().view(np.uint8).reshape(B, cap, 28)
+    dd = d_desc.cpu().numpy()
+    kh = np.ascontiguousarray(kps_h).view(np.uint8).reshape(B, cap, 28)
+    for b in range(B):
+        n = int(cnt_h[b])
+        assert (kd[b, :n] == kh[b, :n]).all() and (dd[b, :n] == np.asarray(desc_h)[b, :n]).all()
+    # frame 3 straight from the device outputs into a matcher index
+    K, dist = (458.654, 457.296, 367.215, 248.375), [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05]
+    b, n = 3, int(cnt_h[3])
+    sfs = ex.GetScaleFactors()
+    fi = api.FrameIndex.from_device(ctx, d_kps[b], d_desc[b], n, K, dist, (w, h), sfs)
+    k_un, bounds = fi.keys()
+    raw = np.ascontiguousarray(kps_h[b][:n])
+    ref = oracle.undistort_keypoints(raw, *K, dist)
+    bref = oracle.compute_image_bounds(w, h, *K, dist)
+    assert k_un.tobytes() == ref.tobytes() and (bounds.view(np.uint32) == bref.view(np.uint32)).all()
+    g = oracle.Grid(ref, *[float(v) for v in bref])
+    rng = np.random.default_rng(0)
+    for _ in range(30):
+        x, y, r = float(rng.uniform(0, w)), float(rng.uniform(0, h)), float(rng.choice([8.0, 30.0]))
+        a, c = fi.GetFeaturesInArea(x, y, r), g.features_in_area(x, y, r)
+        assert len(a) == len(c) and (a == c).all()
+    fi.close()
+    ex.close()

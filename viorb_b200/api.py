@@ -69,6 +69,7 @@ def lib():
         "viorb_frame_index_create": [vp, vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, pp],
         "viorb_frame_index_destroy": [vp],
         "viorb_frame_index_create_distorted": [vp, vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, i32, i32, vp, i32, pp],
+        "viorb_frame_index_create_device": [vp, vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, i32, i32, vp, i32, pp],
         "viorb_frame_index_keys": [vp, vp, vp],
         "viorb_undistort_keypoints": [vp, vp, i32, f32, f32, f32, f32, vp, i32, vp],
         "viorb_compute_image_bounds": [vp, i32, i32, f32, f32, f32, f32, vp, i32, vp],
@@ -317,6 +318,21 @@ class FrameIndex:
                                                      image_size[0], image_size[1], _ptr(sf), len(sf), C.byref(h)))
         self.h = h
         self.n = len(self.kps)
+        return self
+
+    @classmethod
+    def from_device(cls, ctx, d_kps, d_desc, n, K, dist_coef, image_size, scale_factors, d_u_right=None):
+        """the same from device-resident raw keypoints / descriptors (a frame's slice of extract_batch_device outputs)"""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        dc = np.ascontiguousarray(dist_coef, np.float32).ravel()
+        h = C.c_void_p()
+        _ck(lib().viorb_frame_index_create_device(ctx.h, _ptr(d_kps), _ptr(d_desc), _ptr(d_u_right), n, K[0], K[1], K[2], K[3],
+                                                  _ptr(dc) if len(dc) else None, len(dc), image_size[0], image_size[1],
+                                                  _ptr(sf), len(sf), C.byref(h)))
+        self.h = h
+        self.n = n
         return self
 
     def keys(self):

@@ -164,7 +164,7 @@ static int make_undistort_params(float fx, float fy, float cx, float cy, const f
 /* shared by the two constructors: kps are already undistorted (und == NULL) or are undistorted on the device */
 static int frame_index_build(viorb_ctx* c, const viorb_keypoint* kps, const uint8_t* desc, const float* u_right, int n,
                              const UndistortParams* und, int cols, int rows, const float* bounds_in,
-                             const float* scale_factors, int nlevels, viorb_frame_index** out) {
+                             const float* scale_factors, int nlevels, viorb_frame_index** out, bool deviceInputs = false) {
     if (n >= (1 << 20)) return viorb_fail(VIORB_ERR_UNSUPPORTED, "more than 2^20 keypoints in one frame");
     *out = nullptr;
     int rc;
@@ -188,9 +188,22 @@ static int frame_index_build(viorb_ctx* c, const viorb_keypoint* kps, const uint
     fi->ctx = c; fi->n = n; fi->cellOf = cellOf;
     cudaStream_t s = viorb_ctx_stream(c);
     std::vector<float> ur;
-    if (!u_right) { ur.assign(nn, -1.0f); u_right = ur.data(); }
-    if ((rc = upload(c, und ? draw : dk, kps, n)) || (rc = upload(c, dd, desc, (size_t)n * 32)) || (rc = upload(c, dur, u_right, n))) {
-        cudaFree(fi->mem); delete fi; return rc;
+    if (!u_right) { ur.assign(nn, -1.0f); }
+    if (deviceInputs) {
+        /* keypoints and descriptors are already on the device (viorb_extract_batch_device outputs): device-to-device */
+        cudaError_t ce = cudaSuccess;
+        if (n > 0) ce = cudaMemcpyAsync(und ? draw : dk, kps, (size_t)n * sizeof(viorb_keypoint), cudaMemcpyDeviceToDevice, s);
+        if (ce == cudaSuccess && n > 0) ce = cudaMemcpyAsync(dd, desc, (size_t)n * 32, cudaMemcpyDeviceToDevice, s);
+        if (ce == cudaSuccess && n > 0)
+            ce = u_right ? cudaMemcpyAsync(dur, u_right, (size_t)n * 4, cudaMemcpyDeviceToDevice, s)
+                         : cudaMemcpyAsync(dur, ur.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s);
+        if (ce == cudaSuccess && !u_right) ce = cudaStreamSynchronize(s);          /* ur is a local */
+        if (ce != cudaSuccess) { cudaFree(fi->mem); delete fi; return viorb_fail(VIORB_ERR_CUDA, "device copy: %s", cudaGetErrorString(ce)); }
+    } else {
+        if (!u_right) u_right = ur.data();
+        if ((rc = upload(c, und ? draw : dk, kps, n)) || (rc = upload(c, dd, desc, (size_t)n * 32)) || (rc = upload(c, dur, u_right, n))) {
+            cudaFree(fi->mem); delete fi; return rc;
+        }
     }
     float b[4] = {0, 0, 0, 0};
     if (und) {
@@ -236,6 +249,17 @@ int viorb_frame_index_create_distorted(viorb_ctx* c, const viorb_keypoint* kps, 
     int rc;
     if ((rc = make_undistort_params(fx, fy, cx, cy, dist_coef, ndist, &p))) return rc;
     return frame_index_build(c, kps, desc, u_right, n, &p, cols, rows, nullptr, scale_factors, nlevels, out);
+}
+
+int viorb_frame_index_create_device(viorb_ctx* c, const viorb_keypoint* d_kps, const uint8_t* d_desc, const float* d_u_right, int n,
+                                    float fx, float fy, float cx, float cy, const float* dist_coef, int ndist, int cols, int rows,
+                                    const float* scale_factors, int nlevels, viorb_frame_index** out) {
+    if (!c || !out || n < 0 || (n > 0 && (!d_kps || !d_desc)) || !scale_factors || nlevels < 1 || nlevels > 12 || cols <= 0 || rows <= 0)
+        return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    UndistortParams p;
+    int rc;
+    if ((rc = make_undistort_params(fx, fy, cx, cy, dist_coef, ndist, &p))) return rc;
+    return frame_index_build(c, d_kps, d_desc, d_u_right, n, &p, cols, rows, nullptr, scale_factors, nlevels, out, true);
 }
 
 int viorb_frame_index_keys(viorb_frame_index* fi, viorb_keypoint* kps_un, float bounds[4]) {
