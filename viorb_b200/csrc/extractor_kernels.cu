@@ -14,6 +14,7 @@
 #include "extractor_kernels.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "viorb_orb_pattern.h"
@@ -46,12 +47,11 @@ __device__ __forceinline__ uint4 load16_any(const uint8_t* p) {
     return make_uint4(__byte_perm(v0, v1, sel), __byte_perm(v1, v2, sel), __byte_perm(v2, v3, sel), __byte_perm(v3, v4, sel));
 }
 
-__global__ void __launch_bounds__(256) pyr_level0_kernel(const __grid_constant__ FrameGeom g,
-                                                         const uint8_t* __restrict__ images, size_t inStep,
-                                                         size_t frameStride, uint8_t* __restrict__ pyr, int aligned) {
+__device__ __forceinline__ void pyr_level0_tile(const FrameGeom& g, const uint8_t* __restrict__ images, size_t inStep,
+                                                size_t frameStride, uint8_t* __restrict__ pyr, int aligned, int rowBlock,
+                                                int frame) {
     const LevelGeom& L = g.lv[0];
-    const int frame = blockIdx.y;
-    const int row0 = blockIdx.x * L0_ROWS;                      /* first stored row of this CTA */
+    const int row0 = rowBlock * L0_ROWS;                        /* first stored row of this tile */
     const int nrows = min(L0_ROWS, L.h + 2 * VIORB_EDGE - row0);
     const int V = L.step >> 4;                                   /* 16-byte vectors per stored row */
     /* interior vectors: x0 = 16*vi - 32 >= 0 and x0 + 16 <= w */
@@ -91,6 +91,12 @@ __global__ void __launch_bounds__(256) pyr_level0_kernel(const __grid_constant__
     }
 }
 
+__global__ void __launch_bounds__(256) pyr_level0_kernel(const __grid_constant__ FrameGeom g,
+                                                         const uint8_t* __restrict__ images, size_t inStep,
+                                                         size_t frameStride, uint8_t* __restrict__ pyr, int aligned) {
+    pyr_level0_tile(g, images, inStep, frameStride, pyr, aligned, blockIdx.x, blockIdx.y);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * ComputePyramid level l > 0: resize(level l-1 ROI -> level l ROI, INTER_LINEAR) then
  * copyMakeBorder(..., BORDER_REFLECT_101 + BORDER_ISOLATED)                     (:1120-1123)
@@ -118,25 +124,25 @@ __device__ __forceinline__ void reflected_range(int a, int b, int n, int& dmin, 
     dmax = (a <= n - 1 && b >= n - 1) ? n - 1 : max(ra, rb);
 }
 
-__global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__ FrameGeom g, int level,
-                                                         ResizeTables t, uint8_t* __restrict__ pyr) {
-    __shared__ __align__(16) uint8_t src[RZ_SROWS * RZ_SSTRIDE];
-    __shared__ uint4 rowInfo[RZ_TH];          /* {staged byte offset of row sy | of row sy+1 << 16, b0 << 16, b1 << 16, -} */
+/* one 128 x 64 tile (bx, by) of level `level` of frame `frame`; 128 threads; src / rowInfo are the CTA's shared buffers */
+template <int WROWS>      /* rows per warp: tile height = 4 * WROWS (64 for batches, 16 for the per-frame latency path) */
+__device__ __forceinline__ void pyr_resize_tile(const FrameGeom& g, int level, const ResizeTables& t, uint8_t* __restrict__ pyr,
+                                                int bx, int by, int frame, uint8_t* src, uint4* rowInfo) {
+    constexpr int TH = 4 * WROWS;
     const LevelGeom& L = g.lv[level];
     const LevelGeom& P = g.lv[level - 1];
-    const int frame = blockIdx.z;
     const int tid = threadIdx.x;
     uint8_t* base = pyr + (size_t)frame * g.pyrFrameBytes;
     /* tile in ROI coordinates of level l: columns [xa, xa+128), rows [ya, ya+64) */
-    const int xa = blockIdx.x * RZ_TW - VIORB_ROI_X0, ya = blockIdx.y * RZ_TH - VIORB_EDGE;
+    const int xa = bx * RZ_TW - VIORB_ROI_X0, ya = by * TH - VIORB_EDGE;
     const int xlo = max(xa, -VIORB_EDGE), xhi = min(xa + RZ_TW - 1, L.w + VIORB_EDGE - 1);
-    const int ylo = ya, yhi = min(ya + RZ_TH - 1, L.h + VIORB_EDGE - 1);
+    const int ylo = ya, yhi = min(ya + TH - 1, L.h + VIORB_EDGE - 1);
     const int stepWords = L.step >> 2;
-    const int wi = blockIdx.x * (RZ_TW / 4) + (tid & 31);          /* stored word of this thread */
-    const int r0 = (tid >> 5) * RZ_WROWS;
+    const int wi = bx * (RZ_TW / 4) + (tid & 31);          /* stored word of this thread */
+    const int r0 = (tid >> 5) * WROWS;
     if (xlo > xhi) {                                                  /* only alignment padding: write zeros */
         if (wi < stepWords)
-            for (int r = r0; r < r0 + RZ_WROWS; r++)
+            for (int r = r0; r < r0 + WROWS; r++)
                 if (ya + r <= yhi) reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(ya + r + VIORB_EDGE) * L.step)[wi] = 0;
         return;
     }
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
                 *reinterpret_cast<uint4*>(&src[r * RZ_SSTRIDE + 16 * v]) =
                     *reinterpret_cast<const uint4*>(sroi + (size_t)(sy0 + r) * P.step + sx0 + 16 * v);
     }
-    if (tid < RZ_TH && ya + tid <= yhi) {
+    if (tid < TH && ya + tid <= yhi) {
         const int dy = reflect101(ya + tid, L.h);
         const int sy = t.yofs[L.ytab + dy];
         const unsigned b0 = (unsigned)t.yb[2 * (L.ytab + dy)], b1 = (unsigned)t.yb[2 * (L.ytab + dy) + 1];
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
     unsigned prevO1 = 0xffffffffu;
     unsigned Tp[4] = {0, 0, 0, 0};
     uint32_t* out = reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(ya + r0 + VIORB_EDGE) * L.step) + wi;
-    for (int r = r0; r < r0 + RZ_WROWS; r++, out += stepWords) {
+    for (int r = r0; r < r0 + WROWS; r++, out += stepWords) {
         if (ya + r > yhi) break;
         const uint4 ri = rowInfo[r];
         const unsigned o0 = ri.x & 0xffffu, o1 = ri.x >> 16;
@@ -223,6 +229,14 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
         prevO1 = o1;
         *out = word & okMask;
     }
+}
+
+template <int WROWS>
+__global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__ FrameGeom g, int level,
+                                                         ResizeTables t, uint8_t* __restrict__ pyr) {
+    __shared__ __align__(16) uint8_t src[(4 * WROWS * 3 / 2 + 4) * RZ_SSTRIDE];
+    __shared__ uint4 rowInfo[4 * WROWS];      /* {staged byte offset of row sy | of row sy+1 << 16, b0 << 16, b1 << 16, -} */
+    pyr_resize_tile<WROWS>(g, level, t, pyr, blockIdx.x, blockIdx.y, blockIdx.z, src, rowInfo);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -1195,16 +1209,21 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
 /* ------------------------------------------------------------------------------------------------ launchers */
 int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_t* d_images, size_t step,
                          size_t frameStride, int F, const ExtractBuffers& b, cudaStream_t s) {
+    const int aligned = ((uintptr_t)d_images % 16 == 0) && (step % 16 == 0) && (frameStride % 16 == 0);
     int launches = 0;
     for (int l = 0; l < g.nlevels; l++) {
         const LevelGeom& L = g.lv[l];
         if (l == 0) {
             dim3 grid((L.h + 2 * VIORB_EDGE + L0_ROWS - 1) / L0_ROWS, F);
-            const int aligned = ((uintptr_t)d_images % 16 == 0) && (step % 16 == 0) && (frameStride % 16 == 0);
             pyr_level0_kernel<<<grid, 256, 0, s>>>(g, d_images, step, frameStride, b.pyr, aligned);
         } else {
-            dim3 grid((L.step + RZ_TW - 1) / RZ_TW, (L.h + 2 * VIORB_EDGE + RZ_TH - 1) / RZ_TH, F);
-            pyr_resize_kernel<<<grid, 128, 0, s>>>(g, l, t, b.pyr);
+            if (F <= 8) {        /* few frames: 128 x 16 tiles, four times the CTAs, a quarter of the per-tile latency */
+                dim3 grid((L.step + RZ_TW - 1) / RZ_TW, (L.h + 2 * VIORB_EDGE + 15) / 16, F);
+                pyr_resize_kernel<4><<<grid, 128, 0, s>>>(g, l, t, b.pyr);
+            } else {
+                dim3 grid((L.step + RZ_TW - 1) / RZ_TW, (L.h + 2 * VIORB_EDGE + RZ_TH - 1) / RZ_TH, F);
+                pyr_resize_kernel<RZ_WROWS><<<grid, 128, 0, s>>>(g, l, t, b.pyr);
+            }
         }
         launches++;
     }
