@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--queries", type=int, default=1000)
     ap.add_argument("--no-matcher", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the per-call latency block (profiling runs)")
     ap.add_argument("--cpu-frames", type=int, default=2048, help="frames of the CPU-baseline sample (about 30 CPU-seconds)")
     return ap.parse_args()
 
@@ -302,7 +303,7 @@ def main():
 
     # ---- per-call latency of the drop-in entry points (configs[0]: one EuRoC frame; configs[1]: KITTI stereo pair) ----
     latency = None
-    if rank == 0:
+    if rank == 0 and not args.no_latency:
         def med_ms(fn, n, warm):
             for _ in range(warm):
                 fn()

@@ -221,3 +221,21 @@ def test_device_batch_path_and_device_frame_index(api, ctx, oracle):
         assert len(a) == len(c) and (a == c).all()
     fi.close()
     ex.close()
+
+
+def test_two_extractors_with_different_quotas_interleaved(api, ctx, oracle):
+    """the quadtree kernel's opt-in shared-memory limit is per kernel, not per extractor: a small-quota extractor
+    created after a large-quota one must not break the large one"""
+    big_cfg, small_cfg = CONFIGS["hd"], (240, 320, 150, 1.2, 4, 20, 7)
+    img_b, img_s = synth.frame(big_cfg[0], big_cfg[1], 2), synth.frame(small_cfg[0], small_cfg[1], 3)
+    ex_b = api.ORBextractor(*big_cfg[2:], ctx=ctx)
+    kb, db = ex_b(img_b)
+    ex_s = api.ORBextractor(*small_cfg[2:], ctx=ctx)
+    ks, ds = ex_s(img_s)
+    kb2, db2 = ex_b(img_b)                       # the large extractor again, after the small one was set up
+    assert kb2.tobytes() == kb.tobytes() and (db2 == db).all()
+    rs = oracle.Extractor(*small_cfg[2:])
+    k_ref, d_ref = rs(img_s)
+    assert_same_output(ks, ds, k_ref, d_ref)
+    ex_b.close()
+    ex_s.close()

@@ -113,6 +113,10 @@ def main():
             srows = [r for r in csv.reader(src.splitlines()) if len(r) > 6 and r[0].startswith("0x")]
             if not srows:
                 continue
+            for i in range(1, len(srows)):          # the page may list several instances: keep the first
+                if int(srows[i][0], 16) <= int(srows[i - 1][0], 16):
+                    srows = srows[:i]
+                    break
             seg, acc, ops = 0, collections.defaultdict(lambda: [0, 0, 0]), collections.defaultdict(collections.Counter)
             for r in srows:
                 s = r[1].strip()

@@ -1235,7 +1235,12 @@ size_t viorb_fast_smem_bytes(const FrameGeom& g) {
 }
 
 int viorb_fast_prepare(const FrameGeom& g) {
+    static int current[64] = {0};        /* raise-only, see viorb_octree_prepare */
+    int dev = 0;
+    cudaGetDevice(&dev);
     const int smem = (int)viorb_fast_smem_bytes(g);
+    if (dev < 0 || dev >= 64 || smem <= current[dev] || smem <= 48 * 1024) return (int)cudaSuccess;
+    current[dev] = smem;
     cudaError_t e = cudaFuncSetAttribute(fast_cells_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fast_cells_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fast_cells_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1303,9 +1308,17 @@ size_t viorb_octree_smem_bytes(int NC) {
            (size_t)p2 * sizeof(unsigned);
 }
 
+/* The opt-in limit is a property of the kernel (per device), shared by every extractor of the process: it is only
+ * ever raised, so an extractor with a small quota cannot lower it under one with a large quota. */
 int viorb_octree_prepare(int NC) {
-    return (int)cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)viorb_octree_smem_bytes(NC));
+    static int current[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int want = (int)viorb_octree_smem_bytes(NC);
+    if (dev < 0 || dev >= 64 || want <= current[dev]) return (int)cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e == cudaSuccess) current[dev] = want;
+    return (int)e;
 }
 
 int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s) {
