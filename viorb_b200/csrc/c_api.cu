@@ -259,7 +259,11 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
                 const int iniX = VIORB_FAST_BORDER + j * L.wCell, iniY = VIORB_FAST_BORDER + i * L.hCell;
                 const int ww = std::min(iniX + n * L.wCell + 6, maxBorderX) - iniX - 6;
                 const int wh = std::min(iniY + L.hCell + 6, maxBorderY) - iniY - 6;
-                if (ww > 0 && wh > 0) fastWork = std::max(fastWork, ((ww + 3) / 4) * wh);
+                if (ww > 0 && wh > 0) {
+                    fastWork = std::max(fastWork, ((ww + 3) / 4) * wh);
+                    /* the same array later lists the 3x3 local maxima: at most every other pixel per row and column of a cell */
+                    fastWork = std::max(fastWork, n * ((L.wCell + 1) / 2) * ((wh + 1) / 2));
+                }
             }
         }
         fastRows = std::max(fastRows, std::min(L.hCell + 6, VIORB_FAST_TILE_ROWS));

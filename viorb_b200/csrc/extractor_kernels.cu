@@ -408,7 +408,13 @@ __global__ void __launch_bounds__(128, 8) fast_cells_kernel(const __grid_constan
         tma_load_3d(tile, &maps.fast[l], boxX, VIORB_EDGE + iniY, frame, &bar);
         nwork = 0; nwork0 = 0; npix = 0; nout = 0;
     }
-    for (int i = tid; i < (wh + 2) * FAST_SCW; i += blockDim.x) sc[i] = 0;
+    {   /* zero the score rows with 16-byte stores (the array starts on a 128-byte boundary; a few words past the
+         * last needed row stay inside the (fastTileRows - 4)-row array) */
+        uint4* sc4 = reinterpret_cast<uint4*>(sc);
+        const int n4 = min(((wh + 2) * FAST_SCW + 3) >> 2, ((g.fastTileRows - 4) * FAST_SCW) >> 2);
+        for (int i = tid; i < n4; i += blockDim.x) sc4[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 4 * n4 + tid; i < (wh + 2) * FAST_SCW; i += blockDim.x) sc[i] = 0;
+    }
     if (tid < FAST_GROUP * 2) (&cellCnt[0][0])[tid] = 0;
     __syncthreads();
     mbar_wait(&bar, 0);
@@ -552,27 +558,37 @@ __global__ void __launch_bounds__(128, 8) fast_cells_kernel(const __grid_constan
     const uint8_t* scb = reinterpret_cast<const uint8_t*>(sc);
     const int iniShift = g.iniTh - g.minTh + 1;
     const int np = npix;
-    for (int i = tid; i < np; i += blockDim.x) {
-        const unsigned e = pix[i];
-        const int x = e & 0xff, y = (e >> 8) & 0x3f;
-        const int cg = (x >= L.wCell) + (x >= 2 * L.wCell) + (x >= 3 * L.wCell), xin = x - cg * L.wCell;
-        const uint8_t* p = scb + ((y + 1) * FAST_SCW + 1) * 4 + x;
-        const int sv = p[0];
-        const int up = p[-FAST_SCW * 4], dn = p[FAST_SCW * 4];
-        const int lf = max(max((int)p[-1], (int)p[-FAST_SCW * 4 - 1]), (int)p[FAST_SCW * 4 - 1]);
-        const int rt = max(max((int)p[1], (int)p[-FAST_SCW * 4 + 1]), (int)p[FAST_SCW * 4 + 1]);
-        int nb = max(up, dn);
-        if (xin > 0) nb = max(nb, lf);
-        if (xin < L.wCell - 1) nb = max(nb, rt);
-        if (sv > nb) {
-            pix[i] = (unsigned short)(e | 0x8000u);
-            atomicAdd(&cellCnt[cg][sv >= iniShift], 1);
+    unsigned short* lml = work;                      /* local maxima x | y << 8 (the quad list is dead) */
+    for (int i0 = 0; i0 < np; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        bool lm = false;
+        unsigned e = 0;
+        if (i < np) {
+            e = pix[i];
+            const int x = e & 0xff, y = (e >> 8) & 0x3f;
+            const int cg = (x >= L.wCell) + (x >= 2 * L.wCell) + (x >= 3 * L.wCell), xin = x - cg * L.wCell;
+            const uint8_t* p = scb + ((y + 1) * FAST_SCW + 1) * 4 + x;
+            const int sv = p[0];
+            const int up = p[-FAST_SCW * 4], dn = p[FAST_SCW * 4];
+            const int lf = max(max((int)p[-1], (int)p[-FAST_SCW * 4 - 1]), (int)p[FAST_SCW * 4 - 1]);
+            const int rt = max(max((int)p[1], (int)p[-FAST_SCW * 4 + 1]), (int)p[FAST_SCW * 4 + 1]);
+            int nb = max(up, dn);
+            if (xin > 0) nb = max(nb, lf);
+            if (xin < L.wCell - 1) nb = max(nb, rt);
+            lm = sv > nb;
+            if (lm) atomicAdd(&cellCnt[cg][sv >= iniShift], 1);
         }
+        const unsigned m = __ballot_sync(0xffffffffu, lm);
+        int basePos = 0;
+        if (lane == 0 && m) basePos = smem_add(&nout, __popc(m));
+        basePos = __shfl_sync(0xffffffffu, basePos, 0);
+        if (lm) lml[basePos + __popc(m & ((1u << lane) - 1))] = (unsigned short)e;
     }
     __syncthreads();
     /* the cell is retried with minThFAST only if it found nothing at iniThFAST (:812): per cell the kept local
      * maxima are those >= iniThFAST if there is one, else all of them.  One global atomic reserves the CTA's
      * range of the (frame, level) candidate pool. */
+    const int nlm = nout;
     if (tid == 0) {
         int total = 0;
         for (int c = 0; c < FAST_GROUP; c++) total += cellCnt[c][1] ? cellCnt[c][1] : cellCnt[c][0];
@@ -582,30 +598,28 @@ __global__ void __launch_bounds__(128, 8) fast_cells_kernel(const __grid_constan
             if (b + total > L.candCap) atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
         }
         gbase = total ? b : -1;
+        npix = 0;                                    /* reused as the emission cursor */
     }
     __syncthreads();
     const int b0 = gbase;
     if (b0 < 0) return;
     uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
-    for (int i0 = 0; i0 < np; i0 += blockDim.x) {
+    for (int i0 = 0; i0 < nlm; i0 += blockDim.x) {
         const int i = i0 + tid;
         bool keep = false;
         uint32_t rec = 0;
-        if (i < np) {
-            const unsigned e = pix[i];
-            if (e & 0x8000u) {
-                const int x = e & 0xff, y = (e >> 8) & 0x3f;
-                const int cg = (x >= L.wCell) + (x >= 2 * L.wCell) + (x >= 3 * L.wCell);
-                const int sv = scb[((y + 1) * FAST_SCW + 1) * 4 + x];
-                keep = sv >= (cellCnt[cg][1] ? iniShift : 1);
-                /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
-                rec = (uint32_t)(x + 3 + cj0 * L.wCell) | ((uint32_t)(y + 3 + ci * L.hCell) << 12) |
-                      ((uint32_t)(sv + g.minTh - 1) << 24);
-            }
+        if (i < nlm) {
+            const unsigned e = lml[i];
+            const int x = e & 0xff, y = (e >> 8) & 0x3f;
+            const int cg = (x >= L.wCell) + (x >= 2 * L.wCell) + (x >= 3 * L.wCell);
+            const int sv = scb[((y + 1) * FAST_SCW + 1) * 4 + x];
+            keep = sv >= (cellCnt[cg][1] ? iniShift : 1);
+            /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
+            rec = (uint32_t)(x + 3 + cj0 * L.wCell) | ((uint32_t)(y + 3 + ci * L.hCell) << 12) | ((uint32_t)(sv + g.minTh - 1) << 24);
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         int basePos = 0;
-        if (lane == 0 && m) basePos = smem_add(&nout, __popc(m));
+        if (lane == 0 && m) basePos = smem_add(&npix, __popc(m));
         basePos = __shfl_sync(0xffffffffu, basePos, 0);
         const int pos = b0 + basePos + __popc(m & ((1u << lane) - 1));
         if (keep && pos < L.candCap) out[pos] = rec;
