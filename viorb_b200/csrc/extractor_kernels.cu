@@ -196,38 +196,48 @@ __device__ __forceinline__ void pyr_resize_tile(const FrameGeom& g, int level, c
     __syncthreads();
     if (wi >= stepWords) return;
     const unsigned* srcw = reinterpret_cast<const unsigned*>(src) + wb;
-    unsigned prevO1 = 0xffffffffu;
-    unsigned Tp[4] = {0, 0, 0, 0};
-    uint32_t* out = reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(ya + r0 + VIORB_EDGE) * L.step) + wi;
-    for (int r = r0; r < r0 + WROWS; r++, out += stepWords) {
-        if (ya + r > yhi) break;
-        const uint4 ri = rowInfo[r];
-        const unsigned o0 = ri.x & 0xffffu, o1 = ri.x >> 16;
-        unsigned T0[4], T1[4];
-        if (o0 == prevO1) {
+    /* horizontal pass of the staged row at byte offset `off`: T[j] = (S[sx]*a0 + S[sx+1]*a1) >> 4 */
+    auto hpass = [&](unsigned off, unsigned (&T)[4]) {
+        const unsigned* w = srcw + (off >> 2);
+        const unsigned W0 = __byte_perm(w[0], w[1], selN), W1 = __byte_perm(w[1], w[2], selN);
 #pragma unroll
-            for (int j = 0; j < 4; j++) T0[j] = Tp[j];
-        } else {
-            const unsigned* w = srcw + (o0 >> 2);
-            const unsigned W0 = __byte_perm(w[0], w[1], selN), W1 = __byte_perm(w[1], w[2], selN);
-#pragma unroll
-            for (int j = 0; j < 4; j++) T0[j] = __dp2a_lo(coef[j], __byte_perm(W0, W1, selP[j]), 0u) >> 4;
-        }
-        {
-            const unsigned* w = srcw + (o1 >> 2);
-            const unsigned W0 = __byte_perm(w[0], w[1], selN), W1 = __byte_perm(w[1], w[2], selN);
-#pragma unroll
-            for (int j = 0; j < 4; j++) T1[j] = __dp2a_lo(coef[j], __byte_perm(W0, W1, selP[j]), 0u) >> 4;
-        }
-        uint32_t word = 0;
+        for (int j = 0; j < 4; j++) T[j] = __dp2a_lo(coef[j], __byte_perm(W0, W1, selP[j]), 0u) >> 4;
+    };
+    /* vertical pass + packing of four pixels: s = ((b0*T0)>>16) + ((b1*T1)>>16) + 2 as two IMAD.HI with addend
+     * (s <= 1022); two s per register, one shift and mask for both, one PRMT for the four bytes */
+    auto vrow = [&](const uint4& ri, const unsigned (&U)[4], const unsigned (&D)[4]) -> uint32_t {
+        unsigned sj[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t v = (__umulhi(ri.y, T0[j]) + __umulhi(ri.z, T1[j]) + 2u) >> 2;     /* <= 255 */
-            word |= v << (8 * j);
-            Tp[j] = T1[j];
+            unsigned t;
+            asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(ri.y), "r"(U[j]), "r"(2u));
+            asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(sj[j]) : "r"(ri.z), "r"(D[j]), "r"(t));
         }
-        prevO1 = o1;
-        *out = word & okMask;
+        const unsigned p01 = ((sj[1] * 65536u + sj[0]) >> 2) & 0x00ff00ffu;
+        const unsigned p23 = ((sj[3] * 65536u + sj[2]) >> 2) & 0x00ff00ffu;
+        return __byte_perm(p01, p23, 0x6420) & okMask;
+    };
+    /* Consecutive output rows mostly share a source row (sy advances by 1 or 2 per output row): the lower row's T of
+     * one output row is the upper row's T of the next.  Two rows per iteration with the two register sets swapping
+     * roles, so the reuse costs no register moves. */
+    unsigned A[4] = {0, 0, 0, 0}, B[4] = {0, 0, 0, 0};
+    unsigned inA = 0xffffffffu;                       /* staged offset whose T is held in A */
+    uint32_t* out = reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(ya + r0 + VIORB_EDGE) * L.step) + wi;
+#pragma unroll 1
+    for (int r = r0; r < r0 + WROWS; r += 2, out += 2 * stepWords) {
+        if (ya + r > yhi) break;
+        const uint4 ri0 = rowInfo[r];
+        const unsigned o0 = ri0.x & 0xffffu, o1 = ri0.x >> 16;
+        if (o0 != inA) hpass(o0, A);
+        hpass(o1, B);
+        out[0] = vrow(ri0, A, B);
+        if (ya + r + 1 > yhi) break;
+        const uint4 ri1 = rowInfo[r + 1];
+        const unsigned q0 = ri1.x & 0xffffu, q1 = ri1.x >> 16;
+        if (q0 != o1) hpass(q0, B);
+        hpass(q1, A);
+        out[stepWords] = vrow(ri1, B, A);
+        inA = q1;
     }
 }
 
