@@ -239,3 +239,32 @@ def test_two_extractors_with_different_quotas_interleaved(api, ctx, oracle):
     assert_same_output(ks, ds, k_ref, d_ref)
     ex_b.close()
     ex_s.close()
+
+
+def test_two_extractors_in_two_threads(api, oracle):
+    """the stereo Frame constructor runs the left and right extractor in two threads (src/Frame.cc:258-261): distinct
+    instances (each with its own context / stream / graph) must be safe to enter concurrently"""
+    import threading
+    h, w, nf, sf, nl, it, mt = CONFIGS["kitti"]
+    left, right, _ = synth.stereo_pair(h, w, 11)
+    ref = oracle.Extractor(nf, sf, nl, it, mt)
+    want = [ref(left), ref(right)]
+    got, errs = [None, None], []
+
+    def work(i, img):
+        try:
+            c = api.Context(0)
+            ex = api.ORBextractor(nf, sf, nl, it, mt, ctx=c)
+            for _ in range(25):
+                got[i] = ex(img)
+            ex.close()
+            c.close()
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(0, left)), threading.Thread(target=work, args=(1, right))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for i in range(2):
+        assert_same_output(got[i][0], got[i][1], want[i][0], want[i][1])
