@@ -268,3 +268,13 @@ def test_two_extractors_in_two_threads(api, oracle):
     assert not errs, errs
     for i in range(2):
         assert_same_output(got[i][0], got[i][1], want[i][0], want[i][1])
+
+
+def test_differential_fuzz():
+    """tools/fuzz_extract.py: random shapes / parameters / image statistics (noise, low contrast, checkerboards, half-flat
+    frames), every output byte against the oracle"""
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_extract.py"), "80", "3"], capture_output=True,
+                       text=True, cwd=ROOT, timeout=600)
+    assert p.returncode == 0 and " 0 mismatches" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

@@ -45,6 +45,22 @@ def main():
         return api.ComputeStereoMatches(exl, exr, kl, dl, kr, dr, 386.1448, 386.1448 / 718.856)
 
     out["kitti_stereo_pair"] = timeit(stereo, n=100)
+    # the reference extracts left and right in two threads (src/Frame.cc:258-261): one context per thread
+    import threading
+    ctx2 = api.Context(0)
+    exr2 = api.ORBextractor(2000, 1.2, 8, 20, 7, ctx=ctx2)
+    res = [None, None]
+
+    def stereo_threads():
+        def right_job():
+            res[1] = exr2(right)
+        t = threading.Thread(target=right_job)
+        t.start()
+        res[0] = exl(left)
+        t.join()
+        return api.ComputeStereoMatches(exl, exr2, res[0][0], res[0][1], res[1][0], res[1][1], 386.1448, 386.1448 / 718.856)
+
+    out["kitti_stereo_pair_two_threads"] = timeit(stereo_threads, n=100)
     kl, dl = exl(left)
     kr, dr = exr(right)
     out["kitti_compute_stereo_matches"] = timeit(lambda: api.ComputeStereoMatches(exl, exr, kl, dl, kr, dr, 386.1448, 386.1448 / 718.856), n=100)
