@@ -91,3 +91,14 @@ def test_top2_sharded_merge(api, ctx, oracle):
     host = oracle.top2_merge(parts.cpu().numpy().view(oracle.TOP2).reshape(P, Q))
     for i, f in enumerate(("d1", "i1", "d2", "i2")):
         assert (host[f] == ref[f]).all(), f
+
+
+def test_top2_differential_fuzz():
+    """tools/fuzz_match.py: random Q / M around the tile, slice and small-query boundaries, heavy ties, index bases"""
+    import os
+    import subprocess
+    import sys
+    from util import ROOT
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_match.py"), "60", "2"], capture_output=True, text=True,
+                       cwd=ROOT, timeout=600)
+    assert p.returncode == 0 and " 0 mismatches" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
