@@ -372,7 +372,6 @@ __global__ void __launch_bounds__(128, 8) fast_cells_kernel(const __grid_constan
                                                          const int4* __restrict__ groups,
                                                          uint32_t* __restrict__ cand, int* __restrict__ candCount,
                                                          int* __restrict__ status) {
-    /* tile and work0 are contiguous: once both are dead (after phase 2) the region holds the corner-pixel list */
     /* dynamic shared memory, sized by the host for this geometry (FrameGeom::fast*):
      *   [ tile: fastTileRows x 208 B | work0: fastMaxWork u16 | pad ]  = fastPixBytes  (later: the corner-pixel list)
      *   [ sc: (fastTileRows - 4) x 196 B ] [ work: fastMaxWork u16 ] */
@@ -381,10 +380,10 @@ __global__ void __launch_bounds__(128, 8) fast_cells_kernel(const __grid_constan
     unsigned short* work = reinterpret_cast<unsigned short*>(raw + g.fastPixBytes + (g.fastTileRows - 4) * FAST_SCW * 4);   /* quads that survive the high-speed test */
     __shared__ __align__(8) unsigned long long bar;   /* mbarrier of the TMA tile load */
     __shared__ int nwork, nwork0, npix, nout, gbase;
-    __shared__ int cellCnt[FAST_GROUP][2];            /* per cell: local maxima below / at-or-above iniThFAST */
+    __shared__ int cellCnt[FAST_GROUP];               /* per cell: local maxima found by the pass */
     unsigned* tile = reinterpret_cast<unsigned*>(raw);
     unsigned short* work0 = reinterpret_cast<unsigned short*>(raw + g.fastTileRows * FAST_TW * 4);   /* non-flat quads */
-    unsigned short* pix = reinterpret_cast<unsigned short*>(raw);   /* corner pixels: x | y << 8 | localmax << 15 */
+    unsigned short* pix = reinterpret_cast<unsigned short*>(raw);   /* corner pixels x | y << 8 (the tile and work0 are dead then) */
     const int frame = blockIdx.y;
     /* a CTA owns up to FAST_GROUP horizontally adjacent cells of one cell row: {level, cell row, first cell, n} */
     const int4 grp = __ldg(&groups[blockIdx.x]);
@@ -402,237 +401,244 @@ __global__ void __launch_bounds__(128, 8) fast_cells_kernel(const __grid_constan
     if (g.dbg & 16) return;
     const int tid = threadIdx.x, lane = tid & 31;
     const int NQ = (ww + 3) >> 2;            /* quads per window row */
+    const int ntask = NQ * wh;
+    const unsigned invNQ = 0xffffffffu / (unsigned)NQ + 1u;          /* t / NQ == umulhi(t, invNQ) for t < 2^16 */
+    const unsigned lt = (1u << lane) - 1;
+    const uint8_t* scb = reinterpret_cast<const uint8_t*>(sc);
+    uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
+    const int wC = L.wCell;
 
-    /* stage: one TMA box per CTA.  The box starts at the 16-byte boundary A at or below window x = -3 of the
-     * stored row (TMA needs a 16-byte aligned start), so window pixel x of row y sits at tile byte
-     * 4*w0 + SH + x of row y, SH = (stored byte of window x=0) & 3 -- the same for all groups of a launch (the
-     * host sorts the groups by SH; with 4-cell groups every window starts at byte 51 + 4k*wCell, SH = 3).
-     * Bytes of the box outside the stored level read as 0 and are never used. */
+    /* The box starts at the 16-byte boundary A at or below window x = -3 of the stored row (TMA needs a 16-byte
+     * aligned start), so window pixel x of row y sits at tile byte 4*w0 + SH + x of row y,
+     * SH = (stored byte of window x=0) & 3 -- the same for all groups of a launch (the host sorts the groups by SH;
+     * with 4-cell groups every window starts at byte 51 + 4k*wCell, SH = 3).  Bytes of the box outside the stored
+     * level read as 0 and are never used. */
     const int gstart = VIORB_ROI_X0 + iniX + 3;
     const int boxX = (gstart - 3) & ~15;
     const int w0 = (gstart - boxX) >> 2;
-    if (tid == 0) {
-        const int boxH = min(L.hCell + 6, g.fastTileRows);
-        mbar_init(&bar, 1);
-        mbar_expect_tx(&bar, (unsigned)(VIORB_FAST_TILE_BYTES * boxH));
-        tma_load_3d(tile, &maps.fast[l], boxX, VIORB_EDGE + iniY, frame, &bar);
-        nwork = 0; nwork0 = 0; npix = 0; nout = 0;
-    }
-    {   /* zero the score rows with 16-byte stores (the array starts on a 128-byte boundary; a few words past the
-         * last needed row stay inside the (fastTileRows - 4)-row array) */
-        uint4* sc4 = reinterpret_cast<uint4*>(sc);
-        const int n4 = min(((wh + 2) * FAST_SCW + 3) >> 2, ((g.fastTileRows - 4) * FAST_SCW) >> 2);
-        for (int i = tid; i < n4; i += blockDim.x) sc4[i] = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = 4 * n4 + tid; i < (wh + 2) * FAST_SCW; i += blockDim.x) sc[i] = 0;
-    }
-    if (tid < FAST_GROUP * 2) (&cellCnt[0][0])[tid] = 0;
-    __syncthreads();
-    mbar_wait(&bar, 0);
+    const int boxH = min(L.hCell + 6, g.fastTileRows);
+    if (tid == 0) mbar_init(&bar, 1);
 
-    /* phase 0 -- byte-domain pre-test on the four compass samples (k = 0, 4, 8, 12) of every quad: every 9-arc
-     * of the ring contains two ADJACENT compass samples, so a pixel can only be a corner at minTh if
-     * |ring - centre| > minTh at two adjacent compass points.  flag byte bit 7 = (|d| > minTh); carries between
-     * bytes can only add false positives.  Surviving quads are compacted so the later phases run on dense warps. */
-    const int ntask = NQ * wh;
-    const unsigned invNQ = 0xffffffffu / (unsigned)NQ + 1u;          /* t / NQ == umulhi(t, invNQ) for t < 2^16 */
-    {
-        const unsigned addc = (unsigned)(127 - g.minTh) * 0x01010101u;
-        const unsigned lt = (1u << lane) - 1;
-        /* four tasks per thread and iteration: four ballots, one shared atomic per warp */
-        for (int t0 = 0; t0 < ntask; t0 += 4 * blockDim.x) {
-            bool keep[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int t = t0 + j * blockDim.x + tid;
-                keep[j] = false;
-                if (t < ntask) {
-                    const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
-                    const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
-                    const unsigned cw4 = fast_ld4<SH>(row);
-                    const unsigned d0 = __vabsdiffu4(fast_ld4<SH>(row + 3 * FAST_TW), cw4);
-                    const unsigned d8 = __vabsdiffu4(fast_ld4<SH>(row - 3 * FAST_TW), cw4);
-                    const unsigned d4 = __vabsdiffu4(fast_ld4<SH + 3>(row), cw4);
-                    const unsigned d12 = __vabsdiffu4(fast_ld4<SH - 3>(row), cw4);
-                    const unsigned f0 = (d0 + addc) | d0, f4 = (d4 + addc) | d4, f8 = (d8 + addc) | d8, f12 = (d12 + addc) | d12;
-                    keep[j] = ((((f0 | f8) & (f4 | f12))) & 0x80808080u) != 0;   /* (f0&f4)|(f4&f8)|(f8&f12)|(f12&f0) */
-                }
-            }
-            const unsigned m0 = __ballot_sync(0xffffffffu, keep[0]), m1 = __ballot_sync(0xffffffffu, keep[1]);
-            const unsigned m2 = __ballot_sync(0xffffffffu, keep[2]), m3 = __ballot_sync(0xffffffffu, keep[3]);
-            if ((m0 | m1 | m2 | m3) == 0) continue;
-            const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
-            int basePos = 0;
-            if (lane == 0) basePos = smem_add(&nwork0, c0 + c1 + c2 + c3);
-            basePos = __shfl_sync(0xffffffffu, basePos, 0);
-            const int tb = t0 + tid;
-            if (keep[0]) work0[basePos + __popc(m0 & lt)] = (unsigned short)tb;
-            if (keep[1]) work0[basePos + c0 + __popc(m1 & lt)] = (unsigned short)(tb + blockDim.x);
-            if (keep[2]) work0[basePos + c0 + c1 + __popc(m2 & lt)] = (unsigned short)(tb + 2 * blockDim.x);
-            if (keep[3]) work0[basePos + c0 + c1 + c2 + __popc(m3 & lt)] = (unsigned short)(tb + 3 * blockDim.x);
+    /* Two passes, like the reference (:808-816): pass 0 runs cv::FAST at iniThFAST on all cells of the group; a cell
+     * that returns nothing is run again at minThFAST in pass 1 (about one cell in ten, so most CTAs stop after
+     * pass 0 and never pay for the weak-corner work).  Both passes use the same code with a different threshold. */
+    unsigned retry = (1u << ncell) - 1;       /* cells the pass works on */
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const int th = pass == 0 ? g.iniTh : g.minTh;
+        /* stage: one TMA box per CTA and pass (the corner-pixel list of the previous pass overwrote the tile) */
+        if (tid == 0) {
+            mbar_expect_tx(&bar, (unsigned)(VIORB_FAST_TILE_BYTES * boxH));
+            tma_load_3d(tile, &maps.fast[l], boxX, VIORB_EDGE + iniY, frame, &bar);
+            nwork = 0; nwork0 = 0; npix = 0; nout = 0;
         }
-    }
-    __syncthreads();
+        {   /* zero the score rows with 16-byte stores (the array starts on a 128-byte boundary; a few words past the
+             * last needed row stay inside the (fastTileRows - 4)-row array) */
+            uint4* sc4 = reinterpret_cast<uint4*>(sc);
+            const int n4 = min(((wh + 2) * FAST_SCW + 3) >> 2, ((g.fastTileRows - 4) * FAST_SCW) >> 2);
+            for (int i = tid; i < n4; i += blockDim.x) sc4[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = 4 * n4 + tid; i < (wh + 2) * FAST_SCW; i += blockDim.x) sc[i] = 0;
+        }
+        if (tid < FAST_GROUP) cellCnt[tid] = 0;
+        __syncthreads();
+        mbar_wait(&bar, (unsigned)pass);
 
-    /* phase 1 -- high-speed test on the non-flat quads.  A 9-arc of the 16-ring always contains a pair of opposite
-     * samples (k, k+8), so a corner at threshold t needs an opposite pair that is brighter than v + t on both
-     * ends, or darker than v - t on both ends.  Straight edges fail this test. */
-    const unsigned thP = (unsigned)g.minTh * 0x00010001u, nthP = __vneg2(thP);
-    const int n0 = nwork0;
-    for (int i0 = 0; i0 < n0; i0 += blockDim.x) {
-        const int i = i0 + tid;
-        bool keep = false;
-        int t = 0;
-        if (i < n0) {
-            t = work0[i];
+        /* phase 0 -- byte-domain pre-test on the four compass samples (k = 0, 4, 8, 12) of every quad: every 9-arc
+         * of the ring contains two ADJACENT compass samples, so a pixel can only be a corner at th if
+         * |ring - centre| > th at two adjacent compass points.  flag byte bit 7 = (|d| > th); carries between
+         * bytes can only add false positives.  Surviving quads are compacted so the later phases run on dense warps.
+         * Four tasks per thread and iteration: four ballots, one shared atomic per warp. */
+        {
+            const unsigned addc = (unsigned)(127 - th) * 0x01010101u;
+            for (int t0 = 0; t0 < ntask; t0 += 4 * blockDim.x) {
+                bool keep[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int t = t0 + j * blockDim.x + tid;
+                    keep[j] = false;
+                    if (t < ntask) {
+                        const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
+                        if (pass) {     /* only quads that touch a cell under retry */
+                            const int x = 4 * q, x3 = min(x + 3, ww - 1);
+                            const int c0 = (x >= wC) + (x >= 2 * wC) + (x >= 3 * wC), c3 = (x3 >= wC) + (x3 >= 2 * wC) + (x3 >= 3 * wC);
+                            if (!(((retry >> c0) | (retry >> c3)) & 1u)) continue;
+                        }
+                        const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
+                        const unsigned cw4 = fast_ld4<SH>(row);
+                        const unsigned d0 = __vabsdiffu4(fast_ld4<SH>(row + 3 * FAST_TW), cw4);
+                        const unsigned d8 = __vabsdiffu4(fast_ld4<SH>(row - 3 * FAST_TW), cw4);
+                        const unsigned d4 = __vabsdiffu4(fast_ld4<SH + 3>(row), cw4);
+                        const unsigned d12 = __vabsdiffu4(fast_ld4<SH - 3>(row), cw4);
+                        const unsigned f0 = (d0 + addc) | d0, f4 = (d4 + addc) | d4, f8 = (d8 + addc) | d8, f12 = (d12 + addc) | d12;
+                        keep[j] = ((((f0 | f8) & (f4 | f12))) & 0x80808080u) != 0;   /* (f0&f4)|(f4&f8)|(f8&f12)|(f12&f0) */
+                    }
+                }
+                const unsigned m0 = __ballot_sync(0xffffffffu, keep[0]), m1 = __ballot_sync(0xffffffffu, keep[1]);
+                const unsigned m2 = __ballot_sync(0xffffffffu, keep[2]), m3 = __ballot_sync(0xffffffffu, keep[3]);
+                if ((m0 | m1 | m2 | m3) == 0) continue;
+                const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
+                int basePos = 0;
+                if (lane == 0) basePos = smem_add(&nwork0, c0 + c1 + c2 + c3);
+                basePos = __shfl_sync(0xffffffffu, basePos, 0);
+                const int tb = t0 + tid;
+                if (keep[0]) work0[basePos + __popc(m0 & lt)] = (unsigned short)tb;
+                if (keep[1]) work0[basePos + c0 + __popc(m1 & lt)] = (unsigned short)(tb + blockDim.x);
+                if (keep[2]) work0[basePos + c0 + c1 + __popc(m2 & lt)] = (unsigned short)(tb + 2 * blockDim.x);
+                if (keep[3]) work0[basePos + c0 + c1 + c2 + __popc(m3 & lt)] = (unsigned short)(tb + 3 * blockDim.x);
+            }
+        }
+        __syncthreads();
+
+        /* phase 1 -- high-speed test on the non-flat quads.  A 9-arc of the 16-ring always contains a pair of
+         * opposite samples (k, k+8), so a corner at threshold t needs an opposite pair that is brighter than v + t on
+         * both ends, or darker than v - t on both ends.  Straight edges fail this test. */
+        const unsigned thP = (unsigned)th * 0x00010001u, nthP = __vneg2(thP);
+        const int n0 = nwork0;
+        for (int i0 = 0; i0 < n0; i0 += blockDim.x) {
+            const int i = i0 + tid;
+            bool keep = false;
+            int t = 0;
+            if (i < n0) {
+                t = work0[i];
+                const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
+                const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
+                const unsigned cw4 = fast_ld4<SH>(row);
+                unsigned rA[16], rB[16];
+                fast_load_ring<SH>(row, rA, rB);
+                const unsigned nvA = __vneg2(__byte_perm(cw4, 0, 0x4240)), nvB = __vneg2(__byte_perm(cw4, 0, 0x4341));
+                unsigned loA[8], hiA[8], loB[8], hiB[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    loA[k] = __vmins2(rA[k], rA[k + 8]); hiA[k] = __vmaxs2(rA[k], rA[k + 8]);
+                    loB[k] = __vmins2(rB[k], rB[k + 8]); hiB[k] = __vmaxs2(rB[k], rB[k + 8]);
+                }
+                const unsigned brightA = __vimax3_s16x2(__vimax3_s16x2(loA[0], loA[1], loA[2]), __vimax3_s16x2(loA[3], loA[4], loA[5]),
+                                                        __vmaxs2(loA[6], loA[7]));
+                const unsigned brightB = __vimax3_s16x2(__vimax3_s16x2(loB[0], loB[1], loB[2]), __vimax3_s16x2(loB[3], loB[4], loB[5]),
+                                                        __vmaxs2(loB[6], loB[7]));
+                const unsigned darkA = __vimin3_s16x2(__vimin3_s16x2(hiA[0], hiA[1], hiA[2]), __vimin3_s16x2(hiA[3], hiA[4], hiA[5]),
+                                                      __vmins2(hiA[6], hiA[7]));
+                const unsigned darkB = __vimin3_s16x2(__vimin3_s16x2(hiB[0], hiB[1], hiB[2]), __vimin3_s16x2(hiB[3], hiB[4], hiB[5]),
+                                                      __vmins2(hiB[6], hiB[7]));
+                const unsigned up = __vmaxs2(__vadd2(brightA, nvA), __vadd2(brightB, nvB));   /* best opposite-pair excess */
+                const unsigned dn = __vmins2(__vadd2(darkA, nvA), __vadd2(darkB, nvB));
+                keep = !(__vmaxs2(up, thP) == thP && __vmins2(dn, nthP) == nthP);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            int basePos = 0;
+            if (lane == 0 && m) basePos = smem_add(&nwork, __popc(m));
+            basePos = __shfl_sync(0xffffffffu, basePos, 0);
+            if (keep) work[basePos + __popc(m & lt)] = (unsigned short)t;
+        }
+        __syncthreads();
+
+        /* phase 2 -- exact cornerScore on the surviving quads only, densely packed over the CTA.
+         * sc holds relu(S - (th - 1)): 0 = not a corner at th */
+        const unsigned negBias = __vneg2(thP);
+        const int nw = (g.dbg & 2) ? 0 : nwork;
+        for (int i = tid; i < nw; i += blockDim.x) {
+            const int t = work[i];
             const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
             const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
-            const unsigned cw4 = fast_ld4<SH>(row);
             unsigned rA[16], rB[16];
             fast_load_ring<SH>(row, rA, rB);
-            const unsigned nvA = __vneg2(__byte_perm(cw4, 0, 0x4240)), nvB = __vneg2(__byte_perm(cw4, 0, 0x4341));
-            unsigned loA[8], hiA[8], loB[8], hiB[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                loA[k] = __vmins2(rA[k], rA[k + 8]); hiA[k] = __vmaxs2(rA[k], rA[k + 8]);
-                loB[k] = __vmins2(rB[k], rB[k + 8]); hiB[k] = __vmaxs2(rB[k], rB[k + 8]);
+            const unsigned cw4 = fast_ld4<SH>(row);
+            const unsigned sA = fast_score_s16x2(rA, __byte_perm(cw4, 0, 0x4240), negBias);
+            const unsigned sB = fast_score_s16x2(rB, __byte_perm(cw4, 0, 0x4341), negBias);
+            unsigned word = sA | (sB << 8);                       /* bytes = pixels x, x+1, x+2, x+3 */
+            const int x = q * 4;
+            if (x + 4 > ww) word &= 0xffffffffu >> (8 * (x + 4 - ww));   /* beyond the window: not a corner */
+            sc[(y + 1) * FAST_SCW + q + 1] = word;
+        }
+        __syncthreads();
+
+        /* corner pixels (score > 0) as a dense list -- the tile and work0 are dead, the list takes their place
+         * (the host sizes the region for 4 * fastMaxWork entries) */
+        for (int i0 = 0; i0 < nw; i0 += blockDim.x) {
+            const int i = i0 + tid;
+            unsigned word = 0;
+            int y = 0, q = 0;
+            if (i < nw) {
+                const int t = work[i];
+                y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t;
+                q = t - y * NQ;
+                word = sc[(y + 1) * FAST_SCW + q + 1];
             }
-            const unsigned brightA = __vimax3_s16x2(__vimax3_s16x2(loA[0], loA[1], loA[2]), __vimax3_s16x2(loA[3], loA[4], loA[5]),
-                                                    __vmaxs2(loA[6], loA[7]));
-            const unsigned brightB = __vimax3_s16x2(__vimax3_s16x2(loB[0], loB[1], loB[2]), __vimax3_s16x2(loB[3], loB[4], loB[5]),
-                                                    __vmaxs2(loB[6], loB[7]));
-            const unsigned darkA = __vimin3_s16x2(__vimin3_s16x2(hiA[0], hiA[1], hiA[2]), __vimin3_s16x2(hiA[3], hiA[4], hiA[5]),
-                                                  __vmins2(hiA[6], hiA[7]));
-            const unsigned darkB = __vimin3_s16x2(__vimin3_s16x2(hiB[0], hiB[1], hiB[2]), __vimin3_s16x2(hiB[3], hiB[4], hiB[5]),
-                                                  __vmins2(hiB[6], hiB[7]));
-            const unsigned up = __vmaxs2(__vadd2(brightA, nvA), __vadd2(brightB, nvB));   /* best opposite-pair excess */
-            const unsigned dn = __vmins2(__vadd2(darkA, nvA), __vadd2(darkB, nvB));
-            keep = !(__vmaxs2(up, thP) == thP && __vmins2(dn, nthP) == nthP);
+            const unsigned m0 = __ballot_sync(0xffffffffu, (word & 0x000000ffu) != 0), m1 = __ballot_sync(0xffffffffu, (word & 0x0000ff00u) != 0);
+            const unsigned m2 = __ballot_sync(0xffffffffu, (word & 0x00ff0000u) != 0), m3 = __ballot_sync(0xffffffffu, (word & 0xff000000u) != 0);
+            const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
+            int basePos = 0;
+            if (lane == 0 && (m0 | m1 | m2 | m3)) basePos = smem_add(&npix, c0 + c1 + c2 + c3);
+            basePos = __shfl_sync(0xffffffffu, basePos, 0);
+            const unsigned e = (unsigned)(q * 4) | ((unsigned)y << 8);
+            if (word & 0x000000ffu) pix[basePos + __popc(m0 & lt)] = (unsigned short)e;
+            if (word & 0x0000ff00u) pix[basePos + c0 + __popc(m1 & lt)] = (unsigned short)(e + 1);
+            if (word & 0x00ff0000u) pix[basePos + c0 + c1 + __popc(m2 & lt)] = (unsigned short)(e + 2);
+            if (word & 0xff000000u) pix[basePos + c0 + c1 + c2 + __popc(m3 & lt)] = (unsigned short)(e + 3);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        int basePos = 0;
-        if (lane == 0 && m) basePos = smem_add(&nwork, __popc(m));
-        basePos = __shfl_sync(0xffffffffu, basePos, 0);
-        if (keep) work[basePos + __popc(m & ((1u << lane) - 1))] = (unsigned short)t;
-    }
-    __syncthreads();
+        __syncthreads();
 
-    /* phase 2 -- exact cornerScore on the surviving quads only, densely packed over the CTA */
-    const unsigned negBias = __vneg2(thP);
-    const int nw = (g.dbg & 2) ? 0 : nwork;
-    for (int i = tid; i < nw; i += blockDim.x) {
-        const int t = work[i];
-        const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
-        const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
-        unsigned rA[16], rB[16];
-        fast_load_ring<SH>(row, rA, rB);
-        const unsigned cw4 = fast_ld4<SH>(row);
-        const unsigned sA = fast_score_s16x2(rA, __byte_perm(cw4, 0, 0x4240), negBias);
-        const unsigned sB = fast_score_s16x2(rB, __byte_perm(cw4, 0, 0x4341), negBias);
-        unsigned word = sA | (sB << 8);                       /* bytes = pixels x, x+1, x+2, x+3 */
-        const int x = q * 4;
-        if (x + 4 > ww) word &= 0xffffffffu >> (8 * (x + 4 - ww));   /* beyond the window: not a corner */
-        sc[(y + 1) * FAST_SCW + q + 1] = word;
-    }
-    __syncthreads();
-
-    /* corner pixels (score > 0) as a dense list -- the tile and work0 are dead, the list takes their place
-     * (the host sizes the region for 4 * fastMaxWork entries) */
-    for (int i0 = 0; i0 < nw; i0 += blockDim.x) {
-        const int i = i0 + tid;
-        unsigned word = 0;
-        int y = 0, q = 0;
-        if (i < nw) {
-            const int t = work[i];
-            y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t;
-            q = t - y * NQ;
-            word = sc[(y + 1) * FAST_SCW + q + 1];
+        /* 3x3 non-max suppression, one thread per corner pixel.  cv::FAST runs on the cell's own sub-image, so
+         * neighbours in another cell (or outside the window) count as 0.  The local maxima of the cells this pass works
+         * on go to a compact list; cellCnt counts them per cell. */
+        const int np = npix;
+        unsigned short* lml = work;                      /* local maxima x | y << 8 (the quad list is dead) */
+        for (int i0 = 0; i0 < np; i0 += blockDim.x) {
+            const int i = i0 + tid;
+            bool lm = false;
+            unsigned e = 0;
+            if (i < np) {
+                e = pix[i];
+                const int x = e & 0xff, y = (e >> 8) & 0x3f;
+                const int cg = (x >= wC) + (x >= 2 * wC) + (x >= 3 * wC), xin = x - cg * wC;
+                if ((retry >> cg) & 1u) {
+                    const uint8_t* p = scb + ((y + 1) * FAST_SCW + 1) * 4 + x;
+                    const int sv = p[0];
+                    const int up = p[-FAST_SCW * 4], dn = p[FAST_SCW * 4];
+                    const int lf = max(max((int)p[-1], (int)p[-FAST_SCW * 4 - 1]), (int)p[FAST_SCW * 4 - 1]);
+                    const int rt = max(max((int)p[1], (int)p[-FAST_SCW * 4 + 1]), (int)p[FAST_SCW * 4 + 1]);
+                    int nb = max(up, dn);
+                    if (xin > 0) nb = max(nb, lf);
+                    if (xin < wC - 1) nb = max(nb, rt);
+                    lm = sv > nb;
+                    if (lm) atomicAdd(&cellCnt[cg], 1);
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, lm);
+            int basePos = 0;
+            if (lane == 0 && m) basePos = smem_add(&nout, __popc(m));
+            basePos = __shfl_sync(0xffffffffu, basePos, 0);
+            if (lm) lml[basePos + __popc(m & lt)] = (unsigned short)e;
         }
-        const unsigned lt = (1u << lane) - 1;
-        const unsigned m0 = __ballot_sync(0xffffffffu, (word & 0x000000ffu) != 0), m1 = __ballot_sync(0xffffffffu, (word & 0x0000ff00u) != 0);
-        const unsigned m2 = __ballot_sync(0xffffffffu, (word & 0x00ff0000u) != 0), m3 = __ballot_sync(0xffffffffu, (word & 0xff000000u) != 0);
-        const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
-        int basePos = 0;
-        if (lane == 0 && (m0 | m1 | m2 | m3)) basePos = smem_add(&npix, c0 + c1 + c2 + c3);
-        basePos = __shfl_sync(0xffffffffu, basePos, 0);
-        const unsigned e = (unsigned)(q * 4) | ((unsigned)y << 8);
-        if (word & 0x000000ffu) pix[basePos + __popc(m0 & lt)] = (unsigned short)e;
-        if (word & 0x0000ff00u) pix[basePos + c0 + __popc(m1 & lt)] = (unsigned short)(e + 1);
-        if (word & 0x00ff0000u) pix[basePos + c0 + c1 + __popc(m2 & lt)] = (unsigned short)(e + 2);
-        if (word & 0xff000000u) pix[basePos + c0 + c1 + c2 + __popc(m3 & lt)] = (unsigned short)(e + 3);
-    }
-    __syncthreads();
-
-    /* 3x3 non-max suppression, one thread per corner pixel.  sc holds S - (minTh - 1), 0 = no corner.  cv::FAST
-     * runs on the cell's own sub-image, so neighbours in another cell (or outside the window) count as 0.
-     * A local maximum at minThFAST with S >= iniThFAST is also one at iniThFAST (weaker neighbours only drop to 0). */
-    const uint8_t* scb = reinterpret_cast<const uint8_t*>(sc);
-    const int iniShift = g.iniTh - g.minTh + 1;
-    const int np = npix;
-    unsigned short* lml = work;                      /* local maxima x | y << 8 (the quad list is dead) */
-    for (int i0 = 0; i0 < np; i0 += blockDim.x) {
-        const int i = i0 + tid;
-        bool lm = false;
-        unsigned e = 0;
-        if (i < np) {
-            e = pix[i];
-            const int x = e & 0xff, y = (e >> 8) & 0x3f;
-            const int cg = (x >= L.wCell) + (x >= 2 * L.wCell) + (x >= 3 * L.wCell), xin = x - cg * L.wCell;
-            const uint8_t* p = scb + ((y + 1) * FAST_SCW + 1) * 4 + x;
-            const int sv = p[0];
-            const int up = p[-FAST_SCW * 4], dn = p[FAST_SCW * 4];
-            const int lf = max(max((int)p[-1], (int)p[-FAST_SCW * 4 - 1]), (int)p[FAST_SCW * 4 - 1]);
-            const int rt = max(max((int)p[1], (int)p[-FAST_SCW * 4 + 1]), (int)p[FAST_SCW * 4 + 1]);
-            int nb = max(up, dn);
-            if (xin > 0) nb = max(nb, lf);
-            if (xin < L.wCell - 1) nb = max(nb, rt);
-            lm = sv > nb;
-            if (lm) atomicAdd(&cellCnt[cg][sv >= iniShift], 1);
+        __syncthreads();
+        /* every local maximum of the pass is a keypoint of its cell (:808-816): one global atomic reserves the CTA's
+         * range of the (frame, level) candidate pool */
+        const int nlm = nout;
+        if (tid == 0) {
+            int b = 0;
+            if (nlm) {
+                b = atomicAdd(candCount + frame * g.nlevels + l, nlm);
+                if (b + nlm > L.candCap) atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
+            }
+            gbase = b;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, lm);
-        int basePos = 0;
-        if (lane == 0 && m) basePos = smem_add(&nout, __popc(m));
-        basePos = __shfl_sync(0xffffffffu, basePos, 0);
-        if (lm) lml[basePos + __popc(m & ((1u << lane) - 1))] = (unsigned short)e;
-    }
-    __syncthreads();
-    /* the cell is retried with minThFAST only if it found nothing at iniThFAST (:812): per cell the kept local
-     * maxima are those >= iniThFAST if there is one, else all of them.  One global atomic reserves the CTA's
-     * range of the (frame, level) candidate pool. */
-    const int nlm = nout;
-    if (tid == 0) {
-        int total = 0;
-        for (int c = 0; c < FAST_GROUP; c++) total += cellCnt[c][1] ? cellCnt[c][1] : cellCnt[c][0];
-        int b = 0;
-        if (total) {
-            b = atomicAdd(candCount + frame * g.nlevels + l, total);
-            if (b + total > L.candCap) atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
-        }
-        gbase = total ? b : -1;
-        npix = 0;                                    /* reused as the emission cursor */
-    }
-    __syncthreads();
-    const int b0 = gbase;
-    if (b0 < 0) return;
-    uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
-    for (int i0 = 0; i0 < nlm; i0 += blockDim.x) {
-        const int i = i0 + tid;
-        bool keep = false;
-        uint32_t rec = 0;
-        if (i < nlm) {
+        /* cells that found nothing are run again at minThFAST */
+        unsigned again = 0;
+        for (int c = 0; c < ncell; c++) again |= (cellCnt[c] == 0 ? 1u : 0u) << c;
+        again &= retry;
+        __syncthreads();
+        const int b0 = gbase;
+        for (int i = tid; i < nlm; i += blockDim.x) {
             const unsigned e = lml[i];
             const int x = e & 0xff, y = (e >> 8) & 0x3f;
-            const int cg = (x >= L.wCell) + (x >= 2 * L.wCell) + (x >= 3 * L.wCell);
             const int sv = scb[((y + 1) * FAST_SCW + 1) * 4 + x];
-            keep = sv >= (cellCnt[cg][1] ? iniShift : 1);
             /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
-            rec = (uint32_t)(x + 3 + cj0 * L.wCell) | ((uint32_t)(y + 3 + ci * L.hCell) << 12) | ((uint32_t)(sv + g.minTh - 1) << 24);
+            if (b0 + i < L.candCap)
+                out[b0 + i] = (uint32_t)(x + 3 + cj0 * wC) | ((uint32_t)(y + 3 + ci * L.hCell) << 12) | ((uint32_t)(sv + th - 1) << 24);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        int basePos = 0;
-        if (lane == 0 && m) basePos = smem_add(&npix, __popc(m));
-        basePos = __shfl_sync(0xffffffffu, basePos, 0);
-        const int pos = b0 + basePos + __popc(m & ((1u << lane) - 1));
-        if (keep && pos < L.candCap) out[pos] = rec;
+        if (pass == 1 || again == 0 || g.minTh >= g.iniTh) break;
+        retry = again;
+        __syncthreads();                 /* the lists and the score rows are rewritten by the next pass */
     }
 }
 
