@@ -1139,8 +1139,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
         const int d = c_umax[v < 0 ? -v : v];
         const uint8_t* row = reinterpret_cast<const uint8_t*>(P) + (PR + v) * (PWORDS * 4) + PR;
         int sacc = 0;
-        for (int u = -d; u <= d; u++) {
-            const int val = row[u];
+        /* fixed trip count (the row's half-width d only masks): the byte loads of a batch are independent and in flight
+         * together instead of one load-use round trip per pixel */
+#pragma unroll 16
+        for (int u = -15; u <= 15; u++) {
+            const int raw = row[u];
+            const int val = (u >= -d && u <= d) ? raw : 0;
             m10 += u * val;
             sacc += val;
         }
