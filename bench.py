@@ -375,7 +375,7 @@ def main():
                 "alg_bytes_per_launch": alg[dom] * frames_per_pass, "avg_launch_ms": dom_ms_per_launch,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
                 "stage_timing": "separate pass of the same %d steps with per-stage CUDA events, single lane: %.2f ms/step "
-                                "(the timed `value` region overlaps consecutive passes on two lanes)" % (args.steps, prof_ms / args.steps),
+                                "(the timed `value` region overlaps consecutive passes on four lanes)" % (args.steps, prof_ms / args.steps),
                 "step": {"achieved": step_achieved, "frac": step_achieved / peak,
                          "bytes_per_frame": BYTES_PER_FRAME_EUROC,
                          "note": "whole hot path per GPU by SURVEY 8(d) compulsory bytes; latency/INT-bound by design"}}

@@ -90,7 +90,7 @@ struct viorb_extractor {
     int ngroups = 0;
     int groupClass[5] = {0, 0, 0, 0, 0};   /* groups sorted by tile byte shift: class sh = [groupClass[sh], groupClass[sh+1]) */
     ResizeTables tables;
-    /* pass workspaces: consecutive passes alternate between two lanes (own stream + buffers) so that the
+    /* pass workspaces: consecutive passes rotate over `nlanes` lanes (own stream + buffers) so that the
      * latency-bound kernels of one pass overlap with those of the next */
     struct Lane {
         cudaStream_t stream = nullptr;
@@ -112,7 +112,7 @@ struct viorb_extractor {
     const void* graphKey[4] = {nullptr, nullptr, nullptr, nullptr};
     int graphCap = 0, graphGen = -1, graphLaunches = 0, geomGen = 0;
     ExtractBuffers buf = {};       /* buffers of the most recent pass (resident pyramids, debug views) */
-    /* staging for host-buffer entry points (double buffered) */
+    /* staging for host-buffer entry points */
     /* host-buffer path: VIORB_SLOTS staging slots, slot s runs on lane s (H2D(k+2) || H2D(k+1) || compute(k) || D2H(k-1)) */
     DevBuf<uint8_t> in[4];
     DevBuf<viorb_keypoint> okps[4];
@@ -492,7 +492,7 @@ int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, in
     if (ctx_bind(ctx)) { delete e; return VIORB_ERR_CUDA; }
     cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
     cudaHostAlloc((void**)&e->hostStatus, 64, cudaHostAllocDefault);
-    if (getenv("VIORB_LANES")) e->nlanes = std::min(4, std::max(2, atoi(getenv("VIORB_LANES"))));   /* the host-buffer path pairs lanes with its two staging slots */
+    if (getenv("VIORB_LANES")) e->nlanes = std::min(4, std::max(2, atoi(getenv("VIORB_LANES"))));   /* the host-buffer path pairs lanes with its staging slots */
     for (int i = 0; i < 4; i++) {
         cudaStreamCreateWithFlags(&e->lanes[i].stream, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&e->lanes[i].evDone, cudaEventDisableTiming);
