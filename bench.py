@@ -365,8 +365,8 @@ def main():
             if l0.get("alu_pipe_pct") is not None:
                 pipes = {"alu_pipe_pct_of_peak": l0["alu_pipe_pct"], "issue_active_pct": l0["issue_active_pct"],
                          "dram_pct_of_peak": l0.get("dram_pct"),
-                         "note": "same ncu capture: the kernel is bound by the integer ALU pipe (64 lanes/clk/SM measured, "
-                                 "tools/ubench/pipes.cu), not by HBM"}
+                         "note": "same ncu capture: the kernel is bound by instruction issue on the integer (64 lanes/clk/SM "
+                                 "measured, tools/ubench/pipes.cu) and shared-memory pipes, not by HBM"}
             traffic_src = "ncu --set full, %s (dram__bytes_read.sum + dram__bytes_write.sum per 128-frame launch)" % tj[names[0]]["source"]
     except Exception:
         pass
