@@ -355,3 +355,14 @@ def test_search_by_sim3(api, ctx, oracle, stereo):
     f1.close(); f2.close()
     assert n_ref > 20
     assert n == n_ref and (m12 == m_ref).all()
+
+
+def test_matchers_differential_fuzz():
+    """tools/fuzz_search.py: fresh stereo pairs and random scenarios per seed through every matcher entry point"""
+    import os
+    import subprocess
+    import sys
+    from util import ROOT
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_search.py"), "8", "500"], capture_output=True, text=True,
+                       cwd=ROOT, timeout=900)
+    assert p.returncode == 0 and " 0 mismatches" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
