@@ -477,7 +477,7 @@ int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, in
                            viorb_extractor** out) {
     if (!ctx || !out) return fail(VIORB_ERR_INVALID, "NULL argument");
     *out = nullptr;
-    if (nfeatures <= 0 || nlevels < 1 || nlevels > VIORB_MAX_LEVELS || !(scale_factor > 1.0f) || ini < mn || mn < 1 || mn > 127 || ini > 255)
+    if (nfeatures <= 0 || nlevels < 1 || nlevels > VIORB_MAX_LEVELS || !(scale_factor > 1.0f) || ini < mn || mn < 1 || ini > 127)      /* the byte-domain pre-test of the FAST kernel needs thresholds <= 127 */
         return fail(VIORB_ERR_INVALID, "bad ORB parameters (nfeatures %d, scale %f, levels %d, FAST %d/%d)", nfeatures,
                     scale_factor, nlevels, ini, mn);
     if (scale_factor > 1.5f)
