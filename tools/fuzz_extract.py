@@ -40,7 +40,7 @@ def main():
         nl = int(rng.integers(2, 9))
         sf = float(np.float32(rng.choice([1.1, 1.2, 1.2, 1.25, 1.33, 1.5])))
         nf = int(rng.integers(100, 4000))
-        it = int(rng.integers(8, 40))
+        it = int(rng.integers(8, 128)) if rng.random() < 0.3 else int(rng.integers(8, 40))
         mt = int(rng.integers(2, it + 1))
         img = image(rng, h, w)
         try:
