@@ -367,7 +367,7 @@ __device__ __forceinline__ unsigned fast_score_s16x2(const unsigned (&r)[16], un
 }
 
 template <int SH>
-__global__ void __launch_bounds__(128, 8) fast_cells_kernel(const __grid_constant__ FrameGeom g,
+__global__ void __launch_bounds__(128, 9) fast_cells_kernel(const __grid_constant__ FrameGeom g,
                                                          const __grid_constant__ TmaMaps maps,
                                                          const int4* __restrict__ groups,
                                                          uint32_t* __restrict__ cand, int* __restrict__ candCount,
