@@ -984,7 +984,7 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const __grid_consta
  * border rule), blurred there with the OpenCV >= 3.4 fixed-point taps [18 34 48 56 48 34 18]/256,
  * and sampled at the 512 steered pattern points.  The blurred level image never exists in HBM.
  * ---------------------------------------------------------------------------------------------- */
-#define DESC_WARPS 8
+#define DESC_WARPS 4
 #define PR 21                 /* patch radius */
 #define PROWS 43              /* patch rows / columns */
 #define PWORDS 13             /* patch row stride in 32-bit words (odd: conflict-free row pairs; 12 words used) */
