@@ -653,7 +653,8 @@ __global__ void __launch_bounds__(128, 9) fast_cells_kernel(const __grid_constan
  * is replaced by the creation order (newest first == list order), the documented tie convention.
  * Keys never move: each key only tracks the list position of its node (nodeOf).
  * ---------------------------------------------------------------------------------------------- */
-#define OCT_THREADS 256
+#define OCT_THREADS 256           /* upper bound; batches launch 128 threads (more CTAs per SM overlap the barrier waits), single
+                                     frames 256 (shorter critical path of the level-0 CTA) */
 
 struct OctSmem {
     short4* rectA; short4* rectB;   /* x0,y0,x1,y1 */
@@ -1357,7 +1358,7 @@ int viorb_octree_prepare(int NC) {
 
 int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s) {
     dim3 grid(g.nlevels, F);
-    octree_kernel<<<grid, OCT_THREADS, viorb_octree_smem_bytes(nodeCap), s>>>(g, b.cand, b.candCount, b.nodeOf, b.sel,
+    octree_kernel<<<grid, F <= 8 ? OCT_THREADS : OCT_THREADS / 2, viorb_octree_smem_bytes(nodeCap), s>>>(g, b.cand, b.candCount, b.nodeOf, b.sel,
                                                                                b.selCount, b.status, nodeCap);
     return 1;
 }
