@@ -166,7 +166,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     FrameGeom& g = e->geom;
     memset(&g, 0, sizeof(g));
     g.nlevels = e->nlevels; g.rows = rows; g.cols = cols; g.iniTh = e->iniTh; g.minTh = e->minTh;
-    g.dbg = getenv("VIORB_DEBUG") ? atoi(getenv("VIORB_DEBUG")) : 0;
+    g.reserved = 0;
     size_t pyrOff = 0;
     int cellBase = 0, candBase = 0, selBase = 0, xtab = 0, ytab = 0, nodeCap = 0;
     for (int l = 0; l < e->nlevels; l++) {

@@ -398,7 +398,6 @@ __global__ void __launch_bounds__(128, 9) fast_cells_kernel(const __grid_constan
     const int ch = min(iniY + L.hCell + 6, maxBorderY) - iniY;
     const int ww = cwG - 6, wh = ch - 6;      /* detection window of the whole group */
     if (ww <= 0 || wh <= 0) return;
-    if (g.dbg & 16) return;
     const int tid = threadIdx.x, lane = tid & 31;
     const int NQ = (ww + 3) >> 2;            /* quads per window row */
     const int ntask = NQ * wh;
@@ -535,7 +534,7 @@ __global__ void __launch_bounds__(128, 9) fast_cells_kernel(const __grid_constan
         /* phase 2 -- exact cornerScore on the surviving quads only, densely packed over the CTA.
          * sc holds relu(S - (th - 1)): 0 = not a corner at th */
         const unsigned negBias = __vneg2(thP);
-        const int nw = (g.dbg & 2) ? 0 : nwork;
+        const int nw = nwork;
         for (int i = tid; i < nw; i += blockDim.x) {
             const int t = work[i];
             const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
