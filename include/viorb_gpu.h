@@ -173,6 +173,10 @@ int viorb_frame_index_create_device(viorb_ctx* ctx, const viorb_keypoint* d_kps,
                                     const float* scale_factors, int nlevels, viorb_frame_index** out);
 /* mvKeysUn (may be NULL) and {mnMinX, mnMaxX, mnMinY, mnMaxY} (may be NULL) of an index */
 int viorb_frame_index_keys(viorb_frame_index* fi, viorb_keypoint* kps_un, float bounds[4]);
+/* Frame::mGrid (include/Frame.h:191) as built by AssignFeaturesToGrid (src/Frame.cc:410-425): CSR over the 64 x 48
+ * cells, cell id = ix * 48 + iy; cell_start has 64*48 + 1 entries, cell_items (capacity n) lists the keypoint indices
+ * of every cell in ascending order (the reference pushes them in keypoint order).                               */
+int viorb_frame_index_grid(viorb_frame_index* fi, int32_t* cell_start, int32_t* cell_items);
 /* stand-alone forms of the two Frame members, host buffers */
 int viorb_undistort_keypoints(viorb_ctx* ctx, const viorb_keypoint* kps, int n, float fx, float fy, float cx, float cy,
                               const float* dist_coef, int ndist, viorb_keypoint* kps_un);

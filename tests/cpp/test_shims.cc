@@ -582,6 +582,57 @@ int main() {
         orc_grid_destroy(gb);
     }
 
+    /* ---- Frame members on the path: ExtractORB, UndistortKeyPoints, ComputeImageBounds, AssignFeaturesToGrid,
+     *      GetFeaturesInArea (the Frame constructor's sequence, src/Frame.cc:258-293) ---- */
+    {
+        Frame Fc;
+        Fc.mpORBextractorLeft = &exL; Fc.mpORBextractorRight = &exR;
+        Fc.ExtractORB(0, left);
+        Fc.ExtractORB(1, right);
+        Fc.N = (int)Fc.mvKeys.size();
+        CHECK(same_keypoints(Fc.mvKeys, oL.k) && same_keypoints(Fc.mvKeysRight, oR.k), "Frame::ExtractORB differs from the oracle");
+        Fc.mK = cv::Mat::zeros(3, 3, CV_32F);
+        Fc.mK.at<float>(0, 0) = 718.856f; Fc.mK.at<float>(1, 1) = 718.856f; Fc.mK.at<float>(0, 2) = 607.1928f; Fc.mK.at<float>(1, 2) = 185.2157f;
+        Fc.mK.at<float>(2, 2) = 1.0f;
+        const float dist[4] = {-0.28340811f, 0.07395907f, 0.00019359f, 1.76187114e-05f};
+        Fc.mDistCoef = cv::Mat(4, 1, CV_32F);
+        for (int i = 0; i < 4; i++) Fc.mDistCoef.at<float>(i, 0) = dist[i];
+        Fc.mDescriptors = dL;
+        Fc.mvScaleFactors = exL.GetScaleFactors();
+        Fc.UndistortKeyPoints();
+        Fc.ComputeImageBounds(left);
+        std::vector<orc_keypoint> un(oL.k.size());
+        float bref[4];
+        orc_undistort_keypoints(oL.k.data(), (int)oL.k.size(), 718.856f, 718.856f, 607.1928f, 185.2157f, dist, 4, un.data());
+        orc_compute_image_bounds(W, H, 718.856f, 718.856f, 607.1928f, 185.2157f, dist, 4, bref);
+        CHECK(same_keypoints(Fc.mvKeysUn, un), "Frame::UndistortKeyPoints differs from the oracle");
+        CHECK(Fc.mnMinX == bref[0] && Fc.mnMaxX == bref[1] && Fc.mnMinY == bref[2] && Fc.mnMaxY == bref[3], "Frame::ComputeImageBounds differs");
+        Fc.AssignFeaturesToGrid();
+        orc_grid* grid = orc_grid_create(un.data(), (int)un.size(), bref[0], bref[1], bref[2], bref[3]);
+        /* every cell list through a query that covers exactly that cell is awkward; compare whole-area queries and counts */
+        size_t inGrid = 0;
+        for (int i = 0; i < 64; i++) for (int j = 0; j < 48; j++) inGrid += Fc.mGrid[i][j].size();
+        std::vector<int32_t> all(un.size() + 1);
+        const int nall = orc_grid_features_in_area(grid, 0.5f * (bref[0] + bref[1]), 0.5f * (bref[2] + bref[3]), 1e6f, -1, -1, all.data(), (int)all.size());
+        bool same = (int)inGrid == nall;
+        /* grid order: cells ix-major, iy, slot == the oracle's enumeration of the whole area */
+        size_t pos = 0;
+        for (int i = 0; same && i < 64; i++) for (int j = 0; same && j < 48; j++) for (size_t k = 0; same && k < Fc.mGrid[i][j].size(); k++) same = (int)Fc.mGrid[i][j][k] == all[pos++];
+        CHECK(nall > 1000 && same, "Frame::AssignFeaturesToGrid differs from the oracle grid");
+        std::vector<int32_t> ref(un.size() + 1);
+        same = true;
+        for (int q = 0; same && q < 20; q++) {
+            const float x = rndf() * W, y = rndf() * H, r = 5.0f + rndf() * 60.0f;
+            const int lo = q % 3 == 0 ? -1 : (int)(rnd() % 3), hi = q % 3 == 0 ? -1 : lo + (int)(rnd() % 3);
+            const std::vector<size_t> got = Fc.GetFeaturesInArea(x, y, r, lo, hi);
+            const int nr = orc_grid_features_in_area(grid, x, y, r, lo, hi, ref.data(), (int)ref.size());
+            same = (int)got.size() == nr;
+            for (int k = 0; same && k < nr; k++) same = (int)got[k] == ref[k];
+        }
+        CHECK(same, "Frame::GetFeaturesInArea differs from the oracle");
+        orc_grid_destroy(grid);
+    }
+
     orc_extractor_destroy(oL.e);
     orc_extractor_destroy(oR.e);
     if (g_fail == 0) printf("ALL SHIM CHECKS PASSED\n");

@@ -71,6 +71,7 @@ def lib():
         "viorb_frame_index_create_distorted": [vp, vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, i32, i32, vp, i32, pp],
         "viorb_frame_index_create_device": [vp, vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, i32, i32, vp, i32, pp],
         "viorb_frame_index_keys": [vp, vp, vp],
+        "viorb_frame_index_grid": [vp, vp, vp],
         "viorb_undistort_keypoints": [vp, vp, i32, f32, f32, f32, f32, vp, i32, vp],
         "viorb_compute_image_bounds": [vp, i32, i32, f32, f32, f32, f32, vp, i32, vp],
         "viorb_frame_features_in_area": [vp, f32, f32, f32, i32, i32, vp, i32, pi],
@@ -341,6 +342,13 @@ class FrameIndex:
         b = np.zeros(4, np.float32)
         _ck(lib().viorb_frame_index_keys(self.h, _ptr(k) if self.n else None, _ptr(b)))
         return k, b
+
+    def grid(self):
+        """Frame::mGrid as CSR: (cell_start[64*48+1], cell_items), cell id = ix*48 + iy"""
+        cs = np.zeros(64 * 48 + 1, np.int32)
+        ci = np.zeros(max(self.n, 1), np.int32)
+        _ck(lib().viorb_frame_index_grid(self.h, _ptr(cs), _ptr(ci)))
+        return cs, ci[:cs[-1]]
 
     def close(self):
         if getattr(self, "h", None):

@@ -274,6 +274,22 @@ int viorb_frame_index_keys(viorb_frame_index* fi, viorb_keypoint* kps_un, float 
     return VIORB_OK;
 }
 
+int viorb_frame_index_grid(viorb_frame_index* fi, int32_t* cell_start, int32_t* cell_items) {
+    if (!fi || !cell_start) return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    int rc;
+    if ((rc = viorb_ctx_bind(fi->ctx))) return rc;
+    cudaStream_t s = viorb_ctx_stream(fi->ctx);
+    VCU(cudaMemcpyAsync(cell_start, fi->dev.cellStart, (64 * 48 + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    VCU(cudaStreamSynchronize(s));
+    const int total = cell_start[64 * 48];
+    if (total > 0) {
+        if (!cell_items) return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+        VCU(cudaMemcpyAsync(cell_items, fi->dev.cellItems, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        VCU(cudaStreamSynchronize(s));
+    }
+    return VIORB_OK;
+}
+
 int viorb_undistort_keypoints(viorb_ctx* c, const viorb_keypoint* kps, int n, float fx, float fy, float cx, float cy,
                               const float* dist_coef, int ndist, viorb_keypoint* kps_un) {
     if (!c || n < 0 || (n > 0 && (!kps || !kps_un))) return viorb_fail(VIORB_ERR_INVALID, "bad argument");

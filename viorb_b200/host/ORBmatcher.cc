@@ -587,6 +587,69 @@ int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& v
 }
 
 #ifndef VIORB_USE_ORBSLAM_HEADERS
+/* ---- the members of Frame on the ORB path (reference src/Frame.cc); inside the VIORB tree paste these bodies into
+ * src/Frame.cc ---- */
+void Frame::ExtractORB(int flag, const cv::Mat& im) {
+    if (flag == 0) (*mpORBextractorLeft)(im, cv::Mat(), mvKeys, mDescriptors);
+    else (*mpORBextractorRight)(im, cv::Mat(), mvKeysRight, mDescriptorsRight);
+}
+
+namespace {
+void distortion_of(const Frame& F, float k[12], int& nk) {
+    nk = F.mDistCoef.rows * F.mDistCoef.cols;
+    if (nk > 12) nk = 12;
+    for (int i = 0; i < nk; i++) k[i] = F.mDistCoef.rows >= F.mDistCoef.cols ? F.mDistCoef.at<float>(i, 0) : F.mDistCoef.at<float>(0, i);
+}
+}  // namespace
+
+void Frame::UndistortKeyPoints() {
+    float k[12];
+    int nk = 0;
+    distortion_of(*this, k, nk);
+    mvKeysUn.resize(N);
+    if (N == 0) return;
+    check(viorb_undistort_keypoints(thread_ctx(), reinterpret_cast<const viorb_keypoint*>(mvKeys.data()), N, mK.at<float>(0, 0),
+                                    mK.at<float>(1, 1), mK.at<float>(0, 2), mK.at<float>(1, 2), k, nk,
+                                    reinterpret_cast<viorb_keypoint*>(mvKeysUn.data())),
+          "viorb_undistort_keypoints");
+}
+
+void Frame::ComputeImageBounds(const cv::Mat& imLeft) {
+    float k[12], b[4];
+    int nk = 0;
+    distortion_of(*this, k, nk);
+    check(viorb_compute_image_bounds(thread_ctx(), imLeft.cols, imLeft.rows, mK.at<float>(0, 0), mK.at<float>(1, 1), mK.at<float>(0, 2),
+                                     mK.at<float>(1, 2), k, nk, b),
+          "viorb_compute_image_bounds");
+    mnMinX = b[0]; mnMaxX = b[1]; mnMinY = b[2]; mnMaxY = b[3];
+    mfGridElementWidthInv = 64.0f / (mnMaxX - mnMinX);              /* :180-183 */
+    mfGridElementHeightInv = 48.0f / (mnMaxY - mnMinY);
+}
+
+void Frame::AssignFeaturesToGrid() {
+    for (int i = 0; i < 64; i++)
+        for (int j = 0; j < 48; j++) mGrid[i][j].clear();
+    if (N == 0) return;
+    FrameIndexGuard g;
+    make_index(*this, g);
+    std::vector<int32_t> start(64 * 48 + 1), items(N);
+    check(viorb_frame_index_grid(g.fi, start.data(), items.data()), "viorb_frame_index_grid");
+    for (int c = 0; c < 64 * 48; c++)
+        mGrid[c / 48][c % 48].assign(items.begin() + start[c], items.begin() + start[c + 1]);
+}
+
+std::vector<size_t> Frame::GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel, const int maxLevel) const {
+    std::vector<size_t> out;
+    if (N == 0) return out;
+    FrameIndexGuard g;
+    make_index(const_cast<Frame&>(*this), g);
+    std::vector<int32_t> idx(N);
+    int n = 0;
+    check(viorb_frame_features_in_area(g.fi, x, y, r, minLevel, maxLevel, idx.data(), N, &n), "viorb_frame_features_in_area");
+    out.assign(idx.begin(), idx.begin() + n);
+    return out;
+}
+
 /* Frame::ComputeStereoMatches (reference src/Frame.cc:646-820) on the pyramids resident in the two extractors */
 void Frame::ComputeStereoMatches() {
     mvuRight.assign(N, -1.0f);

@@ -87,6 +87,16 @@ public:
     float mfLogScaleFactor = 0.18232156f;      /* log(1.2) */
     cv::Mat mTcw;                              /* 4x4 CV_32F */
     ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
+    cv::Mat mK, mDistCoef;                     /* 3x3 and 4x1 (or 5x1) CV_32F */
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    std::vector<size_t> mGrid[64][48];         /* FRAME_GRID_COLS x FRAME_GRID_ROWS, include/Frame.h:41-42,191 */
+    /* the members of the reference Frame that sit on the ORB path, each one call into libviorb_b200 (host/ORBmatcher.cc) */
+    void ExtractORB(int flag, const cv::Mat& im);                      /* src/Frame.cc:427-433 */
+    void UndistortKeyPoints();                                         /* :584-614 -> viorb_undistort_keypoints */
+    void ComputeImageBounds(const cv::Mat& imLeft);                    /* :616-645 -> viorb_compute_image_bounds */
+    void AssignFeaturesToGrid();                                       /* :410-425 -> viorb_frame_index_create + _grid */
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
+                                          const int maxLevel = -1) const;      /* :507-560 -> viorb_frame_features_in_area */
     void ComputeStereoMatches();               /* src/Frame.cc:646-820 -> viorb_stereo_match */
 };
 
