@@ -67,6 +67,22 @@ def main():
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             md.append("| %s | %d | %.1f | %.1f%% | %.1f |" % (k, a[0], a[1], 100 * a[1] / tot, a[1] / a[0]))
         md.append("")
+        step = {"pyramid": ("pyr_level0_kernel", "pyr_resize_kernel"), "fast": ("fast_cells_kernel",), "octree": ("octree_kernel",),
+                "describe": ("orient_describe_kernel",)}
+        stot = sum(agg[k][1] for ks in step.values() for k in ks if k in agg)
+        if stot > 0:
+            md += ["Shares inside the extraction step (what `bench.py` times; the matcher launches above belong to its separate",
+                   "`matcher` block): " + ", ".join("%s %.1f%%" % (n, 100 * sum(agg[k][1] for k in ks if k in agg) / stot)
+                                                    for n, ks in step.items()) + ".", ""]
+            bj = os.path.join(go, tag + "_bench.json")
+            if os.path.exists(bj):
+                try:
+                    st = json.loads(open(bj).read().strip().splitlines()[-1])["roofline"]["stage_ms_per_step"]
+                    t2 = sum(st.values())
+                    md += ["Live CUDA-event stage timers of the default 4096-frame bench of the same call: " +
+                           ", ".join("%s %.1f%%" % (n, 100 * st[n] / t2) for n in step) + ".", ""]
+                except Exception:
+                    pass
     # ---- full capture
     rep = os.path.join(go, tag + "_prof.ncu-rep")
     traffic = {}
