@@ -43,6 +43,8 @@ def lib(path=None):
     L.orc_fast_atan2.argtypes = [f32, f32]
     L.orc_fast_atan2.restype = f32
     L.orc_sincosf.argtypes = [f32, C.POINTER(f32), C.POINTER(f32)]
+    L.orc_steering_sweep.argtypes = [C.c_uint32, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_steering_sweep.restype = C.c_int64
     L.orc_cv_round_f.argtypes = [f32]
     L.orc_extractor_create.argtypes = [i32, f32, i32, i32, i32]
     L.orc_extractor_create.restype = vp
@@ -147,6 +149,18 @@ def sincosf(x):
     s, c = C.c_float(), C.c_float()
     lib().orc_sincosf(float(x), C.byref(s), C.byref(c))
     return s.value, c.value
+
+
+def steering_sweep(first_bits, n, which=0, outputs=True, threads=None):
+    """(sin, cos, mismatches) of the steering pair for n consecutive float bit patterns as angles in degrees;
+    which=0 -> this image's libm, which=1 -> the restatement; mismatches counts restatement != libm."""
+    import os
+    threads = threads or max(1, os.cpu_count() or 1)
+    s = np.empty(n, np.float32) if outputs else None
+    c = np.empty(n, np.float32) if outputs else None
+    bad = lib().orc_steering_sweep(int(first_bits), int(n), int(which), s.ctypes.data if outputs else None,
+                                   c.ctypes.data if outputs else None, threads)
+    return s, c, int(bad)
 
 
 # ---------------------------------------------------------------- extractor

@@ -362,6 +362,36 @@ extern "C" void orc_sincosf(float y, float* sinp, float* cosp) {
     }
 }
 
+/* Sweep of the steering of computeOrbDescriptor (ORBextractor.cc:107-113) over the n consecutive float bit patterns
+ * first_bits, first_bits+1, ... taken as keypoint angles in degrees.  which = 0: this image's libm sincosf (what the
+ * reference binary calls); which = 1: the restatement above.  Outputs may be null; the return value is
+ * the number of inputs on which restatement and libm differ in either output. */
+extern "C" int64_t orc_steering_sweep(uint32_t first_bits, int64_t n, int which, float* sin_out, float* cos_out, int threads) {
+    if (threads < 1) threads = 1;
+    std::vector<int64_t> bad((size_t)threads, 0);
+    std::vector<std::thread> pool;
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&, t]() {
+            const int64_t lo = n * t / threads, hi = n * (t + 1) / threads;
+            for (int64_t i = lo; i < hi; i++) {
+                const uint32_t u = first_bits + (uint32_t)i;
+                float deg, sl, cl, sr, cr;
+                memcpy(&deg, &u, 4);
+                const float ang = deg * factorPI;
+                sincosf(ang, &sl, &cl);
+                orc_sincosf(ang, &sr, &cr);
+                if (memcmp(&sl, &sr, 4) || memcmp(&cl, &cr, 4)) bad[(size_t)t]++;
+                if (sin_out) sin_out[i] = which ? sr : sl;
+                if (cos_out) cos_out[i] = which ? cr : cl;
+            }
+        });
+    for (auto& th : pool) th.join();
+    int64_t total = 0;
+    for (int64_t b : bad) total += b;
+    return total;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * ORBextractor
  * ---------------------------------------------------------------------------------------------- */

@@ -98,6 +98,16 @@ def test_sincosf_vs_glibc(oracle):
         assert (ms, mc) == (s.value, c.value), x
 
 
+def test_sincosf_restatement_exhaustive(oracle):
+    """every angle the extractor can produce is a float in [0, 360] degrees; the restatement must equal
+    this image's libm on all 1.1e9 of them (bit patterns 0 .. bits(360.0f))."""
+    last = int(np.array([360.0], np.float32).view(np.uint32)[0])
+    bad, chunk = 0, 1 << 27
+    for first in range(0, last + 1, chunk):
+        bad += oracle.steering_sweep(first, min(chunk, last + 1 - first), outputs=False)[2]
+    assert bad == 0
+
+
 def test_tables(oracle):
     e = oracle.Extractor(1000, 1.2, 8, 20, 7)
     assert e.quotas() == [217, 181, 151, 126, 105, 87, 73, 60]

@@ -61,6 +61,7 @@ def lib():
         "viorb_extractor_resident": [vp, pi, pi],
         "viorb_extractor_debug_candidates": [vp, i32, i32, vp, i32, pi],
         "viorb_extractor_debug_selected": [vp, i32, i32, vp, i32, pi],
+        "viorb_debug_steering": [vp, C.c_uint32, i64, vp, vp],
         "viorb_descriptor_distance": [vp, vp, vp, i32, vp],
         "viorb_hamming_top2": [vp, vp, i32, vp, i64, i64, vp],
         "viorb_hamming_top2_device": [vp, vp, i32, vp, i64, i64, vp],
@@ -132,6 +133,12 @@ class Context:
 
     def launch_count(self):
         return int(lib().viorb_ctx_launch_count(self.h))
+
+    def debug_steering(self, first_bits, n):
+        """(sin, cos) the descriptor kernel uses for n consecutive float bit patterns taken as angles in degrees."""
+        s, c = np.empty(n, np.float32), np.empty(n, np.float32)
+        _ck(lib().viorb_debug_steering(self.h, int(first_bits), int(n), _ptr(s), _ptr(c)))
+        return s, c
 
     def close(self):
         if getattr(self, "h", None):

@@ -847,6 +847,20 @@ int viorb_extractor_debug_selected(viorb_extractor* e, int frame, int level, int
 }
 
 /* ---------------------------------------------------------------------------------------------- matcher */
+int viorb_debug_steering(viorb_ctx* c, uint32_t first_bits, int64_t n, float* sin_out, float* cos_out) {
+    if (!c || !sin_out || !cos_out || n < 0 || n > (1ll << 28)) return fail(VIORB_ERR_INVALID, "bad argument");
+    if (n == 0) return VIORB_OK;
+    int rc;
+    if ((rc = ctx_bind(c))) return rc;
+    if ((rc = c->scratchA.ensure((size_t)n * 8))) return rc;
+    float* d = reinterpret_cast<float*>(c->scratchA.p);
+    c->launches += viorb_launch_steering_sweep(first_bits, n, d, d + n, c->sms, c->stream);
+    CU(cudaMemcpyAsync(sin_out, d, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(cos_out, d + n, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VIORB_OK;
+}
+
 int viorb_descriptor_distance(viorb_ctx* c, const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {
     if (!c || !a || !b || !dist || n < 0) return fail(VIORB_ERR_INVALID, "bad argument");
     if (n == 0) return VIORB_OK;

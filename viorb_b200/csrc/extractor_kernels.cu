@@ -1362,6 +1362,24 @@ int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int 
     return 1;
 }
 
+/* parity hook: the steering pair (b, a) of :112-113 for the consecutive float bit patterns firstBits, firstBits+1, ...
+ * taken as keypoint angles in degrees -- lets the tests sweep every angle the extractor can produce */
+__global__ void __launch_bounds__(256) steering_sweep_kernel(unsigned firstBits, long long n, float* __restrict__ sinOut,
+                                                             float* __restrict__ cosOut) {
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
+        float a, b;
+        sincosf_glibc(__fmul_rn(__uint_as_float(firstBits + (unsigned)i), factorPI), &b, &a);
+        sinOut[i] = b;
+        cosOut[i] = a;
+    }
+}
+
+int viorb_launch_steering_sweep(unsigned firstBits, long long n, float* d_sin, float* d_cos, int sms, cudaStream_t s) {
+    steering_sweep_kernel<<<sms * 8, 256, 0, s>>>(firstBits, n, d_sin, d_cos);
+    return 1;
+}
+
 int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps, uint8_t* d_desc,
                           int cap, int32_t* d_counts, cudaStream_t s) {
     const int slots = g.selPerFrame < cap ? g.selPerFrame : cap;
