@@ -117,6 +117,9 @@ int viorb_extractor_resident(const viorb_extractor* ex, int* first_frame, int* n
  * in no particular order, and the quadtree-selected keypoints of a level in reference list order. */
 int viorb_extractor_debug_candidates(viorb_extractor* ex, int frame, int level, int32_t* xys, int cap, int* n);
 int viorb_extractor_debug_selected(viorb_extractor* ex, int frame, int level, int32_t* xys, int cap, int* n);
+/* parity hook for IC_Angle's cv::fastAtan2((float)m_01, (float)m_10) (src/ORBextractor.cc:103): degrees in [0, 360)
+ * for n pairs of integer patch moments (n <= 2^28 per call); host buffers. */
+int viorb_debug_orientation(viorb_ctx* ctx, const int32_t* m01, const int32_t* m10, int64_t n, float* deg);
 /* parity hook for the steering of computeOrbDescriptor (src/ORBextractor.cc:107-113): b = sinf, a = cosf of
  * angle_deg * (float)(CV_PI/180.f) for the n consecutive float bit patterns first_bits, first_bits+1, ... taken as
  * keypoint angles in degrees (n <= 2^28 per call); host outputs. */

@@ -43,6 +43,8 @@ def lib(path=None):
     L.orc_fast_atan2.argtypes = [f32, f32]
     L.orc_fast_atan2.restype = f32
     L.orc_sincosf.argtypes = [f32, C.POINTER(f32), C.POINTER(f32)]
+    L.orc_orientation_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+    L.orc_orientation_sweep.restype = None
     L.orc_steering_sweep.argtypes = [C.c_uint32, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     L.orc_steering_sweep.restype = C.c_int64
     L.orc_cv_round_f.argtypes = [f32]
@@ -149,6 +151,15 @@ def sincosf(x):
     s, c = C.c_float(), C.c_float()
     lib().orc_sincosf(float(x), C.byref(s), C.byref(c))
     return s.value, c.value
+
+
+def orientation_sweep(m01, m10, threads=None):
+    import os
+    m01 = np.ascontiguousarray(m01, np.int32)
+    m10 = np.ascontiguousarray(m10, np.int32)
+    out = np.empty(len(m01), np.float32)
+    lib().orc_orientation_sweep(m01.ctypes.data, m10.ctypes.data, len(m01), out.ctypes.data, threads or max(1, os.cpu_count() or 1))
+    return out
 
 
 def steering_sweep(first_bits, n, which=0, outputs=True, threads=None):

@@ -362,6 +362,17 @@ extern "C" void orc_sincosf(float y, float* sinp, float* cosp) {
     }
 }
 
+/* IC_Angle's fastAtan2((float)m_01, (float)m_10) (ORBextractor.cc:103) over arrays of integer moments */
+extern "C" void orc_orientation_sweep(const int32_t* m01, const int32_t* m10, int64_t n, float* deg, int threads) {
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([=]() {
+            for (int64_t i = n * t / threads; i < n * (t + 1) / threads; i++) deg[i] = orc_fast_atan2((float)m01[i], (float)m10[i]);
+        });
+    for (auto& th : pool) th.join();
+}
+
 /* Sweep of the steering of computeOrbDescriptor (ORBextractor.cc:107-113) over the n consecutive float bit patterns
  * first_bits, first_bits+1, ... taken as keypoint angles in degrees.  which = 0: this image's libm sincosf (what the
  * reference binary calls); which = 1: the restatement above.  Outputs may be null; the return value is

@@ -44,6 +44,7 @@ int  orc_fast9_16(const uint8_t* img, int w, int h, size_t step, int threshold, 
 void orc_gaussian7_u8(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep);
 float orc_fast_atan2(float y, float x);
 void orc_sincosf(float x, float* s, float* c);
+void orc_orientation_sweep(const int32_t* m01, const int32_t* m10, int64_t n, float* deg, int threads);
 int64_t orc_steering_sweep(uint32_t first_bits, int64_t n, int which, float* sin_out, float* cos_out, int threads);
 int  orc_cv_round_f(float v);
 

@@ -94,6 +94,22 @@ def test_steering_exhaustive_vs_libm(ctx, oracle):
         assert (s.view(np.uint32) == rs.view(np.uint32)).all() and (c.view(np.uint32) == rc.view(np.uint32)).all(), hex(first)
 
 
+def test_orientation_dense_vs_oracle(ctx, oracle):
+    """fastAtan2 on integer moments (|m| <= 255*4896): 2^27 random pairs, every pair of a small-magnitude
+    square (ties, axes, diagonals, zero) and the extreme corners, bit for bit."""
+    lim = 255 * 4896
+    rng = np.random.default_rng(11)
+    small = np.arange(-300, 301, dtype=np.int32)
+    sets = [(np.repeat(small, small.size), np.tile(small, small.size)),
+            (np.array([0, 0, lim, -lim, lim, -lim, lim, -lim], np.int32), np.array([0, lim, 0, 0, lim, lim, -lim, -lim], np.int32))]
+    for _ in range(4):
+        sets.append((rng.integers(-lim, lim + 1, 1 << 25, dtype=np.int32), rng.integers(-lim, lim + 1, 1 << 25, dtype=np.int32)))
+    for m01, m10 in sets:
+        g = ctx.debug_orientation(m01, m10)
+        r = oracle.orientation_sweep(m01, m10)
+        assert (g.view(np.uint32) == r.view(np.uint32)).all()
+
+
 def test_batch_matches_single(api, ctx, oracle):
     h, w, nf, sf, nl, it, mt = CONFIGS["euroc"]
     B = 9

@@ -98,6 +98,19 @@ def test_sincosf_vs_glibc(oracle):
         assert (ms, mc) == (s.value, c.value), x
 
 
+def test_fast_atan2_vs_cv2_dense(oracle):
+    """orc_fast_atan2 against the scalar cv2.fastAtan2 (the call of ORBextractor.cc:103) on integer moments."""
+    cv2 = pytest.importorskip("cv2")
+    lim = 255 * 4896
+    rng = np.random.default_rng(3)
+    small = np.arange(-30, 31, dtype=np.int32)
+    m01 = np.concatenate([np.repeat(small, small.size), rng.integers(-lim, lim + 1, 200000, dtype=np.int32), [lim, -lim, lim, 0]])
+    m10 = np.concatenate([np.tile(small, small.size), rng.integers(-lim, lim + 1, 200000, dtype=np.int32), [lim, lim, -lim, -lim]])
+    ref = np.array([cv2.fastAtan2(float(a), float(b)) for a, b in zip(m01, m10)], np.float32)
+    mine = oracle.orientation_sweep(m01, m10)
+    assert (mine.view(np.uint32) == ref.view(np.uint32)).all()
+
+
 def test_sincosf_restatement_exhaustive(oracle):
     """every angle the extractor can produce is a float in [0, 360] degrees; the restatement must equal
     this image's libm on all 1.1e9 of them (bit patterns 0 .. bits(360.0f))."""

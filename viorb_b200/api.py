@@ -62,6 +62,7 @@ def lib():
         "viorb_extractor_debug_candidates": [vp, i32, i32, vp, i32, pi],
         "viorb_extractor_debug_selected": [vp, i32, i32, vp, i32, pi],
         "viorb_debug_steering": [vp, C.c_uint32, i64, vp, vp],
+        "viorb_debug_orientation": [vp, vp, vp, i64, vp],
         "viorb_descriptor_distance": [vp, vp, vp, i32, vp],
         "viorb_hamming_top2": [vp, vp, i32, vp, i64, i64, vp],
         "viorb_hamming_top2_device": [vp, vp, i32, vp, i64, i64, vp],
@@ -133,6 +134,13 @@ class Context:
 
     def launch_count(self):
         return int(lib().viorb_ctx_launch_count(self.h))
+
+    def debug_orientation(self, m01, m10):
+        """IC_Angle's fastAtan2 (degrees) for arrays of integer patch moments."""
+        m01, m10 = np.ascontiguousarray(m01, np.int32), np.ascontiguousarray(m10, np.int32)
+        out = np.empty(len(m01), np.float32)
+        _ck(lib().viorb_debug_orientation(self.h, _ptr(m01), _ptr(m10), len(m01), _ptr(out)))
+        return out
 
     def debug_steering(self, first_bits, n):
         """(sin, cos) the descriptor kernel uses for n consecutive float bit patterns taken as angles in degrees."""

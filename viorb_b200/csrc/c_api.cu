@@ -847,6 +847,22 @@ int viorb_extractor_debug_selected(viorb_extractor* e, int frame, int level, int
 }
 
 /* ---------------------------------------------------------------------------------------------- matcher */
+int viorb_debug_orientation(viorb_ctx* c, const int32_t* m01, const int32_t* m10, int64_t n, float* deg) {
+    if (!c || !m01 || !m10 || !deg || n < 0 || n > (1ll << 28)) return fail(VIORB_ERR_INVALID, "bad argument");
+    if (n == 0) return VIORB_OK;
+    int rc;
+    if ((rc = ctx_bind(c))) return rc;
+    if ((rc = c->scratchA.ensure((size_t)n * 8)) || (rc = c->scratchB.ensure((size_t)n * 4))) return rc;
+    int* d = reinterpret_cast<int*>(c->scratchA.p);
+    float* o = reinterpret_cast<float*>(c->scratchB.p);
+    CU(cudaMemcpyAsync(d, m01, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + n, m10, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    c->launches += viorb_launch_orientation_sweep(d, d + n, n, o, c->sms, c->stream);
+    CU(cudaMemcpyAsync(deg, o, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VIORB_OK;
+}
+
 int viorb_debug_steering(viorb_ctx* c, uint32_t first_bits, int64_t n, float* sin_out, float* cos_out) {
     if (!c || !sin_out || !cos_out || n < 0 || n > (1ll << 28)) return fail(VIORB_ERR_INVALID, "bad argument");
     if (n == 0) return VIORB_OK;

@@ -1375,6 +1375,18 @@ __global__ void __launch_bounds__(256) steering_sweep_kernel(unsigned firstBits,
     }
 }
 
+/* parity hook: the orientation of IC_Angle (:103) for given integer moments */
+__global__ void __launch_bounds__(256) orientation_sweep_kernel(const int* __restrict__ m01, const int* __restrict__ m10,
+                                                                long long n, float* __restrict__ deg) {
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll)
+        deg[i] = fast_atan2_deg((float)m01[i], (float)m10[i]);
+}
+
+int viorb_launch_orientation_sweep(const int* d_m01, const int* d_m10, long long n, float* d_deg, int sms, cudaStream_t s) {
+    orientation_sweep_kernel<<<sms * 8, 256, 0, s>>>(d_m01, d_m10, n, d_deg);
+    return 1;
+}
+
 int viorb_launch_steering_sweep(unsigned firstBits, long long n, float* d_sin, float* d_cos, int sms, cudaStream_t s) {
     steering_sweep_kernel<<<sms * 8, 256, 0, s>>>(firstBits, n, d_sin, d_cos);
     return 1;

@@ -104,6 +104,7 @@ size_t viorb_fast_smem_bytes(const FrameGeom& g);
 int viorb_fast_prepare(const FrameGeom& g);   /* opt-in dynamic shared memory; returns cudaError */
 #define VIORB_FAST_GROUP 4      /* horizontally adjacent FAST cells per CTA (extractor_kernels.cu FAST_GROUP) */
 int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s);
+int viorb_launch_orientation_sweep(const int* d_m01, const int* d_m10, long long n, float* d_deg, int sms, cudaStream_t s);
 int viorb_launch_steering_sweep(unsigned firstBits, long long n, float* d_sin, float* d_cos, int sms, cudaStream_t s);
 int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps,
                           uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s);
