@@ -65,7 +65,8 @@ int viorb_host_free(void* p);
 int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, int nlevels,
                            int ini_th_fast, int min_th_fast, viorb_extractor** out);
 int viorb_extractor_destroy(viorb_extractor* ex);
-/* optional tuning: frames processed per device pass (working set sized for the 126 MB L2) and the
+/* optional tuning: frames processed per device pass (default 128: working set sized for the 126 MB L2; the
+ * host-buffer batch call uses 32..128 depending on the batch so that short batches still pipeline) and the
  * candidate pool per level as a fraction 1/div of the level's pixel count. */
 int viorb_extractor_configure(viorb_extractor* ex, int chunk_frames, int cand_div);
 

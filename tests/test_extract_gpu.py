@@ -127,6 +127,20 @@ def test_batch_matches_single(api, ctx, oracle):
     ex.close()
 
 
+def test_host_batch_default_pass_size(api, ctx, oracle):
+    """Host-buffer batch call without configure(): the pass size follows the batch (32..128 frames), here 75 small
+    frames -> passes of 32, 32 and 11 through three staging slots."""
+    B, h, w = 75, 120, 160
+    imgs = synth.frames(B, h, w, seed0=900)
+    ex = api.ORBextractor(300, 1.2, 3, 20, 7, ctx=ctx)
+    kps, desc, counts = ex.extract_batch(imgs)
+    ref = oracle.Extractor(300, 1.2, 3, 20, 7)
+    for b in range(B):
+        k_ref, d_ref = ref(imgs[b])
+        assert_same_output(kps[b, :counts[b]], desc[b, :counts[b]], k_ref, d_ref)
+    ex.close()
+
+
 @pytest.mark.parametrize("cfg", ["hd", "uhd"])
 def test_large_frames(api, ctx, oracle, cfg):
     """BASELINE config 4: 1920x1080 and 3840x2160, 5000 features"""

@@ -80,6 +80,7 @@ struct viorb_extractor {
     std::vector<float> scale, invScale, sigma2, invSigma2;
     std::vector<int> quota;
     int chunk = 128, candDiv = 16;
+    bool chunkUser = false;      /* viorb_extractor_configure chose the pass size */
     /* geometry for the current image size */
     int rows = 0, cols = 0;
     FrameGeom geom;
@@ -536,7 +537,7 @@ int viorb_extractor_destroy(viorb_extractor* e) {
 
 int viorb_extractor_configure(viorb_extractor* e, int chunk_frames, int cand_div) {
     if (!e) return fail(VIORB_ERR_INVALID, "extractor is NULL");
-    if (chunk_frames > 0) e->chunk = chunk_frames;
+    if (chunk_frames > 0) { e->chunk = chunk_frames; e->chunkUser = true; }
     if (cand_div > 0 && cand_div != e->candDiv) { e->candDiv = cand_div; e->rows = e->cols = 0; }
     return VIORB_OK;
 }
@@ -662,7 +663,12 @@ static int extract_batch_once(viorb_extractor* e, const uint8_t* images, int B, 
     viorb_ctx* c = e->ctx;
     if ((rc = ctx_bind(c))) return rc;
     if ((rc = build_geometry(e, rows, cols))) return rc;
-    const int F = std::min(e->chunk, B);
+    /* frames per pass of the copy/compute pipeline: about a twelfth of the call, so that filling and draining the
+     * pipeline (first copy in, last pass, last copy out) stays small for short batches; 32..128 (measured:
+     * tools/small_batch_sweep.sh) */
+    int passFrames = e->chunk;
+    if (!e->chunkUser) passFrames = std::min(e->chunk, std::max(32, (B / 12 + 15) / 16 * 16));
+    const int F = std::min(passFrames, B);
     if ((rc = ensure_workspace(e, F))) return rc;
     const size_t inFrame = (size_t)rows * cols;        /* device copy is packed */
     const int nslots = B <= F ? 1 : std::min(e->nslots, (B + F - 1) / F);
