@@ -996,6 +996,24 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const __grid_consta
 __device__ __align__(16) const float d_pattern[1024] = VIORB_ORB_PATTERN_INIT;   /* as floats: x*b + y*a needs no I2F */
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
+/* shifts that give 0 for amounts >= 32 (PTX shl/shr clamp; C++ << is undefined there) */
+__device__ __forceinline__ unsigned shl_clamp(unsigned x, int n) {
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
+__device__ __forceinline__ unsigned shr_clamp(unsigned x, int n) {
+    unsigned r;
+    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
+/* four unsigned bytes x four signed bytes + c */
+__device__ __forceinline__ int dp4a_u8s8(unsigned a, int b, int c) {
+    int r;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 /* cv::fastAtan2 (degrees), OpenCV core mathfuncs_core atan_f32 polynomial, no FMA */
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     const float scale = (float)(180.0 / 3.14159265358979323846);
@@ -1137,24 +1155,24 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
     if (lane < 31) {
         const int v = lane - 15;
         const int d = c_umax[v < 0 ? -v : v];
-        const uint8_t* row = reinterpret_cast<const uint8_t*>(P) + (PR + v) * (PWORDS * 4) + PR;
-        int sacc = 0;
-        /* fixed trip count (the row's half-width d only masks): the byte loads of a batch are independent and in flight
-         * together instead of one load-use round trip per pixel */
-#pragma unroll 16
-        for (int u = -15; u <= 15; u++) {
-            const int raw = row[u];
-            const int val = (u >= -d && u <= d) ? raw : 0;
-            m10 += u * val;
-            sacc += val;
-        }
-        m01 = v * sacc;
-    }
+        /* the row as nine aligned words (bytes 4..39 of the patch row: u = -17..18); bytes outside the row's
+         * half-width d are masked off, then one IDP.4A per word and moment (weights u as signed bytes) */
+        const unsigned* rw = P + (PR + v) * PWORDS;
+        unsigned sacc = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        for (int w = 1; w <= 9; w++) {
+            const int u0 = 4 * w - PR;
+            unsigned x = rw[w];
+            if (u0 + 3 < 0) x &= shl_clamp(0xffffffffu, 8 * max(-d - u0, 0));
+            else if (u0 > 0) x &= shr_clamp(0xffffffffu, 8 * max(u0 + 3 - d, 0));
+            const int wts = (u0 & 0xff) | (((u0 + 1) & 0xff) << 8) | (((u0 + 2) & 0xff) << 16) | (((u0 + 3) & 0xff) << 24);
+            m10 = dp4a_u8s8(x, wts, m10);
+            sacc = __dp4a(x, 0x01010101u, sacc);
+        }
+        m01 = v * (int)sacc;
     }
+    m10 = __reduce_add_sync(0xffffffffu, m10);          /* REDUX.SUM: one instruction per moment instead of five shuffles */
+    m01 = __reduce_add_sync(0xffffffffu, m01);
     const float angle = fast_atan2_deg((float)m01, (float)m10);
     /* horizontal 7-tap pass: a task = 2 rows x 4 columns, two IDP.4A per output.  The 16-bit sums (exact:
      * the taps sum to 256) of vertically adjacent rows are packed into one word and stored transposed
