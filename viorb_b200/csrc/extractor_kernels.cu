@@ -985,6 +985,7 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const __grid_consta
  * and sampled at the 512 steered pattern points.  The blurred level image never exists in HBM.
  * ---------------------------------------------------------------------------------------------- */
 #define DESC_WARPS 4
+#define DESC_KPW 4            /* keypoints per warp in batch launches */
 #define PR 21                 /* patch radius */
 #define PROWS 43              /* patch rows / columns */
 #define PWORDS 13             /* patch row stride in 32-bit words (odd: conflict-free row pairs; 12 words used) */
@@ -1091,64 +1092,67 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
                                                                           viorb_keypoint* __restrict__ kps,
                                                                           uint8_t* __restrict__ desc, int cap,
                                                                           int32_t* __restrict__ counts,
-                                                                          int* __restrict__ status) {
+                                                                          int* __restrict__ status, int kpw) {
     /* per warp: patch (43 x 12 words; later reused for the blurred 37x37 bytes) + transposed H-pass buffer */
     __shared__ __align__(16) unsigned patchW[DESC_WARPS][PROWS * PWORDS];
     __shared__ __align__(16) unsigned hbW[DESC_WARPS][BW * HT_WORDS];
     const int frame = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * DESC_WARPS + warp;
-    /* locate (level, index) of this slot in the concatenated per-level lists (:1076-1103) */
-    int level = -1, idx = 0, total = 0;
+    /* lane l holds [lo, hi) of level l in the concatenated per-level lists (:1076-1103) */
+    int myLo, myHi, total;
     {
-        int acc = 0;
-        for (int l = 0; l < g.nlevels; l++) {
-            const int c = selCount[frame * g.nlevels + l];
-            if (level < 0 && slot < acc + c) { level = l; idx = slot - acc; }
-            acc += c;
+        const int c = lane < g.nlevels ? selCount[frame * g.nlevels + lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        total = acc;
+        myHi = incl;
+        myLo = incl - c;
+        total = __shfl_sync(0xffffffffu, incl, 31);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         counts[frame] = min(total, cap);
         if (total > cap) atomicOr(status, VIORB_DEV_OUT_OVERFLOW);
     }
-    if (level < 0 || slot >= cap) return;
+    /* this lane's 8 binary tests (16 sampling points, 32 floats), kept in registers for all keypoints of the warp:
+     * read per keypoint they were 4 KB through L1 -- twice the patch */
+    float4 pat[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) pat[k] = __ldg(reinterpret_cast<const float4*>(d_pattern) + 8 * lane + k);
+    unsigned* P = patchW[warp];
+    unsigned* Hw = hbW[warp];
+    for (int it = 0; it < kpw; it++) {
+    const int slot = (it * gridDim.x + blockIdx.x) * DESC_WARPS + warp;
+    if (slot >= total || slot >= cap) break;
+    const int level = __ffs(__ballot_sync(0xffffffffu, slot >= myLo && slot < myHi)) - 1;
+    const int idx = slot - __shfl_sync(0xffffffffu, myLo, level);
     const LevelGeom& L = g.lv[level];
     const uint32_t key = sel[(size_t)frame * g.selPerFrame + L.selBase + idx];
     const int kx = key & 0xfff, ky = (key >> 12) & 0xfff, score = key >> 24;
     const uint8_t* roi = pyr + (size_t)frame * g.pyrFrameBytes + L.pyrOff + (size_t)VIORB_EDGE * L.step + VIORB_ROI_X0;
-    unsigned* P = patchW[warp];
-    unsigned* Hw = hbW[warp];
-    /* stage the 43x43 neighbourhood as aligned words: patch byte (r, c) = level pixel (kx-21+c, ky-21+r).
-     * Half a warp loads one row (13 aligned words), the funnel shift takes the next word from the next lane;
-     * all 22 loads of a lane are issued before the first use. */
+    /* stage the 43x43 neighbourhood with cp.async (global -> shared without a register round trip): patch row r =
+     * the 13 aligned words that hold level pixels (kx-21 .. kx+21, ky-21+r), i.e. patch byte (r, c) sits at byte
+     * sh + c of the row, sh = (kx-21) & 3.  Half a warp copies one row; the consumers below realign by sh. */
+    const int sh = (kx - PR) & 3;
     {
         const int gx0 = kx - PR;
-        const int sh = gx0 & 3;
         const int w = lane & 15, rsub = lane >> 4;
-        /* word pointer of (row rsub, word w); rows advance by two per step (64-bit add only) */
         const unsigned* p = reinterpret_cast<const unsigned*>(roi + (ptrdiff_t)(ky - PR + rsub) * L.step + (gx0 - sh)) + w;
         const ptrdiff_t twoRows = (ptrdiff_t)(L.step >> 1);           /* 2 * step bytes in words */
+        unsigned dst = (unsigned)__cvta_generic_to_shared(P + rsub * PWORDS + w);
         const bool okW = w < 13;
-        unsigned g[22];
 #pragma unroll
         for (int k = 0; k < 22; k++) {
-            const bool ok = okW && (k < 21 || rsub == 0);               /* row 2k + rsub < 43 */
-            g[k] = ok ? __ldg(p) : 0u;
+            if (okW && (k < 21 || rsub == 0))                           /* row 2k + rsub < 43 */
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(p) : "memory");
             p += twoRows;
+            dst += 2 * PWORDS * 4;
         }
-        unsigned* dst = P + rsub * PWORDS + w;
-#pragma unroll
-        for (int k = 0; k < 22; k++) {
-            const unsigned hi = __shfl_down_sync(0xffffffffu, g[k], 1);
-            if (w < 12 && (k < 21 || rsub == 0)) dst[k * 2 * PWORDS] = funnel_bytes(g[k], hi, sh);
-        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    /* this lane's 8 binary tests (16 sampling points, 32 floats) */
-    float4 pat[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) pat[k] = __ldg(reinterpret_cast<const float4*>(d_pattern) + 8 * lane + k);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     /* IC_Angle: lane v+15 sums row v of the circular patch */
     int m10 = 0, m01 = 0;
@@ -1159,10 +1163,13 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
          * half-width d are masked off, then one IDP.4A per word and moment (weights u as signed bytes) */
         const unsigned* rw = P + (PR + v) * PWORDS;
         unsigned sacc = 0;
+        unsigned nxt = rw[1];
 #pragma unroll
         for (int w = 1; w <= 9; w++) {
             const int u0 = 4 * w - PR;
-            unsigned x = rw[w];
+            const unsigned cur = nxt;
+            nxt = rw[w + 1];
+            unsigned x = funnel_bytes(cur, nxt, sh);
             if (u0 + 3 < 0) x &= shl_clamp(0xffffffffu, 8 * max(-d - u0, 0));
             else if (u0 > 0) x &= shr_clamp(0xffffffffu, 8 * max(u0 + 3 - d, 0));
             const int wts = (u0 & 0xff) | (((u0 + 1) & 0xff) << 8) | (((u0 + 2) & 0xff) << 16) | (((u0 + 3) & 0xff) << 24);
@@ -1183,7 +1190,10 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
             const int rp = t / 10, j = t - rp * 10;          /* row pair, column quad */
             const unsigned* p0 = &P[(2 * rp) * PWORDS + j];
             const unsigned* p1 = rp < 21 ? p0 + PWORDS : p0; /* row 43 does not exist: its sums are never used */
-            const unsigned a0 = p0[0], a1 = p0[1], a2 = p0[2], b0 = p1[0], b1 = p1[1], b2 = p1[2];
+            const unsigned ra3 = p0[3], rb3 = p1[3];
+            const unsigned ra2 = p0[2], rb2 = p1[2], ra1 = p0[1], rb1 = p1[1];
+            const unsigned a0 = funnel_bytes(p0[0], ra1, sh), a1 = funnel_bytes(ra1, ra2, sh), a2 = funnel_bytes(ra2, ra3, sh);
+            const unsigned b0 = funnel_bytes(p1[0], rb1, sh), b1 = funnel_bytes(rb1, rb2, sh), b2 = funnel_bytes(rb2, rb3, sh);
             unsigned h[4];
             h[0] = __byte_perm(__dp4a(a0, KLO, __dp4a(a1, KHI, 0u)), __dp4a(b0, KLO, __dp4a(b1, KHI, 0u)), 0x5410);
 #pragma unroll
@@ -1253,6 +1263,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
         kp.octave = level;
         kp.class_id = -1;
         kps[(size_t)frame * cap + slot] = kp;
+    }
+    __syncwarp();           /* the next keypoint's copies overwrite the blurred patch */
     }
 }
 
@@ -1413,9 +1425,12 @@ int viorb_launch_steering_sweep(unsigned firstBits, long long n, float* d_sin, f
 int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps, uint8_t* d_desc,
                           int cap, int32_t* d_counts, cudaStream_t s) {
     const int slots = g.selPerFrame < cap ? g.selPerFrame : cap;
-    dim3 grid((slots + DESC_WARPS - 1) / DESC_WARPS, F);
+    /* keypoints per warp: batches amortise the warp's pattern registers over four keypoints; a few frames keep one
+     * keypoint per warp (all SMs busy, shortest latency) */
+    const int kpw = F > 8 ? DESC_KPW : 1;
+    dim3 grid((slots + DESC_WARPS * kpw - 1) / (DESC_WARPS * kpw), F);
     if (grid.x == 0) grid.x = 1;
     orient_describe_kernel<<<grid, DESC_WARPS * 32, 0, s>>>(g, b.pyr, b.sel, b.selCount, d_kps, d_desc, cap, d_counts,
-                                                            b.status);
+                                                            b.status, kpw);
     return 1;
 }
