@@ -985,14 +985,14 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const __grid_consta
  * and sampled at the 512 steered pattern points.  The blurred level image never exists in HBM.
  * ---------------------------------------------------------------------------------------------- */
 #define DESC_WARPS 4
-#define DESC_KPW 4            /* keypoints per warp in batch launches */
+#define DESC_KPW 8            /* most keypoints per warp (batch launches) */
 #define PR 21                 /* patch radius */
 #define PROWS 43              /* patch rows / columns */
 #define PWORDS 13             /* patch row stride in 32-bit words (odd: conflict-free row pairs; 12 words used) */
 #define BW 37                 /* blurred width (radius 18) */
 #define HT_WORDS 25           /* words per column of the transposed horizontal-pass buffer (>= 23; = 1 mod 8 so the
                                  transposed stores of 4-column quads fall into distinct banks) */
-#define VT_STRIDE 40          /* bytes per column of the transposed blurred patch (37 rows + pad) */
+#define VT_STRIDE 44          /* bytes per column of the transposed blurred patch (37 rows + pad; 11 words: odd) */
 
 __device__ __align__(16) const float d_pattern[1024] = VIORB_ORB_PATTERN_INIT;   /* as floats: x*b + y*a needs no I2F */
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
@@ -1183,44 +1183,68 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
     const float angle = fast_atan2_deg((float)m01, (float)m10);
     /* horizontal 7-tap pass: a task = 2 rows x 4 columns, two IDP.4A per output.  The 16-bit sums (exact:
      * the taps sum to 256) of vertically adjacent rows are packed into one word and stored transposed
-     * (Hw[c][r/2]) so the vertical pass can use IDP.2A on row pairs. */
+     * (Hw[c][pos(rp)]) so the vertical pass can use IDP.2A on row pairs.
+     * Shared-memory banks (the L1 data pipe is this kernel's busiest unit): an instruction covers columns 0..31
+     * (8 quads) of four row pairs whose patch rows start 8 banks apart -- {b, b+4, b+8, b+12}, and {16, 20, 18},
+     * {17, 21, 19} for the rest (row pair rp starts at bank 26*rp mod 32) -- so the 32 loaded words fall into 32
+     * banks; row pair rp is stored at pos(rp) = 6*(rp&3) + (rp>>2), which makes the four row pairs of an
+     * instruction neighbours in Hw and the transposed stores conflict-free as well.  Columns 32..36 are a seventh
+     * instruction with one row pair per lane. */
     {
         const unsigned KLO = 18u | (34u << 8) | (48u << 16) | (56u << 24), KHI = 48u | (34u << 8) | (18u << 16);
-        for (int t = lane; t < 22 * 10; t += 32) {
-            const int rp = t / 10, j = t - rp * 10;          /* row pair, column quad */
+        const int q = lane >> 3, j = lane & 7;
+#pragma unroll 1
+        for (int it = 0; it < 6; it++) {
+            int rp;
+            if (it < 4) rp = it + 4 * q;
+            else rp = (q == 3) ? -1 : 12 + it + (q == 1 ? 4 : (q == 2 ? 2 : 0));
+            if (rp < 0) continue;
             const unsigned* p0 = &P[(2 * rp) * PWORDS + j];
             const unsigned* p1 = rp < 21 ? p0 + PWORDS : p0; /* row 43 does not exist: its sums are never used */
             const unsigned ra3 = p0[3], rb3 = p1[3];
             const unsigned ra2 = p0[2], rb2 = p1[2], ra1 = p0[1], rb1 = p1[1];
             const unsigned a0 = funnel_bytes(p0[0], ra1, sh), a1 = funnel_bytes(ra1, ra2, sh), a2 = funnel_bytes(ra2, ra3, sh);
             const unsigned b0 = funnel_bytes(p1[0], rb1, sh), b1 = funnel_bytes(rb1, rb2, sh), b2 = funnel_bytes(rb2, rb3, sh);
-            unsigned h[4];
-            h[0] = __byte_perm(__dp4a(a0, KLO, __dp4a(a1, KHI, 0u)), __dp4a(b0, KLO, __dp4a(b1, KHI, 0u)), 0x5410);
+            unsigned* dst = &Hw[(4 * j) * HT_WORDS + 6 * (rp & 3) + (rp >> 2)];
+            dst[0] = __byte_perm(__dp4a(a0, KLO, __dp4a(a1, KHI, 0u)), __dp4a(b0, KLO, __dp4a(b1, KHI, 0u)), 0x5410);
 #pragma unroll
             for (int i = 1; i < 4; i++)
-                h[i] = __byte_perm(__dp4a(funnel_bytes(a0, a1, i), KLO, __dp4a(funnel_bytes(a1, a2, i), KHI, 0u)),
-                                   __dp4a(funnel_bytes(b0, b1, i), KLO, __dp4a(funnel_bytes(b1, b2, i), KHI, 0u)), 0x5410);
-            const int c = 4 * j;
-            Hw[c * HT_WORDS + rp] = h[0];
-            if (c + 1 < BW) Hw[(c + 1) * HT_WORDS + rp] = h[1];
-            if (c + 2 < BW) Hw[(c + 2) * HT_WORDS + rp] = h[2];
-            if (c + 3 < BW) Hw[(c + 3) * HT_WORDS + rp] = h[3];
+                dst[i * HT_WORDS] = __byte_perm(__dp4a(funnel_bytes(a0, a1, i), KLO, __dp4a(funnel_bytes(a1, a2, i), KHI, 0u)),
+                                                __dp4a(funnel_bytes(b0, b1, i), KLO, __dp4a(funnel_bytes(b1, b2, i), KHI, 0u)), 0x5410);
+        }
+        if (lane < 22) {                                       /* columns 32..36 of row pair `lane` */
+            const int rp = lane;
+            const unsigned* p0 = &P[(2 * rp) * PWORDS + 8];
+            const unsigned* p1 = rp < 21 ? p0 + PWORDS : p0;
+            const unsigned ra3 = p0[3], rb3 = p1[3];
+            const unsigned ra2 = p0[2], rb2 = p1[2], ra1 = p0[1], rb1 = p1[1];
+            const unsigned a0 = funnel_bytes(p0[0], ra1, sh), a1 = funnel_bytes(ra1, ra2, sh), a2 = funnel_bytes(ra2, ra3, sh);
+            const unsigned b0 = funnel_bytes(p1[0], rb1, sh), b1 = funnel_bytes(rb1, rb2, sh), b2 = funnel_bytes(rb2, rb3, sh);
+            unsigned* dst = &Hw[32 * HT_WORDS + 6 * (rp & 3) + (rp >> 2)];
+            dst[0] = __byte_perm(__dp4a(a0, KLO, __dp4a(a1, KHI, 0u)), __dp4a(b0, KLO, __dp4a(b1, KHI, 0u)), 0x5410);
+#pragma unroll
+            for (int i = 1; i < 4; i++)
+                dst[i * HT_WORDS] = __byte_perm(__dp4a(funnel_bytes(a0, a1, i), KLO, __dp4a(funnel_bytes(a1, a2, i), KHI, 0u)),
+                                                __dp4a(funnel_bytes(b0, b1, i), KLO, __dp4a(funnel_bytes(b1, b2, i), KHI, 0u)), 0x5410);
+            dst[4 * HT_WORDS] = __byte_perm(__dp4a(a1, KLO, __dp4a(a2, KHI, 0u)), __dp4a(b1, KLO, __dp4a(b2, KHI, 0u)), 0x5410);
         }
     }
     __syncwarp();
-    /* vertical pass: a task = 8 output rows of one column, read as 7 words (row pairs); even and
-     * odd rows use the tap pairs shifted by one.  out = (sum + 32768) >> 16 (GaussianBlur's rounding); the
-     * blurred patch is stored transposed as well (Vt[c][r]) so a task writes two words. */
+    /* vertical pass: a task = 8 output rows (segment seg) of one column, read as 7 words (row pairs 4*seg + k at
+     * pos = seg + {0, 6, 12, 18, 1, 7, 13}); even and odd rows use the tap pairs shifted by one.
+     * out = (sum + 32768) >> 16 (GaussianBlur's rounding); the blurred patch is stored transposed as well
+     * (Vt[c][r], 11-word column stride) so a task writes two words.  Tasks are ordered segment-major: the lanes
+     * of an instruction hold neighbouring columns, whose words are 25 (loads) and 11 (stores) banks apart. */
     uint8_t* Vt = reinterpret_cast<uint8_t*>(P);       /* the patch is dead now */
     {
         const unsigned E01 = 18u | (34u << 8), E23 = 48u | (56u << 8), E45 = 48u | (34u << 8), E6 = 18u;   /* even row */
         const unsigned O0 = 18u << 8, O12 = 34u | (48u << 8), O34 = 56u | (48u << 8), O56 = 34u | (18u << 8);  /* odd row */
         for (int t = lane; t < BW * 5; t += 32) {
-            const int c = t / 5, seg = t - c * 5;            /* rows 8*seg .. 8*seg+7 */
-            const unsigned* hcol = &Hw[c * HT_WORDS + 4 * seg];
+            const int seg = t / BW, c = t - seg * BW;        /* rows 8*seg .. 8*seg+7 */
+            const unsigned* hcol = &Hw[c * HT_WORDS + seg];
             unsigned w[7];
 #pragma unroll
-            for (int k = 0; k < 7; k++) w[k] = hcol[k];
+            for (int k = 0; k < 7; k++) w[k] = hcol[6 * (k & 3) + (k >> 2)];
             unsigned out[8];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -1425,9 +1449,10 @@ int viorb_launch_steering_sweep(unsigned firstBits, long long n, float* d_sin, f
 int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps, uint8_t* d_desc,
                           int cap, int32_t* d_counts, cudaStream_t s) {
     const int slots = g.selPerFrame < cap ? g.selPerFrame : cap;
-    /* keypoints per warp: batches amortise the warp's pattern registers over four keypoints; a few frames keep one
-     * keypoint per warp (all SMs busy, shortest latency) */
-    const int kpw = F > 8 ? DESC_KPW : 1;
+    /* keypoints per warp: batches amortise the warp's pattern registers over up to DESC_KPW keypoints, as long as the
+     * grid still holds two waves of CTAs (148 SMs x 7); a few frames keep one keypoint per warp (shortest latency) */
+    int kpw = (int)(((long long)F * slots) / (DESC_WARPS * 148 * 14));
+    kpw = kpw < 1 ? 1 : (kpw > DESC_KPW ? DESC_KPW : kpw);
     dim3 grid((slots + DESC_WARPS * kpw - 1) / (DESC_WARPS * kpw), F);
     if (grid.x == 0) grid.x = 1;
     orient_describe_kernel<<<grid, DESC_WARPS * 32, 0, s>>>(g, b.pyr, b.sel, b.selCount, d_kps, d_desc, cap, d_counts,
