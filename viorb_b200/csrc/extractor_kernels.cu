@@ -1039,6 +1039,65 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
+/* Horizontal blur pass of orient_describe_kernel for a patch whose rows sit SH bytes into their first word.
+ * The 7-tap window of output column 4j+i starts at byte i+SH of raw word j: instead of shifting the pixels into place
+ * the tap words are shifted (compile-time constants per SH), two or three IDP.4A per output and no PRMT. */
+__host__ __device__ constexpr unsigned blur_tap_word(int o, int w) {
+    const int k[7] = {18, 34, 48, 56, 48, 34, 18};
+    unsigned r = 0;
+    for (int b = 0; b < 4; b++) {
+        const int p = 4 * w + b - o;
+        if (p >= 0 && p < 7) r |= (unsigned)k[p] << (8 * b);
+    }
+    return r;
+}
+template <int O>
+__device__ __forceinline__ unsigned blur_hsum(unsigned r0, unsigned r1, unsigned r2, unsigned r3) {
+    unsigned acc = 0;
+    if constexpr (blur_tap_word(O, 3) != 0) acc = __dp4a(r3, blur_tap_word(O, 3), acc);
+    if constexpr (blur_tap_word(O, 2) != 0) acc = __dp4a(r2, blur_tap_word(O, 2), acc);
+    if constexpr (blur_tap_word(O, 1) != 0) acc = __dp4a(r1, blur_tap_word(O, 1), acc);
+    if constexpr (blur_tap_word(O, 0) != 0) acc = __dp4a(r0, blur_tap_word(O, 0), acc);
+    return acc;
+}
+/* Shared-memory banks (the L1 data pipe is this kernel's busiest unit): an instruction covers columns 0..31
+ * (8 quads) of four row pairs whose patch rows start 8 banks apart -- {b, b+4, b+8, b+12}, and {16, 20, 18},
+ * {17, 21, 19} for the rest (row pair rp starts at bank 26*rp mod 32) -- so the 32 loaded words fall into 32
+ * banks; row pair rp is stored at pos(rp) = 6*(rp&3) + (rp>>2), which makes the four row pairs of an
+ * instruction neighbours in Hw and the transposed stores conflict-free as well.  Columns 32..36 are a seventh
+ * instruction with one row pair per lane. */
+template <int SH>
+__device__ __forceinline__ void blur_h_pass(const unsigned* __restrict__ P, unsigned* __restrict__ Hw, int lane) {
+    const int q = lane >> 3, j = lane & 7;
+#pragma unroll 1
+    for (int it = 0; it < 6; it++) {
+        int rp;
+        if (it < 4) rp = it + 4 * q;
+        else rp = (q == 3) ? -1 : 12 + it + (q == 1 ? 4 : (q == 2 ? 2 : 0));
+        if (rp < 0) continue;
+        const unsigned* p0 = &P[(2 * rp) * PWORDS + j];
+        const unsigned* p1 = rp < 21 ? p0 + PWORDS : p0;     /* row 43 does not exist: its sums are never used */
+        const unsigned a0 = p0[0], a1 = p0[1], a2 = p0[2], a3 = p0[3], b0 = p1[0], b1 = p1[1], b2 = p1[2], b3 = p1[3];
+        unsigned* dst = &Hw[(4 * j) * HT_WORDS + 6 * (rp & 3) + (rp >> 2)];
+        dst[0 * HT_WORDS] = __byte_perm(blur_hsum<SH + 0>(a0, a1, a2, a3), blur_hsum<SH + 0>(b0, b1, b2, b3), 0x5410);
+        dst[1 * HT_WORDS] = __byte_perm(blur_hsum<SH + 1>(a0, a1, a2, a3), blur_hsum<SH + 1>(b0, b1, b2, b3), 0x5410);
+        dst[2 * HT_WORDS] = __byte_perm(blur_hsum<SH + 2>(a0, a1, a2, a3), blur_hsum<SH + 2>(b0, b1, b2, b3), 0x5410);
+        dst[3 * HT_WORDS] = __byte_perm(blur_hsum<SH + 3>(a0, a1, a2, a3), blur_hsum<SH + 3>(b0, b1, b2, b3), 0x5410);
+    }
+    if (lane < 22) {                                           /* columns 32..36 of row pair `lane` */
+        const int rp = lane;
+        const unsigned* p0 = &P[(2 * rp) * PWORDS + 8];
+        const unsigned* p1 = rp < 21 ? p0 + PWORDS : p0;
+        const unsigned a0 = p0[0], a1 = p0[1], a2 = p0[2], a3 = p0[3], b0 = p1[0], b1 = p1[1], b2 = p1[2], b3 = p1[3];
+        unsigned* dst = &Hw[32 * HT_WORDS + 6 * (rp & 3) + (rp >> 2)];
+        dst[0 * HT_WORDS] = __byte_perm(blur_hsum<SH + 0>(a0, a1, a2, a3), blur_hsum<SH + 0>(b0, b1, b2, b3), 0x5410);
+        dst[1 * HT_WORDS] = __byte_perm(blur_hsum<SH + 1>(a0, a1, a2, a3), blur_hsum<SH + 1>(b0, b1, b2, b3), 0x5410);
+        dst[2 * HT_WORDS] = __byte_perm(blur_hsum<SH + 2>(a0, a1, a2, a3), blur_hsum<SH + 2>(b0, b1, b2, b3), 0x5410);
+        dst[3 * HT_WORDS] = __byte_perm(blur_hsum<SH + 3>(a0, a1, a2, a3), blur_hsum<SH + 3>(b0, b1, b2, b3), 0x5410);
+        dst[4 * HT_WORDS] = __byte_perm(blur_hsum<SH + 4>(a0, a1, a2, a3), blur_hsum<SH + 4>(b0, b1, b2, b3), 0x5410);
+    }
+}
+
 /* glibc flt-32 sincosf (double polynomial, generic reduction), every op rounded separately.
  * Valid for |y| < 120; the extractor feeds angles in [0, 2*pi].   */
 __device__ __forceinline__ void sincosf_glibc(float y, float* sinp, float* cosp) {
@@ -1181,53 +1240,14 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
     m10 = __reduce_add_sync(0xffffffffu, m10);          /* REDUX.SUM: one instruction per moment instead of five shuffles */
     m01 = __reduce_add_sync(0xffffffffu, m01);
     const float angle = fast_atan2_deg((float)m01, (float)m10);
-    /* horizontal 7-tap pass: a task = 2 rows x 4 columns, two IDP.4A per output.  The 16-bit sums (exact:
-     * the taps sum to 256) of vertically adjacent rows are packed into one word and stored transposed
-     * (Hw[c][pos(rp)]) so the vertical pass can use IDP.2A on row pairs.
-     * Shared-memory banks (the L1 data pipe is this kernel's busiest unit): an instruction covers columns 0..31
-     * (8 quads) of four row pairs whose patch rows start 8 banks apart -- {b, b+4, b+8, b+12}, and {16, 20, 18},
-     * {17, 21, 19} for the rest (row pair rp starts at bank 26*rp mod 32) -- so the 32 loaded words fall into 32
-     * banks; row pair rp is stored at pos(rp) = 6*(rp&3) + (rp>>2), which makes the four row pairs of an
-     * instruction neighbours in Hw and the transposed stores conflict-free as well.  Columns 32..36 are a seventh
-     * instruction with one row pair per lane. */
-    {
-        const unsigned KLO = 18u | (34u << 8) | (48u << 16) | (56u << 24), KHI = 48u | (34u << 8) | (18u << 16);
-        const int q = lane >> 3, j = lane & 7;
-#pragma unroll 1
-        for (int it = 0; it < 6; it++) {
-            int rp;
-            if (it < 4) rp = it + 4 * q;
-            else rp = (q == 3) ? -1 : 12 + it + (q == 1 ? 4 : (q == 2 ? 2 : 0));
-            if (rp < 0) continue;
-            const unsigned* p0 = &P[(2 * rp) * PWORDS + j];
-            const unsigned* p1 = rp < 21 ? p0 + PWORDS : p0; /* row 43 does not exist: its sums are never used */
-            const unsigned ra3 = p0[3], rb3 = p1[3];
-            const unsigned ra2 = p0[2], rb2 = p1[2], ra1 = p0[1], rb1 = p1[1];
-            const unsigned a0 = funnel_bytes(p0[0], ra1, sh), a1 = funnel_bytes(ra1, ra2, sh), a2 = funnel_bytes(ra2, ra3, sh);
-            const unsigned b0 = funnel_bytes(p1[0], rb1, sh), b1 = funnel_bytes(rb1, rb2, sh), b2 = funnel_bytes(rb2, rb3, sh);
-            unsigned* dst = &Hw[(4 * j) * HT_WORDS + 6 * (rp & 3) + (rp >> 2)];
-            dst[0] = __byte_perm(__dp4a(a0, KLO, __dp4a(a1, KHI, 0u)), __dp4a(b0, KLO, __dp4a(b1, KHI, 0u)), 0x5410);
-#pragma unroll
-            for (int i = 1; i < 4; i++)
-                dst[i * HT_WORDS] = __byte_perm(__dp4a(funnel_bytes(a0, a1, i), KLO, __dp4a(funnel_bytes(a1, a2, i), KHI, 0u)),
-                                                __dp4a(funnel_bytes(b0, b1, i), KLO, __dp4a(funnel_bytes(b1, b2, i), KHI, 0u)), 0x5410);
-        }
-        if (lane < 22) {                                       /* columns 32..36 of row pair `lane` */
-            const int rp = lane;
-            const unsigned* p0 = &P[(2 * rp) * PWORDS + 8];
-            const unsigned* p1 = rp < 21 ? p0 + PWORDS : p0;
-            const unsigned ra3 = p0[3], rb3 = p1[3];
-            const unsigned ra2 = p0[2], rb2 = p1[2], ra1 = p0[1], rb1 = p1[1];
-            const unsigned a0 = funnel_bytes(p0[0], ra1, sh), a1 = funnel_bytes(ra1, ra2, sh), a2 = funnel_bytes(ra2, ra3, sh);
-            const unsigned b0 = funnel_bytes(p1[0], rb1, sh), b1 = funnel_bytes(rb1, rb2, sh), b2 = funnel_bytes(rb2, rb3, sh);
-            unsigned* dst = &Hw[32 * HT_WORDS + 6 * (rp & 3) + (rp >> 2)];
-            dst[0] = __byte_perm(__dp4a(a0, KLO, __dp4a(a1, KHI, 0u)), __dp4a(b0, KLO, __dp4a(b1, KHI, 0u)), 0x5410);
-#pragma unroll
-            for (int i = 1; i < 4; i++)
-                dst[i * HT_WORDS] = __byte_perm(__dp4a(funnel_bytes(a0, a1, i), KLO, __dp4a(funnel_bytes(a1, a2, i), KHI, 0u)),
-                                                __dp4a(funnel_bytes(b0, b1, i), KLO, __dp4a(funnel_bytes(b1, b2, i), KHI, 0u)), 0x5410);
-            dst[4 * HT_WORDS] = __byte_perm(__dp4a(a1, KLO, __dp4a(a2, KHI, 0u)), __dp4a(b1, KLO, __dp4a(b2, KHI, 0u)), 0x5410);
-        }
+    /* horizontal 7-tap pass: a task = 2 rows x 4 columns.  The 16-bit sums (exact: the taps sum to 256) of
+     * vertically adjacent rows are packed into one word and stored transposed (Hw[c][pos(rp)]) so the vertical
+     * pass can use IDP.2A on row pairs.  One instantiation per byte offset of the patch rows (warp-uniform). */
+    switch (sh) {
+        case 0: blur_h_pass<0>(P, Hw, lane); break;
+        case 1: blur_h_pass<1>(P, Hw, lane); break;
+        case 2: blur_h_pass<2>(P, Hw, lane); break;
+        default: blur_h_pass<3>(P, Hw, lane); break;
     }
     __syncwarp();
     /* vertical pass: a task = 8 output rows (segment seg) of one column, read as 7 words (row pairs 4*seg + k at
