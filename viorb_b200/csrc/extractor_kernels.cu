@@ -1265,17 +1265,16 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const 
             unsigned w[7];
 #pragma unroll
             for (int k = 0; k < 7; k++) w[k] = hcol[6 * (k & 3) + (k >> 2)];
-            unsigned out[8];
+            unsigned pr[4];          /* rows 2k, 2k+1: the sums are < 2^24, so (sum >> 16) is byte 2 -- picked by PRMT */
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const unsigned ve = __dp2a_lo(w[k], E01, __dp2a_lo(w[k + 1], E23, __dp2a_lo(w[k + 2], E45, __dp2a_lo(w[k + 3], E6, 32768u))));
                 const unsigned vo = __dp2a_lo(w[k], O0, __dp2a_lo(w[k + 1], O12, __dp2a_lo(w[k + 2], O34, __dp2a_lo(w[k + 3], O56, 32768u))));
-                out[2 * k] = ve >> 16;
-                out[2 * k + 1] = vo >> 16;
+                pr[k] = __byte_perm(ve, vo, 0x0062);
             }
             unsigned* dst = reinterpret_cast<unsigned*>(Vt + c * VT_STRIDE + 8 * seg);
-            dst[0] = out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24);
-            dst[1] = out[4] | (out[5] << 8) | (out[6] << 16) | (out[7] << 24);
+            dst[0] = __byte_perm(pr[0], pr[1], 0x5410);
+            dst[1] = __byte_perm(pr[2], pr[3], 0x5410);
         }
     }
     __syncwarp();
