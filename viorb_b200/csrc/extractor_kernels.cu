@@ -1144,7 +1144,7 @@ __device__ __forceinline__ void sincosf_glibc(float y, float* sinp, float* cosp)
     else { *sinp = sv; *cosp = cv; }
 }
 
-__global__ void __launch_bounds__(DESC_WARPS * 32) orient_describe_kernel(const __grid_constant__ FrameGeom g,
+__global__ void __launch_bounds__(DESC_WARPS * 32, 6) orient_describe_kernel(const __grid_constant__ FrameGeom g,
                                                                           const uint8_t* __restrict__ pyr,
                                                                           const uint32_t* __restrict__ sel,
                                                                           const int* __restrict__ selCount,
