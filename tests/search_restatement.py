@@ -1,0 +1,202 @@
+"""Second, independent numpy/float32 restatement of the windowed searches of the hot path, statement by statement
+from the reference (line numbers inline).  Test infrastructure: it pins oracle/match_oracle.cpp the way
+tests/cv2_restatement.py pins the extractor oracle.
+
+  Grid                       Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea   src/Frame.cc:410-425,507-572
+  search_by_projection_local ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) src/ORBmatcher.cc:45-137
+  search_by_projection_frame ORBmatcher::SearchByProjection(Cur, Last, th, bMono)          src/ORBmatcher.cc:1378-1468
+  compute_three_maxima       ORBmatcher::ComputeThreeMaxima                                 src/ORBmatcher.cc:1602-1643
+
+The map-point graph is flattened the way the oracle's interface does it: obs[i] > 0 stands for
+"F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0", nobs[k] is Observations() of map point k.
+"""
+import math
+
+import numpy as np
+
+F = np.float32
+GRID_COLS, GRID_ROWS = 64, 48                 # include/Frame.h:41-42
+TH_HIGH, HISTO_LENGTH = 100, 30               # src/ORBmatcher.cc:37-39
+
+
+def _roundf(x):
+    x = float(x)
+    return int(math.floor(x + 0.5) if x >= 0 else math.ceil(x - 0.5))
+
+
+def _hamming(a, b):
+    return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+class Grid:
+    def __init__(self, kps_un, min_x, max_x, min_y, max_y):
+        self.kps = kps_un
+        self.min_x, self.max_x, self.min_y, self.max_y = F(min_x), F(max_x), F(min_y), F(max_y)
+        self.inv_w = F(F(GRID_COLS) / F(self.max_x - self.min_x))        # Frame.cc (ctor): mfGridElementWidthInv
+        self.inv_h = F(F(GRID_ROWS) / F(self.max_y - self.min_y))
+        self.cells = [[[] for _ in range(GRID_ROWS)] for _ in range(GRID_COLS)]
+        for i in range(len(kps_un)):                                     # :417-424
+            px = _roundf(F(F(kps_un["x"][i] - self.min_x) * self.inv_w))  # :564-565
+            py = _roundf(F(F(kps_un["y"][i] - self.min_y) * self.inv_h))
+            if px < 0 or px >= GRID_COLS or py < 0 or py >= GRID_ROWS:   # :568
+                continue
+            self.cells[px][py].append(i)
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        x, y, r = F(x), F(y), F(r)
+        out = []
+        c0 = max(0, int(math.floor(F(F(F(x - self.min_x) - r) * self.inv_w))))       # :512
+        if c0 >= GRID_COLS:
+            return out
+        c1 = min(GRID_COLS - 1, int(math.ceil(F(F(F(x - self.min_x) + r) * self.inv_w))))
+        if c1 < 0:
+            return out
+        r0 = max(0, int(math.floor(F(F(F(y - self.min_y) - r) * self.inv_h))))
+        if r0 >= GRID_ROWS:
+            return out
+        r1 = min(GRID_ROWS - 1, int(math.ceil(F(F(F(y - self.min_y) + r) * self.inv_h))))
+        if r1 < 0:
+            return out
+        check = (min_level > 0) or (max_level >= 0)                                   # :528
+        for ix in range(c0, c1 + 1):
+            for iy in range(r0, r1 + 1):
+                for j in self.cells[ix][iy]:
+                    o = int(self.kps["octave"][j])
+                    if check:
+                        if o < min_level:
+                            continue
+                        if max_level >= 0 and o > max_level:
+                            continue
+                    dx = F(self.kps["x"][j] - x)
+                    dy = F(self.kps["y"][j] - y)
+                    if abs(dx) < r and abs(dy) < r:                                   # :552
+                        out.append(j)
+        return out
+
+
+def search_by_projection_local(grid, fdesc, u_right, obs0, scale_factors, proj_x, proj_y, proj_xr, pred_level,
+                               view_cos, valid, nobs, mp_desc, th, nnratio):
+    kps = grid.kps
+    sf = np.asarray(scale_factors, np.float32)
+    obs = np.array(obs0, np.int32)
+    match = np.full(len(kps), -1, np.int32)
+    th, nnratio = F(th), F(nnratio)
+    factor = float(th) != 1.0                                            # :49
+    n = 0
+    for k in range(len(mp_desc)):
+        if not valid[k]:                                                 # :54-58
+            continue
+        level = int(pred_level[k])
+        r = F(2.5) if float(view_cos[k]) > 0.998 else F(4.0)             # :131-137 (double literal vs float)
+        if factor:
+            r = F(r * th)
+        rs = F(r * sf[level])
+        idx = grid.features_in_area(proj_x[k], proj_y[k], rs, level - 1, level)       # :68-69
+        if not idx:
+            continue
+        best, best_lvl, best2, best_lvl2, best_i = 256, -1, 256, -1, -1
+        for i in idx:
+            if obs[i] > 0:                                               # :87-89
+                continue
+            if u_right[i] > 0:                                           # :91-96
+                er = abs(F(F(proj_xr[k]) - F(u_right[i])))
+                if er > rs:
+                    continue
+            d = _hamming(mp_desc[k], fdesc[i])
+            if d < best:                                                 # :102-114
+                best2, best = best, d
+                best_lvl2, best_lvl = best_lvl, int(kps["octave"][i])
+                best_i = i
+            elif d < best2:
+                best_lvl2 = int(kps["octave"][i])
+                best2 = d
+        if best <= TH_HIGH:                                              # :118-124
+            if best_lvl == best_lvl2 and F(best) > F(nnratio * F(best2)):
+                continue
+            match[best_i] = k
+            obs[best_i] = nobs[k]
+            n += 1
+    return n, match, obs
+
+
+def compute_three_maxima(histo):
+    max1 = max2 = max3 = 0
+    ind1 = ind2 = ind3 = -1
+    for i, h in enumerate(histo):
+        s = len(h)
+        if s > max1:
+            max3, max2, max1 = max2, max1, s
+            ind3, ind2, ind1 = ind2, ind1, i
+        elif s > max2:
+            max3, max2 = max2, s
+            ind3, ind2 = ind2, i
+        elif s > max3:
+            max3, ind3 = s, i
+    if F(max2) < F(F(0.1) * F(max1)):                                    # :1632-1641
+        ind2 = ind3 = -1
+    elif F(max3) < F(F(0.1) * F(max1)):
+        ind3 = -1
+    return ind1, ind2, ind3
+
+
+def search_by_projection_frame(grid, fdesc, u_right, obs0, scale_factors, u, v, invz, last_octave, last_angle, valid,
+                               nobs, mp_desc, th, mbf, forward, backward, check_ori):
+    kps = grid.kps
+    sf = np.asarray(scale_factors, np.float32)
+    obs = np.array(obs0, np.int32)
+    match = np.full(len(kps), -1, np.int32)
+    th, mbf = F(th), F(mbf)
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    factor = F(F(1.0) / F(HISTO_LENGTH))                                 # :1336
+    n = 0
+    for i in range(len(mp_desc)):
+        if not valid[i]:                                                 # pMP && !mvbOutlier && invzc >= 0 (:1356-1369)
+            continue
+        ui, vi, iz = F(u[i]), F(v[i]), F(invz[i])
+        if ui < grid.min_x or ui > grid.max_x:                           # :1374-1377
+            continue
+        if vi < grid.min_y or vi > grid.max_y:
+            continue
+        lo = int(last_octave[i])                                         # :1379
+        radius = F(th * sf[lo])                                          # :1382
+        if forward:                                                      # :1386-1391
+            idx = grid.features_in_area(ui, vi, radius, lo)
+        elif backward:
+            idx = grid.features_in_area(ui, vi, radius, 0, lo)
+        else:
+            idx = grid.features_in_area(ui, vi, radius, lo - 1, lo + 1)
+        if not idx:
+            continue
+        best, best_i = 256, -1
+        for i2 in idx:                                                   # :1402-1426
+            if obs[i2] > 0:
+                continue
+            if u_right[i2] > 0:
+                ur = F(ui - F(mbf * iz))
+                er = abs(F(ur - F(u_right[i2])))
+                if er > radius:
+                    continue
+            d = _hamming(mp_desc[i], fdesc[i2])
+            if d < best:
+                best, best_i = d, i2
+        if best <= TH_HIGH:                                              # :1428-1445
+            match[best_i] = i
+            obs[best_i] = nobs[i]
+            n += 1
+            if check_ori:
+                rot = F(F(last_angle[i]) - F(kps["angle"][best_i]))
+                if rot < 0.0:
+                    rot = F(rot + F(360.0))
+                b = _roundf(F(rot * factor))
+                if b == HISTO_LENGTH:
+                    b = 0
+                hist[b].append(best_i)
+    if check_ori:                                                        # :1449-1467
+        keep = compute_three_maxima(hist)
+        for b in range(HISTO_LENGTH):
+            if b not in keep:
+                for j in hist[b]:
+                    match[j] = -1
+                    obs[j] = 0
+                    n -= 1
+    return n, match, obs

@@ -94,6 +94,78 @@ def test_stereo_recovers_synthetic_disparity(oracle):
     assert np.allclose(depth[ok], mbf / (kl["x"][ok] - ur[ok]), rtol=1e-5)
 
 
+@pytest.mark.parametrize("cfg,seed", [("kitti", 7), ("kitti12", 3)])
+def test_stereo_vs_second_restatement(oracle, cfg, seed):
+    """orc_stereo_match against tests/stereo_restatement.py, an independent numpy reading of Frame.cc:646-820."""
+    import stereo_restatement
+    h, w, nf, sf, nl, it, mt = CONFIGS[cfg]
+    left, right, _ = synth.stereo_pair(h, w, seed)
+    ol, orr = oracle.Extractor(nf, sf, nl, it, mt), oracle.Extractor(nf, sf, nl, it, mt)
+    kl, dl = ol(left)
+    kr, dr = orr(right)
+    mbf, mb = S.KITTI_BF, S.KITTI_BF / S.KITTI_FX
+    pl, pr = [ol.pyramid(l) for l in range(nl)], [orr.pyramid(l) for l in range(nl)]
+    ur, depth, _, _, n = oracle.stereo_match(kl, dl, kr, dr, pl, pr, ol.scale_factors(), mbf, mb)
+    roi = lambda levels: [p[19:-19, 19:-19] for p in levels]        # mvImagePyramid[l] is the ROI of the padded level
+    ur2, depth2 = stereo_restatement.compute_stereo_matches(kl, dl, kr, dr, roi(pl), roi(pr), ol.scale_factors(), mbf, mb)
+    assert n > 100
+    assert (ur.view(np.uint32) == ur2.view(np.uint32)).all()
+    assert (depth.view(np.uint32) == depth2.view(np.uint32)).all()
+
+
+@pytest.fixture(scope="module")
+def kitti_frame(oracle):
+    h, w, nf, sf, nl, it, mt = CONFIGS["kitti"]
+    left, _, _ = synth.stereo_pair(h, w, 7)
+    ex = oracle.Extractor(nf, sf, nl, it, mt)
+    k, d = ex(left)
+    return dict(k=k, d=d, sf=ex.scale_factors(), bounds=(0.0, float(w), 0.0, float(h)), shape=(h, w))
+
+
+def test_grid_vs_second_restatement(oracle, kitti_frame):
+    import search_restatement as R
+    f = kitti_frame
+    g, g2 = oracle.Grid(f["k"], *f["bounds"]), R.Grid(f["k"], *f["bounds"])
+    rng = np.random.default_rng(5)
+    h, w = f["shape"]
+    for _ in range(80):
+        x, y = float(rng.uniform(-20, w + 20)), float(rng.uniform(-20, h + 20))
+        r = float(rng.choice([3.0, 10.0, 25.0, 60.0]))
+        lo, hi = [(-1, -1), (0, 3), (2, -1), (1, 2), (4, 4)][int(rng.integers(0, 5))]
+        assert g.features_in_area(x, y, r, lo, hi).tolist() == g2.features_in_area(x, y, r, lo, hi)
+
+
+@pytest.mark.parametrize("th,nnratio", [(1.0, 0.8), (3.0, 0.8), (5.0, 0.6)])
+def test_search_by_projection_local_vs_second_restatement(oracle, kitti_frame, th, nnratio):
+    """orc_search_by_projection_local against tests/search_restatement.py (ORBmatcher.cc:45-137 read a second time)."""
+    import search_restatement as R
+    f = kitti_frame
+    sc = S.projection_scenario(f["k"], f["d"], f["sf"], seed=11)
+    args = (f["d"], sc["u_right"], sc["obs0"], f["sf"], sc["proj_x"], sc["proj_y"], sc["proj_xr"], sc["pred_level"],
+            sc["view_cos"], sc["valid"], sc["nobs"], sc["mp_desc"], th, nnratio)
+    n, m, obs = oracle.search_by_projection_local(oracle.Grid(f["k"], *f["bounds"]), *args)
+    n2, m2, obs2 = R.search_by_projection_local(R.Grid(f["k"], *f["bounds"]), *args)
+    assert n > 50 and n == n2 and (m == m2).all() and (obs == obs2).all()
+
+
+@pytest.mark.parametrize("mode,th,check_ori", [(0, 15.0, True), (1, 7.0, True), (2, 7.0, False), (0, 7.0, False)])
+def test_search_by_projection_frame_vs_second_restatement(oracle, kitti_frame, mode, th, check_ori):
+    """orc_search_by_projection_frame (modes 0/1/2 = neither / forward / backward) against
+    tests/search_restatement.py (ORBmatcher.cc:1378-1468 and ComputeThreeMaxima read a second time)."""
+    import search_restatement as R
+    f = kitti_frame
+    sc = S.projection_scenario(f["k"], f["d"], f["sf"], seed=11)
+    n, m, obs = oracle.search_by_projection_frame(
+        oracle.Grid(f["k"], *f["bounds"]), f["d"], sc["u_right"], sc["obs0"], f["sf"], sc["proj_x"], sc["proj_y"],
+        sc["invz"], sc["last_octave"], sc["last_angle"], sc["valid"], sc["nobs"], sc["mp_desc"], th, S.KITTI_BF, mode,
+        check_ori, 100)
+    n2, m2, obs2 = R.search_by_projection_frame(
+        R.Grid(f["k"], *f["bounds"]), f["d"], sc["u_right"], sc["obs0"], f["sf"], sc["proj_x"], sc["proj_y"], sc["invz"],
+        sc["last_octave"], sc["last_angle"], sc["valid"], sc["nobs"], sc["mp_desc"], th, S.KITTI_BF, mode == 1, mode == 2,
+        check_ori)
+    assert n > 30 and n == n2 and (m == m2).all() and (obs == obs2).all()
+
+
 def test_projection_scenario_is_meaningful(oracle):
     h, w, nf, sf, nl, it, mt = CONFIGS["kitti"]
     e = oracle.Extractor(nf, sf, nl, it, mt)
