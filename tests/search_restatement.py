@@ -6,6 +6,7 @@ tests/cv2_restatement.py pins the extractor oracle.
   search_by_projection_local ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) src/ORBmatcher.cc:45-137
   search_by_projection_frame ORBmatcher::SearchByProjection(Cur, Last, th, bMono)          src/ORBmatcher.cc:1378-1468
   compute_three_maxima       ORBmatcher::ComputeThreeMaxima                                 src/ORBmatcher.cc:1602-1643
+  search_for_triangulation   ORBmatcher::SearchForTriangulation + CheckDistEpipolarLine     src/ORBmatcher.cc:140-157,657-823
 
 The map-point graph is flattened the way the oracle's interface does it: obs[i] > 0 stands for
 "F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0", nobs[k] is Observations() of map point k.
@@ -200,3 +201,86 @@ def search_by_projection_frame(grid, fdesc, u_right, obs0, scale_factors, u, v, 
                     obs[j] = 0
                     n -= 1
     return n, match, obs
+
+
+def check_dist_epipolar_line(kp1, kp2, F12, sigma2_2):
+    """ORBmatcher::CheckDistEpipolarLine, src/ORBmatcher.cc:140-157; F12[r][c] = F12.at<float>(r, c)."""
+    x1, y1, x2, y2 = F(kp1["x"]), F(kp1["y"]), F(kp2["x"]), F(kp2["y"])
+    a = F(F(F(x1 * F12[0][0]) + F(y1 * F12[1][0])) + F12[2][0])
+    b = F(F(F(x1 * F12[0][1]) + F(y1 * F12[1][1])) + F12[2][1])
+    c = F(F(F(x1 * F12[0][2]) + F(y1 * F12[1][2])) + F12[2][2])
+    num = F(F(F(a * x2) + F(b * y2)) + c)
+    den = F(F(a * a) + F(b * b))
+    if den == 0:
+        return False
+    dsqr = F(F(num * num) / den)
+    return float(dsqr) < 3.84 * float(sigma2_2[int(kp2["octave"])])      # double comparison
+
+
+def search_for_triangulation(k1, d1, ur1, has_mp1, k2, d2, ur2, has_mp2, fv1, fv2, F12, ex, ey, scale2, sigma2_2,
+                             only_stereo, check_ori):
+    """ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:657-823 (epipole :667-670 computed by the caller).
+    fv = (node_ids ascending, node_ptr, idx): the std::map<node, vector<idx>> of DBoW2::FeatureVector."""
+    TH_LOW = 50
+    F12 = np.asarray(F12, np.float32).reshape(3, 3)
+    ex, ey = F(ex), F(ey)
+    m12 = np.full(len(k1), -1, np.int32)
+    matched2 = np.zeros(len(k2), bool)                                   # never set by the reference (:681)
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    factor = F(F(1.0) / F(HISTO_LENGTH))
+    ids1, ptr1, idx1v = fv1
+    ids2, ptr2, idx2v = fv2
+    n, i1, i2 = 0, 0, 0
+    while i1 < len(ids1) and i2 < len(ids2):                             # :697
+        if ids1[i1] == ids2[i2]:
+            for a in idx1v[ptr1[i1]:ptr1[i1 + 1]]:                       # :701
+                if has_mp1[a]:                                           # :707-709
+                    continue
+                stereo1 = ur1[a] >= 0
+                if only_stereo and not stereo1:
+                    continue
+                best, best2 = TH_LOW, -1
+                for b in idx2v[ptr2[i2]:ptr2[i2 + 1]]:                   # :724
+                    if matched2[b] or has_mp2[b]:
+                        continue
+                    stereo2 = ur2[b] >= 0
+                    if only_stereo and not stereo2:
+                        continue
+                    dist = _hamming(d1[a], d2[b])
+                    if dist > TH_LOW or dist > best:                     # :744 (an equal distance replaces the best)
+                        continue
+                    if not stereo1 and not stereo2:                      # :749-755
+                        dx = F(ex - F(k2["x"][b]))
+                        dy = F(ey - F(k2["y"][b]))
+                        if F(F(dx * dx) + F(dy * dy)) < F(F(100) * F(scale2[int(k2["octave"][b])])):
+                            continue
+                    if check_dist_epipolar_line(k1[a], k2[b], F12, sigma2_2):
+                        best2, best = int(b), dist
+                if best2 >= 0:                                           # :764-781
+                    m12[a] = best2
+                    n += 1
+                    if check_ori:
+                        rot = F(F(k1["angle"][a]) - F(k2["angle"][best2]))
+                        if rot < 0.0:
+                            rot = F(rot + F(360.0))
+                        bn = _roundf(F(rot * factor))
+                        if bn == HISTO_LENGTH:
+                            bn = 0
+                        hist[bn].append(int(a))
+            i1 += 1
+            i2 += 1
+        elif ids1[i1] < ids2[i2]:                                        # lower_bound (:787-793)
+            while i1 < len(ids1) and ids1[i1] < ids2[i2]:
+                i1 += 1
+        else:
+            while i2 < len(ids2) and ids2[i2] < ids1[i1]:
+                i2 += 1
+    if check_ori:                                                        # :796-814
+        keep = compute_three_maxima(hist)
+        for bn in range(HISTO_LENGTH):
+            if bn in keep:
+                continue
+            for a in hist[bn]:
+                m12[a] = -1
+                n -= 1
+    return n, m12

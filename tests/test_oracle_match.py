@@ -166,6 +166,30 @@ def test_search_by_projection_frame_vs_second_restatement(oracle, kitti_frame, m
     assert n > 30 and n == n2 and (m == m2).all() and (obs == obs2).all()
 
 
+@pytest.mark.parametrize("only_stereo,check_ori", [(False, False), (False, True), (True, False)])
+def test_search_for_triangulation_vs_second_restatement(oracle, only_stereo, check_ori):
+    """orc_search_for_triangulation against tests/search_restatement.py (ORBmatcher.cc:140-157, 657-823 read again)."""
+    import search_restatement as R
+    h, w, nf, sf_, nl, it, mt = CONFIGS["kitti"]
+    left, right, _ = synth.stereo_pair(h, w, 7)
+    e1, e2 = oracle.Extractor(nf, sf_, nl, it, mt), oracle.Extractor(nf, sf_, nl, it, mt)
+    k1, d1 = e1(left)
+    k2, d2 = e2(right)
+    rng = np.random.default_rng(4)
+    ur1 = np.where(rng.random(len(k1)) < 0.4, k1["x"] - 10, -1).astype(np.float32)
+    ur2 = np.where(rng.random(len(k2)) < 0.4, k2["x"] - 10, -1).astype(np.float32)
+    mp1 = (rng.random(len(k1)) < 0.2).astype(np.uint8)
+    mp2 = (rng.random(len(k2)) < 0.2).astype(np.uint8)
+    fv1 = S.feature_vector(k1, S.row_band_nodes())
+    fv2 = S.feature_vector(k2, S.row_band_nodes(drop_every=5))
+    sf = e1.scale_factors()
+    sigma2 = (sf * sf).astype(np.float32)
+    args = (k1, d1, ur1, mp1, k2, d2, ur2, mp2, fv1, fv2, S.RECTIFIED_F12, 600.0, 180.0, sf, sigma2, only_stereo, check_ori)
+    n, m = oracle.search_for_triangulation(*args)
+    n2, m2 = R.search_for_triangulation(*args)
+    assert n > (5 if only_stereo else 40) and n == n2 and (m == m2).all()
+
+
 def test_projection_scenario_is_meaningful(oracle):
     h, w, nf, sf, nl, it, mt = CONFIGS["kitti"]
     e = oracle.Extractor(nf, sf, nl, it, mt)
