@@ -7,6 +7,7 @@ tests/cv2_restatement.py pins the extractor oracle.
   search_by_projection_frame ORBmatcher::SearchByProjection(Cur, Last, th, bMono)          src/ORBmatcher.cc:1378-1468
   compute_three_maxima       ORBmatcher::ComputeThreeMaxima                                 src/ORBmatcher.cc:1602-1643
   search_for_triangulation   ORBmatcher::SearchForTriangulation + CheckDistEpipolarLine     src/ORBmatcher.cc:140-157,657-823
+  search_for_initialization  ORBmatcher::SearchForInitialization                            src/ORBmatcher.cc:405-520
 
 The map-point graph is flattened the way the oracle's interface does it: obs[i] > 0 stands for
 "F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0", nobs[k] is Observations() of map point k.
@@ -284,3 +285,65 @@ def search_for_triangulation(k1, d1, ur1, has_mp1, k2, d2, ur2, has_mp2, fv1, fv
                 m12[a] = -1
                 n -= 1
     return n, m12
+
+
+def search_for_initialization(grid2, d2, k1, d1, prev_matched, window, nnratio, check_ori):
+    """ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:405-520.  grid2 = frame 2 (keypoints + grid),
+    prev_matched = vbPrevMatched as an (N1, 2) float array; returns (nmatches, vnMatches12, updated vbPrevMatched)."""
+    TH_LOW, INT_MAX = 50, 2147483647
+    k2 = grid2.kps
+    nnratio = F(nnratio)
+    prev = np.array(prev_matched, np.float32)
+    m12 = np.full(len(k1), -1, np.int32)
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    factor = F(F(1.0) / F(HISTO_LENGTH))
+    matched_dist = [INT_MAX] * len(k2)                                   # :416-417
+    m21 = [-1] * len(k2)
+    n = 0
+    for i1 in range(len(k1)):
+        level1 = int(k1["octave"][i1])
+        if level1 > 0:                                                   # :423-424
+            continue
+        idx = grid2.features_in_area(prev[i1][0], prev[i1][1], F(window), level1, level1)   # :426
+        if not idx:
+            continue
+        best, best2, best_i = INT_MAX, INT_MAX, -1
+        for i2 in idx:                                                   # :437-458
+            dist = _hamming(d1[i1], d2[i2])
+            if matched_dist[i2] <= dist:
+                continue
+            if dist < best:
+                best2, best, best_i = best, dist, i2
+            elif dist < best2:
+                best2 = dist
+        if best <= TH_LOW:                                               # :460-486
+            if F(best) < F(F(best2) * nnratio):
+                if m21[best_i] >= 0:
+                    m12[m21[best_i]] = -1
+                    n -= 1
+                m12[i1] = best_i
+                m21[best_i] = i1
+                matched_dist[best_i] = best
+                n += 1
+                if check_ori:
+                    rot = F(F(k1["angle"][i1]) - F(k2["angle"][best_i]))
+                    if rot < 0.0:
+                        rot = F(rot + F(360.0))
+                    b = _roundf(F(rot * factor))
+                    if b == HISTO_LENGTH:
+                        b = 0
+                    hist[b].append(i1)
+    if check_ori:                                                        # :490-512
+        keep = compute_three_maxima(hist)
+        for b in range(HISTO_LENGTH):
+            if b in keep:
+                continue
+            for i1 in hist[b]:
+                if m12[i1] >= 0:
+                    m12[i1] = -1
+                    n -= 1
+    for i1 in range(len(k1)):                                            # :515-517
+        if m12[i1] >= 0:
+            prev[i1][0] = k2["x"][m12[i1]]
+            prev[i1][1] = k2["y"][m12[i1]]
+    return n, m12, prev

@@ -190,6 +190,24 @@ def test_search_for_triangulation_vs_second_restatement(oracle, only_stereo, che
     assert n > (5 if only_stereo else 40) and n == n2 and (m == m2).all()
 
 
+@pytest.mark.parametrize("window,check_ori,nnratio", [(100, True, 0.9), (30, False, 0.9), (60, True, 0.7)])
+def test_search_for_initialization_vs_second_restatement(oracle, window, check_ori, nnratio):
+    """orc_search_for_initialization against tests/search_restatement.py (ORBmatcher.cc:405-520 read again), including
+    the stolen-match dependence between consecutive keypoints."""
+    import search_restatement as R
+    h, w, nf, sf_, nl, it, mt = CONFIGS["kitti"]
+    left, right, _ = synth.stereo_pair(h, w, 7)
+    e1, e2 = oracle.Extractor(nf, sf_, nl, it, mt), oracle.Extractor(nf, sf_, nl, it, mt)
+    k1, d1 = e1(left)
+    k2, d2 = e2(right)
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    n, m, p = oracle.search_for_initialization(oracle.Grid(k2, 0.0, float(w), 0.0, float(h)), d2, k1, d1, prev, window,
+                                               nnratio, check_ori)
+    n2, m2, p2 = R.search_for_initialization(R.Grid(k2, 0.0, float(w), 0.0, float(h)), d2, k1, d1, prev, window, nnratio,
+                                             check_ori)
+    assert n > 20 and n == n2 and (m == m2).all() and (p.view(np.uint32) == p2.view(np.uint32)).all()
+
+
 def test_projection_scenario_is_meaningful(oracle):
     h, w, nf, sf, nl, it, mt = CONFIGS["kitti"]
     e = oracle.Extractor(nf, sf, nl, it, mt)
