@@ -66,6 +66,26 @@ def row_band_nodes(band=24, drop_every=7):
 RECTIFIED_F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32)   # l = x1' F12 = [0, 1, -y1]
 
 
+def bow_inputs(k1, d1, k2, d2, seed):
+    """two keypoint sets with feature vectors; some descriptors of set 1 are planted into set 2 (exact ties)"""
+    rng = np.random.default_rng(seed)
+    k2, d2 = k2.copy(), d2.copy()
+    fv1 = feature_vector(k1, row_band_nodes())
+    fv2 = feature_vector(k2, row_band_nodes(drop_every=5))
+    # plant near-copies of set-1 descriptors into set 2 inside the same node band, several per source (competition)
+    for _ in range(300):
+        i = int(rng.integers(0, len(k1)))
+        band = np.nonzero((k2["y"] // 24) == (k1["y"][i] // 24))[0]
+        if len(band) == 0:
+            continue
+        j = int(band[rng.integers(0, len(band))])
+        d2[j] = flip_bits(d1[i:i + 1], rng, 12)[0]
+        k2["angle"][j] = (k1["angle"][i] + rng.choice([0.0, 0.0, 0.0, 0.0, 100.0, 250.0])) % 360.0
+    v1 = (rng.random(len(k1)) < 0.8).astype(np.uint8)
+    v2 = (rng.random(len(k2)) < 0.8).astype(np.uint8)
+    return k1, d1, v1, k2, d2, v2, fv1, fv2
+
+
 def distinctive_batch(seed, nmp=300, max_obs=40, big=(0, 1, 2, 33, 257)):
     """CSR batch of map-point observation descriptors for MapPoint::ComputeDistinctiveDescriptors: clusters of noisy
     copies of a base descriptor (so medians tie between rows), plus points with 0/1/2 and many observations."""

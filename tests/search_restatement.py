@@ -8,6 +8,7 @@ tests/cv2_restatement.py pins the extractor oracle.
   compute_three_maxima       ORBmatcher::ComputeThreeMaxima                                 src/ORBmatcher.cc:1602-1643
   search_for_triangulation   ORBmatcher::SearchForTriangulation + CheckDistEpipolarLine     src/ORBmatcher.cc:140-157,657-823
   search_for_initialization  ORBmatcher::SearchForInitialization                            src/ORBmatcher.cc:405-520
+  search_by_bow              ORBmatcher::SearchByBoW, both overloads                        src/ORBmatcher.cc:159-288,522-655
 
 The map-point graph is flattened the way the oracle's interface does it: obs[i] > 0 stands for
 "F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0", nobs[k] is Observations() of map point k.
@@ -347,3 +348,70 @@ def search_for_initialization(grid2, d2, k1, d1, prev_matched, window, nnratio, 
             prev[i1][0] = k2["x"][m12[i1]]
             prev[i1][1] = k2["y"][m12[i1]]
     return n, m12, prev
+
+
+def search_by_bow(mode, k1, d1, valid1, k2, d2, valid2, fv1, fv2, nnratio, check_ori):
+    """ORBmatcher::SearchByBoW.  mode 0 = (KeyFrame* pKF, Frame& F), src/ORBmatcher.cc:159-288: set 1 is the key
+    frame (valid1[i] = map point present and not bad), set 2 the frame; returns per frame keypoint the key-frame
+    keypoint whose map point it received.  mode 1 = (KeyFrame*, KeyFrame*), :522-655: valid2 likewise; returns per
+    keypoint of key frame 1 the matched keypoint of key frame 2."""
+    TH_LOW = 50
+    nnratio = F(nnratio)
+    match = np.full(len(k2) if mode == 0 else len(k1), -1, np.int32)
+    matched2 = np.zeros(len(k2), bool)
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    factor = F(F(1.0) / F(HISTO_LENGTH))
+    ids1, ptr1, idx1v = fv1
+    ids2, ptr2, idx2v = fv2
+    n, i1, i2 = 0, 0, 0
+    while i1 < len(ids1) and i2 < len(ids2):
+        if ids1[i1] == ids2[i2]:
+            for a in idx1v[ptr1[i1]:ptr1[i1 + 1]]:
+                if not valid1[a]:                                        # :194-200 / :566-573
+                    continue
+                best1, best2, best_i = 256, 256, -1
+                for b in idx2v[ptr2[i2]:ptr2[i2 + 1]]:
+                    if mode == 0:
+                        if match[b] >= 0:                                # :212-213 vpMapPointMatches[realIdxF]
+                            continue
+                    else:
+                        if matched2[b] or not valid2[b]:                 # :587-591
+                            continue
+                    dist = _hamming(d1[a], d2[b])
+                    if dist < best1:
+                        best2, best1, best_i = best1, dist, int(b)
+                    elif dist < best2:
+                        best2 = dist
+                ok = best1 <= TH_LOW if mode == 0 else best1 < TH_LOW     # :232 vs :610
+                if ok and F(best1) < F(nnratio * F(best2)):
+                    rot = F(F(k1["angle"][a]) - F(k2["angle"][best_i]))
+                    if mode == 0:
+                        match[best_i] = a
+                    else:
+                        match[a] = best_i
+                        matched2[best_i] = True
+                    if check_ori:
+                        if rot < 0.0:
+                            rot = F(rot + F(360.0))
+                        bn = _roundf(F(rot * factor))
+                        if bn == HISTO_LENGTH:
+                            bn = 0
+                        hist[bn].append(best_i if mode == 0 else int(a))
+                    n += 1
+            i1 += 1
+            i2 += 1
+        elif ids1[i1] < ids2[i2]:
+            while i1 < len(ids1) and ids1[i1] < ids2[i2]:
+                i1 += 1
+        else:
+            while i2 < len(ids2) and ids2[i2] < ids1[i1]:
+                i2 += 1
+    if check_ori:
+        keep = compute_three_maxima(hist)
+        for bn in range(HISTO_LENGTH):
+            if bn in keep:
+                continue
+            for j in hist[bn]:
+                match[j] = -1
+                n -= 1
+    return n, match

@@ -208,6 +208,21 @@ def test_search_for_initialization_vs_second_restatement(oracle, window, check_o
     assert n > 20 and n == n2 and (m == m2).all() and (p.view(np.uint32) == p2.view(np.uint32)).all()
 
 
+@pytest.mark.parametrize("mode,check_ori,nnratio", [(0, True, 0.7), (0, False, 0.9), (1, True, 0.75), (1, False, 0.6)])
+def test_search_by_bow_vs_second_restatement(oracle, mode, check_ori, nnratio):
+    """orc_search_by_bow against tests/search_restatement.py (ORBmatcher.cc:159-288 and :522-655 read again)."""
+    import search_restatement as R
+    h, w, nf, sf_, nl, it, mt = CONFIGS["kitti"]
+    left, right, _ = synth.stereo_pair(h, w, 7)
+    e1, e2 = oracle.Extractor(nf, sf_, nl, it, mt), oracle.Extractor(nf, sf_, nl, it, mt)
+    k1, d1 = e1(left)
+    k2, d2 = e2(right)
+    k1, d1, v1, k2, d2, v2, fv1, fv2 = S.bow_inputs(k1, d1, k2, d2, 5 + mode)
+    n, m = oracle.search_by_bow(mode, k1, d1, v1, k2, d2, v2 if mode else None, fv1, fv2, nnratio, check_ori)
+    n2, m2 = R.search_by_bow(mode, k1, d1, v1, k2, d2, v2 if mode else None, fv1, fv2, nnratio, check_ori)
+    assert n > 50 and n == n2 and (m == m2).all()
+
+
 def test_projection_scenario_is_meaningful(oracle):
     h, w, nf, sf, nl, it, mt = CONFIGS["kitti"]
     e = oracle.Extractor(nf, sf, nl, it, mt)

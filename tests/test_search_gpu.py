@@ -227,23 +227,7 @@ def test_bow_transform(api, ctx, oracle, weighting, scoring, k, L, levelsup):
 
 
 def _bow_inputs(s, seed):
-    """two keypoint sets with feature vectors; some descriptors of set 1 are planted into set 2 (exact ties)"""
-    rng = np.random.default_rng(seed)
-    k1, d1, k2, d2 = s["kl"], s["dl"], s["kr"].copy(), s["dr"].copy()
-    fv1 = S.feature_vector(k1, S.row_band_nodes())
-    fv2 = S.feature_vector(k2, S.row_band_nodes(drop_every=5))
-    # plant near-copies of set-1 descriptors into set 2 inside the same node band, several per source (competition)
-    for _ in range(300):
-        i = int(rng.integers(0, len(k1)))
-        band = np.nonzero((k2["y"] // 24) == (k1["y"][i] // 24))[0]
-        if len(band) == 0:
-            continue
-        j = int(band[rng.integers(0, len(band))])
-        d2[j] = S.flip_bits(d1[i:i + 1], rng, 12)[0]
-        k2["angle"][j] = (k1["angle"][i] + rng.choice([0.0, 0.0, 0.0, 0.0, 100.0, 250.0])) % 360.0
-    v1 = (rng.random(len(k1)) < 0.8).astype(np.uint8)
-    v2 = (rng.random(len(k2)) < 0.8).astype(np.uint8)
-    return k1, d1, v1, k2, d2, v2, fv1, fv2
+    return S.bow_inputs(s["kl"], s["dl"], s["kr"], s["dr"], seed)
 
 
 @pytest.mark.parametrize("mode,check_ori,nnratio", [(0, True, 0.7), (0, False, 0.9), (1, True, 0.75), (1, False, 0.6)])
