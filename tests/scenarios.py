@@ -86,6 +86,17 @@ def bow_inputs(k1, d1, k2, d2, seed):
     return k1, d1, v1, k2, d2, v2, fv1, fv2
 
 
+def window_queries(k_src, d_src, k_dst, seed, disp):
+    """map points of `src` keypoints projected near the corresponding place in `dst` (stereo pair: shift by disparity)"""
+    rng = np.random.default_rng(seed)
+    n = len(k_src)
+    u = (k_src["x"] - disp + rng.normal(0, 1.5, n)).astype(np.float32)
+    v = (k_src["y"] + rng.normal(0, 1.0, n)).astype(np.float32)
+    level = np.clip(k_src["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
+    valid = (rng.random(n) < 0.85).astype(np.uint8)
+    return u, v, level, valid, flip_bits(d_src, rng, 20)
+
+
 def distinctive_batch(seed, nmp=300, max_obs=40, big=(0, 1, 2, 33, 257)):
     """CSR batch of map-point observation descriptors for MapPoint::ComputeDistinctiveDescriptors: clusters of noisy
     copies of a base descriptor (so medians tie between rows), plus points with 0/1/2 and many observations."""

@@ -9,6 +9,9 @@ tests/cv2_restatement.py pins the extractor oracle.
   search_for_triangulation   ORBmatcher::SearchForTriangulation + CheckDistEpipolarLine     src/ORBmatcher.cc:140-157,657-823
   search_for_initialization  ORBmatcher::SearchForInitialization                            src/ORBmatcher.cc:405-520
   search_by_bow              ORBmatcher::SearchByBoW, both overloads                        src/ORBmatcher.cc:159-288,522-655
+  search_by_projection_reloc / _sim3   the two KeyFrame overloads of SearchByProjection     src/ORBmatcher.cc:1473-1600, 290-403
+  search_window_top1         candidate loop of Fuse x2 and SearchBySim3                     src/ORBmatcher.cc:883-943,1043-1073,1193-1226
+  search_by_sim3             ORBmatcher::SearchBySim3 (searches + agreement)                src/ORBmatcher.cc:1193-1320
 
 The map-point graph is flattened the way the oracle's interface does it: obs[i] > 0 stands for
 "F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0", nobs[k] is Observations() of map point k.
@@ -415,3 +418,146 @@ def search_by_bow(mode, k1, d1, valid1, k2, d2, valid2, fv1, fv2, nnratio, check
                 match[j] = -1
                 n -= 1
     return n, match
+
+
+def search_by_projection_reloc(grid, fdesc, assigned0, scale_factors, u, v, pred_level, kf_angle, valid, mp_desc, th,
+                               orb_dist, check_ori):
+    """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, ORBdist), src/ORBmatcher.cc:1473-1600,
+    from the image-bounds test (:1505) on; the projection, the distance gate and PredictScale are the caller's
+    (valid / pred_level).  assigned0[i] != 0 <=> CurrentFrame.mvpMapPoints[i] != NULL."""
+    kps = grid.kps
+    sf = np.asarray(scale_factors, np.float32)
+    assigned = np.array(assigned0, np.int32)
+    match = np.full(len(kps), -1, np.int32)
+    th = F(th)
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    factor = F(F(1.0) / F(HISTO_LENGTH))
+    n = 0
+    for i in range(len(mp_desc)):
+        if not valid[i]:
+            continue
+        ui, vi = F(u[i]), F(v[i])
+        if ui < grid.min_x or ui > grid.max_x or vi < grid.min_y or vi > grid.max_y:       # :1505-1508
+            continue
+        level = int(pred_level[i])
+        radius = F(th * sf[level])                                                          # :1525
+        idx = grid.features_in_area(ui, vi, radius, level - 1, level + 1)                   # :1527
+        best, best_i = 256, -1
+        for i2 in idx:
+            if assigned[i2]:                                                                # :1540-1541
+                continue
+            d = _hamming(mp_desc[i], fdesc[i2])
+            if d < best:
+                best, best_i = d, i2
+        if best <= orb_dist:                                                                # :1554
+            match[best_i] = i
+            assigned[best_i] = 1
+            n += 1
+            if check_ori:
+                rot = F(F(kf_angle[i]) - F(kps["angle"][best_i]))
+                if rot < 0.0:
+                    rot = F(rot + F(360.0))
+                b = _roundf(F(rot * factor))
+                if b == HISTO_LENGTH:
+                    b = 0
+                hist[b].append(best_i)
+    if check_ori:
+        keep = compute_three_maxima(hist)
+        for b in range(HISTO_LENGTH):
+            if b not in keep:
+                for j in hist[b]:
+                    match[j] = -1
+                    assigned[j] = 0
+                    n -= 1
+    return n, match, assigned
+
+
+def search_by_projection_sim3(grid, fdesc, assigned0, scale_factors, u, v, pred_level, valid, mp_desc, th):
+    """ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th), src/ORBmatcher.cc:290-403, from the
+    search radius (:365) on: KeyFrame::GetFeaturesInArea has no level arguments (src/KeyFrame.cc:906-945), the level
+    window [l-1, l] is applied inside the candidate loop, any keypoint with a match is skipped, TH_LOW."""
+    TH_LOW = 50
+    kps = grid.kps
+    sf = np.asarray(scale_factors, np.float32)
+    assigned = np.array(assigned0, np.int32)
+    match = np.full(len(kps), -1, np.int32)
+    n = 0
+    for i in range(len(mp_desc)):
+        if not valid[i]:
+            continue
+        level = int(pred_level[i])
+        radius = F(F(int(th)) * sf[level])                                                  # :365 (int th)
+        idx = grid.features_in_area(u[i], v[i], radius)                                     # :367
+        best, best_i = 256, -1
+        for j in idx:
+            if assigned[j]:                                                                 # :378-379
+                continue
+            lvl = int(kps["octave"][j])
+            if lvl < level - 1 or lvl > level:                                              # :383-384
+                continue
+            d = _hamming(mp_desc[i], fdesc[j])
+            if d < best:
+                best, best_i = d, j
+        if best <= TH_LOW:                                                                  # :396
+            match[best_i] = i
+            assigned[best_i] = 1
+            n += 1
+    return n, match, assigned
+
+
+def search_window_top1(grid, kdesc, u_right, scale_factors, u, v, ur, pred_level, valid, mp_desc, th, th_dist,
+                       inv_level_sigma2=None):
+    """The candidate loop shared by ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:883-943, with the
+    chi-square gates: ur given), Fuse(KeyFrame*, Scw, ...) (:1043-1073) and SearchBySim3 (:1193-1226, :1272-1303):
+    KeyFrame::GetFeaturesInArea, level window [l-1, l], best distance <= th_dist.  -> (best index or -1, distance)."""
+    INT_MAX = 2147483647
+    kps = grid.kps
+    sf = np.asarray(scale_factors, np.float32)
+    th = F(th)
+    n = len(u)
+    best_idx = np.full(n, -1, np.int32)
+    best_dist = np.full(n, INT_MAX, np.int32)
+    for i in range(n):
+        if not valid[i]:
+            continue
+        level = int(pred_level[i])
+        radius = F(th * sf[level])
+        ui, vi = F(u[i]), F(v[i])
+        best, bi = (256 if ur is not None else INT_MAX), -1                               # :885 vs :1045, :1198
+        for j in grid.features_in_area(ui, vi, radius):
+            lvl = int(kps["octave"][j])
+            if lvl < level - 1 or lvl > level:
+                continue
+            if ur is not None:                                                            # :901-927
+                ex = F(ui - F(kps["x"][j]))
+                ey = F(vi - F(kps["y"][j]))
+                if u_right[j] >= 0:
+                    er = F(F(ur[i]) - F(u_right[j]))
+                    e2 = F(F(F(ex * ex) + F(ey * ey)) + F(er * er))
+                    if float(F(e2 * F(inv_level_sigma2[lvl]))) > 7.8:
+                        continue
+                else:
+                    e2 = F(F(ex * ex) + F(ey * ey))
+                    if float(F(e2 * F(inv_level_sigma2[lvl]))) > 5.99:
+                        continue
+            d = _hamming(mp_desc[i], kdesc[j])
+            if d < best:
+                best, bi = d, j
+        if best <= th_dist:
+            best_idx[i], best_dist[i] = bi, best
+    return best_idx, best_dist
+
+
+def search_by_sim3(g1, d1, sf1, g2, d2, sf2, q12, q21, th):
+    """ORBmatcher::SearchBySim3, src/ORBmatcher.cc:1102-1326 from the projections on: q12 = (u, v, level, valid,
+    descriptor) of key frame 1's map points in key frame 2, q21 the reverse; TH_HIGH; agreement check :1305-1320."""
+    m1, _ = search_window_top1(g2, d2, None, sf2, q12[0], q12[1], None, q12[2], q12[3], q12[4], th, TH_HIGH)
+    m2, _ = search_window_top1(g1, d1, None, sf1, q21[0], q21[1], None, q21[2], q21[3], q21[4], th, TH_HIGH)
+    m12 = np.full(len(g1.kps), -1, np.int32)
+    n = 0
+    for i1 in range(len(g1.kps)):
+        i2 = m1[i1]
+        if i2 >= 0 and m2[i2] == i1:
+            m12[i1] = i2
+            n += 1
+    return n, m12

@@ -223,6 +223,59 @@ def test_search_by_bow_vs_second_restatement(oracle, mode, check_ori, nnratio):
     assert n > 50 and n == n2 and (m == m2).all()
 
 
+def test_keyframe_projection_overloads_vs_second_restatement(oracle, kitti_frame):
+    """relocalisation (ORBmatcher.cc:1473-1600) and Sim3 (:290-403) overloads: the oracle's flag combinations
+    (mode 0|8 and 3|8 of orc_search_by_projection_frame) against the overloads read a second time."""
+    import search_restatement as R
+    f = kitti_frame
+    sc = S.projection_scenario(f["k"], f["d"], f["sf"], seed=11)
+    obs0 = (sc["obs0"] > 0).astype(np.int32)
+    nobs = np.ones(len(sc["valid"]), np.int32)
+    g, g2 = oracle.Grid(f["k"], *f["bounds"]), R.Grid(f["k"], *f["bounds"])
+    for th, orb_dist, check_ori in ((10.0, 100, True), (3.0, 64, True), (10.0, 100, False)):
+        n, m, obs = oracle.search_by_projection_frame(g, f["d"], sc["u_right"], obs0, f["sf"], sc["proj_x"], sc["proj_y"],
+                                                      sc["invz"], sc["pred_level"], sc["last_angle"], sc["valid"], nobs,
+                                                      sc["mp_desc"], th, S.KITTI_BF, 0 | 8, check_ori, orb_dist)
+        n2, m2, a2 = R.search_by_projection_reloc(g2, f["d"], obs0, f["sf"], sc["proj_x"], sc["proj_y"], sc["pred_level"],
+                                                  sc["last_angle"], sc["valid"], sc["mp_desc"], th, orb_dist, check_ori)
+        assert n > 30 and n == n2 and (m == m2).all() and (obs == a2).all()
+    n, m, obs = oracle.search_by_projection_frame(g, f["d"], sc["u_right"], obs0, f["sf"], sc["proj_x"], sc["proj_y"],
+                                                  sc["invz"], sc["pred_level"], sc["last_angle"], sc["valid"], nobs,
+                                                  sc["mp_desc"], 10.0, S.KITTI_BF, 3 | 8, False, 50)
+    n2, m2, a2 = R.search_by_projection_sim3(g2, f["d"], obs0, f["sf"], sc["proj_x"], sc["proj_y"], sc["pred_level"],
+                                             sc["valid"], sc["mp_desc"], 10)
+    assert n > 30 and n == n2 and (m == m2).all() and (obs == a2).all()
+
+
+def test_fuse_loop_and_sim3_vs_second_restatement(oracle):
+    """orc_search_window_top1 (the Fuse candidate loops, with and without the chi-square gates) and orc_search_by_sim3
+    against tests/search_restatement.py (ORBmatcher.cc:883-943, :1043-1073, :1193-1320 read again)."""
+    import search_restatement as R
+    h, w, nf, sf_, nl, it, mt = CONFIGS["kitti"]
+    left, right, _ = synth.stereo_pair(h, w, 7)
+    e1, e2 = oracle.Extractor(nf, sf_, nl, it, mt), oracle.Extractor(nf, sf_, nl, it, mt)
+    kl, dl = e1(left)
+    kr, dr = e2(right)
+    sf = e1.scale_factors()
+    inv_sigma2 = (1.0 / (sf * sf)).astype(np.float32)
+    b = (0.0, float(w), 0.0, float(h))
+    for gates, th in ((True, 3.0), (False, 4.0), (False, 10.0)):
+        rng = np.random.default_rng(2)
+        u_right = np.where(rng.random(len(kr)) < 0.5, kr["x"] - rng.uniform(2, 40, len(kr)), -1).astype(np.float32)
+        u, v, level, valid, mpd = S.window_queries(kl, dl, kr, 3, 20.0)
+        ur = (u - rng.uniform(2, 40, len(u))).astype(np.float32) if gates else None
+        args = (dr, u_right, sf, u, v, ur, level, valid, mpd, th, 50, inv_sigma2 if gates else None)
+        bi, bd = oracle.search_window_top1(oracle.Grid(kr, *b), *args)
+        bi2, bd2 = R.search_window_top1(R.Grid(kr, *b), *args)
+        assert (bi >= 0).sum() > (5 if gates else 30)
+        assert (bi == bi2).all() and (bd[bi >= 0] == bd2[bi >= 0]).all()
+    q12 = S.window_queries(kl, dl, kr, 5, 20.0)
+    q21 = S.window_queries(kr, dr, kl, 6, -20.0)
+    n, m = oracle.search_by_sim3(oracle.Grid(kl, *b), dl, sf, oracle.Grid(kr, *b), dr, sf, q12, q21, 25.0)
+    n2, m2 = R.search_by_sim3(R.Grid(kl, *b), dl, sf, R.Grid(kr, *b), dr, sf, q12, q21, 25.0)
+    assert n > 20 and n == n2 and (m == m2).all()
+
+
 def test_projection_scenario_is_meaningful(oracle):
     h, w, nf, sf, nl, it, mt = CONFIGS["kitti"]
     e = oracle.Extractor(nf, sf, nl, it, mt)

@@ -291,14 +291,7 @@ def test_undistort_and_grid_on_device(api, ctx, oracle, stereo, K, dist, size):
 
 
 def _window_queries(k_src, d_src, k_dst, seed, disp):
-    """map points of `src` keypoints projected near the corresponding place in `dst` (stereo pair: shift by disparity)"""
-    rng = np.random.default_rng(seed)
-    n = len(k_src)
-    u = (k_src["x"] - disp + rng.normal(0, 1.5, n)).astype(np.float32)
-    v = (k_src["y"] + rng.normal(0, 1.0, n)).astype(np.float32)
-    level = np.clip(k_src["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
-    valid = (rng.random(n) < 0.85).astype(np.uint8)
-    return u, v, level, valid, S.flip_bits(d_src, rng, 20)
+    return S.window_queries(k_src, d_src, k_dst, seed, disp)
 
 
 @pytest.mark.parametrize("gates,th", [(True, 3.0), (False, 4.0), (False, 10.0)])
