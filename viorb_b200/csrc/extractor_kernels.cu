@@ -159,10 +159,14 @@ __device__ __forceinline__ void pyr_resize_tile(const FrameGeom& g, int level, c
     {
         const uint8_t* sroi = base + P.pyrOff + (size_t)VIORB_EDGE * P.step + VIORB_ROI_X0;   /* 16-byte aligned */
         const int v = tid & 15;
-        if (v < nvec)
-            for (int r = tid >> 4; r < nrow; r += 8)
-                *reinterpret_cast<uint4*>(&src[r * RZ_SSTRIDE + 16 * v]) =
-                    *reinterpret_cast<const uint4*>(sroi + (size_t)(sy0 + r) * P.step + sx0 + 16 * v);
+        /* cp.async: the copies stay in flight while the thread sets up its row and column tables below */
+        if (v < nvec) {
+            const uint8_t* gp = sroi + (size_t)(sy0 + (tid >> 4)) * P.step + sx0 + 16 * v;
+            unsigned sp = (unsigned)__cvta_generic_to_shared(&src[(tid >> 4) * RZ_SSTRIDE + 16 * v]);
+            for (int r = tid >> 4; r < nrow; r += 8, gp += 8 * (size_t)P.step, sp += 8 * RZ_SSTRIDE)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     if (tid < TH && ya + tid <= yhi) {
         const int dy = reflect101(ya + tid, L.h);
@@ -193,6 +197,7 @@ __device__ __forceinline__ void pyr_resize_tile(const FrameGeom& g, int level, c
         const unsigned d = (unsigned)(rel[j] - lo);
         selP[j] = d | ((d + 1) << 4);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (wi >= stepWords) return;
     const unsigned* srcw = reinterpret_cast<const unsigned*>(src) + wb;
