@@ -23,10 +23,29 @@ class _Image(C.Structure):
 
 
 _lib = None
+_override = None          # set by using(): routes every wrapper of this module to another library (oracle/ref_py.py)
+
+
+class using:
+    """with using(other_lib): ...  -- the wrappers below call `other_lib` (same orc_* names and signatures)."""
+
+    def __init__(self, other):
+        self.other = other
+
+    def __enter__(self):
+        global _override
+        self.prev, _override = _override, self.other
+        return self.other
+
+    def __exit__(self, *a):
+        global _override
+        _override = self.prev
 
 
 def lib(path=None):
     global _lib
+    if _override is not None and path is None:
+        return _override
     if _lib is not None and path is None:
         return _lib
     if path is None:
@@ -40,6 +59,7 @@ def lib(path=None):
     L.orc_border_reflect101_u8.argtypes = [vp, i32, i32, sz, vp, sz, i32]
     L.orc_fast9_16.argtypes = [vp, i32, i32, sz, i32, i32, vp, i32]
     L.orc_gaussian7_u8.argtypes = [vp, i32, i32, sz, vp, sz]
+    L.orc_gaussian7_u8_variant.argtypes = [vp, i32, i32, sz, vp, sz, i32]
     L.orc_fast_atan2.argtypes = [f32, f32]
     L.orc_fast_atan2.restype = f32
     L.orc_sincosf.argtypes = [f32, C.POINTER(f32), C.POINTER(f32)]
@@ -51,6 +71,8 @@ def lib(path=None):
     L.orc_extractor_create.argtypes = [i32, f32, i32, i32, i32]
     L.orc_extractor_create.restype = vp
     L.orc_extractor_destroy.argtypes = [vp]
+    L.orc_extractor_set_gaussian.argtypes = [vp, i32]
+    L.orc_extractor_set_gaussian.restype = None
     L.orc_extract.argtypes = [vp, vp, i32, i32, sz, vp, vp, i32]
     L.orc_extractor_levels.argtypes = [vp]
     L.orc_extractor_quota.argtypes = [vp, i32]
@@ -136,10 +158,11 @@ def fast9(img, threshold, nms=True, cap=1 << 16):
     return out[:n]
 
 
-def gaussian7(src):
+def gaussian7(src, variant=0):
+    """variant 0 = OpenCV >= 3.4 taps (cv2-pinned), 1 = OpenCV 2.4 taps"""
     src = _c(src, np.uint8)
     dst = np.empty_like(src)
-    lib().orc_gaussian7_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0])
+    lib().orc_gaussian7_u8_variant(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0], int(variant))
     return dst
 
 
@@ -196,6 +219,10 @@ class Extractor:
         n = self.L.orc_extract(self.h, _p(img), img.shape[0], img.shape[1], img.strides[0], _p(kps), _p(desc), cap)
         assert 0 <= n <= cap, n
         return kps[:n].copy(), desc[:n].copy()
+
+    def set_gaussian_variant(self, variant):
+        """0 = OpenCV >= 3.4 taps (default), 1 = OpenCV 2.4 taps"""
+        self.L.orc_extractor_set_gaussian(self.h, int(variant))
 
     def quotas(self):
         return [self.L.orc_extractor_quota(self.h, l) for l in range(self.nlevels)]

@@ -249,8 +249,13 @@ extern "C" int orc_fast9_16(const uint8_t* img, int w, int h, size_t step, int t
  * fixed-point path (smooth.dispatch: ufixedpoint16 taps [18,34,48,56,48,34,18]/256).
  * Called at ORBextractor.cc:1086 on a clone of the level ROI (border reflects at the ROI edge).
  * ---------------------------------------------------------------------------------------------- */
-extern "C" void orc_gaussian7_u8(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep) {
-    static const int k[7] = {18, 34, 48, 56, 48, 34, 18};
+/* variant 0: OpenCV >= 3.4 (the 4.13 in this image; verified on cv2).  variant 1: OpenCV 2.4.x, the version the reference
+ * pins (CMakeLists.txt:31): getGaussianKernel(7, 2) in float, scaled by 256 and rounded (filter.cpp createSeparableLinearFilter,
+ * bits = 8) = [18,34,49,55,49,34,18] (sum 257), row filter 8u->32s, column filter FixedPtCastEx (v + 2^15) >> 16.  The 2.4
+ * taps are restated from its published source; no 2.4 binary is runnable here. */
+extern "C" void orc_gaussian7_u8_variant(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep, int variant) {
+    static const int taps[2][7] = {{18, 34, 48, 56, 48, 34, 18}, {18, 34, 49, 55, 49, 34, 18}};
+    const int* k = taps[variant ? 1 : 0];
     std::vector<uint16_t> t((size_t)w * h);
     std::vector<uint8_t> row((size_t)w + 6);
     for (int y = 0; y < h; y++) {
@@ -260,7 +265,7 @@ extern "C" void orc_gaussian7_u8(const uint8_t* src, int w, int h, size_t sstep,
         const uint8_t* r = row.data();
         for (int x = 0; x < w; x++)
             T[x] = (uint16_t)(k[0] * r[x] + k[1] * r[x + 1] + k[2] * r[x + 2] + k[3] * r[x + 3] + k[4] * r[x + 4] +
-                              k[5] * r[x + 5] + k[6] * r[x + 6]);
+                              k[5] * r[x + 5] + k[6] * r[x + 6]);             /* <= 255*257 = 65535 */
     }
     for (int y = 0; y < h; y++) {
         uint8_t* D = dst + (size_t)y * dstep;
@@ -270,9 +275,13 @@ extern "C" void orc_gaussian7_u8(const uint8_t* src, int w, int h, size_t sstep,
             uint32_t acc = (uint32_t)k[0] * T[0][x] + (uint32_t)k[1] * T[1][x] + (uint32_t)k[2] * T[2][x] +
                            (uint32_t)k[3] * T[3][x] + (uint32_t)k[4] * T[4][x] + (uint32_t)k[5] * T[5][x] +
                            (uint32_t)k[6] * T[6][x];
-            D[x] = (uint8_t)((acc + 32768u) >> 16);
+            const uint32_t v = (acc + 32768u) >> 16;
+            D[x] = (uint8_t)(v > 255u ? 255u : v);                              /* 2.4 taps can reach 256 on saturated areas */
         }
     }
+}
+extern "C" void orc_gaussian7_u8(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep) {
+    orc_gaussian7_u8_variant(src, w, h, sstep, dst, dstep, 0);
 }
 
 /* cv::fastAtan2 (OpenCV core mathfuncs_core: atan_f32 polynomial, degrees).  ORBextractor.cc:103 */
@@ -574,6 +583,7 @@ struct orc_extractor {
     std::vector<std::vector<orc_keypoint> > levelKeys;
     double stage[6];
     int retried;
+    int gaussVariant = 0;        /* 0 = OpenCV >= 3.4 taps, 1 = OpenCV 2.4 taps (orc_gaussian7_u8_variant) */
 };
 
 extern "C" orc_extractor* orc_extractor_create(int nfeatures, float scale_factor, int nlevels, int ini, int mn) {
@@ -779,7 +789,7 @@ extern "C" int orc_extract(orc_extractor* e, const uint8_t* img, int rows, int c
         double t1 = now_s();
         bl.w = im.w; bl.h = im.h; bl.step = im.step;
         bl.buf.assign(im.buf.size(), 0);
-        orc_gaussian7_u8(im.roi(), im.w, im.h, im.step, bl.roi(), bl.step);
+        orc_gaussian7_u8_variant(im.roi(), im.w, im.h, im.step, bl.roi(), bl.step, e->gaussVariant);
         double t2 = now_s();
         for (size_t i = 0; i < keypoints.size(); i++) {
             if (offset + (int)i < cap) compute_orb_descriptor(keypoints[i], bl, desc + (size_t)(offset + i) * 32);
@@ -799,6 +809,7 @@ extern "C" int orc_extract(orc_extractor* e, const uint8_t* img, int rows, int c
     return offset;
 }
 
+extern "C" void orc_extractor_set_gaussian(orc_extractor* e, int variant) { e->gaussVariant = variant ? 1 : 0; }
 extern "C" int orc_extractor_levels(const orc_extractor* e) { return e->nlevels; }
 extern "C" int orc_extractor_quota(const orc_extractor* e, int l) { return e->mnFeaturesPerLevel[l]; }
 extern "C" float orc_extractor_scale(const orc_extractor* e, int l) { return e->mvScaleFactor[l]; }

@@ -42,6 +42,8 @@ void orc_border_reflect101_u8(const uint8_t* src, int w, int h, size_t sstep,
 int  orc_fast9_16(const uint8_t* img, int w, int h, size_t step, int threshold, int nms,
                   orc_corner* out, int cap);
 void orc_gaussian7_u8(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep);
+/* variant 0 = OpenCV >= 3.4 taps [18,34,48,56,48,34,18], 1 = OpenCV 2.4 taps [18,34,49,55,49,34,18] */
+void orc_gaussian7_u8_variant(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep, int variant);
 float orc_fast_atan2(float y, float x);
 void orc_sincosf(float x, float* s, float* c);
 void orc_orientation_sweep(const int32_t* m01, const int32_t* m10, int64_t n, float* deg, int threads);
@@ -53,6 +55,8 @@ typedef struct orc_extractor orc_extractor;
 orc_extractor* orc_extractor_create(int nfeatures, float scale_factor, int nlevels,
                                     int ini_th_fast, int min_th_fast);
 void orc_extractor_destroy(orc_extractor*);
+/* GaussianBlur taps of ORBextractor.cc:1086: 0 = OpenCV >= 3.4 (default), 1 = OpenCV 2.4 */
+void orc_extractor_set_gaussian(orc_extractor*, int variant);
 /* runs operator(); returns number of keypoints (<= cap written), or <0 on error */
 int orc_extract(orc_extractor*, const uint8_t* img, int rows, int cols, size_t step,
                 orc_keypoint* kps, uint8_t* desc, int cap);

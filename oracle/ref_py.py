@@ -1,0 +1,80 @@
+"""ctypes binding of oracle/_ref/libviorb_ref.so: the REFERENCE's own source files (src/ORBextractor.cc, src/ORBmatcher.cc,
+the ORB members of src/Frame.cc / KeyFrame.cc / MapPoint.cc, Thirdparty/DBoW2) compiled unmodified by oracle/refbuild/Makefile.
+TEST INFRASTRUCTURE ONLY -- same import rules as oracle_py.
+
+The library exports ref_X for the orc_X entry points of oracle/orb_oracle.h with identical signatures, so
+
+    with O.using(ref_py.lib()):
+        kps, desc = O.Extractor(...)(img)          # runs the reference
+
+drives every wrapper of oracle_py through the reference instead of the restatement.
+
+/root/reference exists only in the build container.  There the library is (re)built on demand; on the GPU box the prebuilt
+file that travelled with the snapshot is loaded as is; with neither, available() is False and callers skip.
+"""
+import ctypes as C
+import os
+import subprocess
+
+from . import oracle_py as O
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = os.environ.get("VIORB_REFERENCE", "/root/reference")
+PATH = os.path.join(_HERE, "_ref", "libviorb_ref.so")
+
+
+class RefLib:
+    """Attribute orc_X resolves to the library's ref_X, typed like the oracle's orc_X."""
+
+    def __init__(self, path):
+        self._l = C.CDLL(path)
+        self._o = O.lib(os.path.join(_HERE, "_build", "liborb_oracle.so")) if O._lib is None else O._lib
+
+    def __getattr__(self, name):
+        if name.startswith("orc_"):
+            f = getattr(self._l, "ref_" + name[4:])          # AttributeError when the reference has no such entry point
+            o = getattr(self._o, name)
+            f.argtypes, f.restype = o.argtypes, o.restype
+            setattr(self, name, f)
+            return f
+        return getattr(self._l, name)
+
+
+_lib = None
+
+
+def build():
+    """make -C oracle/refbuild; only possible where the reference sources are."""
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "refbuild"), "REF=" + REF_ROOT], stdout=subprocess.DEVNULL)
+    return PATH
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "src")) or os.path.exists(PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        O.lib()
+        if os.path.isdir(os.path.join(REF_ROOT, "src")):
+            build()
+        if not os.path.exists(PATH):
+            raise RuntimeError("oracle/_ref/libviorb_ref.so is missing and %s is not here to build it from" % REF_ROOT)
+        _lib = RefLib(PATH)
+        _lib._l.ref_arena_overflows.restype = C.c_long
+    return _lib
+
+
+def set_allocator(mode):
+    """0 = process allocator, 1 = ascending addresses (the oracle's convention), 2 = descending addresses"""
+    lib()._l.ref_set_allocator(int(mode))
+
+
+def set_gaussian_variant(variant):
+    """0 = OpenCV >= 3.4 taps, 1 = OpenCV 2.4 taps (the version the reference pins)"""
+    lib()._l.ref_set_gaussian_variant(int(variant))
+
+
+def arena_overflows():
+    return int(lib()._l.ref_arena_overflows())

@@ -6,43 +6,21 @@ import sys
 import numpy as np
 
 sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
 from oracle import oracle_py as O  # noqa: E402
-from viorb_b200 import api, synth  # noqa: E402
-
-
-def image(rng, h, w):
-    kind = rng.integers(0, 5)
-    if kind == 0:
-        return synth.frame(h, w, int(rng.integers(0, 1 << 30)))
-    if kind == 1:
-        return rng.integers(0, 256, (h, w)).astype(np.uint8)                       # pure noise: every pixel a corner
-    if kind == 2:
-        img = synth.frame(h, w, int(rng.integers(0, 1 << 30))).astype(np.int32)
-        return np.clip((img - 128) * 0.15 + 128, 0, 255).astype(np.uint8)            # low contrast: the 20 -> 7 retry
-    if kind == 3:
-        yy, xx = np.mgrid[0:h, 0:w]
-        s = int(rng.integers(3, 17))
-        return (((yy // s + xx // s) & 1) * int(rng.integers(30, 255))).astype(np.uint8)   # checkerboard
-    img = synth.frame(h, w, int(rng.integers(0, 1 << 30)))
-    img[:, : w // 2] = int(rng.integers(0, 256))                                     # half flat
-    return img
+from viorb_b200 import api  # noqa: E402
+from util import fuzz_extract_cases  # noqa: E402
 
 
 def main():
     cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     ctx = api.Context(0)
     bad = 0
     skipped = 0
     total_kp = 0
-    for c in range(cases):
-        h, w = int(rng.integers(96, 900)), int(rng.integers(128, 1400))
-        nl = int(rng.integers(2, 9))
-        sf = float(np.float32(rng.choice([1.1, 1.2, 1.2, 1.25, 1.33, 1.5])))
-        nf = int(rng.integers(100, 4000))
-        it = int(rng.integers(8, 128)) if rng.random() < 0.3 else int(rng.integers(8, 40))
-        mt = int(rng.integers(2, it + 1))
-        img = image(rng, h, w)
+    for c, img, (nf, sf, nl, it, mt) in fuzz_extract_cases(cases, seed):
+        h, w = img.shape
         try:
             ex = api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx)
             kg, dg = ex(img)

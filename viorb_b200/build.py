@@ -83,6 +83,15 @@ def build_oracle(force=False, march=None, outdir=None):
     return os.path.join(odir, outdir or "_build", "liborb_oracle.so")
 
 
+def build_reference_oracle(reference_root="/root/reference"):
+    """oracle/_ref/libviorb_ref.so: the reference's own sources compiled unmodified (oracle/refbuild/Makefile) -- the
+    checker's checker.  Only where the reference tree exists (the build container); returns None elsewhere."""
+    if not os.path.isdir(os.path.join(reference_root, "src")):
+        return None
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "refbuild"), "REF=" + reference_root], stdout=subprocess.DEVNULL)
+    return os.path.join(ROOT, "oracle", "_ref", "libviorb_ref.so")
+
+
 def build_all(force=False, verbose=False):
     return build_cuda(force, verbose), build_synth(force)
 

@@ -164,6 +164,8 @@ void build_tables(viorb_extractor* e) {
 /* geometry + cv::resize coefficient tables for a given image size */
 int build_geometry(viorb_extractor* e, int rows, int cols) {
     if (e->rows == rows && e->cols == cols) return VIORB_OK;
+    /* the cached size is only valid while e->geom is complete: a failing rebuild must not leave the old size behind */
+    e->rows = e->cols = 0;
     FrameGeom& g = e->geom;
     memset(&g, 0, sizeof(g));
     g.nlevels = e->nlevels; g.rows = rows; g.cols = cols; g.iniTh = e->iniTh; g.minTh = e->minTh;

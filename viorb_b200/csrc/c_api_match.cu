@@ -62,14 +62,19 @@ namespace {
 struct Arena {
     uint8_t* base = nullptr;
     size_t cap = 0, off = 0;
+    bool overflow = false;
+    /* returns NULL (and latches `overflow`) when the request does not fit: callers check ok() once after their takes */
     template <typename T>
     T* take(size_t n) {
         off = (off + 255) & ~(size_t)255;
+        if (off + n * sizeof(T) > cap) { overflow = true; return nullptr; }
         T* p = reinterpret_cast<T*>(base + off);
         off += n * sizeof(T);
         return p;
     }
+    bool ok() const { return !overflow; }
 };
+#define ARENA_CHECK(a) do { if (!(a).ok()) return viorb_fail(VIORB_ERR_CAPACITY, "%s: scratch arena under-sized (%zu B)", __func__, (a).cap); } while (0)
 
 size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -379,7 +384,7 @@ int viorb_search_by_projection_local(viorb_frame_index* fi, int32_t* frame_mp_ob
     if ((rc = viorb_ctx_bind(c))) return rc;
     const int nf = fi->n, nq = std::max(nmp, 1);
     Arena a;
-    if ((rc = search_common_alloc(c, nf, nmp, 5 * pad((size_t)nq * 4) + pad(nq) + pad((size_t)nq * 32), &a))) return rc;
+    if ((rc = search_common_alloc(c, nf, nmp, 6 * pad((size_t)nq * 4) + pad(nq) + pad((size_t)nq * 32), &a))) return rc;
     int* dobs = a.take<int>(std::max(nf, 1));
     int* dmin = a.take<int>(std::max(nf, 1));
     int* dmatch = a.take<int>(std::max(nf, 1));
