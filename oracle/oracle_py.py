@@ -330,16 +330,17 @@ def stereo_match(kl, dl, kr, dr, pyr_l, pyr_r, scale_factors, mbf, mb):
 class Grid:
     def __init__(self, kps_un, minx, maxx, miny, maxy):
         self.kps = _c(kps_un, KEYPOINT)
-        self.g = lib().orc_grid_create(_p(self.kps), len(self.kps), minx, maxx, miny, maxy)
+        self.L = lib()                      # the handle belongs to the library that made it (see using())
+        self.g = self.L.orc_grid_create(_p(self.kps), len(self.kps), minx, maxx, miny, maxy)
 
     def __del__(self):
         if getattr(self, "g", None):
-            lib().orc_grid_destroy(self.g)
+            self.L.orc_grid_destroy(self.g)
             self.g = None
 
     def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
         out = np.zeros(len(self.kps) + 1, np.int32)
-        n = lib().orc_grid_features_in_area(self.g, x, y, r, min_level, max_level, _p(out), len(out))
+        n = self.L.orc_grid_features_in_area(self.g, x, y, r, min_level, max_level, _p(out), len(out))
         return out[:n]
 
 
@@ -351,7 +352,7 @@ def search_by_projection_local(grid, fdesc, fu_right, frame_mp_obs, scale_factor
     match = np.full(len(grid.kps), -1, i32)
     args = [_c(a, t) for a, t in ((fu_right, f32), (scale_factors, f32), (proj_x, f32), (proj_y, f32), (proj_xr, f32),
                                   (pred_level, i32), (view_cos, f32), (valid, u8), (mp_nobs, i32))]
-    n = lib().orc_search_by_projection_local(grid.g, _p(grid.kps), _p(fdesc), _p(args[0]), _p(obs), len(grid.kps),
+    n = grid.L.orc_search_by_projection_local(grid.g, _p(grid.kps), _p(fdesc), _p(args[0]), _p(obs), len(grid.kps),
                                              _p(args[1]), _p(args[2]), _p(args[3]), _p(args[4]), _p(args[5]),
                                              _p(args[6]), _p(args[7]), _p(args[8]), _p(mpdesc), len(mpdesc),
                                              th, nnratio, _p(match))
@@ -366,7 +367,7 @@ def search_by_projection_frame(grid, fdesc, fu_right, frame_mp_obs, scale_factor
     match = np.full(len(grid.kps), -1, i32)
     a = [_c(x, t) for x, t in ((fu_right, f32), (scale_factors, f32), (u, f32), (v, f32), (invz, f32),
                                (last_octave, i32), (last_angle, f32), (valid, u8), (mp_nobs, i32))]
-    n = lib().orc_search_by_projection_frame(grid.g, _p(grid.kps), _p(fdesc), _p(a[0]), _p(obs), len(grid.kps),
+    n = grid.L.orc_search_by_projection_frame(grid.g, _p(grid.kps), _p(fdesc), _p(a[0]), _p(obs), len(grid.kps),
                                              _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), _p(a[7]),
                                              _p(a[8]), _p(mpdesc), len(mpdesc), th, mbf, mode, int(check_ori),
                                              th_high, _p(match))
@@ -409,11 +410,12 @@ class Vocabulary:
 
     def __init__(self, k, L, parent, node_desc, node_weight, weighting=0, scoring=0):
         par, d, w = _c(parent, np.int32), _c(node_desc, np.uint8), _c(node_weight, np.float64)
-        self.h = lib().orc_vocabulary_create(k, L, weighting, scoring, len(par), _p(par), _p(d), _p(w))
+        self.L = lib()
+        self.h = self.L.orc_vocabulary_create(k, L, weighting, scoring, len(par), _p(par), _p(d), _p(w))
 
     def __del__(self):
         try:
-            lib().orc_vocabulary_destroy(self.h)
+            self.L.orc_vocabulary_destroy(self.h)
         except Exception:
             pass
 
@@ -424,7 +426,7 @@ class Vocabulary:
         fvn, fvp, fvi = np.zeros(max(n, 1), np.int32), np.zeros(n + 1, np.int32), np.zeros(max(n, 1), np.int32)
         wo, no = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
         nf = C.c_int()
-        nb = lib().orc_bow_transform(self.h, _p(d), n, levelsup, _p(ids), _p(vals), _p(fvn), _p(fvp), _p(fvi), C.byref(nf),
+        nb = self.L.orc_bow_transform(self.h, _p(d), n, levelsup, _p(ids), _p(vals), _p(fvn), _p(fvp), _p(fvi), C.byref(nf),
                                      _p(wo), _p(no))
         nfv = nf.value
         return ((ids[:nb], vals[:nb]), (fvn[:nfv], fvp[:nfv + 1], fvi[:fvp[nfv] if nfv else 0]), wo[:n], no[:n])
@@ -449,7 +451,7 @@ def search_for_initialization(grid2, d2, k1, d1, prev, window, nnratio, check_or
     k1, d1, d2 = _c(k1, KEYPOINT), _c(d1, u8), _c(d2, u8)
     prev = np.ascontiguousarray(prev, np.float32).copy()
     m12 = np.full(len(k1), -1, i32)
-    n = lib().orc_search_for_initialization(grid2.g, _p(grid2.kps), _p(d2), len(grid2.kps), _p(k1), _p(d1), len(k1), _p(prev),
+    n = grid2.L.orc_search_for_initialization(grid2.g, _p(grid2.kps), _p(d2), len(grid2.kps), _p(k1), _p(d1), len(k1), _p(prev),
                                             int(window), nnratio, int(check_ori), _p(m12))
     return n, m12, prev
 
@@ -481,7 +483,7 @@ def search_window_top1(grid, kdesc, u_right, scale_factors, u, v, ur, pred_level
     urr = _c(ur, f32) if ur is not None else None
     inv = _c(inv_level_sigma2, f32) if inv_level_sigma2 is not None else None
     bi, bd = np.full(n, -1, i32), np.zeros(n, i32)
-    lib().orc_search_window_top1(grid.g, _p(grid.kps), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(urr), _p(a[5]),
+    grid.L.orc_search_window_top1(grid.g, _p(grid.kps), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(urr), _p(a[5]),
                                  _p(a[6]), _p(a[7]), n, th, th_dist, _p(inv), _p(bi), _p(bd))
     return bi, bd
 
@@ -494,7 +496,7 @@ def search_by_sim3(g1, d1, sf1, g2, d2, sf2, q12, q21, th):
     a, b = prep(q12), prep(q21)
     d1, d2, sf1, sf2 = _c(d1, u8), _c(d2, u8), _c(sf1, f32), _c(sf2, f32)
     m = np.full(len(g1.kps), -1, i32)
-    n = lib().orc_search_by_sim3(g1.g, _p(g1.kps), _p(d1), _p(sf1), len(g1.kps), g2.g, _p(g2.kps), _p(d2), _p(sf2), len(g2.kps),
+    n = g1.L.orc_search_by_sim3(g1.g, _p(g1.kps), _p(d1), _p(sf1), len(g1.kps), g2.g, _p(g2.kps), _p(d2), _p(sf2), len(g2.kps),
                                  _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(b[0]), _p(b[1]), _p(b[2]), _p(b[3]),
                                  _p(b[4]), th, _p(m))
     return n, m

@@ -14,6 +14,17 @@ def flip_bits(desc, rng, max_flips):
     return out
 
 
+def snap_projection(u, v, invz):
+    """(u, v, 1/z) that a camera with identity pose and unit intrinsics reproduces exactly from a float world point:
+    Z = float(1/invz), 1/z = float(1/Z), X = float(u / (1/z)), u = float(X * (1/z)).  The adapters that drive the reference's
+    own SearchByProjection overloads (oracle/refbuild/ref_matcher_capi.cpp) can only be given such projections."""
+    f32 = np.float32
+    Z = (1.0 / invz.astype(np.float64)).astype(f32)
+    iz = (1.0 / Z.astype(np.float64)).astype(f32)
+    X, Y = (u.astype(f32) / iz).astype(f32), (v.astype(f32) / iz).astype(f32)
+    return (X * iz).astype(f32), (Y * iz).astype(f32), iz
+
+
 def projection_scenario(kps, desc, scale_factors, seed, n_mp=600, conflicts=60):
     """A current frame (kps/desc) and a set of map points projecting near its keypoints.
     Returns dict of arrays for SearchByProjection (local) and (frame) variants."""
@@ -33,12 +44,14 @@ def projection_scenario(kps, desc, scale_factors, seed, n_mp=600, conflicts=60):
     u_right = np.where(rng.random(n) < 0.5, kps["x"] - rng.uniform(2, 60, n), -1).astype(np.float32)
     proj_xr = (px - (kps["x"][pick] - u_right[pick]) + rng.normal(0, 3.0, n_mp)).astype(np.float32)
     obs0 = (rng.random(n) < 0.1).astype(np.int32) * 2
+    valid = (rng.random(n_mp) < 0.9).astype(np.uint8)
+    nobs = rng.integers(0, 4, n_mp).astype(np.int32)
+    invz = rng.uniform(0.02, 0.5, n_mp).astype(np.float32)
+    px, py, invz = snap_projection(px.astype(np.float32), py.astype(np.float32), invz)
     return dict(
-        proj_x=px.astype(np.float32), proj_y=py.astype(np.float32), proj_xr=proj_xr,
+        proj_x=px, proj_y=py, proj_xr=proj_xr,
         pred_level=pred, view_cos=rng.uniform(0.99, 1.0, n_mp).astype(np.float32),
-        valid=(rng.random(n_mp) < 0.9).astype(np.uint8), nobs=rng.integers(0, 4, n_mp).astype(np.int32),
-        mp_desc=mp_desc, u_right=u_right, obs0=obs0,
-        invz=rng.uniform(0.02, 0.5, n_mp).astype(np.float32), last_octave=octave.astype(np.int32),
+        valid=valid, nobs=nobs, mp_desc=mp_desc, u_right=u_right, obs0=obs0, invz=invz, last_octave=octave.astype(np.int32),
         last_angle=(kps["angle"][pick] + rng.choice([0.0, 0.0, 0.0, 90.0, 200.0], n_mp) +
                     rng.normal(0, 3, n_mp)).astype(np.float32) % np.float32(360.0))
 

@@ -15,20 +15,34 @@
 
 #include <cmath>
 #include <map>
+#include <mutex>
 #include <set>
 #include <vector>
 
 #include "cv_compat.h"
 
+#ifndef VIORB_HAVE_DBOW2          /* defined when the real Thirdparty/DBoW2 headers are on the include path */
 namespace DBoW2 {
 typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;   /* Thirdparty/DBoW2/DBoW2/FeatureVector.h */
 typedef std::map<unsigned int, double> BowVector;                          /* Thirdparty/DBoW2/DBoW2/BowVector.h:56-57 */
 }
+#endif
+
+#define FRAME_GRID_ROWS 48        /* include/Frame.h:41-42 */
+#define FRAME_GRID_COLS 64
 
 namespace ORB_SLAM2 {
 
 class ORBextractor;
 class KeyFrame;
+class Frame;
+
+/* the reference guards these members with std::mutex; the stand-ins stay copyable */
+struct CompatMutex : std::mutex {
+    CompatMutex() {}
+    CompatMutex(const CompatMutex&) {}
+    CompatMutex& operator=(const CompatMutex&) { return *this; }
+};
 
 class MapPoint {   /* include/MapPoint.h */
 public:
@@ -59,6 +73,16 @@ public:
     cv::Mat GetDescriptor() const { return descriptor; }
     cv::Mat GetWorldPos() const { return worldPos; }
     cv::Mat GetNormal() const { return normal; }
+    CompatMutex mMutexPos, mMutexFeatures;
+#ifdef VIORB_REF_MEMBERS        /* oracle/refbuild: the bodies are the reference's own source lines (src/MapPoint.cc) */
+    float GetMinDistanceInvariance();
+    float GetMaxDistanceInvariance();
+    int PredictScale(const float& currentDist, KeyFrame* pKF);
+    int PredictScale(const float& currentDist, Frame* pF);
+    void ComputeDistinctiveDescriptors();       /* src/MapPoint.cc:249-314 */
+    cv::Mat mDescriptor;                        /* written by ComputeDistinctiveDescriptors */
+    bool mbBad = false;
+#else
     float GetMinDistanceInvariance() const { return 0.8f * mfMinDistance; }     /* src/MapPoint.cc:380-384 */
     float GetMaxDistanceInvariance() const { return 1.2f * mfMaxDistance; }     /* :386-390 */
     template <class FrameOrKeyFrame>
@@ -69,6 +93,7 @@ public:
         else if (nScale >= pF->mnScaleLevels) nScale = pF->mnScaleLevels - 1;
         return nScale;
     }
+#endif
 };
 
 class Frame {      /* include/Frame.h */
@@ -98,6 +123,9 @@ public:
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
                                           const int maxLevel = -1) const;      /* :507-560 -> viorb_frame_features_in_area */
     void ComputeStereoMatches();               /* src/Frame.cc:646-820 -> viorb_stereo_match */
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);     /* :562-572 */
+    bool isInFrustum(MapPoint* pMP, float viewingCosLimit);            /* :449-505, fills the mTrack* fields read by :45-129 */
+    cv::Mat mRcw, mtcw, mOw;                   /* pose parts read by isInFrustum (Frame::UpdatePoseMatrices, :441-447) */
 };
 
 class KeyFrame {   /* include/KeyFrame.h */
@@ -130,7 +158,14 @@ public:
     bool IsInImage(const float& x, const float& y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }
     cv::Mat GetCameraCenter() const { return Ow; }
     cv::Mat GetRotation() const { return Rcw; }
+    bool mbBad = false;
+    bool isBad() const { return mbBad; }
     cv::Mat GetTranslation() const { return tcw; }
+    /* grid copied from the Frame the key frame was made of (src/KeyFrame.cc:301-306) and its window query (:906-945) */
+    int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    std::vector<std::vector<std::vector<size_t> > > mGrid;
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const;
 };
 
 inline void MapPoint::Replace(MapPoint* pMP) {
