@@ -26,7 +26,62 @@ def build_exe():
     return EXE
 
 
+POSE_EXE = os.path.join(ROOT, "tests", "cpp", "_build", "pose_driver")
+POSE_REF = os.path.join(ROOT, "oracle", "_ref", "pose_driver_ref")
+POSE_GOLD = os.path.join(ROOT, "tests", "golden", "ref_pose_driver.txt")
+
+
+def build_pose_driver():
+    """tests/cpp/pose_driver.cc against the product's drop-in classes"""
+    from viorb_b200 import build
+    lib = build.build_cuda()
+    os.makedirs(os.path.dirname(POSE_EXE), exist_ok=True)
+    libdir = os.path.dirname(lib)
+    subprocess.check_call([build.CXX, "-O1", "-std=gnu++17", "-I", os.path.join(ROOT, "viorb_b200", "host"), "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "pose_driver.cc"), "-o", POSE_EXE, "-L", libdir, "-lviorb_b200",
+                           "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"])
+    return POSE_EXE
+
+
+def write_pose_keys(path):
+    """keypoints + descriptors of the synthetic KITTI-shape pair (BASELINE configs[1]) from the CPU oracle"""
+    import numpy as np
+    from oracle import oracle_py as O
+    from util import CONFIGS
+    from viorb_b200 import synth
+    h, w, nf, sf, nl, it, mt = CONFIGS["kitti"]
+    left, right, _ = synth.stereo_pair(h, w, 7)
+    with open(path, "wb") as f:
+        for img in (left, right):
+            k, d = O.Extractor(nf, sf, nl, it, mt)(img)
+            f.write(np.int32(len(k)).tobytes())
+            f.write(k.tobytes())
+            f.write(np.ascontiguousarray(d).tobytes())
+
+
+def test_reference_pose_driver_matches_committed_output(tmp_path):
+    """the reference build of tests/cpp/pose_driver.cc (src/ORBmatcher.cc compiled unmodified) reproduces the committed
+    tests/golden/ref_pose_driver.txt -- the file the GPU test compares the product against where the binary is absent"""
+    if not os.path.exists(POSE_REF):
+        import pytest
+        pytest.skip("oracle/_ref/pose_driver_ref not built (no /root/reference here)")
+    keys, out = str(tmp_path / "keys.bin"), str(tmp_path / "ref.txt")
+    write_pose_keys(keys)
+    subprocess.check_call([POSE_REF, keys, out])
+    got = open(out).read()
+    assert got == open(POSE_GOLD).read()
+    # the scenarios must really exercise the searches
+    counts = {}
+    for line in got.splitlines():
+        t = line.split()
+        if len(t) > 3 and t[-2] == "n":
+            counts.setdefault(t[0], []).append(int(t[-1]))
+    for name in ("last_frame", "reloc", "sim3_projection", "fuse", "fuse_sim3", "search_by_sim3", "triangulation"):
+        assert min(counts[name]) > 20, (name, counts[name])
+
+
 def test_shims_compile_and_link():
+    build_pose_driver()
     exe = build_exe()
     assert os.path.exists(exe)
     # the library exports the reference's C++ entry points (mangled names of SURVEY.md section 8(b), modulo cv::Mat
@@ -47,6 +102,35 @@ def test_shims_compile_and_link():
                 "ORB_SLAM2::ORBVocabulary::loadFromTextFile(", "ORB_SLAM2::ORBVocabulary::transform(",
                 "ORB_SLAM2::Frame::ComputeStereoMatches()"):
         assert sym in out, sym
+    # ... and under exactly the mangled names the reference's libORB_SLAM2.so exports
+    raw = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "viorb_b200", "lib", "libviorb_b200.so")], text=True)
+    for sym in ("_ZN9ORB_SLAM212ORBextractorC1Eifiii",
+                "_ZN9ORB_SLAM212ORBextractorclERKN2cv11_InputArrayES4_RSt6vectorINS1_8KeyPointESaIS6_EERKNS1_12_OutputArrayE",
+                "_ZN9ORB_SLAM210ORBmatcherC1Efb", "_ZN9ORB_SLAM210ORBmatcher18DescriptorDistanceERKN2cv3MatES4_",
+                "_ZN9ORB_SLAM210ORBmatcher22SearchForTriangulationEPNS_8KeyFrameES2_N2cv3MatERSt6vectorISt4pairImmESaIS7_EEb",
+                "_ZN9ORB_SLAM25Frame20ComputeStereoMatchesEv"):
+        assert sym in raw, sym
+
+
+@pytest.mark.gpu
+def test_shims_match_reference_on_general_poses(tmp_path):
+    """The CUDA drop-in classes and the REFERENCE's own ORBmatcher.cc, driven by the same source (tests/cpp/pose_driver.cc)
+    through the overloads that project map points themselves -- general poses, Sim3 transforms, both Fuse overloads with
+    their map-graph bookkeeping, SearchBySim3, SearchForTriangulation -- must print identical results."""
+    exe = build_pose_driver()
+    keys, out = str(tmp_path / "keys.bin"), str(tmp_path / "gpu.txt")
+    write_pose_keys(keys)
+    p = subprocess.run([exe, keys, out], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    got = open(out).read().splitlines()
+    want = open(POSE_GOLD).read().splitlines()
+    if os.path.exists(POSE_REF):                     # the prebuilt reference binary travels with the snapshot: run it live too
+        ref_out = str(tmp_path / "ref.txt")
+        subprocess.check_call([POSE_REF, keys, ref_out])
+        assert open(ref_out).read().splitlines() == want
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a == b, "first difference:\n  gpu: %s\n  ref: %s" % (a[:300], b[:300])
 
 
 @pytest.mark.gpu

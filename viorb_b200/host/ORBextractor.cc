@@ -15,7 +15,7 @@ static void check(int rc, const char* what) {
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
-      mpCtx(nullptr), mpHandle(nullptr), mbDownloadPyramid(true) {
+      mvImagePyramid(this), mpCtx(nullptr), mpHandle(nullptr), mbDownloadPyramid(false), mbPyramidStale(false) {
     check(viorb_ctx_create(0, nullptr, &mpCtx), "viorb_ctx_create");
     check(viorb_extractor_create(mpCtx, nfeatures, _scaleFactor, nlevels, iniThFAST, minThFAST, &mpHandle), "viorb_extractor_create");
     mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);
@@ -24,7 +24,7 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     int n = 0;
     check(viorb_extractor_tables(mpHandle, &n, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
                                  mvInvLevelSigma2.data(), mnFeaturesPerLevel.data()), "viorb_extractor_tables");
-    mvImagePyramid.resize(nlevels);
+    mvRoiLevels.resize(nlevels);
     mvPaddedLevels.resize(nlevels);
 }
 
@@ -33,9 +33,10 @@ ORBextractor::~ORBextractor() {
     viorb_ctx_destroy(mpCtx);
 }
 
-void ORBextractor::operator()(cv::InputArray image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& _keypoints,
+void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& _keypoints,
                               cv::OutputArray _descriptors) {
-    if (image.empty()) return;                                   /* reference :1046-1047 */
+    if (_image.empty()) return;                                  /* reference :1046-1047 */
+    const cv::Mat image = _image.getMat();
     assert(image.type() == CV_8UC1);                             /* reference :1050 */
     const int cap = nfeatures + 8 * nlevels + 64;                /* the quadtree may overshoot nfeatures by a few */
     _keypoints.resize(cap);
@@ -48,17 +49,24 @@ void ORBextractor::operator()(cv::InputArray image, cv::InputArray /*mask*/, std
     if (n == 0) _descriptors.release();                          /* reference :1064-1065 */
     else {
         _descriptors.create(n, 32, CV_8U);
-        memcpy(_descriptors.data, desc.data, (size_t)n * 32);
+        cv::Mat out = _descriptors.getMat();
+        for (int i = 0; i < n; i++) memcpy(out.ptr<unsigned char>(i), desc.ptr<unsigned char>(i), 32);
     }
-    if (mbDownloadPyramid) {
-        for (int l = 0; l < nlevels; l++) {
-            int w = 0, h = 0;
-            check(viorb_extractor_pyramid_info(mpHandle, l, &w, &h), "viorb_extractor_pyramid_info");
-            mvPaddedLevels[l].create(h + 38, w + 38, CV_8U);
-            check(viorb_extractor_pyramid_download(mpHandle, 0, l, mvPaddedLevels[l].data, mvPaddedLevels[l].step), "pyramid download");
-            mvImagePyramid[l] = mvPaddedLevels[l].roi(19, 19, w, h);
-        }
+    mbPyramidStale = true;
+    if (mbDownloadPyramid) SyncPyramid();
+}
+
+/* host copy of the padded levels of the last call (reference ComputePyramid :1107-1132 leaves them in mvImagePyramid) */
+void ORBextractor::SyncPyramid() {
+    if (!mbPyramidStale) return;
+    for (int l = 0; l < nlevels; l++) {
+        int w = 0, h = 0;
+        check(viorb_extractor_pyramid_info(mpHandle, l, &w, &h), "viorb_extractor_pyramid_info");
+        mvPaddedLevels[l].create(h + 38, w + 38, CV_8U);
+        check(viorb_extractor_pyramid_download(mpHandle, 0, l, mvPaddedLevels[l].data, mvPaddedLevels[l].step), "pyramid download");
+        mvRoiLevels[l] = mvPaddedLevels[l](cv::Rect(19, 19, w, h));
     }
+    mbPyramidStale = false;
 }
 
 void ORBextractor::ExtractBatch(const std::vector<cv::Mat>& images, std::vector<std::vector<cv::KeyPoint> >& keypoints,

@@ -35,11 +35,24 @@ public:
     std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
     std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
-    /* ROI views into padded (border 19) level images, as in the reference.  Downloaded after every call while
-     * SetPyramidDownload(true) (default); the device copy stays resident either way and is what the GPU
-     * ComputeStereoMatches reads. */
-    std::vector<cv::Mat> mvImagePyramid;
+    /* mvImagePyramid[l]: ROI view into the padded (border 19) level image, as in the reference (include/ORBextractor.h:85).
+     * The levels live on the device (that copy is what the GPU ComputeStereoMatches reads); the host copy is fetched
+     * lazily, on the first mvImagePyramid[l] after a call, so callers that never look at it (monocular tracking) pay
+     * nothing.  Source compatible with the reference's std::vector<cv::Mat> for what Frame.cc does with it:
+     * operator[], size(). */
+    class LazyPyramid {
+    public:
+        explicit LazyPyramid(ORBextractor* owner = nullptr) : mpOwner(owner) {}
+        const cv::Mat& operator[](size_t level) const { mpOwner->SyncPyramid(); return mpOwner->mvRoiLevels[level]; }
+        size_t size() const { return mpOwner->mvRoiLevels.size(); }
+        void resize(size_t) {}
+    private:
+        ORBextractor* mpOwner;
+    };
+    LazyPyramid mvImagePyramid;
+    /* true: fetch the host copy inside every operator() (the reference's timing behaviour); default false = lazy */
     void SetPyramidDownload(bool on) { mbDownloadPyramid = on; }
+    void SyncPyramid();
 
     /* B200 extension: the same operator over a batch of equally sized frames (one device pass per 128 frames) */
     void ExtractBatch(const std::vector<cv::Mat>& images, std::vector<std::vector<cv::KeyPoint> >& keypoints,
@@ -59,8 +72,10 @@ protected:
 
     viorb_ctx* mpCtx;
     viorb_extractor* mpHandle;
-    bool mbDownloadPyramid;
-    std::vector<cv::Mat> mvPaddedLevels;
+    bool mbDownloadPyramid, mbPyramidStale;
+    std::vector<cv::Mat> mvPaddedLevels, mvRoiLevels;
+    ORBextractor(const ORBextractor&);              /* owns device state: not copyable (the reference's is never copied) */
+    ORBextractor& operator=(const ORBextractor&);
 };
 
 }  // namespace ORB_SLAM2

@@ -17,6 +17,45 @@ const int ORBmatcher::HISTO_LENGTH = 30;
 
 namespace {
 
+/* OpenCV's arithmetic for the 3x3 / 3x1 CV_32F expressions of src/ORBmatcher.cc.  Each convention is pinned on the real
+ * cv::gemm / cv::norm (python cv2) by tests/test_ref_minicv.py and on the reference compiled against those conventions by
+ * tests/test_cpp_shims.py:
+ *   R*x + t         one gemm, the hand-unrolled block of core/matmul.cpp: float products summed left to right, then + t
+ *                   (written inline below as  R[0]*X + R[1]*Y + R[2]*Z + t[0]  -- same operations in the same order);
+ *   -R.t()*t        gemm with GEMM_1_T and alpha = -1: products and the running sum in double, rounded once;
+ *   M/s             MatExpr operator/ scales by 1./s: every element is multiplied by (float)(1./s), not divided;
+ *   a.dot(b)        double products summed in double;  cv::norm(a) = sqrt of that in double. */
+inline void neg_transpose_mul(const float R[9], const float t[3], float out[3]) {
+    for (int r = 0; r < 3; r++) {
+        double s = 0;
+        s += (double)R[r] * (double)t[0];
+        s += (double)R[3 + r] * (double)t[1];
+        s += (double)R[6 + r] * (double)t[2];
+        out[r] = (float)(s * -1.0);
+    }
+}
+inline float reciprocal_scale(float s) { return (float)(1. / (double)s); }
+inline double dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    double r = 0;
+    r += (double)ax * (double)bx;
+    r += (double)ay * (double)by;
+    r += (double)az * (double)bz;
+    return r;
+}
+inline float norm3(float x, float y, float z) { return (float)std::sqrt(dot3(x, y, z, x, y, z)); }
+
+/* ORBmatcher::DescriptorDistance, reference src/ORBmatcher.cc:1648-1664: the same eight 32-bit words, hardware popcount */
+inline int hamming256(const unsigned char* a, const unsigned char* b) {
+    int dist = 0;
+    for (int i = 0; i < 4; i++) {
+        unsigned long long x, y;
+        memcpy(&x, a + 8 * i, 8);
+        memcpy(&y, b + 8 * i, 8);
+        dist += __builtin_popcountll(x ^ y);
+    }
+    return dist;
+}
+
 void check(int rc, const char* what) {
     if (rc != VIORB_OK) throw std::runtime_error(std::string(what) + ": " + viorb_last_error());
 }
@@ -66,10 +105,11 @@ void flatten(const DBoW2::FeatureVector& fv, std::vector<int32_t>& ids, std::vec
 
 ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
 
+/* One pair is 32 bytes: the reference calls this inside O(N^2) host loops (MapPoint::ComputeDistinctiveDescriptors,
+ * src/MapPoint.cc:289), where a device round trip per pair would cost four orders of magnitude more than the popcounts.
+ * Batches go to the GPU through DescriptorDistances / viorb_descriptor_distance / viorb_distinctive_descriptors. */
 int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
-    int32_t d = 0;
-    check(viorb_descriptor_distance(thread_ctx(), a.ptr<uint8_t>(), b.ptr<uint8_t>(), 1, &d), "viorb_descriptor_distance");
-    return d;
+    return hamming256(a.ptr<unsigned char>(), b.ptr<unsigned char>());
 }
 
 std::vector<int> ORBmatcher::DescriptorDistances(const cv::Mat& a, const cv::Mat& b) {
@@ -113,7 +153,7 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
         for (int c = 0; c < 3; c++) Rcw[3 * r + c] = Tcw.at<float>(r, c);
         tcw[r] = Tcw.at<float>(r, 3);
     }
-    for (int r = 0; r < 3; r++) twc[r] = -(Rcw[r] * tcw[0] + Rcw[3 + r] * tcw[1] + Rcw[6 + r] * tcw[2]);
+    neg_transpose_mul(Rcw, tcw, twc);                                                    /* -Rcw.t()*tcw, :1341 */
     for (int r = 0; r < 3; r++)
         tlc[r] = Tlw.at<float>(r, 0) * twc[0] + Tlw.at<float>(r, 1) * twc[1] + Tlw.at<float>(r, 2) * twc[2] + Tlw.at<float>(r, 3);
     const bool bForward = tlc[2] > CurrentFrame.mb && !bMono;
@@ -171,7 +211,7 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std
         for (int c = 0; c < 3; c++) Rcw[3 * r + c] = Tcw.at<float>(r, c);
         tcw[r] = Tcw.at<float>(r, 3);
     }
-    for (int r = 0; r < 3; r++) Ow[r] = -(Rcw[r] * tcw[0] + Rcw[3 + r] * tcw[1] + Rcw[6 + r] * tcw[2]);
+    neg_transpose_mul(Rcw, tcw, Ow);                                                     /* Ow = -Rcw.t()*tcw */
     const std::vector<MapPoint*> vpMPs = pKF->GetMapPointMatches();
     const int nq = (int)vpMPs.size();
     std::vector<float> u(nq), v(nq), invz(nq), ang(nq);
@@ -190,7 +230,7 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std
         if (uu < CurrentFrame.mnMinX || uu > CurrentFrame.mnMaxX) continue;
         if (vv < CurrentFrame.mnMinY || vv > CurrentFrame.mnMaxY) continue;
         const float px = X - Ow[0], py = Y - Ow[1], pz = Z - Ow[2];
-        const float dist3D = (float)std::sqrt((double)px * px + (double)py * py + (double)pz * pz);     /* cv::norm */
+        const float dist3D = norm3(px, py, pz);     /* cv::norm */
         if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
         u[i] = uu; v[i] = vv; invz[i] = invzc;
         lvl[i] = pMP->PredictScale(dist3D, &CurrentFrame);
@@ -217,10 +257,11 @@ int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector
     float sR[9], Rcw[9], tcw[3], Ow[3];
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) sR[3 * r + c] = Scw.at<float>(r, c);
-    const float scw = (float)std::sqrt((double)sR[0] * sR[0] + (double)sR[1] * sR[1] + (double)sR[2] * sR[2]);
-    for (int i = 0; i < 9; i++) Rcw[i] = sR[i] / scw;
-    for (int r = 0; r < 3; r++) tcw[r] = Scw.at<float>(r, 3) / scw;
-    for (int r = 0; r < 3; r++) Ow[r] = -(Rcw[r] * tcw[0] + Rcw[3 + r] * tcw[1] + Rcw[6 + r] * tcw[2]);
+    const float scw = (float)std::sqrt(dot3(sR[0], sR[1], sR[2], sR[0], sR[1], sR[2]));
+    const float iscw = reciprocal_scale(scw);                                            /* sRcw/scw scales by 1./scw */
+    for (int i = 0; i < 9; i++) Rcw[i] = sR[i] * iscw;
+    for (int r = 0; r < 3; r++) tcw[r] = Scw.at<float>(r, 3) * iscw;
+    neg_transpose_mul(Rcw, tcw, Ow);                                                     /* Ow = -Rcw.t()*tcw */
     std::set<MapPoint*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
     spAlreadyFound.erase(static_cast<MapPoint*>(nullptr));
     const int nq = (int)vpPoints.size();
@@ -240,10 +281,10 @@ int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector
         const float uu = pKF->fx * (xc * iz) + pKF->cx, vv = pKF->fy * (yc * iz) + pKF->cy;
         if (!pKF->IsInImage(uu, vv)) continue;
         const float px = X - Ow[0], py = Y - Ow[1], pz = Z - Ow[2];
-        const float dist = (float)std::sqrt((double)px * px + (double)py * py + (double)pz * pz);
+        const float dist = norm3(px, py, pz);
         if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) continue;
         const cv::Mat Pn = pMP->GetNormal();
-        if (px * Pn.at<float>(0) + py * Pn.at<float>(1) + pz * Pn.at<float>(2) < 0.5 * dist) continue;   /* < 60 deg */
+        if (dot3(px, py, pz, Pn.at<float>(0), Pn.at<float>(1), Pn.at<float>(2)) < 0.5 * dist) continue;   /* < 60 deg */
         u[i] = uu; v[i] = vv;
         lvl[i] = pMP->PredictScale(dist, pKF);
         memcpy(&desc[(size_t)i * 32], pMP->GetDescriptor().ptr<uint8_t>(), 32);
@@ -400,7 +441,7 @@ void sim3_queries(const std::vector<MapPoint*>& pts, const std::vector<bool>& al
         const float x = b[0] * invz, y = b[1] * invz;
         const float uu = fx * x + cx, vv = fy * y + cy;
         if (!to->IsInImage(uu, vv)) continue;
-        const float dist3D = (float)std::sqrt((double)b[0] * b[0] + (double)b[1] * b[1] + (double)b[2] * b[2]);
+        const float dist3D = norm3(b[0], b[1], b[2]);
         if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
         q.u[i] = uu; q.v[i] = vv;
         q.lvl[i] = pMP->PredictScale(dist3D, to);
@@ -421,7 +462,7 @@ int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoin
         for (int c = 0; c < 3; c++) {
             R1w[3 * r + c] = mR1w.at<float>(r, c); R2w[3 * r + c] = mR2w.at<float>(r, c);
             sR12[3 * r + c] = s12 * R12.at<float>(r, c);                       /* :1119 */
-            sR21[3 * r + c] = (float)((1.0 / s12) * R12.at<float>(c, r));      /* :1120 */
+            sR21[3 * r + c] = R12.at<float>(c, r) * (float)(1.0 / s12);        /* :1120: transpose, then scale by (float)(1./s12) */
         }
     }
     for (int r = 0; r < 3; r++) t21[r] = -(sR21[3 * r] * t12f[0] + sR21[3 * r + 1] * t12f[1] + sR21[3 * r + 2] * t12f[2]);   /* :1121 */
@@ -475,22 +516,20 @@ int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, c
         if (!pKF->IsInImage(u, v)) return;
         const float ur = u - bf * invz;
         const float px = X - Ow[0], py = Y - Ow[1], pz = Z - Ow[2];
-        const float dist3D = (float)std::sqrt((double)px * px + (double)py * py + (double)pz * pz);
+        const float dist3D = norm3(px, py, pz);
         if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) return;
         const cv::Mat Pn = pMP->GetNormal();
-        if (px * Pn.at<float>(0) + py * Pn.at<float>(1) + pz * Pn.at<float>(2) < 0.5 * dist3D) return;
+        if (dot3(px, py, pz, Pn.at<float>(0), Pn.at<float>(1), Pn.at<float>(2)) < 0.5 * dist3D) return;
         q.u[i] = u; q.v[i] = v; q.ur[i] = ur;
         q.lvl[i] = pMP->PredictScale(dist3D, pKF);
         memcpy(&q.desc[(size_t)i * 32], pMP->GetDescriptor().ptr<uint8_t>(), 32);
         q.valid[i] = 1;
     };
     Queries q(nMPs);
-    std::vector<cv::Mat> descAtSearch(nMPs);
     for (int i = 0; i < nMPs; i++) {
         MapPoint* pMP = vpMapPoints[i];
         if (!pMP || pMP->isBad()) continue;
         project(pMP, q, i);
-        descAtSearch[i] = pMP->GetDescriptor();
     }
     FrameIndexGuard g;
     make_kf_index(pKF, g);
@@ -505,7 +544,7 @@ int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, c
         if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;                   /* :842-843, in loop order */
         int bestIdx = best[i];
         const cv::Mat dNow = pMP->GetDescriptor();
-        if (!q.valid[i] || dNow.data != descAtSearch[i].data || memcmp(dNow.ptr<uint8_t>(), &q.desc[(size_t)i * 32], 32) != 0) {
+        if (q.valid[i] && memcmp(dNow.ptr<uint8_t>(), &q.desc[(size_t)i * 32], 32) != 0) {
             /* an earlier Replace recomputed this point's descriptor (MapPoint.cc:221): search it again on its own */
             Queries q1(1);
             project(pMP, q1, 0);
@@ -536,10 +575,11 @@ int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& v
     float sR[9], Rcw[9], tcw[3], Ow[3];
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) sR[3 * r + c] = Scw.at<float>(r, c);
-    const float scw = (float)std::sqrt((double)sR[0] * sR[0] + (double)sR[1] * sR[1] + (double)sR[2] * sR[2]);     /* :989 */
-    for (int i = 0; i < 9; i++) Rcw[i] = sR[i] / scw;
-    for (int r = 0; r < 3; r++) tcw[r] = Scw.at<float>(r, 3) / scw;
-    for (int r = 0; r < 3; r++) Ow[r] = -(Rcw[r] * tcw[0] + Rcw[3 + r] * tcw[1] + Rcw[6 + r] * tcw[2]);
+    const float scw = (float)std::sqrt(dot3(sR[0], sR[1], sR[2], sR[0], sR[1], sR[2]));     /* :989 */
+    const float iscw = reciprocal_scale(scw);                                            /* sRcw/scw scales by 1./scw */
+    for (int i = 0; i < 9; i++) Rcw[i] = sR[i] * iscw;
+    for (int r = 0; r < 3; r++) tcw[r] = Scw.at<float>(r, 3) * iscw;
+    neg_transpose_mul(Rcw, tcw, Ow);                                                     /* Ow = -Rcw.t()*tcw */
     const std::set<MapPoint*> spAlreadyFound = pKF->GetMapPoints();                                                /* :995 */
     const int nPoints = (int)vpPoints.size();
     Queries q(nPoints);
@@ -555,10 +595,10 @@ int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& v
         const float u = pKF->fx * (p[0] * invz) + pKF->cx, v = pKF->fy * (p[1] * invz) + pKF->cy;
         if (!pKF->IsInImage(u, v)) continue;
         const float px = X - Ow[0], py = Y - Ow[1], pz = Z - Ow[2];
-        const float dist3D = (float)std::sqrt((double)px * px + (double)py * py + (double)pz * pz);
+        const float dist3D = norm3(px, py, pz);
         if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
         const cv::Mat Pn = pMP->GetNormal();
-        if (px * Pn.at<float>(0) + py * Pn.at<float>(1) + pz * Pn.at<float>(2) < 0.5 * dist3D) continue;
+        if (dot3(px, py, pz, Pn.at<float>(0), Pn.at<float>(1), Pn.at<float>(2)) < 0.5 * dist3D) continue;
         q.u[i] = u; q.v[i] = v;
         q.lvl[i] = pMP->PredictScale(dist3D, pKF);
         memcpy(&q.desc[(size_t)i * 32], pMP->GetDescriptor().ptr<uint8_t>(), 32);

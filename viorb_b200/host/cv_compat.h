@@ -29,6 +29,12 @@ struct Point2f {
     Point2f(float x_, float y_) : x(x_), y(y_) {}
 };
 
+struct Rect {
+    int x, y, width, height;
+    Rect() : x(0), y(0), width(0), height(0) {}
+    Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {}
+};
+
 struct KeyPoint {
     Point2f pt;
     float size, angle, response;
@@ -66,7 +72,7 @@ public:
         return m;
     }
     Mat row(int r) const { Mat m(*this); m.rows = 1; m.data = data + (size_t)r * step; return m; }
-    Mat roi(int x, int y, int w, int h) const { Mat m(*this); m.rows = h; m.cols = w; m.data = data + (size_t)y * step + (size_t)x * elemSize(); return m; }
+    Mat operator()(const Rect& r) const { Mat m(*this); m.rows = r.height; m.cols = r.width; m.data = data + (size_t)r.y * step + (size_t)r.x * elemSize(); return m; }
     template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
     template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
     template <typename T> T& at(int r, int c) { return ptr<T>(r)[c]; }
@@ -79,8 +85,30 @@ private:
     std::shared_ptr<std::vector<unsigned char> > buf_;
 };
 
-typedef const Mat& InputArray;
-typedef Mat& OutputArray;
+/* the proxies of core/mat.hpp: same class names (hence the same mangled operator() as the reference's library) and the
+ * members the shims call -- getMat / empty / type on inputs, create / release / getMat on outputs */
+class _InputArray {
+public:
+    _InputArray() : m_(nullptr) {}
+    _InputArray(const Mat& m) : m_(const_cast<Mat*>(&m)) {}
+    Mat getMat(int = -1) const { return m_ ? *m_ : Mat(); }
+    bool empty() const { return !m_ || m_->empty(); }
+    int type() const { return m_ ? m_->type() : 0; }
+
+protected:
+    Mat* m_;
+};
+class _OutputArray : public _InputArray {
+public:
+    _OutputArray() {}
+    _OutputArray(Mat& m) { m_ = &m; }
+    void create(int r, int c, int type) const {
+        if (m_ && !(m_->data && m_->rows == r && m_->cols == c && m_->type() == type)) m_->create(r, c, type);
+    }
+    void release() const { if (m_) m_->release(); }
+};
+typedef const _InputArray& InputArray;
+typedef const _OutputArray& OutputArray;
 
 }  // namespace cv
 #endif  /* VIORB_USE_OPENCV */
