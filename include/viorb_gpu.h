@@ -218,7 +218,10 @@ int viorb_search_by_projection_local(viorb_frame_index* fi, int32_t* frame_mp_ob
  *     nobs = 1 for every point (any assigned keypoint is skipped, :1541-1542);
  *   SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th)             :290-403 (loop closing):
  *     mode 3|8, th_high = TH_LOW, no orientation check, the frame index built from the KeyFrame's keypoints,
- *     frame_mp_obs[k] = (vpMatched[k] != NULL), nobs = 1.                                             */
+ *     frame_mp_obs[k] = (vpMatched[k] != NULL), nobs = 1.
+ * match[k] = index of the point assigned to keypoint k, -1 = untouched, -2 = assigned and then removed by the
+ * rotation-consistency check: the reference leaves such a slot NULL (:1460, :1586) even if it held a map point
+ * without observations before the call, so the caller must clear it.                                  */
 int viorb_search_by_projection_frame(viorb_frame_index* fi, int32_t* frame_mp_obs,
                                      const float* u, const float* v, const float* invz,
                                      const int32_t* last_octave, const float* last_angle,

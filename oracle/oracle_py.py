@@ -129,6 +129,15 @@ def _p(a):
     return a.ctypes.data if a is not None else None
 
 
+def _supported(n, what):
+    """adapters of oracle/refbuild return -2 / -3 for argument combinations that exist in no reference function
+    (e.g. the frame-to-frame overload with a threshold other than TH_HIGH): nothing to compare against"""
+    if n < 0 and _override is not None:
+        import pytest
+        pytest.skip("%s: no reference function takes this combination (adapter code %d)" % (what, n))
+    return n
+
+
 def _c(a, dtype=None):
     a = np.ascontiguousarray(a, dtype=dtype)
     return a
@@ -371,7 +380,7 @@ def search_by_projection_frame(grid, fdesc, fu_right, frame_mp_obs, scale_factor
                                              _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), _p(a[7]),
                                              _p(a[8]), _p(mpdesc), len(mpdesc), th, mbf, mode, int(check_ori),
                                              th_high, _p(match))
-    return n, match, obs
+    return _supported(n, "search_by_projection_frame"), match, obs
 
 
 def search_for_triangulation(k1, d1, ur1, has_mp1, k2, d2, ur2, has_mp2, fv1, fv2, F12, ex, ey, scale2, sigma2_2,

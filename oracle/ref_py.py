@@ -23,6 +23,11 @@ REF_ROOT = os.environ.get("VIORB_REFERENCE", "/root/reference")
 PATH = os.path.join(_HERE, "_ref", "libviorb_ref.so")
 
 
+_STATELESS = {"orc_hamming_top2", "orc_top2_merge", "orc_orientation_sweep", "orc_steering_sweep", "orc_sincosf", "orc_cv_round_f",
+              "orc_num_threads", "orc_resize_linear_u8", "orc_border_reflect101_u8", "orc_fast9_16", "orc_gaussian7_u8",
+              "orc_gaussian7_u8_variant", "orc_fast_atan2"}
+
+
 class RefLib:
     """Attribute orc_X resolves to the library's ref_X, typed like the oracle's orc_X."""
 
@@ -37,11 +42,17 @@ class RefLib:
             try:
                 f = getattr(self._l, "ref_" + name[4:])
             except AttributeError:
-                # the reference has no such function (the brute-force top-2 of BASELINE configs[4], debug sweeps,
-                # intermediate results the reference never stores): only the restatement can answer
                 if not self._fallback:
                     raise
-                f = o
+                if name in _STATELESS:
+                    # no counterpart in the reference (the brute-force top-2 of BASELINE configs[4] is not a reference
+                    # function; sweeps of single primitives): the restatement answers
+                    f = o
+                else:
+                    # handle-based entry points must never mix libraries: the calling test is skipped for this checker
+                    def f(*a, _n=name, **k):
+                        import pytest
+                        pytest.skip("the reference has no counterpart of %s" % _n)
             else:
                 f.argtypes, f.restype = o.argtypes, o.restype
             setattr(self, name, f)

@@ -8,11 +8,17 @@
 #include "minicv/minicv.hpp"
 
 #include "../orb_oracle.h"
+#include "minicv_hooks.h"
 
 namespace cv {
 
 static int g_gaussian_variant = 0;      /* 0 = OpenCV >= 3.4 fixed point taps, 1 = OpenCV 2.4 taps */
 void minicv_set_gaussian_variant(int v) { g_gaussian_variant = v; }
+
+/* optional record of every cv::FAST call (image origin, threshold, result): lets the test adapters reconstruct the
+ * candidate lists that ComputeKeyPointsOctTree keeps in a local variable (src/ORBextractor.cc:778, :822-825) */
+static thread_local std::vector<MinicvFastCall>* g_fast_log = nullptr;
+void minicv_set_fast_log(std::vector<MinicvFastCall>* log) { g_fast_log = log; }
 
 /* cv::gemm for the CV_32F shapes the reference produces (core/matmul.cpp).
  *  - flags == 0 and inner length 2..4: the hand-unrolled block -- float products summed left to right,
@@ -185,6 +191,15 @@ void FAST(InputArray image_, std::vector<KeyPoint>& keypoints, int threshold, bo
     const int n = orc_fast9_16(img.data, img.cols, img.rows, img.step, threshold, nms ? 1 : 0, c.data(), (int)c.size());
     keypoints.reserve(n);
     for (int i = 0; i < n; i++) keypoints.push_back(KeyPoint((float)c[i].x, (float)c[i].y, 7.f, -1, (float)c[i].score));
+    if (g_fast_log) {
+        std::vector<MinicvFastCall>* log = g_fast_log;
+        g_fast_log = nullptr;                       /* the record itself must not be logged or come from a test arena */
+        MinicvFastCall call;
+        call.origin = img.data; call.step = img.step; call.threshold = threshold;
+        call.corners.assign(c.begin(), c.begin() + n);
+        log->push_back(call);
+        g_fast_log = log;
+    }
 }
 
 float fastAtan2(float y, float x) { return orc_fast_atan2(y, x); }

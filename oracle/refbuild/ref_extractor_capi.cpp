@@ -23,7 +23,7 @@
 #include "ORBextractor.h"
 #include "../orb_oracle.h"
 
-namespace cv { void minicv_set_gaussian_variant(int v); }
+#include "minicv_hooks.h"
 
 /* ---------------------------------------------------------------------------------- allocator modes */
 #include <sys/mman.h>
@@ -137,6 +137,8 @@ public:
 struct RefExtractor {
     Probe* ex = nullptr;
     std::vector<std::vector<cv::KeyPoint> > levelKeys;      /* per level, level coordinates, list order */
+    std::vector<std::vector<orc_corner> > candidates;       /* per level, window coordinates, the order of vToDistributeKeys */
+    int retried = 0;
     Block* cur = nullptr;                                   /* holds mvImagePyramid of the last call */
     size_t blockBytes = (size_t)16 << 30;
 };
@@ -178,11 +180,41 @@ int ref_extract(RefExtractor* r, const uint8_t* img, int rows, int cols, size_t 
         }
         /* per-level keypoints before the final scaling: the reference's own stage method on the pyramid it just built */
         std::vector<std::vector<cv::KeyPoint> > all;
+        std::vector<MinicvFastCall> calls;
+        {
+            ArenaPause pause;
+            calls.reserve(1 << 16);
+        }
+        cv::minicv_set_fast_log(&calls);
         r->ex->ComputeKeyPointsOctTree(all);
+        cv::minicv_set_fast_log(nullptr);
         ArenaPause pause;
         std::vector<std::vector<cv::KeyPoint> > out(all.size());
         for (size_t l = 0; l < all.size(); l++) out[l].assign(all[l].begin(), all[l].end());
         r->levelKeys.swap(out);
+        /* vToDistributeKeys of every level (:778-829): a cell contributes the result of its last FAST call (the retry at
+         * minThFAST happens only when the first came back empty), shifted by the cell origin inside the level's window */
+        std::vector<std::vector<orc_corner> > cand(all.size());
+        int retried = 0;
+        for (size_t ci = 0; ci < calls.size(); ci++) {
+            const MinicvFastCall& c = calls[ci];
+            const bool hasRetry = ci + 1 < calls.size() && calls[ci + 1].origin == c.origin && c.corners.empty();
+            if (hasRetry) { retried++; continue; }
+            for (int l = 0; l < (int)all.size(); l++) {
+                const cv::Mat& m = r->ex->mvImagePyramid[l];
+                const ptrdiff_t off = c.origin - m.data;
+                if (off < 0 || off >= (ptrdiff_t)(m.step * (size_t)m.rows)) continue;
+                const int iniY = (int)(off / (ptrdiff_t)m.step), iniX = (int)(off % (ptrdiff_t)m.step);
+                for (size_t k = 0; k < c.corners.size(); k++) {
+                    orc_corner o = c.corners[k];
+                    o.x += iniX - 16; o.y += iniY - 16;             /* minBorderX = minBorderY = EDGE_THRESHOLD - 3 */
+                    cand[l].push_back(o);
+                }
+                break;
+            }
+        }
+        r->candidates.swap(cand);
+        r->retried = retried;
     }
     /* the previous call's block only held the previous pyramid, which operator() has replaced */
     block_destroy(r->cur);
@@ -202,6 +234,13 @@ const uint8_t* ref_extractor_pyramid(const RefExtractor* r, int level, int* w, i
     if (m.empty()) return nullptr;
     return m.data - 19 * (size_t)m.step - 19;
 }
+
+int ref_extractor_candidates(const RefExtractor* r, int level, orc_corner* out, int cap) {
+    const std::vector<orc_corner>& c = r->candidates[level];
+    for (size_t i = 0; i < c.size() && (int)i < cap; i++) out[i] = c[i];
+    return (int)c.size();
+}
+int ref_extractor_retried_cells(const RefExtractor* r) { return r->retried; }
 
 int ref_extractor_level_keypoints(const RefExtractor* r, int level, orc_keypoint* out, int cap) {
     const std::vector<cv::KeyPoint>& k = r->levelKeys[level];

@@ -15,6 +15,7 @@
  */
 #include <opencv2/core/core.hpp>
 
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -271,6 +272,9 @@ int ref_search_by_projection_frame(const RefGrid* grid, const orc_keypoint* kps_
     std::vector<MapPoint*> pts(nlast, static_cast<MapPoint*>(NULL));
     const int lm = mode & 7;
     const int nlevels = Cur.mnScaleLevels;
+    if (mode & 8)            /* the KeyFrame overloads skip ANY occupied keypoint (:1541-1542, :372-373): every match blocks later points */
+        for (int i = 0; i < nlast; i++)
+            if (valid[i] && mp_nobs[i] != 1) return -3;
     for (int i = 0; i < nlast; i++) {
         if (!valid[i]) continue;
         float w[3];
@@ -445,8 +449,8 @@ int ref_search_for_initialization(const RefGrid* grid2, const orc_keypoint* k2, 
 /* MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:249-314, for one point observed in N key frames.  The reference
  * iterates a std::map keyed by KeyFrame*: the key frames sit in one array here, so the iteration follows the row order. */
 int ref_distinctive_descriptor(const uint8_t* desc, int N, int* median_out) {
-    if (median_out) *median_out = 0;
-    if (N <= 0) return -1;
+    if (median_out) *median_out = INT_MAX;
+    if (N <= 0) return -1;                   /* the reference returns early and leaves mDescriptor untouched (:263-264) */
     std::vector<KeyFrame> kfs(N);
     MapPoint mp;
     for (int i = 0; i < N; i++) {
@@ -530,6 +534,8 @@ int ref_bow_transform(const RefVocabulary* voc, const uint8_t* desc, int n, int 
     DBoW2::BowVector v;
     DBoW2::FeatureVector fv;
     voc->RefVocabularyBase::transform(features, v, fv, levelsup);
+    bool undefinedNode = false;
+    DBoW2::FeatureVector byFeature;
     for (int i = 0; i < n; i++) {
         DBoW2::WordId id = 0;
         DBoW2::WordValue w = 0;
@@ -537,7 +543,16 @@ int ref_bow_transform(const RefVocabulary* voc, const uint8_t* desc, int n, int 
         if (n > 0 && !voc->empty()) voc->one(features[i], id, w, &nid, levelsup);
         if (word_of) word_of[i] = (int32_t)id;
         if (node_of) node_of[i] = (int32_t)nid;
+        if (w > 0) {
+            if (nid == 0 && levelsup > 0) undefinedNode = true;
+            byFeature.addFeature(nid, (unsigned)i);
+        }
     }
+    /* transform(features, v, fv, levelsup) passes an UNINITIALISED NodeId to the per-feature transform, which only writes it
+     * when the descent passes level L - levelsup (TemplatedVocabulary.h:1170-1185, :1230-1272): for a word that is a leaf
+     * above that level the node in the reference's FeatureVector is whatever the stack held.  Where that happens the
+     * FeatureVector is rebuilt from the per-feature calls with node 0 for those features (DESIGN.md convention C.8). */
+    if (undefinedNode) fv = byFeature;
     int k = 0;
     for (DBoW2::BowVector::const_iterator it = v.begin(); it != v.end(); ++it, ++k) { bow_ids[k] = (int32_t)it->first; bow_values[k] = it->second; }
     int f = 0, pos = 0;

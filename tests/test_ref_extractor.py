@@ -55,6 +55,9 @@ def test_oracle_equals_reference_on_configs(oracle, ref, cfg, seed):
         assert (eo.pyramid(l) == er.pyramid(l)).all(), "pyramid level %d" % l
         a, b = eo.level_keypoints(l), er.level_keypoints(l)
         assert a.tobytes() == b.tobytes(), "level %d keypoint list (order included)" % l
+        a, b = eo.candidates(l), er.candidates(l)          # every cv::FAST call the reference made, cell by cell
+        assert a.tobytes() == b.tobytes(), "level %d FAST candidates (vToDistributeKeys)" % l
+    assert eo.retried_cells() == er.retried_cells() > 0
 
 
 def test_oracle_equals_reference_stereo_pair(oracle, ref):

@@ -433,6 +433,7 @@ class ORBmatcher:
         n = C.c_int()
         _ck(lib().viorb_search_by_projection_frame(fi.h, _ptr(obs), *[_ptr(x) for x in a], len(a[0]), th, mbf, mode,
                                                    int(self.mbCheckOrientation), th_high, _ptr(match), C.byref(n)))
+        match[match == -2] = -1      # -2 = "assigned, then removed by the rotation check": an empty slot for the flat comparison
         return n.value, match, obs
 
     def SearchForTriangulation(self, k1, d1, ur1, has_mp1, k2, d2, ur2, has_mp2, fv1, fv2, F12, ex, ey, scale2,

@@ -71,6 +71,16 @@ struct viorb_ctx {
     DevBuf<uint8_t> scratchA, scratchB;
     DevBuf<int32_t> scratchI;
     DevBuf<uint8_t> arena;
+    /* pinned host mirrors of the arena: a matcher call packs all its inputs into one block and moves it with ONE copy.
+     * slot 0 serves the searches (they end in a stream synchronisation), slot 1 the frame-index builds (which do not);
+     * the event records when the last upload from a slot has been consumed */
+    uint8_t* stage[2] = {nullptr, nullptr};
+    size_t stageBytes[2] = {0, 0};
+    cudaEvent_t stageDone[2] = {nullptr, nullptr};
+    bool stagePending[2] = {false, false};
+    /* device blocks of destroyed frame indices, reused by the next index of the context (stream ordered: no cudaMalloc /
+     * cudaFree and no synchronisation on the per-frame path) */
+    std::vector<std::pair<size_t, uint8_t*> > pool;
 };
 
 struct viorb_extractor {
@@ -448,6 +458,11 @@ int viorb_ctx_destroy(viorb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->mq.release(); c->mmap.release(); c->mparts.release(); c->mout.release();
     c->scratchA.release(); c->scratchB.release(); c->scratchI.release(); c->arena.release();
+    for (int i = 0; i < 2; i++) {
+        if (c->stage[i]) cudaFreeHost(c->stage[i]);
+        if (c->stageDone[i]) cudaEventDestroy(c->stageDone[i]);
+    }
+    for (size_t i = 0; i < c->pool.size(); i++) cudaFree(c->pool[i].second);
     if (c->ownStream) cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->h2d);
     cudaStreamDestroy(c->d2h);
@@ -563,6 +578,55 @@ int viorb_ctx_scratch(viorb_ctx* c, size_t bytes, uint8_t** out) {
     return VIORB_OK;
 }
 void viorb_ctx_add_launches(viorb_ctx* c, int n) { c->launches += n; }
+
+/* pinned staging block `slot` of at least `bytes`; waits until the previous upload from it has left the host */
+int viorb_ctx_stage(viorb_ctx* c, int slot, size_t bytes, uint8_t** out) {
+    if (c->stagePending[slot]) {
+        CU(cudaEventSynchronize(c->stageDone[slot]));
+        c->stagePending[slot] = false;
+    }
+    if (bytes > c->stageBytes[slot]) {
+        if (c->stage[slot]) cudaFreeHost(c->stage[slot]);
+        c->stage[slot] = nullptr; c->stageBytes[slot] = 0;
+        const size_t want = std::max<size_t>(bytes + bytes / 2, 1 << 20);
+        CU(cudaHostAlloc((void**)&c->stage[slot], want, cudaHostAllocDefault));
+        c->stageBytes[slot] = want;
+    }
+    if (!c->stageDone[slot]) CU(cudaEventCreateWithFlags(&c->stageDone[slot], cudaEventDisableTiming));
+    *out = c->stage[slot];
+    return VIORB_OK;
+}
+int viorb_ctx_stage_mark(viorb_ctx* c, int slot) {
+    CU(cudaEventRecord(c->stageDone[slot], c->stream));
+    c->stagePending[slot] = true;
+    return VIORB_OK;
+}
+
+/* device block of at least `bytes` from the context's pool (or a fresh allocation); *got = its real size */
+int viorb_ctx_block_get(viorb_ctx* c, size_t bytes, uint8_t** out, size_t* got) {
+    int best = -1;
+    for (size_t i = 0; i < c->pool.size(); i++)
+        if (c->pool[i].first >= bytes && (best < 0 || c->pool[i].first < c->pool[best].first)) best = (int)i;
+    if (best >= 0) {
+        *out = c->pool[best].second; *got = c->pool[best].first;
+        c->pool.erase(c->pool.begin() + best);
+        return VIORB_OK;
+    }
+    const size_t want = (bytes + (bytes >> 2) + 65535) & ~(size_t)65535;
+    CU(cudaMalloc((void**)out, want));
+    *got = want;
+    return VIORB_OK;
+}
+void viorb_ctx_block_put(viorb_ctx* c, uint8_t* p, size_t bytes) {
+    if (!p) return;
+    if (c->pool.size() >= 16) {                    /* keep the pool small: drop the smallest block */
+        size_t k = 0;
+        for (size_t i = 1; i < c->pool.size(); i++) if (c->pool[i].first < c->pool[k].first) k = i;
+        cudaFree(c->pool[k].second);
+        c->pool.erase(c->pool.begin() + k);
+    }
+    c->pool.push_back(std::make_pair(bytes, p));
+}
 viorb_ctx* viorb_extractor_ctx(viorb_extractor* e) { return e->ctx; }
 
 extern "C" {

@@ -25,12 +25,13 @@ int viorb_launch_features_in_area(const FrameIndexDev& fi, float x, float y, flo
                                   unsigned long long* d_keys, int* d_count, cudaStream_t s);
 int viorb_launch_search_local(const FrameIndexDev& fi, const float* projX, const float* projY, const float* projXR,
                               const int* predLevel, const float* viewCos, const uint8_t* valid, const int* nobs,
-                              const uint8_t* mpDesc, int nmp, float th, float nnratio, int* d_obs, int* d_claim,
-                              int* d_minClaim, int* d_match, int* d_nmatches, cudaStream_t s);
+                              const uint8_t* mpDesc, int nmp, float th, float nnratio, const int* d_obs0, int* d_obs,
+                              int* d_scratch, int* d_match, int* d_nmatches, cudaStream_t s);
+int viorb_search_scratch_ints(int nq, int nf);
 int viorb_launch_search_frame(const FrameIndexDev& fi, const float* u, const float* v, const float* invz,
                               const int* lastOctave, const float* lastAngle, const uint8_t* valid, const int* nobs,
                               const uint8_t* mpDesc, int nlast, float th, float mbf, int mode, int checkOri, int thHigh,
-                              int* d_obs, int* d_claim, int* d_minClaim, int* d_match, int* d_nmatches, cudaStream_t s);
+                              const int* d_obs0, int* d_obs, int* d_scratch, int* d_match, int* d_nmatches, cudaStream_t s);
 int viorb_launch_triangulation(const viorb_keypoint* k1, const uint8_t* d1, const float* ur1, const uint8_t* mp1, int n1,
                                const viorb_keypoint* k2, const uint8_t* d2, const float* ur2, const uint8_t* mp2, int n2,
                                const int* nodeId1, const int* nodePtr1, const int* idx1, int nn1, int nentries1,
@@ -58,12 +59,21 @@ int viorb_launch_sim3_agree(const int* d_m1, const int* d_m2, int n1, int* d_mat
 
 namespace {
 
-/* bump allocator over one device scratch buffer: a call uploads all its inputs into a single arena */
+/* Bump allocator over one device block with a pinned host mirror of the same layout.  A call take()s all its arrays,
+ * put()s its inputs into the mirror, flush()es them with ONE host-to-device copy, launches its kernels, registers its
+ * results with get() and finish()es: ONE device-to-host copy into the mirror, one stream synchronisation, then plain
+ * memcpy into the caller's buffers.  (A dozen small pageable copies per search cost more than the search itself.) */
 struct Arena {
     uint8_t* base = nullptr;
-    size_t cap = 0, off = 0;
+    uint8_t* host = nullptr;
+    size_t cap = 0, hostCap = 0, off = 0;
+    int slot = 0;
     bool overflow = false;
-    /* returns NULL (and latches `overflow`) when the request does not fit: callers check ok() once after their takes */
+    size_t dirtyLo = (size_t)-1, dirtyHi = 0;
+    struct Pending { void* user; size_t off, bytes; };
+    Pending outs[12];
+    int nouts = 0;
+    /* returns NULL (and latches `overflow`) when the request does not fit: callers check once after their takes */
     template <typename T>
     T* take(size_t n) {
         off = (off + 255) & ~(size_t)255;
@@ -73,15 +83,64 @@ struct Arena {
         return p;
     }
     bool ok() const { return !overflow; }
+    template <typename T>
+    void put(T* dst, const T* src, size_t n) {
+        if (n == 0 || !dst || !src) return;
+        const size_t o = (size_t)(reinterpret_cast<uint8_t*>(dst) - base), bytes = n * sizeof(T);
+        if (o + bytes > hostCap) { overflow = true; return; }
+        memcpy(host + o, src, bytes);
+        dirtyLo = std::min(dirtyLo, o);
+        dirtyHi = std::max(dirtyHi, o + bytes);
+    }
+    int flush(viorb_ctx* c) {
+        if (overflow) return viorb_fail(VIORB_ERR_CAPACITY, "scratch arena under-sized (%zu B)", cap);
+        if (dirtyHi > dirtyLo) {
+            VCU(cudaMemcpyAsync(base + dirtyLo, host + dirtyLo, dirtyHi - dirtyLo, cudaMemcpyHostToDevice, viorb_ctx_stream(c)));
+            const int rc = viorb_ctx_stage_mark(c, slot);
+            if (rc) return rc;
+        }
+        dirtyLo = (size_t)-1; dirtyHi = 0;
+        return VIORB_OK;
+    }
+    void get(void* user, const void* dsrc, size_t bytes) {
+        if (bytes == 0 || !user) return;
+        const size_t o = (size_t)(reinterpret_cast<const uint8_t*>(dsrc) - base);
+        if (nouts >= 12 || o + bytes > hostCap) { overflow = true; return; }
+        outs[nouts].user = user; outs[nouts].off = o; outs[nouts].bytes = bytes;
+        nouts++;
+    }
+    int finish(viorb_ctx* c) {
+        if (overflow) return viorb_fail(VIORB_ERR_CAPACITY, "scratch arena under-sized (%zu B)", cap);
+        cudaStream_t s = viorb_ctx_stream(c);
+        VCU(cudaGetLastError());
+        size_t lo = (size_t)-1, hi = 0, sum = 0;
+        for (int i = 0; i < nouts; i++) { lo = std::min(lo, outs[i].off); hi = std::max(hi, outs[i].off + outs[i].bytes); sum += outs[i].bytes; }
+        if (nouts > 0) {
+            if (hi - lo <= 2 * sum + 65536) {
+                VCU(cudaMemcpyAsync(host + lo, base + lo, hi - lo, cudaMemcpyDeviceToHost, s));
+            } else {
+                for (int i = 0; i < nouts; i++)
+                    VCU(cudaMemcpyAsync(host + outs[i].off, base + outs[i].off, outs[i].bytes, cudaMemcpyDeviceToHost, s));
+            }
+        }
+        VCU(cudaStreamSynchronize(s));
+        for (int i = 0; i < nouts; i++) memcpy(outs[i].user, host + outs[i].off, outs[i].bytes);
+        nouts = 0;
+        return VIORB_OK;
+    }
 };
 #define ARENA_CHECK(a) do { if (!(a).ok()) return viorb_fail(VIORB_ERR_CAPACITY, "%s: scratch arena under-sized (%zu B)", __func__, (a).cap); } while (0)
 
 size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
 
-template <typename T>
-int upload(viorb_ctx* c, T* dst, const T* src, size_t n) {
-    if (n == 0) return VIORB_OK;
-    VCU(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, viorb_ctx_stream(c)));
+/* the context's scratch arena, sized by the caller: every take() is bounds-checked against `bytes`.  The first `mirror`
+ * bytes (all of it by default) are mirrored in pinned host memory: whatever a call put()s or get()s must lie below that. */
+int arena_open(viorb_ctx* c, size_t bytes, Arena* a, size_t mirror = 0) {
+    int rc = viorb_ctx_scratch(c, bytes, &a->base);
+    if (rc) return rc;
+    if (mirror == 0 || mirror > bytes) mirror = bytes;
+    if ((rc = viorb_ctx_stage(c, 0, mirror, &a->host))) return rc;
+    a->cap = bytes; a->hostCap = mirror; a->off = 0; a->overflow = false; a->slot = 0;
     return VIORB_OK;
 }
 
@@ -89,7 +148,8 @@ int upload(viorb_ctx* c, T* dst, const T* src, size_t n) {
 
 struct viorb_frame_index {
     viorb_ctx* ctx = nullptr;
-    uint8_t* mem = nullptr;
+    uint8_t* mem = nullptr;        /* block of the context's pool (viorb_ctx_block_get) */
+    size_t memBytes = 0;
     FrameIndexDev dev;
     int* cellOf = nullptr;
     int n = 0;
@@ -134,8 +194,7 @@ int viorb_stereo_match(viorb_extractor* left, int frame_l, viorb_extractor* righ
     const size_t bytes = pad((size_t)nl * sizeof(viorb_keypoint)) + pad((size_t)nl * 32) + pad((size_t)std::max(nr, 1) * sizeof(viorb_keypoint)) +
                          pad((size_t)std::max(nr, 1) * 32) + 3 * pad((size_t)nl * 4) + pad(64) + 4096;
     Arena a;
-    if ((rc = viorb_ctx_scratch(c, bytes, &a.base))) return rc;
-    a.cap = bytes;
+    if ((rc = arena_open(c, bytes, &a))) return rc;
     viorb_keypoint* dkl = a.take<viorb_keypoint>(nl);
     uint8_t* ddl = a.take<uint8_t>((size_t)nl * 32);
     viorb_keypoint* dkr = a.take<viorb_keypoint>(std::max(nr, 1));
@@ -144,15 +203,14 @@ int viorb_stereo_match(viorb_extractor* left, int frame_l, viorb_extractor* righ
     float* ddp = a.take<float>(nl);
     int* dsad = a.take<int>(nl);
     int* dscr = a.take<int>(16);
-    if ((rc = upload(c, dkl, kps_l, nl)) || (rc = upload(c, ddl, desc_l, (size_t)nl * 32)) ||
-        (rc = upload(c, dkr, kps_r, nr)) || (rc = upload(c, ddr, desc_r, (size_t)nr * 32)))
-        return rc;
+    ARENA_CHECK(a);
+    a.put(dkl, kps_l, nl); a.put(ddl, desc_l, (size_t)nl * 32);
+    a.put(dkr, kps_r, nr); a.put(ddr, desc_r, (size_t)nr * 32);
+    if ((rc = a.flush(c))) return rc;
     viorb_ctx_add_launches(c, viorb_launch_stereo(p, dkl, ddl, dkr, ddr, dscr, dur, ddp, dsad, viorb_ctx_stream(c)));
-    VCU(cudaGetLastError());
-    VCU(cudaMemcpyAsync(u_right, dur, (size_t)nl * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaMemcpyAsync(depth, ddp, (size_t)nl * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
-    return VIORB_OK;
+    a.get(u_right, dur, (size_t)nl * 4);
+    a.get(depth, ddp, (size_t)nl * 4);
+    return a.finish(c);
 }
 
 static int make_undistort_params(float fx, float fy, float cx, float cy, const float* dist, int ndist, UndistortParams* p) {
@@ -177,47 +235,61 @@ static int frame_index_build(viorb_ctx* c, const viorb_keypoint* kps, const uint
     viorb_frame_index* fi = new (std::nothrow) viorb_frame_index();
     if (!fi) return viorb_fail(VIORB_ERR_INVALID, "out of host memory");
     const int nn = std::max(n, 1);
-    const size_t bytes = pad((size_t)nn * sizeof(viorb_keypoint)) * 2 + pad((size_t)nn * 32) + pad((size_t)nn * 4) * 3 +
-                         pad((64 * 48 + 1) * 4) + pad(64) + 4096;
-    if (cudaMalloc((void**)&fi->mem, bytes) != cudaSuccess) { delete fi; return viorb_fail(VIORB_ERR_CUDA, "cudaMalloc failed"); }
+    /* inputs first (one staged copy), then what the kernels produce */
+    const size_t inBytes = pad((size_t)nn * sizeof(viorb_keypoint)) + pad((size_t)nn * 32) + pad((size_t)nn * 4) + 1024;
+    const size_t bytes = inBytes + pad((size_t)nn * sizeof(viorb_keypoint)) + pad((size_t)nn * 4) * 2 + pad((64 * 48 + 1) * 4) + pad(64) + 4096;
+    /* the block comes from the context's pool and goes back to it (viorb_frame_index_destroy): the per-frame path
+     * performs no cudaMalloc / cudaFree and, for undistorted keypoints, no synchronisation at all */
+    if ((rc = viorb_ctx_block_get(c, bytes, &fi->mem, &fi->memBytes))) { delete fi; return rc; }
+    auto fail_index = [&](int code) { viorb_ctx_block_put(c, fi->mem, fi->memBytes); delete fi; return code; };
     Arena a;
-    a.base = fi->mem; a.cap = bytes;
-    viorb_keypoint* dk = a.take<viorb_keypoint>(nn);
-    viorb_keypoint* draw = a.take<viorb_keypoint>(nn);
+    a.base = fi->mem; a.cap = bytes; a.slot = 1;
+    if (!deviceInputs) {
+        if ((rc = viorb_ctx_stage(c, 1, inBytes, &a.host))) return fail_index(rc);
+        a.hostCap = inBytes;
+    }
+    viorb_keypoint* din = a.take<viorb_keypoint>(nn);          /* keypoints as given: undistorted already, or raw */
     uint8_t* dd = a.take<uint8_t>((size_t)nn * 32);
     float* dur = a.take<float>(nn);
+    viorb_keypoint* dund = a.take<viorb_keypoint>(nn);         /* output of the undistortion kernel */
     int* cellOf = a.take<int>(nn);
     int* cellItems = a.take<int>(nn);
     int* cellStart = a.take<int>(64 * 48 + 1);
     float* dbounds = a.take<float>(4);
+    if (!a.ok()) return fail_index(viorb_fail(VIORB_ERR_CAPACITY, "frame index arena under-sized"));
+    viorb_keypoint* dk = und ? dund : din;
     fi->ctx = c; fi->n = n; fi->cellOf = cellOf;
     cudaStream_t s = viorb_ctx_stream(c);
-    std::vector<float> ur;
-    if (!u_right) { ur.assign(nn, -1.0f); }
     if (deviceInputs) {
         /* keypoints and descriptors are already on the device (viorb_extract_batch_device outputs): device-to-device */
         cudaError_t ce = cudaSuccess;
-        if (n > 0) ce = cudaMemcpyAsync(und ? draw : dk, kps, (size_t)n * sizeof(viorb_keypoint), cudaMemcpyDeviceToDevice, s);
+        if (n > 0) ce = cudaMemcpyAsync(din, kps, (size_t)n * sizeof(viorb_keypoint), cudaMemcpyDeviceToDevice, s);
         if (ce == cudaSuccess && n > 0) ce = cudaMemcpyAsync(dd, desc, (size_t)n * 32, cudaMemcpyDeviceToDevice, s);
-        if (ce == cudaSuccess && n > 0)
-            ce = u_right ? cudaMemcpyAsync(dur, u_right, (size_t)n * 4, cudaMemcpyDeviceToDevice, s)
-                         : cudaMemcpyAsync(dur, ur.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s);
-        if (ce == cudaSuccess && !u_right) ce = cudaStreamSynchronize(s);          /* ur is a local */
-        if (ce != cudaSuccess) { cudaFree(fi->mem); delete fi; return viorb_fail(VIORB_ERR_CUDA, "device copy: %s", cudaGetErrorString(ce)); }
-    } else {
-        if (!u_right) u_right = ur.data();
-        if ((rc = upload(c, und ? draw : dk, kps, n)) || (rc = upload(c, dd, desc, (size_t)n * 32)) || (rc = upload(c, dur, u_right, n))) {
-            cudaFree(fi->mem); delete fi; return rc;
+        if (ce == cudaSuccess && n > 0) {
+            if (u_right) ce = cudaMemcpyAsync(dur, u_right, (size_t)n * 4, cudaMemcpyDeviceToDevice, s);
+            else ce = cudaMemsetAsync(dur, 0xbf, (size_t)n * 4, s);              /* 0xbfbfbfbf = -1.49: "no right match" (< 0) */
         }
+        if (ce != cudaSuccess) return fail_index(viorb_fail(VIORB_ERR_CUDA, "device copy: %s", cudaGetErrorString(ce)));
+    } else {
+        a.put(din, kps, n);
+        a.put(dd, desc, (size_t)n * 32);
+        if (u_right) a.put(dur, u_right, n);
+        else if (n > 0) {
+            float* h = reinterpret_cast<float*>(a.host + (reinterpret_cast<uint8_t*>(dur) - a.base));
+            for (int i = 0; i < n; i++) h[i] = -1.0f;
+            a.dirtyLo = std::min(a.dirtyLo, (size_t)(reinterpret_cast<uint8_t*>(dur) - a.base));
+            a.dirtyHi = std::max(a.dirtyHi, (size_t)(reinterpret_cast<uint8_t*>(dur) - a.base) + (size_t)n * 4);
+        }
+        if ((rc = a.flush(c))) return fail_index(rc);
     }
     float b[4] = {0, 0, 0, 0};
     if (und) {
         /* Frame::UndistortKeyPoints + ComputeImageBounds on the device; only the four bounds come back */
-        viorb_ctx_add_launches(c, viorb_launch_undistort(*und, draw, n, dk, s));
+        viorb_ctx_add_launches(c, viorb_launch_undistort(*und, din, n, dund, s));
         viorb_ctx_add_launches(c, viorb_launch_image_bounds(*und, cols, rows, dbounds, s));
         cudaError_t e = cudaMemcpyAsync(b, dbounds, sizeof(b), cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) { cudaFree(fi->mem); delete fi; return viorb_fail(VIORB_ERR_CUDA, "undistort: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) return fail_index(viorb_fail(VIORB_ERR_CUDA, "undistort: %s", cudaGetErrorString(e)));
     } else {
         memcpy(b, bounds_in, sizeof(b));
     }
@@ -230,8 +302,8 @@ static int frame_index_build(viorb_ctx* c, const viorb_keypoint* kps, const uint
     d.nlevels = nlevels;
     for (int l = 0; l < nlevels; l++) d.scale[l] = scale_factors[l];
     viorb_ctx_add_launches(c, viorb_launch_grid_build(dk, n, d.minX, d.minY, d.invW, d.invH, cellOf, cellStart, cellItems, s));
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) { cudaFree(fi->mem); delete fi; return viorb_fail(VIORB_ERR_CUDA, "grid build: %s", cudaGetErrorString(e)); }
+    const cudaError_t e = cudaGetLastError();      /* the index is used by later calls on the same stream: no wait here */
+    if (e != cudaSuccess) return fail_index(viorb_fail(VIORB_ERR_CUDA, "grid build: %s", cudaGetErrorString(e)));
     *out = fi;
     return VIORB_OK;
 }
@@ -304,15 +376,14 @@ int viorb_undistort_keypoints(viorb_ctx* c, const viorb_keypoint* kps, int n, fl
     if (n == 0) return VIORB_OK;
     if ((rc = viorb_ctx_bind(c))) return rc;
     Arena a;
-    if ((rc = viorb_ctx_scratch(c, 2 * pad((size_t)n * sizeof(viorb_keypoint)) + 1024, &a.base))) return rc;
+    if ((rc = arena_open(c, 2 * pad((size_t)n * sizeof(viorb_keypoint)) + 1024, &a))) return rc;
     viorb_keypoint* din = a.take<viorb_keypoint>(n);
     viorb_keypoint* dout = a.take<viorb_keypoint>(n);
-    if ((rc = upload(c, din, kps, n))) return rc;
+    a.put(din, kps, n);
+    if ((rc = a.flush(c))) return rc;
     viorb_ctx_add_launches(c, viorb_launch_undistort(p, din, n, dout, viorb_ctx_stream(c)));
-    VCU(cudaGetLastError());
-    VCU(cudaMemcpyAsync(kps_un, dout, (size_t)n * sizeof(viorb_keypoint), cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
-    return VIORB_OK;
+    a.get(kps_un, dout, (size_t)n * sizeof(viorb_keypoint));
+    return a.finish(c);
 }
 
 int viorb_compute_image_bounds(viorb_ctx* c, int cols, int rows, float fx, float fy, float cx, float cy, const float* dist_coef,
@@ -323,20 +394,18 @@ int viorb_compute_image_bounds(viorb_ctx* c, int cols, int rows, float fx, float
     if ((rc = make_undistort_params(fx, fy, cx, cy, dist_coef, ndist, &p))) return rc;
     if ((rc = viorb_ctx_bind(c))) return rc;
     Arena a;
-    if ((rc = viorb_ctx_scratch(c, 1024, &a.base))) return rc;
+    if ((rc = arena_open(c, 1024, &a))) return rc;
     float* db = a.take<float>(4);
     viorb_ctx_add_launches(c, viorb_launch_image_bounds(p, cols, rows, db, viorb_ctx_stream(c)));
-    VCU(cudaGetLastError());
-    VCU(cudaMemcpyAsync(bounds, db, 16, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
-    return VIORB_OK;
+    a.get(bounds, db, 16);
+    return a.finish(c);
 }
 
 int viorb_frame_index_destroy(viorb_frame_index* fi) {
     if (!fi) return VIORB_OK;
-    cudaSetDevice(viorb_ctx_device(fi->ctx));
-    cudaStreamSynchronize(viorb_ctx_stream(fi->ctx));
-    cudaFree(fi->mem);
+    /* the block returns to the context's pool; work still queued on the context's stream that reads it is ordered
+     * before whatever the next owner enqueues on the same stream, so no synchronisation is needed */
+    viorb_ctx_block_put(fi->ctx, fi->mem, fi->memBytes);
     delete fi;
     return VIORB_OK;
 }
@@ -349,13 +418,13 @@ int viorb_frame_features_in_area(viorb_frame_index* fi, float x, float y, float 
     if ((rc = viorb_ctx_bind(c))) return rc;
     const size_t bytes = pad((size_t)std::max(fi->n, 1) * 8) + pad(64) + 1024;
     Arena a;
-    if ((rc = viorb_ctx_scratch(c, bytes, &a.base))) return rc;
+    if ((rc = arena_open(c, bytes, &a))) return rc;
     unsigned long long* keys = a.take<unsigned long long>(std::max(fi->n, 1));
     int* cnt = a.take<int>(4);
     viorb_ctx_add_launches(c, viorb_launch_features_in_area(fi->dev, x, y, r, min_level, max_level, keys, cnt, viorb_ctx_stream(c)));
     int h = 0;
-    VCU(cudaMemcpyAsync(&h, cnt, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    a.get(&h, cnt, 4);
+    if ((rc = a.finish(c))) return rc;
     std::vector<unsigned long long> k(std::max(h, 1));
     VCU(cudaMemcpy(k.data(), keys, (size_t)h * 8, cudaMemcpyDeviceToHost));
     std::sort(k.begin(), k.begin() + h);          /* presentation order only: enumeration rank is part of the key */
@@ -364,12 +433,16 @@ int viorb_frame_features_in_area(viorb_frame_index* fi, float x, float y, float 
     return VIORB_OK;
 }
 
-static int search_common_alloc(viorb_ctx* c, int nf, int nq, size_t extra, Arena* a) {
-    const size_t bytes = pad((size_t)std::max(nf, 1) * 4) * 3 + pad((size_t)std::max(nq, 1) * 4) + extra + pad(64) + 8192;
-    int rc;
-    if ((rc = viorb_ctx_scratch(c, bytes, &a->base))) return rc;
-    a->cap = bytes;
+static int check_levels(const int32_t* level, const uint8_t* valid, int n, int nlevels) {
+    for (int i = 0; i < n; i++)
+        if (valid[i] && (level[i] < 0 || level[i] >= nlevels)) return viorb_fail(VIORB_ERR_INVALID, "query %d: level %d out of range", i, level[i]);
     return VIORB_OK;
+}
+
+/* inputs first (one staged host-to-device copy), then the outputs (one copy back), then device-only scratch */
+static size_t search_bytes(int nf, int nq) {
+    const size_t f = (size_t)std::max(nf, 1), q = (size_t)std::max(nq, 1);
+    return pad(f * 4) * 3 + 6 * pad(q * 4) + pad(q) + pad(q * 32) + pad(64) + pad((size_t)viorb_search_scratch_ints((int)q, (int)f) * 4) + 8192;
 }
 
 int viorb_search_by_projection_local(viorb_frame_index* fi, int32_t* frame_mp_obs, const float* proj_x, const float* proj_y,
@@ -379,32 +452,33 @@ int viorb_search_by_projection_local(viorb_frame_index* fi, int32_t* frame_mp_ob
     if (!fi || !frame_mp_obs || !match || !nmatches || nmp < 0 ||
         (nmp > 0 && (!proj_x || !proj_y || !proj_xr || !pred_level || !view_cos || !valid || !nobs || !mp_desc)))
         return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    if (nmp >= (1 << 20) || fi->n >= (1 << 20)) return viorb_fail(VIORB_ERR_UNSUPPORTED, "more than 2^20 map points or keypoints");
     viorb_ctx* c = fi->ctx;
     int rc;
     if ((rc = viorb_ctx_bind(c))) return rc;
-    const int nf = fi->n, nq = std::max(nmp, 1);
+    if ((rc = check_levels(pred_level, valid, nmp, fi->dev.nlevels))) return rc;
+    const int nf = fi->n, nq = std::max(nmp, 1), mf = std::max(nf, 1);
     Arena a;
-    if ((rc = search_common_alloc(c, nf, nmp, 6 * pad((size_t)nq * 4) + pad(nq) + pad((size_t)nq * 32), &a))) return rc;
-    int* dobs = a.take<int>(std::max(nf, 1));
-    int* dmin = a.take<int>(std::max(nf, 1));
-    int* dmatch = a.take<int>(std::max(nf, 1));
-    int* dclaim = a.take<int>(nq);
+    if ((rc = arena_open(c, search_bytes(nf, nmp), &a))) return rc;
+    int* dobs0 = a.take<int>(mf);
     float* dpx = a.take<float>(nq); float* dpy = a.take<float>(nq); float* dpr = a.take<float>(nq);
     float* dvc = a.take<float>(nq); int* dlv = a.take<int>(nq); int* dno = a.take<int>(nq);
     uint8_t* dva = a.take<uint8_t>(nq); uint8_t* dde = a.take<uint8_t>((size_t)nq * 32);
+    int* dmatch = a.take<int>(mf);
+    int* dobs = a.take<int>(mf);
     int* dn = a.take<int>(4);
-    if ((rc = upload(c, dobs, frame_mp_obs, nf)) || (rc = upload(c, dpx, proj_x, nmp)) || (rc = upload(c, dpy, proj_y, nmp)) ||
-        (rc = upload(c, dpr, proj_xr, nmp)) || (rc = upload(c, dvc, view_cos, nmp)) || (rc = upload(c, dlv, pred_level, nmp)) ||
-        (rc = upload(c, dno, nobs, nmp)) || (rc = upload(c, dva, valid, nmp)) || (rc = upload(c, dde, mp_desc, (size_t)nmp * 32)))
-        return rc;
-    viorb_ctx_add_launches(c, viorb_launch_search_local(fi->dev, dpx, dpy, dpr, dlv, dvc, dva, dno, dde, nmp, th, nnratio, dobs,
-                                                        dclaim, dmin, dmatch, dn, viorb_ctx_stream(c)));
-    VCU(cudaGetLastError());
-    VCU(cudaMemcpyAsync(match, dmatch, (size_t)nf * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaMemcpyAsync(frame_mp_obs, dobs, (size_t)nf * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
-    return VIORB_OK;
+    int* dscratch = a.take<int>((size_t)viorb_search_scratch_ints(nq, mf));
+    ARENA_CHECK(a);
+    a.put(dobs0, frame_mp_obs, nf);
+    a.put(dpx, proj_x, nmp); a.put(dpy, proj_y, nmp); a.put(dpr, proj_xr, nmp); a.put(dvc, view_cos, nmp);
+    a.put(dlv, pred_level, nmp); a.put(dno, nobs, nmp); a.put(dva, valid, nmp); a.put(dde, mp_desc, (size_t)nmp * 32);
+    if ((rc = a.flush(c))) return rc;
+    viorb_ctx_add_launches(c, viorb_launch_search_local(fi->dev, dpx, dpy, dpr, dlv, dvc, dva, dno, dde, nmp, th, nnratio, dobs0, dobs,
+                                                        dscratch, dmatch, dn, viorb_ctx_stream(c)));
+    a.get(match, dmatch, (size_t)nf * 4);
+    a.get(frame_mp_obs, dobs, (size_t)nf * 4);
+    a.get(nmatches, dn, 4);
+    return a.finish(c);
 }
 
 int viorb_search_by_projection_frame(viorb_frame_index* fi, int32_t* frame_mp_obs, const float* u, const float* v,
@@ -414,33 +488,34 @@ int viorb_search_by_projection_frame(viorb_frame_index* fi, int32_t* frame_mp_ob
     if (!fi || !frame_mp_obs || !match || !nmatches || nlast < 0 || mode < 0 || (mode & 7) > 3 || mode > 15 ||
         (nlast > 0 && (!u || !v || !invz || !last_octave || !last_angle || !valid || !nobs || !mp_desc)))
         return viorb_fail(VIORB_ERR_INVALID, "bad argument");
+    if (nlast >= (1 << 24) || fi->n >= (1 << 24)) return viorb_fail(VIORB_ERR_UNSUPPORTED, "more than 2^24 map points or keypoints");
     viorb_ctx* c = fi->ctx;
     int rc;
     if ((rc = viorb_ctx_bind(c))) return rc;
-    const int nf = fi->n, nq = std::max(nlast, 1);
+    if ((rc = check_levels(last_octave, valid, nlast, fi->dev.nlevels))) return rc;
+    const int nf = fi->n, nq = std::max(nlast, 1), mf = std::max(nf, 1);
     Arena a;
-    if ((rc = search_common_alloc(c, nf, nlast, 6 * pad((size_t)nq * 4) + pad(nq) + pad((size_t)nq * 32), &a))) return rc;
-    int* dobs = a.take<int>(std::max(nf, 1));
-    int* dmin = a.take<int>(std::max(nf, 1));
-    int* dmatch = a.take<int>(std::max(nf, 1));
-    int* dclaim = a.take<int>(nq);
+    if ((rc = arena_open(c, search_bytes(nf, nlast), &a))) return rc;
+    int* dobs0 = a.take<int>(mf);
     float* du = a.take<float>(nq); float* dv = a.take<float>(nq); float* dz = a.take<float>(nq); float* dan = a.take<float>(nq);
     int* doc = a.take<int>(nq); int* dno = a.take<int>(nq);
     uint8_t* dva = a.take<uint8_t>(nq); uint8_t* dde = a.take<uint8_t>((size_t)nq * 32);
+    int* dmatch = a.take<int>(mf);
+    int* dobs = a.take<int>(mf);
     int* dn = a.take<int>(4);
-    if ((rc = upload(c, dobs, frame_mp_obs, nf)) || (rc = upload(c, du, u, nlast)) || (rc = upload(c, dv, v, nlast)) ||
-        (rc = upload(c, dz, invz, nlast)) || (rc = upload(c, dan, last_angle, nlast)) || (rc = upload(c, doc, last_octave, nlast)) ||
-        (rc = upload(c, dno, nobs, nlast)) || (rc = upload(c, dva, valid, nlast)) || (rc = upload(c, dde, mp_desc, (size_t)nlast * 32)))
-        return rc;
+    int* dscratch = a.take<int>((size_t)viorb_search_scratch_ints(nq, mf));
+    ARENA_CHECK(a);
+    a.put(dobs0, frame_mp_obs, nf);
+    a.put(du, u, nlast); a.put(dv, v, nlast); a.put(dz, invz, nlast); a.put(dan, last_angle, nlast);
+    a.put(doc, last_octave, nlast); a.put(dno, nobs, nlast); a.put(dva, valid, nlast); a.put(dde, mp_desc, (size_t)nlast * 32);
+    if ((rc = a.flush(c))) return rc;
     viorb_ctx_add_launches(c, viorb_launch_search_frame(fi->dev, du, dv, dz, doc, dan, dva, dno, dde, nlast, th, mbf, mode,
-                                                        check_orientation, th_high, dobs, dclaim, dmin, dmatch, dn,
+                                                        check_orientation, th_high, dobs0, dobs, dscratch, dmatch, dn,
                                                         viorb_ctx_stream(c)));
-    VCU(cudaGetLastError());
-    VCU(cudaMemcpyAsync(match, dmatch, (size_t)nf * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaMemcpyAsync(frame_mp_obs, dobs, (size_t)nf * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
-    return VIORB_OK;
+    a.get(match, dmatch, (size_t)nf * 4);
+    a.get(frame_mp_obs, dobs, (size_t)nf * 4);
+    a.get(nmatches, dn, 4);
+    return a.finish(c);
 }
 
 int viorb_search_for_triangulation(viorb_ctx* c, const viorb_keypoint* k1, const uint8_t* d1, const float* ur1,
@@ -463,7 +538,7 @@ int viorb_search_for_triangulation(viorb_ctx* c, const viorb_keypoint* k1, const
                          pad((size_t)m2 * 32) + pad((size_t)m2 * 4) + pad(m2) + pad((size_t)(nn1 + 2) * 4) * 2 + pad((size_t)(e1 + 1) * 4) +
                          pad((size_t)(nn2 + 2) * 4) * 2 + pad((size_t)(e2 + 1) * 4) + pad(64) + 16384;
     Arena a;
-    if ((rc = viorb_ctx_scratch(c, bytes, &a.base))) return rc;
+    if ((rc = arena_open(c, bytes, &a))) return rc;
     viorb_keypoint* dk1 = a.take<viorb_keypoint>(m1); uint8_t* dd1 = a.take<uint8_t>((size_t)m1 * 32);
     float* du1 = a.take<float>(m1); uint8_t* dm1 = a.take<uint8_t>(m1); int* dmatch = a.take<int>(m1);
     viorb_keypoint* dk2 = a.take<viorb_keypoint>(m2); uint8_t* dd2 = a.take<uint8_t>((size_t)m2 * 32);
@@ -471,20 +546,27 @@ int viorb_search_for_triangulation(viorb_ctx* c, const viorb_keypoint* k1, const
     int* dni1 = a.take<int>(nn1 + 1); int* dnp1 = a.take<int>(nn1 + 2); int* di1 = a.take<int>(e1 + 1);
     int* dni2 = a.take<int>(nn2 + 1); int* dnp2 = a.take<int>(nn2 + 2); int* di2 = a.take<int>(e2 + 1);
     int* dn = a.take<int>(4);
-    if ((rc = upload(c, dk1, k1, n1)) || (rc = upload(c, dd1, d1, (size_t)n1 * 32)) || (rc = upload(c, du1, ur1, n1)) ||
-        (rc = upload(c, dm1, has_mp1, n1)) || (rc = upload(c, dk2, k2, n2)) || (rc = upload(c, dd2, d2, (size_t)n2 * 32)) ||
-        (rc = upload(c, du2, ur2, n2)) || (rc = upload(c, dm2, has_mp2, n2)) || (rc = upload(c, dni1, node_id1, nn1)) ||
-        (rc = upload(c, dnp1, node_ptr1, nn1 ? nn1 + 1 : 0)) || (rc = upload(c, di1, idx1, e1)) || (rc = upload(c, dni2, node_id2, nn2)) ||
-        (rc = upload(c, dnp2, node_ptr2, nn2 ? nn2 + 1 : 0)) || (rc = upload(c, di2, idx2, e2)))
-        return rc;
+    a.put(dk1, k1, n1);
+    a.put(dd1, d1, (size_t)n1 * 32);
+    a.put(du1, ur1, n1);
+    a.put(dm1, has_mp1, n1);
+    a.put(dk2, k2, n2);
+    a.put(dd2, d2, (size_t)n2 * 32);
+    a.put(du2, ur2, n2);
+    a.put(dm2, has_mp2, n2);
+    a.put(dni1, node_id1, nn1);
+    a.put(dnp1, node_ptr1, nn1 ? nn1 + 1 : 0);
+    a.put(di1, idx1, e1);
+    a.put(dni2, node_id2, nn2);
+    a.put(dnp2, node_ptr2, nn2 ? nn2 + 1 : 0);
+    a.put(di2, idx2, e2);
+    if ((rc = a.flush(c))) return rc;
     viorb_ctx_add_launches(c, viorb_launch_triangulation(dk1, dd1, du1, dm1, n1, dk2, dd2, du2, dm2, n2, dni1, dnp1, di1, nn1, e1,
                                                          dni2, dnp2, di2, nn2, F12, ex, ey, scale_factors2, level_sigma2_2, nlevels,
                                                          only_stereo, check_orientation, dmatch, dn, viorb_ctx_stream(c)));
-    VCU(cudaGetLastError());
-    VCU(cudaMemcpyAsync(matches12, dmatch, (size_t)n1 * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
-    return VIORB_OK;
+    a.get(matches12, dmatch, (size_t)n1 * 4);
+    a.get(nmatches, dn, 4);
+    return a.finish(c);
 }
 
 int viorb_distinctive_descriptors(viorb_ctx* c, const uint8_t* obs_desc, const int32_t* obs_ptr, int nmp, int32_t* best,
@@ -500,18 +582,18 @@ int viorb_distinctive_descriptors(viorb_ctx* c, const uint8_t* obs_desc, const i
     if ((rc = viorb_ctx_bind(c))) return rc;
     const size_t bytes = pad(std::max<size_t>(total, 1) * 32) + pad((size_t)(nmp + 1) * 4) + 2 * pad((size_t)nmp * 4) + 2048;
     Arena a;
-    if ((rc = viorb_ctx_scratch(c, bytes, &a.base))) return rc;
+    if ((rc = arena_open(c, bytes, &a))) return rc;
     uint8_t* dd = a.take<uint8_t>(std::max<size_t>(total, 1) * 32);
     int* dp = a.take<int>(nmp + 1);
     int* db = a.take<int>(nmp);
     int* dm = a.take<int>(nmp);
-    if ((rc = upload(c, dd, obs_desc, total * 32)) || (rc = upload(c, dp, obs_ptr, (size_t)nmp + 1))) return rc;
+    a.put(dd, obs_desc, total * 32);
+    a.put(dp, obs_ptr, (size_t)nmp + 1);
+    if ((rc = a.flush(c))) return rc;
     viorb_ctx_add_launches(c, viorb_launch_distinctive(dd, dp, nmp, db, dm, viorb_ctx_stream(c)));
-    VCU(cudaGetLastError());
-    VCU(cudaMemcpyAsync(best, db, (size_t)nmp * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    if (best_median) VCU(cudaMemcpyAsync(best_median, dm, (size_t)nmp * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
-    return VIORB_OK;
+    a.get(best, db, (size_t)nmp * 4);
+    if (best_median) a.get(best_median, dm, (size_t)nmp * 4);
+    return a.finish(c);
 }
 
 int viorb_search_by_bow(viorb_ctx* c, int mode, const viorb_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
@@ -532,26 +614,32 @@ int viorb_search_by_bow(viorb_ctx* c, int mode, const viorb_keypoint* k1, const 
                          pad((size_t)m2 * 4) + pad((size_t)mo * 4) + pad((size_t)(nn1 + 2) * 4) * 2 + pad((size_t)(e1 + 1) * 4) +
                          pad((size_t)(nn2 + 2) * 4) * 2 + pad((size_t)(e2 + 1) * 4) + pad(64) + 16384;
     Arena a;
-    if ((rc = viorb_ctx_scratch(c, bytes, &a.base))) return rc;
+    if ((rc = arena_open(c, bytes, &a))) return rc;
     viorb_keypoint* dk1 = a.take<viorb_keypoint>(m1); uint8_t* dd1 = a.take<uint8_t>((size_t)m1 * 32); uint8_t* dv1 = a.take<uint8_t>(m1);
     viorb_keypoint* dk2 = a.take<viorb_keypoint>(m2); uint8_t* dd2 = a.take<uint8_t>((size_t)m2 * 32); uint8_t* dv2 = a.take<uint8_t>(m2);
     int* dtaken = a.take<int>(m2); int* dmatch = a.take<int>(mo);
     int* dni1 = a.take<int>(nn1 + 1); int* dnp1 = a.take<int>(nn1 + 2); int* di1 = a.take<int>(e1 + 1);
     int* dni2 = a.take<int>(nn2 + 1); int* dnp2 = a.take<int>(nn2 + 2); int* di2 = a.take<int>(e2 + 1);
     int* dn = a.take<int>(4);
-    if ((rc = upload(c, dk1, k1, n1)) || (rc = upload(c, dd1, d1, (size_t)n1 * 32)) || (rc = upload(c, dv1, valid1, n1)) ||
-        (rc = upload(c, dk2, k2, n2)) || (rc = upload(c, dd2, d2, (size_t)n2 * 32)) || (valid2 && (rc = upload(c, dv2, valid2, n2))) ||
-        (rc = upload(c, dni1, node_id1, nn1)) || (rc = upload(c, dnp1, node_ptr1, nn1 ? nn1 + 1 : 0)) || (rc = upload(c, di1, idx1, e1)) ||
-        (rc = upload(c, dni2, node_id2, nn2)) || (rc = upload(c, dnp2, node_ptr2, nn2 ? nn2 + 1 : 0)) || (rc = upload(c, di2, idx2, e2)))
-        return rc;
+    a.put(dk1, k1, n1);
+    a.put(dd1, d1, (size_t)n1 * 32);
+    a.put(dv1, valid1, n1);
+    a.put(dk2, k2, n2);
+    a.put(dd2, d2, (size_t)n2 * 32);
+    if (valid2) a.put(dv2, valid2, n2);
+    a.put(dni1, node_id1, nn1);
+    a.put(dnp1, node_ptr1, nn1 ? nn1 + 1 : 0);
+    a.put(di1, idx1, e1);
+    a.put(dni2, node_id2, nn2);
+    a.put(dnp2, node_ptr2, nn2 ? nn2 + 1 : 0);
+    a.put(di2, idx2, e2);
+    if ((rc = a.flush(c))) return rc;
     viorb_ctx_add_launches(c, viorb_launch_search_bow(mode, dk1, dd1, dv1, n1, dk2, dd2, valid2 ? dv2 : nullptr, n2, dni1, dnp1, di1,
                                                       nn1, dni2, dnp2, di2, nn2, nnratio, check_orientation, dtaken, dmatch, dn,
                                                       viorb_ctx_stream(c)));
-    VCU(cudaGetLastError());
-    VCU(cudaMemcpyAsync(match, dmatch, (size_t)(mode == 0 ? n2 : n1) * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
-    return VIORB_OK;
+    a.get(match, dmatch, (size_t)(mode == 0 ? n2 : n1) * 4);
+    a.get(nmatches, dn, 4);
+    return a.finish(c);
 }
 
 int viorb_search_for_initialization(viorb_frame_index* f2, const viorb_keypoint* k1_un, const uint8_t* d1, int n1,
@@ -573,31 +661,35 @@ int viorb_search_for_initialization(viorb_frame_index* f2, const viorb_keypoint*
     const size_t bytes = pad((size_t)m1 * 28) + pad((size_t)m1 * 32) + pad((size_t)m1 * 8) + pad((size_t)cap * 8) + 4 * pad((size_t)m1 * 4) +
                          2 * pad((size_t)m2 * 4) + 3 * pad(64) + 16384;
     Arena a;
-    if ((rc = viorb_ctx_scratch(c, bytes, &a.base))) return rc;
+    /* the candidate pool is device-only scratch: it goes last and stays outside of the pinned mirror */
+    if ((rc = arena_open(c, bytes, &a, bytes - pad((size_t)cap * 8)))) return rc;
     viorb_keypoint* dk1 = a.take<viorb_keypoint>(m1); uint8_t* dd1 = a.take<uint8_t>((size_t)m1 * 32);
     float* dprev = a.take<float>((size_t)m1 * 2);
-    unsigned long long* dent = a.take<unsigned long long>((size_t)cap);
-    int* dstart = a.take<int>(m1); int* dcount = a.take<int>(m1); int* dbin = a.take<int>(m1); int* dm12 = a.take<int>(m1);
+    int* dm12 = a.take<int>(m1);
+    int* dovf = a.take<int>(4); int* dn = a.take<int>(4);
+    int* dstart = a.take<int>(m1); int* dcount = a.take<int>(m1); int* dbin = a.take<int>(m1);
     int* dmd = a.take<int>(m2); int* dm21 = a.take<int>(m2);
     unsigned long long* dcur = a.take<unsigned long long>(2);
-    int* dovf = a.take<int>(4); int* dn = a.take<int>(4);
-    if ((rc = upload(c, dk1, k1_un, n1)) || (rc = upload(c, dd1, d1, (size_t)n1 * 32)) || (rc = upload(c, dprev, prev_matched, (size_t)n1 * 2)))
-        return rc;
+    unsigned long long* dent = a.take<unsigned long long>((size_t)cap);
+    ARENA_CHECK(a);
+    a.put(dk1, k1_un, n1);
+    a.put(dd1, d1, (size_t)n1 * 32);
+    a.put(dprev, prev_matched, (size_t)n1 * 2);
+    if ((rc = a.flush(c))) return rc;
     viorb_ctx_add_launches(c, viorb_launch_search_init(f2->dev, dk1, dd1, n1, dprev, (float)window_size, nnratio, check_orientation, dent,
                                                        cap, dstart, dcount, dcur, dovf, dmd, dm21, dbin, dm12, dn, viorb_ctx_stream(c)));
-    VCU(cudaGetLastError());
     int ovf = 0;
-    VCU(cudaMemcpyAsync(matches12, dm12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaMemcpyAsync(prev_matched, dprev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaMemcpyAsync(&ovf, dovf, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
+    a.get(matches12, dm12, (size_t)n1 * 4);
+    a.get(prev_matched, dprev, (size_t)n1 * 8);
+    a.get(nmatches, dn, 4);
+    a.get(&ovf, dovf, 4);
+    if ((rc = a.finish(c))) return rc;
     if (ovf) return viorb_fail(VIORB_ERR_CAPACITY, "candidate pool overflow");
     return VIORB_OK;
 }
 
 /* uploads one direction's queries into the arena and launches the windowed top-1 search */
-static int window_search_upload(viorb_ctx* c, Arena& a, viorb_frame_index* kf, const float* u, const float* v, const float* ur,
+static int window_search_stage(viorb_ctx* c, Arena& a, viorb_frame_index* kf, const float* u, const float* v, const float* ur,
                                 const int32_t* level, const uint8_t* valid, const uint8_t* desc, int n, float th, int thDist,
                                 const float* invSigma2, int** d_best, int** d_dist) {
     const int m = std::max(n, 1);
@@ -606,9 +698,13 @@ static int window_search_upload(viorb_ctx* c, Arena& a, viorb_frame_index* kf, c
     *d_best = a.take<int>(m);
     *d_dist = a.take<int>(m);
     int rc;
-    if ((rc = upload(c, du, u, n)) || (rc = upload(c, dv, v, n)) || (ur && (rc = upload(c, dr, ur, n))) || (rc = upload(c, dl, level, n)) ||
-        (rc = upload(c, dva, valid, n)) || (rc = upload(c, dde, desc, (size_t)n * 32)))
-        return rc;
+    a.put(du, u, n);
+    a.put(dv, v, n);
+    if (ur) a.put(dr, ur, n);
+    a.put(dl, level, n);
+    a.put(dva, valid, n);
+    a.put(dde, desc, (size_t)n * 32);
+    if ((rc = a.flush(c))) return rc;
     viorb_ctx_add_launches(c, viorb_launch_search_window(kf->dev, du, dv, ur ? dr : nullptr, dl, dva, dde, n, th, thDist, invSigma2,
                                                          kf->dev.nlevels, *d_best, *d_dist, viorb_ctx_stream(c)));
     return VIORB_OK;
@@ -617,12 +713,6 @@ static int window_search_upload(viorb_ctx* c, Arena& a, viorb_frame_index* kf, c
 static size_t window_search_bytes(int n) {
     const size_t m = (size_t)std::max(n, 1);
     return 6 * pad(m * 4) + pad(m) + pad(m * 32) + 4096;
-}
-
-static int check_levels(const int32_t* level, const uint8_t* valid, int n, int nlevels) {
-    for (int i = 0; i < n; i++)
-        if (valid[i] && (level[i] < 0 || level[i] >= nlevels)) return viorb_fail(VIORB_ERR_INVALID, "query %d: level %d out of range", i, level[i]);
-    return VIORB_OK;
 }
 
 int viorb_search_window_top1(viorb_frame_index* kf, const float* u, const float* v, const float* ur, const int32_t* pred_level,
@@ -637,14 +727,12 @@ int viorb_search_window_top1(viorb_frame_index* kf, const float* u, const float*
     if ((rc = check_levels(pred_level, valid, n, kf->dev.nlevels))) return rc;
     if ((rc = viorb_ctx_bind(c))) return rc;
     Arena a;
-    if ((rc = viorb_ctx_scratch(c, window_search_bytes(n), &a.base))) return rc;
+    if ((rc = arena_open(c, window_search_bytes(n), &a))) return rc;
     int *db = nullptr, *dd = nullptr;
-    if ((rc = window_search_upload(c, a, kf, u, v, ur, pred_level, valid, mp_desc, n, th, th_dist, inv_level_sigma2, &db, &dd))) return rc;
-    VCU(cudaGetLastError());
-    VCU(cudaMemcpyAsync(best_idx, db, (size_t)n * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    if (best_dist) VCU(cudaMemcpyAsync(best_dist, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
-    return VIORB_OK;
+    if ((rc = window_search_stage(c, a, kf, u, v, ur, pred_level, valid, mp_desc, n, th, th_dist, inv_level_sigma2, &db, &dd))) return rc;
+    a.get(best_idx, db, (size_t)n * 4);
+    if (best_dist) a.get(best_dist, dd, (size_t)n * 4);
+    return a.finish(c);
 }
 
 int viorb_search_by_sim3(viorb_frame_index* kf1, viorb_frame_index* kf2, const float* u12, const float* v12,
@@ -661,19 +749,17 @@ int viorb_search_by_sim3(viorb_frame_index* kf1, viorb_frame_index* kf2, const f
     if ((rc = check_levels(level12, valid12, n1, kf2->dev.nlevels)) || (rc = check_levels(level21, valid21, n2, kf1->dev.nlevels))) return rc;
     if ((rc = viorb_ctx_bind(c))) return rc;
     Arena a;
-    if ((rc = viorb_ctx_scratch(c, window_search_bytes(n1) + window_search_bytes(n2) + pad((size_t)std::max(n1, 1) * 4) + 1024, &a.base))) return rc;
+    if ((rc = arena_open(c, window_search_bytes(n1) + window_search_bytes(n2) + pad((size_t)std::max(n1, 1) * 4) + 1024, &a))) return rc;
     int *dm1 = nullptr, *dm2 = nullptr, *dd = nullptr;
     /* KF1's map points searched in KF2 (:1149-1226), KF2's in KF1 (:1228-1303), TH_HIGH = 100 */
-    if ((rc = window_search_upload(c, a, kf2, u12, v12, nullptr, level12, valid12, mp_desc1, n1, th, 100, nullptr, &dm1, &dd))) return rc;
-    if ((rc = window_search_upload(c, a, kf1, u21, v21, nullptr, level21, valid21, mp_desc2, n2, th, 100, nullptr, &dm2, &dd))) return rc;
+    if ((rc = window_search_stage(c, a, kf2, u12, v12, nullptr, level12, valid12, mp_desc1, n1, th, 100, nullptr, &dm1, &dd))) return rc;
+    if ((rc = window_search_stage(c, a, kf1, u21, v21, nullptr, level21, valid21, mp_desc2, n2, th, 100, nullptr, &dm2, &dd))) return rc;
     int* dmatch = a.take<int>(std::max(n1, 1));
     int* dn = a.take<int>(4);
     viorb_ctx_add_launches(c, viorb_launch_sim3_agree(dm1, dm2, n1, dmatch, dn, viorb_ctx_stream(c)));
-    VCU(cudaGetLastError());
-    VCU(cudaMemcpyAsync(match12, dmatch, (size_t)n1 * 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaMemcpyAsync(nfound, dn, 4, cudaMemcpyDeviceToHost, viorb_ctx_stream(c)));
-    VCU(cudaStreamSynchronize(viorb_ctx_stream(c)));
-    return VIORB_OK;
+    a.get(match12, dmatch, (size_t)n1 * 4);
+    a.get(nfound, dn, 4);
+    return a.finish(c);
 }
 
 }  // extern "C"

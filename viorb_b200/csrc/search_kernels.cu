@@ -243,12 +243,26 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const viorb_keypoint* 
     }
     if (tid == 1023) cellStart[NCELL] = part[1023];
     __syncthreads();
-    for (int i = tid; i < n; i += 1024) {
-        const int c = cellOf[i];
-        if (c < 0) continue;
-        int r = 0;
-        for (int j = 0; j < i; j++) r += cellOf[j] == c;
-        cellItems[cnt[c] + r] = i;
+    /* slot order inside a cell = keypoint index order (mGrid[x][y].push_back(i), :419-423): blocks of 1024 keypoints in
+     * index order, the 32 warps of a block take turns, and inside a warp a keypoint's slot is the cell's running count
+     * plus the number of lower lanes that fall into the same cell */
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int c = i < n ? cellOf[i] : -1;
+        const unsigned same = __match_any_sync(0xffffffffu, c);
+        const int rank = __popc(same & ((1u << lane) - 1));
+        for (int w = 0; w < 32; w++) {
+            if (warp == w) {
+                const int start = c >= 0 ? cnt[c] : 0;
+                __syncwarp();
+                if (c >= 0) {
+                    cellItems[start + rank] = i;
+                    if (rank == 0) cnt[c] = start + __popc(same);
+                }
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -296,9 +310,21 @@ __global__ void features_in_area_kernel(FrameIndexDev fi, float x, float y, floa
 }
 
 /* ------------------------------------------------------------------------------------------------
- * ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)     (:45-129)
- * single CTA, one warp per map point per pass, fixed-point iteration (see file header)
+ * The projection searches (ORBmatcher::SearchByProjection x4) in two steps:
+ *
+ *  (1) candidate lists -- every query (map point) in parallel, one warp each, many CTAs: enumerate the grid window,
+ *      apply every gate that does not depend on other queries (level range, window, stereo gate, keypoints that
+ *      already hold an observed map point on entry), compute the Hamming distances and keep the LIST_T best
+ *      candidates sorted by (distance, enumeration rank) plus the total number of passing candidates;
+ *  (2) ordered resolve -- one CTA.  In the reference a keypoint claimed by an earlier map point is skipped by later
+ *      ones (:87-89, :123), so query i depends on the queries j < i only: all queries are re-evaluated in parallel
+ *      (one thread each, walking its short list) until nothing changes -- the unique fixed point of that triangular
+ *      system, reached after (longest dependence chain + 1) sweeps, typically 2-3.  A query whose list runs out while
+ *      more candidates exist (more than LIST_T, with the best ones claimed) falls back to a full enumeration by a warp.
  * ---------------------------------------------------------------------------------------------- */
+#define LIST_T 8
+#define LIST_BUF 160
+
 struct LocalArgs {
     const float *projX, *projY, *projXR, *viewCos;
     const int* predLevel;
@@ -309,76 +335,6 @@ struct LocalArgs {
     float th, nnratio;
 };
 
-__global__ void __launch_bounds__(1024) search_local_kernel(FrameIndexDev fi, LocalArgs a, int* __restrict__ obs,
-                                                            int* __restrict__ claim, int* __restrict__ minClaim,
-                                                            int* __restrict__ match, int* __restrict__ nmatches) {
-    __shared__ int changed;
-    __shared__ int total;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int i = tid; i < a.nmp; i += blockDim.x) claim[i] = -1;
-    for (int k = tid; k < fi.n; k += blockDim.x) { minClaim[k] = INT_MAX; match[k] = -1; }
-    if (tid == 0) total = 0;
-    __syncthreads();
-    const bool bFactor = a.th != 1.0f;
-    for (int iter = 0; iter <= a.nmp; iter++) {
-        if (tid == 0) changed = 0;
-        __syncthreads();
-        for (int i = warp; i < a.nmp; i += nwarps) {
-            int result = -1;
-            if (a.valid[i]) {
-                const int lvl = a.predLevel[i];
-                float r = (double)a.viewCos[i] > 0.998 ? 2.5f : 4.0f;          /* RadiusByViewingCos :131-137 */
-                if (bFactor) r = __fmul_rn(r, a.th);
-                const float rad = __fmul_rn(r, fi.scale[lvl]);
-                const uint8_t* dMP = a.mpDesc + (size_t)i * 32;
-                const float projXR = a.projXR[i];
-                unsigned long long k1 = ~0ull, k2 = ~0ull;
-                for_features_in_area(fi, a.projX[i], a.projY[i], rad, lvl - 1, lvl, lane, [&](int pos, int idx, int oct) {
-                    if (obs[idx] > 0 || minClaim[idx] < i) return;               /* :87-89 (+ earlier matches :123) */
-                    const float ur = fi.uRight[idx];
-                    if (ur > 0) {
-                        const float er = fabsf(__fsub_rn(projXR, ur));
-                        if (er > rad) return;                                     /* :91-96 */
-                    }
-                    const int dist = hamming_rows(dMP, fi.desc + (size_t)idx * 32);
-                    const unsigned long long key = ((unsigned long long)dist << 48) | ((unsigned long long)pos << 28) |
-                                                   ((unsigned long long)oct << 20) | (unsigned)idx;
-                    if (key < k1) { k2 = k1; k1 = key; }
-                    else if (key < k2) k2 = key;
-                });
-                warp_two_min(k1, k2);
-                if (k1 != ~0ull) {
-                    const int bestDist = (int)(k1 >> 48), bestLevel = (int)((k1 >> 20) & 0xff), bestIdx = (int)(k1 & 0xfffff);
-                    const int bestDist2 = k2 != ~0ull ? (int)(k2 >> 48) : 256;
-                    const int bestLevel2 = k2 != ~0ull ? (int)((k2 >> 20) & 0xff) : -1;
-                    if (bestDist <= TH_HIGH) {
-                        if (!(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(a.nnratio, (float)bestDist2)))
-                            result = bestIdx;                                     /* :118-124 */
-                    }
-                }
-            }
-            if (lane == 0 && result != claim[i]) { claim[i] = result; changed = 1; }
-        }
-        __syncthreads();
-        if (!changed) break;
-        for (int k = tid; k < fi.n; k += blockDim.x) minClaim[k] = INT_MAX;
-        __syncthreads();
-        for (int i = tid; i < a.nmp; i += blockDim.x)
-            if (claim[i] >= 0 && a.nobs[i] > 0) atomicMin(&minClaim[claim[i]], i);
-        __syncthreads();
-    }
-    /* the last claimant of a keypoint owns it (F.mvpMapPoints[bestIdx]=pMP overwrites) */
-    for (int i = tid; i < a.nmp; i += blockDim.x)
-        if (claim[i] >= 0) { atomicMax(&match[claim[i]], i); atomicAdd(&total, 1); }
-    __syncthreads();
-    for (int k = tid; k < fi.n; k += blockDim.x)
-        if (match[k] >= 0) obs[k] = a.nobs[match[k]];
-    if (tid == 0) *nmatches = total;
-}
-
-/* ------------------------------------------------------------------------------------------------
- * ORBmatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, bMono)   (:1328-1471, search from :1378)
- * ---------------------------------------------------------------------------------------------- */
 struct FrameArgs {
     const float *u, *v, *invz, *lastAngle;
     const int* lastOctave;
@@ -389,6 +345,144 @@ struct FrameArgs {
     float th, mbf;
     int mode, checkOri, thHigh;
 };
+
+/* the window of one query: centre, radius, level range, stereo prediction */
+struct Window {
+    bool valid;
+    float x, y, rad, ur;
+    int minL, maxL;
+    bool stereoGate;
+};
+
+__device__ __forceinline__ Window make_window(const FrameIndexDev& fi, const LocalArgs& a, int i) {
+    Window w;
+    w.valid = a.valid[i] != 0;
+    if (!w.valid) return w;
+    const int lvl = a.predLevel[i];
+    float r = (double)a.viewCos[i] > 0.998 ? 2.5f : 4.0f;                      /* RadiusByViewingCos :131-137 */
+    if (a.th != 1.0f) r = __fmul_rn(r, a.th);
+    w.rad = __fmul_rn(r, fi.scale[lvl]);
+    w.x = a.projX[i]; w.y = a.projY[i]; w.ur = a.projXR[i];
+    w.minL = lvl - 1; w.maxL = lvl;                                            /* :68-69 */
+    w.stereoGate = true;
+    return w;
+}
+
+__device__ __forceinline__ Window make_window(const FrameIndexDev& fi, const FrameArgs& a, int i) {
+    Window w;
+    const float u = a.u[i], v = a.v[i];
+    w.valid = a.valid[i] && !(u < fi.minX || u > fi.maxX) && !(v < fi.minY || v > fi.maxY);
+    if (!w.valid) return w;
+    const int oct = a.lastOctave[i];
+    w.rad = __fmul_rn(a.th, fi.scale[oct]);
+    const int lm = a.mode & 7;
+    if (lm == 1) { w.minL = oct; w.maxL = -1; }                                /* forward  :1385-1386 */
+    else if (lm == 2) { w.minL = 0; w.maxL = oct; }                            /* backward :1387-1388 */
+    else if (lm == 3) { w.minL = oct - 1; w.maxL = oct; }                      /* Sim3 overload :375-379 */
+    else { w.minL = oct - 1; w.maxL = oct + 1; }
+    w.stereoGate = !(a.mode & 8);                                              /* the KeyFrame overloads have no uRight gate */
+    w.x = u; w.y = v;
+    w.ur = __fsub_rn(u, __fmul_rn(a.mbf, a.invz[i]));
+    return w;
+}
+
+/* key of one candidate, or ~0 when a gate rejects it.  LOCAL keys carry the octave (the ratio test of :118-124 compares
+ * the levels of best and second best): dist:16 | rank:20 | octave:8 | index:20; FRAME keys: dist:16 | rank:24 | index:24 */
+template <bool LOCAL>
+__device__ __forceinline__ unsigned long long candidate_key(const FrameIndexDev& fi, const Window& w, const uint8_t* dMP,
+                                                            int pos, int idx, int oct) {
+    const float uR = fi.uRight[idx];
+    if (w.stereoGate && uR > 0) {
+        const float er = fabsf(__fsub_rn(w.ur, uR));
+        if (er > w.rad) return ~0ull;                                           /* :91-96, :1408-1414 */
+    }
+    const unsigned long long dist = (unsigned long long)hamming_rows(dMP, fi.desc + (size_t)idx * 32);
+    if (LOCAL) return (dist << 48) | ((unsigned long long)pos << 28) | ((unsigned long long)oct << 20) | (unsigned)idx;
+    return (dist << 48) | ((unsigned long long)pos << 24) | (unsigned)idx;
+}
+template <bool LOCAL>
+__device__ __forceinline__ int key_index(unsigned long long k) { return LOCAL ? (int)(k & 0xfffff) : (int)(k & 0xffffff); }
+
+template <bool LOCAL, typename ARGS>
+__global__ void __launch_bounds__(128) candidate_lists_kernel(FrameIndexDev fi, ARGS a, int nq, const int* __restrict__ obs0,
+                                                              unsigned long long* __restrict__ listKeys, int* __restrict__ listCount) {
+    __shared__ unsigned long long buf[4][LIST_BUF];
+    __shared__ int cnt[4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * 4 + wib;
+    if (i >= nq) return;
+    const Window w = make_window(fi, a, i);
+    if (lane == 0) cnt[wib] = 0;
+    __syncwarp();
+    int total = 0;
+    if (w.valid) {
+        const uint8_t* dMP = a.mpDesc + (size_t)i * 32;
+        for_features_in_area(fi, w.x, w.y, w.rad, w.minL, w.maxL, lane, [&](int pos, int idx, int oct) {
+            if (obs0[idx] > 0) return;                                          /* :87-89 on entry */
+            const unsigned long long key = candidate_key<LOCAL>(fi, w, dMP, pos, idx, oct);
+            if (key == ~0ull) return;
+            const int slot = atomicAdd(&cnt[wib], 1);
+            if (slot < LIST_BUF) buf[wib][slot] = key;
+        });
+        __syncwarp();
+        total = cnt[wib];
+    }
+    if (total > LIST_BUF) {                                                     /* a window this crowded is resolved by full scans */
+        if (lane == 0) listCount[i] = -1;
+        return;
+    }
+    /* the LIST_T smallest keys in ascending order: keys are distinct (they contain the keypoint index) */
+    unsigned long long last = 0;
+    const int keep = min(total, LIST_T);
+    for (int t = 0; t < keep; t++) {
+        unsigned long long m = ~0ull;
+        for (int j = lane; j < total; j += 32) {
+            const unsigned long long k = buf[wib][j];
+            if ((t == 0 || k > last) && k < m) m = k;
+        }
+        m = warp_min_u64(m);
+        if (lane == 0) listKeys[(size_t)i * LIST_T + t] = m;
+        last = m;
+    }
+    if (lane == 0) listCount[i] = total;
+}
+
+/* full evaluation of one query by a warp under the current claims (the slow path of the resolve step) */
+template <bool LOCAL>
+__device__ __forceinline__ void scan_window(const FrameIndexDev& fi, const Window& w, const uint8_t* dMP, int i, int lane,
+                                            const int* __restrict__ obs0, const int* __restrict__ minClaim,
+                                            unsigned long long& k1, unsigned long long& k2) {
+    k1 = ~0ull; k2 = ~0ull;
+    if (!w.valid) return;
+    for_features_in_area(fi, w.x, w.y, w.rad, w.minL, w.maxL, lane, [&](int pos, int idx, int oct) {
+        if (obs0[idx] > 0 || minClaim[idx] < i) return;                         /* :87-89 (+ earlier matches :123) */
+        const unsigned long long key = candidate_key<LOCAL>(fi, w, dMP, pos, idx, oct);
+        if (key < k1) { k2 = k1; k1 = key; }
+        else if (key < k2) k2 = key;
+    });
+    warp_two_min(k1, k2);
+}
+
+/* accept / reject of the two best candidates: the local-map overload applies the ratio test between candidates of the
+ * same level (:118-124), the others a plain threshold (:1421, :1551, :389) */
+__device__ __forceinline__ int decide(const LocalArgs& a, unsigned long long k1, unsigned long long k2) {
+    const float nnratio = a.nnratio;
+    if (k1 == ~0ull) return -1;
+    const int bestDist = (int)(k1 >> 48), bestLevel = (int)((k1 >> 20) & 0xff);
+    const int bestDist2 = k2 != ~0ull ? (int)(k2 >> 48) : 256;
+    const int bestLevel2 = k2 != ~0ull ? (int)((k2 >> 20) & 0xff) : -1;
+    if (bestDist > TH_HIGH) return -1;
+    if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) return -1;
+    return (int)(k1 & 0xfffff);
+}
+__device__ __forceinline__ int decide(const FrameArgs& a, unsigned long long k1, unsigned long long) {
+    return (k1 != ~0ull && (int)(k1 >> 48) <= a.thHigh) ? (int)(k1 & 0xffffff) : -1;
+}
+/* the rotation-consistency histogram exists in the top-1 overloads only (:1432-1468) */
+__device__ __forceinline__ bool wants_histogram(const LocalArgs&) { return false; }
+__device__ __forceinline__ bool wants_histogram(const FrameArgs& a) { return a.checkOri != 0; }
+__device__ __forceinline__ float query_angle(const LocalArgs&, int) { return 0.f; }
+__device__ __forceinline__ float query_angle(const FrameArgs& a, int i) { return a.lastAngle[i]; }
 
 /* ComputeThreeMaxima :1602-1643 on bin counts */
 __device__ void three_maxima(const int* histo, int L, int& ind1, int& ind2, int& ind3) {
@@ -413,76 +507,83 @@ __device__ __forceinline__ int rot_bin(float a1, float a2) {
     return bin;
 }
 
-__global__ void __launch_bounds__(1024) search_frame_kernel(FrameIndexDev fi, FrameArgs a, int* __restrict__ obs,
-                                                            int* __restrict__ claim, int* __restrict__ minClaim,
-                                                            int* __restrict__ match, int* __restrict__ nmatches) {
-    __shared__ int changed;
-    __shared__ int total;
+/* the ordered resolve, one CTA.  LOCAL: SearchByProjection(Frame&, const vector<MapPoint*>&, th) (:45-129);
+ * otherwise the three overloads that share the top-1 loop (:1378-1468, :1473-1600, :290-403). */
+template <bool LOCAL, typename ARGS>
+__global__ void __launch_bounds__(1024) resolve_kernel(FrameIndexDev fi, ARGS a, int nq, const int* __restrict__ obs0,
+                                                       const unsigned long long* __restrict__ listKeys,
+                                                       const int* __restrict__ listCount, int* __restrict__ obs,
+                                                       int* __restrict__ claim, int* __restrict__ minClaim, int* __restrict__ slowQueue,
+                                                       int* __restrict__ match, int* __restrict__ nmatches) {
+    __shared__ int changed, total, nslow;
     __shared__ int hist[HISTO_LENGTH];
     __shared__ int keep[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int i = tid; i < a.nlast; i += blockDim.x) claim[i] = -1;
+    for (int i = tid; i < nq; i += blockDim.x) claim[i] = -1;
     for (int k = tid; k < fi.n; k += blockDim.x) { minClaim[k] = INT_MAX; match[k] = -1; }
     if (tid < HISTO_LENGTH) hist[tid] = 0;
     if (tid == 0) total = 0;
     __syncthreads();
-    for (int iter = 0; iter <= a.nlast; iter++) {
-        if (tid == 0) changed = 0;
+    for (int iter = 0; iter <= nq; iter++) {
+        if (tid == 0) { changed = 0; nslow = 0; }
         __syncthreads();
-        for (int i = warp; i < a.nlast; i += nwarps) {
-            int result = -1;
-            const float u = a.u[i], v = a.v[i];
-            if (a.valid[i] && !(u < fi.minX || u > fi.maxX) && !(v < fi.minY || v > fi.maxY)) {
-                const int oct = a.lastOctave[i];
-                const float radius = __fmul_rn(a.th, fi.scale[oct]);
-                int minL, maxL;
-                const int lm = a.mode & 7;
-                if (lm == 1) { minL = oct; maxL = -1; }                     /* forward  :1385-1386 */
-                else if (lm == 2) { minL = 0; maxL = oct; }                 /* backward :1387-1388 */
-                else if (lm == 3) { minL = oct - 1; maxL = oct; }           /* Sim3 overload :375-379 */
-                else { minL = oct - 1; maxL = oct + 1; }
-                const bool stereoGate = !(a.mode & 8);                      /* the KeyFrame overloads have no uRight gate */
-                const float ur = __fsub_rn(u, __fmul_rn(a.mbf, a.invz[i]));
-                const uint8_t* dMP = a.mpDesc + (size_t)i * 32;
-                unsigned long long k1 = ~0ull;
-                for_features_in_area(fi, u, v, radius, minL, maxL, lane, [&](int pos, int idx, int) {
-                    if (obs[idx] > 0 || minClaim[idx] < i) return;
-                    const float uR = fi.uRight[idx];
-                    if (stereoGate && uR > 0) {
-                        const float er = fabsf(__fsub_rn(ur, uR));
-                        if (er > radius) return;
-                    }
-                    const int dist = hamming_rows(dMP, fi.desc + (size_t)idx * 32);
-                    const unsigned long long key = ((unsigned long long)dist << 48) | ((unsigned long long)pos << 24) | (unsigned)idx;
-                    k1 = key < k1 ? key : k1;
-                });
-                k1 = warp_min_u64(k1);
-                if (k1 != ~0ull && (int)(k1 >> 48) <= a.thHigh) result = (int)(k1 & 0xffffff);
+        /* fast path: one thread per query walks its sorted list and skips what earlier queries hold */
+        for (int i = tid; i < nq; i += blockDim.x) {
+            const int cnt = listCount[i];
+            if (cnt == 0) continue;                                             /* no candidate at all: claim stays -1 */
+            bool slow = cnt < 0;
+            if (!slow) {
+                const int len = min(cnt, LIST_T);
+                unsigned long long k1 = ~0ull, k2 = ~0ull;
+                for (int t = 0; t < len; t++) {
+                    const unsigned long long k = listKeys[(size_t)i * LIST_T + t];
+                    if (minClaim[key_index<LOCAL>(k)] < i) continue;
+                    if (k1 == ~0ull) { k1 = k; if (!LOCAL) break; }
+                    else { k2 = k; break; }
+                }
+                /* the list answers the query unless it ran out before `more` candidates were seen */
+                const bool exhausted = cnt > LIST_T && (LOCAL ? k2 == ~0ull : k1 == ~0ull);
+                if (exhausted) slow = true;
+                else {
+                    const int result = decide(a, k1, k2);
+                    if (result != claim[i]) { claim[i] = result; changed = 1; }
+                }
             }
+            if (slow) slowQueue[atomicAdd(&nslow, 1)] = i;
+        }
+        __syncthreads();
+        for (int s = warp; s < nslow; s += nwarps) {
+            const int i = slowQueue[s];
+            const Window w = make_window(fi, a, i);
+            unsigned long long k1, k2;
+            scan_window<LOCAL>(fi, w, a.mpDesc + (size_t)i * 32, i, lane, obs0, minClaim, k1, k2);
+            const int result = decide(a, k1, k2);
             if (lane == 0 && result != claim[i]) { claim[i] = result; changed = 1; }
         }
         __syncthreads();
         if (!changed) break;
         for (int k = tid; k < fi.n; k += blockDim.x) minClaim[k] = INT_MAX;
         __syncthreads();
-        for (int i = tid; i < a.nlast; i += blockDim.x)
+        for (int i = tid; i < nq; i += blockDim.x)
             if (claim[i] >= 0 && a.nobs[i] > 0) atomicMin(&minClaim[claim[i]], i);
         __syncthreads();
     }
-    for (int i = tid; i < a.nlast; i += blockDim.x)
+    /* the last claimant of a keypoint owns it (F.mvpMapPoints[bestIdx]=pMP overwrites) */
+    const bool checkOri = wants_histogram(a);
+    for (int i = tid; i < nq; i += blockDim.x)
         if (claim[i] >= 0) {
             atomicMax(&match[claim[i]], i);
             atomicAdd(&total, 1);
-            if (a.checkOri) atomicAdd(&hist[rot_bin(a.lastAngle[i], fi.kps[claim[i]].angle)], 1);
+            if (checkOri) atomicAdd(&hist[rot_bin(query_angle(a, i), fi.kps[claim[i]].angle)], 1);
         }
     __syncthreads();
-    if (a.checkOri) {
+    if (checkOri) {
         if (tid == 0) three_maxima(hist, HISTO_LENGTH, keep[0], keep[1], keep[2]);
         __syncthreads();
         /* every claim in a rejected bin nulls its keypoint and decrements the count (:1455-1465) */
-        for (int i = tid; i < a.nlast; i += blockDim.x)
+        for (int i = tid; i < nq; i += blockDim.x)
             if (claim[i] >= 0) {
-                const int b = rot_bin(a.lastAngle[i], fi.kps[claim[i]].angle);
+                const int b = rot_bin(query_angle(a, i), fi.kps[claim[i]].angle);
                 if (b != keep[0] && b != keep[1] && b != keep[2]) { match[claim[i]] = -2; atomicSub(&total, 1); }
             }
         __syncthreads();
@@ -490,7 +591,8 @@ __global__ void __launch_bounds__(1024) search_frame_kernel(FrameIndexDev fi, Fr
     for (int k = tid; k < fi.n; k += blockDim.x) {
         const int m = match[k];
         if (m >= 0) obs[k] = a.nobs[m];
-        else if (m == -2) { obs[k] = 0; match[k] = -1; }
+        else if (m == -2) obs[k] = 0;                  /* the caller sees -2: matched, then removed (:1455-1465) */
+        else obs[k] = obs0[k];
     }
     if (tid == 0) *nmatches = total;
 }
@@ -1029,26 +1131,53 @@ int viorb_launch_features_in_area(const FrameIndexDev& fi, float x, float y, flo
     return 1;
 }
 
+int viorb_search_scratch_ints(int nq, int nf) {
+    /* list keys (2 ints each) + list counts + claim + slow queue per query, minClaim per frame keypoint */
+    return nq * (2 * LIST_T + 3) + nf + 64;
+}
+
 int viorb_launch_search_local(const FrameIndexDev& fi, const float* projX, const float* projY, const float* projXR,
                               const int* predLevel, const float* viewCos, const uint8_t* valid, const int* nobs,
-                              const uint8_t* mpDesc, int nmp, float th, float nnratio, int* d_obs, int* d_claim,
-                              int* d_minClaim, int* d_match, int* d_nmatches, cudaStream_t s) {
+                              const uint8_t* mpDesc, int nmp, float th, float nnratio, const int* d_obs0, int* d_obs,
+                              int* d_scratch, int* d_match, int* d_nmatches, cudaStream_t s) {
     LocalArgs a;
     a.projX = projX; a.projY = projY; a.projXR = projXR; a.viewCos = viewCos; a.predLevel = predLevel;
     a.valid = valid; a.nobs = nobs; a.mpDesc = mpDesc; a.nmp = nmp; a.th = th; a.nnratio = nnratio;
-    search_local_kernel<<<1, 1024, 0, s>>>(fi, a, d_obs, d_claim, d_minClaim, d_match, d_nmatches);
-    return 1;
+    const int nq = nmp > 0 ? nmp : 0;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(d_scratch);
+    int* count = d_scratch + (size_t)2 * LIST_T * nq;
+    int* claim = count + nq;
+    int* slow = claim + nq;
+    int* minClaim = slow + nq;
+    int launches = 1;
+    if (nq > 0) {
+        candidate_lists_kernel<true, LocalArgs><<<(nq + 3) / 4, 128, 0, s>>>(fi, a, nq, d_obs0, keys, count);
+        launches++;
+    }
+    resolve_kernel<true, LocalArgs><<<1, 1024, 0, s>>>(fi, a, nq, d_obs0, keys, count, d_obs, claim, minClaim, slow, d_match, d_nmatches);
+    return launches;
 }
 
 int viorb_launch_search_frame(const FrameIndexDev& fi, const float* u, const float* v, const float* invz,
                               const int* lastOctave, const float* lastAngle, const uint8_t* valid, const int* nobs,
                               const uint8_t* mpDesc, int nlast, float th, float mbf, int mode, int checkOri, int thHigh,
-                              int* d_obs, int* d_claim, int* d_minClaim, int* d_match, int* d_nmatches, cudaStream_t s) {
+                              const int* d_obs0, int* d_obs, int* d_scratch, int* d_match, int* d_nmatches, cudaStream_t s) {
     FrameArgs a;
     a.u = u; a.v = v; a.invz = invz; a.lastAngle = lastAngle; a.lastOctave = lastOctave; a.valid = valid; a.nobs = nobs;
     a.mpDesc = mpDesc; a.nlast = nlast; a.th = th; a.mbf = mbf; a.mode = mode; a.checkOri = checkOri; a.thHigh = thHigh;
-    search_frame_kernel<<<1, 1024, 0, s>>>(fi, a, d_obs, d_claim, d_minClaim, d_match, d_nmatches);
-    return 1;
+    const int nq = nlast > 0 ? nlast : 0;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(d_scratch);
+    int* count = d_scratch + (size_t)2 * LIST_T * nq;
+    int* claim = count + nq;
+    int* slow = claim + nq;
+    int* minClaim = slow + nq;
+    int launches = 1;
+    if (nq > 0) {
+        candidate_lists_kernel<false, FrameArgs><<<(nq + 3) / 4, 128, 0, s>>>(fi, a, nq, d_obs0, keys, count);
+        launches++;
+    }
+    resolve_kernel<false, FrameArgs><<<1, 1024, 0, s>>>(fi, a, nq, d_obs0, keys, count, d_obs, claim, minClaim, slow, d_match, d_nmatches);
+    return launches;
 }
 
 int viorb_launch_triangulation(const viorb_keypoint* k1, const uint8_t* d1, const float* ur1, const uint8_t* mp1, int n1,

@@ -14,6 +14,11 @@ int viorb_ctx_bind(viorb_ctx* c);
 /* per-context device scratch arena, grown on demand; contents are valid until the next call on the context */
 int viorb_ctx_scratch(viorb_ctx* c, size_t bytes, uint8_t** out);
 void viorb_ctx_add_launches(viorb_ctx* c, int n);
+/* pinned host staging blocks (slot 0: searches, slot 1: frame-index builds) and the pool of frame-index device blocks */
+int viorb_ctx_stage(viorb_ctx* c, int slot, size_t bytes, uint8_t** out);
+int viorb_ctx_stage_mark(viorb_ctx* c, int slot);
+int viorb_ctx_block_get(viorb_ctx* c, size_t bytes, uint8_t** out, size_t* got);
+void viorb_ctx_block_put(viorb_ctx* c, uint8_t* p, size_t bytes);
 viorb_ctx* viorb_extractor_ctx(viorb_extractor* e);
 
 #define VCU(call)                                                                                              \

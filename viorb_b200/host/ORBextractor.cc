@@ -14,8 +14,8 @@ static void check(int rc, const char* what) {
 }
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
-    : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
-      mvImagePyramid(this), mpCtx(nullptr), mpHandle(nullptr), mbDownloadPyramid(false), mbPyramidStale(false) {
+    : mvImagePyramid(this), nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
+      mpCtx(nullptr), mpHandle(nullptr), mbDownloadPyramid(false), mbPyramidStale(false) {
     check(viorb_ctx_create(0, nullptr, &mpCtx), "viorb_ctx_create");
     check(viorb_extractor_create(mpCtx, nfeatures, _scaleFactor, nlevels, iniThFAST, minThFAST, &mpHandle), "viorb_extractor_create");
     mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);

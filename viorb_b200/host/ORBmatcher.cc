@@ -194,9 +194,9 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
           "viorb_search_by_projection_frame");
     for (int k = 0; k < CurrentFrame.N; k++) {
         if (match[k] >= 0) CurrentFrame.mvpMapPoints[k] = LastFrame.mvpMapPoints[match[k]];
-        else if (obs[k] == 0 && CurrentFrame.mvpMapPoints[k] && CurrentFrame.mvpMapPoints[k]->Observations() > 0) {
-            /* unreachable: only this call can clear an entry, and cleared entries never held observations */
-        }
+        /* matched, then rejected by the rotation histogram: the reference nulls the slot (:1460), also when it held a map
+         * point without observations before the call (such a point does not block the search, :1403-1405) */
+        else if (match[k] == -2) CurrentFrame.mvpMapPoints[k] = static_cast<MapPoint*>(NULL);
     }
     return n;
 }
@@ -246,8 +246,10 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std
                                            valid.data(), nobs.data(), desc.data(), nq, th, CurrentFrame.mbf, 0 | 8,
                                            mbCheckOrientation, ORBdist, match.data(), &n),
           "viorb_search_by_projection_frame");
-    for (int k = 0; k < CurrentFrame.N; k++)
+    for (int k = 0; k < CurrentFrame.N; k++) {
         if (match[k] >= 0) CurrentFrame.mvpMapPoints[k] = vpMPs[match[k]];
+        else if (match[k] == -2) CurrentFrame.mvpMapPoints[k] = static_cast<MapPoint*>(NULL);    /* :1586 */
+    }
     return n;
 }
 
