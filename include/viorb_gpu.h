@@ -69,6 +69,14 @@ int viorb_extractor_destroy(viorb_extractor* ex);
  * host-buffer batch call uses 32..128 depending on the batch so that short batches still pipeline) and the
  * candidate pool per level as a fraction 1/div of the level's pixel count. */
 int viorb_extractor_configure(viorb_extractor* ex, int chunk_frames, int cand_div);
+/* Which OpenCV the GaussianBlur(workingMat, ..., Size(7,7), 2, 2, BORDER_REFLECT_101) of src/ORBextractor.cc:1086 is:
+ * the 8-bit kernel differs between releases and the reference does not vendor OpenCV.
+ *   VIORB_GAUSSIAN_OPENCV4  (default) OpenCV >= 3.4 fixed point [18,34,48,56,48,34,18]/256 -- bit-equal to cv2 4.13;
+ *   VIORB_GAUSSIAN_OPENCV24 OpenCV 2.4.x, the version the reference pins (CMakeLists.txt:31, README.md:58) and its
+ *                           shipped libORB_SLAM2.so links: [18,34,49,55,49,34,18]/256, saturating.
+ * Keypoints are unaffected (the blur only feeds the descriptor tests); descriptors differ in a few bits. */
+enum { VIORB_GAUSSIAN_OPENCV4 = 0, VIORB_GAUSSIAN_OPENCV24 = 1 };
+int viorb_extractor_set_gaussian(viorb_extractor* ex, int opencv_variant);
 
 /* per-stage device timing (CUDA events on the context stream around each stage of every pass):
  * ms[0..3] = pyramid, FAST, quadtree, orient+describe, summed over `passes` passes since the last query. */

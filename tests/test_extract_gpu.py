@@ -321,3 +321,84 @@ def test_differential_fuzz():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_extract.py"), "80", "3"], capture_output=True,
                        text=True, cwd=ROOT, timeout=600)
     assert p.returncode == 0 and " 0 mismatches" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("kind", ["scene", "saturated"])
+def test_opencv24_gaussian_variant(api, ctx, oracle, kind):
+    """viorb_extractor_set_gaussian(VIORB_GAUSSIAN_OPENCV24): the 8-bit kernel of the OpenCV the reference pins
+    ([18,34,49,55,49,34,18], sum 257, saturating) -- descriptors bit-equal to the oracle / the reference built with
+    those taps, and back to the default taps afterwards"""
+    img = synth.frame(480, 752, 0)
+    if kind == "saturated":                                   # 255-valued regions drive the 257/256 gain into saturation
+        img = img.copy()
+        img[img > 140] = 255
+    ex = api.ORBextractor(1000, 1.2, 8, 20, 7, ctx=ctx)
+    k0, d0 = ex(img)
+    ex.set_gaussian(1)
+    k1, d1 = ex(img)
+    ref = oracle.Extractor(1000, 1.2, 8, 20, 7)
+    from oracle import oracle_py, ref_py
+    under_reference = oracle_py._override is not None
+    if under_reference:
+        ref_py.set_gaussian_variant(1)
+    else:
+        ref.set_gaussian_variant(1)
+    try:
+        kr, dr = ref(img)
+    finally:
+        if under_reference:
+            ref_py.set_gaussian_variant(0)
+    assert len(k1) == len(kr) > 500 and k1.tobytes() == kr.tobytes() and (d1 == dr).all()
+    assert k0.tobytes() == k1.tobytes() and (d0 != d1).any()
+    ex.set_gaussian(0)
+    k2, d2 = ex(img)
+    assert (d2 == d0).all()
+    ex.close()
+
+
+def test_extract_equals_committed_reference_outputs(api, ctx):
+    """GPU output against files written by the REFERENCE ITSELF (src/ORBextractor.cc compiled unmodified and run in the
+    build container, tests/golden/make_ref_golden.py): full records for three configurations, digests for the KITTI
+    stereo pair, 1080p, 4K and the differential-fuzz corpus.  Needs neither the oracle nor the reference library."""
+    import json
+    from util import extraction_digest, fuzz_extract_cases
+    gold = os.path.join(ROOT, "tests", "golden")
+    for cfg, seed in (("euroc", 0), ("odd", 5), ("kitti12", 7)):
+        g = np.load(os.path.join(gold, "ref_extract_%s_seed%d.npz" % (cfg, seed)))
+        h, w, nf, sf, nl, it, mt = CONFIGS[cfg]
+        ex = api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx)
+        k, d = ex(synth.frame(h, w, seed))
+        assert k.tobytes() == g["keypoints"].tobytes() and (d == g["descriptors"]).all(), cfg
+        ex.close()
+    hashes = json.load(open(os.path.join(gold, "ref_extract_hashes.json")))
+    left, right, _ = synth.stereo_pair(376, 1241, 7)
+    ex = api.ORBextractor(*CONFIGS["kitti"][2:], ctx=ctx)
+    for name, img in (("kitti_left", left), ("kitti_right", right)):
+        k, d = ex(img)
+        assert extraction_digest(k, d) == hashes["configs"][name]["digest"], name
+    ex.close()
+    for cfg, seed in (("euroc", 1), ("euroc", 4095), ("hd", 0), ("uhd", 0)):
+        h, w = CONFIGS[cfg][:2]
+        ex = api.ORBextractor(*CONFIGS[cfg][2:], ctx=ctx)
+        k, d = ex(synth.frame(h, w, seed))
+        assert extraction_digest(k, d) == hashes["configs"]["%s_seed%d" % (cfg, seed)]["digest"], (cfg, seed)
+        ex.close()
+    ex = api.ORBextractor(*CONFIGS["euroc"][2:], ctx=ctx)
+    ex.set_gaussian(1)
+    k, d = ex(synth.frame(480, 752, 0))
+    assert extraction_digest(k, d) == hashes["cv24"]["euroc_seed0"]["digest"]
+    ex.close()
+    compared = 0
+    for c, img, params in fuzz_extract_cases(hashes["fuzz"]["cases"], hashes["fuzz"]["seed"]):
+        if str(c) not in hashes["fuzz"]["digest"]:
+            continue
+        try:
+            ex = api.ORBextractor(*params, ctx=ctx)
+            k, d = ex(img)
+        except api.ViorbError as e:
+            assert e.code == -4, e          # outside the documented envelope: refused, never guessed
+            continue
+        assert extraction_digest(k, d) == hashes["fuzz"]["digest"][str(c)], "fuzz case %d %s" % (c, (img.shape, params))
+        ex.close()
+        compared += 1
+    assert compared >= 120

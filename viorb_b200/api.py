@@ -48,6 +48,7 @@ def lib():
         "viorb_extractor_create": [vp, i32, f32, i32, i32, i32, pp],
         "viorb_extractor_destroy": [vp],
         "viorb_extractor_configure": [vp, i32, i32],
+        "viorb_extractor_set_gaussian": [vp, i32],
         "viorb_extractor_tables": [vp, pi, vp, vp, vp, vp, vp],
         "viorb_extractor_profile": [vp, i32],
         "viorb_extractor_stage_ms": [vp, vp, pi],
@@ -232,6 +233,10 @@ class ORBextractor:
 
     def configure(self, chunk_frames=0, cand_div=0):
         _ck(lib().viorb_extractor_configure(self.h, chunk_frames, cand_div))
+
+    def set_gaussian(self, opencv_variant):
+        """0 = OpenCV >= 3.4 taps (default), 1 = OpenCV 2.4 taps (viorb_extractor_set_gaussian)"""
+        _ck(lib().viorb_extractor_set_gaussian(self.h, int(opencv_variant)))
 
     def __call__(self, image, mask=None):
         """operator()(image, mask, keypoints, descriptors): returns (keypoints[KEYPOINT], descriptors[N,32])."""

@@ -90,6 +90,7 @@ struct viorb_extractor {
     std::vector<float> scale, invScale, sigma2, invSigma2;
     std::vector<int> quota;
     int chunk = 128, candDiv = 16;
+    int gaussVariant = 0;        /* viorb_extractor_set_gaussian */
     bool chunkUser = false;      /* viorb_extractor_configure chose the pass size */
     /* geometry for the current image size */
     int rows = 0, cols = 0;
@@ -179,7 +180,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     FrameGeom& g = e->geom;
     memset(&g, 0, sizeof(g));
     g.nlevels = e->nlevels; g.rows = rows; g.cols = cols; g.iniTh = e->iniTh; g.minTh = e->minTh;
-    g.reserved = 0;
+    g.gaussVariant = e->gaussVariant;
     size_t pyrOff = 0;
     int cellBase = 0, candBase = 0, selBase = 0, xtab = 0, ytab = 0, nodeCap = 0;
     for (int l = 0; l < e->nlevels; l++) {
@@ -549,6 +550,16 @@ int viorb_extractor_destroy(viorb_extractor* e) {
         if (e->evOut[i]) cudaEventDestroy(e->evOut[i]);
     }
     delete e;
+    return VIORB_OK;
+}
+
+int viorb_extractor_set_gaussian(viorb_extractor* e, int opencv_variant) {
+    if (!e) return fail(VIORB_ERR_INVALID, "extractor is NULL");
+    if (opencv_variant != VIORB_GAUSSIAN_OPENCV4 && opencv_variant != VIORB_GAUSSIAN_OPENCV24)
+        return fail(VIORB_ERR_INVALID, "unknown Gaussian variant %d", opencv_variant);
+    e->gaussVariant = opencv_variant;
+    e->geom.gaussVariant = opencv_variant;
+    e->geomGen++;                  /* the captured single-frame graph holds the kernel choice */
     return VIORB_OK;
 }
 

@@ -11,6 +11,8 @@
  * FMA contraction (the file is compiled with -fmad=false and uses __f*_rn where order matters).
  * Nothing here is a dense contraction: no tensor cores, by design.
  */
+#include <mutex>
+
 #include "extractor_kernels.cuh"
 
 #include <cuda.h>
@@ -1047,22 +1049,28 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 /* Horizontal blur pass of orient_describe_kernel for a patch whose rows sit SH bytes into their first word.
  * The 7-tap window of output column 4j+i starts at byte i+SH of raw word j: instead of shifting the pixels into place
  * the tap words are shifted (compile-time constants per SH), two or three IDP.4A per output and no PRMT. */
-__host__ __device__ constexpr unsigned blur_tap_word(int o, int w) {
-    const int k[7] = {18, 34, 48, 56, 48, 34, 18};
+/* GV selects the 8-bit Gaussian kernel of cv::GaussianBlur(7x7, sigma 2): 0 = OpenCV >= 3.4 (fixed point
+ * [18,34,48,56,48,34,18]/256), 1 = OpenCV 2.4, the version the reference pins (round(getGaussianKernel * 256) =
+ * [18,34,49,55,49,34,18], sum 257; the result saturates at 255).  viorb_extractor_set_gaussian. */
+__host__ __device__ constexpr int blur_tap(int gv, int p) {
+    const int k[2][7] = {{18, 34, 48, 56, 48, 34, 18}, {18, 34, 49, 55, 49, 34, 18}};
+    return k[gv][p];
+}
+__host__ __device__ constexpr unsigned blur_tap_word(int gv, int o, int w) {
     unsigned r = 0;
     for (int b = 0; b < 4; b++) {
         const int p = 4 * w + b - o;
-        if (p >= 0 && p < 7) r |= (unsigned)k[p] << (8 * b);
+        if (p >= 0 && p < 7) r |= (unsigned)blur_tap(gv, p) << (8 * b);
     }
     return r;
 }
-template <int O>
+template <int GV, int O>
 __device__ __forceinline__ unsigned blur_hsum(unsigned r0, unsigned r1, unsigned r2, unsigned r3) {
     unsigned acc = 0;
-    if constexpr (blur_tap_word(O, 3) != 0) acc = __dp4a(r3, blur_tap_word(O, 3), acc);
-    if constexpr (blur_tap_word(O, 2) != 0) acc = __dp4a(r2, blur_tap_word(O, 2), acc);
-    if constexpr (blur_tap_word(O, 1) != 0) acc = __dp4a(r1, blur_tap_word(O, 1), acc);
-    if constexpr (blur_tap_word(O, 0) != 0) acc = __dp4a(r0, blur_tap_word(O, 0), acc);
+    if constexpr (blur_tap_word(GV, O, 3) != 0) acc = __dp4a(r3, blur_tap_word(GV, O, 3), acc);
+    if constexpr (blur_tap_word(GV, O, 2) != 0) acc = __dp4a(r2, blur_tap_word(GV, O, 2), acc);
+    if constexpr (blur_tap_word(GV, O, 1) != 0) acc = __dp4a(r1, blur_tap_word(GV, O, 1), acc);
+    if constexpr (blur_tap_word(GV, O, 0) != 0) acc = __dp4a(r0, blur_tap_word(GV, O, 0), acc);
     return acc;
 }
 /* Shared-memory banks (the L1 data pipe is this kernel's busiest unit): an instruction covers columns 0..31
@@ -1071,7 +1079,7 @@ __device__ __forceinline__ unsigned blur_hsum(unsigned r0, unsigned r1, unsigned
  * banks; row pair rp is stored at pos(rp) = 6*(rp&3) + (rp>>2), which makes the four row pairs of an
  * instruction neighbours in Hw and the transposed stores conflict-free as well.  Columns 32..36 are a seventh
  * instruction with one row pair per lane. */
-template <int SH>
+template <int GV, int SH>
 __device__ __forceinline__ void blur_h_pass(const unsigned* __restrict__ P, unsigned* __restrict__ Hw, int lane) {
     const int q = lane >> 3, j = lane & 7;
 #pragma unroll 1
@@ -1084,10 +1092,10 @@ __device__ __forceinline__ void blur_h_pass(const unsigned* __restrict__ P, unsi
         const unsigned* p1 = rp < 21 ? p0 + PWORDS : p0;     /* row 43 does not exist: its sums are never used */
         const unsigned a0 = p0[0], a1 = p0[1], a2 = p0[2], a3 = p0[3], b0 = p1[0], b1 = p1[1], b2 = p1[2], b3 = p1[3];
         unsigned* dst = &Hw[(4 * j) * HT_WORDS + 6 * (rp & 3) + (rp >> 2)];
-        dst[0 * HT_WORDS] = __byte_perm(blur_hsum<SH + 0>(a0, a1, a2, a3), blur_hsum<SH + 0>(b0, b1, b2, b3), 0x5410);
-        dst[1 * HT_WORDS] = __byte_perm(blur_hsum<SH + 1>(a0, a1, a2, a3), blur_hsum<SH + 1>(b0, b1, b2, b3), 0x5410);
-        dst[2 * HT_WORDS] = __byte_perm(blur_hsum<SH + 2>(a0, a1, a2, a3), blur_hsum<SH + 2>(b0, b1, b2, b3), 0x5410);
-        dst[3 * HT_WORDS] = __byte_perm(blur_hsum<SH + 3>(a0, a1, a2, a3), blur_hsum<SH + 3>(b0, b1, b2, b3), 0x5410);
+        dst[0 * HT_WORDS] = __byte_perm(blur_hsum<GV, SH + 0>(a0, a1, a2, a3), blur_hsum<GV, SH + 0>(b0, b1, b2, b3), 0x5410);
+        dst[1 * HT_WORDS] = __byte_perm(blur_hsum<GV, SH + 1>(a0, a1, a2, a3), blur_hsum<GV, SH + 1>(b0, b1, b2, b3), 0x5410);
+        dst[2 * HT_WORDS] = __byte_perm(blur_hsum<GV, SH + 2>(a0, a1, a2, a3), blur_hsum<GV, SH + 2>(b0, b1, b2, b3), 0x5410);
+        dst[3 * HT_WORDS] = __byte_perm(blur_hsum<GV, SH + 3>(a0, a1, a2, a3), blur_hsum<GV, SH + 3>(b0, b1, b2, b3), 0x5410);
     }
     if (lane < 22) {                                           /* columns 32..36 of row pair `lane` */
         const int rp = lane;
@@ -1095,11 +1103,11 @@ __device__ __forceinline__ void blur_h_pass(const unsigned* __restrict__ P, unsi
         const unsigned* p1 = rp < 21 ? p0 + PWORDS : p0;
         const unsigned a0 = p0[0], a1 = p0[1], a2 = p0[2], a3 = p0[3], b0 = p1[0], b1 = p1[1], b2 = p1[2], b3 = p1[3];
         unsigned* dst = &Hw[32 * HT_WORDS + 6 * (rp & 3) + (rp >> 2)];
-        dst[0 * HT_WORDS] = __byte_perm(blur_hsum<SH + 0>(a0, a1, a2, a3), blur_hsum<SH + 0>(b0, b1, b2, b3), 0x5410);
-        dst[1 * HT_WORDS] = __byte_perm(blur_hsum<SH + 1>(a0, a1, a2, a3), blur_hsum<SH + 1>(b0, b1, b2, b3), 0x5410);
-        dst[2 * HT_WORDS] = __byte_perm(blur_hsum<SH + 2>(a0, a1, a2, a3), blur_hsum<SH + 2>(b0, b1, b2, b3), 0x5410);
-        dst[3 * HT_WORDS] = __byte_perm(blur_hsum<SH + 3>(a0, a1, a2, a3), blur_hsum<SH + 3>(b0, b1, b2, b3), 0x5410);
-        dst[4 * HT_WORDS] = __byte_perm(blur_hsum<SH + 4>(a0, a1, a2, a3), blur_hsum<SH + 4>(b0, b1, b2, b3), 0x5410);
+        dst[0 * HT_WORDS] = __byte_perm(blur_hsum<GV, SH + 0>(a0, a1, a2, a3), blur_hsum<GV, SH + 0>(b0, b1, b2, b3), 0x5410);
+        dst[1 * HT_WORDS] = __byte_perm(blur_hsum<GV, SH + 1>(a0, a1, a2, a3), blur_hsum<GV, SH + 1>(b0, b1, b2, b3), 0x5410);
+        dst[2 * HT_WORDS] = __byte_perm(blur_hsum<GV, SH + 2>(a0, a1, a2, a3), blur_hsum<GV, SH + 2>(b0, b1, b2, b3), 0x5410);
+        dst[3 * HT_WORDS] = __byte_perm(blur_hsum<GV, SH + 3>(a0, a1, a2, a3), blur_hsum<GV, SH + 3>(b0, b1, b2, b3), 0x5410);
+        dst[4 * HT_WORDS] = __byte_perm(blur_hsum<GV, SH + 4>(a0, a1, a2, a3), blur_hsum<GV, SH + 4>(b0, b1, b2, b3), 0x5410);
     }
 }
 
@@ -1149,6 +1157,7 @@ __device__ __forceinline__ void sincosf_glibc(float y, float* sinp, float* cosp)
     else { *sinp = sv; *cosp = cv; }
 }
 
+template <int GV>
 __global__ void __launch_bounds__(DESC_WARPS * 32, 6) orient_describe_kernel(const __grid_constant__ FrameGeom g,
                                                                           const uint8_t* __restrict__ pyr,
                                                                           const uint32_t* __restrict__ sel,
@@ -1249,10 +1258,10 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) orient_describe_kernel(con
      * vertically adjacent rows are packed into one word and stored transposed (Hw[c][pos(rp)]) so the vertical
      * pass can use IDP.2A on row pairs.  One instantiation per byte offset of the patch rows (warp-uniform). */
     switch (sh) {
-        case 0: blur_h_pass<0>(P, Hw, lane); break;
-        case 1: blur_h_pass<1>(P, Hw, lane); break;
-        case 2: blur_h_pass<2>(P, Hw, lane); break;
-        default: blur_h_pass<3>(P, Hw, lane); break;
+        case 0: blur_h_pass<GV, 0>(P, Hw, lane); break;
+        case 1: blur_h_pass<GV, 1>(P, Hw, lane); break;
+        case 2: blur_h_pass<GV, 2>(P, Hw, lane); break;
+        default: blur_h_pass<GV, 3>(P, Hw, lane); break;
     }
     __syncwarp();
     /* vertical pass: a task = 8 output rows (segment seg) of one column, read as 7 words (row pairs 4*seg + k at
@@ -1262,8 +1271,10 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) orient_describe_kernel(con
      * of an instruction hold neighbouring columns, whose words are 25 (loads) and 11 (stores) banks apart. */
     uint8_t* Vt = reinterpret_cast<uint8_t*>(P);       /* the patch is dead now */
     {
-        const unsigned E01 = 18u | (34u << 8), E23 = 48u | (56u << 8), E45 = 48u | (34u << 8), E6 = 18u;   /* even row */
-        const unsigned O0 = 18u << 8, O12 = 34u | (48u << 8), O34 = 56u | (48u << 8), O56 = 34u | (18u << 8);  /* odd row */
+        constexpr unsigned K0 = blur_tap(GV, 0), K1 = blur_tap(GV, 1), K2 = blur_tap(GV, 2), K3 = blur_tap(GV, 3);
+        constexpr unsigned K4 = blur_tap(GV, 4), K5 = blur_tap(GV, 5), K6 = blur_tap(GV, 6);
+        const unsigned E01 = K0 | (K1 << 8), E23 = K2 | (K3 << 8), E45 = K4 | (K5 << 8), E6 = K6;              /* even row */
+        const unsigned O0 = K0 << 8, O12 = K1 | (K2 << 8), O34 = K3 | (K4 << 8), O56 = K5 | (K6 << 8);          /* odd row */
         for (int t = lane; t < BW * 5; t += 32) {
             const int seg = t / BW, c = t - seg * BW;        /* rows 8*seg .. 8*seg+7 */
             const unsigned* hcol = &Hw[c * HT_WORDS + seg];
@@ -1273,8 +1284,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) orient_describe_kernel(con
             unsigned pr[4];          /* rows 2k, 2k+1: the sums are < 2^24, so (sum >> 16) is byte 2 -- picked by PRMT */
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const unsigned ve = __dp2a_lo(w[k], E01, __dp2a_lo(w[k + 1], E23, __dp2a_lo(w[k + 2], E45, __dp2a_lo(w[k + 3], E6, 32768u))));
-                const unsigned vo = __dp2a_lo(w[k], O0, __dp2a_lo(w[k + 1], O12, __dp2a_lo(w[k + 2], O34, __dp2a_lo(w[k + 3], O56, 32768u))));
+                unsigned ve = __dp2a_lo(w[k], E01, __dp2a_lo(w[k + 1], E23, __dp2a_lo(w[k + 2], E45, __dp2a_lo(w[k + 3], E6, 32768u))));
+                unsigned vo = __dp2a_lo(w[k], O0, __dp2a_lo(w[k + 1], O12, __dp2a_lo(w[k + 2], O34, __dp2a_lo(w[k + 3], O56, 32768u))));
+                if constexpr (GV == 1) {              /* taps sum to 257: a saturated neighbourhood reaches 257 -> saturate_cast<uchar> */
+                    ve = min(ve, 0x00ffffffu);
+                    vo = min(vo, 0x00ffffffu);
+                }
                 pr[k] = __byte_perm(ve, vo, 0x0062);
             }
             unsigned* dst = reinterpret_cast<unsigned*>(Vt + c * VT_STRIDE + 8 * seg);
@@ -1348,6 +1363,8 @@ size_t viorb_fast_smem_bytes(const FrameGeom& g) {
 
 int viorb_fast_prepare(const FrameGeom& g) {
     static int current[64] = {0};        /* raise-only, see viorb_octree_prepare */
+    static std::mutex guard;             /* extractors are created from several threads (stereo: Frame.cc:258-261) */
+    std::lock_guard<std::mutex> lock(guard);
     int dev = 0;
     cudaGetDevice(&dev);
     const int smem = (int)viorb_fast_smem_bytes(g);
@@ -1424,6 +1441,8 @@ size_t viorb_octree_smem_bytes(int NC) {
  * ever raised, so an extractor with a small quota cannot lower it under one with a large quota. */
 int viorb_octree_prepare(int NC) {
     static int current[64] = {0};
+    static std::mutex guard;
+    std::lock_guard<std::mutex> lock(guard);
     int dev = 0;
     cudaGetDevice(&dev);
     const int want = (int)viorb_octree_smem_bytes(NC);
@@ -1479,7 +1498,9 @@ int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, vi
     kpw = kpw < 1 ? 1 : (kpw > DESC_KPW ? DESC_KPW : kpw);
     dim3 grid((slots + DESC_WARPS * kpw - 1) / (DESC_WARPS * kpw), F);
     if (grid.x == 0) grid.x = 1;
-    orient_describe_kernel<<<grid, DESC_WARPS * 32, 0, s>>>(g, b.pyr, b.sel, b.selCount, d_kps, d_desc, cap, d_counts,
-                                                            b.status, kpw);
+    if (g.gaussVariant)
+        orient_describe_kernel<1><<<grid, DESC_WARPS * 32, 0, s>>>(g, b.pyr, b.sel, b.selCount, d_kps, d_desc, cap, d_counts, b.status, kpw);
+    else
+        orient_describe_kernel<0><<<grid, DESC_WARPS * 32, 0, s>>>(g, b.pyr, b.sel, b.selCount, d_kps, d_desc, cap, d_counts, b.status, kpw);
     return 1;
 }

@@ -48,7 +48,7 @@ struct LevelGeom {
 struct FrameGeom {
     int nlevels, rows, cols;
     int iniTh, minTh;
-    int reserved;
+    int gaussVariant;        /* GaussianBlur taps: 0 = OpenCV >= 3.4, 1 = OpenCV 2.4 (viorb_extractor_set_gaussian) */
     int cellsPerFrame, candPerFrame, selPerFrame;
     /* fast_cells_kernel shared-memory layout for this geometry: tile rows (max hCell + 6), quads per CTA (max NQ * wh),
      * bytes of the tile + work0 region, which later holds the corner-pixel list (>= 8 * fastMaxWork) */

@@ -56,6 +56,10 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
     if (mbDownloadPyramid) SyncPyramid();
 }
 
+void ORBextractor::SetGaussianVariant(int opencvVariant) {
+    check(viorb_extractor_set_gaussian(mpHandle, opencvVariant), "viorb_extractor_set_gaussian");
+}
+
 /* host copy of the padded levels of the last call (reference ComputePyramid :1107-1132 leaves them in mvImagePyramid) */
 void ORBextractor::SyncPyramid() {
     if (!mbPyramidStale) return;

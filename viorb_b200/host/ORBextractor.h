@@ -53,6 +53,9 @@ public:
     /* true: fetch the host copy inside every operator() (the reference's timing behaviour); default false = lazy */
     void SetPyramidDownload(bool on) { mbDownloadPyramid = on; }
     void SyncPyramid();
+    /* which OpenCV's GaussianBlur (:1086) to reproduce: 0 = OpenCV >= 3.4 (default), 1 = OpenCV 2.4, the version the
+     * reference's CMakeLists.txt pins.  See viorb_extractor_set_gaussian. */
+    void SetGaussianVariant(int opencvVariant);
 
     /* B200 extension: the same operator over a batch of equally sized frames (one device pass per 128 frames) */
     void ExtractBatch(const std::vector<cv::Mat>& images, std::vector<std::vector<cv::KeyPoint> >& keypoints,
