@@ -104,3 +104,33 @@ def set_gaussian_variant(variant):
 
 def arena_overflows():
     return int(lib()._l.ref_arena_overflows())
+
+
+class PlainExtractor:
+    """The reference's ORBextractor::operator() (src/ORBextractor.cc:1043-1105) and nothing else, on the process allocator,
+    into preallocated buffers: what bench.py's CPU arm times.  One instance per thread."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        l = lib()._l
+        l.ref_extractor_create.restype = C.c_void_p
+        l.ref_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        l.ref_extractor_destroy.argtypes = [C.c_void_p]
+        l.ref_extract_plain.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+        l.ref_extract_plain.restype = C.c_int
+        self._l = l
+        self.h = l.ref_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.cap = nfeatures * 2 + 64
+        import numpy as np
+        self.kps = np.zeros(self.cap, O.KEYPOINT)
+        self.desc = np.zeros((self.cap, 32), np.uint8)
+
+    def __call__(self, img):
+        assert img.dtype.name == "uint8" and img.strides[1] == 1
+        n = self._l.ref_extract_plain(self.h, img.ctypes.data, img.shape[0], img.shape[1], img.strides[0],
+                                      self.kps.ctypes.data, self.desc.ctypes.data, self.cap)
+        return self.kps[:n], self.desc[:n]
+
+    def close(self):
+        if self.h:
+            self._l.ref_extractor_destroy(self.h)
+            self.h = None

@@ -222,6 +222,21 @@ int ref_extract(RefExtractor* r, const uint8_t* img, int rows, int cols, size_t 
     return n;
 }
 
+/* ORBextractor::operator() and nothing else, on the process allocator: the call bench.py --impl reference times
+ * (ref_extract above runs the detection stage a second time to expose the per-level intermediates to the tests) */
+int ref_extract_plain(RefExtractor* r, const uint8_t* img, int rows, int cols, size_t step, orc_keypoint* kps, uint8_t* desc, int cap) {
+    cv::Mat image(rows, cols, CV_8UC1, (void*)img, step);
+    std::vector<cv::KeyPoint> keys;
+    cv::Mat d;
+    (*r->ex)(image, cv::Mat(), keys, d);
+    const int n = (int)keys.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        memcpy(&kps[i], &keys[i], sizeof(orc_keypoint));
+        memcpy(desc + (size_t)i * 32, d.ptr(i), 32);
+    }
+    return n;
+}
+
 int ref_extractor_levels(const RefExtractor* r) { return r->ex->nlevels; }
 int ref_extractor_quota(const RefExtractor* r, int level) { return r->ex->mnFeaturesPerLevel[level]; }
 float ref_extractor_scale(const RefExtractor* r, int level) { return r->ex->mvScaleFactor[level]; }

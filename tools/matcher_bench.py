@@ -21,6 +21,11 @@ def build_product():
     lib = build.build_cuda()
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     libdir = os.path.dirname(lib)
+    deps = [lib, os.path.join(ROOT, "tests", "cpp", "matcher_bench.cc"), os.path.join(ROOT, "tests", "cpp", "pose_scenarios.h")]
+    hostdir = os.path.join(ROOT, "viorb_b200", "host")
+    deps += [os.path.join(hostdir, f) for f in os.listdir(hostdir)]
+    if os.path.exists(EXE) and all(os.path.getmtime(EXE) >= os.path.getmtime(d) for d in deps):
+        return EXE
     subprocess.check_call([build.CXX, "-O2", "-std=gnu++17", "-I", os.path.join(ROOT, "viorb_b200", "host"), "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "tests", "cpp", "matcher_bench.cc"), "-o", EXE, "-L", libdir, "-lviorb_b200",
                            "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"])
