@@ -96,8 +96,7 @@ struct viorb_extractor {
     int rows = 0, cols = 0;
     FrameGeom geom;
     int nodeCap = 0;
-    DevBuf<uint16_t> tabU16;       /* xofs | yofs */
-    DevBuf<int16_t> tabI16;        /* xa | yb */
+    DevBuf<uint4> tabCol, tabRow;  /* resize tables (ResizeTables) */
     DevBuf<int4> groups;           /* FAST cell groups: {level, cell row, first cell, cells} */
     int ngroups = 0;
     int groupClass[5] = {0, 0, 0, 0, 0};   /* groups sorted by tile byte shift: class sh = [groupClass[sh], groupClass[sh+1]) */
@@ -218,7 +217,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
         L.scale = e->scale[l];
         L.patchSize = (int)(31 * e->scale[l]);               /* :837 */
         L.xtab = xtab; L.ytab = ytab;
-        xtab += L.w; ytab += L.h;
+        xtab += L.step / 4; ytab += L.h + 2 * VIORB_EDGE;
     }
     if (pyrOff >= (1ull << 31)) return fail(VIORB_ERR_UNSUPPORTED, "pyramid larger than 2 GiB per frame");
     g.pyrFrameBytes = pyrOff;
@@ -226,31 +225,56 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     if (nodeCap > 4096 || viorb_octree_smem_bytes(nodeCap) > 200 * 1024)
         return fail(VIORB_ERR_UNSUPPORTED, "per-level feature quota %d too large for the quadtree kernel", nodeCap);
     e->nodeCap = nodeCap;
-    /* cv::resize INTER_LINEAR coefficient tables (OpenCV resize.cpp), level l from level l-1 */
-    std::vector<uint16_t> tu((size_t)xtab + ytab);
-    std::vector<int16_t> ti(2 * ((size_t)xtab + ytab));
+    /* cv::resize INTER_LINEAR coefficient tables (OpenCV resize.cpp), level l from level l-1, expanded per stored word /
+     * stored row of the padded level (ResizeTables, extractor_kernels.cuh) */
+    std::vector<uint4> tcol(3 * (size_t)xtab), trow((size_t)ytab);
+    auto reflect = [](int p, int n) { return p < 0 ? -p : (p >= n ? 2 * n - 2 - p : p); };
     for (int l = 1; l < e->nlevels; l++) {
         const LevelGeom& L = g.lv[l];
         const LevelGeom& P = g.lv[l - 1];
         const double inv_sx = (double)L.w / P.w, inv_sy = (double)L.h / P.h;
         const double sx_ = 1. / inv_sx, sy_ = 1. / inv_sy;
+        std::vector<int> xs(L.w);
+        std::vector<uint32_t> xc(L.w);
         for (int dx = 0; dx < L.w; dx++) {
             float fx = (float)((dx + 0.5) * sx_ - 0.5);
             int sx = (int)floorf(fx);
             fx -= sx;
             if (sx < 0) { fx = 0; sx = 0; }
             if (sx >= P.w - 1) { fx = 0; sx = P.w - 1; }
-            tu[L.xtab + dx] = (uint16_t)sx;
-            ti[2 * (L.xtab + dx)] = (int16_t)cvRoundF((1.f - fx) * 2048);
-            ti[2 * (L.xtab + dx) + 1] = (int16_t)cvRoundF(fx * 2048);
+            xs[dx] = sx;
+            xc[dx] = (uint32_t)(uint16_t)cvRoundF((1.f - fx) * 2048) | ((uint32_t)(uint16_t)cvRoundF(fx * 2048) << 16);
         }
-        for (int dy = 0; dy < L.h; dy++) {
+        for (int wi = 0; wi < L.step / 4; wi++) {
+            int rel[4];
+            uint32_t coef[4], ok = 0;
+            for (int j = 0; j < 4; j++) {
+                const int x = wi * 4 + j - VIORB_ROI_X0;
+                /* columns in the alignment padding borrow the nearest stored column so the 8-byte window stays valid */
+                const int dx = reflect(std::min(std::max(x, -VIORB_EDGE), L.w + VIORB_EDGE - 1), L.w);
+                rel[j] = xs[dx];
+                coef[j] = xc[dx];
+                if (x >= -VIORB_EDGE && x < L.w + VIORB_EDGE) ok |= 0xffu << (8 * j);
+            }
+            const int lo = std::min(std::min(rel[0], rel[1]), std::min(rel[2], rel[3]));
+            const int hi = std::max(std::max(rel[0], rel[1]), std::max(rel[2], rel[3])) + 1;
+            if (hi - lo > 7) return fail(VIORB_ERR_UNSUPPORTED, "scale factor too large for the resize kernel's 8-byte window");
+            uint32_t sel[4];
+            for (int j = 0; j < 4; j++) sel[j] = (uint32_t)(rel[j] - lo) | ((uint32_t)(rel[j] - lo + 1) << 4);
+            uint4* c = &tcol[3 * ((size_t)L.xtab + wi)];
+            c[0] = make_uint4(coef[0], coef[1], coef[2], coef[3]);
+            c[1] = make_uint4(sel[0], sel[1], sel[2], sel[3]);
+            c[2] = make_uint4((uint32_t)lo, (uint32_t)hi, ok, 0u);
+        }
+        for (int r = 0; r < L.h + 2 * VIORB_EDGE; r++) {
+            const int dy = reflect(r - VIORB_EDGE, L.h);
             float fy = (float)((dy + 0.5) * sy_ - 0.5);
             int sy = (int)floorf(fy);
             fy -= sy;
-            tu[xtab + L.ytab + dy] = (uint16_t)std::max(sy, 0);
-            ti[2 * (xtab + L.ytab + dy)] = (int16_t)cvRoundF((1.f - fy) * 2048);
-            ti[2 * (xtab + L.ytab + dy) + 1] = (int16_t)cvRoundF(fy * 2048);
+            sy = std::max(sy, 0);
+            const uint32_t b0 = (uint32_t)(uint16_t)cvRoundF((1.f - fy) * 2048), b1 = (uint32_t)(uint16_t)cvRoundF(fy * 2048);
+            const uint32_t s0 = (uint32_t)std::min(sy, P.h - 1), s1 = (uint32_t)std::min(sy + 1, P.h - 1);
+            trow[(size_t)L.ytab + r] = make_uint4(s0 | (s1 << 16), b0 << 16, b1 << 16, 0u);
         }
     }
     /* FAST cell groups: the cells the reference visits (:789-806), VIORB_FAST_GROUP neighbours per CTA */
@@ -298,16 +322,13 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     int rc;
     if ((rc = e->groups.ensure(groups.size() + 1))) return rc;
     CU(cudaMemcpyAsync(e->groups.p, groups.data(), groups.size() * sizeof(int4), cudaMemcpyHostToDevice, e->ctx->stream));
-    if ((rc = e->tabU16.ensure(tu.size() + 1))) return rc;
-    if ((rc = e->tabI16.ensure(ti.size() + 2))) return rc;
-    CU(cudaMemcpyAsync(e->tabU16.p, tu.data(), tu.size() * 2, cudaMemcpyHostToDevice, e->ctx->stream));
-    CU(cudaMemcpyAsync(e->tabI16.p, ti.data(), ti.size() * 2, cudaMemcpyHostToDevice, e->ctx->stream));
+    if ((rc = e->tabCol.ensure(tcol.size() + 1))) return rc;
+    if ((rc = e->tabRow.ensure(trow.size() + 1))) return rc;
+    CU(cudaMemcpyAsync(e->tabCol.p, tcol.data(), tcol.size() * sizeof(uint4), cudaMemcpyHostToDevice, e->ctx->stream));
+    CU(cudaMemcpyAsync(e->tabRow.p, trow.data(), trow.size() * sizeof(uint4), cudaMemcpyHostToDevice, e->ctx->stream));
     CU(cudaStreamSynchronize(e->ctx->stream));
-    e->tables.xofs = e->tabU16.p;
-    e->tables.yofs = e->tabU16.p + xtab;
-    e->tables.xa = e->tabI16.p;
-    e->tables.yb = e->tabI16.p + 2 * (size_t)xtab;
-    /* ytab offsets index into the y arrays which start after the x block */
+    e->tables.col = e->tabCol.p;
+    e->tables.row = e->tabRow.p;
     cudaError_t ce = (cudaError_t)viorb_octree_prepare(nodeCap);
     if (ce != cudaSuccess) return fail(VIORB_ERR_CUDA, "octree kernel attribute: %s", cudaGetErrorString(ce));
     e->rows = rows; e->cols = cols;
@@ -533,7 +554,7 @@ int viorb_extractor_destroy(viorb_extractor* e) {
     cudaStreamSynchronize(e->ctx->stream);
     cudaStreamSynchronize(e->ctx->h2d);
     cudaStreamSynchronize(e->ctx->d2h);
-    e->tabU16.release(); e->tabI16.release(); e->groups.release();
+    e->tabCol.release(); e->tabRow.release(); e->groups.release();
     for (int i = 0; i < 4; i++) {
         viorb_extractor::Lane& ln = e->lanes[i];
         if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }

@@ -119,49 +119,45 @@ __global__ void __launch_bounds__(256) pyr_level0_kernel(const __grid_constant__
 #define RZ_SSTRIDE 224          /* staged source row stride (bytes): 128*1.5 + 1 + 15, rounded up to 16 */
 #define RZ_SROWS 100            /* staged source rows: 64*1.5 + 2, padded (scaleFactor <= 1.5) */
 
-__device__ __forceinline__ void reflected_range(int a, int b, int n, int& dmin, int& dmax) {
-    /* min / max of reflect101(i, n) over i in [a, b], with -19 <= a <= b <= n+18 */
-    const int ra = reflect101(a, n), rb = reflect101(b, n);
-    dmin = (a <= 0 && b >= 0) ? 0 : min(ra, rb);
-    dmax = (a <= n - 1 && b >= n - 1) ? n - 1 : max(ra, rb);
-}
-
-/* one 128 x 64 tile (bx, by) of level `level` of frame `frame`; 128 threads; src / rowInfo are the CTA's shared buffers */
+/* one 128 x (4*WROWS) tile (bx, by) of level `level` of frame `frame`; 128 threads; src / rowInfo are the CTA's shared
+ * buffers.  Everything that depends only on the geometry comes from two host-built tables (c_api.cu build_geometry):
+ *   col[3 * word]   per stored word of a level row (4 output columns): {coef[4]} {selP[4]} {lo, hi, okMask, -}
+ *                   coef = a0 | a1 << 16, lo = leftmost source byte of the four columns (ROI x of level l-1), hi = last
+ *                   source byte, selP = PRMT selector picking (S[sx], S[sx+1]) of a column out of the 8-byte window at lo
+ *   row[stored row] {sy | sy+1 << 16 (clamped source rows), b0 << 16, b1 << 16, -}
+ * so a tile's setup is five 16-byte loads and four warp reductions (the source rectangle) per thread. */
 template <int WROWS>      /* rows per warp: tile height = 4 * WROWS (64 for batches, 16 for the per-frame latency path) */
 __device__ __forceinline__ void pyr_resize_tile(const FrameGeom& g, int level, const ResizeTables& t, uint8_t* __restrict__ pyr,
                                                 int bx, int by, int frame, uint8_t* src, uint4* rowInfo) {
     constexpr int TH = 4 * WROWS;
     const LevelGeom& L = g.lv[level];
     const LevelGeom& P = g.lv[level - 1];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     uint8_t* base = pyr + (size_t)frame * g.pyrFrameBytes;
-    /* tile in ROI coordinates of level l: columns [xa, xa+128), rows [ya, ya+64) */
-    const int xa = bx * RZ_TW - VIORB_ROI_X0, ya = by * TH - VIORB_EDGE;
-    const int xlo = max(xa, -VIORB_EDGE), xhi = min(xa + RZ_TW - 1, L.w + VIORB_EDGE - 1);
-    const int ylo = ya, yhi = min(ya + TH - 1, L.h + VIORB_EDGE - 1);
-    const int stepWords = L.step >> 2;
-    const int wi = bx * (RZ_TW / 4) + (tid & 31);          /* stored word of this thread */
-    const int r0 = (tid >> 5) * WROWS;
-    if (xlo > xhi) {                                                  /* only alignment padding: write zeros */
-        if (wi < stepWords)
-            for (int r = r0; r < r0 + WROWS; r++)
-                if (ya + r <= yhi) reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(ya + r + VIORB_EDGE) * L.step)[wi] = 0;
-        return;
+    const int stepWords = L.step >> 2, nstored = L.h + 2 * VIORB_EDGE;
+    const int wi = bx * (RZ_TW / 4) + lane;                /* stored word of this thread */
+    const int row0 = by * TH, r0 = (tid >> 5) * WROWS;     /* first stored row of the tile / of this warp inside it */
+    const int rlast = min(TH, nstored - row0) - 1;         /* last tile row that exists */
+    const uint4* cd = t.col + 3 * (size_t)(L.xtab + min(wi, stepWords - 1));
+    const uint4 coef = __ldg(cd), selP = __ldg(cd + 1), cinfo = __ldg(cd + 2);
+    /* row descriptors of the whole tile (every warp reduces the same values: no shared round trip) */
+    uint4 rd[(TH + 31) / 32];
+    int symin = 0x7fffffff, symax = 0;
+#pragma unroll
+    for (int k = 0; k < (TH + 31) / 32; k++) {
+        const int r = min(TH >= 32 ? lane + 32 * k : (lane & (TH - 1)), rlast);
+        rd[k] = __ldg(t.row + L.ytab + row0 + r);
+        symin = min(symin, (int)(rd[k].x & 0xffffu));
+        symax = max(symax, (int)(rd[k].x >> 16));
     }
-    int dxmin, dxmax, dymin, dymax;
-    reflected_range(xlo, xhi, L.w, dxmin, dxmax);
-    reflected_range(ylo, yhi, L.h, dymin, dymax);
-    /* source rectangle (level l-1 ROI coordinates), x origin aligned down to 16 bytes */
-    const int sx0 = (int)t.xofs[L.xtab + dxmin] & ~15;
-    const int sx1 = min((int)t.xofs[L.xtab + dxmax] + 1, P.w - 1);
-    const int sy0 = min((int)t.yofs[L.ytab + dymin], P.h - 1);
-    const int sy1 = min((int)t.yofs[L.ytab + dymax] + 1, P.h - 1);
+    const int sx0 = __reduce_min_sync(0xffffffffu, (int)cinfo.x) & ~15;      /* x origin aligned down to 16 bytes */
+    const int sx1 = __reduce_max_sync(0xffffffffu, (int)cinfo.y);
+    const int sy0 = __reduce_min_sync(0xffffffffu, symin), sy1 = __reduce_max_sync(0xffffffffu, symax);
     const int nvec = ((sx1 - sx0) >> 4) + 1;                         /* 16-byte vectors per staged row (<= 14) */
     const int nrow = sy1 - sy0 + 1;
     {
         const uint8_t* sroi = base + P.pyrOff + (size_t)VIORB_EDGE * P.step + VIORB_ROI_X0;   /* 16-byte aligned */
         const int v = tid & 15;
-        /* cp.async: the copies stay in flight while the thread sets up its row and column tables below */
         if (v < nvec) {
             const uint8_t* gp = sroi + (size_t)(sy0 + (tid >> 4)) * P.step + sx0 + 16 * v;
             unsigned sp = (unsigned)__cvta_generic_to_shared(&src[(tid >> 4) * RZ_SSTRIDE + 16 * v]);
@@ -170,75 +166,57 @@ __device__ __forceinline__ void pyr_resize_tile(const FrameGeom& g, int level, c
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    if (tid < TH && ya + tid <= yhi) {
-        const int dy = reflect101(ya + tid, L.h);
-        const int sy = t.yofs[L.ytab + dy];
-        const unsigned b0 = (unsigned)t.yb[2 * (L.ytab + dy)], b1 = (unsigned)t.yb[2 * (L.ytab + dy) + 1];
-        const unsigned o0 = (unsigned)((min(sy, P.h - 1) - sy0) * RZ_SSTRIDE), o1 = (unsigned)((min(sy + 1, P.h - 1) - sy0) * RZ_SSTRIDE);
-        rowInfo[tid] = make_uint4(o0 | (o1 << 16), b0 << 16, b1 << 16, 0u);
-    }
-    /* this thread's four output columns: staged offsets relative to the lowest one (<= 6 at scale <= 1.5) */
-    int rel[4];
-    unsigned coef[4], okMask = 0;
+    if (tid < 32) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int x = xa + (tid & 31) * 4 + j;
-        const bool ok = x >= -VIORB_EDGE && x < L.w + VIORB_EDGE;
-        /* columns in the alignment padding borrow the nearest stored column so the 8-byte window stays valid */
-        const int dx = reflect101(min(max(x, -VIORB_EDGE), L.w + VIORB_EDGE - 1), L.w);
-        rel[j] = (int)t.xofs[L.xtab + dx] - sx0;
-        coef[j] = (unsigned)(unsigned short)t.xa[2 * (L.xtab + dx)] | ((unsigned)(unsigned short)t.xa[2 * (L.xtab + dx) + 1] << 16);
-        okMask |= ok ? 0xffu << (8 * j) : 0u;
+        for (int k = 0; k < (TH + 31) / 32; k++) {
+            const int r = lane + 32 * k;
+            if (r < TH) {
+                const unsigned o0 = ((rd[k].x & 0xffffu) - (unsigned)sy0) * RZ_SSTRIDE, o1 = ((rd[k].x >> 16) - (unsigned)sy0) * RZ_SSTRIDE;
+                rowInfo[r] = make_uint4(o0 | (o1 << 16), rd[k].y, rd[k].z, 0u);
+            }
+        }
     }
-    const int lo = min(min(rel[0], rel[1]), min(rel[2], rel[3]));
-    const int wb = lo >> 2;                                        /* first staged word of the 8-byte window */
+    const int lo = (int)cinfo.x - sx0;
     const unsigned selN = 0x3210u + 0x1111u * (unsigned)(lo & 3);  /* normalise: window byte 0 = staged byte lo */
-    unsigned selP[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const unsigned d = (unsigned)(rel[j] - lo);
-        selP[j] = d | ((d + 1) << 4);
-    }
+    const unsigned okMask = cinfo.z;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (wi >= stepWords) return;
-    const unsigned* srcw = reinterpret_cast<const unsigned*>(src) + wb;
+    const unsigned* srcw = reinterpret_cast<const unsigned*>(src) + (lo >> 2);
     /* horizontal pass of the staged row at byte offset `off`: T[j] = (S[sx]*a0 + S[sx+1]*a1) >> 4 */
     auto hpass = [&](unsigned off, unsigned (&T)[4]) {
         const unsigned* w = srcw + (off >> 2);
         const unsigned W0 = __byte_perm(w[0], w[1], selN), W1 = __byte_perm(w[1], w[2], selN);
-#pragma unroll
-        for (int j = 0; j < 4; j++) T[j] = __dp2a_lo(coef[j], __byte_perm(W0, W1, selP[j]), 0u) >> 4;
+        T[0] = __dp2a_lo(coef.x, __byte_perm(W0, W1, selP.x), 0u) >> 4;
+        T[1] = __dp2a_lo(coef.y, __byte_perm(W0, W1, selP.y), 0u) >> 4;
+        T[2] = __dp2a_lo(coef.z, __byte_perm(W0, W1, selP.z), 0u) >> 4;
+        T[3] = __dp2a_lo(coef.w, __byte_perm(W0, W1, selP.w), 0u) >> 4;
     };
-    /* vertical pass + packing of four pixels: s = ((b0*T0)>>16) + ((b1*T1)>>16) + 2 as two IMAD.HI with addend
-     * (s <= 1022); two s per register, one shift and mask for both, one PRMT for the four bytes */
+    /* vertical pass + packing of four pixels: s = ((b0*T0)>>16) + ((b1*T1)>>16) + 2 <= 1022, result s >> 2.  The two
+     * high products are plain IMAD.HI (no 64-bit addend to set up); 64*s is formed with two IMADs so that (s >> 2) is
+     * byte 1 of the word and three PRMTs gather the four result bytes (the arithmetic stays on the FMA pipe, the ALU
+     * pipe -- the busier one in this kernel -- only does the byte picking) */
     auto vrow = [&](const uint4& ri, const unsigned (&U)[4], const unsigned (&D)[4]) -> uint32_t {
         unsigned sj[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            unsigned t;
-            asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(ri.y), "r"(U[j]), "r"(2u));
-            asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(sj[j]) : "r"(ri.z), "r"(D[j]), "r"(t));
-        }
-        const unsigned p01 = ((sj[1] * 65536u + sj[0]) >> 2) & 0x00ff00ffu;
-        const unsigned p23 = ((sj[3] * 65536u + sj[2]) >> 2) & 0x00ff00ffu;
-        return __byte_perm(p01, p23, 0x6420) & okMask;
+        for (int j = 0; j < 4; j++) sj[j] = __umulhi(ri.y, U[j]) * 64u + (__umulhi(ri.z, D[j]) * 64u + 128u);
+        return __byte_perm(__byte_perm(sj[0], sj[1], 0x0051), __byte_perm(sj[2], sj[3], 0x0051), 0x5410) & okMask;
     };
     /* Consecutive output rows mostly share a source row (sy advances by 1 or 2 per output row): the lower row's T of
      * one output row is the upper row's T of the next.  Two rows per iteration with the two register sets swapping
      * roles, so the reuse costs no register moves. */
     unsigned A[4] = {0, 0, 0, 0}, B[4] = {0, 0, 0, 0};
     unsigned inA = 0xffffffffu;                       /* staged offset whose T is held in A */
-    uint32_t* out = reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(ya + r0 + VIORB_EDGE) * L.step) + wi;
+    uint32_t* out = reinterpret_cast<uint32_t*>(base + L.pyrOff + (size_t)(row0 + r0) * L.step) + wi;
 #pragma unroll 1
     for (int r = r0; r < r0 + WROWS; r += 2, out += 2 * stepWords) {
-        if (ya + r > yhi) break;
+        if (r > rlast) break;
         const uint4 ri0 = rowInfo[r];
         const unsigned o0 = ri0.x & 0xffffu, o1 = ri0.x >> 16;
         if (o0 != inA) hpass(o0, A);
         hpass(o1, B);
         out[0] = vrow(ri0, A, B);
-        if (ya + r + 1 > yhi) break;
+        if (r + 1 > rlast) break;
         const uint4 ri1 = rowInfo[r + 1];
         const unsigned q0 = ri1.x & 0xffffu, q1 = ri1.x >> 16;
         if (q0 != o1) hpass(q0, B);

@@ -42,7 +42,7 @@ struct LevelGeom {
     int nIni;             /* root nodes of the quadtree, src/ORBextractor.cc:543 */
     int patchSize;        /* (int)(PATCH_SIZE * mvScaleFactor[level]) */
     float scale;          /* mvScaleFactor[level] */
-    int xtab, ytab;       /* offsets into the resize tables */
+    int xtab, ytab;       /* offsets into the resize tables: first stored word / first stored row of this level */
 };
 
 struct FrameGeom {
@@ -57,12 +57,17 @@ struct FrameGeom {
     LevelGeom lv[VIORB_MAX_LEVELS];
 };
 
-/* per-level bilinear tables (cv::resize fixed point, 11 fractional bits) */
+/* per-level bilinear tables (cv::resize fixed point, 11 fractional bits), laid out for pyr_resize_kernel:
+ *   col[3 * (L.xtab + word)]  word = stored 32-bit word of a level row (4 output columns, border and padding included):
+ *                             {a0 | a1 << 16 per column} {PRMT selector per column} {lo, hi, okMask, 0}
+ *                             lo / hi = first / last source byte (ROI x of level l-1) the four columns read; the selector
+ *                             picks (S[sx], S[sx+1]) out of the 8 bytes starting at lo; okMask = 0xff per stored column
+ *                             (columns of the alignment padding are written as 0)
+ *   row[L.ytab + stored row]  {sy | (sy+1) << 16 (source rows, clamped to the level), b0 << 16, b1 << 16, 0}
+ * Border columns / rows carry the coefficients of their REFLECT_101 source coordinate. */
 struct ResizeTables {
-    const uint16_t* xofs;    /* sx per dst x */
-    const int16_t* xa;       /* a0,a1 interleaved */
-    const uint16_t* yofs;
-    const int16_t* yb;       /* b0,b1 interleaved */
+    const uint4* col;
+    const uint4* row;
 };
 
 enum {
