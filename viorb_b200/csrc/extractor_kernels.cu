@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
 #define FAST_ROWS VIORB_FAST_TILE_ROWS   /* cell sub-image rows  (hCell + 6 <= 66) */
 #define FAST_MAXQ 45            /* quads per window row: 4 cells x wCell (<= 45 when nCols >= 2; one cell of <= 59 otherwise) */
 #define FAST_TW (VIORB_FAST_TILE_BYTES / 4)   /* tile row stride in words = the TMA box width: 1 lead word + 45 quads + 1 tail word */
+#define FAST_STRIP 8           /* rows per phase-0 task (a vertical strip of one quad column) */
 #define FAST_SCW 49             /* score row stride in words (odd): 1 zero word + 45 quads + 1 zero word, padded */
 
 __device__ __forceinline__ unsigned funnel_bytes(unsigned lo, unsigned hi, int sh) {
@@ -431,44 +432,67 @@ __global__ void __launch_bounds__(128, 9) fast_cells_kernel(const __grid_constan
          * of the ring contains two ADJACENT compass samples, so a pixel can only be a corner at th if
          * |ring - centre| > th at two adjacent compass points.  flag byte bit 7 = (|d| > th); carries between
          * bytes can only add false positives.  Surviving quads are compacted so the later phases run on dense warps.
-         * Four tasks per thread and iteration: four ballots, one shared atomic per warp. */
+         * A task is a vertical strip of FAST_STRIP rows of one quad column: the centre words of its FAST_STRIP + 6 tile
+         * rows are loaded once, the vertical difference |C[j] - C[j+3]| serves row j as its south and row j+3 as its
+         * north sample, and only the east / west samples are fetched per row.  One shared atomic per warp and strip. */
         {
             const unsigned addc = (unsigned)(127 - th) * 0x01010101u;
-            for (int t0 = 0; t0 < ntask; t0 += 4 * blockDim.x) {
-                bool keep[4];
+            const int nstrip = (wh + FAST_STRIP - 1) / FAST_STRIP, ntask0 = NQ * nstrip;
+            for (int t0 = 0; t0 < ntask0; t0 += blockDim.x) {
+                const int t = t0 + tid;
+                unsigned keepMask = 0;                  /* bit r: window row ys + r of this quad column survives */
+                int q = 0, ys = 0;
+                if (t < ntask0) {
+                    const int sidx = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t;
+                    q = t - sidx * NQ;
+                    ys = sidx * FAST_STRIP;
+                    bool active = true;
+                    if (pass) {     /* only quads that touch a cell under retry */
+                        const int x = 4 * q, x3 = min(x + 3, ww - 1);
+                        const int c0 = (x >= wC) + (x >= 2 * wC) + (x >= 3 * wC), c3 = (x3 >= wC) + (x3 >= 2 * wC) + (x3 >= 3 * wC);
+                        active = (((retry >> c0) | (retry >> c3)) & 1u) != 0;
+                    }
+                    if (active) {
+                        /* tile row ys + j holds window row ys + j - 3; rows past the tile read the lists that follow it in
+                         * shared memory and only reach rows >= wh, which are masked below */
+                        const unsigned* col = &tile[ys * FAST_TW + w0 + q];
+                        unsigned C[FAST_STRIP + 6], fV[FAST_STRIP + 3];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int t = t0 + j * blockDim.x + tid;
-                    keep[j] = false;
-                    if (t < ntask) {
-                        const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
-                        if (pass) {     /* only quads that touch a cell under retry */
-                            const int x = 4 * q, x3 = min(x + 3, ww - 1);
-                            const int c0 = (x >= wC) + (x >= 2 * wC) + (x >= 3 * wC), c3 = (x3 >= wC) + (x3 >= 2 * wC) + (x3 >= 3 * wC);
-                            if (!(((retry >> c0) | (retry >> c3)) & 1u)) continue;
+                        for (int j = 0; j < FAST_STRIP + 6; j++) C[j] = fast_ld4<SH>(col + j * FAST_TW);
+#pragma unroll
+                        for (int j = 0; j < FAST_STRIP + 3; j++) {
+                            const unsigned d = __vabsdiffu4(C[j], C[j + 3]);
+                            fV[j] = (d + addc) | d;
                         }
-                        const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
-                        const unsigned cw4 = fast_ld4<SH>(row);
-                        const unsigned d0 = __vabsdiffu4(fast_ld4<SH>(row + 3 * FAST_TW), cw4);
-                        const unsigned d8 = __vabsdiffu4(fast_ld4<SH>(row - 3 * FAST_TW), cw4);
-                        const unsigned d4 = __vabsdiffu4(fast_ld4<SH + 3>(row), cw4);
-                        const unsigned d12 = __vabsdiffu4(fast_ld4<SH - 3>(row), cw4);
-                        const unsigned f0 = (d0 + addc) | d0, f4 = (d4 + addc) | d4, f8 = (d8 + addc) | d8, f12 = (d12 + addc) | d12;
-                        keep[j] = ((((f0 | f8) & (f4 | f12))) & 0x80808080u) != 0;   /* (f0&f4)|(f4&f8)|(f8&f12)|(f12&f0) */
+                        const unsigned rowsLeft = (unsigned)(wh - ys);
+#pragma unroll
+                        for (int r = 0; r < FAST_STRIP; r++) {
+                            const unsigned* row = col + (r + 3) * FAST_TW;
+                            const unsigned dE = __vabsdiffu4(fast_ld4<SH + 3>(row), C[r + 3]);
+                            const unsigned dW = __vabsdiffu4(fast_ld4<SH - 3>(row), C[r + 3]);
+                            const unsigned fEW = (dE + addc) | dE | (dW + addc) | dW;
+                            /* (f0&f4)|(f4&f8)|(f8&f12)|(f12&f0) = (f0|f8) & (f4|f12) */
+                            if ((((fV[r] | fV[r + 3]) & fEW) & 0x80808080u) != 0 && (unsigned)r < rowsLeft) keepMask |= 1u << r;
+                        }
                     }
                 }
-                const unsigned m0 = __ballot_sync(0xffffffffu, keep[0]), m1 = __ballot_sync(0xffffffffu, keep[1]);
-                const unsigned m2 = __ballot_sync(0xffffffffu, keep[2]), m3 = __ballot_sync(0xffffffffu, keep[3]);
-                if ((m0 | m1 | m2 | m3) == 0) continue;
-                const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
+                unsigned m[FAST_STRIP];
+                int total = 0;
+#pragma unroll
+                for (int r = 0; r < FAST_STRIP; r++) {
+                    m[r] = __ballot_sync(0xffffffffu, (keepMask >> r) & 1u);
+                    total += __popc(m[r]);
+                }
+                if (total == 0) continue;
                 int basePos = 0;
-                if (lane == 0) basePos = smem_add(&nwork0, c0 + c1 + c2 + c3);
+                if (lane == 0) basePos = smem_add(&nwork0, total);
                 basePos = __shfl_sync(0xffffffffu, basePos, 0);
-                const int tb = t0 + tid;
-                if (keep[0]) work0[basePos + __popc(m0 & lt)] = (unsigned short)tb;
-                if (keep[1]) work0[basePos + c0 + __popc(m1 & lt)] = (unsigned short)(tb + blockDim.x);
-                if (keep[2]) work0[basePos + c0 + c1 + __popc(m2 & lt)] = (unsigned short)(tb + 2 * blockDim.x);
-                if (keep[3]) work0[basePos + c0 + c1 + c2 + __popc(m3 & lt)] = (unsigned short)(tb + 3 * blockDim.x);
+                const int tb = ys * NQ + q;                  /* task id of window row ys: y * NQ + q */
+#pragma unroll
+                for (int r = 0; r < FAST_STRIP; r++) {
+                    if ((keepMask >> r) & 1u) work0[basePos + __popc(m[r] & lt)] = (unsigned short)(tb + r * NQ);
+                    basePos += __popc(m[r]);
+                }
             }
         }
         __syncthreads();
