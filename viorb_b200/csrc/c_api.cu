@@ -380,13 +380,18 @@ int run_pass(viorb_extractor* e, int lane, const uint8_t* d_images, size_t step,
             e->profEvents.push_back(ev[i]);
         }
     if (e->profiling) CU(cudaEventRecord(ev[0], st));
-    c->launches += viorb_launch_pyramid(g, e->tables, d_images, step, frameStride, F, ln.buf, st);
+    /* programmatic dependent launch along the pass's kernel chain.  Default: between the pyramid levels (single-lane pyramid
+     * stage 5.4 -> 4.9 ms per 4096 frames); on the stage edges it changes nothing measurable once four lanes overlap, and the
+     * waiting CTAs of the next stage would hold shared memory the other lanes could use.  VIORB_PDL=0..3 for A/B runs. */
+    static const int pdlEnv = [] { const char* v = getenv("VIORB_PDL"); return v ? atoi(v) : VIORB_PDL_INNER; }();
+    const int pdl = e->profiling ? (pdlEnv & VIORB_PDL_INNER) : pdlEnv;
+    c->launches += viorb_launch_pyramid(g, e->tables, d_images, step, frameStride, F, ln.buf, st, pdl);
     if (e->profiling) CU(cudaEventRecord(ev[1], st));
-    c->launches += viorb_launch_fast(g, ln.maps, e->groups.p, e->groupClass, F, ln.buf, st);
+    c->launches += viorb_launch_fast(g, ln.maps, e->groups.p, e->groupClass, F, ln.buf, st, pdl);
     if (e->profiling) CU(cudaEventRecord(ev[2], st));
-    c->launches += viorb_launch_octree(g, F, ln.buf, e->nodeCap, st);
+    c->launches += viorb_launch_octree(g, F, ln.buf, e->nodeCap, st, pdl);
     if (e->profiling) CU(cudaEventRecord(ev[3], st));
-    c->launches += viorb_launch_describe(g, F, ln.buf, d_kps, d_desc, cap, d_counts, st);
+    c->launches += viorb_launch_describe(g, F, ln.buf, d_kps, d_desc, cap, d_counts, st, pdl);
     if (e->profiling) CU(cudaEventRecord(ev[4], st));
     CU(cudaGetLastError());
     e->buf = ln.buf;

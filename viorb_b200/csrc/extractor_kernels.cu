@@ -39,6 +39,15 @@ __device__ __forceinline__ int reflect101(int i, int n) {
  * ---------------------------------------------------------------------------------------------- */
 #define L0_ROWS 16
 
+/* Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may start
+ * while its predecessor in the stream is still running; it runs its prologue (table loads, barrier set-up, zeroing of its
+ * own shared memory) and blocks in pdl_wait() until the predecessor has completed and flushed.  Every kernel of a pass
+ * calls pdl_trigger() first, which lets its successor be scheduled as soon as all of this grid's CTAs are resident.  Nothing
+ * a predecessor writes may be touched, and no global memory written, before pdl_wait().  Both are no-ops in a kernel that
+ * was launched without the attribute. */
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint4 load16_any(const uint8_t* p) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     const int sh = (int)(a & 3);
@@ -96,6 +105,7 @@ __device__ __forceinline__ void pyr_level0_tile(const FrameGeom& g, const uint8_
 __global__ void __launch_bounds__(256) pyr_level0_kernel(const __grid_constant__ FrameGeom g,
                                                          const uint8_t* __restrict__ images, size_t inStep,
                                                          size_t frameStride, uint8_t* __restrict__ pyr, int aligned) {
+    pdl_trigger();
     pyr_level0_tile(g, images, inStep, frameStride, pyr, aligned, blockIdx.x, blockIdx.y);
 }
 
@@ -155,6 +165,7 @@ __device__ __forceinline__ void pyr_resize_tile(const FrameGeom& g, int level, c
     const int sy0 = __reduce_min_sync(0xffffffffu, symin), sy1 = __reduce_max_sync(0xffffffffu, symax);
     const int nvec = ((sx1 - sx0) >> 4) + 1;                         /* 16-byte vectors per staged row (<= 14) */
     const int nrow = sy1 - sy0 + 1;
+    pdl_wait();                                    /* level l-1 is complete from here on */
     {
         const uint8_t* sroi = base + P.pyrOff + (size_t)VIORB_EDGE * P.step + VIORB_ROI_X0;   /* 16-byte aligned */
         const int v = tid & 15;
@@ -231,6 +242,7 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
                                                          ResizeTables t, uint8_t* __restrict__ pyr) {
     __shared__ __align__(16) uint8_t src[(4 * WROWS * 3 / 2 + 4) * RZ_SSTRIDE];
     __shared__ uint4 rowInfo[4 * WROWS];      /* {staged byte offset of row sy | of row sy+1 << 16, b0 << 16, b1 << 16, -} */
+    pdl_trigger();
     pyr_resize_tile<WROWS>(g, level, t, pyr, blockIdx.x, blockIdx.y, blockIdx.z, src, rowInfo);
 }
 
@@ -403,6 +415,8 @@ __global__ void __launch_bounds__(128, 9) fast_cells_kernel(const __grid_constan
     const int w0 = (gstart - boxX) >> 2;
     const int boxH = min(L.hCell + 6, g.fastTileRows);
     if (tid == 0) mbar_init(&bar, 1);
+    pdl_trigger();
+    pdl_wait();                               /* the pyramid is complete from here on */
 
     /* Two passes, like the reference (:808-816): pass 0 runs cv::FAST at iniThFAST on all cells of the group; a cell
      * that returns nothing is run again at minThFAST in pass 1 (about one cell in ten, so most CTAs stop after
@@ -754,6 +768,8 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const __grid_consta
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom& L = g.lv[level];
     const int tid = threadIdx.x, nt = blockDim.x;
+    pdl_trigger();
+    pdl_wait();                               /* the candidate pools are complete from here on */
     const int n = min(candCount[frame * g.nlevels + level], L.candCap);
     const uint32_t* keys = cand + (size_t)frame * g.candPerFrame + L.candBase;
     uint16_t* nodeOf = nodeOfAll + (size_t)frame * g.candPerFrame + L.candBase;
@@ -1173,6 +1189,13 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) orient_describe_kernel(con
     __shared__ __align__(16) unsigned hbW[DESC_WARPS][BW * HT_WORDS];
     const int frame = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
+    /* this lane's 8 binary tests (16 sampling points, 32 floats), kept in registers for all keypoints of the warp:
+     * read per keypoint they were 4 KB through L1 -- twice the patch */
+    float4 pat[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) pat[k] = __ldg(reinterpret_cast<const float4*>(d_pattern) + 8 * lane + k);
+    pdl_wait();                               /* the selected keypoints (and the pyramid) are complete from here on */
     /* lane l holds [lo, hi) of level l in the concatenated per-level lists (:1076-1103) */
     int myLo, myHi, total;
     {
@@ -1191,11 +1214,6 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) orient_describe_kernel(con
         counts[frame] = min(total, cap);
         if (total > cap) atomicOr(status, VIORB_DEV_OUT_OVERFLOW);
     }
-    /* this lane's 8 binary tests (16 sampling points, 32 floats), kept in registers for all keypoints of the warp:
-     * read per keypoint they were 4 KB through L1 -- twice the patch */
-    float4 pat[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) pat[k] = __ldg(reinterpret_cast<const float4*>(d_pattern) + 8 * lane + k);
     unsigned* P = patchW[warp];
     unsigned* Hw = hbW[warp];
     for (int it = 0; it < kpw; it++) {
@@ -1336,22 +1354,39 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) orient_describe_kernel(con
 }  // namespace
 
 /* ------------------------------------------------------------------------------------------------ launchers */
+/* kernel launch with or without the programmatic-dependent-launch attribute (see pdl_wait).  The launchers take a `pdl`
+ * mask: VIORB_PDL_INNER = between the kernels of one stage, VIORB_PDL_EDGE = on the first kernel of a stage (off while the
+ * per-stage timers are on: an event is recorded between the stages then). */
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_t* d_images, size_t step,
-                         size_t frameStride, int F, const ExtractBuffers& b, cudaStream_t s) {
+                         size_t frameStride, int F, const ExtractBuffers& b, cudaStream_t s, int pdl) {
+    const bool inner = (pdl & VIORB_PDL_INNER) != 0;
     const int aligned = ((uintptr_t)d_images % 16 == 0) && (step % 16 == 0) && (frameStride % 16 == 0);
     int launches = 0;
     for (int l = 0; l < g.nlevels; l++) {
         const LevelGeom& L = g.lv[l];
         if (l == 0) {
             dim3 grid((L.h + 2 * VIORB_EDGE + L0_ROWS - 1) / L0_ROWS, F);
-            pyr_level0_kernel<<<grid, 256, 0, s>>>(g, d_images, step, frameStride, b.pyr, aligned);
+            /* the first kernel of a pass follows a memset or another pass: ordinary stream order */
+            launch_k(pyr_level0_kernel, grid, dim3(256), 0, s, false, g, d_images, step, frameStride, b.pyr, aligned);
         } else {
             if (F <= 8) {        /* few frames: 128 x 16 tiles, four times the CTAs, a quarter of the per-tile latency */
                 dim3 grid((L.step + RZ_TW - 1) / RZ_TW, (L.h + 2 * VIORB_EDGE + 15) / 16, F);
-                pyr_resize_kernel<4><<<grid, 128, 0, s>>>(g, l, t, b.pyr);
+                launch_k(pyr_resize_kernel<4>, grid, dim3(128), 0, s, inner, g, l, t, b.pyr);
             } else {
                 dim3 grid((L.step + RZ_TW - 1) / RZ_TW, (L.h + 2 * VIORB_EDGE + RZ_TH - 1) / RZ_TH, F);
-                pyr_resize_kernel<RZ_WROWS><<<grid, 128, 0, s>>>(g, l, t, b.pyr);
+                launch_k(pyr_resize_kernel<RZ_WROWS>, grid, dim3(128), 0, s, inner, g, l, t, b.pyr);
             }
         }
         launches++;
@@ -1380,19 +1415,20 @@ int viorb_fast_prepare(const FrameGeom& g) {
 }
 
 int viorb_launch_fast(const FrameGeom& g, const TmaMaps& maps, const int4* d_groups, const int* classStart, int F,
-                      const ExtractBuffers& b, cudaStream_t s) {
+                      const ExtractBuffers& b, cudaStream_t s, int pdl) {
     int launches = 0;
     const size_t smem = viorb_fast_smem_bytes(g);
     for (int sh = 0; sh < 4; sh++) {
         const int n = classStart[sh + 1] - classStart[sh];
         if (n <= 0) continue;
+        const bool first = launches == 0;
         dim3 grid(n, F);
         const int4* grp = d_groups + classStart[sh];
         switch (sh) {
-            case 0: fast_cells_kernel<0><<<grid, 128, smem, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
-            case 1: fast_cells_kernel<1><<<grid, 128, smem, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
-            case 2: fast_cells_kernel<2><<<grid, 128, smem, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
-            default: fast_cells_kernel<3><<<grid, 128, smem, s>>>(g, maps, grp, b.cand, b.candCount, b.status); break;
+            case 0: launch_k(fast_cells_kernel<0>, grid, dim3(128), smem, s, (pdl & (first ? VIORB_PDL_EDGE : VIORB_PDL_INNER)) != 0, g, maps, grp, b.cand, b.candCount, b.status); break;
+            case 1: launch_k(fast_cells_kernel<1>, grid, dim3(128), smem, s, (pdl & (first ? VIORB_PDL_EDGE : VIORB_PDL_INNER)) != 0, g, maps, grp, b.cand, b.candCount, b.status); break;
+            case 2: launch_k(fast_cells_kernel<2>, grid, dim3(128), smem, s, (pdl & (first ? VIORB_PDL_EDGE : VIORB_PDL_INNER)) != 0, g, maps, grp, b.cand, b.candCount, b.status); break;
+            default: launch_k(fast_cells_kernel<3>, grid, dim3(128), smem, s, (pdl & (first ? VIORB_PDL_EDGE : VIORB_PDL_INNER)) != 0, g, maps, grp, b.cand, b.candCount, b.status); break;
         }
         launches++;
     }
@@ -1454,10 +1490,10 @@ int viorb_octree_prepare(int NC) {
     return (int)e;
 }
 
-int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s) {
+int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s, int pdl) {
     dim3 grid(g.nlevels, F);
-    octree_kernel<<<grid, F <= 8 ? OCT_THREADS : OCT_THREADS / 2, viorb_octree_smem_bytes(nodeCap), s>>>(g, b.cand, b.candCount, b.nodeOf, b.sel,
-                                                                               b.selCount, b.status, nodeCap);
+    launch_k(octree_kernel, grid, dim3(F <= 8 ? OCT_THREADS : OCT_THREADS / 2), viorb_octree_smem_bytes(nodeCap), s, (pdl & VIORB_PDL_EDGE) != 0,
+             g, b.cand, b.candCount, b.nodeOf, b.sel, b.selCount, b.status, nodeCap);
     return 1;
 }
 
@@ -1492,7 +1528,8 @@ int viorb_launch_steering_sweep(unsigned firstBits, long long n, float* d_sin, f
 }
 
 int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps, uint8_t* d_desc,
-                          int cap, int32_t* d_counts, cudaStream_t s) {
+                          int cap, int32_t* d_counts, cudaStream_t s, int pdl) {
+    const bool edge = (pdl & VIORB_PDL_EDGE) != 0;
     const int slots = g.selPerFrame < cap ? g.selPerFrame : cap;
     /* keypoints per warp: batches amortise the warp's pattern registers over up to DESC_KPW keypoints, as long as the
      * grid still holds two waves of CTAs (148 SMs x 7); a few frames keep one keypoint per warp (shortest latency) */
@@ -1501,8 +1538,8 @@ int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, vi
     dim3 grid((slots + DESC_WARPS * kpw - 1) / (DESC_WARPS * kpw), F);
     if (grid.x == 0) grid.x = 1;
     if (g.gaussVariant)
-        orient_describe_kernel<1><<<grid, DESC_WARPS * 32, 0, s>>>(g, b.pyr, b.sel, b.selCount, d_kps, d_desc, cap, d_counts, b.status, kpw);
+        launch_k(orient_describe_kernel<1>, grid, dim3(DESC_WARPS * 32), 0, s, edge, g, b.pyr, b.sel, b.selCount, d_kps, d_desc, cap, d_counts, b.status, kpw);
     else
-        orient_describe_kernel<0><<<grid, DESC_WARPS * 32, 0, s>>>(g, b.pyr, b.sel, b.selCount, d_kps, d_desc, cap, d_counts, b.status, kpw);
+        launch_k(orient_describe_kernel<0>, grid, dim3(DESC_WARPS * 32), 0, s, edge, g, b.pyr, b.sel, b.selCount, d_kps, d_desc, cap, d_counts, b.status, kpw);
     return 1;
 }

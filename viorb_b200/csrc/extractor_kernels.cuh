@@ -98,21 +98,25 @@ struct TmaMaps {
 /* encodes the maps for a pyramid buffer holding F frames (host, driver entry point cuTensorMapEncodeTiled) */
 int viorb_encode_tma_maps(const FrameGeom& g, uint8_t* d_pyr, int F, TmaMaps* out);
 
-/* launchers (extractor_kernels.cu); every launcher returns the number of kernel launches issued */
+/* launchers (extractor_kernels.cu); every launcher returns the number of kernel launches issued.  `pdl`: which launches carry
+ * the programmatic-dependent-launch attribute (the kernels of a pass form one dependency chain; with the attribute a kernel's
+ * CTAs are scheduled, and run their set-up, while the tail of its predecessor is still executing) */
+#define VIORB_PDL_INNER 1       /* between the kernels of one stage (pyramid levels, FAST shift classes) */
+#define VIORB_PDL_EDGE 2        /* on the first kernel of FAST / quadtree / describe */
 int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_t* d_images, size_t step,
-                         size_t frameStride, int F, const ExtractBuffers& b, cudaStream_t s);
+                         size_t frameStride, int F, const ExtractBuffers& b, cudaStream_t s, int pdl);
 /* d_groups is sorted by the byte shift SH = (stored byte of the group's window x=0) & 3; class sh owns
  * [classStart[sh], classStart[sh+1]) and is one launch of the kernel instantiated for that shift */
 int viorb_launch_fast(const FrameGeom& g, const TmaMaps& maps, const int4* d_groups, const int* classStart, int F,
-                      const ExtractBuffers& b, cudaStream_t s);
+                      const ExtractBuffers& b, cudaStream_t s, int pdl);
 size_t viorb_fast_smem_bytes(const FrameGeom& g);
 int viorb_fast_prepare(const FrameGeom& g);   /* opt-in dynamic shared memory; returns cudaError */
 #define VIORB_FAST_GROUP 4      /* horizontally adjacent FAST cells per CTA (extractor_kernels.cu FAST_GROUP) */
-int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s);
+int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s, int pdl);
 int viorb_launch_orientation_sweep(const int* d_m01, const int* d_m10, long long n, float* d_deg, int sms, cudaStream_t s);
 int viorb_launch_steering_sweep(unsigned firstBits, long long n, float* d_sin, float* d_cos, int sms, cudaStream_t s);
 int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps,
-                          uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s);
+                          uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s, int pdl);
 size_t viorb_octree_smem_bytes(int nodeCap);
 int viorb_octree_prepare(int nodeCap);   /* opt-in dynamic shared memory; returns cudaError */
 
