@@ -618,8 +618,7 @@ def main():
             s_kps = torch.empty((B, scap, 7), dtype=torch.float32, device=dev)
             s_desc = torch.empty((B, scap, 32), dtype=torch.uint8, device=dev)
             s_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
-            chunk = max(1, min(128, (128 * 752 * 480) // (h * w)))
-            exs.configure(chunk_frames=chunk)
+            chunk = max(1, min(128, (192 * 752 * 480 + h * w // 2) // (h * w)))      # the library's default pass size
             for _ in range(3):
                 exs.extract_batch_device(d, B, h, w, s_kps, s_desc, s_cnt)
             exs.check()

@@ -2,7 +2,7 @@
 # profiling half of tools/gpu_round.sh: launch list + full captures of a short, latency-free bench run
 TAG=${1:-r1}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --frames 256 --no-cpu --no-latency --map 2000000"
+CMD="python bench.py --steps 2 --warmup 3 --frames 256 --no-cpu --no-latency --no-shapes --map 2000000"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "ncu1 rc=$?"

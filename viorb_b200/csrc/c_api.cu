@@ -171,6 +171,16 @@ void build_tables(viorb_extractor* e) {
     e->quota[nl - 1] = std::max(e->nfeatures - sum, 0);
 }
 
+/* frames per device pass when the caller did not choose: about 69 Mpixel of input per pass, at most 128 frames.  Larger
+ * passes mean more CTAs per launch (full waves, shorter tails); L2 residency of a pass does not matter -- the kernels are
+ * bound by integer issue (tools/shape_bench.py: 1080p 12 frames/pass 30.7 k, 48 frames/pass 32.4 k frames/s; 4K 3 -> 7.1 k,
+ * 8 -> 8.8 k) */
+int default_pass_frames(const viorb_extractor* e, int rows, int cols) {
+    if (e->chunkUser) return e->chunk;
+    const long long px = (long long)rows * cols;
+    return (int)std::max<long long>(1, std::min<long long>(128, (192LL * 752 * 480 + px / 2) / px));
+}
+
 /* geometry + cv::resize coefficient tables for a given image size */
 int build_geometry(viorb_extractor* e, int rows, int cols) {
     if (e->rows == rows && e->cols == cols) return VIORB_OK;
@@ -714,7 +724,7 @@ int viorb_extract_batch_device(viorb_extractor* e, const uint8_t* d_images, int 
     int rc;
     if ((rc = ctx_bind(e->ctx))) return rc;
     if ((rc = build_geometry(e, rows, cols))) return rc;
-    const int F = std::min(e->chunk, B);
+    const int F = std::min(default_pass_frames(e, rows, cols), B);
     if ((rc = ensure_workspace(e, F))) return rc;
     if ((rc = lanes_fork(e))) return rc;
     int k = 0;
@@ -769,8 +779,8 @@ static int extract_batch_once(viorb_extractor* e, const uint8_t* images, int B, 
     /* frames per pass of the copy/compute pipeline: about a twelfth of the call, so that filling and draining the
      * pipeline (first copy in, last pass, last copy out) stays small for short batches; 32..128 (measured:
      * tools/small_batch_sweep.sh) */
-    int passFrames = e->chunk;
-    if (!e->chunkUser) passFrames = std::min(e->chunk, std::max(32, (B / 12 + 15) / 16 * 16));
+    int passFrames = default_pass_frames(e, rows, cols);
+    if (!e->chunkUser) passFrames = std::min(passFrames, std::max(std::min(32, passFrames), (B / 12 + 15) / 16 * 16));
     const int F = std::min(passFrames, B);
     if ((rc = ensure_workspace(e, F))) return rc;
     const size_t inFrame = (size_t)rows * cols;        /* device copy is packed */

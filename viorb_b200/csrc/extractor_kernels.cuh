@@ -1,8 +1,8 @@
 /*
  * extractor_kernels.cuh -- shared declarations of the sm_100a ORB extraction kernels.
  *
- * Device data layout (one "pass" = F frames processed together; F is sized so the pass working set
- * stays resident in the 126 MB L2):
+ * Device data layout (one "pass" = F frames processed together; F = 128 by default: full waves of CTAs per
+ * launch; the 229 MB working set of such a pass does not fit the 126 MB L2 and does not need to -- DESIGN.md):
  *
  *   pyramid   [F][pyrFrameBytes]   per frame, all levels back to back.  A level is stored as
  *                                  (h+38) rows of `step` bytes; the ROI (x=0) starts at byte 32 of a
