@@ -71,6 +71,14 @@ int viorb_extractor_destroy(viorb_extractor* ex);
  * host-buffer batch call uses 32..128 depending on the batch so that short batches still pipeline) and the
  * candidate pool per level as a fraction 1/div of the level's pixel count. */
 int viorb_extractor_configure(viorb_extractor* ex, int chunk_frames, int cand_div);
+/* How viorb_extract_batch schedules its host<->device copies.  VIORB_COPY_DUPLEX (default): input and output copies on two
+ * streams, both directions of the link busy at once -- the faster order on a host that sustains both (one GPU of this pool:
+ * 27.3 ms for a 4096-frame step against 26.7 + 5.0 ms one after the other).  VIORB_COPY_SERIAL: the output copies queue behind
+ * the input copies on one stream, for hosts where concurrent device-to-host writes slow the host-to-device reads down by
+ * more than they take on their own (all four GPUs of a 4-GPU box of this pool copying at once: 9.8 ms duplex, 6.8 + 1.3 ms
+ * serial).  bench.py measures both and picks; DESIGN.md section 6. */
+enum { VIORB_COPY_DUPLEX = 0, VIORB_COPY_SERIAL = 1 };
+int viorb_extractor_set_copy_mode(viorb_extractor* ex, int mode);
 /* Which OpenCV the GaussianBlur(workingMat, ..., Size(7,7), 2, 2, BORDER_REFLECT_101) of src/ORBextractor.cc:1086 is:
  * the 8-bit kernel differs between releases and the reference does not vendor OpenCV.
  *   VIORB_GAUSSIAN_OPENCV4  (default) OpenCV >= 3.4 fixed point [18,34,48,56,48,34,18]/256 -- bit-equal to cv2 4.13;

@@ -402,3 +402,20 @@ def test_extract_equals_committed_reference_outputs(api, ctx):
         ex.close()
         compared += 1
     assert compared >= 120
+
+
+def test_serial_copy_mode_equals_duplex(api, ctx):
+    """viorb_extractor_set_copy_mode(VIORB_COPY_SERIAL): the output copies of viorb_extract_batch queue behind the input copies
+    on one stream (two passes late); results must not depend on the order -- ragged last pass, more passes than slots"""
+    imgs = synth.frames(150, 240, 320, seed0=40)
+    ex = api.ORBextractor(300, 1.2, 6, 20, 7, ctx=ctx)
+    ex.configure(chunk_frames=16)
+    k0, d0, c0 = ex.extract_batch(imgs)
+    ex.set_copy_mode(1)
+    k1, d1, c1 = ex.extract_batch(imgs)
+    ex.set_copy_mode(0)
+    assert (c0 == c1).all() and c0.min() > 100
+    for b in range(len(imgs)):
+        n = c0[b]
+        assert k0[b, :n].tobytes() == k1[b, :n].tobytes() and (d0[b, :n] == d1[b, :n]).all(), b
+    ex.close()

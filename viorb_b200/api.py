@@ -49,6 +49,7 @@ def lib():
         "viorb_extractor_destroy": [vp],
         "viorb_extractor_configure": [vp, i32, i32],
         "viorb_extractor_set_gaussian": [vp, i32],
+        "viorb_extractor_set_copy_mode": [vp, i32],
         "viorb_extractor_tables": [vp, pi, vp, vp, vp, vp, vp],
         "viorb_extractor_profile": [vp, i32],
         "viorb_extractor_stage_ms": [vp, vp, pi],
@@ -233,6 +234,10 @@ class ORBextractor:
 
     def configure(self, chunk_frames=0, cand_div=0):
         _ck(lib().viorb_extractor_configure(self.h, chunk_frames, cand_div))
+
+    def set_copy_mode(self, mode):
+        """0 = input and output copies of extract_batch on two streams (default), 1 = on one (viorb_extractor_set_copy_mode)"""
+        _ck(lib().viorb_extractor_set_copy_mode(self.h, int(mode)))
 
     def set_gaussian(self, opencv_variant):
         """0 = OpenCV >= 3.4 taps (default), 1 = OpenCV 2.4 taps (viorb_extractor_set_gaussian)"""

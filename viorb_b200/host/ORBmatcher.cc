@@ -44,16 +44,20 @@ inline double dot3(float ax, float ay, float az, float bx, float by, float bz) {
 }
 inline float norm3(float x, float y, float z) { return (float)std::sqrt(dot3(x, y, z, x, y, z)); }
 
-/* ORBmatcher::DescriptorDistance, reference src/ORBmatcher.cc:1648-1664: the same eight 32-bit words, hardware popcount */
+/* ORBmatcher::DescriptorDistance, reference src/ORBmatcher.cc:1648-1664: the same SWAR bit count, on four 64-bit words
+ * instead of eight 32-bit ones (no -mpopcnt needed: the host files are built for a generic x86-64) */
 inline int hamming256(const unsigned char* a, const unsigned char* b) {
-    int dist = 0;
+    unsigned long long dist = 0;
     for (int i = 0; i < 4; i++) {
         unsigned long long x, y;
         memcpy(&x, a + 8 * i, 8);
         memcpy(&y, b + 8 * i, 8);
-        dist += __builtin_popcountll(x ^ y);
+        unsigned long long v = x ^ y;
+        v = v - ((v >> 1) & 0x5555555555555555ull);
+        v = (v & 0x3333333333333333ull) + ((v >> 2) & 0x3333333333333333ull);
+        dist += (((v + (v >> 4)) & 0x0f0f0f0f0f0f0f0full) * 0x0101010101010101ull) >> 56;
     }
-    return dist;
+    return (int)dist;
 }
 
 void check(int rc, const char* what) {
