@@ -87,6 +87,14 @@ int viorb_extractor_set_copy_mode(viorb_extractor* ex, int mode);
  * Keypoints are unaffected (the blur only feeds the descriptor tests); descriptors differ in a few bits. */
 enum { VIORB_GAUSSIAN_OPENCV4 = 0, VIORB_GAUSSIAN_OPENCV24 = 1 };
 int viorb_extractor_set_gaussian(viorb_extractor* ex, int opencv_variant);
+/* Where the GaussianBlur of src/ORBextractor.cc:1085-1086 is evaluated (results are identical -- the fixed-point blur is
+ * exact in any order):
+ *   VIORB_DESCRIBE_AUTO   (default) whole levels when the pyramid has fewer than about 2300 pixels per feature and the
+ *                         pass holds more than 8 frames, per keypoint otherwise;
+ *   VIORB_DESCRIBE_FUSED  on the 43 x 43 neighbourhood of every selected keypoint, inside the descriptor kernel;
+ *   VIORB_DESCRIBE_LEVELS every level once (the reference's own order: workingMat, then computeDescriptors). */
+enum { VIORB_DESCRIBE_AUTO = 0, VIORB_DESCRIBE_FUSED = 1, VIORB_DESCRIBE_LEVELS = 2 };
+int viorb_extractor_set_describe_mode(viorb_extractor* ex, int mode);
 
 /* per-stage device timing (CUDA events on the context stream around each stage of every pass):
  * ms[0..3] = pyramid, FAST, quadtree, orient+describe, summed over `passes` passes since the last query. */

@@ -219,6 +219,64 @@ def test_parameter_sweep(api, ctx, oracle, cfg):
     ex.close()
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["per_keypoint", "whole_levels"])
+def test_describe_modes(api, ctx, oracle, mode):
+    """viorb_extractor_set_describe_mode: the GaussianBlur evaluated per keypoint (fused kernel) or once per level
+    (blur_levels_kernel + describe_blurred_kernel) -- forced either way on single frames, odd shapes, unaligned strided
+    views, saturated / noisy / flat images, both Gaussian variants and a batch with a ragged last pass; every byte against
+    the oracle.  (Without the call the library picks per geometry and pass size.)"""
+    for cfg in SWEEP + [CONFIGS["kitti"]]:
+        h, w, nf, sf, nl, it, mt = cfg
+        img = synth.frame(h, w, h * 7 + w)
+        ref = oracle.Extractor(nf, sf, nl, it, mt)
+        k_ref, d_ref = ref(img)
+        ex = api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx)
+        ex.set_describe_mode(mode)
+        k, d = ex(img)
+        assert_same_output(k, d, k_ref, d_ref)
+        wide = np.zeros((h, w + 13), np.uint8)
+        wide[:, 5:5 + w] = img
+        k2, d2 = ex(wide[:, 5:5 + w])
+        assert_same_output(k2, d2, k_ref, d_ref)
+        ex.close()
+    ex = api.ORBextractor(1000, 1.2, 8, 20, 7, ctx=ctx)
+    ex.set_describe_mode(mode)
+    ref = oracle.Extractor(1000, 1.2, 8, 20, 7)
+    yy, xx = np.mgrid[0:480, 0:752]
+    checker = (((yy // 8 + xx // 8) & 1) * 255).astype(np.uint8)
+    noise = np.random.default_rng(3).integers(0, 256, (480, 752)).astype(np.uint8)
+    sat = synth.frame(480, 752, 0).copy()
+    sat[sat > 140] = 255
+    for img in (checker, noise, sat):
+        k_ref, d_ref = ref(img)
+        k, d = ex(img)
+        assert_same_output(k, d, k_ref, d_ref)
+    k, d = ex(np.full((480, 752), 77, np.uint8))
+    assert len(k) == 0
+    # a batch: 13 frames in passes of 5, 5 and 3 (and 13 > 8: the automatic mode would blur whole levels here)
+    imgs = synth.frames(13, 480, 752, seed0=300)
+    ex.configure(chunk_frames=5)
+    kps, desc, counts = ex.extract_batch(imgs)
+    for b in range(13):
+        k_ref, d_ref = ref(imgs[b])
+        assert_same_output(kps[b, :counts[b]], desc[b, :counts[b]], k_ref, d_ref)
+    ex.close()
+    # OpenCV 2.4 taps: digest written by the reference itself
+    import json
+    from util import extraction_digest
+    hashes = json.load(open(os.path.join(GOLD, "ref_extract_hashes.json")))
+    ex = api.ORBextractor(*CONFIGS["euroc"][2:], ctx=ctx)
+    ex.set_describe_mode(mode)
+    ex.set_gaussian(1)
+    for img in (synth.frame(480, 752, 0),):
+        k, d = ex(img)
+        assert extraction_digest(k, d) == hashes["cv24"]["euroc_seed0"]["digest"]
+    imgs = synth.frames(9, 480, 752, seed0=0)
+    kps, desc, counts = ex.extract_batch(imgs)
+    assert extraction_digest(kps[0, :counts[0]], desc[0, :counts[0]]) == hashes["cv24"]["euroc_seed0"]["digest"]
+    ex.close()
+
+
 def test_device_batch_path_and_device_frame_index(api, ctx, oracle):
     """viorb_extract_batch_device (device frames in, device outputs, ragged last pass) returns the bytes of the host
     path, and a frame index built from its device outputs (undistortion + grid on the device, no host round trip)

@@ -23,6 +23,7 @@ def main():
         h, w = img.shape
         try:
             ex = api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx)
+            ex.set_describe_mode(1 + c % 2)      # odd cases blur whole levels, even cases blur per keypoint
             kg, dg = ex(img)
         except api.ViorbError as e:
             if e.code == -4:         # outside the documented envelope (tiny top level, portrait aspect): refused, not guessed

@@ -49,6 +49,7 @@ def lib():
         "viorb_extractor_destroy": [vp],
         "viorb_extractor_configure": [vp, i32, i32],
         "viorb_extractor_set_gaussian": [vp, i32],
+        "viorb_extractor_set_describe_mode": [vp, i32],
         "viorb_extractor_set_copy_mode": [vp, i32],
         "viorb_extractor_tables": [vp, pi, vp, vp, vp, vp, vp],
         "viorb_extractor_profile": [vp, i32],
@@ -242,6 +243,10 @@ class ORBextractor:
     def set_gaussian(self, opencv_variant):
         """0 = OpenCV >= 3.4 taps (default), 1 = OpenCV 2.4 taps (viorb_extractor_set_gaussian)"""
         _ck(lib().viorb_extractor_set_gaussian(self.h, int(opencv_variant)))
+
+    def set_describe_mode(self, mode):
+        """0 = automatic, 1 = blur per keypoint (fused kernel), 2 = blur whole levels (viorb_extractor_set_describe_mode)"""
+        _ck(lib().viorb_extractor_set_describe_mode(self.h, int(mode)))
 
     def __call__(self, image, mask=None):
         """operator()(image, mask, keypoints, descriptors): returns (keypoints[KEYPOINT], descriptors[N,32])."""

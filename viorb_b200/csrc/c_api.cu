@@ -93,6 +93,13 @@ struct viorb_extractor {
     int gaussVariant = 0;        /* viorb_extractor_set_gaussian */
     int copyMode = 0;            /* viorb_extractor_set_copy_mode: 0 = input and output copies on two streams, 1 = on one */
     bool chunkUser = false;      /* viorb_extractor_configure chose the pass size */
+    /* GaussianBlur of whole levels (blur_levels_kernel + describe_blurred_kernel) or per keypoint inside
+     * orient_describe_kernel.  Measured cost per frame in thread instructions: 12.9 per pyramid pixel + 16.5 k per keypoint
+     * against 46.4 k per keypoint, so whole levels win while the pyramid has fewer than about 2300 pixels per feature
+     * (EuRoC 1100, KITTI 720, 1080p 1300: +9 %, +21 %, +4 % frames/s; 4K 5100: -7 %); single-frame calls keep the fused
+     * kernel (one launch less on the latency path).  VIORB_DESCRIBE=fused|dense overrides. */
+    int describeMode = 0;        /* 0 = by the rule above, 1 = always fused, 2 = always whole levels */
+    bool denseBlur = false;      /* decision for the current geometry (build_geometry) */
     /* geometry for the current image size */
     int rows = 0, cols = 0;
     FrameGeom geom;
@@ -109,7 +116,7 @@ struct viorb_extractor {
         cudaEvent_t evDone = nullptr;
         int allocFrames = 0;
         ExtractBuffers buf = {};
-        DevBuf<uint8_t> pyr;
+        DevBuf<uint8_t> pyr, blur;
         DevBuf<uint32_t> cand, sel;
         DevBuf<int> counters;      /* candCount | selCount | status */
         DevBuf<uint16_t> nodeOf;
@@ -192,7 +199,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     g.nlevels = e->nlevels; g.rows = rows; g.cols = cols; g.iniTh = e->iniTh; g.minTh = e->minTh;
     g.gaussVariant = e->gaussVariant;
     size_t pyrOff = 0;
-    int cellBase = 0, candBase = 0, selBase = 0, xtab = 0, ytab = 0, nodeCap = 0;
+    int cellBase = 0, candBase = 0, selBase = 0, xtab = 0, ytab = 0, nodeCap = 0, blurTasks = 0;
     for (int l = 0; l < e->nlevels; l++) {
         LevelGeom& L = g.lv[l];
         L.w = cvRoundF((float)cols * e->invScale[l]);       /* :1112 */
@@ -229,6 +236,19 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
         L.patchSize = (int)(31 * e->scale[l]);               /* :837 */
         L.xtab = xtab; L.ytab = ytab;
         xtab += L.step / 4; ytab += L.h + 2 * VIORB_EDGE;
+        /* dense blur: bands of at most 48 output rows (the 6 extra input rows of a band cost 1/8), equal per level */
+        static const int bandMax = [] { const char* v = getenv("VIORB_BLUR_BAND"); return v ? std::max(8, atoi(v)) : 48; }();
+        const int bands = (L.h + bandMax - 1) / bandMax;
+        L.blurRows = ((L.h + bands - 1) / bands + 7) / 8 * 8;
+        L.blurStrips = (L.w + 7) / 8;
+        L.blurBase = blurTasks;
+        blurTasks += L.blurStrips * ((L.h + L.blurRows - 1) / L.blurRows);
+    }
+    g.blurTasks = blurTasks;
+    {
+        long long px = 0;
+        for (int l = 0; l < e->nlevels; l++) px += (long long)g.lv[l].w * g.lv[l].h;
+        e->denseBlur = e->describeMode == VIORB_DESCRIBE_LEVELS || (e->describeMode == VIORB_DESCRIBE_AUTO && px < 2300LL * e->nfeatures);
     }
     if (pyrOff >= (1ull << 31)) return fail(VIORB_ERR_UNSUPPORTED, "pyramid larger than 2 GiB per frame");
     g.pyrFrameBytes = pyrOff;
@@ -355,12 +375,14 @@ int ensure_workspace(viorb_extractor* e, int F) {
         if (F <= ln.allocFrames) continue;
         int rc;
         if ((rc = ln.pyr.ensure((size_t)F * g.pyrFrameBytes))) return rc;
+        if (e->denseBlur && (rc = ln.blur.ensure((size_t)F * g.pyrFrameBytes + 64))) return rc;
         if ((rc = ln.cand.ensure((size_t)F * g.candPerFrame))) return rc;
         if ((rc = ln.nodeOf.ensure((size_t)F * g.candPerFrame))) return rc;
         if ((rc = ln.sel.ensure((size_t)F * g.selPerFrame))) return rc;
         if ((rc = ln.counters.ensure((size_t)F * g.nlevels * 2 + 4))) return rc;
         CU(cudaMemsetAsync(ln.counters.p, 0, ln.counters.n * sizeof(int), e->ctx->stream));
         ln.buf.pyr = ln.pyr.p;
+        ln.buf.blur = e->denseBlur ? ln.blur.p : nullptr;
         if (viorb_encode_tma_maps(g, ln.pyr.p, F, &ln.maps)) return fail(VIORB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
         ln.buf.cand = ln.cand.p;
         ln.buf.nodeOf = ln.nodeOf.p;
@@ -402,7 +424,12 @@ int run_pass(viorb_extractor* e, int lane, const uint8_t* d_images, size_t step,
     if (e->profiling) CU(cudaEventRecord(ev[2], st));
     c->launches += viorb_launch_octree(g, F, ln.buf, e->nodeCap, st, pdl);
     if (e->profiling) CU(cudaEventRecord(ev[3], st));
-    c->launches += viorb_launch_describe(g, F, ln.buf, d_kps, d_desc, cap, d_counts, st, pdl);
+    /* (sub-batches of 16..64 frames, to keep the blurred levels in the L2 until they are sampled, were measured and are
+     * slower than one launch per pass: 6.2 ms -> 7.2 ms (64) / 8.9 ms (32) per 4096 frames) */
+    ExtractBuffers db = ln.buf;
+    if (F <= 8 && e->describeMode != VIORB_DESCRIBE_LEVELS) db.blur = nullptr;        /* latency path: fused kernel */
+    c->launches += viorb_launch_blur(g, 0, F, db, st, pdl);
+    c->launches += viorb_launch_describe(g, 0, F, db, d_kps, d_desc, cap, d_counts, st, pdl);
     if (e->profiling) CU(cudaEventRecord(ev[4], st));
     CU(cudaGetLastError());
     e->buf = ln.buf;
@@ -553,6 +580,8 @@ int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, in
         cudaStreamCreateWithFlags(&e->lanes[i].stream, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&e->lanes[i].evDone, cudaEventDisableTiming);
     }
+    if (const char* v = getenv("VIORB_DESCRIBE"))
+        e->describeMode = !strcmp(v, "fused") ? VIORB_DESCRIBE_FUSED : (!strcmp(v, "dense") ? VIORB_DESCRIBE_LEVELS : VIORB_DESCRIBE_AUTO);
     if (getenv("VIORB_SLOTS")) e->nslots = std::min(4, std::max(2, atoi(getenv("VIORB_SLOTS"))));
     e->nlanes = std::max(e->nlanes, e->nslots);
     for (int i = 0; i < 4; i++) {
@@ -575,7 +604,7 @@ int viorb_extractor_destroy(viorb_extractor* e) {
         viorb_extractor::Lane& ln = e->lanes[i];
         if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
         if (ln.evDone) cudaEventDestroy(ln.evDone);
-        ln.pyr.release(); ln.cand.release(); ln.sel.release(); ln.counters.release(); ln.nodeOf.release();
+        ln.pyr.release(); ln.blur.release(); ln.cand.release(); ln.sel.release(); ln.counters.release(); ln.nodeOf.release();
     }
     if (e->evFork) cudaEventDestroy(e->evFork);
     if (e->hostStatus) cudaFreeHost(e->hostStatus);
@@ -597,6 +626,17 @@ int viorb_extractor_set_gaussian(viorb_extractor* e, int opencv_variant) {
     e->gaussVariant = opencv_variant;
     e->geom.gaussVariant = opencv_variant;
     e->geomGen++;                  /* the captured single-frame graph holds the kernel choice */
+    return VIORB_OK;
+}
+
+int viorb_extractor_set_describe_mode(viorb_extractor* e, int mode) {
+    if (!e) return fail(VIORB_ERR_INVALID, "extractor is NULL");
+    if (mode != VIORB_DESCRIBE_AUTO && mode != VIORB_DESCRIBE_FUSED && mode != VIORB_DESCRIBE_LEVELS)
+        return fail(VIORB_ERR_INVALID, "unknown describe mode %d", mode);
+    if (mode != e->describeMode) {
+        e->describeMode = mode;
+        e->rows = e->cols = 0;         /* the workspace (blurred levels) and the captured graph follow the mode */
+    }
     return VIORB_OK;
 }
 

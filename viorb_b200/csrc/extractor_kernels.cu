@@ -12,6 +12,7 @@
  * Nothing here is a dense contraction: no tensor cores, by design.
  */
 #include <mutex>
+#include <type_traits>
 
 #include "extractor_kernels.cuh"
 
@@ -1010,7 +1011,8 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const __grid_consta
  * and sampled at the 512 steered pattern points.  The blurred level image never exists in HBM.
  * ---------------------------------------------------------------------------------------------- */
 #define DESC_WARPS 4
-#define DESC_KPW 8            /* most keypoints per warp (batch launches) */
+#define DESC_KPW 8            /* most keypoints per warp (batch launches), fused kernel */
+#define DESC2_KPW 16          /* the same for describe_blurred_kernel (<= 32: lane j keeps keypoint j) */
 #define PR 21                 /* patch radius */
 #define PROWS 43              /* patch rows / columns */
 #define PWORDS 13             /* patch row stride in 32-bit words (odd: conflict-free row pairs; 12 words used) */
@@ -1351,6 +1353,355 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) orient_describe_kernel(con
     }
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * GaussianBlur 7x7 sigma 2 of every pyramid level (:1085-1086), dense.  A batch holds about as many keypoint
+ * neighbourhoods (1 000 x 43 x 43 px per EuRoC frame) as pyramid pixels (1.12 M) and the neighbourhoods overlap -- 3x on
+ * the small levels -- so blurring the levels once costs less than half the instructions of blurring per keypoint, and
+ * the work is regular: a thread owns an 8-pixel column strip of a band of output rows and walks down it.
+ *   horizontal: the row's 4 words (one LDG.64 + two LDG.32) -> eight 16-bit sums, 20 IDP.4A with shifted tap words
+ *   vertical:   the sums of rows (2m, 2m+1) packed into one word per column; an output row needs four such words
+ *               (IDP.2A x4); the window of four pair rows lives in registers and rotates (loop unrolled by four)
+ * The fixed-point blur rounds once at the end ((sum + 32768) >> 16), so it is exact in any evaluation order.  The
+ * source is the padded pyramid, whose REFLECT_101 border equals the blur's own border rule; only ROI pixels are
+ * written (same layout as the pyramid; a keypoint is >= 19 px from the level's edge and the pattern reaches 18).
+ * ---------------------------------------------------------------------------------------------- */
+#define BLUR_THREADS 128
+
+struct BlurRow { unsigned wm; uint2 w01; unsigned w2; };     /* the 16 bytes around an 8-pixel strip of one row */
+
+__device__ __forceinline__ BlurRow blur_load_row(const uint8_t* __restrict__ p) {
+    BlurRow r;
+    r.wm = __ldg(reinterpret_cast<const unsigned*>(p - 4));
+    r.w01 = __ldg(reinterpret_cast<const uint2*>(p));
+    r.w2 = __ldg(reinterpret_cast<const unsigned*>(p + 8));
+    return r;
+}
+
+template <int GV>
+__device__ __forceinline__ void blur_hrow8(const BlurRow& r, unsigned (&h)[8]) {
+    h[0] = blur_hsum<GV, 1>(r.wm, r.w01.x, r.w01.y, r.w2);
+    h[1] = blur_hsum<GV, 2>(r.wm, r.w01.x, r.w01.y, r.w2);
+    h[2] = blur_hsum<GV, 3>(r.wm, r.w01.x, r.w01.y, r.w2);
+    h[3] = blur_hsum<GV, 4>(r.wm, r.w01.x, r.w01.y, r.w2);
+    h[4] = blur_hsum<GV, 1>(r.w01.x, r.w01.y, r.w2, 0u);
+    h[5] = blur_hsum<GV, 2>(r.w01.x, r.w01.y, r.w2, 0u);
+    h[6] = blur_hsum<GV, 3>(r.w01.x, r.w01.y, r.w2, 0u);
+    h[7] = blur_hsum<GV, 4>(r.w01.x, r.w01.y, r.w2, 0u);
+}
+
+/* rows (2m, 2m+1) -> one word per column: low half = the sums of row 2m, high half = row 2m+1 */
+template <int GV>
+__device__ __forceinline__ void blur_pair8(const BlurRow& r0, const BlurRow& r1, unsigned (&P)[8]) {
+    unsigned h0[8], h1[8];
+    blur_hrow8<GV>(r0, h0);
+    blur_hrow8<GV>(r1, h1);
+#pragma unroll
+    for (int c = 0; c < 8; c++) P[c] = __byte_perm(h0[c], h1[c], 0x5410);
+}
+
+template <int GV>
+__global__ void __launch_bounds__(BLUR_THREADS) blur_levels_kernel(const __grid_constant__ FrameGeom g,
+                                                                   const uint8_t* __restrict__ pyr,
+                                                                   uint8_t* __restrict__ blur, int frame0) {
+    pdl_trigger();
+    const int frame = frame0 + blockIdx.y;
+    int t = blockIdx.x * BLUR_THREADS + threadIdx.x;
+    if (t >= g.blurTasks) return;
+    int l = 0;
+    while (l + 1 < g.nlevels && t >= g.lv[l + 1].blurBase) l++;
+    const LevelGeom& L = g.lv[l];
+    t -= L.blurBase;
+    const int band = t / L.blurStrips, strip = t - band * L.blurStrips;
+    const int y0 = band * L.blurRows;
+    const size_t step = (size_t)L.step;
+    const size_t off = (size_t)frame * g.pyrFrameBytes + L.pyrOff + (size_t)(VIORB_EDGE + y0) * step + VIORB_ROI_X0 + 8 * strip;
+    const uint8_t* src = pyr + off - 3 * step;        /* input row y0 - 3 */
+    uint8_t* dst = blur + off;
+    const int nrows = min(L.blurRows, L.h - y0);                /* output rows of this band that exist */
+    constexpr unsigned K0 = blur_tap(GV, 0), K1 = blur_tap(GV, 1), K2 = blur_tap(GV, 2), K3 = blur_tap(GV, 3);
+    constexpr unsigned K4 = blur_tap(GV, 4), K5 = blur_tap(GV, 5), K6 = blur_tap(GV, 6);
+    constexpr unsigned E01 = K0 | (K1 << 8), E23 = K2 | (K3 << 8), E45 = K4 | (K5 << 8), E6 = K6;              /* even output row */
+    constexpr unsigned O0 = K0 << 8, O12 = K1 | (K2 << 8), O34 = K3 | (K4 << 8), O56 = K5 | (K6 << 8);          /* odd output row */
+    pdl_wait();                               /* the pyramid is complete from here on */
+    unsigned P[4][8];
+    BlurRow n0, n1;                           /* the next row pair, loaded one step ahead of its use */
+    {
+        const BlurRow a0 = blur_load_row(src), a1 = blur_load_row(src + step);
+        const BlurRow b0 = blur_load_row(src + 2 * step), b1 = blur_load_row(src + 3 * step);
+        const BlurRow c0 = blur_load_row(src + 4 * step), c1 = blur_load_row(src + 5 * step);
+        n0 = blur_load_row(src + 6 * step);
+        n1 = blur_load_row(src + 7 * step);
+        blur_pair8<GV>(a0, a1, P[0]);
+        blur_pair8<GV>(b0, b1, P[1]);
+        blur_pair8<GV>(c0, c1, P[2]);
+    }
+    src += 8 * step;
+    /* step k: input rows 6+2k, 7+2k (loaded during step k-1) complete the window of output rows 2k, 2k+1; the rows of
+     * step k+1 are requested before the vertical pass (they lie inside the stored level: at most 12 rows below the ROI).
+     * The kernel runs at the rate of the integer pipe (IDP.4A / IDP.2A issue at 64 lanes per clock and SM): 6.5 IDP per pixel */
+#pragma unroll 1
+    for (int r = 0; r < nrows; r += 8) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (r + 2 * j < nrows) {
+                blur_pair8<GV>(n0, n1, P[(j + 3) & 3]);
+                n0 = blur_load_row(src);
+                n1 = blur_load_row(src + step);
+                unsigned e[8], o[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const unsigned a0 = P[j & 3][c], a1 = P[(j + 1) & 3][c], a2 = P[(j + 2) & 3][c], a3 = P[(j + 3) & 3][c];
+                    e[c] = __dp2a_lo(a0, E01, __dp2a_lo(a1, E23, __dp2a_lo(a2, E45, __dp2a_lo(a3, E6, 32768u))));
+                    o[c] = __dp2a_lo(a0, O0, __dp2a_lo(a1, O12, __dp2a_lo(a2, O34, __dp2a_lo(a3, O56, 32768u))));
+                    if constexpr (GV == 1) {      /* taps sum to 257: saturate_cast<uchar> */
+                        e[c] = min(e[c], 0x00ffffffu);
+                        o[c] = min(o[c], 0x00ffffffu);
+                    }
+                }
+                /* (sum >> 16) is byte 2 of each result */
+                const uint2 we = make_uint2(__byte_perm(__byte_perm(e[0], e[1], 0x0062), __byte_perm(e[2], e[3], 0x0062), 0x5410),
+                                            __byte_perm(__byte_perm(e[4], e[5], 0x0062), __byte_perm(e[6], e[7], 0x0062), 0x5410));
+                *reinterpret_cast<uint2*>(dst) = we;
+                if (r + 2 * j + 1 < nrows) {
+                    const uint2 wo = make_uint2(__byte_perm(__byte_perm(o[0], o[1], 0x0062), __byte_perm(o[2], o[3], 0x0062), 0x5410),
+                                                __byte_perm(__byte_perm(o[4], o[5], 0x0062), __byte_perm(o[6], o[7], 0x0062), 0x5410));
+                    *reinterpret_cast<uint2*>(dst + step) = wo;
+                }
+                src += 2 * step;
+                dst += 2 * step;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * IC_Angle (:77-104) + computeOrbDescriptor (:108-147) on the blurred levels: one warp per selected keypoint.
+ * The circular patch of the level (31 rows x 48 bytes) and the 37 x 37 blurred neighbourhood (37 rows x 64 bytes) are
+ * staged with 16-byte cp.async from the 16-byte aligned rows at or left of the keypoint's window; the consumers add the
+ * byte offset.  Orientation: lane v+15 sums row v (three conflict-free LDS.128; masked IDP.4A per word).
+ * ---------------------------------------------------------------------------------------------- */
+#define D2_RAW_STRIDE 48          /* bytes per staged row of the level patch (31 + <= 15 alignment bytes; 3 x 16 B: LDS.128 of eight rows hit eight bank groups) */
+#define D2_BLUR_STRIDE 64         /* bytes per staged row of the blurred patch (37 + <= 15 alignment bytes) */
+#define D2_RAW_BYTES (31 * D2_RAW_STRIDE)
+#define D2_BLUR_BYTES (37 * D2_BLUR_STRIDE)
+
+/* cvRound of a float with |x| < 2^22 on the FMA pipe: adding 1.5 * 2^23 leaves the integer (round to nearest even, like
+ * cvRound's lrint) in the low mantissa bits; the caller subtracts D2_RND_BITS -- F2I would go through the quarter-rate XU pipe */
+#define D2_RND_MAGIC 12582912.0f
+#define D2_RND_BITS 0x4B400000
+
+__global__ void __launch_bounds__(DESC_WARPS * 32, 7) describe_blurred_kernel(const __grid_constant__ FrameGeom g,
+                                                                          const uint8_t* __restrict__ pyr,
+                                                                          const uint8_t* __restrict__ blur,
+                                                                          const uint32_t* __restrict__ sel,
+                                                                          const int* __restrict__ selCount,
+                                                                          viorb_keypoint* __restrict__ kps,
+                                                                          uint8_t* __restrict__ desc, int cap,
+                                                                          int32_t* __restrict__ counts,
+                                                                          int* __restrict__ status, int kpw, int frame0) {
+    /* A warp owns up to kpw (<= 32) keypoints and works in two sweeps: (A) the intensity-centroid moments of every
+     * keypoint, then atan2 and sincos of all of them at once -- lane j does the scalar math of keypoint j, which would
+     * otherwise be a 150-instruction dependent chain run by 32 identical lanes per keypoint; (B) the steered tests.
+     * Both sweeps stage through two buffers per warp so that the copies of keypoint j+1 and j+2 are in flight while
+     * keypoint j is being worked on. */
+    __shared__ __align__(16) uint8_t rawS[DESC_WARPS][2][D2_RAW_BYTES];
+    __shared__ __align__(16) uint8_t blurS[DESC_WARPS][2][D2_BLUR_BYTES];
+    const int frame = frame0 + blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
+    float4 pat[8];      /* this lane's 8 binary tests, kept for all keypoints of the warp */
+#pragma unroll
+    for (int k = 0; k < 8; k++) pat[k] = __ldg(reinterpret_cast<const float4*>(d_pattern) + 8 * lane + k);
+    const int rawRow = lane / 3, rawCh = lane - 3 * rawRow;       /* this lane's (row, chunk) of a level-patch copy step */
+    const unsigned rawDst = (unsigned)__cvta_generic_to_shared(rawS[warp][0]) + rawRow * D2_RAW_STRIDE + 16 * rawCh;
+    const unsigned blurDst = (unsigned)__cvta_generic_to_shared(blurS[warp][0]) + (lane >> 2) * D2_BLUR_STRIDE + 16 * (lane & 3);
+    unsigned icMask[8];       /* IC_Angle: bytes of this lane's patch row (u = 4j-15 .. 4j-12 in word j) inside the circle */
+    {
+        const int v = lane - 15, d = c_umax[min(v < 0 ? -v : v, 15)];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            icMask[j] = shl_clamp(0xffffffffu, 8 * max(15 - d - 4 * j, 0)) & shr_clamp(0xffffffffu, 8 * max(4 * j + 3 - 15 - d, 0));
+    }
+    pdl_wait();                               /* the selected keypoints and the blurred levels are complete from here on */
+    /* lane l holds [lo, hi) of level l in the concatenated per-level lists (:1076-1103) */
+    int myLo, myHi, total;
+    {
+        const int c = lane < g.nlevels ? selCount[frame * g.nlevels + lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        myHi = incl;
+        myLo = incl - c;
+        total = __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        counts[frame] = min(total, cap);
+        if (total > cap) atomicOr(status, VIORB_DEV_OUT_OVERFLOW);
+    }
+    /* the warp's keypoints: lane j keeps keypoint j -- its key and level, the row stride of the level and the offsets
+     * (inside the frame's pyramid block, < 2 GiB) of the 16-byte aligned top-left corners of its two staged windows */
+    uint32_t myKey = 0;
+    int myLevel = 0, myStep = 0;
+    unsigned myRawOff = 0, myBlurOff = 0;
+    int nkp;
+    {
+        const int slot = (lane * gridDim.x + blockIdx.x) * DESC_WARPS + warp;
+        const bool valid = lane < kpw && slot < total && slot < cap;
+        nkp = __popc(__ballot_sync(0xffffffffu, valid));          /* slots grow with the lane: the valid lanes are a prefix */
+        int lo = 0;
+        for (int l = 0; l + 1 < g.nlevels; l++) {
+            const int hi = __shfl_sync(0xffffffffu, myHi, l);
+            if (slot >= hi) { myLevel = l + 1; lo = hi; }
+        }
+        if (valid) {
+            const LevelGeom& L = g.lv[myLevel];
+            myKey = sel[(size_t)frame * g.selPerFrame + L.selBase + (slot - lo)];
+            const int kx = myKey & 0xfff, ky = (myKey >> 12) & 0xfff;
+            myStep = L.step;
+            myRawOff = (unsigned)L.pyrOff + (unsigned)(VIORB_EDGE + ky - 15) * (unsigned)L.step + VIORB_ROI_X0 + ((kx - 15) & ~15);
+            myBlurOff = (unsigned)L.pyrOff + (unsigned)(VIORB_EDGE + ky - 18) * (unsigned)L.step + VIORB_ROI_X0 + ((kx - 18) & ~15);
+        }
+    }
+    const uint8_t* pyrF = pyr + (size_t)frame * g.pyrFrameBytes;
+    const uint8_t* blurF = blur + (size_t)frame * g.pyrFrameBytes;
+    /* sixteen-byte copies of keypoint j into buffer j & 1, lane -> (row, chunk) fixed: ten rows x 3 chunks of the level
+     * patch (4 instructions) / eight rows x 4 chunks of the blurred patch (5 instructions) per step; the lanes of a row
+     * read neighbouring chunks, so each 32-byte sector is fetched once.  One cp.async group per call (an empty one past
+     * the last keypoint keeps the group count uniform). */
+    auto stage_raw = [&](int j) {
+        if (j < nkp) {
+            const unsigned st = (unsigned)__shfl_sync(0xffffffffu, myStep, j);
+            const uint8_t* src = pyrF + (__shfl_sync(0xffffffffu, myRawOff, j) + (unsigned)rawRow * st + 16u * (unsigned)rawCh);
+            const size_t rstep = (size_t)(10u * st);
+            unsigned d = rawDst + (j & 1) * D2_RAW_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (lane < 30 && (k < 3 || lane < 3))
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+                src += rstep;
+                d += 10 * D2_RAW_STRIDE;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    /* the fourth chunk of a blurred row is only needed (and only inside the stored row) when the window starts at
+     * byte >= 12 of its first chunk */
+    auto stage_blur = [&](int j) {
+        if (j < nkp) {
+            const unsigned st = (unsigned)__shfl_sync(0xffffffffu, myStep, j);
+            const unsigned kx = __shfl_sync(0xffffffffu, myKey, j) & 0xfff;
+            const uint8_t* src = blurF + (__shfl_sync(0xffffffffu, myBlurOff, j) + (unsigned)(lane >> 2) * st + 16u * (unsigned)(lane & 3));
+            const size_t bstep = (size_t)(8u * st);
+            const bool chOk = (lane & 3) < 3 || ((kx - 18) & 15) >= 12;
+            unsigned d = blurDst + (j & 1) * D2_BLUR_BYTES;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                if (chOk && (k < 4 || lane < 20))
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+                src += bstep;
+                d += 8 * D2_BLUR_STRIDE;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage_raw(0);
+    stage_raw(1);
+    stage_blur(0);
+    stage_blur(1);
+    /* ---- sweep A: IC_Angle moments (:77-104).  Lane v+15 sums row v of the circular patch: three LDS.128, the eight
+     * words that hold u = -15..16 funnelled into place (the word offset selects one of four instantiations, the byte
+     * offset is a PRMT selector), masked to the row's half-width and one IDP.4A per word and moment. */
+    int myM01 = 0, myM10 = 0;
+    for (int it = 0; it < nkp; it++) {
+        /* groups so far: raw 0, raw 1, blur 0, blur 1, raw 2 .. raw it+1: all but the latest min(it, 1) + 2... are needed;
+         * waiting for everything except the most recent group is enough once it >= 1, and in iteration 0 three groups may stay */
+        if (it == 0) asm volatile("cp.async.wait_group 3;" ::: "memory");
+        else asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const int roff = ((__shfl_sync(0xffffffffu, myKey, it) & 0xfff) - 15) & 15;      /* staged bytes roff .. roff+30 hold x = kx-15 .. kx+15 */
+        const uint8_t* R = rawS[warp][it & 1];
+        int m10 = 0, m01 = 0;
+        if (lane < 31) {
+            const uint4* rw = reinterpret_cast<const uint4*>(R + lane * D2_RAW_STRIDE);
+            const uint4 q0 = rw[0], q1 = rw[1], q2 = rw[2];
+            const unsigned w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            const unsigned selN = 0x3210u + 0x1111u * (unsigned)(roff & 3);
+            unsigned s1 = 0;
+            auto rows = [&](auto O) {
+                constexpr int o = decltype(O)::value;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const unsigned x = __byte_perm(w[o + j], w[o + j + 1], selN) & icMask[j];
+                    const int u0 = 4 * j - 15;
+                    const int wts = (u0 & 0xff) | (((u0 + 1) & 0xff) << 8) | (((u0 + 2) & 0xff) << 16) | (((u0 + 3) & 0xff) << 24);
+                    m10 = dp4a_u8s8(x, wts, m10);
+                    s1 = __dp4a(x, 0x01010101u, s1);
+                }
+            };
+            switch (roff >> 2) {
+                case 0: rows(std::integral_constant<int, 0>()); break;
+                case 1: rows(std::integral_constant<int, 1>()); break;
+                case 2: rows(std::integral_constant<int, 2>()); break;
+                default: rows(std::integral_constant<int, 3>()); break;
+            }
+            m01 = (lane - 15) * (int)s1;
+        }
+        m10 = __reduce_add_sync(0xffffffffu, m10);          /* REDUX.SUM (also orders the reads before the next copies) */
+        m01 = __reduce_add_sync(0xffffffffu, m01);
+        if (lane == it) { myM10 = m10; myM01 = m01; }
+        stage_raw(it + 2);
+    }
+    /* orientation and steering of all the warp's keypoints at once: lane j = keypoint j (:103, :112-113) */
+    const float myAngle = fast_atan2_deg((float)myM01, (float)myM10);
+    float myA, myB;
+    sincosf_glibc(__fmul_rn(myAngle, (float)(3.14159265358979323846 / 180.f)), &myB, &myA);
+    /* ---- sweep B: steered BRIEF, lane i produces descriptor byte i (:123-144) */
+    for (int it = 0; it < nkp; it++) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");       /* blur it is complete (blur it+1 may be in flight) */
+        __syncwarp();
+        const int slot = (it * gridDim.x + blockIdx.x) * DESC_WARPS + warp;
+        const uint32_t key = __shfl_sync(0xffffffffu, myKey, it);
+        const int level = __shfl_sync(0xffffffffu, myLevel, it);
+        const float angle = __shfl_sync(0xffffffffu, myAngle, it);
+        const float a = __shfl_sync(0xffffffffu, myA, it), b = __shfl_sync(0xffffffffu, myB, it);
+        const LevelGeom& L = g.lv[level];
+        const int kx = key & 0xfff, ky = (key >> 12) & 0xfff, score = key >> 24;
+        const int boff = (kx - 18) & 15;      /* staged bytes boff .. boff+36 hold x = kx-18 .. kx+18 */
+        /* shared address = centre + r * 64 + c with r, c still biased by D2_RND_BITS: the bias goes into the base (32-bit
+         * wrap-around arithmetic) */
+        const unsigned centre = (unsigned)__cvta_generic_to_shared(blurS[warp][it & 1]) + 18 * D2_BLUR_STRIDE + boff + 18 -
+                                (unsigned)D2_RND_BITS * (D2_BLUR_STRIDE + 1);
+        auto tap = [&](float x, float y) -> unsigned {
+            const unsigned r = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(x, b), __fmul_rn(y, a)), D2_RND_MAGIC));
+            const unsigned c = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(x, a), __fmul_rn(y, b)), D2_RND_MAGIC));
+            unsigned v;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(r * D2_BLUR_STRIDE + c + centre));
+            return v;
+        };
+        unsigned val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) val |= (unsigned)(tap(pat[k].x, pat[k].y) < tap(pat[k].z, pat[k].w)) << k;
+        desc[((size_t)frame * cap + slot) * 32 + lane] = (uint8_t)val;
+        if (lane == 0) {
+            viorb_keypoint kp;
+            kp.x = level ? __fmul_rn((float)kx, L.scale) : (float)kx;       /* pt *= mvScaleFactor[level] (:1094-1101) */
+            kp.y = level ? __fmul_rn((float)ky, L.scale) : (float)ky;
+            kp.size = (float)L.patchSize;
+            kp.angle = angle;
+            kp.response = (float)score;
+            kp.octave = level;
+            kp.class_id = -1;
+            kps[(size_t)frame * cap + slot] = kp;
+        }
+        __syncwarp();           /* the copies of keypoint it + 2 overwrite this buffer */
+        stage_blur(it + 2);
+    }
+}
+
 }  // namespace
 
 /* ------------------------------------------------------------------------------------------------ launchers */
@@ -1527,19 +1878,39 @@ int viorb_launch_steering_sweep(unsigned firstBits, long long n, float* d_sin, f
     return 1;
 }
 
-int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps, uint8_t* d_desc,
+int viorb_launch_describe(const FrameGeom& g, int frame0, int F, const ExtractBuffers& b, viorb_keypoint* d_kps, uint8_t* d_desc,
                           int cap, int32_t* d_counts, cudaStream_t s, int pdl) {
     const bool edge = (pdl & VIORB_PDL_EDGE) != 0;
     const int slots = g.selPerFrame < cap ? g.selPerFrame : cap;
     /* keypoints per warp: batches amortise the warp's pattern registers over up to DESC_KPW keypoints, as long as the
      * grid still holds two waves of CTAs (148 SMs x 7); a few frames keep one keypoint per warp (shortest latency) */
     int kpw = (int)(((long long)F * slots) / (DESC_WARPS * 148 * 14));
-    kpw = kpw < 1 ? 1 : (kpw > DESC_KPW ? DESC_KPW : kpw);
+    static const int kpwMax = [] { const char* v = getenv("VIORB_KPW"); return v ? atoi(v) : 0; }();
+    const int kmax = b.blur ? ((kpwMax > 0 && kpwMax <= 32) ? kpwMax : DESC2_KPW) : DESC_KPW;
+    kpw = kpw < 1 ? 1 : (kpw > kmax ? kmax : kpw);
     dim3 grid((slots + DESC_WARPS * kpw - 1) / (DESC_WARPS * kpw), F);
     if (grid.x == 0) grid.x = 1;
+    if (b.blur) {
+        launch_k(describe_blurred_kernel, grid, dim3(DESC_WARPS * 32), 0, s, edge, g, b.pyr, b.blur, b.sel, b.selCount, d_kps, d_desc, cap, d_counts, b.status, kpw, frame0);
+        return 1;
+    }
+    /* the fused kernel indexes frames by blockIdx.y: whole passes only */
     if (g.gaussVariant)
         launch_k(orient_describe_kernel<1>, grid, dim3(DESC_WARPS * 32), 0, s, edge, g, b.pyr, b.sel, b.selCount, d_kps, d_desc, cap, d_counts, b.status, kpw);
     else
         launch_k(orient_describe_kernel<0>, grid, dim3(DESC_WARPS * 32), 0, s, edge, g, b.pyr, b.sel, b.selCount, d_kps, d_desc, cap, d_counts, b.status, kpw);
+    return 1;
+}
+
+/* GaussianBlur of all levels of frames [frame0, frame0 + F) (no-op when the lane has no blur buffer: the fused kernel
+ * blurs per keypoint) */
+int viorb_launch_blur(const FrameGeom& g, int frame0, int F, const ExtractBuffers& b, cudaStream_t s, int pdl) {
+    if (!b.blur) return 0;
+    const bool edge = (pdl & VIORB_PDL_EDGE) != 0;
+    dim3 grid((g.blurTasks + BLUR_THREADS - 1) / BLUR_THREADS, F);
+    if (g.gaussVariant)
+        launch_k(blur_levels_kernel<1>, grid, dim3(BLUR_THREADS), 0, s, edge, g, (const uint8_t*)b.pyr, b.blur, frame0);
+    else
+        launch_k(blur_levels_kernel<0>, grid, dim3(BLUR_THREADS), 0, s, edge, g, (const uint8_t*)b.pyr, b.blur, frame0);
     return 1;
 }

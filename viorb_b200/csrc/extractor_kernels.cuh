@@ -9,6 +9,8 @@
  *                                  row so that ROI rows are 16-byte aligned; the 19-pixel
  *                                  REFLECT_101 border of the reference's mvImagePyramid occupies
  *                                  bytes [13,32) and [32+w, 32+w+19) of the row.
+ *   blur      [F][pyrFrameBytes]   the 7x7 Gaussian blur of every level (the reference's workingMat, :1085-1086), same
+ *                                  layout; only ROI pixels are written
  *   cand      [F][candPerFrame]    FAST candidates, packed x:12 | y:12 | score:8 (window coordinates,
  *                                  i.e. level coordinates minus 16), appended with atomics
  *   candCount [F][nlevels]
@@ -43,6 +45,9 @@ struct LevelGeom {
     int patchSize;        /* (int)(PATCH_SIZE * mvScaleFactor[level]) */
     float scale;          /* mvScaleFactor[level] */
     int xtab, ytab;       /* offsets into the resize tables: first stored word / first stored row of this level */
+    /* blur_levels_kernel: a thread blurs an 8-pixel column strip of a band of blurRows (multiple of 8) output rows;
+     * thread blurBase + band * blurStrips + strip of a frame */
+    int blurStrips, blurRows, blurBase;
 };
 
 struct FrameGeom {
@@ -53,6 +58,7 @@ struct FrameGeom {
     /* fast_cells_kernel shared-memory layout for this geometry: tile rows (max hCell + 6), quads per CTA (max NQ * wh),
      * bytes of the tile + work0 region, which later holds the corner-pixel list (>= 8 * fastMaxWork) */
     int fastTileRows, fastMaxWork, fastPixBytes;
+    int blurTasks;           /* threads of blur_levels_kernel per frame */
     unsigned long long pyrFrameBytes;
     LevelGeom lv[VIORB_MAX_LEVELS];
 };
@@ -79,6 +85,7 @@ enum {
 
 struct ExtractBuffers {
     uint8_t* pyr;
+    uint8_t* blur;        /* GaussianBlur of every level, same layout as pyr (ROI pixels only); NULL: blur per keypoint */
     uint32_t* cand;
     int* candCount;
     uint16_t* nodeOf;
@@ -115,8 +122,10 @@ int viorb_fast_prepare(const FrameGeom& g);   /* opt-in dynamic shared memory; r
 int viorb_launch_octree(const FrameGeom& g, int F, const ExtractBuffers& b, int nodeCap, cudaStream_t s, int pdl);
 int viorb_launch_orientation_sweep(const int* d_m01, const int* d_m10, long long n, float* d_deg, int sms, cudaStream_t s);
 int viorb_launch_steering_sweep(unsigned firstBits, long long n, float* d_sin, float* d_cos, int sms, cudaStream_t s);
-int viorb_launch_describe(const FrameGeom& g, int F, const ExtractBuffers& b, viorb_keypoint* d_kps,
+/* describe / blur work on frames [frame0, frame0 + F) of the pass (sub-batches keep the blurred levels in the L2) */
+int viorb_launch_describe(const FrameGeom& g, int frame0, int F, const ExtractBuffers& b, viorb_keypoint* d_kps,
                           uint8_t* d_desc, int cap, int32_t* d_counts, cudaStream_t s, int pdl);
+int viorb_launch_blur(const FrameGeom& g, int frame0, int F, const ExtractBuffers& b, cudaStream_t s, int pdl);
 size_t viorb_octree_smem_bytes(int nodeCap);
 int viorb_octree_prepare(int nodeCap);   /* opt-in dynamic shared memory; returns cudaError */
 
