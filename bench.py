@@ -566,14 +566,15 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     dom = max(stage_ms, key=stage_ms.get)
     kernel_names = {"pyramid": "pyr_level0_kernel+pyr_resize_kernel x7", "fast": "fast_cells_kernel",
-                    "octree": "octree_kernel", "describe": "orient_describe_kernel"}
+                    "octree": "octree_kernel", "describe": "blur_levels_kernel+describe_blurred_kernel"}
     frames_timed = nloc * args.steps
     # per-kernel algorithmic bytes per frame (DESIGN.md "Kernels"): pyramid = read input + write padded pyramid;
     # fast = read every level ROI once + 4 B per candidate; octree = 6 B per candidate + 4 B per selected;
-    # describe = 43x43 patch + 60 B per keypoint
+    # describe = blur (read the padded levels, write the blurred ROI pixels) + per keypoint the 31x31 level patch, the
+    # 37x37 blurred patch and the 60 B record
     P, Ppad, ncand, nkp = 1117367, 1344493, 6085, 1006
     alg = {"pyramid": rows * cols + Ppad, "fast": P + 4 * ncand, "octree": 6 * ncand + 4 * nkp,
-           "describe": nkp * (43 * 43 + 60)}
+           "describe": Ppad + P + nkp * (31 * 31 + 37 * 37 + 60)}
     dom_ms_per_launch = stage_ms[dom] / max(passes, 1)
     frames_per_pass = frames_timed / max(passes, 1)
     achieved = alg[dom] * frames_per_pass / (dom_ms_per_launch * 1e-3) / 1e9
@@ -584,7 +585,7 @@ def main():
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         names = {"pyramid": ["pyr_level0_kernel", "pyr_resize_kernel"], "fast": ["fast_cells_kernel"],
-                 "octree": ["octree_kernel"], "describe": ["orient_describe_kernel"]}[dom]
+                 "octree": ["octree_kernel"], "describe": ["blur_levels_kernel", "describe_blurred_kernel"]}[dom]
         if all(n in tj for n in names) and int(round(frames_per_pass)) == 128:
             traffic = float(sum(l["dram_bytes"] for n in names for l in tj[n]["launches"]))
             l0 = tj[names[0]]["launches"][0]

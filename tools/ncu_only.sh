@@ -7,6 +7,6 @@ $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "ncu1 rc=$?"
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'fast_|orient_describe|pyr_|octree' -s 24 -c 13 -o gpurun_out/${TAG}_prof -f $CMD > gpurun_out/${TAG}_ncu2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'fast_|describe|blur_|pyr_|octree' -s 24 -c 13 -o gpurun_out/${TAG}_prof -f $CMD > gpurun_out/${TAG}_ncu2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'hamming|top2' -s 4 -c 4 -o gpurun_out/${TAG}_prof_match -f $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
 echo "ncu2 rc=$?"

@@ -69,7 +69,7 @@ def main():
             md.append("| %s | %d | %.1f | %.1f%% | %.1f |" % (k, a[0], a[1], 100 * a[1] / tot, a[1] / a[0]))
         md.append("")
         step = {"pyramid": ("pyr_level0_kernel", "pyr_resize_kernel"), "fast": ("fast_cells_kernel",), "octree": ("octree_kernel",),
-                "describe": ("orient_describe_kernel",)}
+                "describe": ("orient_describe_kernel", "blur_levels_kernel", "describe_blurred_kernel")}
         stot = sum(agg[k][1] for ks in step.values() for k in ks if k in agg)
         if stot > 0:
             md += ["Shares inside the extraction step (what `bench.py` times; the matcher launches above belong to its separate",
@@ -124,7 +124,7 @@ def main():
                                   "dram_pct": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")})
             md.append("")
         # ---- SASS phase breakdown between barriers for the two big kernels
-        for kname in ("fast_cells_kernel", "orient_describe_kernel", "pyr_resize_kernel"):
+        for kname in ("fast_cells_kernel", "describe_blurred_kernel", "blur_levels_kernel", "pyr_resize_kernel"):
             src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kname, "-c", "1"],
                                  capture_output=True, text=True).stdout
             srows = [r for r in csv.reader(src.splitlines()) if len(r) > 6 and r[0].startswith("0x")]

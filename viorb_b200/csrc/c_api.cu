@@ -83,6 +83,7 @@ struct viorb_ctx {
     std::vector<std::pair<size_t, uint8_t*> > pool;
 };
 
+#define VIORB_MAX_LANES 4
 struct viorb_extractor {
     viorb_ctx* ctx = nullptr;
     int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
@@ -121,7 +122,7 @@ struct viorb_extractor {
         DevBuf<int> counters;      /* candCount | selCount | status */
         DevBuf<uint16_t> nodeOf;
         TmaMaps maps;              /* TMA descriptors of this lane's pyramid buffer */
-    } lanes[4];
+    } lanes[VIORB_MAX_LANES];
     int nlanes = 4;
     cudaEvent_t evFork = nullptr;
     int* hostStatus = nullptr;     /* pinned copy of the device status word (single-pass host path) */
@@ -310,7 +311,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     }
     /* FAST cell groups: the cells the reference visits (:789-806), VIORB_FAST_GROUP neighbours per CTA */
     std::vector<int4> groups;
-    int fastRows = 8, fastWork = 64;
+    int fastRows = 8, fastWork = 64, fastStage = 0;
     for (int l = 0; l < e->nlevels; l++) {
         const LevelGeom& L = g.lv[l];
         const int maxBorderX = L.w - VIORB_FAST_BORDER, maxBorderY = L.h - VIORB_FAST_BORDER;
@@ -330,8 +331,9 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
                 const int wh = std::min(iniY + L.hCell + 6, maxBorderY) - iniY - 6;
                 if (ww > 0 && wh > 0) {
                     fastWork = std::max(fastWork, ((ww + 3) / 4) * wh);
-                    /* the same array later lists the 3x3 local maxima: at most every other pixel per row and column of a cell */
-                    fastWork = std::max(fastWork, n * ((L.wCell + 1) / 2) * ((wh + 1) / 2));
+                    /* staged candidate records (4 bytes each, in the tile + work0 region): at most every other pixel per
+                     * row and column of a cell is a 3x3 local maximum */
+                    fastStage = std::max(fastStage, 4 * n * ((L.wCell + 1) / 2) * ((wh + 1) / 2));
                 }
             }
         }
@@ -339,7 +341,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     }
     g.fastTileRows = fastRows;
     g.fastMaxWork = (fastWork + 63) & ~63;
-    g.fastPixBytes = (std::max(fastRows * VIORB_FAST_TILE_BYTES + g.fastMaxWork * 2, g.fastMaxWork * 8) + 127) & ~127;
+    g.fastPixBytes = (std::max(fastRows * VIORB_FAST_TILE_BYTES + g.fastMaxWork * 2, fastStage) + 127) & ~127;
     if (viorb_fast_prepare(g) != 0) return fail(VIORB_ERR_CUDA, "FAST kernel attribute: %s", cudaGetErrorString(cudaGetLastError()));
     e->ngroups = (int)groups.size();
     {   /* sort by the byte shift of the group's window inside a 4-byte word of the stored row (fast_cells_kernel<SH>) */
@@ -364,7 +366,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     if (ce != cudaSuccess) return fail(VIORB_ERR_CUDA, "octree kernel attribute: %s", cudaGetErrorString(ce));
     e->rows = rows; e->cols = cols;
     e->geomGen++;                  /* invalidates the captured single-frame graph */
-    for (int i = 0; i < 4; i++) e->lanes[i].allocFrames = 0;
+    for (int i = 0; i < VIORB_MAX_LANES; i++) e->lanes[i].allocFrames = 0;
     return VIORB_OK;
 }
 
@@ -575,8 +577,8 @@ int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, in
     if (ctx_bind(ctx)) { delete e; return VIORB_ERR_CUDA; }
     cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
     cudaHostAlloc((void**)&e->hostStatus, 64, cudaHostAllocDefault);
-    if (getenv("VIORB_LANES")) e->nlanes = std::min(4, std::max(2, atoi(getenv("VIORB_LANES"))));   /* the host-buffer path pairs lanes with its staging slots */
-    for (int i = 0; i < 4; i++) {
+    if (getenv("VIORB_LANES")) e->nlanes = std::min(VIORB_MAX_LANES, std::max(2, atoi(getenv("VIORB_LANES"))));   /* the host-buffer path pairs its staging slots with the first lanes */
+    for (int i = 0; i < VIORB_MAX_LANES; i++) {
         cudaStreamCreateWithFlags(&e->lanes[i].stream, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&e->lanes[i].evDone, cudaEventDisableTiming);
     }
@@ -600,7 +602,7 @@ int viorb_extractor_destroy(viorb_extractor* e) {
     cudaStreamSynchronize(e->ctx->h2d);
     cudaStreamSynchronize(e->ctx->d2h);
     e->tabCol.release(); e->tabRow.release(); e->groups.release();
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < VIORB_MAX_LANES; i++) {
         viorb_extractor::Lane& ln = e->lanes[i];
         if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
         if (ln.evDone) cudaEventDestroy(ln.evDone);

@@ -372,17 +372,17 @@ __global__ void __launch_bounds__(128, 9) fast_cells_kernel(const __grid_constan
                                                          uint32_t* __restrict__ cand, int* __restrict__ candCount,
                                                          int* __restrict__ status) {
     /* dynamic shared memory, sized by the host for this geometry (FrameGeom::fast*):
-     *   [ tile: fastTileRows x 208 B | work0: fastMaxWork u16 | pad ]  = fastPixBytes  (later: the corner-pixel list)
+     *   [ tile: fastTileRows x 208 B | work0: fastMaxWork u16 | pad ]  = fastPixBytes
      *   [ sc: (fastTileRows - 4) x 196 B ] [ work: fastMaxWork u16 ] */
     extern __shared__ __align__(128) unsigned char raw[];
     unsigned* sc = reinterpret_cast<unsigned*>(raw + g.fastPixBytes);
     unsigned short* work = reinterpret_cast<unsigned short*>(raw + g.fastPixBytes + (g.fastTileRows - 4) * FAST_SCW * 4);   /* quads that survive the high-speed test */
     __shared__ __align__(8) unsigned long long bar;   /* mbarrier of the TMA tile load */
-    __shared__ int nwork, nwork0, npix, nout, gbase;
+    __shared__ int nwork, nwork0, nout;
     __shared__ int cellCnt[FAST_GROUP];               /* per cell: local maxima found by the pass */
     unsigned* tile = reinterpret_cast<unsigned*>(raw);
     unsigned short* work0 = reinterpret_cast<unsigned short*>(raw + g.fastTileRows * FAST_TW * 4);   /* non-flat quads */
-    unsigned short* pix = reinterpret_cast<unsigned short*>(raw);   /* corner pixels x | y << 8 (the tile and work0 are dead then) */
+    uint32_t* stage = reinterpret_cast<uint32_t*>(raw);      /* the pass's candidate records (the tile and work0 are dead by then) */
     const int frame = blockIdx.y;
     /* a CTA owns up to FAST_GROUP horizontally adjacent cells of one cell row: {level, cell row, first cell, n} */
     const int4 grp = __ldg(&groups[blockIdx.x]);
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(128, 9) fast_cells_kernel(const __grid_constan
         if (tid == 0) {
             mbar_expect_tx(&bar, (unsigned)(VIORB_FAST_TILE_BYTES * boxH));
             tma_load_3d(tile, &maps.fast[l], boxX, VIORB_EDGE + iniY, frame, &bar);
-            nwork = 0; nwork0 = 0; npix = 0; nout = 0;
+            nwork = 0; nwork0 = 0; nout = 0;
         }
         {   /* zero the score rows with 16-byte stores (the array starts on a 128-byte boundary; a few words past the
              * last needed row stay inside the (fastTileRows - 4)-row array) */
@@ -575,90 +575,100 @@ __global__ void __launch_bounds__(128, 9) fast_cells_kernel(const __grid_constan
         }
         __syncthreads();
 
-        /* corner pixels (score > 0) as a dense list -- the tile and work0 are dead, the list takes their place
-         * (the host sizes the region for 4 * fastMaxWork entries) */
+        /* 3x3 non-max suppression and output, one thread per scored quad.  cv::FAST runs on the cell's own sub-image, so
+         * neighbours in another cell (or outside the window) count as 0.  The nine score words around the quad are split
+         * into u16 lanes (pixels 0,2 / 1,3) and reduced with the packed 3-input max: first over the three rows (per
+         * column), then over the left and right neighbour columns, which are the same words shifted by one pixel.  A
+         * pixel survives iff its score exceeds all eight neighbours (scores are > 0 exactly for the corners at th, and
+         * every local maximum of the cells this pass works on is a keypoint of its cell, :808-816).  The records
+         * are staged in shared memory. */
         for (int i0 = 0; i0 < nw; i0 += blockDim.x) {
             const int i = i0 + tid;
-            unsigned word = 0;
-            int y = 0, q = 0;
+            unsigned lm = 0;                 /* bit k: pixel k of the quad is a local maximum of a cell under work */
+            unsigned cw = 0;
+            int x0 = 0, y = 0, cg0 = 0, jb = 8;
             if (i < nw) {
                 const int t = work[i];
                 y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t;
-                q = t - y * NQ;
-                word = sc[(y + 1) * FAST_SCW + q + 1];
-            }
-            const unsigned m0 = __ballot_sync(0xffffffffu, (word & 0x000000ffu) != 0), m1 = __ballot_sync(0xffffffffu, (word & 0x0000ff00u) != 0);
-            const unsigned m2 = __ballot_sync(0xffffffffu, (word & 0x00ff0000u) != 0), m3 = __ballot_sync(0xffffffffu, (word & 0xff000000u) != 0);
-            const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
-            int basePos = 0;
-            if (lane == 0 && (m0 | m1 | m2 | m3)) basePos = smem_add(&npix, c0 + c1 + c2 + c3);
-            basePos = __shfl_sync(0xffffffffu, basePos, 0);
-            const unsigned e = (unsigned)(q * 4) | ((unsigned)y << 8);
-            if (word & 0x000000ffu) pix[basePos + __popc(m0 & lt)] = (unsigned short)e;
-            if (word & 0x0000ff00u) pix[basePos + c0 + __popc(m1 & lt)] = (unsigned short)(e + 1);
-            if (word & 0x00ff0000u) pix[basePos + c0 + c1 + __popc(m2 & lt)] = (unsigned short)(e + 2);
-            if (word & 0xff000000u) pix[basePos + c0 + c1 + c2 + __popc(m3 & lt)] = (unsigned short)(e + 3);
-        }
-        __syncthreads();
-
-        /* 3x3 non-max suppression, one thread per corner pixel.  cv::FAST runs on the cell's own sub-image, so
-         * neighbours in another cell (or outside the window) count as 0.  The local maxima of the cells this pass works
-         * on go to a compact list; cellCnt counts them per cell. */
-        const int np = npix;
-        unsigned short* lml = work;                      /* local maxima x | y << 8 (the quad list is dead) */
-        for (int i0 = 0; i0 < np; i0 += blockDim.x) {
-            const int i = i0 + tid;
-            bool lm = false;
-            unsigned e = 0;
-            if (i < np) {
-                e = pix[i];
-                const int x = e & 0xff, y = (e >> 8) & 0x3f;
-                const int cg = (x >= wC) + (x >= 2 * wC) + (x >= 3 * wC), xin = x - cg * wC;
-                if ((retry >> cg) & 1u) {
-                    const uint8_t* p = scb + ((y + 1) * FAST_SCW + 1) * 4 + x;
-                    const int sv = p[0];
-                    const int up = p[-FAST_SCW * 4], dn = p[FAST_SCW * 4];
-                    const int lf = max(max((int)p[-1], (int)p[-FAST_SCW * 4 - 1]), (int)p[FAST_SCW * 4 - 1]);
-                    const int rt = max(max((int)p[1], (int)p[-FAST_SCW * 4 + 1]), (int)p[FAST_SCW * 4 + 1]);
-                    int nb = max(up, dn);
-                    if (xin > 0) nb = max(nb, lf);
-                    if (xin < wC - 1) nb = max(nb, rt);
-                    lm = sv > nb;
-                    if (lm) atomicAdd(&cellCnt[cg], 1);
+                const int q = t - y * NQ;
+                const unsigned* c = &sc[(y + 1) * FAST_SCW + q + 1];
+                cw = c[0];
+                if (cw) {
+                    x0 = 4 * q;
+                    cg0 = (x0 >= wC) + (x0 >= 2 * wC) + (x0 >= 3 * wC);
+                    jb = wC - (x0 - cg0 * wC);       /* pixel jb of the quad is the first column of the next cell (jb >= 1) */
+                    const unsigned ul = c[-FAST_SCW - 1], uc = c[-FAST_SCW], ur = c[-FAST_SCW + 1];
+                    const unsigned ml = c[-1], mr = c[1];
+                    const unsigned dl = c[FAST_SCW - 1], dc = c[FAST_SCW], dr = c[FAST_SCW + 1];
+                    /* vertical maxima per column, u16 lanes: A = pixels 0,2, B = pixels 1,3 of a word */
+                    const unsigned lB = __vimax3_u16x2(__byte_perm(ul, 0, 0x4341), __byte_perm(ml, 0, 0x4341), __byte_perm(dl, 0, 0x4341));
+                    const unsigned rA = __vimax3_u16x2(__byte_perm(ur, 0, 0x4240), __byte_perm(mr, 0, 0x4240), __byte_perm(dr, 0, 0x4240));
+                    const unsigned cA = __byte_perm(cw, 0, 0x4240), cB = __byte_perm(cw, 0, 0x4341);
+                    const unsigned udA = __vmaxu2(__byte_perm(uc, 0, 0x4240), __byte_perm(dc, 0, 0x4240));
+                    const unsigned udB = __vmaxu2(__byte_perm(uc, 0, 0x4341), __byte_perm(dc, 0, 0x4341));
+                    const unsigned vA = __vmaxu2(udA, cA), vB = __vmaxu2(udB, cB);      /* the column itself, three rows */
+                    /* neighbour columns: left of pixels (0,2) = (pixel 3 of the left word, pixel 1), right of (1,3) = (pixel 2,
+                     * pixel 0 of the right word); left of (1,3) = (0,2) and right of (0,2) = (1,3) of the same word */
+                    unsigned leftA = __byte_perm(lB, vB, 0x5432), rightB = __byte_perm(vA, rA, 0x5432);
+                    unsigned leftB = vA, rightA = vB;
+                    /* cell borders: the first column of a cell has no left neighbours, the last one no right neighbours */
+                    if (x0 - cg0 * wC == 0) leftA &= 0xffff0000u;
+                    if (jb <= 4) {
+                        if (jb == 1) { leftB &= 0xffff0000u; rightA &= 0xffff0000u; }
+                        else if (jb == 2) { leftA &= 0x0000ffffu; rightB &= 0xffff0000u; }
+                        else if (jb == 3) { leftB &= 0x0000ffffu; rightA &= 0x0000ffffu; }
+                        else rightB &= 0x0000ffffu;
+                    }
+                    const unsigned nA = __vimax3_u16x2(leftA, rightA, udA), nB = __vimax3_u16x2(leftB, rightB, udB);
+                    /* score > neighbours per lane: bit 15 of (score + 0x7fff - max) (all values <= 255: no carries between lanes) */
+                    const unsigned gA = (cA + 0x7fff7fffu - nA) & 0x80008000u, gB = (cB + 0x7fff7fffu - nB) & 0x80008000u;
+                    lm = ((gA >> 15) & 1u) | ((gB >> 14) & 2u) | ((gA >> 29) & 4u) | ((gB >> 28) & 8u);
+                    /* only the cells this pass works on */
+                    const unsigned inLo = (retry >> cg0) & 1u, inHi = (retry >> min(cg0 + 1, FAST_GROUP - 1)) & 1u;
+                    const unsigned loMask = jb >= 4 ? 0xfu : ((1u << jb) - 1u);
+                    lm &= (inLo ? loMask : 0u) | (inHi ? (0xfu & ~loMask) : 0u);
                 }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, lm);
-            int basePos = 0;
-            if (lane == 0 && m) basePos = smem_add(&nout, __popc(m));
-            basePos = __shfl_sync(0xffffffffu, basePos, 0);
-            if (lm) lml[basePos + __popc(m & lt)] = (unsigned short)e;
+            const unsigned m0 = __ballot_sync(0xffffffffu, lm & 1u), m1 = __ballot_sync(0xffffffffu, lm & 2u);
+            const unsigned m2 = __ballot_sync(0xffffffffu, lm & 4u), m3 = __ballot_sync(0xffffffffu, lm & 8u);
+            if ((m0 | m1 | m2 | m3) == 0) continue;
+            const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
+            int base = 0;
+            if (lane == 0) base = smem_add(&nout, c0 + c1 + c2 + c3);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lm) {
+                /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
+                const uint32_t rec = (uint32_t)(x0 + 3 + cj0 * wC) | ((uint32_t)(y + 3 + ci * L.hCell) << 12);
+                const uint32_t bias = (uint32_t)(th - 1);
+                if (lm & 1u) stage[base + __popc(m0 & lt)] = rec | (((cw & 0xffu) + bias) << 24);
+                if (lm & 2u) stage[base + c0 + __popc(m1 & lt)] = (rec + 1) | ((((cw >> 8) & 0xffu) + bias) << 24);
+                if (lm & 4u) stage[base + c0 + c1 + __popc(m2 & lt)] = (rec + 2) | ((((cw >> 16) & 0xffu) + bias) << 24);
+                if (lm & 8u) stage[base + c0 + c1 + c2 + __popc(m3 & lt)] = (rec + 3) | (((cw >> 24) + bias) << 24);
+                const unsigned lo = lm & (jb >= 4 ? 0xfu : ((1u << jb) - 1u));
+                if (lo) smem_add(&cellCnt[cg0], __popc(lo));
+                if (lm & ~lo) smem_add(&cellCnt[cg0 + 1], __popc(lm & ~lo));
+            }
         }
         __syncthreads();
-        /* every local maximum of the pass is a keypoint of its cell (:808-816): one global atomic reserves the CTA's
-         * range of the (frame, level) candidate pool */
-        const int nlm = nout;
-        if (tid == 0) {
-            int b = 0;
-            if (nlm) {
-                b = atomicAdd(candCount + frame * g.nlevels + l, nlm);
-                if (b + nlm > L.candCap) atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
+        /* warp 0 appends the CTA's records to the (frame, level) candidate pool: one global atomic per CTA and pass; the
+         * other warps go on (the staging area is the dead tile, which warp 0 itself reloads at the top of a retry pass) */
+        if (tid < 32) {
+            const int n = nout;
+            if (n) {
+                int b0 = 0;
+                if (lane == 0) {
+                    b0 = atomicAdd(candCount + frame * g.nlevels + l, n);
+                    if (b0 + n > L.candCap) atomicOr(status, VIORB_DEV_CAND_OVERFLOW);
+                }
+                b0 = __shfl_sync(0xffffffffu, b0, 0);
+                for (int i = lane; i < n; i += 32)
+                    if (b0 + i < L.candCap) out[b0 + i] = stage[i];
             }
-            gbase = b;
         }
         /* cells that found nothing are run again at minThFAST */
         unsigned again = 0;
         for (int c = 0; c < ncell; c++) again |= (cellCnt[c] == 0 ? 1u : 0u) << c;
         again &= retry;
-        __syncthreads();
-        const int b0 = gbase;
-        for (int i = tid; i < nlm; i += blockDim.x) {
-            const unsigned e = lml[i];
-            const int x = e & 0xff, y = (e >> 8) & 0x3f;
-            const int sv = scb[((y + 1) * FAST_SCW + 1) * 4 + x];
-            /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
-            if (b0 + i < L.candCap)
-                out[b0 + i] = (uint32_t)(x + 3 + cj0 * wC) | ((uint32_t)(y + 3 + ci * L.hCell) << 12) | ((uint32_t)(sv + th - 1) << 24);
-        }
         if (pass == 1 || again == 0 || g.minTh >= g.iniTh) break;
         retry = again;
         __syncthreads();                 /* the lists and the score rows are rewritten by the next pass */
@@ -1736,6 +1746,11 @@ int viorb_launch_pyramid(const FrameGeom& g, const ResizeTables& t, const uint8_
                 dim3 grid((L.step + RZ_TW - 1) / RZ_TW, (L.h + 2 * VIORB_EDGE + 15) / 16, F);
                 launch_k(pyr_resize_kernel<4>, grid, dim3(128), 0, s, inner, g, l, t, b.pyr);
             } else {
+                /* 128 x 64 tiles on every level.  Measured alternatives for the levels above the third, whose launches hold
+                 * less than three waves of CTAs and lose 20-47 % of their threads to ragged tiles: 128 x 32 and 128 x 16 tiles
+                 * (more CTAs, but each repeats the set-up: 4.9 -> 4.9 / 5.2 ms per 4096 frames) and a tile-free kernel with one
+                 * thread per stored word and 16-row band reading the source rows straight from L1/L2 (no staging, no ragged
+                 * tiles, a third fewer instructions, but two dependent global loads per row: 5.6 ms) */
                 dim3 grid((L.step + RZ_TW - 1) / RZ_TW, (L.h + 2 * VIORB_EDGE + RZ_TH - 1) / RZ_TH, F);
                 launch_k(pyr_resize_kernel<RZ_WROWS>, grid, dim3(128), 0, s, inner, g, l, t, b.pyr);
             }

@@ -56,7 +56,7 @@ struct FrameGeom {
     int gaussVariant;        /* GaussianBlur taps: 0 = OpenCV >= 3.4, 1 = OpenCV 2.4 (viorb_extractor_set_gaussian) */
     int cellsPerFrame, candPerFrame, selPerFrame;
     /* fast_cells_kernel shared-memory layout for this geometry: tile rows (max hCell + 6), quads per CTA (max NQ * wh),
-     * bytes of the tile + work0 region, which later holds the corner-pixel list (>= 8 * fastMaxWork) */
+     * bytes of the tile + work0 region */
     int fastTileRows, fastMaxWork, fastPixBytes;
     int blurTasks;           /* threads of blur_levels_kernel per frame */
     unsigned long long pyrFrameBytes;

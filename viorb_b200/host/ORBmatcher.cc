@@ -44,9 +44,19 @@ inline double dot3(float ax, float ay, float az, float bx, float by, float bz) {
 }
 inline float norm3(float x, float y, float z) { return (float)std::sqrt(dot3(x, y, z, x, y, z)); }
 
-/* ORBmatcher::DescriptorDistance, reference src/ORBmatcher.cc:1648-1664: the same SWAR bit count, on four 64-bit words
- * instead of eight 32-bit ones (no -mpopcnt needed: the host files are built for a generic x86-64) */
-inline int hamming256(const unsigned char* a, const unsigned char* b) {
+/* ORBmatcher::DescriptorDistance, reference src/ORBmatcher.cc:1648-1664 (a SWAR bit count on eight 32-bit words).  The
+ * host files are built for a generic x86-64, so the POPCNT version is a separately targeted function chosen once at load
+ * time; the fallback is the reference's SWAR count on four 64-bit words.  Both give the reference's value. */
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("popcnt"))) int hamming256_popcnt(const unsigned char* a, const unsigned char* b) {
+    unsigned long long x[4], y[4];
+    memcpy(x, a, 32);
+    memcpy(y, b, 32);
+    return (int)(__builtin_popcountll(x[0] ^ y[0]) + __builtin_popcountll(x[1] ^ y[1]) + __builtin_popcountll(x[2] ^ y[2]) +
+                 __builtin_popcountll(x[3] ^ y[3]));
+}
+#endif
+int hamming256_swar(const unsigned char* a, const unsigned char* b) {
     unsigned long long dist = 0;
     for (int i = 0; i < 4; i++) {
         unsigned long long x, y;
@@ -59,6 +69,15 @@ inline int hamming256(const unsigned char* a, const unsigned char* b) {
     }
     return (int)dist;
 }
+typedef int (*Hamming256Fn)(const unsigned char*, const unsigned char*);
+Hamming256Fn pick_hamming256() {
+#if defined(__x86_64__) && defined(__GNUC__)
+    __builtin_cpu_init();
+    if (__builtin_cpu_supports("popcnt")) return hamming256_popcnt;
+#endif
+    return hamming256_swar;
+}
+const Hamming256Fn hamming256 = pick_hamming256();
 
 void check(int rc, const char* what) {
     if (rc != VIORB_OK) throw std::runtime_error(std::string(what) + ": " + viorb_last_error());
