@@ -56,6 +56,10 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
     if (mbDownloadPyramid) SyncPyramid();
 }
 
+void ORBextractor::SetDescribeMode(int mode) {
+    check(viorb_extractor_set_describe_mode(mpHandle, mode), "viorb_extractor_set_describe_mode");
+}
+
 void ORBextractor::SetGaussianVariant(int opencvVariant) {
     check(viorb_extractor_set_gaussian(mpHandle, opencvVariant), "viorb_extractor_set_gaussian");
 }

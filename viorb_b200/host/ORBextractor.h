@@ -56,6 +56,9 @@ public:
     /* which OpenCV's GaussianBlur (:1086) to reproduce: 0 = OpenCV >= 3.4 (default), 1 = OpenCV 2.4, the version the
      * reference's CMakeLists.txt pins.  See viorb_extractor_set_gaussian. */
     void SetGaussianVariant(int opencvVariant);
+    /* where the GaussianBlur is evaluated (0 automatic, 1 per keypoint, 2 whole levels): results are identical.  See
+     * viorb_extractor_set_describe_mode. */
+    void SetDescribeMode(int mode);
 
     /* B200 extension: the same operator over a batch of equally sized frames (one device pass per 128 frames) */
     void ExtractBatch(const std::vector<cv::Mat>& images, std::vector<std::vector<cv::KeyPoint> >& keypoints,
