@@ -110,6 +110,35 @@ def test_search_by_projection_local(api, ctx, oracle, stereo, frame, th, nnratio
     assert n == n_ref and (match == m_ref).all() and (obs == obs_ref).all()
 
 
+@pytest.mark.parametrize("n_mp", [2500, 6000])
+def test_search_by_projection_large_local_map(api, ctx, oracle, stereo, n_mp):
+    """Tracking::SearchLocalPoints passes local maps of several thousand points (the other scenarios stay below 1000): the
+    scratch arena must hold seven per-point arrays and the descriptors, and the ordered resolve must still equal the
+    reference's sequential loop when three map points compete for every keypoint"""
+    s = stereo
+    h, w = s["shape"]
+    sf = s["ol"].scale_factors()
+    sc = S.projection_scenario(s["kl"], s["dl"], sf, seed=23, n_mp=n_mp, conflicts=n_mp // 10)
+    bounds = (0.0, float(w), 0.0, float(h))
+    fi = api.FrameIndex(ctx, s["kl"], s["dl"], sc["u_right"], bounds, sf)
+    g = oracle.Grid(s["kl"], *bounds)
+    n_ref, m_ref, obs_ref = oracle.search_by_projection_local(
+        g, s["dl"], sc["u_right"], sc["obs0"], sf, sc["proj_x"], sc["proj_y"], sc["proj_xr"], sc["pred_level"],
+        sc["view_cos"], sc["valid"], sc["nobs"], sc["mp_desc"], 3.0, 0.8)
+    m = api.ORBmatcher(0.8, True, ctx=ctx)
+    n, match, obs = m.SearchByProjectionLocal(fi, sc["obs0"], sc["proj_x"], sc["proj_y"], sc["proj_xr"], sc["pred_level"],
+                                              sc["view_cos"], sc["valid"], sc["nobs"], sc["mp_desc"], 3.0)
+    assert n_ref > 500
+    assert n == n_ref and (match == m_ref).all() and (obs == obs_ref).all()
+    n2, match2, _ = m.SearchByProjectionFrame(fi, sc["obs0"], sc["proj_x"], sc["proj_y"], sc["invz"], sc["last_octave"],
+                                              sc["last_angle"], sc["valid"], sc["nobs"], sc["mp_desc"], 7.0, S.KITTI_BF, 0, 100)[:3]
+    n2_ref, m2_ref = oracle.search_by_projection_frame(g, s["dl"], sc["u_right"], sc["obs0"], sf, sc["proj_x"], sc["proj_y"], sc["invz"],
+                                                       sc["last_octave"], sc["last_angle"], sc["valid"], sc["nobs"], sc["mp_desc"], 7.0,
+                                                       S.KITTI_BF, 0, True, 100)[:2]
+    assert n2 == n2_ref and (match2 == m2_ref).all()
+    fi.close()
+
+
 @pytest.mark.parametrize("mode,th,check_ori,th_high", [(0, 15.0, True, 100), (1, 7.0, True, 100), (2, 7.0, False, 100),
                                                        (0, 10.0, True, 64), (0 | 8, 10.0, True, 64), (0 | 8, 3.0, True, 100),
                                                        (3 | 8, 10.0, False, 50)])

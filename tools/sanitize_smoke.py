@@ -20,6 +20,13 @@ for (h, w, nf) in ((360, 640, 777), (97, 211, 200)):
     imgs = synth.frames(3, h, w, seed0=9)
     ex.configure(chunk_frames=2)
     ex.extract_batch(imgs)
+    ex.set_describe_mode(2)             # blur_levels_kernel + describe_blurred_kernel on the same inputs
+    k2, d2 = ex(synth.frame(h, w, 5))
+    assert k2.tobytes() == k.tobytes() and (d2 == d).all()
+    ex.extract_batch(imgs)
+    ex.set_describe_mode(0)
+    ex.configure(chunk_frames=12)
+    ex.extract_batch(synth.frames(12, h, w, seed0=20))      # more than 8 frames per pass: whole levels by default
     ex.close()
 left, right, disp = synth.stereo_pair(376, 620, 7)
 exl, exr = api.ORBextractor(800, 1.2, 8, 20, 7, ctx=ctx), api.ORBextractor(800, 1.2, 8, 20, 7, ctx=ctx)

@@ -262,6 +262,9 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
  * thresholds and the per-cell retry (:812) only re-filters by minThFAST.
  * ---------------------------------------------------------------------------------------------- */
 #define FAST_GROUP 4            /* horizontally adjacent cells per CTA */
+#ifndef FAST_MIN_CTAS
+#define FAST_MIN_CTAS 9
+#endif
 #define FAST_ROWS VIORB_FAST_TILE_ROWS   /* cell sub-image rows  (hCell + 6 <= 66) */
 #define FAST_MAXQ 45            /* quads per window row: 4 cells x wCell (<= 45 when nCols >= 2; one cell of <= 59 otherwise) */
 #define FAST_TW (VIORB_FAST_TILE_BYTES / 4)   /* tile row stride in words = the TMA box width: 1 lead word + 45 quads + 1 tail word */
@@ -366,7 +369,7 @@ __device__ __forceinline__ unsigned fast_score_s16x2(const unsigned (&r)[16], un
 }
 
 template <int SH>
-__global__ void __launch_bounds__(128, 9) fast_cells_kernel(const __grid_constant__ FrameGeom g,
+__global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __grid_constant__ FrameGeom g,
                                                          const __grid_constant__ TmaMaps maps,
                                                          const int4* __restrict__ groups,
                                                          uint32_t* __restrict__ cand, int* __restrict__ candCount,
