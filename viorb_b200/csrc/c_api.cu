@@ -331,8 +331,8 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
                 const int wh = std::min(iniY + L.hCell + 6, maxBorderY) - iniY - 6;
                 if (ww > 0 && wh > 0) {
                     fastWork = std::max(fastWork, ((ww + 3) / 4) * wh);
-                    /* staged candidate records (4 bytes each, in the tile + work0 region): at most every other pixel per
-                     * row and column of a cell is a 3x3 local maximum */
+                    /* staged candidate records (4 bytes each, in the work0 region): at most every other pixel per row and
+                     * column of a cell is a 3x3 local maximum */
                     fastStage = std::max(fastStage, 4 * n * ((L.wCell + 1) / 2) * ((wh + 1) / 2));
                 }
             }
@@ -341,7 +341,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     }
     g.fastTileRows = fastRows;
     g.fastMaxWork = (fastWork + 63) & ~63;
-    g.fastPixBytes = (std::max(fastRows * VIORB_FAST_TILE_BYTES + g.fastMaxWork * 2, fastStage) + 127) & ~127;
+    g.fastPixBytes = (fastRows * VIORB_FAST_TILE_BYTES + std::max(g.fastMaxWork * 2, fastStage) + 127) & ~127;
     if (viorb_fast_prepare(g) != 0) return fail(VIORB_ERR_CUDA, "FAST kernel attribute: %s", cudaGetErrorString(cudaGetLastError()));
     e->ngroups = (int)groups.size();
     {   /* sort by the byte shift of the group's window inside a 4-byte word of the stored row (fast_cells_kernel<SH>) */

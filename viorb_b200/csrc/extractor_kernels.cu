@@ -375,52 +375,55 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __
                                                          uint32_t* __restrict__ cand, int* __restrict__ candCount,
                                                          int* __restrict__ status) {
     /* dynamic shared memory, sized by the host for this geometry (FrameGeom::fast*):
-     *   [ tile: fastTileRows x 208 B | work0: fastMaxWork u16 | pad ]  = fastPixBytes
+     *   [ tile: fastTileRows x 208 B | work0: fastMaxWork u16, later the staged candidate records | pad ]  = fastPixBytes
      *   [ sc: (fastTileRows - 4) x 196 B ] [ work: fastMaxWork u16 ] */
     extern __shared__ __align__(128) unsigned char raw[];
     unsigned* sc = reinterpret_cast<unsigned*>(raw + g.fastPixBytes);
     unsigned short* work = reinterpret_cast<unsigned short*>(raw + g.fastPixBytes + (g.fastTileRows - 4) * FAST_SCW * 4);   /* quads that survive the high-speed test */
     __shared__ __align__(8) unsigned long long bar;   /* mbarrier of the TMA tile load */
-    __shared__ int nwork, nwork0, nout;
+    __shared__ int nwork, nwork0, nout, nqLo, nqHi;
+    __shared__ unsigned char qlist[64];               /* retry pass: quad columns under work (first warp's at 0, second's at 32) */
     __shared__ int cellCnt[FAST_GROUP];               /* per cell: local maxima found by the pass */
     unsigned* tile = reinterpret_cast<unsigned*>(raw);
     unsigned short* work0 = reinterpret_cast<unsigned short*>(raw + g.fastTileRows * FAST_TW * 4);   /* non-flat quads */
-    uint32_t* stage = reinterpret_cast<uint32_t*>(raw);      /* the pass's candidate records (the tile and work0 are dead by then) */
+    uint32_t* stage = reinterpret_cast<uint32_t*>(raw + g.fastTileRows * FAST_TW * 4);   /* the pass's candidate records (work0 is dead by then; the tile stays for the retry pass) */
     const int frame = blockIdx.y;
     /* a CTA owns up to FAST_GROUP horizontally adjacent cells of one cell row: {level, cell row, first cell, n} */
     const int4 grp = __ldg(&groups[blockIdx.x]);
     const int l = grp.x, ci = grp.y, cj0 = grp.z, ncell = grp.w;
     const LevelGeom& L = g.lv[l];
-    const int maxBorderX = L.w - VIORB_FAST_BORDER, maxBorderY = L.h - VIORB_FAST_BORDER;
     const int iniY = VIORB_FAST_BORDER + ci * L.hCell;
     const int iniX = VIORB_FAST_BORDER + cj0 * L.wCell;
+    const int tid = threadIdx.x, lane = tid & 31;
+    /* The tile first: one TMA box per CTA, requested before the rest of the set-up.  The box starts at the 16-byte boundary
+     * at or below window x = -3 of the stored row (TMA needs a 16-byte aligned start), so window pixel x of row y sits at
+     * tile byte 4*w0 + SH + x of row y, SH = (stored byte of window x=0) & 3 -- the same for all groups of a launch (the
+     * host sorts the groups by SH; with 4-cell groups every window starts at byte 51 + 4k*wCell, SH = 3).  Bytes of the box
+     * outside the stored level read as 0 and are never used. */
+    const int gstart = VIORB_ROI_X0 + iniX + 3;
+    const int boxX = (gstart - 3) & ~15;
+    const int w0 = (gstart - boxX) >> 2;
+    const int boxH = min(L.hCell + 6, g.fastTileRows);
+    const int maxBorderX = L.w - VIORB_FAST_BORDER, maxBorderY = L.h - VIORB_FAST_BORDER;
     /* the cells of the group tile the window exactly: cell j detects x in [j*wCell, (j+1)*wCell), the last one
      * is clipped at maxBorderX (:798-806).  Skipped cells (:795-796, :804-805) are not in the table. */
     const int cwG = min(iniX + ncell * L.wCell + 6, maxBorderX) - iniX;
     const int ch = min(iniY + L.hCell + 6, maxBorderY) - iniY;
     const int ww = cwG - 6, wh = ch - 6;      /* detection window of the whole group */
     if (ww <= 0 || wh <= 0) return;
-    const int tid = threadIdx.x, lane = tid & 31;
+    pdl_trigger();
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        pdl_wait();                           /* the pyramid is complete from here on */
+        mbar_expect_tx(&bar, (unsigned)(VIORB_FAST_TILE_BYTES * boxH));
+        tma_load_3d(tile, &maps.fast[l], boxX, VIORB_EDGE + iniY, frame, &bar);
+    }
     const int NQ = (ww + 3) >> 2;            /* quads per window row */
-    const int ntask = NQ * wh;
     const unsigned invNQ = 0xffffffffu / (unsigned)NQ + 1u;          /* t / NQ == umulhi(t, invNQ) for t < 2^16 */
     const unsigned lt = (1u << lane) - 1;
-    const uint8_t* scb = reinterpret_cast<const uint8_t*>(sc);
     uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
     const int wC = L.wCell;
-
-    /* The box starts at the 16-byte boundary A at or below window x = -3 of the stored row (TMA needs a 16-byte
-     * aligned start), so window pixel x of row y sits at tile byte 4*w0 + SH + x of row y,
-     * SH = (stored byte of window x=0) & 3 -- the same for all groups of a launch (the host sorts the groups by SH;
-     * with 4-cell groups every window starts at byte 51 + 4k*wCell, SH = 3).  Bytes of the box outside the stored
-     * level read as 0 and are never used. */
-    const int gstart = VIORB_ROI_X0 + iniX + 3;
-    const int boxX = (gstart - 3) & ~15;
-    const int w0 = (gstart - boxX) >> 2;
-    const int boxH = min(L.hCell + 6, g.fastTileRows);
-    if (tid == 0) mbar_init(&bar, 1);
-    pdl_trigger();
-    pdl_wait();                               /* the pyramid is complete from here on */
+    pdl_wait();                               /* every thread: the candidate pool is written below */
 
     /* Two passes, like the reference (:808-816): pass 0 runs cv::FAST at iniThFAST on all cells of the group; a cell
      * that returns nothing is run again at minThFAST in pass 1 (about one cell in ten, so most CTAs stop after
@@ -429,12 +432,7 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         const int th = pass == 0 ? g.iniTh : g.minTh;
-        /* stage: one TMA box per CTA and pass (the corner-pixel list of the previous pass overwrote the tile) */
-        if (tid == 0) {
-            mbar_expect_tx(&bar, (unsigned)(VIORB_FAST_TILE_BYTES * boxH));
-            tma_load_3d(tile, &maps.fast[l], boxX, VIORB_EDGE + iniY, frame, &bar);
-            nwork = 0; nwork0 = 0; nout = 0;
-        }
+        if (tid == 0) { nwork = 0; nwork0 = 0; nout = 0; }
         {   /* zero the score rows with 16-byte stores (the array starts on a 128-byte boundary; a few words past the
              * last needed row stay inside the (fastTileRows - 4)-row array) */
             uint4* sc4 = reinterpret_cast<uint4*>(sc);
@@ -443,8 +441,23 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __
             for (int i = 4 * n4 + tid; i < (wh + 2) * FAST_SCW; i += blockDim.x) sc[i] = 0;
         }
         if (tid < FAST_GROUP) cellCnt[tid] = 0;
+        if (pass && tid < 64) {
+            /* retry pass: the pre-test only visits the quad columns that touch a cell under retry (one cell in ten is, so
+             * the dense task grid of pass 0 would run at a quarter of its lanes) -- warps 0 and 1 list them */
+            const int q = tid;
+            bool on = false;
+            if (q < NQ) {
+                const int x = 4 * q, x3 = min(x + 3, ww - 1);
+                const int c0 = (x >= wC) + (x >= 2 * wC) + (x >= 3 * wC), c3 = (x3 >= wC) + (x3 >= 2 * wC) + (x3 >= 3 * wC);
+                on = (((retry >> c0) | (retry >> c3)) & 1u) != 0;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (tid < 32) nqLo = __popc(m);
+            else nqHi = __popc(m);
+            if (on) qlist[(tid < 32 ? 0 : 32) + __popc(m & lt)] = (unsigned char)q;
+        }
         __syncthreads();
-        mbar_wait(&bar, (unsigned)pass);
+        if (pass == 0) mbar_wait(&bar, 0u);        /* the tile has landed (it stays intact for the retry pass) */
 
         /* phase 0 -- byte-domain pre-test on the four compass samples (k = 0, 4, 8, 12) of every quad: every 9-arc
          * of the ring contains two ADJACENT compass samples, so a pixel can only be a corner at th if
@@ -455,22 +468,20 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __
          * north sample, and only the east / west samples are fetched per row.  One shared atomic per warp and strip. */
         {
             const unsigned addc = (unsigned)(127 - th) * 0x01010101u;
-            const int nstrip = (wh + FAST_STRIP - 1) / FAST_STRIP, ntask0 = NQ * nstrip;
+            const int nq0 = pass ? nqLo : NQ, nqe = pass ? nq0 + nqHi : NQ;        /* quad columns this pass visits */
+            const unsigned invNQe = pass ? 0xffffffffu / (unsigned)nqe + 1u : invNQ;
+            const int nstrip = (wh + FAST_STRIP - 1) / FAST_STRIP, ntask0 = nqe * nstrip;
             for (int t0 = 0; t0 < ntask0; t0 += blockDim.x) {
                 const int t = t0 + tid;
                 unsigned keepMask = 0;                  /* bit r: window row ys + r of this quad column survives */
                 int q = 0, ys = 0;
-                if (t < ntask0) {
-                    const int sidx = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t;
-                    q = t - sidx * NQ;
+                const bool active = t < ntask0;
+                if (active) {
+                    const int sidx = nqe > 1 ? (int)__umulhi((unsigned)t, invNQe) : t;
+                    q = t - sidx * nqe;
+                    if (pass) q = qlist[q < nq0 ? q : 32 + q - nq0];
                     ys = sidx * FAST_STRIP;
-                    bool active = true;
-                    if (pass) {     /* only quads that touch a cell under retry */
-                        const int x = 4 * q, x3 = min(x + 3, ww - 1);
-                        const int c0 = (x >= wC) + (x >= 2 * wC) + (x >= 3 * wC), c3 = (x3 >= wC) + (x3 >= 2 * wC) + (x3 >= 3 * wC);
-                        active = (((retry >> c0) | (retry >> c3)) & 1u) != 0;
-                    }
-                    if (active) {
+                    {
                         /* tile row ys + j holds window row ys + j - 3; rows past the tile read the lists that follow it in
                          * shared memory and only reach rows >= wh, which are masked below */
                         const unsigned* col = &tile[ys * FAST_TW + w0 + q];
