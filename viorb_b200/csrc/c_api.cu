@@ -238,7 +238,7 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
         L.xtab = xtab; L.ytab = ytab;
         xtab += L.step / 4; ytab += L.h + 2 * VIORB_EDGE;
         /* dense blur: bands of at most 48 output rows (the 6 extra input rows of a band cost 1/8), equal per level */
-        static const int bandMax = [] { const char* v = getenv("VIORB_BLUR_BAND"); return v ? std::max(8, atoi(v)) : 48; }();
+        const int bandMax = 48;            /* 24 .. 96 measure within 2 % of each other */
         const int bands = (L.h + bandMax - 1) / bandMax;
         L.blurRows = ((L.h + bands - 1) / bands + 7) / 8 * 8;
         L.blurStrips = (L.w + 7) / 8;

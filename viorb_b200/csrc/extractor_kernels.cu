@@ -1914,8 +1914,7 @@ int viorb_launch_describe(const FrameGeom& g, int frame0, int F, const ExtractBu
     /* keypoints per warp: batches amortise the warp's pattern registers over up to DESC_KPW keypoints, as long as the
      * grid still holds two waves of CTAs (148 SMs x 7); a few frames keep one keypoint per warp (shortest latency) */
     int kpw = (int)(((long long)F * slots) / (DESC_WARPS * 148 * 14));
-    static const int kpwMax = [] { const char* v = getenv("VIORB_KPW"); return v ? atoi(v) : 0; }();
-    const int kmax = b.blur ? ((kpwMax > 0 && kpwMax <= 32) ? kpwMax : DESC2_KPW) : DESC_KPW;
+    const int kmax = b.blur ? DESC2_KPW : DESC_KPW;         /* (8 keypoints per warp: 2.5 % slower describe stage; 32: no different from 16) */
     kpw = kpw < 1 ? 1 : (kpw > kmax ? kmax : kpw);
     dim3 grid((slots + DESC_WARPS * kpw - 1) / (DESC_WARPS * kpw), F);
     if (grid.x == 0) grid.x = 1;
