@@ -526,46 +526,48 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __
         }
         __syncthreads();
 
-        /* phase 1 -- high-speed test on the non-flat quads.  A 9-arc of the 16-ring always contains a pair of
-         * opposite samples (k, k+8), so a corner at threshold t needs an opposite pair that is brighter than v + t on
-         * both ends, or darker than v - t on both ends.  Straight edges fail this test. */
-        const unsigned thP = (unsigned)th * 0x00010001u, nthP = __vneg2(thP);
-        const int n0 = nwork0;
-        for (int i0 = 0; i0 < n0; i0 += blockDim.x) {
-            const int i = i0 + tid;
-            bool keep = false;
-            int t = 0;
-            if (i < n0) {
-                t = work0[i];
-                const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
-                const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
-                const unsigned cw4 = fast_ld4<SH>(row);
-                unsigned rA[16], rB[16];
-                fast_load_ring<SH>(row, rA, rB);
-                const unsigned nvA = __vneg2(__byte_perm(cw4, 0, 0x4240)), nvB = __vneg2(__byte_perm(cw4, 0, 0x4341));
-                unsigned loA[8], hiA[8], loB[8], hiB[8];
+        /* phase 1 -- segment test without signs on the non-flat quads, still in the byte domain (four pixels per
+         * operation, no splitting into 16-bit lanes): a corner at th has 9 contiguous ring samples that all differ from the
+         * centre by more than th (all brighter or all darker; ignoring which only admits a few more quads: 11.9 % of all
+         * quads pass on the benchmark frames, 11.0 % pass the signed opposite-pair test used before, 9.5 % hold a corner).
+         * f[k] bit 7 = |ring k - centre| > th; 9 in a row = and3 of and3s, any start = or over the 16 arcs. */
+        const unsigned thP = (unsigned)th * 0x00010001u;
+        {
+            const unsigned addc = (unsigned)(127 - th) * 0x01010101u;
+            const int n0 = nwork0;
+            for (int i0 = 0; i0 < n0; i0 += blockDim.x) {
+                const int i = i0 + tid;
+                bool keep = false;
+                int t = 0;
+                if (i < n0) {
+                    t = work0[i];
+                    const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
+                    const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
+                    const unsigned cw4 = fast_ld4<SH>(row);
+                    unsigned f[16];
+#define RING(k, dy, dx)                                                                               \
+                    {                                                                                  \
+                        const unsigned d_ = __vabsdiffu4(fast_ld4<SH + (dx)>(row + (dy) * FAST_TW), cw4); \
+                        f[k] = (d_ + addc) | d_;                                                       \
+                    }
+                    FAST_RING_LIST(RING)
+#undef RING
+                    unsigned a3[16];
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    loA[k] = __vmins2(rA[k], rA[k + 8]); hiA[k] = __vmaxs2(rA[k], rA[k + 8]);
-                    loB[k] = __vmins2(rB[k], rB[k + 8]); hiB[k] = __vmaxs2(rB[k], rB[k + 8]);
+                    for (int k = 0; k < 16; k++) a3[k] = f[k] & f[(k + 1) & 15] & f[(k + 2) & 15];
+                    unsigned a9[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k++) a9[k] = a3[k] & a3[(k + 3) & 15] & a3[(k + 6) & 15];
+                    const unsigned o0 = a9[0] | a9[1] | a9[2], o1 = a9[3] | a9[4] | a9[5], o2 = a9[6] | a9[7] | a9[8];
+                    const unsigned o3 = a9[9] | a9[10] | a9[11], o4 = a9[12] | a9[13] | a9[14];
+                    keep = (((o0 | o1 | o2) | (o3 | o4 | a9[15])) & 0x80808080u) != 0;
                 }
-                const unsigned brightA = __vimax3_s16x2(__vimax3_s16x2(loA[0], loA[1], loA[2]), __vimax3_s16x2(loA[3], loA[4], loA[5]),
-                                                        __vmaxs2(loA[6], loA[7]));
-                const unsigned brightB = __vimax3_s16x2(__vimax3_s16x2(loB[0], loB[1], loB[2]), __vimax3_s16x2(loB[3], loB[4], loB[5]),
-                                                        __vmaxs2(loB[6], loB[7]));
-                const unsigned darkA = __vimin3_s16x2(__vimin3_s16x2(hiA[0], hiA[1], hiA[2]), __vimin3_s16x2(hiA[3], hiA[4], hiA[5]),
-                                                      __vmins2(hiA[6], hiA[7]));
-                const unsigned darkB = __vimin3_s16x2(__vimin3_s16x2(hiB[0], hiB[1], hiB[2]), __vimin3_s16x2(hiB[3], hiB[4], hiB[5]),
-                                                      __vmins2(hiB[6], hiB[7]));
-                const unsigned up = __vmaxs2(__vadd2(brightA, nvA), __vadd2(brightB, nvB));   /* best opposite-pair excess */
-                const unsigned dn = __vmins2(__vadd2(darkA, nvA), __vadd2(darkB, nvB));
-                keep = !(__vmaxs2(up, thP) == thP && __vmins2(dn, nthP) == nthP);
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                int basePos = 0;
+                if (lane == 0 && m) basePos = smem_add(&nwork, __popc(m));
+                basePos = __shfl_sync(0xffffffffu, basePos, 0);
+                if (keep) work[basePos + __popc(m & lt)] = (unsigned short)t;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            int basePos = 0;
-            if (lane == 0 && m) basePos = smem_add(&nwork, __popc(m));
-            basePos = __shfl_sync(0xffffffffu, basePos, 0);
-            if (keep) work[basePos + __popc(m & lt)] = (unsigned short)t;
         }
         __syncthreads();
 
