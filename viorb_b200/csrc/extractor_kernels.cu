@@ -493,34 +493,37 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __
                             const unsigned d = __vabsdiffu4(C[j], C[j + 3]);
                             fV[j] = (d + addc) | d;
                         }
-                        const unsigned rowsLeft = (unsigned)(wh - ys);
 #pragma unroll
                         for (int r = 0; r < FAST_STRIP; r++) {
                             const unsigned* row = col + (r + 3) * FAST_TW;
                             const unsigned dE = __vabsdiffu4(fast_ld4<SH + 3>(row), C[r + 3]);
                             const unsigned dW = __vabsdiffu4(fast_ld4<SH - 3>(row), C[r + 3]);
                             const unsigned fEW = (dE + addc) | dE | (dW + addc) | dW;
-                            /* (f0&f4)|(f4&f8)|(f8&f12)|(f12&f0) = (f0|f8) & (f4|f12) */
-                            if ((((fV[r] | fV[r + 3]) & fEW) & 0x80808080u) != 0 && (unsigned)r < rowsLeft) keepMask |= 1u << r;
+                            /* (f0&f4)|(f4&f8)|(f8&f12)|(f12&f0) = (f0|f8) & (f4|f12); the row's bit without a predicate */
+                            keepMask += min(((fV[r] | fV[r + 3]) & fEW) & 0x80808080u, 1u) << r;
                         }
+                        const int rowsLeft = wh - ys;                 /* rows past the window do not exist */
+                        if (rowsLeft < FAST_STRIP) keepMask &= (1u << rowsLeft) - 1u;
                     }
                 }
-                unsigned m[FAST_STRIP];
-                int total = 0;
+                /* compaction: warp scan of the per-thread counts (five shuffles), one shared atomic per warp, each thread
+                 * appends its rows */
+                const int n = __popc(keepMask);
+                int incl = n;
 #pragma unroll
-                for (int r = 0; r < FAST_STRIP; r++) {
-                    m[r] = __ballot_sync(0xffffffffu, (keepMask >> r) & 1u);
-                    total += __popc(m[r]);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
                 }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
                 if (total == 0) continue;
                 int basePos = 0;
-                if (lane == 0) basePos = smem_add(&nwork0, total);
-                basePos = __shfl_sync(0xffffffffu, basePos, 0);
+                if (lane == 31) basePos = smem_add(&nwork0, total);
+                int pos = __shfl_sync(0xffffffffu, basePos, 31) + incl - n;
                 const int tb = ys * NQ + q;                  /* task id of window row ys: y * NQ + q */
 #pragma unroll
                 for (int r = 0; r < FAST_STRIP; r++) {
-                    if ((keepMask >> r) & 1u) work0[basePos + __popc(m[r] & lt)] = (unsigned short)(tb + r * NQ);
-                    basePos += __popc(m[r]);
+                    if ((keepMask >> r) & 1u) work0[pos++] = (unsigned short)(tb + r * NQ);
                 }
             }
         }
