@@ -324,12 +324,12 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
             while (G > 1 && (G * L.wCell > 180 || ((G * L.wCell + 3) / 4) * std::min(L.hCell, 59) > 2048)) G--;
             for (int j = 0; j < nvalid; j += G) {
                 const int n = std::min(G, nvalid - j);
-                groups.push_back(make_int4(l, i, j, n));
                 /* the group's detection window (fast_cells_kernel): ww x wh pixels, NQ quads per row */
                 const int iniX = VIORB_FAST_BORDER + j * L.wCell, iniY = VIORB_FAST_BORDER + i * L.hCell;
                 const int ww = std::min(iniX + n * L.wCell + 6, maxBorderX) - iniX - 6;
                 const int wh = std::min(iniY + L.hCell + 6, maxBorderY) - iniY - 6;
                 if (ww > 0 && wh > 0) {
+                    groups.push_back(make_int4(l, i, j, n));
                     fastWork = std::max(fastWork, ((ww + 3) / 4) * wh);
                     /* staged candidate records (4 bytes each, in the work0 region): at most every other pixel per row and
                      * column of a cell is a 3x3 local maximum */
@@ -343,7 +343,6 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
     g.fastMaxWork = (fastWork + 63) & ~63;
     g.fastPixBytes = (fastRows * VIORB_FAST_TILE_BYTES + std::max(g.fastMaxWork * 2, fastStage) + 127) & ~127;
     if (viorb_fast_prepare(g) != 0) return fail(VIORB_ERR_CUDA, "FAST kernel attribute: %s", cudaGetErrorString(cudaGetLastError()));
-    e->ngroups = (int)groups.size();
     {   /* sort by the byte shift of the group's window inside a 4-byte word of the stored row (fast_cells_kernel<SH>) */
         auto shiftOf = [&](const int4& gr) { return (VIORB_ROI_X0 + VIORB_FAST_BORDER + gr.z * g.lv[gr.x].wCell + 3) & 3; };
         std::stable_sort(groups.begin(), groups.end(), [&](const int4& a, const int4& b) { return shiftOf(a) < shiftOf(b); });
@@ -352,9 +351,29 @@ int build_geometry(viorb_extractor* e, int rows, int cols) {
         e->groupClass[0] = 0;
         for (int i = 0; i < 4; i++) e->groupClass[i + 1] = e->groupClass[i] + cnt[i];
     }
+    e->ngroups = (int)groups.size();
+    /* what the kernel needs per group, precomputed (two int4 per group, fast_cells_kernel) */
+    std::vector<int4> gdesc;
+    gdesc.reserve(2 * groups.size());
+    for (const int4& gr : groups) {
+        const LevelGeom& L = g.lv[gr.x];
+        const int i = gr.y, j0 = gr.z, n = gr.w;
+        const int maxBorderX = L.w - VIORB_FAST_BORDER, maxBorderY = L.h - VIORB_FAST_BORDER;
+        const int iniX = VIORB_FAST_BORDER + j0 * L.wCell, iniY = VIORB_FAST_BORDER + i * L.hCell;
+        const int ww = std::min(iniX + n * L.wCell + 6, maxBorderX) - iniX - 6;
+        const int wh = std::min(iniY + L.hCell + 6, maxBorderY) - iniY - 6;
+        const int NQ = (ww + 3) >> 2;
+        const int gstart = VIORB_ROI_X0 + iniX + 3, boxX = (gstart - 3) & ~15, w0 = (gstart - boxX) >> 2;
+        const int boxH = std::min(L.hCell + 6, g.fastTileRows);
+        if (L.wCell > 255 || NQ > 255 || ww > 65535 || wh > 32767 || boxH > 32767)
+            return fail(VIORB_ERR_UNSUPPORTED, "FAST cell %dx%d outside the kernel's envelope", L.wCell, L.hCell);
+        gdesc.push_back(make_int4(gr.x | (n << 8) | (L.wCell << 16), ww | (wh << 16), NQ | (w0 << 8) | (boxH << 16),
+                                  (int)(0xffffffffu / (unsigned)NQ + 1u)));
+        gdesc.push_back(make_int4(boxX, VIORB_EDGE + iniY, L.candBase, (3 + j0 * L.wCell) | ((3 + i * L.hCell) << 12)));
+    }
     int rc;
-    if ((rc = e->groups.ensure(groups.size() + 1))) return rc;
-    CU(cudaMemcpyAsync(e->groups.p, groups.data(), groups.size() * sizeof(int4), cudaMemcpyHostToDevice, e->ctx->stream));
+    if ((rc = e->groups.ensure(gdesc.size() + 1))) return rc;
+    CU(cudaMemcpyAsync(e->groups.p, gdesc.data(), gdesc.size() * sizeof(int4), cudaMemcpyHostToDevice, e->ctx->stream));
     if ((rc = e->tabCol.ensure(tcol.size() + 1))) return rc;
     if ((rc = e->tabRow.ensure(trow.size() + 1))) return rc;
     CU(cudaMemcpyAsync(e->tabCol.p, tcol.data(), tcol.size() * sizeof(uint4), cudaMemcpyHostToDevice, e->ctx->stream));

@@ -388,41 +388,34 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __
     unsigned short* work0 = reinterpret_cast<unsigned short*>(raw + g.fastTileRows * FAST_TW * 4);   /* non-flat quads */
     uint32_t* stage = reinterpret_cast<uint32_t*>(raw + g.fastTileRows * FAST_TW * 4);   /* the pass's candidate records (work0 is dead by then; the tile stays for the retry pass) */
     const int frame = blockIdx.y;
-    /* a CTA owns up to FAST_GROUP horizontally adjacent cells of one cell row: {level, cell row, first cell, n} */
-    const int4 grp = __ldg(&groups[blockIdx.x]);
-    const int l = grp.x, ci = grp.y, cj0 = grp.z, ncell = grp.w;
-    const LevelGeom& L = g.lv[l];
-    const int iniY = VIORB_FAST_BORDER + ci * L.hCell;
-    const int iniX = VIORB_FAST_BORDER + cj0 * L.wCell;
+    /* A CTA owns up to FAST_GROUP horizontally adjacent cells of one cell row.  Everything that depends only on the
+     * geometry comes precomputed from the host (c_api.cu build_geometry), two 16-byte words per group:
+     *   {level | cells << 8 | wCell << 16, ww | wh << 16, NQ | w0 << 8 | boxH << 16, 2^32 / NQ}
+     *   {boxX, first stored row of the box, candBase, recBase = (3 + j0 * wCell) | (3 + i * hCell) << 12}
+     * ww x wh = detection window of the group (the cells tile it exactly: cell j detects x in [j*wCell, (j+1)*wCell), the
+     * last one is clipped at maxBorderX, :798-806; skipped cells, :795-796, :804-805, and empty windows are not listed). */
+    const int4 ga = __ldg(&groups[2 * blockIdx.x]), gb = __ldg(&groups[2 * blockIdx.x + 1]);
+    const int l = ga.x & 0xff, ncell = (ga.x >> 8) & 0xff, wC = ga.x >> 16;
+    const int ww = ga.y & 0xffff, wh = ga.y >> 16;
+    const int NQ = ga.z & 0xff, w0 = (ga.z >> 8) & 0xff, boxH = ga.z >> 16;      /* quads per window row, first window word of a tile row */
+    const unsigned invNQ = (unsigned)ga.w;                                       /* t / NQ == umulhi(t, invNQ) for t < 2^16 */
     const int tid = threadIdx.x, lane = tid & 31;
     /* The tile first: one TMA box per CTA, requested before the rest of the set-up.  The box starts at the 16-byte boundary
      * at or below window x = -3 of the stored row (TMA needs a 16-byte aligned start), so window pixel x of row y sits at
      * tile byte 4*w0 + SH + x of row y, SH = (stored byte of window x=0) & 3 -- the same for all groups of a launch (the
      * host sorts the groups by SH; with 4-cell groups every window starts at byte 51 + 4k*wCell, SH = 3).  Bytes of the box
      * outside the stored level read as 0 and are never used. */
-    const int gstart = VIORB_ROI_X0 + iniX + 3;
-    const int boxX = (gstart - 3) & ~15;
-    const int w0 = (gstart - boxX) >> 2;
-    const int boxH = min(L.hCell + 6, g.fastTileRows);
-    const int maxBorderX = L.w - VIORB_FAST_BORDER, maxBorderY = L.h - VIORB_FAST_BORDER;
-    /* the cells of the group tile the window exactly: cell j detects x in [j*wCell, (j+1)*wCell), the last one
-     * is clipped at maxBorderX (:798-806).  Skipped cells (:795-796, :804-805) are not in the table. */
-    const int cwG = min(iniX + ncell * L.wCell + 6, maxBorderX) - iniX;
-    const int ch = min(iniY + L.hCell + 6, maxBorderY) - iniY;
-    const int ww = cwG - 6, wh = ch - 6;      /* detection window of the whole group */
-    if (ww <= 0 || wh <= 0) return;
     pdl_trigger();
     if (tid == 0) {
         mbar_init(&bar, 1);
         pdl_wait();                           /* the pyramid is complete from here on */
         mbar_expect_tx(&bar, (unsigned)(VIORB_FAST_TILE_BYTES * boxH));
-        tma_load_3d(tile, &maps.fast[l], boxX, VIORB_EDGE + iniY, frame, &bar);
+        tma_load_3d(tile, &maps.fast[l], gb.x, gb.y, frame, &bar);
     }
-    const int NQ = (ww + 3) >> 2;            /* quads per window row */
-    const unsigned invNQ = 0xffffffffu / (unsigned)NQ + 1u;          /* t / NQ == umulhi(t, invNQ) for t < 2^16 */
+    const LevelGeom& L = g.lv[l];
     const unsigned lt = (1u << lane) - 1;
-    uint32_t* out = cand + (size_t)frame * g.candPerFrame + L.candBase;
-    const int wC = L.wCell;
+    uint32_t* out = cand + (size_t)frame * g.candPerFrame + gb.z;
+    const uint32_t recBase = (uint32_t)gb.w;
     pdl_wait();                               /* every thread: the candidate pool is written below */
 
     /* Two passes, like the reference (:808-816): pass 0 runs cv::FAST at iniThFAST on all cells of the group; a cell
@@ -648,21 +641,25 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __
                     lm &= (inLo ? loMask : 0u) | (inHi ? (0xfu & ~loMask) : 0u);
                 }
             }
-            const unsigned m0 = __ballot_sync(0xffffffffu, lm & 1u), m1 = __ballot_sync(0xffffffffu, lm & 2u);
-            const unsigned m2 = __ballot_sync(0xffffffffu, lm & 4u), m3 = __ballot_sync(0xffffffffu, lm & 8u);
-            if ((m0 | m1 | m2 | m3) == 0) continue;
-            const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
+            /* compaction as in phase 0: warp scan of the per-thread counts, one shared atomic per warp */
+            const int n = __popc(lm);
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) continue;
             int base = 0;
-            if (lane == 0) base = smem_add(&nout, c0 + c1 + c2 + c3);
-            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lane == 31) base = smem_add(&nout, total);
+            int pos = __shfl_sync(0xffffffffu, base, 31) + incl - n;
             if (lm) {
-                /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825) */
-                const uint32_t rec = (uint32_t)(x0 + 3 + cj0 * wC) | ((uint32_t)(y + 3 + ci * L.hCell) << 12);
-                const uint32_t bias = (uint32_t)(th - 1);
-                if (lm & 1u) stage[base + __popc(m0 & lt)] = rec | (((cw & 0xffu) + bias) << 24);
-                if (lm & 2u) stage[base + c0 + __popc(m1 & lt)] = (rec + 1) | ((((cw >> 8) & 0xffu) + bias) << 24);
-                if (lm & 4u) stage[base + c0 + c1 + __popc(m2 & lt)] = (rec + 2) | ((((cw >> 16) & 0xffu) + bias) << 24);
-                if (lm & 8u) stage[base + c0 + c1 + c2 + __popc(m3 & lt)] = (rec + 3) | (((cw >> 24) + bias) << 24);
+                /* window coordinates: cell-relative (x+3, y+3) + (j*wCell, i*hCell)   (:820-825); score byte + th - 1 */
+                const uint32_t rec = recBase + (uint32_t)x0 + ((uint32_t)y << 12) + ((uint32_t)(th - 1) << 24);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((lm >> k) & 1u) stage[pos++] = rec + (uint32_t)k + (((cw >> (8 * k)) & 0xffu) << 24);
                 const unsigned lo = lm & (jb >= 4 ? 0xfu : ((1u << jb) - 1u));
                 if (lo) smem_add(&cellCnt[cg0], __popc(lo));
                 if (lm & ~lo) smem_add(&cellCnt[cg0 + 1], __popc(lm & ~lo));
@@ -1554,7 +1551,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 7) describe_blurred_kernel(co
     }
     pdl_wait();                               /* the selected keypoints and the blurred levels are complete from here on */
     /* lane l holds [lo, hi) of level l in the concatenated per-level lists (:1076-1103) */
-    int myLo, myHi, total;
+    int myHi, total;
     {
         const int c = lane < g.nlevels ? selCount[frame * g.nlevels + lane] : 0;
         int incl = c;
@@ -1564,7 +1561,6 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 7) describe_blurred_kernel(co
             if (lane >= o) incl += t;
         }
         myHi = incl;
-        myLo = incl - c;
         total = __shfl_sync(0xffffffffu, incl, 31);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
