@@ -513,10 +513,10 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __
                 int basePos = 0;
                 if (lane == 31) basePos = smem_add(&nwork0, total);
                 int pos = __shfl_sync(0xffffffffu, basePos, 31) + incl - n;
-                const int tb = ys * NQ + q;                  /* task id of window row ys: y * NQ + q */
+                const int tb = (ys << 8) | q;                /* list entry of window row ys: q | y << 8 */
 #pragma unroll
                 for (int r = 0; r < FAST_STRIP; r++) {
-                    if ((keepMask >> r) & 1u) work0[pos++] = (unsigned short)(tb + r * NQ);
+                    if ((keepMask >> r) & 1u) work0[pos++] = (unsigned short)(tb + (r << 8));
                 }
             }
         }
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __
                 int t = 0;
                 if (i < n0) {
                     t = work0[i];
-                    const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
+                    const int y = t >> 8, q = t & 0xff;
                     const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
                     const unsigned cw4 = fast_ld4<SH>(row);
                     unsigned f[16];
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __
         const int nw = nwork;
         for (int i = tid; i < nw; i += blockDim.x) {
             const int t = work[i];
-            const int y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t, q = t - y * NQ;
+            const int y = t >> 8, q = t & 0xff;
             const unsigned* row = &tile[(y + 3) * FAST_TW + w0 + q];
             unsigned rA[16], rB[16];
             fast_load_ring<SH>(row, rA, rB);
@@ -601,8 +601,8 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) fast_cells_kernel(const __
             int x0 = 0, y = 0, cg0 = 0, jb = 8;
             if (i < nw) {
                 const int t = work[i];
-                y = NQ > 1 ? (int)__umulhi((unsigned)t, invNQ) : t;
-                const int q = t - y * NQ;
+                y = t >> 8;
+                const int q = t & 0xff;
                 const unsigned* c = &sc[(y + 1) * FAST_SCW + q + 1];
                 cw = c[0];
                 if (cw) {
