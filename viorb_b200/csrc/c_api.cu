@@ -849,7 +849,14 @@ static int extract_batch_once(viorb_extractor* e, const uint8_t* images, int B, 
      * pipeline (first copy in, last pass, last copy out) stays small for short batches; 32..128 (measured:
      * tools/small_batch_sweep.sh) */
     int passFrames = default_pass_frames(e, rows, cols);
-    if (!e->chunkUser) passFrames = std::min(passFrames, std::max(std::min(32, passFrames), (B / 12 + 15) / 16 * 16));
+    if (!e->chunkUser) {
+        /* this path is bound by the input copies (55 GB/s of PCIe carry 150 k EuRoC frames/s, the kernels do 220 k), so what
+         * counts is how soon the first pass can start and how short the last one is: three eighths of the device-resident
+         * pass size (48 EuRoC frames; 4096 frames per call: 128 -> 138.6 k, 96 -> 144.8 k, 64 -> 145.0 k, 48 -> 146.2 k,
+         * 32 -> 141.4 k frames/s, the copies alone allow 150.8 k) */
+        passFrames = std::max(1, (passFrames * 3 + 4) / 8);
+        passFrames = std::min(passFrames, std::max(std::min(32, passFrames), (B / 12 + 15) / 16 * 16));
+    }
     const int F = std::min(passFrames, B);
     if ((rc = ensure_workspace(e, F))) return rc;
     const size_t inFrame = (size_t)rows * cols;        /* device copy is packed */
