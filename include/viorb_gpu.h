@@ -65,10 +65,11 @@ int viorb_host_free(void* p);
 int viorb_extractor_create(viorb_ctx* ctx, int nfeatures, float scale_factor, int nlevels,
                            int ini_th_fast, int min_th_fast, viorb_extractor** out);
 int viorb_extractor_destroy(viorb_extractor* ex);
-/* optional tuning: frames processed per device pass (default 128 EuRoC-size frames = 229 MB of pyramid + lists per pass,
+/* optional tuning: frames processed per device pass (default 128 EuRoC-size frames = 229 MB of pyramid + lists per pass, 412 MB with the blurred levels,
  * more than the 126 MB L2: the kernels are bound by integer issue, not by DRAM, so the pass is sized for full waves of
  * CTAs per launch rather than for L2 residency -- measured 2.1x the compulsory DRAM bytes at 5 % of the HBM peak; the
- * host-buffer batch call uses 32..128 depending on the batch so that short batches still pipeline) and the
+ * host-buffer batch call, which is bound by its input copies, uses 48, down to 32 for short batches, so that the first
+ * pass starts early and the last one is short) and the
  * candidate pool per level as a fraction 1/div of the level's pixel count. */
 int viorb_extractor_configure(viorb_extractor* ex, int chunk_frames, int cand_div);
 /* How viorb_extract_batch schedules its host<->device copies.  VIORB_COPY_DUPLEX (default): input and output copies on two
