@@ -5,7 +5,9 @@
  *   pyr_level0_kernel / pyr_resize_kernel   ComputePyramid            :1107-1132  (+ cv::resize, copyMakeBorder)
  *   fast_cells_kernel                       ComputeKeyPointsOctTree   :765-829    (+ cv::FAST x2 per cell)
  *   octree_kernel                           DistributeOctTree         :539-763
- *   orient_describe_kernel                  IC_Angle :77-104, GaussianBlur :1086, computeOrbDescriptor :108-147
+ *   blur_levels_kernel                      GaussianBlur :1085-1086 of whole levels               (batches)
+ *   describe_blurred_kernel                 IC_Angle :77-104, computeOrbDescriptor :108-147       (batches)
+ *   orient_describe_kernel                  IC_Angle, GaussianBlur, computeOrbDescriptor fused per keypoint (single frames)
  *
  * All integer stages are bit-exact restatements; float steps use round-to-nearest single ops without
  * FMA contraction (the file is compiled with -fmad=false and uses __f*_rn where order matters).
