@@ -196,7 +196,10 @@ def test_bad_arguments(api, ctx):
 # scale-factor envelope (1.1 .. 1.5), few/many levels, thresholds far apart and equal
 SWEEP = [(97, 131, 200, 1.2, 3, 20, 7), (333, 250, 500, 1.25, 5, 15, 5), (480, 640, 1500, 1.5, 4, 20, 7),
          (241, 1023, 800, 1.1, 8, 25, 10), (720, 1280, 3000, 1.3, 6, 20, 20), (128, 128, 300, 1.2, 4, 30, 3),
-         (479, 751, 1000, 1.2, 8, 20, 7), (600, 799, 1200, 1.41, 5, 12, 7)]
+         (479, 751, 1000, 1.2, 8, 20, 7), (600, 799, 1200, 1.41, 5, 12, 7),
+         # level 3 is 181x91: one row of 38x59 cells whose last group starts at another byte shift than the first -- two
+         # instantiations of the FAST kernel, each with its own slice of the group table (found by the fuzz, seed 31)
+         (158, 312, 236, 1.2, 6, 12, 7)]
 
 
 @pytest.mark.parametrize("cfg", SWEEP, ids=lambda c: "%dx%d_s%.2f_l%d" % (c[1], c[0], c[3], c[4]))

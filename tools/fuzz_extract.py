@@ -15,12 +15,15 @@ from util import fuzz_extract_cases  # noqa: E402
 def main():
     cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    verbose = len(sys.argv) > 3
     ctx = api.Context(0)
     bad = 0
     skipped = 0
     total_kp = 0
     for c, img, (nf, sf, nl, it, mt) in fuzz_extract_cases(cases, seed):
         h, w = img.shape
+        if verbose:
+            print("case %d: %dx%d nf=%d sf=%.3f nl=%d th=%d/%d mode=%d" % (c, w, h, nf, sf, nl, it, mt, 1 + c % 2), flush=True)
         try:
             ex = api.ORBextractor(nf, sf, nl, it, mt, ctx=ctx)
             ex.set_describe_mode(1 + c % 2)      # odd cases blur whole levels, even cases blur per keypoint

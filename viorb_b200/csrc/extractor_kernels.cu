@@ -1806,7 +1806,7 @@ int viorb_launch_fast(const FrameGeom& g, const TmaMaps& maps, const int4* d_gro
         if (n <= 0) continue;
         const bool first = launches == 0;
         dim3 grid(n, F);
-        const int4* grp = d_groups + classStart[sh];
+        const int4* grp = d_groups + 2 * (size_t)classStart[sh];       /* two 16-byte words per group */
         switch (sh) {
             case 0: launch_k(fast_cells_kernel<0>, grid, dim3(128), smem, s, (pdl & (first ? VIORB_PDL_EDGE : VIORB_PDL_INNER)) != 0, g, maps, grp, b.cand, b.candCount, b.status); break;
             case 1: launch_k(fast_cells_kernel<1>, grid, dim3(128), smem, s, (pdl & (first ? VIORB_PDL_EDGE : VIORB_PDL_INNER)) != 0, g, maps, grp, b.cand, b.candCount, b.status); break;
