@@ -37,6 +37,17 @@ def main():
         kr, dr = ref(img)
         total_kp += len(kr)
         ok = len(kg) == len(kr) and kg.tobytes() == kr.tobytes() and (dg == dr).all()
+        if ok and c % 4 == 0 and h * w <= 600 * 800:
+            # the batch kernels (128 x 64 pyramid tiles, several keypoints per warp, whole-level blur by default) on the same
+            # geometry: nine frames in passes of nine, the case's image and its mirror alternating
+            ex.set_describe_mode(c % 3)
+            imgs = np.stack([img if i % 2 == 0 else np.ascontiguousarray(img[:, ::-1]) for i in range(9)])
+            bk, bd, bn = ex.extract_batch(imgs)
+            km, dm = ref(imgs[1])
+            for i in range(9):
+                kx, dx = (kr, dr) if i % 2 == 0 else (km, dm)
+                ok = ok and bn[i] == len(kx) and bk[i, :bn[i]].tobytes() == kx.tobytes() and (bd[i, :bn[i]] == dx).all()
+            total_kp += 4 * len(kr) + 4 * len(km)
         if not ok:
             bad += 1
             print("MISMATCH case %d: %dx%d nf=%d sf=%.2f nl=%d th=%d/%d n=%d/%d" % (c, w, h, nf, sf, nl, it, mt, len(kg), len(kr)))
