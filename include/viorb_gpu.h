@@ -135,6 +135,11 @@ int viorb_extractor_check(viorb_extractor* ex);      /* synchronises, returns de
 int viorb_extractor_pyramid_info(const viorb_extractor* ex, int level, int* w, int* h);
 int viorb_extractor_pyramid_download(viorb_extractor* ex, int frame, int level, uint8_t* dst_padded,
                                      size_t dst_step);
+/* all levels of one frame in one call: a single device-to-host copy of the frame's pyramid block into a pinned staging
+ * buffer, then row copies into dst_padded[l] ((w_l+38) x (h_l+38), row stride dst_step[l]) -- what a caller that reads the
+ * whole mvImagePyramid after operator() wants (eight synchronous pageable copies otherwise) */
+int viorb_extractor_pyramid_download_all(viorb_extractor* ex, int frame, uint8_t* const* dst_padded,
+                                         const size_t* dst_step, int nlevels);
 /* device view of the ROI origin of (frame, level) and its row stride (for device-side consumers) */
 int viorb_extractor_pyramid_device(const viorb_extractor* ex, int frame, int level,
                                    const uint8_t** d_roi, size_t* d_step);

@@ -54,8 +54,10 @@ def test_stages_vs_oracle(api, ctx, oracle, cfg, seed):
     k_gpu, d_gpu = ex(img)
     assert (ex.features_per_level() == ref.quotas()).all()
     assert (ex.GetScaleFactors() == ref.scale_factors()).all()
+    levels = ex.pyramid_all()                 # one copy for all levels (viorb_extractor_pyramid_download_all)
     for l in range(nl):
         assert (ex.pyramid(l) == ref.pyramid(l)).all(), "pyramid level %d" % l
+        assert (levels[l] == ref.pyramid(l)).all(), "pyramid level %d, single-copy download" % l
         c_ref = ref.candidates(l)
         c_ref = np.stack([c_ref["x"] + 16, c_ref["y"] + 16, c_ref["score"]], 1)
         c_gpu = ex.debug_candidates(l)

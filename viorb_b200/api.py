@@ -50,6 +50,7 @@ def lib():
         "viorb_extractor_configure": [vp, i32, i32],
         "viorb_extractor_set_gaussian": [vp, i32],
         "viorb_extractor_set_describe_mode": [vp, i32],
+        "viorb_extractor_pyramid_download_all": [vp, i32, vp, vp, i32],
         "viorb_extractor_set_copy_mode": [vp, i32],
         "viorb_extractor_tables": [vp, pi, vp, vp, vp, vp, vp],
         "viorb_extractor_profile": [vp, i32],
@@ -295,6 +296,18 @@ class ORBextractor:
         n = C.c_int()
         _ck(lib().viorb_extractor_stage_ms(self.h, _ptr(ms), C.byref(n)))
         return dict(zip(("pyramid", "fast", "octree", "describe"), [float(v) for v in ms])), n.value
+
+    def pyramid_all(self, frame=0):
+        """all padded levels of one frame with a single device-to-host copy (viorb_extractor_pyramid_download_all)"""
+        outs = []
+        for l in range(self.nlevels):
+            w, h = C.c_int(), C.c_int()
+            _ck(lib().viorb_extractor_pyramid_info(self.h, l, C.byref(w), C.byref(h)))
+            outs.append(np.zeros((h.value + 38, w.value + 38), np.uint8))
+        ptrs = (C.c_void_p * self.nlevels)(*[o.ctypes.data for o in outs])
+        steps = (C.c_size_t * self.nlevels)(*[o.strides[0] for o in outs])
+        _ck(lib().viorb_extractor_pyramid_download_all(self.h, frame, ptrs, steps, self.nlevels))
+        return outs
 
     # mvImagePyramid, ORBextractor.h:85
     def pyramid(self, level, frame=0):

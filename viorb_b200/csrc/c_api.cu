@@ -126,6 +126,8 @@ struct viorb_extractor {
     int nlanes = 4;
     cudaEvent_t evFork = nullptr;
     int* hostStatus = nullptr;     /* pinned copy of the device status word (single-pass host path) */
+    uint8_t* pyrHost = nullptr;    /* pinned staging of one frame's pyramid block (viorb_extractor_pyramid_download_all) */
+    size_t pyrHostBytes = 0;
     /* CUDA graph of one single-frame pass (memset + 12 kernels) on lane 0: the per-frame call replays it instead of
      * issuing 13 launches; rebuilt when the geometry, the buffers or the capacity change */
     cudaGraphExec_t frameGraph = nullptr;
@@ -629,6 +631,7 @@ int viorb_extractor_destroy(viorb_extractor* e) {
     }
     if (e->evFork) cudaEventDestroy(e->evFork);
     if (e->hostStatus) cudaFreeHost(e->hostStatus);
+    if (e->pyrHost) cudaFreeHost(e->pyrHost);
     if (e->frameGraph) cudaGraphExecDestroy(e->frameGraph);
     for (int i = 0; i < 4; i++) {
         e->in[i].release(); e->okps[i].release(); e->odesc[i].release(); e->ocnt[i].release();
@@ -1013,6 +1016,30 @@ int viorb_extractor_pyramid_download(viorb_extractor* e, int frame, int level, u
     CU(cudaMemcpy2DAsync(dst, dst_step, src, L.step, L.w + 2 * VIORB_EDGE, L.h + 2 * VIORB_EDGE, cudaMemcpyDeviceToHost,
                          e->ctx->stream));
     CU(cudaStreamSynchronize(e->ctx->stream));
+    return VIORB_OK;
+}
+
+int viorb_extractor_pyramid_download_all(viorb_extractor* e, int frame, uint8_t* const* dst, const size_t* dst_step, int nlevels) {
+    if (!e || !dst || !dst_step || nlevels != e->nlevels || !e->rows || frame < 0 || frame >= e->residentCount)
+        return fail(VIORB_ERR_INVALID, "frame %d not resident or bad level count", frame);
+    int rc;
+    if ((rc = ctx_bind(e->ctx))) return rc;
+    const size_t bytes = (size_t)e->geom.pyrFrameBytes;
+    if (bytes > e->pyrHostBytes) {
+        if (e->pyrHost) cudaFreeHost(e->pyrHost);
+        e->pyrHost = nullptr; e->pyrHostBytes = 0;
+        CU(cudaHostAlloc((void**)&e->pyrHost, bytes, cudaHostAllocDefault));
+        e->pyrHostBytes = bytes;
+    }
+    CU(cudaMemcpyAsync(e->pyrHost, e->buf.pyr + (size_t)frame * bytes, bytes, cudaMemcpyDeviceToHost, e->ctx->stream));
+    CU(cudaStreamSynchronize(e->ctx->stream));
+    for (int l = 0; l < nlevels; l++) {
+        const LevelGeom& L = e->geom.lv[l];
+        if (!dst[l]) continue;
+        const uint8_t* src = e->pyrHost + L.pyrOff + (VIORB_ROI_X0 - VIORB_EDGE);
+        const size_t wbytes = (size_t)L.w + 2 * VIORB_EDGE;
+        for (int r = 0; r < L.h + 2 * VIORB_EDGE; r++) memcpy(dst[l] + (size_t)r * dst_step[l], src + (size_t)r * L.step, wbytes);
+    }
     return VIORB_OK;
 }
 

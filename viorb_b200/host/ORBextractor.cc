@@ -67,13 +67,18 @@ void ORBextractor::SetGaussianVariant(int opencvVariant) {
 /* host copy of the padded levels of the last call (reference ComputePyramid :1107-1132 leaves them in mvImagePyramid) */
 void ORBextractor::SyncPyramid() {
     if (!mbPyramidStale) return;
+    std::vector<uint8_t*> dst(nlevels);
+    std::vector<size_t> steps(nlevels);
+    std::vector<int> ws(nlevels), hs(nlevels);
     for (int l = 0; l < nlevels; l++) {
-        int w = 0, h = 0;
-        check(viorb_extractor_pyramid_info(mpHandle, l, &w, &h), "viorb_extractor_pyramid_info");
-        mvPaddedLevels[l].create(h + 38, w + 38, CV_8U);
-        check(viorb_extractor_pyramid_download(mpHandle, 0, l, mvPaddedLevels[l].data, mvPaddedLevels[l].step), "pyramid download");
-        mvRoiLevels[l] = mvPaddedLevels[l](cv::Rect(19, 19, w, h));
+        check(viorb_extractor_pyramid_info(mpHandle, l, &ws[l], &hs[l]), "viorb_extractor_pyramid_info");
+        mvPaddedLevels[l].create(hs[l] + 38, ws[l] + 38, CV_8U);
+        dst[l] = mvPaddedLevels[l].data;
+        steps[l] = mvPaddedLevels[l].step;
     }
+    /* one device-to-host copy of the frame's pyramid block (pinned staging inside the library), then row copies */
+    check(viorb_extractor_pyramid_download_all(mpHandle, 0, dst.data(), steps.data(), nlevels), "pyramid download");
+    for (int l = 0; l < nlevels; l++) mvRoiLevels[l] = mvPaddedLevels[l](cv::Rect(19, 19, ws[l], hs[l]));
     mbPyramidStale = false;
 }
 
